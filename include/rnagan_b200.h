@@ -1,0 +1,88 @@
+/* rnagan_b200.h -- C ABI of the B200-native RNA-GAN hot path (librnagan_b200.so).
+ *
+ * The reference (gevaertlab/RNA-GAN) has NO native/FFI boundary: its hot path is Python calling ATen
+ * (nn.ConvTranspose2d / nn.Conv2d / nn.BatchNorm2d / nn.Linear / autograd / torch.optim.Adam).  Each entry point
+ * below therefore cites the reference call site whose ATen work it replaces.  All pointers are DEVICE pointers
+ * borrowed from the caller (the library never allocates persistent memory), every call is asynchronous on the
+ * given stream, and the return value is 0 on success, a negative RG_E* code for bad arguments, or a positive
+ * cudaError_t.  rg_last_error() returns a human-readable message for the last failure on the calling thread.
+ *
+ * Layout vocabulary
+ *   "link"      one stride-2 4x4 connection between a low-resolution NHWC tensor lo[B,H,W,Cp] and a
+ *               high-resolution NHWC tensor hi[B,2H,2W,Cs] with the torch weight W[Cp][Cs][4][4] (fp32):
+ *               nn.Conv2d(Cs->Cp,4,2,1) has weight [Cout=Cp][Cin=Cs][4][4]   (critic,    torchgan DCGANDiscriminator)
+ *               nn.ConvTranspose2d(Cp->Cs,4,2,1) has weight [Cin=Cp][Cout=Cs][4][4] (generator, src/dcgan.py:52)
+ *               so both directions of both networks are the same three contractions: DOWN, UP, WGRAD.
+ *   w_down      bf16 [Cp][16*Cs]      k = (kh*4+kw)*Cs + s
+ *   w_up        bf16 [4][Cs_pad][4*Cp] phase = (y&1)*2+(x&1), k = tap*Cp + p, Cs_pad = max(Cs,16) rounded to 16
+ *   activations bf16 NHWC; images fp32 NCHW (the reference's tensor layout at the module boundary).
+ */
+#ifndef RNAGAN_B200_H
+#define RNAGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rg_stream_t; /* cudaStream_t */
+
+#define RG_EINVAL (-1)   /* bad shape / alignment / unsupported size */
+#define RG_EARCH (-2)    /* device is not sm_100 */
+#define RG_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable or failed */
+#define RG_EWORKSPACE (-4) /* caller-supplied workspace too small */
+
+int rg_version(void);
+const char* rg_last_error(void);
+/* 0 when the current device can run the library (compute capability 10.x), RG_EARCH otherwise. */
+int rg_check_device(void);
+
+/* ---- weight packing (after every optimizer step) --------------------------------------------------------- */
+/* fp32 W[Cp][Cs][4][4] -> bf16 w_down and/or w_up (either may be NULL).  Replaces nothing in the reference: it is
+ * the derived operand layout for rg_conv_down / rg_conv_up. */
+int rg_pack_link(const float* W, void* w_down, void* w_up, int Cp, int Cs, rg_stream_t st);
+/* generator layer 0, nn.ConvTranspose2d(E, C0, 4, 1, 0) weight [E][C0][4][4] (src/dcgan.py:38-40)
+ * -> bf16 [16*C0][E]  (row = tap*C0 + co), the B operand of rg_gemm_nt. */
+int rg_pack_proj(const float* W, void* w_proj, int E, int C0, rg_stream_t st);
+/* image-side (3-channel) link, K padded to 64: bf16 w_col[Cp][64], k = (kh*4+kw)*4 + c. */
+int rg_pack_edge(const float* W, void* w_col, int Cp, int Cimg, rg_stream_t st);
+/* fp32 [rows][cols] -> bf16 [rows][cols_pad] (zero padded), nn.Linear weights (src/betaVAE.py:31,76). */
+int rg_cast_pad_bf16(const float* src, void* dst, int rows, int cols, int cols_pad, rg_stream_t st);
+
+/* ---- dense contractions on tcgen05 ----------------------------------------------------------------------- */
+/* lo[b,i,j,p] = sum_{kh,kw,s} hi[b,2i-1+kh,2j-1+kw,s] * W[p,s,kh,kw]
+ * critic forward nn.Conv2d(4,2,1) (torchgan DCGANDiscriminator; args src/histopathology_gan.py:186-192) and
+ * generator dgrad (autograd of src/dcgan.py:52). */
+int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int W, int Cs, int Cp, rg_stream_t st);
+/* hi[b,y,x,s] = sum lo[b,i,j,p] * W[p,s,kh,kw] over y=2i-1+kh, x=2j-1+kw
+ * generator forward nn.ConvTranspose2d(4,2,1) (src/dcgan.py:52) and critic dgrad. */
+int rg_conv_up(const void* lo, const void* w_up, void* hi, int B, int H, int W, int Cp, int Cs, rg_stream_t st);
+/* same as rg_conv_up for Cs<=16 image channels, fp32 NCHW output, optional bias + tanh
+ * (generator last layer, src/dcgan.py:82; critic layer-0 dgrad). */
+int rg_conv_up_img(const void* lo, const void* w_up, float* img, const float* bias, int act_tanh, int B, int H,
+                   int W, int Cp, int Cimg, rg_stream_t st);
+/* dW[p,s,kh,kw] = beta*dW + alpha*(*alpha_dev)*sum_{b,i,j} lo[b,i,j,p] * hi[b,2i-1+kh,2j-1+kw,s]  (fp32, torch layout)
+ * autograd wgrad of both conv kinds.  ws: fp32 scratch of at least rg_conv_wgrad_ws_bytes(). alpha_dev may be NULL. */
+size_t rg_conv_wgrad_ws_bytes(int B, int H, int W, int Cp, int Cs);
+int rg_conv_wgrad(const void* lo, const void* hi, float* dW, void* ws, size_t ws_bytes, int B, int H, int W, int Cp,
+                  int Cs, float alpha, const float* alpha_dev, float beta, rg_stream_t st);
+/* generator layer 0 wgrad: dW[e,c,kh,kw] = sum_b z[b,e] * da0[b,kh,kw,c]. */
+size_t rg_proj_wgrad_ws_bytes(int B, int E, int C0);
+int rg_proj_wgrad(const void* z, const void* da0, float* dW, void* ws, size_t ws_bytes, int B, int E, int C0,
+                  float alpha, const float* alpha_dev, float beta, rg_stream_t st);
+/* C[M,N] = act((A[M,K] . Bw[N,K]^T) * col_scale + col_shift); A, Bw bf16 row-major (K multiple of 64), C bf16 or
+ * fp32 with leading dimension ldc.  nn.Linear(+eval BatchNorm1d+LeakyReLU) of the encoder (src/betaVAE.py:29-36),
+ * generator layer 0 (src/dcgan.py:38-40), image-side im2col GEMMs. */
+int rg_gemm_nt(const void* A, const void* Bw, void* C, int M, int N, int K, int ldc, const float* col_scale,
+               const float* col_shift, float slope, int out_f32, rg_stream_t st);
+/* C[M,N] (fp32, row-major) = beta*C + alpha*(*alpha_dev) * sum_r A[r,M]^T B[r,N]; A,B bf16 row-major [R][M],[R][N]. */
+size_t rg_gemm_tn_ws_bytes(int R, int M, int N);
+int rg_gemm_tn(const void* A, const void* Bm, float* C, void* ws, size_t ws_bytes, int R, int M, int N, float alpha,
+               const float* alpha_dev, float beta, rg_stream_t st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNAGAN_B200_H */

@@ -1,0 +1,96 @@
+"""ctypes binding of librnagan_b200.so (the C ABI declared in include/rnagan_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, an exception is raised.
+The product path never routes through oracle/ or a PyTorch re-implementation.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librnagan_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+SOURCES = ["rg_gemm_api.cu", "rg_ops.cu"]
+
+_c = ctypes
+_vp, _i, _f, _sz = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/rnagan_b200.h one to one
+SIGNATURES = {
+    "rg_version": (_i, []),
+    "rg_last_error": (_c.c_char_p, []),
+    "rg_check_device": (_i, []),
+    "rg_pack_link": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "rg_pack_proj": (_i, [_vp, _vp, _i, _i, _vp]),
+    "rg_pack_edge": (_i, [_vp, _vp, _i, _i, _vp]),
+    "rg_cast_pad_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "rg_conv_down": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rg_conv_up": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rg_conv_up_img": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "rg_conv_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "rg_conv_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _f, _vp, _f, _vp]),
+    "rg_proj_wgrad_ws_bytes": (_sz, [_i, _i, _i]),
+    "rg_proj_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp, _f, _vp]),
+    "rg_gemm_nt": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp]),
+    "rg_gemm_tn_ws_bytes": (_sz, [_i, _i, _i]),
+    "rg_gemm_tn": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp, _f, _vp]),
+}
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile every CUDA source for sm_100a into the in-tree shared library (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    cmd = [
+        "nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+        "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH,
+    ] + srcs
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building librnagan_b200.so")
+    global _lib
+    _lib = None
+    return LIB_PATH
+
+
+def _needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    for f in os.listdir(CSRC):
+        if f.endswith((".cu", ".cuh")) and os.path.getmtime(os.path.join(CSRC, f)) > t:
+            return True
+    return False
+
+
+def lib():
+    """Return the loaded library, failing loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)   # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+class RgError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().rg_last_error().decode("utf-8", "replace")
+        raise RgError(f"{what} failed with status {rc}: {msg}")

@@ -1,0 +1,451 @@
+// rg_gemm.cuh -- the tcgen05/TMEM/TMA implicit-GEMM tile engine shared by every dense contraction on the
+// RNA-GAN hot path:
+//
+//   * gemm_fwd_kernel   : D[M=128 pixels, N<=256] += A[pixels, K] * B[N, K]^T, both operands K-major.
+//                         The A tile of one k-block is a 4-D TMA box (64 channels x bw x bh x bb pixels) read at a
+//                         per-tap pixel offset from one of up to four strided views ("parity maps") of an NHWC
+//                         activation, so a stride-2 4x4 convolution (16 taps), its transposed form (4 output phases
+//                         x 4 taps) and a plain GEMM (1 tap, H=W=1) are the same kernel with different tap tables.
+//                         Out-of-image taps are zero-filled by TMA: no padding buffers, no im2col in HBM.
+//   * gemm_wgrad_kernel : dW[tap][p, s] = sum_pixels lo[pixel, p] * hi[pixel@tap, s]; both operands are the raw NHWC
+//                         tiles used as MN-major UMMA operands (reduction over pixel rows), split-K over pixel blocks
+//                         with fp32 partials reduced in a fixed order (deterministic, like cudnn.deterministic=True in
+//                         the reference, src/histopathology_gan.py:289).
+//
+// Both are persistent, warp-specialised kernels: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
+// warps 2-5 = epilogue (TMEM -> registers -> HBM) overlapping the next tile's MMAs through a double-buffered
+// accumulator (2 x 256 TMEM columns).
+#pragma once
+#include "rg_ptx.cuh"
+
+namespace rg {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                  // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kAStageBytes = 128 * 128;      // 16 KiB
+constexpr int kBStageBytes = 256 * 128;      // 32 KiB
+constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kGemmThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;              // TMEM columns per accumulator stage
+
+struct Tap {
+  int8_t map;   // which A-view (parity map) this tap reads
+  int8_t dh;    // row offset added to the tile's first row
+  int8_t dw;    // column offset
+  int8_t rsv;
+};
+
+struct GemmMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+enum OutKind { OUT_BF16_NHWC = 0, OUT_F32_NHWC = 1, OUT_F32_NCHW = 2 };
+
+struct FwdArgs {
+  int nB, H, W;        // M index space: pixels of the low-resolution grid (plain GEMM: H=W=1, nB=M)
+  int bw, bh, bb;      // TMA box (pixels) per M tile; bw*bh*bb == 128
+  int tw, th, tb;      // boxes per dimension
+  int m_tiles;
+  int num_taps, chunks;   // k-blocks per tile = num_taps * chunks (chunks = C_A / 64)
+  int num_phases;         // 1, or 4 for the transposed (upsampling) form
+  int n_total, block_n, n_tiles;
+  int b_phase_rows;       // row offset between phases in the packed weight matrix
+  Tap taps[4][16];
+  void* out;
+  const float* col_scale;   // optional per-output-column scale (folded eval BatchNorm1d)
+  const float* col_shift;   // optional per-output-column shift / bias
+  float slope;              // LeakyReLU slope applied after scale/shift (1.0f = identity)
+  int act_tanh;             // 1: tanh instead of LeakyReLU
+  int OH, OW, OC;           // output tensor dims
+  int sy, sx;               // output pixel = (i*sy + oy[phase], j*sx + ox[phase])
+  int n_valid;              // columns >= n_valid are not stored
+  int8_t oy[4], ox[4];
+};
+
+struct WgradArgs {
+  int nB, H, W;
+  int bw, bh, bb;      // pixel box per k-block; bw*bh*bb == 64
+  int tw, th, tb;
+  int num_pb, splits, pb_per_split;
+  int m_tiles, n_tiles, slabs_per_tile, chunks_s;
+  int Cp, Cs, num_taps;
+  Tap taps[16];
+  float* ws;           // [splits][num_taps][Cp][Cs] fp32 partials
+};
+
+// ------------------------------------------------------------------------------------------------ shared setup
+struct PipeSmem {
+  uint8_t* stages;
+  uint64_t* full;
+  uint64_t* empty;
+  uint64_t* tfull;
+  uint64_t* tempty;
+  uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
+  PipeSmem s;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  s.stages = base;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kStages * kStageBytes);
+  s.full = bars;
+  s.empty = bars + kStages;
+  s.tfull = bars + 2 * kStages;
+  s.tempty = bars + 2 * kStages + 2;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  return s;
+}
+
+__device__ __forceinline__ uint32_t pipeline_prologue(const PipeSmem& s, int warp) {
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < kStages; ++i) {
+        mbar_init(&s.full[i], 1);
+        mbar_init(&s.empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s.tfull[i], 1);
+        mbar_init(&s.tempty[i], 4);   // one arrival per epilogue warp
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(s.tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(s.tmem_slot);
+}
+
+// ------------------------------------------------------------------------------------------------ forward / dgrad
+template <int OUT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ FwdArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const PipeSmem s = carve_smem(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
+  }
+  const uint32_t tmem_base = pipeline_prologue(s, warp);
+
+  const int num_kb = p.num_taps * p.chunks;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.num_phases;
+  const uint32_t stage_tx = kAStageBytes + static_cast<uint32_t>(p.block_n) * 128u;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (one elected lane)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile % p.m_tiles;
+        const int rest = tile / p.m_tiles;
+        const int n_tile = rest % p.n_tiles;
+        const int ph = rest / p.n_tiles;
+        const int jt = m_tile % p.tw;
+        const int it = (m_tile / p.tw) % p.th;
+        const int bt = m_tile / (p.tw * p.th);
+        const int j0 = jt * p.bw, i0 = it * p.bh, b0 = bt * p.bb;
+        const int brow = ph * p.b_phase_rows + n_tile * p.block_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.chunks;
+          const int chunk = kb - tap * p.chunks;
+          const Tap t = p.taps[ph][tap];
+          mbar_wait(&s.empty[stage], phase ^ 1u);
+          uint8_t* sa = s.stages + stage * kStageBytes;
+          uint8_t* sb = sa + kAStageBytes;
+          mbar_expect_tx(&s.full[stage], stage_tx);
+          tma_load_4d(&maps.a[t.map], &s.full[stage], sa, chunk * kBlockK, j0 + t.dw, i0 + t.dh, b0);
+          tma_load_2d(&maps.b, &s.full[stage], sb, kb * kBlockK, brow);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one elected lane)
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1u;
+        mbar_wait(&s.tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&s.full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(s.stages + stage * kStageBytes);
+          const uint32_t sb = sa + kAStageBytes;
+          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 bytes per UMMA_K inside the 128-byte swizzle row => +2 in the (>>4) address field
+            umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&s.empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&s.tfull[acc]);
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (TMEM lanes 32*(warp%4) ...)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int jj = row % p.bw;
+    const int ii = (row / p.bw) % p.bh;
+    const int bbi = row / (p.bw * p.bh);
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1u;
+      const int m_tile = tile % p.m_tiles;
+      const int rest = tile / p.m_tiles;
+      const int n_tile = rest % p.n_tiles;
+      const int ph = rest / p.n_tiles;
+      const int jt = m_tile % p.tw;
+      const int it = (m_tile / p.tw) % p.th;
+      const int bt = m_tile / (p.tw * p.th);
+      const int b = bt * p.bb + bbi, i = it * p.bh + ii, j = jt * p.bw + jj;
+      const bool row_ok = (b < p.nB) && (i < p.H) && (j < p.W);
+      const int y = i * p.sy + p.oy[ph], x = j * p.sx + p.ox[ph];
+      const int n0 = n_tile * p.block_n;
+
+      mbar_wait(&s.tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t v[32];
+        if (p.block_n >= 32) {
+          tmem_ld_32x32(taddr + c, v);
+        } else {
+          uint32_t w[16];
+          tmem_ld_32x16(taddr + c, w);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { v[e] = w[e]; v[16 + e] = 0u; }
+        }
+        tmem_ld_wait();
+        const int ncols = min(32, p.block_n - c);
+        // optional per-column affine + activation
+        if (p.col_scale != nullptr || p.col_shift != nullptr || p.slope != 1.0f || p.act_tanh) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int col = n0 + c + e;
+            float f = __uint_as_float(v[e]);
+            if (e < ncols && col < p.n_valid) {
+              if (p.col_scale) f *= __ldg(p.col_scale + col);
+              if (p.col_shift) f += __ldg(p.col_shift + col);
+              if (p.act_tanh) f = tanhf(f);
+              else f = f > 0.0f ? f : f * p.slope;
+            }
+            v[e] = __float_as_uint(f);
+          }
+        }
+        if (row_ok) {
+          if (OUT == OUT_BF16_NHWC) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                               (static_cast<size_t>(b * p.OH + y) * p.OW + x) * p.OC + n0 + c;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = n0 + c + g * 8;
+              if (g * 8 < ncols && col + 8 <= p.n_valid) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+                u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+                u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+                u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+                *reinterpret_cast<uint4*>(o + g * 8) = u;
+              } else if (g * 8 < ncols) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (col + e < p.n_valid) o[g * 8 + e] = __float2bfloat16(__uint_as_float(v[g * 8 + e]));
+              }
+            }
+          } else if (OUT == OUT_F32_NHWC) {
+            float* o = reinterpret_cast<float*>(p.out) + (static_cast<size_t>(b * p.OH + y) * p.OW + x) * p.OC + n0 + c;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const int col = n0 + c + g * 4;
+              if (g * 4 < ncols && col + 4 <= p.n_valid) {
+                float4 u = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
+                                       __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+                *reinterpret_cast<float4*>(o + g * 4) = u;
+              } else if (g * 4 < ncols) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < p.n_valid) o[g * 4 + e] = __uint_as_float(v[g * 4 + e]);
+              }
+            }
+          } else {   // OUT_F32_NCHW: a handful of image channels, planar fp32
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int col = n0 + c + e;
+              if (e < ncols && col < p.n_valid)
+                o[(static_cast<size_t>(b * p.OC + col) * p.OH + y) * p.OW + x] = __uint_as_float(v[e]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ WgradArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const PipeSmem s = carve_smem(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
+  }
+  const uint32_t tmem_base = pipeline_prologue(s, warp);
+
+  const int total_units = p.m_tiles * p.n_tiles * p.splits;
+  const uint32_t stage_tx = static_cast<uint32_t>(2 + p.slabs_per_tile) * 8192u;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int m_tile = u % p.m_tiles;
+        const int rest = u / p.m_tiles;
+        const int n_tile = rest % p.n_tiles;
+        const int split = rest / p.n_tiles;
+        const int pb0 = split * p.pb_per_split;
+        const int pb1 = min(p.num_pb, pb0 + p.pb_per_split);
+        for (int pb = pb0; pb < pb1; ++pb) {
+          const int jt = pb % p.tw;
+          const int it = (pb / p.tw) % p.th;
+          const int bt = pb / (p.tw * p.th);
+          const int j0 = jt * p.bw, i0 = it * p.bh, b0 = bt * p.bb;
+          mbar_wait(&s.empty[stage], phase ^ 1u);
+          uint8_t* sa = s.stages + stage * kStageBytes;
+          uint8_t* sb = sa + kAStageBytes;
+          mbar_expect_tx(&s.full[stage], stage_tx);
+          // MMA-A operand: two 64-channel slabs of the low-resolution tensor (channels beyond Cp zero-fill)
+          tma_load_4d(&maps.b, &s.full[stage], sa, m_tile * 128, j0, i0, b0);
+          tma_load_4d(&maps.b, &s.full[stage], sa + 8192, m_tile * 128 + 64, j0, i0, b0);
+          // MMA-B operand: one slab per (tap, 64-channel chunk) of the high-resolution tensor
+          for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
+            const int qd = n_tile * p.slabs_per_tile + sl;
+            const int tap = qd / p.chunks_s;
+            const int chunk = qd - tap * p.chunks_s;
+            const Tap t = p.taps[tap];
+            tma_load_4d(&maps.a[t.map], &s.full[stage], sb + sl * 8192, chunk * 64, j0 + t.dw, i0 + t.dh, b0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM, 64 * p.slabs_per_tile, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++iter) {
+        const int split = u / (p.m_tiles * p.n_tiles);
+        const int pb0 = split * p.pb_per_split;
+        const int pb1 = min(p.num_pb, pb0 + p.pb_per_split);
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1u;
+        mbar_wait(&s.tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kAccStride;
+        for (int pb = pb0; pb < pb1; ++pb) {
+          mbar_wait(&s.full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(s.stages + stage * kStageBytes);
+          const uint32_t sb = sa + kAStageBytes;
+          // MN-major SWIZZLE_128B: LBO = stride between 64-element MN slabs (8 KiB),
+          // SBO = stride between 8-row K groups (1 KiB); one UMMA_K = 16 pixel rows = 2 KiB.
+          const uint64_t da = make_smem_desc_sw128(sa, 8192, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(tmem_d, da + 128u * k, db + 128u * k, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&s.empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&s.tfull[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int iter = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1u;
+      const int m_tile = u % p.m_tiles;
+      const int rest = u / p.m_tiles;
+      const int n_tile = rest % p.n_tiles;
+      const int split = rest / p.n_tiles;
+      const int prow = m_tile * 128 + row;
+      const bool row_ok = prow < p.Cp;
+      mbar_wait(&s.tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
+        const int qd = n_tile * p.slabs_per_tile + sl;
+        const int tap = qd / p.chunks_s;
+        const int chunk = qd - tap * p.chunks_s;
+        float* o = p.ws + ((static_cast<size_t>(split) * p.num_taps + tap) * p.Cp + prow) * p.Cs + chunk * 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + sl * 64 + h * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (chunk * 64 + h * 32 + g * 4 + 4 <= p.Cs) {
+                float4 f = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
+                                       __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+                *reinterpret_cast<float4*>(o + h * 32 + g * 4) = f;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace rg

@@ -1,0 +1,582 @@
+// rg_gemm_api.cu -- C-ABI entry points for the tcgen05 tile engine (rg_gemm.cuh) and the weight packers.
+#include <stdarg.h>
+#include <algorithm>
+#include "rg_gemm.cuh"
+#include "rg_host.cuh"
+
+namespace rg {
+
+// ------------------------------------------------------------------------------------------------ errors / device
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return static_cast<int>(e);
+}
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                  const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return RG_EDRIVER;
+  }
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims,
+                  strides_b, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u] base %p",
+              static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+              box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
+    return RG_EDRIVER;
+  }
+  return 0;
+}
+
+int encode_map_4d(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint64_t sw,
+                  uint64_t sh, uint64_t sb, uint32_t boxc, uint32_t bw, uint32_t bh, uint32_t bb) {
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {sw * 2, sh * 2, sb * 2};
+  cuuint32_t box[4] = {boxc, bw, bh, bb};
+  return encode(m, base, 4, dims, strides, box);
+}
+int encode_map_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t boxc,
+                  uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {boxc, box_rows};
+  return encode(m, base, 2, dims, strides, box);
+}
+
+// ------------------------------------------------------------------------------------------------ geometry
+struct Boxing {
+  int bw, bh, bb, tw, th, tb;
+};
+static Boxing make_boxing(int B, int H, int W, int rows) {
+  Boxing g;
+  g.bw = std::min(W, rows);
+  g.bh = std::min(H, rows / g.bw);
+  g.bb = rows / (g.bw * g.bh);
+  g.tw = ceil_div(W, g.bw);
+  g.th = ceil_div(H, g.bh);
+  g.tb = ceil_div(B, g.bb);
+  return g;
+}
+
+// kh (or kw) -> (offset in the low-res grid, parity of the high-res row) for y = 2i - 1 + kh
+static const int kDownOff[4] = {-1, 0, 0, 1};
+static const int kDownPar[4] = {1, 0, 1, 0};
+// output parity r, tap index t -> (low-res offset, kernel index) for the transposed form
+static const int kUpOff[2][2] = {{0, -1}, {0, 1}};
+static const int kUpK[2][2] = {{1, 3}, {2, 0}};
+
+static int pick_block_n(int n_total, int tiles_per_n) {
+  int bn = 256;
+  while (bn > n_total && bn > 16) bn >>= 1;
+  const int target = (num_sms() * 4) / 5;
+  while (bn > 64 && ceil_div(n_total, bn) * tiles_per_n < target) bn >>= 1;
+  return bn;
+}
+
+static int ensure_attrs() {
+  static bool done = false;
+  if (!done) {
+    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_BF16_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kGemmSmemBytes));
+    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_F32_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kGemmSmemBytes));
+    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_F32_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kGemmSmemBytes));
+    RG_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    done = true;
+  }
+  return 0;
+}
+
+static int launch_fwd(const GemmMaps& maps, const FwdArgs& a, int out_kind, cudaStream_t st) {
+  int rc = ensure_attrs();
+  if (rc) return rc;
+  const int total = a.m_tiles * a.n_tiles * a.num_phases;
+  const int grid = std::min(total, num_sms());
+  if (out_kind == OUT_BF16_NHWC)
+    gemm_fwd_kernel<OUT_BF16_NHWC><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
+  else if (out_kind == OUT_F32_NHWC)
+    gemm_fwd_kernel<OUT_F32_NHWC><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
+  else
+    gemm_fwd_kernel<OUT_F32_NCHW><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
+  RG_LAUNCH_CHECK("gemm_fwd_kernel");
+  return 0;
+}
+
+static void fill_common(FwdArgs& a, int B, int H, int W) {
+  memset(&a, 0, sizeof(a));
+  Boxing g = make_boxing(B, H, W, kBlockM);
+  a.nB = B; a.H = H; a.W = W;
+  a.bw = g.bw; a.bh = g.bh; a.bb = g.bb;
+  a.tw = g.tw; a.th = g.th; a.tb = g.tb;
+  a.m_tiles = g.tw * g.th * g.tb;
+  a.slope = 1.0f;
+  a.sy = a.sx = 1;
+  a.num_phases = 1;
+}
+
+// four parity views of hi[B,2H,2W,C]: view (ph,pw) holds pixels (2i+ph, 2j+pw)
+static int encode_parity_maps(GemmMaps& maps, const void* hi, int B, int H, int W, int C, int bw, int bh, int bb) {
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(hi);
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      const __nv_bfloat16* b0 = base + (static_cast<size_t>(ph) * 2 * W + pw) * C;
+      int rc = encode_map_4d(&maps.a[ph * 2 + pw], b0, C, W, H, B, 2ull * C, 4ull * W * C, 4ull * H * W * C, 64, bw,
+                             bh, bb);
+      if (rc) return rc;
+    }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ reduce kernel
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dW, int splits, int taps,
+                                    int Cp, int Cs, float alpha, const float* __restrict__ alpha_dev, float beta) {
+  const size_t n = static_cast<size_t>(Cp) * Cs;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const float a = alpha * (alpha_dev ? __ldg(alpha_dev) : 1.0f);
+  for (int t = 0; t < taps; ++t) {
+    float acc = 0.0f;
+    for (int sp = 0; sp < splits; ++sp) acc += ws[(static_cast<size_t>(sp) * taps + t) * n + idx];
+    const size_t o = idx * taps + t;
+    dW[o] = (beta != 0.0f ? beta * dW[o] : 0.0f) + a * acc;
+  }
+}
+
+static void choose_splits(int units, int num_pb, int& splits, int& pb_per_split) {
+  splits = std::max(1, std::min(num_pb, ceil_div(num_sms(), units)));
+  pb_per_split = ceil_div(num_pb, splits);
+  splits = ceil_div(num_pb, pb_per_split);
+}
+
+struct WgradGeom {
+  Boxing g;
+  int num_pb, m_tiles, chunks_s, slabs_per_tile, n_tiles, splits, pb_per_split, taps;
+};
+static WgradGeom wgrad_geom(int B, int H, int W, int Cp, int Cs, int taps) {
+  WgradGeom w;
+  w.g = make_boxing(B, H, W, 64);
+  w.num_pb = w.g.tw * w.g.th * w.g.tb;
+  w.m_tiles = ceil_div(Cp, 128);
+  w.chunks_s = Cs / 64;
+  w.taps = taps;
+  const int num_slabs = taps * w.chunks_s;
+  w.slabs_per_tile = (num_slabs % 4 == 0) ? 4 : ((num_slabs % 2 == 0) ? 2 : 1);
+  w.n_tiles = num_slabs / w.slabs_per_tile;
+  choose_splits(w.m_tiles * w.n_tiles, w.num_pb, w.splits, w.pb_per_split);
+  return w;
+}
+
+static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* taps, int B, int H, int W, int Cp, int Cs,
+                        float* dW, void* ws, size_t ws_bytes, float alpha, const float* alpha_dev, float beta,
+                        cudaStream_t st) {
+  int rc = ensure_attrs();
+  if (rc) return rc;
+  const size_t need = static_cast<size_t>(w.splits) * w.taps * Cp * Cs * sizeof(float);
+  if (ws_bytes < need || ws == nullptr) {
+    set_error("wgrad workspace too small: need %zu bytes, have %zu", need, ws_bytes);
+    return RG_EWORKSPACE;
+  }
+  WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nB = B; a.H = H; a.W = W;
+  a.bw = w.g.bw; a.bh = w.g.bh; a.bb = w.g.bb;
+  a.tw = w.g.tw; a.th = w.g.th; a.tb = w.g.tb;
+  a.num_pb = w.num_pb; a.splits = w.splits; a.pb_per_split = w.pb_per_split;
+  a.m_tiles = w.m_tiles; a.n_tiles = w.n_tiles; a.slabs_per_tile = w.slabs_per_tile; a.chunks_s = w.chunks_s;
+  a.Cp = Cp; a.Cs = Cs; a.num_taps = w.taps;
+  for (int t = 0; t < w.taps; ++t) a.taps[t] = taps[t];
+  a.ws = static_cast<float*>(ws);
+  const int units = w.m_tiles * w.n_tiles * w.splits;
+  const int grid = std::min(units, num_sms());
+  gemm_wgrad_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
+  RG_LAUNCH_CHECK("gemm_wgrad_kernel");
+  const size_t n = static_cast<size_t>(Cp) * Cs;
+  wgrad_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, w.taps, Cp, Cs,
+                                                                              alpha, alpha_dev, beta);
+  RG_LAUNCH_CHECK("wgrad_reduce_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ pack kernels
+// W[p][s][16] fp32 -> w_down[p][tap*Cs + s] bf16.  One block per (p, 64-wide s chunk).
+__global__ void pack_down_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int Cp, int Cs) {
+  __shared__ float sm[64 * 17];
+  const int p = blockIdx.y;
+  const int s0 = blockIdx.x * 64;
+  const int ns = min(64, Cs - s0);
+  const float* src = W + (static_cast<size_t>(p) * Cs + s0) * 16;
+  for (int e = threadIdx.x; e < ns * 16; e += blockDim.x) sm[(e >> 4) * 17 + (e & 15)] = src[e];
+  __syncthreads();
+  for (int e = threadIdx.x; e < ns * 16; e += blockDim.x) {
+    const int tap = e / ns, sl = e - tap * ns;
+    out[static_cast<size_t>(p) * 16 * Cs + static_cast<size_t>(tap) * Cs + s0 + sl] = __float2bfloat16(sm[sl * 17 + tap]);
+  }
+}
+// W[p][s][16] fp32 -> w_up[phase][s][t*Cp + p] bf16 (rows s >= Cs are left untouched: caller zero-fills once).
+// One block per (32-wide p chunk, 16-wide s chunk).
+__global__ void pack_up_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int Cp, int Cs,
+                               int Cs_pad) {
+  __shared__ float sm[32][257];
+  const int p0 = blockIdx.y * 32, s0 = blockIdx.x * 16;
+  const int np = min(32, Cp - p0), ns = min(16, Cs - s0);
+  for (int e = threadIdx.x; e < np * ns * 16; e += blockDim.x) {
+    const int pl = e / (ns * 16), off = e - pl * ns * 16;
+    sm[pl][off] = W[(static_cast<size_t>(p0 + pl) * Cs + s0) * 16 + off];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ns * 16 * 32; e += blockDim.x) {
+    const int pl = e & 31;
+    const int so = e >> 5;              // (s_local, tap16)
+    if (pl >= np) continue;
+    const int sl = so >> 4, tap16 = so & 15;
+    const int kh = tap16 >> 2, kw = tap16 & 3;
+    // y = 2i - 1 + kh: kh=1,3 feed even rows (taps 0,1); kh=2,0 feed odd rows (taps 0,1)
+    const int rh = (kh == 1 || kh == 3) ? 0 : 1, th = (kh == 1 || kh == 2) ? 0 : 1;
+    const int rw = (kw == 1 || kw == 3) ? 0 : 1, tw = (kw == 1 || kw == 2) ? 0 : 1;
+    const int phase = rh * 2 + rw, t = th * 2 + tw;
+    out[(static_cast<size_t>(phase) * Cs_pad + s0 + sl) * (4 * static_cast<size_t>(Cp)) + static_cast<size_t>(t) * Cp + p0 + pl] =
+        __float2bfloat16(sm[pl][sl * 16 + tap16]);
+  }
+}
+// W[E][C0*16] fp32 -> out[(tap*C0 + co)][E] bf16 : 32x32 tile transpose
+__global__ void pack_proj_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int E, int C0) {
+  __shared__ float sm[32][33];
+  const int e0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int N = C0 * 16;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 256 threads: 8 rows per pass
+  for (int r = ty; r < 32; r += 8)
+    if (e0 + r < E && n0 + tx < N) sm[r][tx] = W[static_cast<size_t>(e0 + r) * N + n0 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r;
+    if (n < N && e0 + tx < E) {
+      const int co = n >> 4, tap = n & 15;
+      out[(static_cast<size_t>(tap) * C0 + co) * E + e0 + tx] = __float2bfloat16(sm[tx][r]);
+    }
+  }
+}
+// W[Cp][Cimg][16] -> w_col[Cp][64], k = tap*4 + c
+__global__ void pack_edge_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int Cp, int Cimg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cp * 64) return;
+  const int p = idx >> 6, k = idx & 63, tap = k >> 2, c = k & 3;
+  const float v = c < Cimg ? W[(static_cast<size_t>(p) * Cimg + c) * 16 + tap] : 0.0f;
+  out[idx] = __float2bfloat16(v);
+}
+__global__ void cast_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols,
+                                int cols_pad) {
+  const size_t n = static_cast<size_t>(rows) * cols_pad;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / cols_pad;
+    const int c = static_cast<int>(i - r * cols_pad);
+    dst[i] = __float2bfloat16(c < cols ? src[r * cols + c] : 0.0f);
+  }
+}
+
+}  // namespace rg
+
+using namespace rg;
+
+extern "C" {
+
+int rg_version(void) { return 100; }
+const char* rg_last_error(void) { return g_err; }
+
+int rg_check_device(void) {
+  int dev = 0;
+  RG_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  RG_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("device compute capability %d.x is not sm_100 (B200)", major);
+    return RG_EARCH;
+  }
+  return 0;
+}
+
+int rg_pack_link(const float* W, void* w_down, void* w_up, int Cp, int Cs, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(W && Cp > 0 && Cs > 0, "rg_pack_link: bad arguments");
+  if (w_down) {
+    dim3 grid(ceil_div(Cs, 64), Cp);
+    pack_down_kernel<<<grid, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(w_down), Cp, Cs);
+    RG_LAUNCH_CHECK("pack_down_kernel");
+  }
+  if (w_up) {
+    const int Cs_pad = std::max(16, (Cs + 15) / 16 * 16);
+    dim3 grid(ceil_div(Cs, 16), ceil_div(Cp, 32));
+    pack_up_kernel<<<grid, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(w_up), Cp, Cs, Cs_pad);
+    RG_LAUNCH_CHECK("pack_up_kernel");
+  }
+  return 0;
+}
+
+int rg_pack_proj(const float* W, void* w_proj, int E, int C0, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(W && w_proj && E > 0 && C0 > 0, "rg_pack_proj: bad arguments");
+  dim3 grid(ceil_div(C0 * 16, 32), ceil_div(E, 32));
+  pack_proj_kernel<<<grid, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(w_proj), E, C0);
+  RG_LAUNCH_CHECK("pack_proj_kernel");
+  return 0;
+}
+
+int rg_pack_edge(const float* W, void* w_col, int Cp, int Cimg, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(W && w_col && Cp > 0 && Cimg > 0 && Cimg <= 4, "rg_pack_edge: bad arguments");
+  pack_edge_kernel<<<ceil_div(Cp * 64, 256), 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(w_col), Cp, Cimg);
+  RG_LAUNCH_CHECK("pack_edge_kernel");
+  return 0;
+}
+
+int rg_cast_pad_bf16(const float* src, void* dst, int rows, int cols, int cols_pad, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(src && dst && rows > 0 && cols > 0 && cols_pad >= cols, "rg_cast_pad_bf16: bad arguments");
+  const size_t n = static_cast<size_t>(rows) * cols_pad;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  cast_pad_kernel<<<grid, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), rows, cols, cols_pad);
+  RG_LAUNCH_CHECK("cast_pad_kernel");
+  return 0;
+}
+
+int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int W, int Cs, int Cp, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(hi && w_down && lo, "rg_conv_down: null pointer");
+  RG_CHECK_ARG(B > 0 && is_pow2(H) && is_pow2(W), "rg_conv_down: H, W must be powers of two (got %d x %d)", H, W);
+  RG_CHECK_ARG(Cs % 64 == 0 && Cp % 8 == 0 && Cp >= 16, "rg_conv_down: need Cs %% 64 == 0, Cp %% 8 == 0 (Cs=%d Cp=%d)", Cs, Cp);
+  GemmMaps maps;
+  FwdArgs a;
+  fill_common(a, B, H, W);
+  int rc = encode_parity_maps(maps, hi, B, H, W, Cs, a.bw, a.bh, a.bb);
+  if (rc) return rc;
+  a.num_taps = 16;
+  a.chunks = Cs / 64;
+  for (int kh = 0; kh < 4; ++kh)
+    for (int kw = 0; kw < 4; ++kw) {
+      Tap t;
+      t.map = static_cast<int8_t>(kDownPar[kh] * 2 + kDownPar[kw]);
+      t.dh = static_cast<int8_t>(kDownOff[kh]);
+      t.dw = static_cast<int8_t>(kDownOff[kw]);
+      t.rsv = 0;
+      a.taps[0][kh * 4 + kw] = t;
+    }
+  a.n_total = Cp;
+  a.block_n = pick_block_n(Cp, a.m_tiles);
+  a.n_tiles = ceil_div(Cp, a.block_n);
+  a.b_phase_rows = 0;
+  rc = encode_map_2d(&maps.b, w_down, 16ull * Cs, Cp, 16ull * Cs, 64, a.block_n);
+  if (rc) return rc;
+  a.out = lo;
+  a.OH = H; a.OW = W; a.OC = Cp;
+  a.n_valid = Cp;
+  return launch_fwd(maps, a, OUT_BF16_NHWC, st);
+}
+
+static int conv_up_common(const void* lo, const void* w_up, void* out, const float* bias, int act_tanh, int B, int H,
+                          int W, int Cp, int Cs, int out_kind, cudaStream_t st) {
+  RG_CHECK_ARG(lo && w_up && out, "rg_conv_up: null pointer");
+  RG_CHECK_ARG(B > 0 && is_pow2(H) && is_pow2(W), "rg_conv_up: H, W must be powers of two (got %d x %d)", H, W);
+  RG_CHECK_ARG(Cp % 64 == 0, "rg_conv_up: need Cp %% 64 == 0 (Cp=%d)", Cp);
+  const int Cs_pad = std::max(16, (Cs + 15) / 16 * 16);
+  GemmMaps maps;
+  FwdArgs a;
+  fill_common(a, B, H, W);
+  int rc = encode_map_4d(&maps.a[0], lo, Cp, W, H, B, Cp, 1ull * W * Cp, 1ull * H * W * Cp, 64, a.bw, a.bh, a.bb);
+  if (rc) return rc;
+  maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+  a.num_taps = 4;
+  a.chunks = Cp / 64;
+  a.num_phases = 4;
+  for (int rh = 0; rh < 2; ++rh)
+    for (int rw = 0; rw < 2; ++rw) {
+      const int ph = rh * 2 + rw;
+      a.oy[ph] = static_cast<int8_t>(rh);
+      a.ox[ph] = static_cast<int8_t>(rw);
+      for (int th = 0; th < 2; ++th)
+        for (int tw = 0; tw < 2; ++tw) {
+          Tap t;
+          t.map = 0;
+          t.dh = static_cast<int8_t>(kUpOff[rh][th]);
+          t.dw = static_cast<int8_t>(kUpOff[rw][tw]);
+          t.rsv = 0;
+          a.taps[ph][th * 2 + tw] = t;
+        }
+    }
+  a.n_total = Cs_pad;
+  a.block_n = pick_block_n(Cs_pad, a.m_tiles * 4);
+  a.n_tiles = ceil_div(Cs_pad, a.block_n);
+  a.b_phase_rows = Cs_pad;
+  rc = encode_map_2d(&maps.b, w_up, 4ull * Cp, 4ull * Cs_pad, 4ull * Cp, 64, a.block_n);
+  if (rc) return rc;
+  a.out = out;
+  a.OH = 2 * H; a.OW = 2 * W; a.OC = Cs;
+  a.sy = a.sx = 2;
+  a.n_valid = Cs;
+  a.col_shift = bias;
+  a.act_tanh = act_tanh;
+  return launch_fwd(maps, a, out_kind, st);
+}
+
+int rg_conv_up(const void* lo, const void* w_up, void* hi, int B, int H, int W, int Cp, int Cs, rg_stream_t st_) {
+  RG_CHECK_ARG(Cs % 16 == 0, "rg_conv_up: need Cs %% 16 == 0 (Cs=%d); use rg_conv_up_img for image channels", Cs);
+  return conv_up_common(lo, w_up, hi, nullptr, 0, B, H, W, Cp, Cs, OUT_BF16_NHWC, static_cast<cudaStream_t>(st_));
+}
+
+int rg_conv_up_img(const void* lo, const void* w_up, float* img, const float* bias, int act_tanh, int B, int H, int W,
+                   int Cp, int Cimg, rg_stream_t st_) {
+  RG_CHECK_ARG(Cimg >= 1 && Cimg <= 8, "rg_conv_up_img: 1..8 image channels supported (got %d)", Cimg);
+  return conv_up_common(lo, w_up, img, bias, act_tanh, B, H, W, Cp, Cimg, OUT_F32_NCHW, static_cast<cudaStream_t>(st_));
+}
+
+int rg_gemm_nt(const void* A, const void* Bw, void* C, int M, int N, int K, int ldc, const float* col_scale,
+               const float* col_shift, float slope, int out_f32, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(A && Bw && C, "rg_gemm_nt: null pointer");
+  RG_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 64 == 0, "rg_gemm_nt: K must be a positive multiple of 64 (K=%d)", K);
+  RG_CHECK_ARG(ldc >= N && (out_f32 ? ldc % 4 == 0 : ldc % 8 == 0), "rg_gemm_nt: bad ldc %d", ldc);
+  GemmMaps maps;
+  FwdArgs a;
+  fill_common(a, M, 1, 1);
+  int rc = encode_map_4d(&maps.a[0], A, K, 1, 1, M, K, K, K, 64, 1, 1, kBlockM);
+  if (rc) return rc;
+  maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+  a.num_taps = 1;
+  a.chunks = K / 64;
+  Tap t = {0, 0, 0, 0};
+  a.taps[0][0] = t;
+  a.n_total = N;
+  a.block_n = pick_block_n(N, a.m_tiles);
+  a.n_tiles = ceil_div(N, a.block_n);
+  rc = encode_map_2d(&maps.b, Bw, K, N, K, 64, a.block_n);
+  if (rc) return rc;
+  a.out = C;
+  a.OH = 1; a.OW = 1; a.OC = ldc;
+  a.n_valid = N;
+  a.col_scale = col_scale;
+  a.col_shift = col_shift;
+  a.slope = slope;
+  return launch_fwd(maps, a, out_f32 ? OUT_F32_NHWC : OUT_BF16_NHWC, st);
+}
+
+size_t rg_conv_wgrad_ws_bytes(int B, int H, int W, int Cp, int Cs) {
+  if (B <= 0 || H <= 0 || W <= 0 || Cp <= 0 || Cs < 64) return 0;
+  WgradGeom w = wgrad_geom(B, H, W, Cp, Cs, 16);
+  return static_cast<size_t>(w.splits) * 16 * Cp * Cs * sizeof(float);
+}
+
+int rg_conv_wgrad(const void* lo, const void* hi, float* dW, void* ws, size_t ws_bytes, int B, int H, int W, int Cp,
+                  int Cs, float alpha, const float* alpha_dev, float beta, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(lo && hi && dW, "rg_conv_wgrad: null pointer");
+  RG_CHECK_ARG(B > 0 && is_pow2(H) && is_pow2(W), "rg_conv_wgrad: H, W must be powers of two (got %d x %d)", H, W);
+  RG_CHECK_ARG(Cs % 64 == 0 && Cp % 8 == 0, "rg_conv_wgrad: need Cs %% 64 == 0 and Cp %% 8 == 0 (Cs=%d Cp=%d)", Cs, Cp);
+  WgradGeom w = wgrad_geom(B, H, W, Cp, Cs, 16);
+  GemmMaps maps;
+  int rc = encode_parity_maps(maps, hi, B, H, W, Cs, w.g.bw, w.g.bh, w.g.bb);
+  if (rc) return rc;
+  rc = encode_map_4d(&maps.b, lo, Cp, W, H, B, Cp, 1ull * W * Cp, 1ull * H * W * Cp, 64, w.g.bw, w.g.bh, w.g.bb);
+  if (rc) return rc;
+  Tap taps[16];
+  for (int kh = 0; kh < 4; ++kh)
+    for (int kw = 0; kw < 4; ++kw) {
+      Tap t;
+      t.map = static_cast<int8_t>(kDownPar[kh] * 2 + kDownPar[kw]);
+      t.dh = static_cast<int8_t>(kDownOff[kh]);
+      t.dw = static_cast<int8_t>(kDownOff[kw]);
+      t.rsv = 0;
+      taps[kh * 4 + kw] = t;
+    }
+  return launch_wgrad(maps, w, taps, B, H, W, Cp, Cs, dW, ws, ws_bytes, alpha, alpha_dev, beta, st);
+}
+
+size_t rg_proj_wgrad_ws_bytes(int B, int E, int C0) {
+  if (B <= 0 || E <= 0 || C0 < 64) return 0;
+  WgradGeom w = wgrad_geom(B, 1, 1, E, C0, 16);
+  return static_cast<size_t>(w.splits) * 16 * E * C0 * sizeof(float);
+}
+
+int rg_proj_wgrad(const void* z, const void* da0, float* dW, void* ws, size_t ws_bytes, int B, int E, int C0,
+                  float alpha, const float* alpha_dev, float beta, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(z && da0 && dW, "rg_proj_wgrad: null pointer");
+  RG_CHECK_ARG(B > 0 && E % 8 == 0 && C0 % 64 == 0, "rg_proj_wgrad: need E %% 8 == 0, C0 %% 64 == 0 (E=%d C0=%d)", E, C0);
+  WgradGeom w = wgrad_geom(B, 1, 1, E, C0, 16);
+  GemmMaps maps;
+  // hi = da0[B][4][4][C0]; tap (kh,kw) reads pixel (kh,kw) of every sample
+  int rc = encode_map_4d(&maps.a[0], da0, C0, 4, 4, B, C0, 4ull * C0, 16ull * C0, 64, 1, 1, 64);
+  if (rc) return rc;
+  maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+  rc = encode_map_4d(&maps.b, z, E, 1, 1, B, E, E, E, 64, 1, 1, 64);
+  if (rc) return rc;
+  Tap taps[16];
+  for (int kh = 0; kh < 4; ++kh)
+    for (int kw = 0; kw < 4; ++kw) {
+      Tap t = {0, static_cast<int8_t>(kh), static_cast<int8_t>(kw), 0};
+      taps[kh * 4 + kw] = t;
+    }
+  return launch_wgrad(maps, w, taps, B, 1, 1, E, C0, dW, ws, ws_bytes, alpha, alpha_dev, beta, st);
+}
+
+size_t rg_gemm_tn_ws_bytes(int R, int M, int N) {
+  if (R <= 0 || M <= 0 || N < 64) return 0;
+  WgradGeom w = wgrad_geom(R, 1, 1, M, N, 1);
+  return static_cast<size_t>(w.splits) * M * N * sizeof(float);
+}
+
+int rg_gemm_tn(const void* A, const void* Bm, float* C, void* ws, size_t ws_bytes, int R, int M, int N, float alpha,
+               const float* alpha_dev, float beta, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(A && Bm && C, "rg_gemm_tn: null pointer");
+  RG_CHECK_ARG(R > 0 && M % 8 == 0 && N % 64 == 0, "rg_gemm_tn: need M %% 8 == 0, N %% 64 == 0 (M=%d N=%d)", M, N);
+  WgradGeom w = wgrad_geom(R, 1, 1, M, N, 1);
+  GemmMaps maps;
+  int rc = encode_map_4d(&maps.a[0], Bm, N, 1, 1, R, N, N, N, 64, 1, 1, 64);
+  if (rc) return rc;
+  maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+  rc = encode_map_4d(&maps.b, A, M, 1, 1, R, M, M, M, 64, 1, 1, 64);
+  if (rc) return rc;
+  Tap taps[1] = {{0, 0, 0, 0}};
+  return launch_wgrad(maps, w, taps, R, 1, 1, M, N, C, ws, ws_bytes, alpha, alpha_dev, beta, st);
+}
+
+}  // extern "C"

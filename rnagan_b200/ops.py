@@ -1,0 +1,175 @@
+"""Tensor-level wrappers over the C ABI: torch supplies device memory and streams, nothing else.
+
+Every function takes CUDA tensors, checks dtype/contiguity, and launches asynchronously on the current stream.
+"""
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if t.device.type != "cuda":
+        raise ValueError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    """Grow-only fp32 scratch per device (split-K partials); caller-owned from the library's point of view."""
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    cur = _ws_cache.get(key)
+    if cur is None or cur.numel() * 4 < nbytes:
+        cur = torch.empty((max(nbytes, 1) + 3) // 4, dtype=torch.float32, device=device)
+        _ws_cache[key] = cur
+    return cur
+
+
+def up_pad(cs):
+    return max(16, (cs + 15) // 16 * 16)
+
+
+# ------------------------------------------------------------------------------------------------ packing
+def pack_link(W, w_down=None, w_up=None, want_down=True, want_up=True):
+    """W: fp32 [Cp, Cs, 4, 4] -> (w_down bf16 [Cp, 16*Cs], w_up bf16 [4, Cs_pad, 4*Cp])."""
+    _chk(W, torch.float32, "W")
+    Cp, Cs = W.shape[0], W.shape[1]
+    if want_down and w_down is None:
+        w_down = torch.empty(Cp, 16 * Cs, dtype=BF16, device=W.device)
+    if want_up and w_up is None:
+        w_up = torch.zeros(4, up_pad(Cs), 4 * Cp, dtype=BF16, device=W.device)
+    _lib.check(_lib.lib().rg_pack_link(_p(W), _p(w_down) if want_down else None, _p(w_up) if want_up else None,
+                                       Cp, Cs, _st()), "rg_pack_link")
+    return w_down, w_up
+
+
+def pack_proj(W, out=None):
+    """W: fp32 [E, C0, 4, 4] -> bf16 [16*C0, E]."""
+    _chk(W, torch.float32, "W")
+    E, C0 = W.shape[0], W.shape[1]
+    if out is None:
+        out = torch.empty(16 * C0, E, dtype=BF16, device=W.device)
+    _lib.check(_lib.lib().rg_pack_proj(_p(W), _p(out), E, C0, _st()), "rg_pack_proj")
+    return out
+
+
+def pack_edge(W, out=None):
+    """W: fp32 [Cp, Cimg, 4, 4] -> bf16 [Cp, 64] (k = tap*4 + c)."""
+    _chk(W, torch.float32, "W")
+    Cp, Cimg = W.shape[0], W.shape[1]
+    if out is None:
+        out = torch.empty(Cp, 64, dtype=BF16, device=W.device)
+    _lib.check(_lib.lib().rg_pack_edge(_p(W), _p(out), Cp, Cimg, _st()), "rg_pack_edge")
+    return out
+
+
+def cast_pad_bf16(src, cols_pad=None, out=None):
+    _chk(src, torch.float32, "src")
+    rows, cols = src.shape
+    cols_pad = cols if cols_pad is None else cols_pad
+    if out is None:
+        out = torch.empty(rows, cols_pad, dtype=BF16, device=src.device)
+    _lib.check(_lib.lib().rg_cast_pad_bf16(_p(src), _p(out), rows, cols, cols_pad, _st()), "rg_cast_pad_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ contractions
+def conv_down(hi, w_down, out=None):
+    """hi bf16 [B, 2H, 2W, Cs], w_down bf16 [Cp, 16*Cs] -> lo bf16 [B, H, W, Cp]."""
+    _chk(hi, BF16, "hi"); _chk(w_down, BF16, "w_down")
+    B, H2, W2, Cs = hi.shape
+    Cp = w_down.shape[0]
+    H, W = H2 // 2, W2 // 2
+    if out is None:
+        out = torch.empty(B, H, W, Cp, dtype=BF16, device=hi.device)
+    _lib.check(_lib.lib().rg_conv_down(_p(hi), _p(w_down), _p(out), B, H, W, Cs, Cp, _st()), "rg_conv_down")
+    return out
+
+
+def conv_up(lo, w_up, Cs, out=None):
+    """lo bf16 [B, H, W, Cp], w_up bf16 [4, Cs_pad, 4*Cp] -> hi bf16 [B, 2H, 2W, Cs]."""
+    _chk(lo, BF16, "lo"); _chk(w_up, BF16, "w_up")
+    B, H, W, Cp = lo.shape
+    if out is None:
+        out = torch.empty(B, 2 * H, 2 * W, Cs, dtype=BF16, device=lo.device)
+    _lib.check(_lib.lib().rg_conv_up(_p(lo), _p(w_up), _p(out), B, H, W, Cp, Cs, _st()), "rg_conv_up")
+    return out
+
+
+def conv_up_img(lo, w_up, Cimg, bias=None, act_tanh=False, out=None):
+    """lo bf16 [B, H, W, Cp] -> fp32 NCHW image [B, Cimg, 2H, 2W] (+bias, tanh)."""
+    _chk(lo, BF16, "lo"); _chk(w_up, BF16, "w_up")
+    B, H, W, Cp = lo.shape
+    if out is None:
+        out = torch.empty(B, Cimg, 2 * H, 2 * W, dtype=torch.float32, device=lo.device)
+    _lib.check(_lib.lib().rg_conv_up_img(_p(lo), _p(w_up), _p(out), _p(bias), int(act_tanh), B, H, W, Cp, Cimg, _st()),
+               "rg_conv_up_img")
+    return out
+
+
+def conv_wgrad(lo, hi, dW, alpha=1.0, alpha_dev=None, beta=0.0):
+    """dW fp32 [Cp, Cs, 4, 4] = beta*dW + alpha * sum lo (x) hi@tap."""
+    _chk(lo, BF16, "lo"); _chk(hi, BF16, "hi"); _chk(dW, torch.float32, "dW")
+    B, H, W, Cp = lo.shape
+    Cs = hi.shape[3]
+    L = _lib.lib()
+    nbytes = L.rg_conv_wgrad_ws_bytes(B, H, W, Cp, Cs)
+    ws = _workspace(nbytes, lo.device)
+    _lib.check(L.rg_conv_wgrad(_p(lo), _p(hi), _p(dW), _p(ws), ws.numel() * 4, B, H, W, Cp, Cs, float(alpha),
+                               _p(alpha_dev), float(beta), _st()), "rg_conv_wgrad")
+    return dW
+
+
+def proj_wgrad(z, da0, dW, alpha=1.0, alpha_dev=None, beta=0.0):
+    """dW fp32 [E, C0, 4, 4] = sum_b z[b, e] * da0[b, kh, kw, c]."""
+    _chk(z, BF16, "z"); _chk(da0, BF16, "da0"); _chk(dW, torch.float32, "dW")
+    B, E = z.shape
+    C0 = da0.shape[-1]
+    L = _lib.lib()
+    nbytes = L.rg_proj_wgrad_ws_bytes(B, E, C0)
+    ws = _workspace(nbytes, z.device)
+    _lib.check(L.rg_proj_wgrad(_p(z), _p(da0), _p(dW), _p(ws), ws.numel() * 4, B, E, C0, float(alpha), _p(alpha_dev),
+                               float(beta), _st()), "rg_proj_wgrad")
+    return dW
+
+
+def gemm_nt(A, Bw, out=None, col_scale=None, col_shift=None, slope=1.0, out_f32=False, N=None):
+    """C[M, N] = lrelu((A[M, K] @ Bw[N, K]^T) * col_scale + col_shift)."""
+    _chk(A, BF16, "A"); _chk(Bw, BF16, "Bw")
+    M, K = A.shape
+    N = Bw.shape[0] if N is None else N
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32 if out_f32 else BF16, device=A.device)
+    ldc = out.stride(0)
+    _lib.check(_lib.lib().rg_gemm_nt(_p(A), _p(Bw), _p(out), M, N, K, ldc, _p(col_scale), _p(col_shift), float(slope),
+                                     int(out.dtype == torch.float32), _st()), "rg_gemm_nt")
+    return out
+
+
+def gemm_tn(A, Bm, out=None, alpha=1.0, alpha_dev=None, beta=0.0):
+    """C[M, N] fp32 = beta*C + alpha * A[R, M]^T @ Bm[R, N]."""
+    _chk(A, BF16, "A"); _chk(Bm, BF16, "Bm")
+    R, M = A.shape
+    N = Bm.shape[1]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    L = _lib.lib()
+    nbytes = L.rg_gemm_tn_ws_bytes(R, M, N)
+    ws = _workspace(nbytes, A.device)
+    _lib.check(L.rg_gemm_tn(_p(A), _p(Bm), _p(out), _p(ws), ws.numel() * 4, R, M, N, float(alpha), _p(alpha_dev),
+                            float(beta), _st()), "rg_gemm_tn")
+    return out

@@ -1,0 +1,158 @@
+"""GPU parity of the tcgen05 tile engine (C ABI: rg_conv_down / rg_conv_up / rg_conv_up_img / rg_conv_wgrad /
+rg_proj_wgrad / rg_gemm_nt / rg_gemm_tn) against fp32 torch ops evaluated on the SAME bf16-rounded operands, so the
+only difference is accumulation order: tolerance 2e-3 of the output scale for fp32 outputs, bf16 rounding
+(2^-8 relative) on top of that for bf16 outputs.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _nhwc(x):   # NCHW fp32 -> NHWC bf16
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _nchw(x):   # NHWC -> NCHW fp32
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (256, 128, 64), (64, 64, 64), (16, 2048, 2048),
+                                   (1000, 200, 192), (384, 6000, 640)])
+def test_gemm_nt(cuda_dev, M, N, K):
+    from rnagan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = _bf(torch.randn(M, K, generator=g)).to(cuda_dev)
+    Bw = _bf(torch.randn(N, K, generator=g)).to(cuda_dev)
+    ref = A @ Bw.t()
+    out = ops.gemm_nt(A.to(torch.bfloat16), Bw.to(torch.bfloat16), out_f32=True)
+    assert _rel(out, ref) < 2e-3
+    out16 = ops.gemm_nt(A.to(torch.bfloat16), Bw.to(torch.bfloat16))
+    assert _rel(out16, ref) < 8e-3
+
+
+def test_gemm_nt_epilogue(cuda_dev):
+    from rnagan_b200 import ops
+    M, N, K = 64, 6000, 19200
+    g = torch.Generator(device="cpu").manual_seed(5)
+    A = _bf(torch.randn(M, K, generator=g)).to(cuda_dev)
+    Bw = _bf(torch.randn(N, K, generator=g) * 0.01).to(cuda_dev)
+    sc = (torch.rand(N, generator=g) + 0.5).to(cuda_dev)
+    sh = torch.randn(N, generator=g).to(cuda_dev)
+    ref = F.leaky_relu((A @ Bw.t()) * sc + sh, 0.01)
+    out = ops.gemm_nt(A.to(torch.bfloat16), Bw.to(torch.bfloat16), col_scale=sc, col_shift=sh, slope=0.01,
+                      out_f32=True)
+    assert _rel(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cs,Cp", [(16, 16, 16, 256, 512), (8, 4, 4, 1024, 2048), (4, 64, 64, 64, 128),
+                                         (2, 32, 32, 128, 256), (16, 8, 8, 128, 64)])
+def test_conv_down(cuda_dev, B, H, W, Cs, Cp):
+    """lo = conv2d(hi, W[Cp,Cs,4,4], stride 2, pad 1) -- critic forward / generator dgrad."""
+    from rnagan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B + H + Cs + Cp)
+    x = _bf(torch.randn(B, Cs, 2 * H, 2 * W, generator=g)).to(cuda_dev)
+    Wt = _bf(torch.randn(Cp, Cs, 4, 4, generator=g) * 0.05).to(cuda_dev)
+    ref = F.conv2d(x, Wt, stride=2, padding=1)
+    w_down, _ = ops.pack_link(Wt, want_up=False)
+    out = ops.conv_down(_nhwc(x), w_down)
+    assert out.shape == (B, H, W, Cp)
+    assert _rel(_nchw(out), ref) < 8e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cp,Cs", [(16, 16, 16, 512, 256), (8, 4, 4, 2048, 1024), (4, 64, 64, 128, 64),
+                                         (2, 32, 32, 256, 128), (16, 8, 8, 64, 128)])
+def test_conv_up(cuda_dev, B, H, W, Cp, Cs):
+    """hi = conv_transpose2d(lo, W[Cp,Cs,4,4], stride 2, pad 1) -- generator forward / critic dgrad."""
+    from rnagan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B + H + Cs + Cp + 1)
+    x = _bf(torch.randn(B, Cp, H, W, generator=g)).to(cuda_dev)
+    Wt = _bf(torch.randn(Cp, Cs, 4, 4, generator=g) * 0.05).to(cuda_dev)
+    ref = F.conv_transpose2d(x, Wt, stride=2, padding=1)
+    _, w_up = ops.pack_link(Wt, want_down=False)
+    out = ops.conv_up(_nhwc(x), w_up, Cs)
+    assert out.shape == (B, 2 * H, 2 * W, Cs)
+    assert _rel(_nchw(out), ref) < 8e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cp", [(4, 32, 32, 64), (2, 128, 128, 64)])
+def test_conv_up_img(cuda_dev, B, H, W, Cp):
+    from rnagan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B + H)
+    x = _bf(torch.randn(B, Cp, H, W, generator=g)).to(cuda_dev)
+    Wt = _bf(torch.randn(Cp, 3, 4, 4, generator=g) * 0.05).to(cuda_dev)
+    bias = torch.randn(3, generator=g).to(cuda_dev)
+    ref = torch.tanh(F.conv_transpose2d(x, Wt, bias=bias, stride=2, padding=1))
+    _, w_up = ops.pack_link(Wt, want_down=False)
+    out = ops.conv_up_img(_nhwc(x), w_up, 3, bias=bias, act_tanh=True)
+    assert (out - ref).abs().max().item() < 2e-3
+    ref2 = F.conv_transpose2d(x, Wt, stride=2, padding=1)
+    out2 = ops.conv_up_img(_nhwc(x), w_up, 3)
+    assert _rel(out2, ref2) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cs,Cp", [(16, 16, 16, 256, 512), (8, 4, 4, 1024, 2048), (4, 64, 64, 64, 128),
+                                         (2, 32, 32, 128, 256), (16, 8, 8, 128, 64)])
+def test_conv_wgrad(cuda_dev, B, H, W, Cs, Cp):
+    """dW[p,s,kh,kw] = sum lo[b,i,j,p] hi[b,2i-1+kh,2j-1+kw,s] == conv2d weight gradient."""
+    from rnagan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B + H + Cs + Cp + 2)
+    hi = _bf(torch.randn(B, Cs, 2 * H, 2 * W, generator=g)).to(cuda_dev)
+    lo = _bf(torch.randn(B, Cp, H, W, generator=g)).to(cuda_dev)
+    ref = torch.nn.grad.conv2d_weight(hi, (Cp, Cs, 4, 4), lo, stride=2, padding=1)
+    dW = torch.empty(Cp, Cs, 4, 4, device=cuda_dev)
+    ops.conv_wgrad(_nhwc(lo), _nhwc(hi), dW)
+    assert _rel(dW, ref) < 2e-3
+    # accumulate + scale
+    scale = torch.tensor([0.5], device=cuda_dev)
+    ops.conv_wgrad(_nhwc(lo), _nhwc(hi), dW, alpha=2.0, alpha_dev=scale, beta=1.0)
+    assert _rel(dW, 2 * ref) < 2e-3
+
+
+def test_proj_wgrad_and_fwd(cuda_dev):
+    """generator layer 0: ConvTranspose2d(E, C0, 4, 1, 0) on a 1x1 input as a plain GEMM, and its weight gradient."""
+    from rnagan_b200 import ops
+    B, E, C0 = 16, 256, 128
+    g = torch.Generator(device="cpu").manual_seed(11)
+    z = _bf(torch.randn(B, E, generator=g)).to(cuda_dev)
+    Wt = _bf(torch.randn(E, C0, 4, 4, generator=g) * 0.05).to(cuda_dev)
+    ref = F.conv_transpose2d(z.view(B, E, 1, 1), Wt)           # [B, C0, 4, 4]
+    wp = ops.pack_proj(Wt)
+    out = ops.gemm_nt(z.to(torch.bfloat16), wp, out_f32=True).view(B, 4, 4, C0)
+    assert _rel(_nchw(out), ref) < 2e-3
+    da0 = _bf(torch.randn(B, C0, 4, 4, generator=g)).to(cuda_dev)
+    refw = torch.einsum("be,bchw->echw", z, da0)
+    dW = torch.empty(E, C0, 4, 4, device=cuda_dev)
+    ops.proj_wgrad(z.to(torch.bfloat16), _nhwc(da0), dW)
+    assert _rel(dW, refw) < 2e-3
+
+
+@pytest.mark.parametrize("R,M,N", [(4096, 64, 64), (100000, 64, 64), (64, 128, 256), (777, 256, 128)])
+def test_gemm_tn(cuda_dev, R, M, N):
+    from rnagan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(R + M + N)
+    A = _bf(torch.randn(R, M, generator=g)).to(cuda_dev)
+    Bm = _bf(torch.randn(R, N, generator=g)).to(cuda_dev)
+    ref = A.double().t() @ Bm.double()
+    out = ops.gemm_tn(A.to(torch.bfloat16), Bm.to(torch.bfloat16))
+    assert _rel(out.double(), ref) < 2e-3
+
+
+def test_pack_edge(cuda_dev):
+    from rnagan_b200 import ops
+    Wt = torch.randn(64, 3, 4, 4, device=cuda_dev)
+    wc = ops.pack_edge(Wt).float().view(64, 16, 4)
+    ref = _bf(Wt).permute(0, 2, 3, 1).reshape(64, 16, 3)
+    assert torch.equal(wc[:, :, :3], ref)
+    assert wc[:, :, 3].abs().max().item() == 0
