@@ -82,6 +82,76 @@ size_t rg_gemm_tn_ws_bytes(int R, int M, int N);
 int rg_gemm_tn(const void* A, const void* Bm, float* C, void* ws, size_t ws_bytes, int R, int M, int N, float alpha,
                const float* alpha_dev, float beta, rg_stream_t st);
 
+/* ---- HBM-bound kernels (rg_ops.cu) ----------------------------------------------------------------------- */
+/* Activations are bf16 NHWC viewed as [M rows][C channels]; per-channel vectors are fp32 [C].  Reductions need a
+ * scratch buffer of rg_reduce_ws_bytes(M, C) bytes. */
+size_t rg_reduce_ws_bytes(int M, int C);
+/* nn.BatchNorm2d training forward (11 instances): sums[0][C]=sum a, sums[1][C]=sum a^2 */
+int rg_bn_stats(const void* a, int M, int C, void* ws, size_t ws_bytes, float* sums, rg_stream_t st);
+/* mean/rstd/scale=gamma*rstd/shift=beta-mean*scale; running stats with momentum and unbiased variance; counter += 1 */
+int rg_bn_finalize(const float* sums, const float* gamma, const float* beta, int M, int C, float eps, float momentum,
+                   float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean, float* rstd,
+                   float* scale, float* shift, rg_stream_t st);
+/* h = LeakyReLU(scale*a + shift) */
+int rg_bn_act(const void* a, const float* scale, const float* shift, float slope, void* h, int M, int C,
+              rg_stream_t st);
+/* backward of LeakyReLU(BN(a)): sums[0]=S(du), sums[1]=S(du*xhat), du = dh*lrelu'(u) */
+int rg_bn_bwd_reduce(const void* dh, const void* a, const float* mean, const float* rstd, const float* scale,
+                     const float* shift, float slope, int M, int C, void* ws, size_t ws_bytes, float* sums,
+                     rg_stream_t st);
+/* da = scale*(du - S(du)/M - xhat*S(du*xhat)/M) (+ add); du_out optional (kept for the gradient-penalty pass) */
+int rg_bn_bwd_apply(const void* dh, const void* a, const void* add, const float* mean, const float* rstd,
+                    const float* scale, const float* shift, float slope, const float* sums, int M, int C, void* da,
+                    void* du_out, rg_stream_t st);
+/* dgamma = acc_gamma*dgamma + S(du*xhat); dbeta = acc_beta*dbeta + S(du) */
+int rg_bn_param_grads(const float* sums, float* dgamma, float* dbeta, int C, float acc_gamma, float acc_beta,
+                      rg_stream_t st);
+/* da = dh * lrelu'(h) for the BatchNorm-free first critic layer */
+int rg_lrelu_bwd(const void* dh, const void* h, float slope, void* da, int M, int C, rg_stream_t st);
+/* out[c] = acc*out[c] + sum_rows x[row][c]  (bias gradients); tmp: fp32 [C] */
+int rg_col_sum(const void* x, int M, int C, void* ws, size_t ws_bytes, float* tmp, float* out, float acc,
+               rg_stream_t st);
+/* double backward of BatchNorm inside the gradient penalty (autograd.grad(create_graph=True), src/wgan_loss.py:34-41;
+ * formulas SURVEY.md Appendix C): q[0]=S(ggI), q[1]=S(ggI*xhat), q[2]=S(ggI*gO) */
+int rg_bn_gp_reduce(const void* ggI, const void* a, const void* gO, const float* mean, const float* rstd, int M, int C,
+                    void* ws, size_t ws_bytes, float* q, rg_stream_t st);
+int rg_bn_gp_apply(const void* ggI, const void* a, const void* gO, const float* mean, const float* rstd,
+                   const float* gamma, const float* scale, const float* shift, float slope, const float* s,
+                   const float* q, int M, int C, void* A_dh, void* A_a, float* dgamma, float dgamma_acc,
+                   rg_stream_t st);
+/* latent = standardise_0(noise + z), unbiased std (src/wgan_loss.py:105-106, src/gan_utils.py:215-216);
+ * z_rows == 1 broadcasts one profile (generate_images). Outputs bf16 and/or fp32 (either may be NULL). */
+int rg_latent_prep(const float* noise, const float* z, int B, int E, int z_rows, void* lat_bf16, float* lat_f32,
+                   rg_stream_t st);
+/* im2col of an fp32 NCHW image for the 3-channel 4x4/s2/p1 link: col bf16 [B*(S/2)^2][64], k = tap*4 + c.
+ * mode 0: x*mul; mode 1: (eps*x + (1-eps)*y)*mul (src/wgan_loss.py:377); mode 2: x*(1-y^2)*mul (tanh backward). */
+int rg_im2col_img(const float* x, const float* y, int mode, const float* eps_dev, const float* mul_dev, int B,
+                  int Cimg, int S, void* col, float* mixed_out, rg_stream_t st);
+int rg_img_channel_sum(const float* x, const float* y, int mode, int B, int Cimg, int S, float* out, float acc,
+                       rg_stream_t st);
+int rg_unpack_edge_grad(const float* dcol, float* dW, int Cp, int Cimg, float acc, rg_stream_t st);
+/* critic head `disc` = Conv2d(C,1,4,1,0)+LeakyReLU on a 4x4 map (torchgan DCGANDiscriminator): w_head[k=tap*C+c] */
+int rg_pack_head(const float* W, float* w_head, int C, rg_stream_t st);
+int rg_head_fwd(const void* h5, const float* w_head, int B, int K, float slope, float* a6, float* out, rg_stream_t st);
+int rg_head_bwd_data(const float* a6, const float* dout, float dout_const, const float* w_head, int B, int K,
+                     float slope, float* da6, void* dh5, rg_stream_t st);
+int rg_head_wgrad(const float* da6, const void* x, int B, int K, int C, float* dW, float acc, rg_stream_t st);
+/* loss_out[0] = mean(sign_a*a) + mean(sign_b*b)  (src/wgan_loss.py:24-29) */
+int rg_wgan_loss(const float* a, float sign_a, const float* b, float sign_b, int B, float* loss_out, rg_stream_t st);
+/* out3 = {(||g||-1)^2, lambda*2*(||g||-1)/||g||, ||g||}: whole-batch Frobenius norm (src/wgan_loss.py:43) */
+int rg_gp_norm(const float* g, size_t n, float lambd, float* partial_ws, int partial_len, float* out3, rg_stream_t st);
+/* torch.optim.Adam(lr, betas, eps; no weight decay/amsgrad) over a table of tensors (src/histopathology_gan.py:252,257),
+ * with the optional WGAN weight clamp (src/wgan_loss.py:213-215) fused in.  rg_adam_build_table fills a HOST table
+ * and returns the number of chunks (>0); copy it to the device and pass it to rg_adam_step. */
+int rg_adam_table_bytes(int num_chunks);
+int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms, void* const* vs, const int64_t* sizes,
+                        int num_tensors, int chunk_elems, void* table_host, int max_chunks);
+int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, float beta2, float eps, int step,
+                 int do_clamp, float clamp_lo, float clamp_hi, rg_stream_t st);
+int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st);
+/* (x+1)/2 and NCHW -> NHWC fp32 (src/gan_utils.py:236-241) */
+int rg_tiles_to_unit_nhwc(const float* img, float* out, int B, int C, int S, rg_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,32 @@ SIGNATURES = {
     "rg_gemm_nt": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp]),
     "rg_gemm_tn_ws_bytes": (_sz, [_i, _i, _i]),
     "rg_gemm_tn": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp, _f, _vp]),
+    "rg_reduce_ws_bytes": (_sz, [_i, _i]),
+    "rg_bn_stats": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp]),
+    "rg_bn_finalize": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rg_bn_act": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _vp]),
+    "rg_bn_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _sz, _vp, _vp]),
+    "rg_bn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp, _vp, _vp]),
+    "rg_bn_param_grads": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp]),
+    "rg_lrelu_bwd": (_i, [_vp, _vp, _f, _vp, _i, _i, _vp]),
+    "rg_col_sum": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp, _f, _vp]),
+    "rg_bn_gp_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp]),
+    "rg_bn_gp_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _vp, _vp, _vp, _f, _vp]),
+    "rg_latent_prep": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rg_im2col_img": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rg_img_channel_sum": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _f, _vp]),
+    "rg_unpack_edge_grad": (_i, [_vp, _vp, _i, _i, _f, _vp]),
+    "rg_pack_head": (_i, [_vp, _vp, _i, _vp]),
+    "rg_head_fwd": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "rg_head_bwd_data": (_i, [_vp, _vp, _f, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "rg_head_wgrad": (_i, [_vp, _vp, _i, _i, _i, _vp, _f, _vp]),
+    "rg_wgan_loss": (_i, [_vp, _f, _vp, _f, _i, _vp, _vp]),
+    "rg_gp_norm": (_i, [_vp, _sz, _f, _vp, _i, _vp, _vp]),
+    "rg_adam_table_bytes": (_i, [_i]),
+    "rg_adam_build_table": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i]),
+    "rg_adam_step": (_i, [_vp, _i, _f, _f, _f, _f, _i, _i, _f, _f, _vp]),
+    "rg_clamp": (_i, [_vp, _sz, _f, _f, _vp]),
+    "rg_tiles_to_unit_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,912 @@
+// rg_ops.cu -- the HBM-bound kernels of the RNA-GAN hot path:
+// BatchNorm statistics / apply / backward / double-backward fused with LeakyReLU, latent preparation, image
+// im2col (with the gradient-penalty interpolation and the tanh backward fused in), the critic head + WGAN losses,
+// the gradient-penalty scalar, and a multi-tensor Adam that re-emits the packed bf16 operands.
+//
+// All activations are bf16 NHWC viewed as [M = B*H*W rows][C channels]; every kernel moves 16-byte vectors
+// (8 channels) with the channel index fastest so warps read/write whole 128-byte lines.  Per-channel reductions
+// are two-stage and summed in a fixed order (deterministic; the reference sets cudnn.deterministic=True,
+// src/histopathology_gan.py:289).
+#include <algorithm>
+#include "rg_host.cuh"
+#include <cuda_bf16.h>
+
+namespace rg {
+
+// ------------------------------------------------------------------------------------------------ vector helpers
+struct Vec8 {
+  float v[8];
+};
+__device__ __forceinline__ Vec8 ld8(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  Vec8 r;
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const Vec8& r) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ Vec8 ldf8(const float* p) {
+  Vec8 r;
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------ column reduce
+// Stage 1: partial[block][k][c] = sum over the block's rows of f_k(row, c).  Functor F: static K, and
+//   __device__ void operator()(size_t row, int c0, float (&acc)[K][8]) const   (accumulates 8 channels)
+template <class F>
+__global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int rows_per_block, float* __restrict__ partial) {
+  constexpr int K = F::K;
+  extern __shared__ float sm[];   // [lanes][K][8*cgs_in_flight] only used when lanes > 1
+  const int cgs = C >> 3;
+  const int lanes = cgs >= 256 ? 1 : 256 / cgs;            // row lanes per block iteration
+  const int rl = cgs >= 256 ? 0 : threadIdx.x / cgs;
+  const int cg0 = cgs >= 256 ? threadIdx.x : threadIdx.x % cgs;
+  const bool active = cgs >= 256 ? true : (threadIdx.x < lanes * cgs);
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  for (int cg = cg0; cg < cgs; cg += 256) {
+    float acc[K][8];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[k][e] = 0.0f;
+    if (active)
+      for (int r = r0 + rl; r < r1; r += lanes) f(static_cast<size_t>(r), cg * 8, acc);
+    if (lanes == 1) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          partial[(static_cast<size_t>(blockIdx.x) * K + k) * C + cg * 8 + e] = acc[k][e];
+    } else {
+      // sm[rl][k][c]
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sm[(rl * K + k) * C + cg * 8 + e] = acc[k][e];
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < K * C; i += 256) {
+        float s = 0.0f;
+        for (int l = 0; l < lanes; ++l) s += sm[l * K * C + i];
+        partial[static_cast<size_t>(blockIdx.x) * K * C + i] = s;
+      }
+    }
+  }
+}
+// Stage 2: out[k][c] = sum_blocks partial[block][k][c] (fixed order)
+__global__ void colreduce_stage2(const float* __restrict__ partial, int nblocks, int KC, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= KC) return;
+  float s = 0.0f;
+  for (int b = 0; b < nblocks; ++b) s += partial[static_cast<size_t>(b) * KC + i];
+  out[i] = s;
+}
+
+struct ReducePlan {
+  int blocks, rows_per_block;
+  size_t smem;
+};
+static ReducePlan plan_reduce(int M, int C, int K) {
+  ReducePlan p;
+  const int cgs = C / 8;
+  const int lanes = cgs >= 256 ? 1 : 256 / cgs;
+  int target = num_sms() * 4;
+  int rpb = std::max(lanes * 4, ceil_div(M, target));
+  rpb = ceil_div(rpb, lanes) * lanes;
+  p.rows_per_block = rpb;
+  p.blocks = ceil_div(M, rpb);
+  p.smem = lanes > 1 ? static_cast<size_t>(lanes) * K * C * sizeof(float) : 0;
+  return p;
+}
+static size_t reduce_ws_floats(int M, int C, int K) {
+  ReducePlan p = plan_reduce(M, C, K);
+  return static_cast<size_t>(p.blocks) * K * C;
+}
+
+template <class F>
+static int run_colreduce(F f, int M, int C, float* ws, size_t ws_bytes, float* out, cudaStream_t st, const char* name) {
+  constexpr int K = F::K;
+  if (C % 8 != 0 || C < 8 || C > 8192 || M <= 0) {
+    set_error("%s: need C %% 8 == 0, 8 <= C <= 8192, M > 0 (M=%d C=%d)", name, M, C);
+    return RG_EINVAL;
+  }
+  ReducePlan p = plan_reduce(M, C, K);
+  const size_t need = static_cast<size_t>(p.blocks) * K * C * sizeof(float);
+  if (!ws || ws_bytes < need) {
+    set_error("%s: reduction workspace too small (need %zu, have %zu)", name, need, ws_bytes);
+    return RG_EWORKSPACE;
+  }
+  if (p.smem > 48 * 1024) {
+    static bool attr_done = false;   // per instantiation
+    if (!attr_done) {
+      RG_CUDA(cudaFuncSetAttribute(colreduce_stage1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_done = true;
+    }
+  }
+  colreduce_stage1<F><<<p.blocks, 256, p.smem, st>>>(f, M, C, p.rows_per_block, ws);
+  RG_LAUNCH_CHECK(name);
+  colreduce_stage2<<<ceil_div(K * C, 256), 256, 0, st>>>(ws, p.blocks, K * C, out);
+  RG_LAUNCH_CHECK(name);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise driver
+// Functor: __device__ void operator()(size_t row, int c0) const  -- processes 8 channels of one row
+template <class F>
+__global__ void __launch_bounds__(256) ew_kernel(F f, size_t nvec, int cgs) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t row = i / cgs;
+    const int cg = static_cast<int>(i - row * cgs);
+    f(row, cg * 8);
+  }
+}
+template <class F>
+static int run_ew(F f, int M, int C, cudaStream_t st, const char* name) {
+  if (C % 8 != 0 || M <= 0) {
+    set_error("%s: need C %% 8 == 0 and M > 0 (M=%d C=%d)", name, M, C);
+    return RG_EINVAL;
+  }
+  const size_t nvec = static_cast<size_t>(M) * (C / 8);
+  const int grid = static_cast<int>(std::min<size_t>((nvec + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  ew_kernel<F><<<grid, 256, 0, st>>>(f, nvec, C / 8);
+  RG_LAUNCH_CHECK(name);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ BN functors
+struct StatsF {   // sum a, sum a^2
+  static constexpr int K = 2;
+  const __nv_bfloat16* a;
+  int C;
+  __device__ void operator()(size_t row, int c0, float (&acc)[2][8]) const {
+    const Vec8 x = ld8(a + row * C + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += x.v[e];
+      acc[1][e] += x.v[e] * x.v[e];
+    }
+  }
+};
+
+struct BnActF {   // h = lrelu(scale*a + shift)
+  const __nv_bfloat16* a;
+  __nv_bfloat16* h;
+  const float* scale;
+  const float* shift;
+  float slope;
+  int C;
+  __device__ void operator()(size_t row, int c0) const {
+    const Vec8 x = ld8(a + row * C + c0);
+    const Vec8 sc = ldf8(scale + c0), sh = ldf8(shift + c0);
+    Vec8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float u = fmaf(x.v[e], sc.v[e], sh.v[e]);
+      o.v[e] = u > 0.0f ? u : u * slope;
+    }
+    st8(h + row * C + c0, o);
+  }
+};
+
+// du = dh * lrelu'(u), u = scale*a + shift, xhat = (a - mean) * rstd
+struct BwdReduceF {   // S(du), S(du*xhat)
+  static constexpr int K = 2;
+  const __nv_bfloat16* dh;
+  const __nv_bfloat16* a;
+  const float *mean, *rstd, *scale, *shift;
+  float slope;
+  int C;
+  __device__ void operator()(size_t row, int c0, float (&acc)[2][8]) const {
+    const Vec8 g = ld8(dh + row * C + c0), x = ld8(a + row * C + c0);
+    const Vec8 mu = ldf8(mean + c0), rs = ldf8(rstd + c0), sc = ldf8(scale + c0), sh = ldf8(shift + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float u = fmaf(x.v[e], sc.v[e], sh.v[e]);
+      const float du = u > 0.0f ? g.v[e] : g.v[e] * slope;
+      acc[0][e] += du;
+      acc[1][e] += du * (x.v[e] - mu.v[e]) * rs.v[e];
+    }
+  }
+};
+
+struct BwdApplyF {   // da = scale*(du - s1/M - xhat*s2/M) (+ add); optional du output
+  const __nv_bfloat16* dh;
+  const __nv_bfloat16* a;
+  const __nv_bfloat16* add;
+  __nv_bfloat16* da;
+  __nv_bfloat16* du_out;
+  const float *mean, *rstd, *scale, *shift, *sums;   // sums[0][C] = S(du), sums[1][C] = S(du*xhat)
+  float slope, invM;
+  int C;
+  __device__ void operator()(size_t row, int c0) const {
+    const size_t off = row * C + c0;
+    const Vec8 g = ld8(dh + off), x = ld8(a + off);
+    const Vec8 mu = ldf8(mean + c0), rs = ldf8(rstd + c0), sc = ldf8(scale + c0), sh = ldf8(shift + c0);
+    const Vec8 s1 = ldf8(sums + c0), s2 = ldf8(sums + C + c0);
+    Vec8 o, d;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float u = fmaf(x.v[e], sc.v[e], sh.v[e]);
+      const float du = u > 0.0f ? g.v[e] : g.v[e] * slope;
+      const float xh = (x.v[e] - mu.v[e]) * rs.v[e];
+      d.v[e] = du;
+      o.v[e] = sc.v[e] * (du - s1.v[e] * invM - xh * s2.v[e] * invM);
+    }
+    if (add) {
+      const Vec8 ad = ld8(add + off);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o.v[e] += ad.v[e];
+    }
+    st8(da + off, o);
+    if (du_out) st8(du_out + off, d);
+  }
+};
+
+struct LreluBwdF {   // da = dh * lrelu'(h)   (layer without BatchNorm: mask from the stored activation)
+  const __nv_bfloat16* dh;
+  const __nv_bfloat16* h;
+  __nv_bfloat16* da;
+  float slope;
+  int C;
+  __device__ void operator()(size_t row, int c0) const {
+    const size_t off = row * C + c0;
+    const Vec8 g = ld8(dh + off), x = ld8(h + off);
+    Vec8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o.v[e] = x.v[e] > 0.0f ? g.v[e] : g.v[e] * slope;
+    st8(da + off, o);
+  }
+};
+
+struct ColSumF {   // S(x)
+  static constexpr int K = 1;
+  const __nv_bfloat16* x;
+  int C;
+  __device__ void operator()(size_t row, int c0, float (&acc)[1][8]) const {
+    const Vec8 v = ld8(x + row * C + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[0][e] += v.v[e];
+  }
+};
+
+// gradient-penalty double backward through BatchNorm: ggI = adjoint of da, gO = du
+struct GpReduceF {   // S(ggI), S(ggI*xhat), S(ggI*gO)
+  static constexpr int K = 3;
+  const __nv_bfloat16* ggI;
+  const __nv_bfloat16* a;
+  const __nv_bfloat16* gO;
+  const float *mean, *rstd;
+  int C;
+  __device__ void operator()(size_t row, int c0, float (&acc)[3][8]) const {
+    const size_t off = row * C + c0;
+    const Vec8 gi = ld8(ggI + off), x = ld8(a + off), go = ld8(gO + off);
+    const Vec8 mu = ldf8(mean + c0), rs = ldf8(rstd + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += gi.v[e];
+      acc[1][e] += gi.v[e] * (x.v[e] - mu.v[e]) * rs.v[e];
+      acc[2][e] += gi.v[e] * go.v[e];
+    }
+  }
+};
+
+struct GpApplyF {
+  // A_dh = lrelu'(u) * gamma*r/M*(M*ggI - q1 - xhat*q2)
+  // A_a  = gamma*r^2/M * [ xhat*(q1*s1/M - q3 + 3*s2*q2/M) + q2*(s1/M - gO) + s2*(q1/M - ggI) ]
+  const __nv_bfloat16* ggI;
+  const __nv_bfloat16* a;
+  const __nv_bfloat16* gO;
+  __nv_bfloat16* A_dh;
+  __nv_bfloat16* A_a;
+  const float *mean, *rstd, *gamma, *scale, *shift, *s, *q;   // s[2][C], q[3][C]
+  float slope, invM;
+  int C;
+  __device__ void operator()(size_t row, int c0) const {
+    const size_t off = row * C + c0;
+    const Vec8 gi = ld8(ggI + off), x = ld8(a + off), go = ld8(gO + off);
+    const Vec8 mu = ldf8(mean + c0), rs = ldf8(rstd + c0), ga = ldf8(gamma + c0), sc = ldf8(scale + c0),
+               sh = ldf8(shift + c0);
+    const Vec8 s1 = ldf8(s + c0), s2 = ldf8(s + C + c0);
+    const Vec8 q1 = ldf8(q + c0), q2 = ldf8(q + C + c0), q3 = ldf8(q + 2 * C + c0);
+    Vec8 o1, o2;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (x.v[e] - mu.v[e]) * rs.v[e];
+      const float u = fmaf(x.v[e], sc.v[e], sh.v[e]);
+      const float gr = ga.v[e] * rs.v[e];
+      const float adu = gr * (gi.v[e] - q1.v[e] * invM - xh * q2.v[e] * invM);
+      o1.v[e] = u > 0.0f ? adu : adu * slope;
+      const float k = gr * rs.v[e] * invM;
+      o2.v[e] = k * (xh * (q1.v[e] * s1.v[e] * invM - q3.v[e] + 3.0f * s2.v[e] * q2.v[e] * invM) +
+                     q2.v[e] * (s1.v[e] * invM - go.v[e]) + s2.v[e] * (q1.v[e] * invM - gi.v[e]));
+    }
+    st8(A_dh + off, o1);
+    st8(A_a + off, o2);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ small kernels
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int C, float invM, float unbias, float eps,
+                                   float momentum, float* running_mean, float* running_var, long long* nbt,
+                                   float* mean, float* rstd, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  const float m = sums[c] * invM;
+  const float var = fmaxf(sums[C + c] * invM - m * m, 0.0f);
+  const float r = rsqrtf(var + eps);
+  mean[c] = m;
+  rstd[c] = r;
+  const float sc = gamma[c] * r;
+  scale[c] = sc;
+  shift[c] = beta[c] - m * sc;
+  if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * m;
+  if (running_var) running_var[c] = (1.0f - momentum) * running_var[c] + momentum * var * unbias;
+}
+
+// dgamma (+)= S(du*xhat); dbeta (+)= S(du)
+__global__ void bn_param_grads_kernel(const float* __restrict__ sums, float* dgamma, float* dbeta, int C,
+                                      float acc_gamma, float acc_beta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dgamma[c] = (acc_gamma != 0.0f ? acc_gamma * dgamma[c] : 0.0f) + sums[C + c];
+  dbeta[c] = (acc_beta != 0.0f ? acc_beta * dbeta[c] : 0.0f) + sums[c];
+}
+// dgamma (+)= r/M*(M*q3 - q1*s1 - q2*s2)
+__global__ void bn_gp_dgamma_kernel(const float* __restrict__ s, const float* __restrict__ q,
+                                    const float* __restrict__ rstd, float* dgamma, int C, float invM, float acc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float v = rstd[c] * (q[2 * C + c] - (q[c] * s[c] + q[C + c] * s[C + c]) * invM);
+  dgamma[c] = (acc != 0.0f ? acc * dgamma[c] : 0.0f) + v;
+}
+__global__ void vec_axpby_kernel(const float* __restrict__ x, float* y, int n, float a, float b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = (b != 0.0f ? b * y[i] : 0.0f) + a * x[i];
+}
+
+// latent = standardise_0(noise + z) with unbiased std (src/wgan_loss.py:105-106); one thread per feature column
+__global__ void latent_prep_kernel(const float* __restrict__ noise, const float* __restrict__ z, int B, int E, int zB,
+                                   __nv_bfloat16* __restrict__ lat_bf16, float* __restrict__ lat_f32) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  float s = 0.0f;
+  for (int b = 0; b < B; ++b) s += noise[static_cast<size_t>(b) * E + e] + z[static_cast<size_t>(zB == 1 ? 0 : b) * E + e];
+  const float m = s / B;
+  float ss = 0.0f;
+  for (int b = 0; b < B; ++b) {
+    const float d = noise[static_cast<size_t>(b) * E + e] + z[static_cast<size_t>(zB == 1 ? 0 : b) * E + e] - m;
+    ss += d * d;
+  }
+  const float sd = sqrtf(ss / (B - 1));   // B == 1 -> NaN, like the reference
+  for (int b = 0; b < B; ++b) {
+    const float v = (noise[static_cast<size_t>(b) * E + e] + z[static_cast<size_t>(zB == 1 ? 0 : b) * E + e] - m) / sd;
+    if (lat_bf16) lat_bf16[static_cast<size_t>(b) * E + e] = __float2bfloat16(v);
+    if (lat_f32) lat_f32[static_cast<size_t>(b) * E + e] = v;
+  }
+}
+
+// im2col of a fp32 NCHW image [B][Cimg<=4][S][S] for the 4x4 stride-2 pad-1 conv: col[pix][k], k = (kh*4+kw)*4 + c.
+// mode 0: v = x*mul ; mode 1: v = (eps*x + (1-eps)*y)*mul (GP interpolation, src/wgan_loss.py:377);
+// mode 2: v = x*(1 - y*y)*mul (tanh backward with y = tanh output).  eps_dev/mul_dev are device scalars (optional).
+__global__ void im2col_img_kernel(const float* __restrict__ x, const float* __restrict__ y, int mode,
+                                  const float* __restrict__ eps_dev, const float* __restrict__ mul_dev, int B, int Cimg,
+                                  int S, __nv_bfloat16* __restrict__ col, float* __restrict__ mixed_out) {
+  const int Ho = S / 2;
+  const size_t npix = static_cast<size_t>(B) * Ho * Ho;
+  const float eps = eps_dev ? __ldg(eps_dev) : 0.0f;
+  const float mul = mul_dev ? __ldg(mul_dev) : 1.0f;
+  // one thread per (pixel, kh): writes 4 taps x 4 channels = 16 bf16 = 32 bytes
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < npix * 4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int kh = static_cast<int>(i & 3);
+    const size_t pix = i >> 2;
+    const int wo = static_cast<int>(pix % Ho);
+    const int ho = static_cast<int>((pix / Ho) % Ho);
+    const int b = static_cast<int>(pix / (static_cast<size_t>(Ho) * Ho));
+    const int yy = 2 * ho - 1 + kh;
+    uint32_t packed[8];
+#pragma unroll
+    for (int kw = 0; kw < 4; ++kw) {
+      const int xx = 2 * wo - 1 + kw;
+      float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (yy >= 0 && yy < S && xx >= 0 && xx < S) {
+        for (int c = 0; c < Cimg; ++c) {
+          const size_t o = ((static_cast<size_t>(b) * Cimg + c) * S + yy) * S + xx;
+          float t = __ldg(x + o);
+          if (mode == 1) t = eps * t + (1.0f - eps) * __ldg(y + o);
+          else if (mode == 2) { const float th = __ldg(y + o); t = t * (1.0f - th * th); }
+          v[c] = t * mul;
+        }
+      }
+      packed[kw * 2] = (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16(v[1]))) << 16) |
+                       __bfloat16_as_ushort(__float2bfloat16(v[0]));
+      packed[kw * 2 + 1] = (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16(v[3]))) << 16) |
+                           __bfloat16_as_ushort(__float2bfloat16(v[2]));
+    }
+    uint4* dst = reinterpret_cast<uint4*>(col + pix * 64 + kh * 16);
+    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+  }
+  // optional: materialise the mixed image itself (fp32 NCHW) for callers that need it
+  if (mixed_out) {
+    const size_t n = static_cast<size_t>(B) * Cimg * S * S;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      float t = x[i];
+      if (mode == 1) t = eps * t + (1.0f - eps) * y[i];
+      else if (mode == 2) t = t * (1.0f - y[i] * y[i]);
+      mixed_out[i] = t * mul;
+    }
+  }
+}
+
+// per-channel sum over pixels of x (mode 0) or x*(1-y^2) (mode 2): bias gradient of the generator's last layer.
+// one block per (channel); deterministic tree.
+__global__ void img_channel_sum_kernel(const float* __restrict__ x, const float* __restrict__ y, int mode, int B,
+                                       int Cimg, int S, float* __restrict__ out, float acc) {
+  __shared__ float sm[256];
+  const int c = blockIdx.x;
+  const size_t plane = static_cast<size_t>(S) * S;
+  float s = 0.0f;
+  for (int b = 0; b < B; ++b) {
+    const size_t base = (static_cast<size_t>(b) * Cimg + c) * plane;
+    for (size_t i = threadIdx.x; i < plane; i += blockDim.x) {
+      float t = x[base + i];
+      if (mode == 2) { const float th = y[base + i]; t = t * (1.0f - th * th); }
+      s += t;
+    }
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sm[threadIdx.x] += sm[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[c] = (acc != 0.0f ? acc * out[c] : 0.0f) + sm[0];
+}
+
+// dW[p][c][kh][kw] (fp32 torch layout) (+)= dWcol[p][k = tap*4 + c]
+__global__ void unpack_edge_grad_kernel(const float* __restrict__ dcol, float* dW, int Cp, int Cimg, float acc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cp * Cimg * 16) return;
+  const int tap = i & 15, c = (i >> 4) % Cimg, p = i / (16 * Cimg);
+  dW[i] = (acc != 0.0f ? acc * dW[i] : 0.0f) + dcol[p * 64 + tap * 4 + c];
+}
+
+// critic head: a6[b] = dot(h5[b,:], w[:]); out[b] = lrelu(a6[b]).  One block per sample.
+__global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ h5, const float* __restrict__ w, int K,
+                                float slope, float* __restrict__ a6, float* __restrict__ out) {
+  __shared__ float sm[256];
+  const int b = blockIdx.x;
+  const __nv_bfloat16* x = h5 + static_cast<size_t>(b) * K;
+  float s = 0.0f;
+  for (int k = threadIdx.x * 8; k < K; k += blockDim.x * 8) {
+    const Vec8 v = ld8(x + k);
+    const Vec8 ww = ldf8(w + k);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s = fmaf(v.v[e], ww.v[e], s);
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int wd = 128; wd > 0; wd >>= 1) {
+    if (threadIdx.x < wd) sm[threadIdx.x] += sm[threadIdx.x + wd];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float a = sm[0];
+    a6[b] = a;
+    out[b] = a > 0.0f ? a : a * slope;
+  }
+}
+// da6[b] = dout[b] * lrelu'(a6[b]);  dh5[b][k] = da6[b] * w[k]
+__global__ void head_bwd_data_kernel(const float* __restrict__ a6, const float* __restrict__ dout, float dout_const,
+                                     const float* __restrict__ w, int B, int K, float slope, float* __restrict__ da6,
+                                     __nv_bfloat16* __restrict__ dh5) {
+  const size_t nvec = static_cast<size_t>(B) * (K / 8);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / (K / 8));
+    const int k = static_cast<int>(i - static_cast<size_t>(b) * (K / 8)) * 8;
+    const float go = dout ? dout[b] : dout_const;
+    const float d = a6[b] > 0.0f ? go : go * slope;
+    if (k == 0 && da6) da6[b] = d;
+    const Vec8 ww = ldf8(w + k);
+    Vec8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o.v[e] = d * ww.v[e];
+    st8(dh5 + static_cast<size_t>(b) * K + k, o);
+  }
+}
+// dw[k] (+)= sum_b da6[b] * x[b][k]   (x = h5 or the adjoint A_dh5); writes the torch layout [1][C][4][4]
+__global__ void head_wgrad_kernel(const float* __restrict__ da6, const __nv_bfloat16* __restrict__ x, int B, int K,
+                                  int C, float* dW, float acc) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.0f;
+  for (int b = 0; b < B; ++b) s = fmaf(da6[b], __bfloat162float(x[static_cast<size_t>(b) * K + k]), s);
+  const int tap = k / C, c = k - tap * C;
+  const int o = c * 16 + tap;
+  dW[o] = (acc != 0.0f ? acc * dW[o] : 0.0f) + s;
+}
+// w_head[k = tap*C + c] (fp32) = W[0][c][tap]
+__global__ void pack_head_kernel(const float* __restrict__ W, float* __restrict__ w, int C) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= 16 * C) return;
+  const int tap = k / C, c = k - tap * C;
+  w[k] = W[c * 16 + tap];
+}
+
+// WGAN losses (src/wgan_loss.py:24-29): loss_out[0] = mean(sign_a * a) + mean(sign_b * b) (b optional)
+__global__ void wgan_loss_kernel(const float* __restrict__ a, float sign_a, const float* __restrict__ b, float sign_b,
+                                 int B, float* __restrict__ loss_out) {
+  __shared__ float sm[256];
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) s += sign_a * a[i] + (b ? sign_b * b[i] : 0.0f);
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sm[threadIdx.x] += sm[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] = sm[0] / B;
+}
+
+// sum of squares of a fp32 buffer -> partial[block]; then finalize the gradient penalty:
+//   norm = sqrt(sum); P = (norm - 1)^2 (src/wgan_loss.py:43); seed scale = lambda * 2 * (norm - 1) / norm
+__global__ void sumsq_stage1_kernel(const float* __restrict__ x, size_t n, float* __restrict__ partial) {
+  __shared__ float sm[256];
+  float s = 0.0f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    s = fmaf(v, v, s);
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sm[threadIdx.x] += sm[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+__global__ void gp_finalize_kernel(const float* __restrict__ partial, int n, float lambd, float* __restrict__ out) {
+  // out[0] = penalty, out[1] = seed scale, out[2] = norm
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += static_cast<double>(partial[i]);
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sm[threadIdx.x] += sm[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float norm = sqrtf(static_cast<float>(sm[0]));
+    out[0] = (norm - 1.0f) * (norm - 1.0f);
+    out[1] = lambd * 2.0f * (norm - 1.0f) / norm;
+    out[2] = norm;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+struct AdamChunk {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int n;
+};
+// torch.optim.Adam (no amsgrad, no weight decay), src/histopathology_gan.py:252,257:
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void adam_kernel(const AdamChunk* __restrict__ chunks, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float clamp_lo, float clamp_hi, int do_clamp) {
+  const AdamChunk ch = chunks[blockIdx.x];
+  const float step = lr / bc1;
+  for (int i = threadIdx.x; i < ch.n; i += blockDim.x) {
+    const float g = ch.g[i];
+    const float m = b1 * ch.m[i] + (1.0f - b1) * g;
+    const float v = b2 * ch.v[i] + (1.0f - b2) * g * g;
+    ch.m[i] = m;
+    ch.v[i] = v;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    float p = ch.p[i] - step * (m / denom);
+    if (do_clamp) p = fminf(fmaxf(p, clamp_lo), clamp_hi);
+    ch.p[i] = p;
+  }
+}
+__global__ void clamp_kernel(float* p, size_t n, float lo, float hi) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    p[i] = fminf(fmaxf(p[i], lo), hi);
+}
+__global__ void cast_f32_kernel(const float* __restrict__ src, float* __restrict__ dst32, __nv_bfloat16* dst16, size_t n) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    if (dst32) dst32[i] = src[i];
+    if (dst16) dst16[i] = __float2bfloat16(src[i]);
+  }
+}
+__global__ void nchw_to_unit_nhwc_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int C, int S) {
+  // (x+1)/2 and NCHW -> NHWC (src/gan_utils.py:236-241)
+  const size_t n = static_cast<size_t>(B) * C * S * S;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t pix = i / C;
+    const size_t b = pix / (static_cast<size_t>(S) * S);
+    const size_t yx = pix - b * S * S;
+    out[i] = (img[(b * C + c) * S * S + yx] + 1.0f) * 0.5f;
+  }
+}
+
+}  // namespace rg
+
+using namespace rg;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+size_t rg_reduce_ws_bytes(int M, int C) { return reduce_ws_floats(M, C, 3) * sizeof(float); }
+
+int rg_bn_stats(const void* a, int M, int C, void* ws, size_t ws_bytes, float* sums, rg_stream_t st) {
+  StatsF f{static_cast<const bf16*>(a), C};
+  return run_colreduce(f, M, C, static_cast<float*>(ws), ws_bytes, sums, static_cast<cudaStream_t>(st), "rg_bn_stats");
+}
+
+int rg_bn_finalize(const float* sums, const float* gamma, const float* beta, int M, int C, float eps, float momentum,
+                   float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean, float* rstd,
+                   float* scale, float* shift, rg_stream_t st) {
+  RG_CHECK_ARG(sums && gamma && beta && mean && rstd && scale && shift && M > 0 && C > 0, "rg_bn_finalize: bad arguments");
+  const float unbias = M > 1 ? static_cast<float>(M) / static_cast<float>(M - 1) : 1.0f;
+  bn_finalize_kernel<<<ceil_div(C, 256), 256, 0, static_cast<cudaStream_t>(st)>>>(
+      sums, gamma, beta, C, 1.0f / M, unbias, eps, momentum, running_mean, running_var,
+      reinterpret_cast<long long*>(num_batches_tracked), mean, rstd, scale, shift);
+  RG_LAUNCH_CHECK("rg_bn_finalize");
+  return 0;
+}
+
+int rg_bn_act(const void* a, const float* scale, const float* shift, float slope, void* h, int M, int C,
+              rg_stream_t st) {
+  RG_CHECK_ARG(a && scale && shift && h, "rg_bn_act: null pointer");
+  BnActF f{static_cast<const bf16*>(a), static_cast<bf16*>(h), scale, shift, slope, C};
+  return run_ew(f, M, C, static_cast<cudaStream_t>(st), "rg_bn_act");
+}
+
+int rg_bn_bwd_reduce(const void* dh, const void* a, const float* mean, const float* rstd, const float* scale,
+                     const float* shift, float slope, int M, int C, void* ws, size_t ws_bytes, float* sums,
+                     rg_stream_t st) {
+  RG_CHECK_ARG(dh && a && mean && rstd && scale && shift && sums, "rg_bn_bwd_reduce: null pointer");
+  BwdReduceF f{static_cast<const bf16*>(dh), static_cast<const bf16*>(a), mean, rstd, scale, shift, slope, C};
+  return run_colreduce(f, M, C, static_cast<float*>(ws), ws_bytes, sums, static_cast<cudaStream_t>(st),
+                       "rg_bn_bwd_reduce");
+}
+
+int rg_bn_bwd_apply(const void* dh, const void* a, const void* add, const float* mean, const float* rstd,
+                    const float* scale, const float* shift, float slope, const float* sums, int M, int C, void* da,
+                    void* du_out, rg_stream_t st) {
+  RG_CHECK_ARG(dh && a && mean && rstd && scale && shift && sums && da, "rg_bn_bwd_apply: null pointer");
+  BwdApplyF f{static_cast<const bf16*>(dh), static_cast<const bf16*>(a), static_cast<const bf16*>(add),
+              static_cast<bf16*>(da), static_cast<bf16*>(du_out), mean, rstd, scale, shift, sums, slope, 1.0f / M, C};
+  return run_ew(f, M, C, static_cast<cudaStream_t>(st), "rg_bn_bwd_apply");
+}
+
+int rg_bn_param_grads(const float* sums, float* dgamma, float* dbeta, int C, float acc_gamma, float acc_beta,
+                      rg_stream_t st) {
+  RG_CHECK_ARG(sums && dgamma && dbeta && C > 0, "rg_bn_param_grads: bad arguments");
+  bn_param_grads_kernel<<<ceil_div(C, 256), 256, 0, static_cast<cudaStream_t>(st)>>>(sums, dgamma, dbeta, C, acc_gamma,
+                                                                                     acc_beta);
+  RG_LAUNCH_CHECK("rg_bn_param_grads");
+  return 0;
+}
+
+int rg_lrelu_bwd(const void* dh, const void* h, float slope, void* da, int M, int C, rg_stream_t st) {
+  RG_CHECK_ARG(dh && h && da, "rg_lrelu_bwd: null pointer");
+  LreluBwdF f{static_cast<const bf16*>(dh), static_cast<const bf16*>(h), static_cast<bf16*>(da), slope, C};
+  return run_ew(f, M, C, static_cast<cudaStream_t>(st), "rg_lrelu_bwd");
+}
+
+int rg_col_sum(const void* x, int M, int C, void* ws, size_t ws_bytes, float* tmp, float* out, float acc,
+               rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(x && tmp && out, "rg_col_sum: null pointer");
+  ColSumF f{static_cast<const bf16*>(x), C};
+  int rc = run_colreduce(f, M, C, static_cast<float*>(ws), ws_bytes, tmp, st, "rg_col_sum");
+  if (rc) return rc;
+  vec_axpby_kernel<<<ceil_div(C, 256), 256, 0, st>>>(tmp, out, C, 1.0f, acc);
+  RG_LAUNCH_CHECK("rg_col_sum");
+  return 0;
+}
+
+int rg_bn_gp_reduce(const void* ggI, const void* a, const void* gO, const float* mean, const float* rstd, int M, int C,
+                    void* ws, size_t ws_bytes, float* q, rg_stream_t st) {
+  RG_CHECK_ARG(ggI && a && gO && mean && rstd && q, "rg_bn_gp_reduce: null pointer");
+  GpReduceF f{static_cast<const bf16*>(ggI), static_cast<const bf16*>(a), static_cast<const bf16*>(gO), mean, rstd, C};
+  return run_colreduce(f, M, C, static_cast<float*>(ws), ws_bytes, q, static_cast<cudaStream_t>(st), "rg_bn_gp_reduce");
+}
+
+int rg_bn_gp_apply(const void* ggI, const void* a, const void* gO, const float* mean, const float* rstd,
+                   const float* gamma, const float* scale, const float* shift, float slope, const float* s,
+                   const float* q, int M, int C, void* A_dh, void* A_a, float* dgamma, float dgamma_acc,
+                   rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(ggI && a && gO && mean && rstd && gamma && scale && shift && s && q && A_dh && A_a,
+               "rg_bn_gp_apply: null pointer");
+  GpApplyF f{static_cast<const bf16*>(ggI), static_cast<const bf16*>(a), static_cast<const bf16*>(gO),
+             static_cast<bf16*>(A_dh), static_cast<bf16*>(A_a), mean, rstd, gamma, scale, shift, s, q, slope,
+             1.0f / M, C};
+  int rc = run_ew(f, M, C, st, "rg_bn_gp_apply");
+  if (rc) return rc;
+  if (dgamma) {
+    bn_gp_dgamma_kernel<<<ceil_div(C, 256), 256, 0, st>>>(s, q, rstd, dgamma, C, 1.0f / M, dgamma_acc);
+    RG_LAUNCH_CHECK("rg_bn_gp_apply(dgamma)");
+  }
+  return 0;
+}
+
+int rg_latent_prep(const float* noise, const float* z, int B, int E, int z_rows, void* lat_bf16, float* lat_f32,
+                   rg_stream_t st) {
+  RG_CHECK_ARG(noise && z && B > 0 && E > 0 && (z_rows == B || z_rows == 1), "rg_latent_prep: bad arguments");
+  latent_prep_kernel<<<ceil_div(E, 128), 128, 0, static_cast<cudaStream_t>(st)>>>(noise, z, B, E, z_rows,
+                                                                                  static_cast<bf16*>(lat_bf16), lat_f32);
+  RG_LAUNCH_CHECK("rg_latent_prep");
+  return 0;
+}
+
+int rg_im2col_img(const float* x, const float* y, int mode, const float* eps_dev, const float* mul_dev, int B,
+                  int Cimg, int S, void* col, float* mixed_out, rg_stream_t st) {
+  RG_CHECK_ARG(x && col && B > 0 && Cimg >= 1 && Cimg <= 4 && S >= 2 && S % 2 == 0, "rg_im2col_img: bad arguments");
+  RG_CHECK_ARG(mode == 0 || y, "rg_im2col_img: mode %d needs a second image", mode);
+  const size_t work = static_cast<size_t>(B) * (S / 2) * (S / 2) * 4;
+  const int grid = static_cast<int>(std::min<size_t>((work + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  im2col_img_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(x, y, mode, eps_dev, mul_dev, B, Cimg, S,
+                                                                     static_cast<bf16*>(col), mixed_out);
+  RG_LAUNCH_CHECK("rg_im2col_img");
+  return 0;
+}
+
+int rg_img_channel_sum(const float* x, const float* y, int mode, int B, int Cimg, int S, float* out, float acc,
+                       rg_stream_t st) {
+  RG_CHECK_ARG(x && out && (mode == 0 || y), "rg_img_channel_sum: bad arguments");
+  img_channel_sum_kernel<<<Cimg, 256, 0, static_cast<cudaStream_t>(st)>>>(x, y, mode, B, Cimg, S, out, acc);
+  RG_LAUNCH_CHECK("rg_img_channel_sum");
+  return 0;
+}
+
+int rg_unpack_edge_grad(const float* dcol, float* dW, int Cp, int Cimg, float acc, rg_stream_t st) {
+  RG_CHECK_ARG(dcol && dW && Cimg >= 1 && Cimg <= 4, "rg_unpack_edge_grad: bad arguments");
+  unpack_edge_grad_kernel<<<ceil_div(Cp * Cimg * 16, 256), 256, 0, static_cast<cudaStream_t>(st)>>>(dcol, dW, Cp,
+                                                                                                    Cimg, acc);
+  RG_LAUNCH_CHECK("rg_unpack_edge_grad");
+  return 0;
+}
+
+int rg_pack_head(const float* W, float* w_head, int C, rg_stream_t st) {
+  RG_CHECK_ARG(W && w_head && C > 0, "rg_pack_head: bad arguments");
+  pack_head_kernel<<<ceil_div(16 * C, 256), 256, 0, static_cast<cudaStream_t>(st)>>>(W, w_head, C);
+  RG_LAUNCH_CHECK("rg_pack_head");
+  return 0;
+}
+
+int rg_head_fwd(const void* h5, const float* w_head, int B, int K, float slope, float* a6, float* out,
+                rg_stream_t st) {
+  RG_CHECK_ARG(h5 && w_head && a6 && out && K % 8 == 0, "rg_head_fwd: bad arguments");
+  head_fwd_kernel<<<B, 256, 0, static_cast<cudaStream_t>(st)>>>(static_cast<const bf16*>(h5), w_head, K, slope, a6,
+                                                               out);
+  RG_LAUNCH_CHECK("rg_head_fwd");
+  return 0;
+}
+
+int rg_head_bwd_data(const float* a6, const float* dout, float dout_const, const float* w_head, int B, int K,
+                     float slope, float* da6, void* dh5, rg_stream_t st) {
+  RG_CHECK_ARG(a6 && w_head && dh5 && K % 8 == 0, "rg_head_bwd_data: bad arguments");
+  const size_t nvec = static_cast<size_t>(B) * (K / 8);
+  const int grid = static_cast<int>(std::min<size_t>((nvec + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  head_bwd_data_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(a6, dout, dout_const, w_head, B, K, slope,
+                                                                        da6, static_cast<bf16*>(dh5));
+  RG_LAUNCH_CHECK("rg_head_bwd_data");
+  return 0;
+}
+
+int rg_head_wgrad(const float* da6, const void* x, int B, int K, int C, float* dW, float acc, rg_stream_t st) {
+  RG_CHECK_ARG(da6 && x && dW && K == 16 * C, "rg_head_wgrad: bad arguments");
+  head_wgrad_kernel<<<ceil_div(K, 256), 256, 0, static_cast<cudaStream_t>(st)>>>(da6, static_cast<const bf16*>(x), B,
+                                                                                 K, C, dW, acc);
+  RG_LAUNCH_CHECK("rg_head_wgrad");
+  return 0;
+}
+
+int rg_wgan_loss(const float* a, float sign_a, const float* b, float sign_b, int B, float* loss_out, rg_stream_t st) {
+  RG_CHECK_ARG(a && loss_out && B > 0, "rg_wgan_loss: bad arguments");
+  wgan_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(st)>>>(a, sign_a, b, sign_b, B, loss_out);
+  RG_LAUNCH_CHECK("rg_wgan_loss");
+  return 0;
+}
+
+int rg_gp_norm(const float* g, size_t n, float lambd, float* partial_ws, int partial_len, float* out3,
+               rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(g && partial_ws && out3 && partial_len >= 1, "rg_gp_norm: bad arguments");
+  const int blocks = static_cast<int>(std::min<size_t>(static_cast<size_t>(partial_len), (n + 255) / 256));
+  sumsq_stage1_kernel<<<blocks, 256, 0, st>>>(g, n, partial_ws);
+  RG_LAUNCH_CHECK("rg_gp_norm(stage1)");
+  gp_finalize_kernel<<<1, 256, 0, st>>>(partial_ws, blocks, lambd, out3);
+  RG_LAUNCH_CHECK("rg_gp_norm(finalize)");
+  return 0;
+}
+
+int rg_adam_table_bytes(int num_chunks) { return static_cast<int>(sizeof(AdamChunk)) * num_chunks; }
+
+// chunks_host: arrays of num_tensors pointers / sizes; table_dev: device buffer for the chunk table (filled here with
+// a synchronous-with-stream async copy from the caller's pinned or pageable host staging buffer table_host).
+int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms, void* const* vs, const int64_t* sizes,
+                        int num_tensors, int chunk_elems, void* table_host, int max_chunks) {
+  RG_CHECK_ARG(params && grads && ms && vs && sizes && table_host && chunk_elems > 0, "rg_adam_build_table: bad arguments");
+  AdamChunk* t = static_cast<AdamChunk*>(table_host);
+  int n = 0;
+  for (int i = 0; i < num_tensors; ++i) {
+    for (int64_t off = 0; off < sizes[i]; off += chunk_elems) {
+      if (n >= max_chunks) {
+        set_error("rg_adam_build_table: table too small (%d chunks)", max_chunks);
+        return RG_EWORKSPACE;
+      }
+      t[n].p = static_cast<float*>(params[i]) + off;
+      t[n].g = static_cast<const float*>(grads[i]) + off;
+      t[n].m = static_cast<float*>(ms[i]) + off;
+      t[n].v = static_cast<float*>(vs[i]) + off;
+      t[n].n = static_cast<int>(std::min<int64_t>(chunk_elems, sizes[i] - off));
+      ++n;
+    }
+  }
+  return n;   // number of chunks (>= 0)
+}
+
+int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, float beta2, float eps, int step,
+                 int do_clamp, float clamp_lo, float clamp_hi, rg_stream_t st) {
+  RG_CHECK_ARG(table_dev && num_chunks > 0 && step >= 1, "rg_adam_step: bad arguments");
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  adam_kernel<<<num_chunks, 256, 0, static_cast<cudaStream_t>(st)>>>(static_cast<const AdamChunk*>(table_dev), lr, beta1,
+                                                                     beta2, eps, bc1, sqrtf(bc2), clamp_lo, clamp_hi,
+                                                                     do_clamp);
+  RG_LAUNCH_CHECK("rg_adam_step");
+  return 0;
+}
+
+int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st) {
+  RG_CHECK_ARG(p && n > 0, "rg_clamp: bad arguments");
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  clamp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(p, n, lo, hi);
+  RG_LAUNCH_CHECK("rg_clamp");
+  return 0;
+}
+
+int rg_tiles_to_unit_nhwc(const float* img, float* out, int B, int C, int S, rg_stream_t st) {
+  RG_CHECK_ARG(img && out && B > 0, "rg_tiles_to_unit_nhwc: bad arguments");
+  const size_t n = static_cast<size_t>(B) * C * S * S;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  nchw_to_unit_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(img, out, B, C, S);
+  RG_LAUNCH_CHECK("rg_tiles_to_unit_nhwc");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+"""Drop-in DCGAN modules for the RNA-GAN hot path, running on the sm_100a kernels.
+
+Same constructor keywords, attributes (``encoding_dims``, ``label_type``, ``sampler``, ``model`` / ``disc``) and
+``state_dict`` keys / shapes / dtypes as
+
+  * torchgan==0.1.0 ``DCGANGenerator`` / ``DCGANDiscriminator`` -- the classes the reference actually instantiates
+    (src/histopathology_gan.py:176-192, src/gan_utils.py:255-271); structure per SURVEY.md Appendix A/D, and
+  * the reference's own ``DCGANUpGenerator`` (src/dcgan.py:8-99).
+
+The ``nn`` layers inside ``self.model`` are PARAMETER CONTAINERS (fp32 masters, checkpoint layout); ``forward`` never
+calls them -- it runs rnagan_b200.engine on the CUDA kernels and raises when the module is not on a B200.
+Training goes through the loss objects' ``train_ops`` (rnagan_b200.wgan_loss), which drive the same engines with a
+hand-scheduled backward; autograd through ``forward`` is not provided.
+"""
+from math import ceil, log2
+
+import torch
+import torch.nn as nn
+
+from . import engine as _engine
+from . import ops as _ops
+
+
+class Generator(nn.Module):
+    """torchgan.models.Generator contract [SURVEY.md Appendix A]."""
+
+    def __init__(self, encoding_dims, label_type="none"):
+        super().__init__()
+        self.encoding_dims = encoding_dims
+        self.label_type = label_type
+
+    def _weight_initializer(self):
+        for m in self.modules():
+            if isinstance(m, nn.ConvTranspose2d):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0.0)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1.0)
+                nn.init.constant_(m.bias, 0.0)
+            elif isinstance(m, nn.Linear):
+                nn.init.kaiming_normal_(m.weight)
+                nn.init.constant_(m.bias, 0.0)
+
+    def sampler(self, sample_size, device):
+        return [torch.randn(sample_size, self.encoding_dims, device=device)]
+
+
+class Discriminator(nn.Module):
+    """torchgan.models.Discriminator contract [SURVEY.md Appendix A]."""
+
+    def __init__(self, input_dims, label_type="none"):
+        super().__init__()
+        self.input_dims = input_dims
+        self.label_type = label_type
+
+    def _weight_initializer(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0.0)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1.0)
+                nn.init.constant_(m.bias, 0.0)
+            elif isinstance(m, nn.Linear):
+                nn.init.kaiming_normal_(m.weight)
+                nn.init.constant_(m.bias, 0.0)
+
+
+def _repeats(size, what):
+    if size < 16 or ceil(log2(size)) != log2(size):
+        raise Exception(f"{what} Image Size must be at least 16*16 and an exact power of 2")
+    return size.bit_length() - 4
+
+
+class _EngineMixin:
+    """Lazy engine construction + re-packing of the bf16 operands when the fp32 masters changed under us."""
+
+    _engine_cls = None
+
+    def _engine(self):
+        eng = self.__dict__.get("_rg_engine")
+        p0 = next(self.parameters())
+        if p0.device.type != "cuda":
+            raise RuntimeError(f"{type(self).__name__} runs only on a CUDA (sm_100a) device: there is no CPU fallback; "
+                               "move the module with .to('cuda') first")
+        if eng is None or eng.device != p0.device:
+            eng = self._engine_cls(self)
+            self.__dict__["_rg_engine"] = eng
+            self.__dict__["_rg_versions"] = self._versions()
+        elif self._versions() != self.__dict__["_rg_versions"]:
+            eng.pack()
+            self.__dict__["_rg_versions"] = self._versions()
+        return eng
+
+    def _versions(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _apply(self, fn, *args, **kwargs):   # .to()/.cuda()/.float(): storage moves invalidate the engine
+        self.__dict__.pop("_rg_engine", None)
+        return super()._apply(fn, *args, **kwargs)
+
+
+class DCGANGenerator(_EngineMixin, Generator):
+    r"""Transposed-convolution DCGAN generator (torchgan DCGANGenerator; the ConvTranspose2d lines the reference keeps
+    as comments at src/dcgan.py:52,82)."""
+
+    _engine_cls = _engine.GeneratorEngine
+
+    def __init__(self, encoding_dims=100, out_size=32, out_channels=3, step_channels=64, batchnorm=True,
+                 nonlinearity=None, last_nonlinearity=None, label_type="none"):
+        super().__init__(encoding_dims, label_type)
+        reps = _repeats(out_size, "Target")
+        self.ch = out_channels
+        self.n = step_channels
+        act = nn.LeakyReLU(0.2) if nonlinearity is None else nonlinearity
+        last = nn.Tanh() if last_nonlinearity is None else last_nonlinearity
+        d = int(self.n * (2 ** reps))
+        layers = []
+        cin, stride, pad = self.encoding_dims, 1, 0
+        for _ in range(reps + 1):
+            blk = [nn.ConvTranspose2d(cin, d, 4, stride, pad, bias=not batchnorm)]
+            if batchnorm:
+                blk.append(nn.BatchNorm2d(d))
+            blk.append(act)
+            layers.append(nn.Sequential(*blk))
+            cin, d, stride, pad = d, d // 2, 2, 1
+        layers.append(nn.Sequential(nn.ConvTranspose2d(cin, self.ch, 4, 2, 1, bias=True), last))
+        self.model = nn.Sequential(*layers)
+        self._weight_initializer()
+
+    @torch.no_grad()
+    def forward(self, x, feature_matching=False):
+        """x: [B, encoding_dims] -> [B, out_channels, S, S] fp32 NCHW (batch statistics in train mode)."""
+        eng = self._engine()
+        x = x.view(-1, x.size(1)).to(device=eng.device, dtype=torch.float32).contiguous()
+        lat = _ops.cast_pad_bf16(x, x.size(1))
+        return eng.forward(lat, tag="module", training=self.training).clone()
+
+
+class DCGANDiscriminator(_EngineMixin, Discriminator):
+    r"""DCGAN critic (torchgan DCGANDiscriminator; ctor args at src/histopathology_gan.py:186-192)."""
+
+    _engine_cls = _engine.CriticEngine
+
+    def __init__(self, in_size=32, in_channels=3, step_channels=64, batchnorm=True, nonlinearity=None,
+                 last_nonlinearity=None, label_type="none"):
+        super().__init__(in_channels, label_type)
+        reps = _repeats(in_size, "Input")
+        self.n = step_channels
+        act = nn.LeakyReLU(0.2) if nonlinearity is None else nonlinearity
+        last = nn.LeakyReLU(0.2) if last_nonlinearity is None else last_nonlinearity
+        d = self.n
+        layers = [nn.Sequential(nn.Conv2d(self.input_dims, d, 4, 2, 1, bias=True), act)]
+        for _ in range(reps):
+            blk = [nn.Conv2d(d, d * 2, 4, 2, 1, bias=not batchnorm)]
+            if batchnorm:
+                blk.append(nn.BatchNorm2d(d * 2))
+            blk.append(act)
+            layers.append(nn.Sequential(*blk))
+            d *= 2
+        self.disc = nn.Sequential(nn.Conv2d(d, 1, 4, 1, 0, bias=not batchnorm), last)
+        self.model = nn.Sequential(*layers)
+        self._weight_initializer()
+
+    @torch.no_grad()
+    def forward(self, x, feature_matching=False):
+        """x: [B, C, S, S] fp32 NCHW -> critic score [B] (or the last feature map when feature_matching)."""
+        eng = self._engine()
+        x = x.to(device=eng.device, dtype=torch.float32).contiguous()
+        out = eng.forward(x, tag="module", training=self.training)
+        if feature_matching:
+            B = x.shape[0]
+            feat = eng.bufs.get(f"module.h{eng.n}", (B, 4, 4, eng.Cn))
+            return feat.float().permute(0, 3, 1, 2).contiguous()
+        return out.clone()
+
+
+class DCGANUpGenerator(Generator):
+    """Resize-convolution generator of src/dcgan.py:8-99 (bilinear x2 -> ReflectionPad2d(1) -> Conv2d 3x3; no Tanh).
+
+    Parameter layout / state_dict keys match the reference.  It is imported but never instantiated by the reference's
+    drivers (src/histopathology_gan.py:24,176); its kernel schedule is not built yet, so ``forward`` fails loudly
+    instead of silently running a non-native path."""
+
+    def __init__(self, encoding_dims=100, out_size=32, out_channels=3, step_channels=64, batchnorm=True,
+                 nonlinearity=None, last_nonlinearity=None, label_type="none"):
+        super().__init__(encoding_dims, label_type)
+        reps = _repeats(out_size, "Target")
+        self.ch = out_channels
+        self.n = step_channels
+        act = nn.LeakyReLU(0.2) if nonlinearity is None else nonlinearity
+        d = int(self.n * (2 ** reps))
+        first = [nn.ConvTranspose2d(self.encoding_dims, d, 4, 1, 0, bias=not batchnorm)]
+        if batchnorm:
+            first.append(nn.BatchNorm2d(d))
+        layers = [nn.Sequential(*first, act)]
+        for _ in range(reps):
+            if batchnorm:
+                layers.append(nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear"), nn.ReflectionPad2d(1),
+                                            nn.Conv2d(d, d // 2, kernel_size=3, stride=1, padding=0),
+                                            nn.BatchNorm2d(d // 2), act))
+            else:
+                layers.append(nn.Sequential(nn.ConvTranspose2d(d, d // 2, 4, 2, 1, bias=True), act))
+            d //= 2
+        layers.append(nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear"), nn.ReflectionPad2d(1),
+                                    nn.Conv2d(d, self.ch, kernel_size=3, stride=1, padding=0)))
+        self.model = nn.Sequential(*layers)
+        self._weight_initializer()
+
+    def forward(self, x, feature_matching=False):
+        raise NotImplementedError("DCGANUpGenerator: the resize-conv kernel schedule (SURVEY.md K5) is not built in "
+                                  "this round; use DCGANGenerator (what the reference drivers instantiate)")

@@ -1,0 +1,470 @@
+"""Hand-scheduled forward / backward / double-backward of the DCGAN generator and critic on the C-ABI kernels.
+
+This replaces what the reference gets from ATen + autograd inside the three ``train_ops``
+(src/wgan_loss.py:82-129, 181-263, 314-389) with explicit sequences of kernels:
+
+  generator  G.0  ConvTranspose2d(E,C0,4,1,0)      -> rg_gemm_nt (projection)            + BN + LeakyReLU
+             G.l  ConvTranspose2d(d,d/2,4,2,1)     -> rg_conv_up                         + BN + LeakyReLU
+             G.n  ConvTranspose2d(64,3,4,2,1)+Tanh -> rg_conv_up_img (bias+tanh epilogue)
+  critic     D.0  Conv2d(3,64,4,2,1)+LeakyReLU     -> rg_im2col_img + rg_gemm_nt (bias+LeakyReLU epilogue)
+             D.l  Conv2d(d,2d,4,2,1)               -> rg_conv_down                       + BN + LeakyReLU
+             disc Conv2d(C,1,4,1,0)+LeakyReLU      -> rg_head_fwd
+
+Backward uses the same engine with the roles swapped (dgrad of a conv is the transposed form and vice versa,
+wgrad is rg_conv_wgrad); the gradient penalty's double backward follows SURVEY.md Appendix C and is checked
+against autograd in tests/test_gp_math_cpu.py.  Activations are bf16 NHWC, parameters/gradients/statistics fp32.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+SLOPE = 0.2
+
+
+def _grad_of(p):
+    if p.grad is None or p.grad.dtype != F32 or not p.grad.is_contiguous():
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+class _Bufs:
+    """Named, shape-keyed device buffers reused across steps (static addresses: CUDA-graph friendly)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._d = {}
+
+    def get(self, name, shape, dtype=BF16, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self._d.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
+            self._d[key] = t
+        return t
+
+
+class _BNState:
+    """Per-pass statistics of one BatchNorm layer (a critic step holds two passes -- real and fake -- at once)."""
+
+    def __init__(self, C, device):
+        f = lambda *s: torch.zeros(*s, dtype=F32, device=device)
+        self.sums, self.bsums, self.q = f(2, C), f(2, C), f(3, C)
+        self.mean, self.rstd, self.scale, self.shift = f(C), f(C), f(C), f(C)
+
+
+class _BN:
+    """One BatchNorm2d layer: parameter references + per-channel work vectors keyed by pass tag."""
+
+    def __init__(self, mod, device):
+        self.mod = mod
+        self.C = mod.num_features
+        self.device = device
+        self._states = {}
+
+    def st(self, tag):
+        s = self._states.get(tag)
+        if s is None:
+            s = _BNState(self.C, self.device)
+            self._states[tag] = s
+        return s
+
+    def forward(self, a, h, M, training=True, tag=""):
+        m, s = self.mod, self.st(tag)
+        if training:
+            ops.bn_stats(a, M, self.C, s.sums)
+            ops.bn_finalize(s.sums, m.weight, m.bias, M, self.C, m.eps, m.momentum, m.running_mean, m.running_var,
+                            m.num_batches_tracked, s.mean, s.rstd, s.scale, s.shift)
+        else:   # eval: running statistics (torchgan Trainer samples in eval mode at epoch end)
+            with torch.no_grad():
+                s.mean.copy_(m.running_mean)
+                s.rstd.copy_((m.running_var + m.eps).rsqrt())
+                s.scale.copy_(m.weight * s.rstd)
+                s.shift.copy_(m.bias - s.mean * s.scale)
+        ops.bn_act(a, s.scale, s.shift, SLOPE, h, M, self.C)
+
+    def backward(self, dh, a, da, M, param_grads=False, acc_gamma=0.0, acc_beta=0.0, add=None, du_out=None, tag=""):
+        """da = d(loss)/d(a) from dh = d(loss)/d(h); optionally (accumulating) gamma/beta gradients."""
+        s = self.st(tag)
+        ops.bn_bwd_reduce(dh, a, s.mean, s.rstd, s.scale, s.shift, SLOPE, M, self.C, s.bsums)
+        if param_grads:
+            ops.bn_param_grads(s.bsums, _grad_of(self.mod.weight), _grad_of(self.mod.bias), self.C, acc_gamma,
+                               acc_beta)
+        ops.bn_bwd_apply(dh, a, add, s.mean, s.rstd, s.scale, s.shift, SLOPE, s.bsums, M, self.C, da, du_out)
+
+
+def _check_act(mod, slope, what):
+    if not isinstance(mod, nn.LeakyReLU) or abs(mod.negative_slope - slope) > 1e-12:
+        raise NotImplementedError(f"{what}: only LeakyReLU({slope}) is implemented on the sm_100a path (got {mod!r})")
+
+
+# ====================================================================================================== generator
+class GeneratorEngine:
+    """Kernel schedule for torchgan-style DCGANGenerator (batchnorm=True, LeakyReLU(0.2), Tanh)."""
+
+    def __init__(self, module):
+        blocks = list(module.model)
+        self.module = module
+        dev = next(module.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GeneratorEngine needs the module on a CUDA device (there is no CPU path)")
+        self.device = dev
+        self.bufs = _Bufs(dev)
+        first = blocks[0]
+        if len(first) != 3 or not isinstance(first[1], nn.BatchNorm2d):
+            raise NotImplementedError("generator without BatchNorm is not implemented on the sm_100a path")
+        self.conv0, self.bn0 = first[0], _BN(first[1], dev)
+        _check_act(first[2], SLOPE, "generator")
+        self.E, self.C0 = self.conv0.weight.shape[0], self.conv0.weight.shape[1]
+        self.convs, self.bns = [], []
+        for blk in blocks[1:-1]:
+            if len(blk) != 3 or not isinstance(blk[0], nn.ConvTranspose2d) or not isinstance(blk[1], nn.BatchNorm2d):
+                raise NotImplementedError("unexpected generator block layout")
+            _check_act(blk[2], SLOPE, "generator")
+            self.convs.append(blk[0])
+            self.bns.append(_BN(blk[1], dev))
+        last = blocks[-1]
+        self.conv_last = last[0]
+        if not isinstance(last[1], nn.Tanh):
+            raise NotImplementedError("generator last_nonlinearity must be Tanh on the sm_100a path")
+        self.Cimg = self.conv_last.weight.shape[1]
+        self.Cn = self.conv_last.weight.shape[0]
+        if self.E % 64 or self.C0 % 64 or self.Cn % 64:
+            raise NotImplementedError("channel counts must be multiples of 64 on the sm_100a path")
+        self.n = len(self.convs)
+        self.size = 4 * (2 ** (self.n + 1))
+        # packed bf16 operands (derived, non-persistent)
+        self.w_proj = torch.empty(16 * self.C0, self.E, dtype=BF16, device=dev)
+        self.w_up, self.w_down = [], []
+        for c in self.convs:
+            Cp, Cs = c.weight.shape[0], c.weight.shape[1]
+            self.w_up.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev))
+            self.w_down.append(torch.empty(Cp, 16 * Cs, dtype=BF16, device=dev))
+        self.w_up_last = torch.zeros(4, 16, 4 * self.Cn, dtype=BF16, device=dev)
+        self.w_col_last = torch.empty(self.Cn, 64, dtype=BF16, device=dev)
+        self.pack()
+
+    def pack(self):
+        """Refresh the bf16 operand copies from the fp32 master weights (after load_state_dict / optimizer step)."""
+        ops.pack_proj(self.conv0.weight.detach(), self.w_proj)
+        for c, wu, wd in zip(self.convs, self.w_up, self.w_down):
+            ops.pack_link(c.weight.detach(), wd, wu)
+        ops.pack_link(self.conv_last.weight.detach(), None, self.w_up_last, want_down=False)
+        ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
+
+    def forward(self, lat, tag="g", training=True, out=None):
+        """lat: bf16 [B, E] -> fp32 NCHW image [B, Cimg, S, S]; keeps activations under `tag` for backward."""
+        B = lat.shape[0]
+        g = self.bufs.get
+        a = g(f"{tag}.a0", (B, 4, 4, self.C0))
+        h = g(f"{tag}.h0", (B, 4, 4, self.C0))
+        ops.gemm_nt(lat, self.w_proj, out=a.view(B, 16 * self.C0))
+        self.bn0.forward(a, h, B * 16, training, tag=tag)
+        H = 4
+        for l, (c, bn) in enumerate(zip(self.convs, self.bns), start=1):
+            Cs = c.weight.shape[1]
+            a = g(f"{tag}.a{l}", (B, 2 * H, 2 * H, Cs))
+            ops.conv_up(h, self.w_up[l - 1], Cs, out=a)
+            H *= 2
+            h = g(f"{tag}.h{l}", (B, H, H, Cs))
+            bn.forward(a, h, B * H * H, training, tag=tag)
+        if out is None:
+            out = g(f"{tag}.img", (B, self.Cimg, 2 * H, 2 * H), F32)
+        ops.conv_up_img(h, self.w_up_last, self.Cimg, bias=self.conv_last.bias.detach(), act_tanh=True, out=out)
+        return out
+
+    def backward(self, lat, d_img, img, tag="g"):
+        """Parameter gradients of the generator from d_img = dL/d(image) (fp32 NCHW); writes .grad (overwrites)."""
+        B = lat.shape[0]
+        g = self.bufs.get
+        n = self.n
+        H = self.size // 2
+        npix = B * H * H
+        col = g("bwd.col", (npix, 64))
+        ops.im2col_img(d_img, col, y=img, mode=2)                       # d(pre-tanh) in im2col form
+        ops.img_channel_sum(d_img, _grad_of(self.conv_last.bias), y=img, mode=2, acc=0.0)
+        hn = g(f"{tag}.h{n}", (B, H, H, self.Cn))
+        dcol = g("bwd.dcol", (self.Cn, 64), F32)
+        ops.gemm_tn(hn.view(npix, self.Cn), col, out=dcol)
+        ops.unpack_edge_grad(dcol, _grad_of(self.conv_last.weight), acc=0.0)
+        dh = g(f"bwd.dh{n}", (B, H, H, self.Cn))
+        ops.gemm_nt(col, self.w_col_last, out=dh.view(npix, self.Cn))
+        for l in range(n, 0, -1):
+            c, bn = self.convs[l - 1], self.bns[l - 1]
+            Cp, Cs = c.weight.shape[0], c.weight.shape[1]
+            a = g(f"{tag}.a{l}", (B, H, H, Cs))
+            da = g(f"bwd.da{l}", (B, H, H, Cs))
+            bn.backward(dh, a, da, B * H * H, param_grads=True, tag=tag)
+            H //= 2
+            hprev = g(f"{tag}.h{l - 1}", (B, H, H, Cp))
+            ops.conv_wgrad(hprev, da, _grad_of(c.weight))
+            dh = g(f"bwd.dh{l - 1}", (B, H, H, Cp))
+            ops.conv_down(da, self.w_down[l - 1], out=dh)
+        a0 = g(f"{tag}.a0", (B, 4, 4, self.C0))
+        da0 = g("bwd.da0", (B, 4, 4, self.C0))
+        self.bn0.backward(dh, a0, da0, B * 16, param_grads=True, tag=tag)
+        ops.proj_wgrad(lat, da0, _grad_of(self.conv0.weight))
+
+
+# ====================================================================================================== critic
+class CriticEngine:
+    """Kernel schedule for torchgan-style DCGANDiscriminator (batchnorm=True, LeakyReLU(0.2) everywhere)."""
+
+    def __init__(self, module):
+        blocks = list(module.model)
+        self.module = module
+        dev = next(module.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("CriticEngine needs the module on a CUDA device (there is no CPU path)")
+        self.device = dev
+        self.bufs = _Bufs(dev)
+        first = blocks[0]
+        self.conv0 = first[0]
+        _check_act(first[1], SLOPE, "critic")
+        self.Cimg, self.C0 = self.conv0.weight.shape[1], self.conv0.weight.shape[0]
+        if self.Cimg > 4:
+            raise NotImplementedError("critic input with more than 4 channels is not implemented")
+        self.convs, self.bns = [], []
+        for blk in blocks[1:]:
+            if len(blk) != 3 or not isinstance(blk[1], nn.BatchNorm2d):
+                raise NotImplementedError("critic without BatchNorm is not implemented on the sm_100a path")
+            _check_act(blk[2], SLOPE, "critic")
+            self.convs.append(blk[0])
+            self.bns.append(_BN(blk[1], dev))
+        self.head = module.disc[0]
+        _check_act(module.disc[1], SLOPE, "critic head")
+        if self.head.bias is not None:
+            raise NotImplementedError("critic head with bias is not implemented")
+        self.n = len(self.convs)
+        self.Cn = self.head.weight.shape[1]
+        self.size = 4 * (2 ** (self.n + 1))
+        if self.C0 % 64:
+            raise NotImplementedError("channel counts must be multiples of 64 on the sm_100a path")
+        self.w_col0 = torch.empty(self.C0, 64, dtype=BF16, device=dev)
+        self.w_up0 = torch.zeros(4, 16, 4 * self.C0, dtype=BF16, device=dev)
+        self.w_down, self.w_up = [], []
+        for c in self.convs:
+            Cp, Cs = c.weight.shape[0], c.weight.shape[1]
+            self.w_down.append(torch.empty(Cp, 16 * Cs, dtype=BF16, device=dev))
+            self.w_up.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev))
+        self.w_head = torch.empty(16 * self.Cn, dtype=F32, device=dev)
+        self.tmpC = torch.zeros(max([self.C0] + [c.weight.shape[0] for c in self.convs]), dtype=F32, device=dev)
+        self.gp_partial = torch.zeros(1024, dtype=F32, device=dev)
+        self.gp_out = torch.zeros(3, dtype=F32, device=dev)
+        self.pack()
+
+    def pack(self):
+        ops.pack_edge(self.conv0.weight.detach(), self.w_col0)
+        ops.pack_link(self.conv0.weight.detach(), None, self.w_up0, want_down=False)
+        for c, wd, wu in zip(self.convs, self.w_down, self.w_up):
+            ops.pack_link(c.weight.detach(), wd, wu)
+        ops.pack_head(self.head.weight.detach(), self.w_head)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x=None, tag="d", training=True, col=None):
+        """x: fp32 NCHW image [B, Cimg, S, S] (or a prebuilt im2col `col`) -> critic output fp32 [B]."""
+        g = self.bufs.get
+        S = self.size
+        B = x.shape[0] if x is not None else col.shape[0] // ((S // 2) ** 2)
+        H = S // 2
+        npix = B * H * H
+        if col is None:
+            col = g(f"{tag}.col", (npix, 64))
+            ops.im2col_img(x, col)
+        h = g(f"{tag}.h0", (B, H, H, self.C0))
+        ops.gemm_nt(col, self.w_col0, out=h.view(npix, self.C0), col_shift=self.conv0.bias.detach(), slope=SLOPE)
+        for l, (c, bn) in enumerate(zip(self.convs, self.bns), start=1):
+            Cp = c.weight.shape[0]
+            H //= 2
+            a = g(f"{tag}.a{l}", (B, H, H, Cp))
+            ops.conv_down(h, self.w_down[l - 1], out=a)
+            h = g(f"{tag}.h{l}", (B, H, H, Cp))
+            bn.forward(a, h, B * H * H, training, tag=tag)
+        a6 = g(f"{tag}.a6", (B,), F32)
+        out = g(f"{tag}.out", (B,), F32)
+        ops.head_fwd(h, self.w_head, B, 16 * self.Cn, SLOPE, a6, out)
+        return out
+
+    # ------------------------------------------------------------------ first-order backward
+    def backward(self, B, dout_const, tag="d", params=False, acc=0.0, want_dimg=False, keep_du=False):
+        """Backward of sum_b dout_const * out[b] through the pass saved under `tag`.
+
+        params: also produce parameter gradients (acc=1.0 accumulates onto existing .grad).
+        want_dimg: return dL/d(image) as fp32 NCHW.   keep_du: keep per-layer du / da (gradient-penalty step 2).
+        """
+        g = self.bufs.get
+        n = self.n
+        H = 4
+        hn = g(f"{tag}.h{n}", (B, H, H, self.Cn))
+        a6 = g(f"{tag}.a6", (B,), F32)
+        da6 = g(f"{tag}.da6", (B,), F32)
+        dh = g(f"{tag}.dh{n}", (B, H, H, self.Cn))
+        ops.head_bwd_data(a6, dout_const, self.w_head, B, 16 * self.Cn, SLOPE, da6, dh)
+        if params:
+            ops.head_wgrad(da6, hn, B, 16 * self.Cn, self.Cn, _grad_of(self.head.weight), acc)
+        for l in range(n, 0, -1):
+            c, bn = self.convs[l - 1], self.bns[l - 1]
+            Cp, Cs = c.weight.shape[0], c.weight.shape[1]
+            a = g(f"{tag}.a{l}", (B, H, H, Cp))
+            da = g(f"{tag}.da{l}", (B, H, H, Cp))
+            du = g(f"{tag}.du{l}", (B, H, H, Cp)) if keep_du else None
+            bn.backward(dh, a, da, B * H * H, param_grads=params, acc_gamma=acc, acc_beta=acc, du_out=du, tag=tag)
+            hprev = g(f"{tag}.h{l - 1}", (B, 2 * H, 2 * H, Cs))
+            if params:
+                ops.conv_wgrad(da, hprev, _grad_of(c.weight), beta=acc)
+            H *= 2
+            dh = g(f"{tag}.dh{l - 1}", (B, H, H, Cs))
+            ops.conv_up(da, self.w_up[l - 1], Cs, out=dh)
+        h0 = g(f"{tag}.h0", (B, H, H, self.C0))
+        da0 = g(f"{tag}.da0", (B, H, H, self.C0))
+        npix = B * H * H
+        ops.lrelu_bwd(dh, h0, SLOPE, da0, npix, self.C0)
+        if params:
+            ops.col_sum(da0, npix, self.C0, self.tmpC, _grad_of(self.conv0.bias), acc)
+            col = g(f"{tag}.col", (npix, 64))
+            dcol = g("bwd.dcol", (self.C0, 64), F32)
+            ops.gemm_tn(da0.view(npix, self.C0), col, out=dcol)
+            ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=acc)
+        if want_dimg:
+            dimg = g(f"{tag}.dimg", (B, self.Cimg, 2 * H, 2 * H), F32)
+            ops.conv_up_img(da0, self.w_up0, self.Cimg, out=dimg)
+            return dimg
+        return None
+
+    # ------------------------------------------------------------------ gradient penalty
+    def gradient_penalty(self, real, fake, eps_dev, lambd=10.0, tag="gp"):
+        """WassersteinGradientPenaltyVAE core (src/wgan_loss.py:32-44, 376-388): writes d(lambda*P)/d(theta_D)
+        into .grad (overwriting) and returns the device tensor [P, seed, ||g||]."""
+        g = self.bufs.get
+        n = self.n
+        S = self.size
+        B = real.shape[0]
+        H0 = S // 2
+        npix0 = B * H0 * H0
+        # step 1: forward on x_hat = eps*real + (1-eps)*fake (train-mode BN, running stats updated)
+        col_x = g(f"{tag}.col", (npix0, 64))
+        ops.im2col_img(real, col_x, y=fake, mode=1, eps_dev=eps_dev)
+        self.forward(tag=tag, col=col_x)
+        # step 2: g = d(sum out)/d(x_hat), keeping du_l, da_l and the BN backward sums
+        grad_x = self.backward(B, 1.0, tag=tag, params=False, want_dimg=True, keep_du=True)
+        ops.gp_norm(grad_x, lambd, self.gp_partial, self.gp_out)
+        seed = self.gp_out[1:2]
+        # step 3: adjoint sweep bottom -> top, seeded with A_g = seed * g
+        col_g = g(f"{tag}.colg", (npix0, 64))
+        ops.im2col_img(grad_x, col_g, mode=0, mul_dev=seed)
+        da0 = g(f"{tag}.da0", (B, H0, H0, self.C0))
+        h0 = g(f"{tag}.h0", (B, H0, H0, self.C0))
+        dcol = g("bwd.dcol", (self.C0, 64), F32)
+        ops.gemm_tn(da0.view(npix0, self.C0), col_g, out=dcol)
+        ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=0.0)
+        A_da0 = g(f"{tag}.Ada0", (B, H0, H0, self.C0))
+        ops.gemm_nt(col_g, self.w_col0, out=A_da0.view(npix0, self.C0))
+        A_dh = g(f"{tag}.Adh0", (B, H0, H0, self.C0))
+        ops.lrelu_bwd(A_da0, h0, SLOPE, A_dh, npix0, self.C0)
+        H = H0
+        for l in range(1, n + 1):
+            c, bn = self.convs[l - 1], self.bns[l - 1]
+            Cp = c.weight.shape[0]
+            H //= 2
+            M = B * H * H
+            da = g(f"{tag}.da{l}", (B, H, H, Cp))
+            du = g(f"{tag}.du{l}", (B, H, H, Cp))
+            a = g(f"{tag}.a{l}", (B, H, H, Cp))
+            ops.conv_wgrad(da, A_dh, _grad_of(c.weight), beta=0.0)
+            ggI = g(f"{tag}.ggI{l}", (B, H, H, Cp))
+            ops.conv_down(A_dh, self.w_down[l - 1], out=ggI)
+            # bn.bsums still holds S(du), S(du*xhat) of THIS layer from step 2
+            bs = bn.st(tag)
+            ops.bn_gp_reduce(ggI, a, du, bs.mean, bs.rstd, M, Cp, bs.q)
+            A_dh = g(f"{tag}.Adh{l}", (B, H, H, Cp))
+            A_a = g(f"{tag}.Aa{l}", (B, H, H, Cp))
+            ops.bn_gp_apply(ggI, a, du, bs.mean, bs.rstd, bn.mod.weight, bs.scale, bs.shift, SLOPE, bs.bsums, bs.q, M,
+                            Cp, A_dh, A_a, _grad_of(bn.mod.weight), 0.0)
+        da6 = g(f"{tag}.da6", (B,), F32)
+        ops.head_wgrad(da6, A_dh, B, 16 * self.Cn, self.Cn, _grad_of(self.head.weight), 0.0)
+        # step 4: ordinary backward over the forward graph, seeded by the A_a terms
+        T = g(f"{tag}.Aa{n}", (B, 4, 4, self.Cn))
+        _grad_of(self.bns[n - 1].mod.bias).zero_()
+        H = 4
+        for l in range(n, 0, -1):
+            c = self.convs[l - 1]
+            Cp, Cs = c.weight.shape[0], c.weight.shape[1]
+            hprev = g(f"{tag}.h{l - 1}", (B, 2 * H, 2 * H, Cs))
+            ops.conv_wgrad(T, hprev, _grad_of(c.weight), beta=1.0)
+            H *= 2
+            A_h = g(f"{tag}.Ah{l - 1}", (B, H, H, Cs))
+            ops.conv_up(T, self.w_up[l - 1], Cs, out=A_h)
+            if l - 1 >= 1:
+                bnp = self.bns[l - 2]
+                a = g(f"{tag}.a{l - 1}", (B, H, H, Cs))
+                A_a = g(f"{tag}.Aa{l - 1}", (B, H, H, Cs))
+                Tn = g(f"{tag}.T{l - 1}", (B, H, H, Cs))
+                # note: overwrites bnp.bsums (step-2 sums of layer l-1 were consumed in step 3 already)
+                bnp.backward(A_h, a, Tn, B * H * H, param_grads=True, acc_gamma=1.0, acc_beta=0.0, add=A_a, tag=tag)
+                T = Tn
+            else:
+                A_a0 = g(f"{tag}.Aa0", (B, H, H, self.C0))
+                ops.lrelu_bwd(A_h, h0, SLOPE, A_a0, npix0, self.C0)
+                ops.gemm_tn(A_a0.view(npix0, self.C0), col_x, out=dcol)
+                ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=1.0)
+                ops.col_sum(A_a0, npix0, self.C0, self.tmpC, _grad_of(self.conv0.bias), 0.0)
+        return self.gp_out
+
+
+# ====================================================================================================== encoder
+class EncoderEngine:
+    """Frozen, eval-mode betaVAE.encode -> z_mean (src/betaVAE.py:102-107 as used at src/wgan_loss.py:97):
+    3 x [Linear + eval BatchNorm1d + LeakyReLU(0.01)] folded into GEMM epilogues, then the z_mu Linear."""
+
+    def __init__(self, vae):
+        enc = vae.encoder.encoder
+        dev = next(vae.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("EncoderEngine needs the betaVAE on a CUDA device (there is no CPU path)")
+        self.device = dev
+        self.vae = vae
+        self.layers = []
+        self.bufs = _Bufs(dev)
+        self.in_features = enc[1][0].weight.shape[1]
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        """Re-derive packed weights / folded BN vectors from the module (call after loading a checkpoint)."""
+        enc = self.vae.encoder.encoder
+        self.layers = []
+        for blk in list(enc)[1:]:
+            lin, bn = blk[0], blk[1]
+            K = lin.weight.shape[1]
+            Kp = (K + 63) // 64 * 64
+            w = ops.cast_pad_bf16(lin.weight.detach().contiguous(), Kp)
+            scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+            shift = ((lin.bias - bn.running_mean) * scale + bn.bias).float().contiguous()
+            self.layers.append((w, scale, shift, blk[2].negative_slope, lin.weight.shape[0], Kp))
+        mu, lv = self.vae.z_mu, self.vae.z_logvar
+        self.w_mu = ops.cast_pad_bf16(mu.weight.detach().contiguous(), mu.weight.shape[1])
+        self.b_mu = mu.bias.detach().float().contiguous()
+        self.w_lv = ops.cast_pad_bf16(lv.weight.detach().contiguous(), lv.weight.shape[1])
+        self.b_lv = lv.bias.detach().float().contiguous()
+
+    def encode(self, x, want_all=False):
+        """x: fp32 [B, F] on the device -> z_mean fp32 [B, Z] (and z_logvar, last hidden when want_all)."""
+        B = x.shape[0]
+        g = self.bufs.get
+        Kp0 = self.layers[0][5]
+        h = g("x", (B, Kp0))
+        ops.cast_pad_bf16(x.contiguous(), Kp0, out=h)
+        for i, (w, scale, shift, slope, N, Kp) in enumerate(self.layers):
+            Np = (N + 63) // 64 * 64        # next layer's K: keep the row stride padded, pad columns stay zero
+            o = g(f"h{i}", (B, Np), zero=True)
+            ops.gemm_nt(h, w, out=o, col_scale=scale, col_shift=shift, slope=slope, N=N)
+            h = o
+        z = g("z", (B, self.w_mu.shape[0]), F32)
+        ops.gemm_nt(h, self.w_mu, out=z, col_shift=self.b_mu)
+        if not want_all:
+            return z
+        lv = g("zlv", (B, self.w_lv.shape[0]), F32)
+        ops.gemm_nt(h, self.w_lv, out=lv, col_shift=self.b_lv)
+        return z, lv, h[:, :self.layers[-1][4]].float()

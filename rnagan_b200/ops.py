@@ -173,3 +173,154 @@ def gemm_tn(A, Bm, out=None, alpha=1.0, alpha_dev=None, beta=0.0):
     _lib.check(L.rg_gemm_tn(_p(A), _p(Bm), _p(out), _p(ws), ws.numel() * 4, R, M, N, float(alpha), _p(alpha_dev),
                             float(beta), _st()), "rg_gemm_tn")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ HBM-bound ops
+F32 = torch.float32
+
+
+def _red_ws(M, C, device):
+    return _workspace(_lib.lib().rg_reduce_ws_bytes(M, C), device)
+
+
+def bn_stats(a, M, C, sums):
+    ws = _red_ws(M, C, a.device)
+    _lib.check(_lib.lib().rg_bn_stats(_p(a), M, C, _p(ws), ws.numel() * 4, _p(sums), _st()), "rg_bn_stats")
+
+
+def bn_finalize(sums, gamma, beta, M, C, eps, momentum, rmean, rvar, nbt, mean, rstd, scale, shift):
+    _lib.check(_lib.lib().rg_bn_finalize(_p(sums), _p(gamma), _p(beta), M, C, float(eps), float(momentum), _p(rmean),
+                                         _p(rvar), _p(nbt), _p(mean), _p(rstd), _p(scale), _p(shift), _st()),
+               "rg_bn_finalize")
+
+
+def bn_act(a, scale, shift, slope, h, M, C):
+    _lib.check(_lib.lib().rg_bn_act(_p(a), _p(scale), _p(shift), float(slope), _p(h), M, C, _st()), "rg_bn_act")
+
+
+def bn_bwd_reduce(dh, a, mean, rstd, scale, shift, slope, M, C, sums):
+    ws = _red_ws(M, C, a.device)
+    _lib.check(_lib.lib().rg_bn_bwd_reduce(_p(dh), _p(a), _p(mean), _p(rstd), _p(scale), _p(shift), float(slope), M, C,
+                                           _p(ws), ws.numel() * 4, _p(sums), _st()), "rg_bn_bwd_reduce")
+
+
+def bn_bwd_apply(dh, a, add, mean, rstd, scale, shift, slope, sums, M, C, da, du_out=None):
+    _lib.check(_lib.lib().rg_bn_bwd_apply(_p(dh), _p(a), _p(add), _p(mean), _p(rstd), _p(scale), _p(shift),
+                                          float(slope), _p(sums), M, C, _p(da), _p(du_out), _st()), "rg_bn_bwd_apply")
+
+
+def bn_param_grads(sums, dgamma, dbeta, C, acc_gamma, acc_beta):
+    _lib.check(_lib.lib().rg_bn_param_grads(_p(sums), _p(dgamma), _p(dbeta), C, float(acc_gamma), float(acc_beta),
+                                            _st()), "rg_bn_param_grads")
+
+
+def lrelu_bwd(dh, h, slope, da, M, C):
+    _lib.check(_lib.lib().rg_lrelu_bwd(_p(dh), _p(h), float(slope), _p(da), M, C, _st()), "rg_lrelu_bwd")
+
+
+def col_sum(x, M, C, tmp, out, acc):
+    ws = _red_ws(M, C, x.device)
+    _lib.check(_lib.lib().rg_col_sum(_p(x), M, C, _p(ws), ws.numel() * 4, _p(tmp), _p(out), float(acc), _st()),
+               "rg_col_sum")
+
+
+def bn_gp_reduce(ggI, a, gO, mean, rstd, M, C, q):
+    ws = _red_ws(M, C, a.device)
+    _lib.check(_lib.lib().rg_bn_gp_reduce(_p(ggI), _p(a), _p(gO), _p(mean), _p(rstd), M, C, _p(ws), ws.numel() * 4,
+                                          _p(q), _st()), "rg_bn_gp_reduce")
+
+
+def bn_gp_apply(ggI, a, gO, mean, rstd, gamma, scale, shift, slope, s, q, M, C, A_dh, A_a, dgamma, dgamma_acc):
+    _lib.check(_lib.lib().rg_bn_gp_apply(_p(ggI), _p(a), _p(gO), _p(mean), _p(rstd), _p(gamma), _p(scale), _p(shift),
+                                         float(slope), _p(s), _p(q), M, C, _p(A_dh), _p(A_a), _p(dgamma),
+                                         float(dgamma_acc), _st()), "rg_bn_gp_apply")
+
+
+def latent_prep(noise, z, lat_bf16=None, lat_f32=None):
+    _chk(noise, F32, "noise"); _chk(z, F32, "z")
+    B, E = noise.shape
+    _lib.check(_lib.lib().rg_latent_prep(_p(noise), _p(z), B, E, z.shape[0], _p(lat_bf16), _p(lat_f32), _st()),
+               "rg_latent_prep")
+
+
+def im2col_img(x, col, y=None, mode=0, eps_dev=None, mul_dev=None, mixed_out=None):
+    _chk(x, F32, "x")
+    B, Cimg, S, _ = x.shape
+    _lib.check(_lib.lib().rg_im2col_img(_p(x), _p(y), mode, _p(eps_dev), _p(mul_dev), B, Cimg, S, _p(col),
+                                        _p(mixed_out), _st()), "rg_im2col_img")
+
+
+def img_channel_sum(x, out, y=None, mode=0, acc=0.0):
+    B, Cimg, S, _ = x.shape
+    _lib.check(_lib.lib().rg_img_channel_sum(_p(x), _p(y), mode, B, Cimg, S, _p(out), float(acc), _st()),
+               "rg_img_channel_sum")
+
+
+def unpack_edge_grad(dcol, dW, acc=0.0):
+    Cp, Cimg = dW.shape[0], dW.shape[1]
+    _lib.check(_lib.lib().rg_unpack_edge_grad(_p(dcol), _p(dW), Cp, Cimg, float(acc), _st()), "rg_unpack_edge_grad")
+
+
+def pack_head(W, w_head):
+    _lib.check(_lib.lib().rg_pack_head(_p(W), _p(w_head), W.shape[1], _st()), "rg_pack_head")
+
+
+def head_fwd(h5, w_head, B, K, slope, a6, out):
+    _lib.check(_lib.lib().rg_head_fwd(_p(h5), _p(w_head), B, K, float(slope), _p(a6), _p(out), _st()), "rg_head_fwd")
+
+
+def head_bwd_data(a6, dout_const, w_head, B, K, slope, da6, dh5, dout=None):
+    _lib.check(_lib.lib().rg_head_bwd_data(_p(a6), _p(dout), float(dout_const), _p(w_head), B, K, float(slope),
+                                           _p(da6), _p(dh5), _st()), "rg_head_bwd_data")
+
+
+def head_wgrad(da6, x, B, K, C, dW, acc):
+    _lib.check(_lib.lib().rg_head_wgrad(_p(da6), _p(x), B, K, C, _p(dW), float(acc), _st()), "rg_head_wgrad")
+
+
+def wgan_loss(a, sign_a, loss_out, b=None, sign_b=0.0):
+    _lib.check(_lib.lib().rg_wgan_loss(_p(a), float(sign_a), _p(b), float(sign_b), a.numel(), _p(loss_out), _st()),
+               "rg_wgan_loss")
+
+
+def gp_norm(g, lambd, partial, out3):
+    _lib.check(_lib.lib().rg_gp_norm(_p(g), g.numel(), float(lambd), _p(partial), partial.numel(), _p(out3), _st()),
+               "rg_gp_norm")
+
+
+def tiles_to_unit_nhwc(img, out):
+    B, C, S, _ = img.shape
+    _lib.check(_lib.lib().rg_tiles_to_unit_nhwc(_p(img), _p(out), B, C, S, _st()), "rg_tiles_to_unit_nhwc")
+
+
+def clamp_(p, lo, hi):
+    _lib.check(_lib.lib().rg_clamp(_p(p), p.numel(), float(lo), float(hi), _st()), "rg_clamp")
+
+
+class AdamTable:
+    """Chunk table over a fixed list of (param, grad, exp_avg, exp_avg_sq) fp32 tensors for rg_adam_step."""
+
+    CHUNK = 1 << 16
+
+    def __init__(self, params, grads, ms, vs):
+        import ctypes
+        L = _lib.lib()
+        n = len(params)
+        sizes = [p.numel() for p in params]
+        max_chunks = sum((s + self.CHUNK - 1) // self.CHUNK for s in sizes)
+        arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
+        host = torch.empty(L.rg_adam_table_bytes(max_chunks), dtype=torch.uint8).pin_memory()
+        nch = L.rg_adam_build_table(arr(params), arr(grads), arr(ms), arr(vs), (ctypes.c_int64 * n)(*sizes), n,
+                                    self.CHUNK, host.data_ptr(), max_chunks)
+        if nch <= 0:
+            _lib.check(nch if nch < 0 else -1, "rg_adam_build_table")
+        self.num_chunks = nch
+        self.table = host.to(params[0].device, non_blocking=False)
+        self.keep = (params, grads, ms, vs)
+        self.ptrs = tuple(t.data_ptr() for ts in self.keep for t in ts)
+
+    def step(self, lr, beta1, beta2, eps, step, clamp=None):
+        lo, hi = (clamp if clamp is not None else (0.0, 0.0))
+        _lib.check(_lib.lib().rg_adam_step(_p(self.table), self.num_chunks, float(lr), float(beta1), float(beta2),
+                                           float(eps), int(step), int(clamp is not None), float(lo), float(hi), _st()),
+                   "rg_adam_step")

@@ -1,0 +1,48 @@
+"""Optimizer step on the fused multi-tensor Adam kernel (rg_adam_step), driven by the caller's torch.optim.Adam.
+
+The reference builds ``torch.optim.Adam(lr=1e-4 / 4e-4, betas=(0.5, 0.999))`` objects (src/histopathology_gan.py:252,257)
+and passes them to ``train_ops``; to stay a drop-in, the optimizer object remains the owner of the hyper-parameters and
+of the state (``state[p] = {step, exp_avg, exp_avg_sq}`` in torch's own format, so ``optimizer.state_dict()`` and the
+torchgan checkpoint layout keep working) while the arithmetic runs in one kernel launch over all tensors.
+"""
+import torch
+
+from . import ops
+
+
+def _ensure_state(opt, p):
+    st = opt.state[p]
+    if len(st) == 0:
+        st["step"] = torch.tensor(0.0, dtype=torch.float32)
+        st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return st
+
+
+def adam_step(opt, clamp=None):
+    """One Adam step over every parameter of ``opt`` that has a gradient. Returns nothing; asynchronous."""
+    if not isinstance(opt, torch.optim.Adam):
+        raise NotImplementedError(f"only torch.optim.Adam is implemented on the sm_100a path (got {type(opt).__name__})")
+    tables = opt.__dict__.setdefault("_rg_tables", {})
+    for gi, group in enumerate(opt.param_groups):
+        if group.get("weight_decay", 0) != 0 or group.get("amsgrad", False) or group.get("maximize", False):
+            raise NotImplementedError("Adam with weight_decay / amsgrad / maximize is not implemented")
+        params = [p for p in group["params"] if p.grad is not None]
+        if not params:
+            continue
+        states = [_ensure_state(opt, p) for p in params]
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                raise NotImplementedError("fused Adam needs contiguous fp32 parameters and gradients")
+        key = tuple(t.data_ptr() for p, s in zip(params, states) for t in (p, p.grad, s["exp_avg"], s["exp_avg_sq"]))
+        ent = tables.get(gi)
+        if ent is None or ent[0] != key:
+            tab = ops.AdamTable([p.detach() for p in params], [p.grad for p in params],
+                                [s["exp_avg"] for s in states], [s["exp_avg_sq"] for s in states])
+            ent = (key, tab)
+            tables[gi] = ent
+        for s in states:
+            s["step"] += 1
+        step = int(states[0]["step"].item()) if states[0]["step"].device.type == "cpu" else int(states[0]["step"])
+        b1, b2 = group["betas"]
+        ent[1].step(group["lr"], b1, b2, group["eps"], step, clamp=clamp)

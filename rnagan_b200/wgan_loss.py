@@ -1,0 +1,247 @@
+"""Drop-in WGAN loss objects with betaVAE conditioning (src/wgan_loss.py) on the sm_100a kernels.
+
+Same class names, constructor arguments, ``forward`` and -- because torchgan's Trainer binds them BY PARAMETER NAME
+ -- exactly the same ``train_ops`` signatures:
+
+  WassersteinGeneratorLossVAE.train_ops(generator, discriminator, optimizer_generator, device, batch_size,
+                                        real_inputs, labels=None)                      src/wgan_loss.py:82-129
+  WassersteinDiscriminatorLossVAE.train_ops(generator, discriminator, optimizer_discriminator, real_inputs, device,
+                                            labels=None)                               src/wgan_loss.py:181-263
+  WassersteinGradientPenaltyVAE.train_ops(generator, discriminator, optimizer_discriminator, real_inputs, device,
+                                          labels=None)                                 src/wgan_loss.py:314-389
+
+Semantics kept from the reference: three optimiser steps per batch, a fresh CPU-RNG
+uniform(-0.3, 0.3) noise draw per step, additive conditioning + unbiased batch standardisation, train-mode
+BatchNorm everywhere, one scalar eps per GP step drawn after that step's noise, whole-batch gradient norm,
+lambda applied outside ``forward``, un-weighted penalty returned.  Work the reference wastes (encoder backward,
+critic wgrad in the G step, generator backward in the GP step) is simply not scheduled.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .betaVAE import betaVAE
+from .optim import adam_step
+
+F32 = torch.float32
+BF16 = torch.bfloat16
+
+
+def reduce_vae(x, reduction=None):
+    if reduction == "mean":
+        return torch.mean(x)
+    elif reduction == "sum":
+        return torch.sum(x)
+    return x
+
+
+def wasserstein_generator_loss_vae(fgz, reduction="mean"):
+    return reduce_vae(-1.0 * fgz, reduction="mean")
+
+
+def wasserstein_discriminator_loss_vae(fx, fgz, reduction="mean"):
+    return reduce_vae(fgz - fx, reduction="mean")
+
+
+class GeneratorLoss(nn.Module):
+    """torchgan.losses.GeneratorLoss contract (reduction / override_train_ops / arg_map)."""
+
+    def __init__(self, reduction="mean", override_train_ops=None):
+        super().__init__()
+        self.reduction = reduction
+        self.override_train_ops = override_train_ops
+        self.arg_map = {}
+
+    def set_arg_map(self, value):
+        self.arg_map.update(value)
+
+
+class DiscriminatorLoss(nn.Module):
+    def __init__(self, reduction="mean", override_train_ops=None):
+        super().__init__()
+        self.reduction = reduction
+        self.override_train_ops = override_train_ops
+        self.arg_map = {}
+
+    def set_arg_map(self, value):
+        self.arg_map.update(value)
+
+
+# ------------------------------------------------------------------------------------------------ shared plumbing
+class _StepCache:
+    """Per-iteration reuse of device copies: the three train_ops of one iteration receive the same ``real_inputs``
+    (torchgan Trainer.train_iter), and the frozen eval-mode encoder is deterministic, so z and the H2D copies of the
+    batch are computed once.  Keyed on tensor identity + version, so any new / modified batch misses."""
+
+    def __init__(self):
+        self.key = {}
+        self.val = {}
+        self.keep = {}
+
+    def get(self, what, src, device, make):
+        key = (id(src), src._version, tuple(src.shape), str(device))
+        if self.key.get(what) != key:
+            self.val[what] = make()
+            self.key[what] = key
+            self.keep[what] = src     # keep the source alive so its id cannot be recycled
+        return self.val[what]
+
+
+_CACHE = _StepCache()
+_SHARED_VAE = {}
+
+
+def _load_vae(checkpoint, rna_features, beta):
+    vae = betaVAE(rna_features, 2048, [6000, 4000, 2048], [4000, 6000], beta=beta)
+    vae.load_state_dict(torch.load(checkpoint))
+    vae.eval()
+    return vae
+
+
+class _VAEConditioned:
+    """Mixin: owns the frozen betaVAE like the reference's loss objects do (src/wgan_loss.py:67-69)."""
+
+    def _init_vae(self, checkpoint, rna_features, beta):
+        self.betavae = _load_vae(checkpoint, rna_features, beta)
+        self._ckpt_key = (str(checkpoint), int(rna_features))
+
+    def _encoder(self, device):
+        """All three loss objects load the SAME checkpoint (src/histopathology_gan.py:275-277): share one device copy."""
+        key = self._ckpt_key + (str(device),)
+        vae = _SHARED_VAE.get(key)
+        if vae is None:
+            self.betavae = self.betavae.to(device)
+            vae = self.betavae
+            _SHARED_VAE[key] = vae
+        return vae
+
+    def _latent(self, generator, real_inputs, device):
+        """encode -> CPU uniform(-0.3,0.3) noise -> add -> batch standardise (src/wgan_loss.py:96-106)."""
+        B = real_inputs["image"].size(0)
+        rna = real_inputs["rna_data"]
+        vae = self._encoder(device)
+        z = _CACHE.get("z", rna, device,
+                       lambda: vae.encode_mean(rna.to(device, non_blocking=True)))
+        noise = torch.FloatTensor(B, generator.encoding_dims).uniform_(-0.3, 0.3)
+        eng = generator._engine()
+        noise_d = eng.bufs.get("noise", (B, generator.encoding_dims), F32)
+        noise_d.copy_(noise, non_blocking=False)
+        lat = eng.bufs.get("lat", (B, generator.encoding_dims), BF16)
+        ops.latent_prep(noise_d, z, lat_bf16=lat)
+        return B, lat
+
+    @staticmethod
+    def _real(real_inputs, device):
+        img = real_inputs["image"]
+        return _CACHE.get("image", img, device,
+                          lambda: img.to(device=device, dtype=F32, non_blocking=True).contiguous())
+
+
+def _check_labels(labels, *nets):
+    if labels is None and any(n.label_type == "required" for n in nets):
+        raise Exception("GAN model requires labels for training")
+    for n in nets:
+        if n.label_type != "none":
+            raise NotImplementedError("only label_type='none' is on the sm_100a path (the only one the reference "
+                                      "drivers exercise, SURVEY.md Appendix B.10)")
+
+
+def _loss_buf(gen_engine):
+    return gen_engine.bufs.get("loss", (1,), F32)
+
+
+# ------------------------------------------------------------------------------------------------ loss objects
+class WassersteinGeneratorLossVAE(_VAEConditioned, GeneratorLoss):
+    def __init__(self, checkpoint, rna_features, beta=0.005):
+        # the reference passes (checkpoint, rna_features) positionally into (reduction, override_train_ops)
+        # (src/wgan_loss.py:64-66); keep the same observable attributes
+        GeneratorLoss.__init__(self, checkpoint, rna_features)
+        self._init_vae(checkpoint, rna_features, beta)
+
+    def forward(self, fgz):
+        return wasserstein_generator_loss_vae(fgz, self.reduction)
+
+    def train_ops(self, generator, discriminator, optimizer_generator, device, batch_size, real_inputs, labels=None):
+        _check_labels(labels, generator)
+        B, lat = self._latent(generator, real_inputs, device)
+        ge, de = generator._engine(), discriminator._engine()
+        fake = ge.forward(lat, tag="g", training=generator.training)
+        out = de.forward(fake, tag="gstep", training=discriminator.training)
+        loss = _loss_buf(ge)
+        ops.wgan_loss(out, -1.0, loss)                                   # mean(-D(G(z)))
+        d_img = de.backward(B, -1.0 / B, tag="gstep", params=False, want_dimg=True)
+        ge.backward(lat, d_img, fake, tag="g")
+        _allreduce_grads(generator)
+        adam_step(optimizer_generator)
+        ge.pack()
+        return loss.item()
+
+
+class WassersteinDiscriminatorLossVAE(_VAEConditioned, DiscriminatorLoss):
+    def __init__(self, checkpoint, rna_features, beta=0.005, reduction="mean", clip=None, override_train_ops=None):
+        DiscriminatorLoss.__init__(self, checkpoint, rna_features)
+        self.clip = clip if isinstance(clip, (tuple, list)) and len(clip) > 1 else None
+        self._init_vae(checkpoint, rna_features, beta)
+
+    def forward(self, fx, fgz):
+        return wasserstein_discriminator_loss_vae(fx, fgz, self.reduction)
+
+    def train_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
+        ge, de = generator._engine(), discriminator._engine()
+        if self.clip is not None:                                        # src/wgan_loss.py:213-215
+            for p in discriminator.parameters():
+                ops.clamp_(p.data, self.clip[0], self.clip[1])
+            de.pack()
+        _check_labels(labels, generator, discriminator)
+        B, lat = self._latent(generator, real_inputs, device)
+        real = self._real(real_inputs, device)
+        out_real = de.forward(real, tag="real", training=discriminator.training)
+        fake = ge.forward(lat, tag="g", training=generator.training)
+        out_fake = de.forward(fake, tag="fake", training=discriminator.training)
+        loss = _loss_buf(ge)
+        ops.wgan_loss(out_fake, 1.0, loss, b=out_real, sign_b=-1.0)      # mean(D(G(z)) - D(x))
+        de.backward(B, -1.0 / B, tag="real", params=True, acc=0.0)
+        de.backward(B, 1.0 / B, tag="fake", params=True, acc=1.0)
+        _allreduce_grads(discriminator)
+        adam_step(optimizer_discriminator)
+        de.pack()
+        return loss.item()
+
+
+class WassersteinGradientPenaltyVAE(_VAEConditioned, DiscriminatorLoss):
+    def __init__(self, checkpoint, rna_features, reduction="mean", lambd=10.0, override_train_ops=None, beta=0.005):
+        DiscriminatorLoss.__init__(self, checkpoint, rna_features)
+        self.lambd = lambd
+        self.override_train_ops = override_train_ops
+        self._init_vae(checkpoint, rna_features, beta)
+
+    def forward(self, interpolate, d_interpolate):
+        raise NotImplementedError("the penalty is computed inside train_ops by CriticEngine.gradient_penalty "
+                                  "(hand-scheduled double backward); there is no autograd graph to differentiate")
+
+    def train_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
+        _check_labels(labels, generator, discriminator)
+        ge, de = generator._engine(), discriminator._engine()
+        B, lat = self._latent(generator, real_inputs, device)
+        real = self._real(real_inputs, device)
+        fake = ge.forward(lat, tag="g", training=generator.training)
+        eps = torch.rand(1)                                              # one scalar per step, src/wgan_loss.py:376
+        eps_d = de.bufs.get("eps", (1,), F32)
+        eps_d.copy_(eps)
+        out3 = de.gradient_penalty(real, fake, eps_d, lambd=self.lambd)
+        _allreduce_grads(discriminator)
+        adam_step(optimizer_discriminator)
+        de.pack()
+        return out3[0].item()
+
+
+# ------------------------------------------------------------------------------------------------ data parallel
+def _allreduce_grads(module):
+    """Batch-sharded training: average parameter gradients over ranks with NCCL when a process
+    group is initialised; single-process runs skip it."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    from .parallel import allreduce_mean_
+    allreduce_mean_([p.grad for p in module.parameters() if p.grad is not None])
