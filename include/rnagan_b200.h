@@ -38,6 +38,8 @@ int rg_version(void);
 const char* rg_last_error(void);
 /* 0 when the current device can run the library (compute capability 10.x), RG_EARCH otherwise. */
 int rg_check_device(void);
+/* number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches) */
+long long rg_launch_count(void);
 
 /* ---- weight packing (after every optimizer step) --------------------------------------------------------- */
 /* fp32 W[Cp][Cs][4][4] -> bf16 w_down and/or w_up (either may be NULL).  Replaces nothing in the reference: it is

@@ -1,6 +1,7 @@
 // rg_gemm_api.cu -- C-ABI entry points for the tcgen05 tile engine (rg_gemm.cuh) and the weight packers.
 #include <stdarg.h>
 #include <algorithm>
+#include <atomic>
 #include "rg_gemm.cuh"
 #include "rg_host.cuh"
 
@@ -19,6 +20,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) in %s", static_cast<int>(e), cudaGetErrorString(e), what);
   return static_cast<int>(e);
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -321,6 +325,7 @@ using namespace rg;
 extern "C" {
 
 int rg_version(void) { return 100; }
+long long rg_launch_count(void) { return rg::launch_count(); }
 const char* rg_last_error(void) { return g_err; }
 
 int rg_check_device(void) {

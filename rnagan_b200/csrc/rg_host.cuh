@@ -13,6 +13,7 @@ namespace rg {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int num_sms();
+void count_launch();
 
 #define RG_CHECK_ARG(cond, ...)        \
   do {                                 \
@@ -28,8 +29,10 @@ int num_sms();
     if (e__ != cudaSuccess) return rg::cuda_fail(e__, #call); \
   } while (0)
 
+// every kernel launch site goes through this macro: it also feeds rg_launch_count()
 #define RG_LAUNCH_CHECK(name)                                   \
   do {                                                          \
+    rg::count_launch();                                         \
     cudaError_t e__ = cudaGetLastError();                       \
     if (e__ != cudaSuccess) return rg::cuda_fail(e__, name);    \
   } while (0)

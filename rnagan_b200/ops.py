@@ -28,6 +28,21 @@ def _chk(t, dtype, name):
 
 _ws_cache = {}
 
+# When set to a list, every tcgen05 contraction records (kind, algorithmic flops, start event, end event): bench.py
+# uses it to measure per-kernel roofline fractions live, on the launching stream, outside the timed region.
+PROFILE = None
+
+
+def _prof(kind, flops, fn):
+    if PROFILE is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    PROFILE.append((kind, float(flops), e0, e1))
+    return r
+
 
 def _workspace(nbytes, device):
     """Grow-only fp32 scratch per device (split-K partials); caller-owned from the library's point of view."""
@@ -96,7 +111,8 @@ def conv_down(hi, w_down, out=None):
     H, W = H2 // 2, W2 // 2
     if out is None:
         out = torch.empty(B, H, W, Cp, dtype=BF16, device=hi.device)
-    _lib.check(_lib.lib().rg_conv_down(_p(hi), _p(w_down), _p(out), B, H, W, Cs, Cp, _st()), "rg_conv_down")
+    _prof("conv_down", 2.0 * B * H * W * Cp * 16 * Cs, lambda: _lib.check(
+        _lib.lib().rg_conv_down(_p(hi), _p(w_down), _p(out), B, H, W, Cs, Cp, _st()), "rg_conv_down"))
     return out
 
 
@@ -106,7 +122,8 @@ def conv_up(lo, w_up, Cs, out=None):
     B, H, W, Cp = lo.shape
     if out is None:
         out = torch.empty(B, 2 * H, 2 * W, Cs, dtype=BF16, device=lo.device)
-    _lib.check(_lib.lib().rg_conv_up(_p(lo), _p(w_up), _p(out), B, H, W, Cp, Cs, _st()), "rg_conv_up")
+    _prof("conv_up", 2.0 * B * H * W * Cp * 16 * Cs, lambda: _lib.check(
+        _lib.lib().rg_conv_up(_p(lo), _p(w_up), _p(out), B, H, W, Cp, Cs, _st()), "rg_conv_up"))
     return out
 
 
@@ -116,8 +133,9 @@ def conv_up_img(lo, w_up, Cimg, bias=None, act_tanh=False, out=None):
     B, H, W, Cp = lo.shape
     if out is None:
         out = torch.empty(B, Cimg, 2 * H, 2 * W, dtype=torch.float32, device=lo.device)
-    _lib.check(_lib.lib().rg_conv_up_img(_p(lo), _p(w_up), _p(out), _p(bias), int(act_tanh), B, H, W, Cp, Cimg, _st()),
-               "rg_conv_up_img")
+    _prof("conv_up_img", 2.0 * B * H * W * Cp * 16 * Cimg, lambda: _lib.check(
+        _lib.lib().rg_conv_up_img(_p(lo), _p(w_up), _p(out), _p(bias), int(act_tanh), B, H, W, Cp, Cimg, _st()),
+        "rg_conv_up_img"))
     return out
 
 
@@ -129,8 +147,9 @@ def conv_wgrad(lo, hi, dW, alpha=1.0, alpha_dev=None, beta=0.0):
     L = _lib.lib()
     nbytes = L.rg_conv_wgrad_ws_bytes(B, H, W, Cp, Cs)
     ws = _workspace(nbytes, lo.device)
-    _lib.check(L.rg_conv_wgrad(_p(lo), _p(hi), _p(dW), _p(ws), ws.numel() * 4, B, H, W, Cp, Cs, float(alpha),
-                               _p(alpha_dev), float(beta), _st()), "rg_conv_wgrad")
+    _prof("conv_wgrad", 2.0 * B * H * W * Cp * 16 * Cs, lambda: _lib.check(
+        L.rg_conv_wgrad(_p(lo), _p(hi), _p(dW), _p(ws), ws.numel() * 4, B, H, W, Cp, Cs, float(alpha), _p(alpha_dev),
+                        float(beta), _st()), "rg_conv_wgrad"))
     return dW
 
 
@@ -142,8 +161,9 @@ def proj_wgrad(z, da0, dW, alpha=1.0, alpha_dev=None, beta=0.0):
     L = _lib.lib()
     nbytes = L.rg_proj_wgrad_ws_bytes(B, E, C0)
     ws = _workspace(nbytes, z.device)
-    _lib.check(L.rg_proj_wgrad(_p(z), _p(da0), _p(dW), _p(ws), ws.numel() * 4, B, E, C0, float(alpha), _p(alpha_dev),
-                               float(beta), _st()), "rg_proj_wgrad")
+    _prof("proj_wgrad", 2.0 * B * E * 16 * C0, lambda: _lib.check(
+        L.rg_proj_wgrad(_p(z), _p(da0), _p(dW), _p(ws), ws.numel() * 4, B, E, C0, float(alpha), _p(alpha_dev),
+                        float(beta), _st()), "rg_proj_wgrad"))
     return dW
 
 
@@ -155,8 +175,9 @@ def gemm_nt(A, Bw, out=None, col_scale=None, col_shift=None, slope=1.0, out_f32=
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32 if out_f32 else BF16, device=A.device)
     ldc = out.stride(0)
-    _lib.check(_lib.lib().rg_gemm_nt(_p(A), _p(Bw), _p(out), M, N, K, ldc, _p(col_scale), _p(col_shift), float(slope),
-                                     int(out.dtype == torch.float32), _st()), "rg_gemm_nt")
+    _prof("gemm_nt", 2.0 * M * N * K, lambda: _lib.check(
+        _lib.lib().rg_gemm_nt(_p(A), _p(Bw), _p(out), M, N, K, ldc, _p(col_scale), _p(col_shift), float(slope),
+                              int(out.dtype == torch.float32), _st()), "rg_gemm_nt"))
     return out
 
 
@@ -170,8 +191,9 @@ def gemm_tn(A, Bm, out=None, alpha=1.0, alpha_dev=None, beta=0.0):
     L = _lib.lib()
     nbytes = L.rg_gemm_tn_ws_bytes(R, M, N)
     ws = _workspace(nbytes, A.device)
-    _lib.check(L.rg_gemm_tn(_p(A), _p(Bm), _p(out), _p(ws), ws.numel() * 4, R, M, N, float(alpha), _p(alpha_dev),
-                            float(beta), _st()), "rg_gemm_tn")
+    _prof("gemm_tn", 2.0 * R * M * N, lambda: _lib.check(
+        L.rg_gemm_tn(_p(A), _p(Bm), _p(out), _p(ws), ws.numel() * 4, R, M, N, float(alpha), _p(alpha_dev),
+                     float(beta), _st()), "rg_gemm_tn"))
     return out
 
 

@@ -19,9 +19,8 @@ critic wgrad in the G step, generator backward in the GP step) is simply not sch
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, steps
 from .betaVAE import betaVAE
-from .optim import adam_step
 
 F32 = torch.float32
 BF16 = torch.bfloat16
@@ -115,20 +114,17 @@ class _VAEConditioned:
             _SHARED_VAE[key] = vae
         return vae
 
-    def _latent(self, generator, real_inputs, device):
-        """encode -> CPU uniform(-0.3,0.3) noise -> add -> batch standardise (src/wgan_loss.py:96-106)."""
+    def _inputs(self, generator, real_inputs, device):
+        """z = encode(rna) (once per batch) and this step's CPU uniform(-0.3, 0.3) noise draw, both on the device
+        (src/wgan_loss.py:96-101)."""
         B = real_inputs["image"].size(0)
         rna = real_inputs["rna_data"]
         vae = self._encoder(device)
-        z = _CACHE.get("z", rna, device,
-                       lambda: vae.encode_mean(rna.to(device, non_blocking=True)))
+        z = _CACHE.get("z", rna, device, lambda: vae.encode_mean(rna.to(device, non_blocking=True)))
         noise = torch.FloatTensor(B, generator.encoding_dims).uniform_(-0.3, 0.3)
-        eng = generator._engine()
-        noise_d = eng.bufs.get("noise", (B, generator.encoding_dims), F32)
+        noise_d = generator._engine().bufs.get("noise", (B, generator.encoding_dims), F32)
         noise_d.copy_(noise, non_blocking=False)
-        lat = eng.bufs.get("lat", (B, generator.encoding_dims), BF16)
-        ops.latent_prep(noise_d, z, lat_bf16=lat)
-        return B, lat
+        return noise_d, z
 
     @staticmethod
     def _real(real_inputs, device):
@@ -146,10 +142,6 @@ def _check_labels(labels, *nets):
                                       "drivers exercise, SURVEY.md Appendix B.10)")
 
 
-def _loss_buf(gen_engine):
-    return gen_engine.bufs.get("loss", (1,), F32)
-
-
 # ------------------------------------------------------------------------------------------------ loss objects
 class WassersteinGeneratorLossVAE(_VAEConditioned, GeneratorLoss):
     def __init__(self, checkpoint, rna_features, beta=0.005):
@@ -163,17 +155,8 @@ class WassersteinGeneratorLossVAE(_VAEConditioned, GeneratorLoss):
 
     def train_ops(self, generator, discriminator, optimizer_generator, device, batch_size, real_inputs, labels=None):
         _check_labels(labels, generator)
-        B, lat = self._latent(generator, real_inputs, device)
-        ge, de = generator._engine(), discriminator._engine()
-        fake = ge.forward(lat, tag="g", training=generator.training)
-        out = de.forward(fake, tag="gstep", training=discriminator.training)
-        loss = _loss_buf(ge)
-        ops.wgan_loss(out, -1.0, loss)                                   # mean(-D(G(z)))
-        d_img = de.backward(B, -1.0 / B, tag="gstep", params=False, want_dimg=True)
-        ge.backward(lat, d_img, fake, tag="g")
-        _allreduce_grads(generator)
-        adam_step(optimizer_generator)
-        ge.pack()
+        noise_d, z = self._inputs(generator, real_inputs, device)
+        loss = steps.g_step(generator, discriminator, optimizer_generator, noise_d, z, allreduce=_allreduce_grads)
         return loss.item()
 
 
@@ -187,24 +170,11 @@ class WassersteinDiscriminatorLossVAE(_VAEConditioned, DiscriminatorLoss):
         return wasserstein_discriminator_loss_vae(fx, fgz, self.reduction)
 
     def train_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
-        ge, de = generator._engine(), discriminator._engine()
-        if self.clip is not None:                                        # src/wgan_loss.py:213-215
-            for p in discriminator.parameters():
-                ops.clamp_(p.data, self.clip[0], self.clip[1])
-            de.pack()
         _check_labels(labels, generator, discriminator)
-        B, lat = self._latent(generator, real_inputs, device)
+        noise_d, z = self._inputs(generator, real_inputs, device)
         real = self._real(real_inputs, device)
-        out_real = de.forward(real, tag="real", training=discriminator.training)
-        fake = ge.forward(lat, tag="g", training=generator.training)
-        out_fake = de.forward(fake, tag="fake", training=discriminator.training)
-        loss = _loss_buf(ge)
-        ops.wgan_loss(out_fake, 1.0, loss, b=out_real, sign_b=-1.0)      # mean(D(G(z)) - D(x))
-        de.backward(B, -1.0 / B, tag="real", params=True, acc=0.0)
-        de.backward(B, 1.0 / B, tag="fake", params=True, acc=1.0)
-        _allreduce_grads(discriminator)
-        adam_step(optimizer_discriminator)
-        de.pack()
+        loss = steps.critic_step(generator, discriminator, optimizer_discriminator, noise_d, z, real, clip=self.clip,
+                                 allreduce=_allreduce_grads)
         return loss.item()
 
 
@@ -221,17 +191,13 @@ class WassersteinGradientPenaltyVAE(_VAEConditioned, DiscriminatorLoss):
 
     def train_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
         _check_labels(labels, generator, discriminator)
-        ge, de = generator._engine(), discriminator._engine()
-        B, lat = self._latent(generator, real_inputs, device)
+        noise_d, z = self._inputs(generator, real_inputs, device)
         real = self._real(real_inputs, device)
-        fake = ge.forward(lat, tag="g", training=generator.training)
         eps = torch.rand(1)                                              # one scalar per step, src/wgan_loss.py:376
-        eps_d = de.bufs.get("eps", (1,), F32)
+        eps_d = discriminator._engine().bufs.get("eps", (1,), F32)
         eps_d.copy_(eps)
-        out3 = de.gradient_penalty(real, fake, eps_d, lambd=self.lambd)
-        _allreduce_grads(discriminator)
-        adam_step(optimizer_discriminator)
-        de.pack()
+        out3 = steps.gp_step(generator, discriminator, optimizer_discriminator, noise_d, z, real, eps_d,
+                             lambd=self.lambd, allreduce=_allreduce_grads)
         return out3[0].item()
 
 
