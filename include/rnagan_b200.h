@@ -129,8 +129,15 @@ int rg_latent_prep(const float* noise, const float* z, int B, int E, int z_rows,
  * mode 0: x*mul; mode 1: (eps*x + (1-eps)*y)*mul (src/wgan_loss.py:377); mode 2: x*(1-y^2)*mul (tanh backward). */
 int rg_im2col_img(const float* x, const float* y, int mode, const float* eps_dev, const float* mul_dev, int B,
                   int Cimg, int S, void* col, float* mixed_out, rg_stream_t st);
-int rg_img_channel_sum(const float* x, const float* y, int mode, int B, int Cimg, int S, float* out, float acc,
-                       rg_stream_t st);
+int rg_img_channel_sum(const float* x, const float* y, int mode, int B, int Cimg, int S, float* partial_ws,
+                       int partial_len, float* out, float acc, rg_stream_t st);
+/* image-side transposed conv in "dgrad form": col[pix][tap*Cimg+c] (fp32, from rg_gemm_nt with w_colT) is folded back
+ * onto the 2x larger image: img[b,c,y,x] = act(bias[c] + sum of the 4 taps hitting (y,x)); fp32 NCHW output.
+ * Generator last layer (ConvTranspose2d(64,3,4,2,1)+Tanh, src/dcgan.py:82) and the critic's layer-0 dgrad. */
+int rg_col2im_img(const float* col, int ldc, const float* bias, int act_tanh, int B, int Cimg, int H, int W, float* img,
+                  rg_stream_t st);
+/* W[Cp][Cimg][4][4] -> bf16 w_colT[rows][Cp], row n = tap*Cimg + c (rows beyond 16*Cimg zero) */
+int rg_pack_edge_t(const float* W, void* w_colT, int Cp, int Cimg, int rows, rg_stream_t st);
 int rg_unpack_edge_grad(const float* dcol, float* dW, int Cp, int Cimg, float acc, rg_stream_t st);
 /* critic head `disc` = Conv2d(C,1,4,1,0)+LeakyReLU on a 4x4 map (torchgan DCGANDiscriminator): w_head[k=tap*C+c] */
 int rg_pack_head(const float* W, float* w_head, int C, rg_stream_t st);

@@ -49,7 +49,9 @@ SIGNATURES = {
     "rg_bn_gp_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "rg_latent_prep": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "rg_im2col_img": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
-    "rg_img_channel_sum": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _f, _vp]),
+    "rg_img_channel_sum": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _f, _vp]),
+    "rg_col2im_img": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rg_pack_edge_t": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rg_unpack_edge_grad": (_i, [_vp, _vp, _i, _i, _f, _vp]),
     "rg_pack_head": (_i, [_vp, _vp, _i, _vp]),
     "rg_head_fwd": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp]),

@@ -110,7 +110,7 @@ static const int kUpK[2][2] = {{1, 3}, {2, 0}};
 
 static int pick_block_n(int n_total, int tiles_per_n) {
   int bn = 256;
-  while (bn > n_total && bn > 16) bn >>= 1;
+  while ((bn >> 1) >= n_total && bn > 16) bn >>= 1;   // smallest power of two >= n_total (rows beyond zero-fill)
   const int target = (num_sms() * 4) / 5;
   while (bn > 64 && ceil_div(n_total, bn) * tiles_per_n < target) bn >>= 1;
   return bn;
@@ -172,17 +172,35 @@ static int encode_parity_maps(GemmMaps& maps, const void* hi, int B, int H, int 
 }
 
 // ------------------------------------------------------------------------------------------------ reduce kernel
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dW, int splits, int taps,
-                                    int Cp, int Cs, float alpha, const float* __restrict__ alpha_dev, float beta) {
+template <int TAPS>
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dW,
+                                                           int splits, int Cp, int Cs, float alpha,
+                                                           const float* __restrict__ alpha_dev, float beta) {
   const size_t n = static_cast<size_t>(Cp) * Cs;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const float a = alpha * (alpha_dev ? __ldg(alpha_dev) : 1.0f);
-  for (int t = 0; t < taps; ++t) {
-    float acc = 0.0f;
-    for (int sp = 0; sp < splits; ++sp) acc += ws[(static_cast<size_t>(sp) * taps + t) * n + idx];
-    const size_t o = idx * taps + t;
-    dW[o] = (beta != 0.0f ? beta * dW[o] : 0.0f) + a * acc;
+  float acc[TAPS];
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) acc[t] = 0.0f;
+  for (int sp = 0; sp < splits; ++sp) {
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) acc[t] += ws[(static_cast<size_t>(sp) * TAPS + t) * n + idx];
+  }
+  float* o = dW + idx * TAPS;
+  if (TAPS % 4 == 0) {
+#pragma unroll
+    for (int t = 0; t < TAPS; t += 4) {
+      float4 v = make_float4(a * acc[t], a * acc[t + 1], a * acc[t + 2], a * acc[t + 3]);
+      if (beta != 0.0f) {
+        const float4 old = *reinterpret_cast<const float4*>(o + t);
+        v.x += beta * old.x; v.y += beta * old.y; v.z += beta * old.z; v.w += beta * old.w;
+      }
+      *reinterpret_cast<float4*>(o + t) = v;
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) o[t] = (beta != 0.0f ? beta * o[t] : 0.0f) + a * acc[t];
   }
 }
 
@@ -235,8 +253,12 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
   gemm_wgrad_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
   RG_LAUNCH_CHECK("gemm_wgrad_kernel");
   const size_t n = static_cast<size_t>(Cp) * Cs;
-  wgrad_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, w.taps, Cp, Cs,
-                                                                              alpha, alpha_dev, beta);
+  if (w.taps == 16)
+    wgrad_reduce_kernel<16><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, alpha,
+                                                                                    alpha_dev, beta);
+  else
+    wgrad_reduce_kernel<1><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, alpha,
+                                                                                   alpha_dev, beta);
   RG_LAUNCH_CHECK("wgrad_reduce_kernel");
   return 0;
 }

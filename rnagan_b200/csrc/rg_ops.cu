@@ -90,13 +90,23 @@ __global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int r
     }
   }
 }
-// Stage 2: out[k][c] = sum_blocks partial[block][k][c] (fixed order)
-__global__ void colreduce_stage2(const float* __restrict__ partial, int nblocks, int KC, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= KC) return;
+// Stage 2: out[k][c] = sum_blocks partial[block][k][c]; 32 columns x 8 block-lanes per CTA, summed in a fixed order
+__global__ void __launch_bounds__(256) colreduce_stage2(const float* __restrict__ partial, int nblocks, int KC,
+                                                        float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cx;
   float s = 0.0f;
-  for (int b = 0; b < nblocks; ++b) s += partial[static_cast<size_t>(b) * KC + i];
-  out[i] = s;
+  if (i < KC)
+    for (int b = g; b < nblocks; b += 8) s += partial[static_cast<size_t>(b) * KC + i];
+  sm[g][cx] = s;
+  __syncthreads();
+  if (g == 0 && i < KC) {
+    float t = sm[0][cx];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) t += sm[l][cx];
+    out[i] = t;
+  }
 }
 
 struct ReducePlan {
@@ -107,7 +117,7 @@ static ReducePlan plan_reduce(int M, int C, int K) {
   ReducePlan p;
   const int cgs = C / 8;
   const int lanes = cgs >= 256 ? 1 : 256 / cgs;
-  int target = num_sms() * 4;
+  int target = num_sms() * 2;
   int rpb = std::max(lanes * 4, ceil_div(M, target));
   rpb = ceil_div(rpb, lanes) * lanes;
   p.rows_per_block = rpb;
@@ -142,7 +152,7 @@ static int run_colreduce(F f, int M, int C, float* ws, size_t ws_bytes, float* o
   }
   colreduce_stage1<F><<<p.blocks, 256, p.smem, st>>>(f, M, C, p.rows_per_block, ws);
   RG_LAUNCH_CHECK(name);
-  colreduce_stage2<<<ceil_div(K * C, 256), 256, 0, st>>>(ws, p.blocks, K * C, out);
+  colreduce_stage2<<<ceil_div(K * C, 32), 256, 0, st>>>(ws, p.blocks, K * C, out);
   RG_LAUNCH_CHECK(name);
   return 0;
 }
@@ -418,11 +428,12 @@ __global__ void im2col_img_kernel(const float* __restrict__ x, const float* __re
   // one thread per (pixel, kh): writes 4 taps x 4 channels = 16 bf16 = 32 bytes
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < npix * 4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int kh = static_cast<int>(i & 3);
-    const size_t pix = i >> 2;
-    const int wo = static_cast<int>(pix % Ho);
-    const int ho = static_cast<int>((pix / Ho) % Ho);
-    const int b = static_cast<int>(pix / (static_cast<size_t>(Ho) * Ho));
+    // index order (b, ho, kh, wo): neighbouring threads read neighbouring input pixels of the same row
+    const int wo = static_cast<int>(i % Ho);
+    const int kh = static_cast<int>((i / Ho) & 3);
+    const int ho = static_cast<int>((i / (4 * static_cast<size_t>(Ho))) % Ho);
+    const int b = static_cast<int>(i / (4 * static_cast<size_t>(Ho) * Ho));
+    const size_t pix = (static_cast<size_t>(b) * Ho + ho) * Ho + wo;
     const int yy = 2 * ho - 1 + kh;
     uint32_t packed[8];
 #pragma unroll
@@ -461,20 +472,22 @@ __global__ void im2col_img_kernel(const float* __restrict__ x, const float* __re
 }
 
 // per-channel sum over pixels of x (mode 0) or x*(1-y^2) (mode 2): bias gradient of the generator's last layer.
-// one block per (channel); deterministic tree.
-__global__ void img_channel_sum_kernel(const float* __restrict__ x, const float* __restrict__ y, int mode, int B,
-                                       int Cimg, int S, float* __restrict__ out, float acc) {
+// stage 1: grid (nblk, Cimg) -> partial[c][blk]; stage 2: one block per channel, fixed-order tree (deterministic).
+__global__ void __launch_bounds__(256) img_channel_sum_stage1(const float* __restrict__ x, const float* __restrict__ y,
+                                                              int mode, int B, int Cimg, int S,
+                                                              float* __restrict__ partial) {
   __shared__ float sm[256];
-  const int c = blockIdx.x;
+  const int c = blockIdx.y;
   const size_t plane = static_cast<size_t>(S) * S;
+  const size_t total = static_cast<size_t>(B) * plane;
   float s = 0.0f;
-  for (int b = 0; b < B; ++b) {
-    const size_t base = (static_cast<size_t>(b) * Cimg + c) * plane;
-    for (size_t i = threadIdx.x; i < plane; i += blockDim.x) {
-      float t = x[base + i];
-      if (mode == 2) { const float th = y[base + i]; t = t * (1.0f - th * th); }
-      s += t;
-    }
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / plane;
+    const size_t o = (b * Cimg + c) * plane + (i - b * plane);
+    float t = x[o];
+    if (mode == 2) { const float th = y[o]; t = t * (1.0f - th * th); }
+    s += t;
   }
   sm[threadIdx.x] = s;
   __syncthreads();
@@ -482,7 +495,70 @@ __global__ void img_channel_sum_kernel(const float* __restrict__ x, const float*
     if (threadIdx.x < w) sm[threadIdx.x] += sm[threadIdx.x + w];
     __syncthreads();
   }
+  if (threadIdx.x == 0) partial[c * gridDim.x + blockIdx.x] = sm[0];
+}
+__global__ void __launch_bounds__(256) img_channel_sum_stage2(const float* __restrict__ partial, int nblk,
+                                                              float* __restrict__ out, float acc) {
+  __shared__ float sm[256];
+  const int c = blockIdx.x;
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) s += partial[c * nblk + i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sm[threadIdx.x] += sm[threadIdx.x + w];
+    __syncthreads();
+  }
   if (threadIdx.x == 0) out[c] = (acc != 0.0f ? acc * out[c] : 0.0f) + sm[0];
+}
+
+// col2im for the image-side transposed conv computed in "dgrad form": col[pix][n = tap*Cimg + c] (fp32) holds each
+// low-res pixel's contribution to its 4x4 output patch; out[b][c][y][x] = act(bias[c] + sum of the 4 taps that hit it).
+__global__ void __launch_bounds__(256) col2im_img_kernel(const float* __restrict__ col, int ldc,
+                                                         const float* __restrict__ bias, int act_tanh, int B, int Cimg,
+                                                         int H, int W, float* __restrict__ img) {
+  const int OH = 2 * H, OW = 2 * W;
+  const size_t n = static_cast<size_t>(B) * OH * OW;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % OW);
+    const int y = static_cast<int>((i / OW) % OH);
+    const int b = static_cast<int>(i / (static_cast<size_t>(OW) * OH));
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    // y = 2*ii - 1 + kh  ->  kh has the parity of (y + 1); two candidates each for rows and columns
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int kh = ((y + 1) & 1) + 2 * a;
+      const int ii = (y + 1 - kh) >> 1;
+      if (ii < 0 || ii >= H) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int kw = ((x + 1) & 1) + 2 * e;
+        const int jj = (x + 1 - kw) >> 1;
+        if (jj < 0 || jj >= W) continue;
+        const float* src = col + ((static_cast<size_t>(b) * H + ii) * W + jj) * ldc + (kh * 4 + kw) * Cimg;
+        for (int c = 0; c < Cimg; ++c) acc[c] += __ldg(src + c);
+      }
+    }
+    for (int c = 0; c < Cimg; ++c) {
+      float v = acc[c] + (bias ? __ldg(bias + c) : 0.0f);
+      if (act_tanh) v = tanhf(v);
+      img[((static_cast<size_t>(b) * Cimg + c) * OH + y) * OW + x] = v;
+    }
+  }
+}
+// W[Cp][Cimg][16] -> w_colT[n = tap*Cimg + c][Cp] bf16 (rows >= 16*Cimg zero): B operand of the dgrad-form GEMM
+__global__ void pack_edge_t_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int Cp, int Cimg,
+                                   int rows) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Cp) return;
+  const int n = idx / Cp, p = idx - n * Cp;
+  float v = 0.0f;
+  if (n < 16 * Cimg) {
+    const int tap = n / Cimg, c = n - tap * Cimg;
+    v = W[(static_cast<size_t>(p) * Cimg + c) * 16 + tap];
+  }
+  out[idx] = __float2bfloat16(v);
 }
 
 // dW[p][c][kh][kw] (fp32 torch layout) (+)= dWcol[p][k = tap*4 + c]
@@ -618,18 +694,42 @@ struct AdamChunk {
 };
 // torch.optim.Adam (no amsgrad, no weight decay), src/histopathology_gan.py:252,257:
 //   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
-__global__ void adam_kernel(const AdamChunk* __restrict__ chunks, float lr, float b1, float b2, float eps, float bc1,
-                            float bc2_sqrt, float clamp_lo, float clamp_hi, int do_clamp) {
+__global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__ chunks, float lr, float b1, float b2,
+                                                   float eps, float bc1, float bc2_sqrt, float clamp_lo, float clamp_hi,
+                                                   int do_clamp) {
   const AdamChunk ch = chunks[blockIdx.x];
   const float step = lr / bc1;
-  for (int i = threadIdx.x; i < ch.n; i += blockDim.x) {
+  const float ob1 = 1.0f - b1, ob2 = 1.0f - b2;
+  const int n4 = ((reinterpret_cast<uintptr_t>(ch.p) | reinterpret_cast<uintptr_t>(ch.g) |
+                   reinterpret_cast<uintptr_t>(ch.m) | reinterpret_cast<uintptr_t>(ch.v)) & 15) == 0 ? (ch.n >> 2) : 0;
+  float4* p4 = reinterpret_cast<float4*>(ch.p);
+  const float4* g4 = reinterpret_cast<const float4*>(ch.g);
+  float4* m4 = reinterpret_cast<float4*>(ch.m);
+  float4* v4 = reinterpret_cast<float4*>(ch.v);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 p = p4[i], m = m4[i], v = v4[i];
+    const float4 g = g4[i];
+    float* pp = reinterpret_cast<float*>(&p);
+    float* mm = reinterpret_cast<float*>(&m);
+    float* vv = reinterpret_cast<float*>(&v);
+    const float* gg = reinterpret_cast<const float*>(&g);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      mm[e] = b1 * mm[e] + ob1 * gg[e];
+      vv[e] = b2 * vv[e] + ob2 * gg[e] * gg[e];
+      float q = pp[e] - step * (mm[e] / (sqrtf(vv[e]) / bc2_sqrt + eps));
+      if (do_clamp) q = fminf(fmaxf(q, clamp_lo), clamp_hi);
+      pp[e] = q;
+    }
+    p4[i] = p; m4[i] = m; v4[i] = v;
+  }
+  for (int i = n4 * 4 + threadIdx.x; i < ch.n; i += blockDim.x) {
     const float g = ch.g[i];
-    const float m = b1 * ch.m[i] + (1.0f - b1) * g;
-    const float v = b2 * ch.v[i] + (1.0f - b2) * g * g;
+    const float m = b1 * ch.m[i] + ob1 * g;
+    const float v = b2 * ch.v[i] + ob2 * g * g;
     ch.m[i] = m;
     ch.v[i] = v;
-    const float denom = sqrtf(v) / bc2_sqrt + eps;
-    float p = ch.p[i] - step * (m / denom);
+    float p = ch.p[i] - step * (m / (sqrtf(v) / bc2_sqrt + eps));
     if (do_clamp) p = fminf(fmaxf(p, clamp_lo), clamp_hi);
     ch.p[i] = p;
   }
@@ -784,11 +884,34 @@ int rg_im2col_img(const float* x, const float* y, int mode, const float* eps_dev
   return 0;
 }
 
-int rg_img_channel_sum(const float* x, const float* y, int mode, int B, int Cimg, int S, float* out, float acc,
-                       rg_stream_t st) {
-  RG_CHECK_ARG(x && out && (mode == 0 || y), "rg_img_channel_sum: bad arguments");
-  img_channel_sum_kernel<<<Cimg, 256, 0, static_cast<cudaStream_t>(st)>>>(x, y, mode, B, Cimg, S, out, acc);
-  RG_LAUNCH_CHECK("rg_img_channel_sum");
+int rg_img_channel_sum(const float* x, const float* y, int mode, int B, int Cimg, int S, float* partial_ws,
+                       int partial_len, float* out, float acc, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(x && out && partial_ws && (mode == 0 || y), "rg_img_channel_sum: bad arguments");
+  const int nblk = std::min(256, partial_len / std::max(Cimg, 1));
+  RG_CHECK_ARG(nblk >= 1, "rg_img_channel_sum: partial workspace too small");
+  img_channel_sum_stage1<<<dim3(nblk, Cimg), 256, 0, st>>>(x, y, mode, B, Cimg, S, partial_ws);
+  RG_LAUNCH_CHECK("rg_img_channel_sum(stage1)");
+  img_channel_sum_stage2<<<Cimg, 256, 0, st>>>(partial_ws, nblk, out, acc);
+  RG_LAUNCH_CHECK("rg_img_channel_sum(stage2)");
+  return 0;
+}
+
+int rg_col2im_img(const float* col, int ldc, const float* bias, int act_tanh, int B, int Cimg, int H, int W, float* img,
+                  rg_stream_t st) {
+  RG_CHECK_ARG(col && img && Cimg >= 1 && Cimg <= 4 && ldc >= 16 * Cimg, "rg_col2im_img: bad arguments");
+  const size_t n = static_cast<size_t>(B) * 4 * H * W;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  col2im_img_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(col, ldc, bias, act_tanh, B, Cimg, H, W, img);
+  RG_LAUNCH_CHECK("rg_col2im_img");
+  return 0;
+}
+
+int rg_pack_edge_t(const float* W, void* w_colT, int Cp, int Cimg, int rows, rg_stream_t st) {
+  RG_CHECK_ARG(W && w_colT && Cimg >= 1 && Cimg <= 4 && rows >= 16 * Cimg, "rg_pack_edge_t: bad arguments");
+  pack_edge_t_kernel<<<ceil_div(rows * Cp, 256), 256, 0, static_cast<cudaStream_t>(st)>>>(
+      W, static_cast<bf16*>(w_colT), Cp, Cimg, rows);
+  RG_LAUNCH_CHECK("rg_pack_edge_t");
   return 0;
 }
 

@@ -142,7 +142,7 @@ class GeneratorEngine:
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
             self.w_up.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev))
             self.w_down.append(torch.empty(Cp, 16 * Cs, dtype=BF16, device=dev))
-        self.w_up_last = torch.zeros(4, 16, 4 * self.Cn, dtype=BF16, device=dev)
+        self.w_colT_last = torch.zeros(16 * self.Cimg, self.Cn, dtype=BF16, device=dev)
         self.w_col_last = torch.empty(self.Cn, 64, dtype=BF16, device=dev)
         self.pack()
 
@@ -151,7 +151,7 @@ class GeneratorEngine:
         ops.pack_proj(self.conv0.weight.detach(), self.w_proj)
         for c, wu, wd in zip(self.convs, self.w_up, self.w_down):
             ops.pack_link(c.weight.detach(), wd, wu)
-        ops.pack_link(self.conv_last.weight.detach(), None, self.w_up_last, want_down=False)
+        ops.pack_edge_t(self.conv_last.weight.detach(), self.w_colT_last)
         ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
 
     def forward(self, lat, tag="g", training=True, out=None):
@@ -172,7 +172,8 @@ class GeneratorEngine:
             bn.forward(a, h, B * H * H, training, tag=tag)
         if out is None:
             out = g(f"{tag}.img", (B, self.Cimg, 2 * H, 2 * H), F32)
-        ops.conv_up_img(h, self.w_up_last, self.Cimg, bias=self.conv_last.bias.detach(), act_tanh=True, out=out)
+        col = g("fwd.colimg", (B * H * H, 16 * self.Cimg), F32)
+        ops.conv_up_img_col(h, self.w_colT_last, self.Cimg, col, out, bias=self.conv_last.bias.detach(), act_tanh=True)
         return out
 
     def backward(self, lat, d_img, img, tag="g"):
@@ -243,7 +244,7 @@ class CriticEngine:
         if self.C0 % 64:
             raise NotImplementedError("channel counts must be multiples of 64 on the sm_100a path")
         self.w_col0 = torch.empty(self.C0, 64, dtype=BF16, device=dev)
-        self.w_up0 = torch.zeros(4, 16, 4 * self.C0, dtype=BF16, device=dev)
+        self.w_colT0 = torch.zeros(16 * self.Cimg, self.C0, dtype=BF16, device=dev)
         self.w_down, self.w_up = [], []
         for c in self.convs:
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
@@ -257,7 +258,7 @@ class CriticEngine:
 
     def pack(self):
         ops.pack_edge(self.conv0.weight.detach(), self.w_col0)
-        ops.pack_link(self.conv0.weight.detach(), None, self.w_up0, want_down=False)
+        ops.pack_edge_t(self.conv0.weight.detach(), self.w_colT0)
         for c, wd, wu in zip(self.convs, self.w_down, self.w_up):
             ops.pack_link(c.weight.detach(), wd, wu)
         ops.pack_head(self.head.weight.detach(), self.w_head)
@@ -329,7 +330,8 @@ class CriticEngine:
             ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=acc)
         if want_dimg:
             dimg = g(f"{tag}.dimg", (B, self.Cimg, 2 * H, 2 * H), F32)
-            ops.conv_up_img(da0, self.w_up0, self.Cimg, out=dimg)
+            colimg = g("bwd.colimg", (npix, 16 * self.Cimg), F32)
+            ops.conv_up_img_col(da0, self.w_colT0, self.Cimg, colimg, dimg)
             return dimg
         return None
 

@@ -272,10 +272,35 @@ def im2col_img(x, col, y=None, mode=0, eps_dev=None, mul_dev=None, mixed_out=Non
                                         _p(mixed_out), _st()), "rg_im2col_img")
 
 
+_partial_cache = {}
+
+
 def img_channel_sum(x, out, y=None, mode=0, acc=0.0):
     B, Cimg, S, _ = x.shape
-    _lib.check(_lib.lib().rg_img_channel_sum(_p(x), _p(y), mode, B, Cimg, S, _p(out), float(acc), _st()),
-               "rg_img_channel_sum")
+    part = _partial_cache.get(x.device.index)
+    if part is None:
+        part = torch.empty(1024, dtype=F32, device=x.device)
+        _partial_cache[x.device.index] = part
+    _lib.check(_lib.lib().rg_img_channel_sum(_p(x), _p(y), mode, B, Cimg, S, _p(part), part.numel(), _p(out),
+                                             float(acc), _st()), "rg_img_channel_sum")
+
+
+def pack_edge_t(W, out):
+    """W fp32 [Cp, Cimg, 4, 4] -> bf16 [rows, Cp] (row = tap*Cimg + c), B operand of the dgrad-form image GEMM."""
+    Cp, Cimg = W.shape[0], W.shape[1]
+    _lib.check(_lib.lib().rg_pack_edge_t(_p(W), _p(out), Cp, Cimg, out.shape[0], _st()), "rg_pack_edge_t")
+    return out
+
+
+def conv_up_img_col(lo, w_colT, Cimg, col, out, bias=None, act_tanh=False):
+    """Image-side transposed conv as GEMM (K = Cp only, each input pixel read once) + col2im:
+    lo bf16 [B, H, W, Cp] -> out fp32 NCHW [B, Cimg, 2H, 2W]; col: fp32 scratch [B*H*W, 16*Cimg]."""
+    B, H, W, Cp = lo.shape
+    N = 16 * Cimg
+    gemm_nt(lo.view(B * H * W, Cp), w_colT, out=col, N=N)
+    _lib.check(_lib.lib().rg_col2im_img(_p(col), col.stride(0), _p(bias), int(act_tanh), B, Cimg, H, W, _p(out),
+                                        _st()), "rg_col2im_img")
+    return out
 
 
 def unpack_edge_grad(dcol, dW, acc=0.0):

@@ -156,3 +156,42 @@ def test_pack_edge(cuda_dev):
     ref = _bf(Wt).permute(0, 2, 3, 1).reshape(64, 16, 3)
     assert torch.equal(wc[:, :, :3], ref)
     assert wc[:, :, 3].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("B,H,W,Cp", [(4, 32, 32, 64), (2, 128, 128, 64)])
+def test_conv_up_img_col(cuda_dev, B, H, W, Cp):
+    """image-side transposed conv as dgrad-form GEMM + col2im (rg_gemm_nt + rg_col2im_img)."""
+    from rnagan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B + H + 7)
+    x = _bf(torch.randn(B, Cp, H, W, generator=g)).to(cuda_dev)
+    Wt = _bf(torch.randn(Cp, 3, 4, 4, generator=g) * 0.05).to(cuda_dev)
+    bias = torch.randn(3, generator=g).to(cuda_dev)
+    ref = torch.tanh(F.conv_transpose2d(x, Wt, bias=bias, stride=2, padding=1))
+    wT = ops.pack_edge_t(Wt, torch.zeros(48, Cp, dtype=torch.bfloat16, device=cuda_dev))
+    col = torch.empty(B * H * W, 48, device=cuda_dev)
+    out = torch.empty(B, 3, 2 * H, 2 * W, device=cuda_dev)
+    ops.conv_up_img_col(_nhwc(x), wT, 3, col, out, bias=bias, act_tanh=True)
+    assert (out - ref).abs().max().item() < 2e-3
+    ops.conv_up_img_col(_nhwc(x), wT, 3, col, out)
+    assert _rel(out, F.conv_transpose2d(x, Wt, stride=2, padding=1)) < 2e-3
+
+
+def test_img_channel_sum_and_im2col(cuda_dev):
+    from rnagan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(5, 3, 64, 64, generator=g).to(cuda_dev)
+    y = torch.tanh(torch.randn(5, 3, 64, 64, generator=g)).to(cuda_dev)
+    out = torch.zeros(3, device=cuda_dev)
+    ops.img_channel_sum(x, out, y=y, mode=2)
+    ref = (x * (1 - y * y)).sum(dim=(0, 2, 3))
+    assert _rel(out, ref) < 1e-4
+    # im2col: col[pix][tap*4+c] equals unfold of the (eps-mixed) image
+    eps = torch.tensor([0.3], device=cuda_dev)
+    col = torch.empty(5 * 32 * 32, 64, dtype=torch.bfloat16, device=cuda_dev)
+    ops.im2col_img(x, col, y=y, mode=1, eps_dev=eps)
+    mixed = 0.3 * x + 0.7 * y
+    unf = F.unfold(mixed, kernel_size=4, stride=2, padding=1)            # [B, 3*16, L] index c*16+tap
+    unf = unf.view(5, 3, 16, 32 * 32).permute(0, 3, 2, 1)                   # [B, L, tap, c]
+    got = col.float().view(5, 32 * 32, 16, 4)
+    assert (got[..., :3] - _bf(unf)).abs().max().item() < 1e-6
+    assert got[..., 3].abs().max().item() == 0

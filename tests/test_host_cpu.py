@@ -1,0 +1,165 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/rnagan_b200.h declares, the
+ctypes table matches the header, the product refuses to run without CUDA (no fallback), host logic of the trainer /
+data-parallel plumbing (gloo, world_size 2), state_dict layout equals the reference layout."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "rnagan_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rnagan_b200 import _lib
+    if _lib._needs_build():
+        _lib.build()
+    lib = _lib.lib()
+    names = _header_functions()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/rnagan_b200.h but not exported by the .so"
+        assert n in _lib.SIGNATURES, f"{n} missing from the ctypes signature table"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.rg_version() >= 100
+    assert lib.rg_launch_count() == 0          # loading launches nothing; no compute without a GPU
+
+
+def test_size_queries_work_without_gpu():
+    from rnagan_b200 import _lib
+    lib = _lib.lib()
+    assert lib.rg_conv_wgrad_ws_bytes(64, 64, 64, 128, 64) > 0
+    assert lib.rg_gemm_tn_ws_bytes(1 << 20, 64, 64) > 0
+    assert lib.rg_reduce_ws_bytes(1 << 20, 64) > 0
+    assert lib.rg_adam_table_bytes(10) == 10 * 40
+
+
+def test_no_cpu_fallback():
+    from rnagan_b200 import dcgan, ops
+    from rnagan_b200.betaVAE import betaVAE
+    G = dcgan.DCGANGenerator(2048, 32, 3, 64)
+    D = dcgan.DCGANDiscriminator(32, 3, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G(torch.randn(2, 2048))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        D(torch.randn(2, 3, 32, 32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        betaVAE(32, 2048, [6000, 4000, 2048], [4000, 6000]).eval().encode(torch.randn(2, 32))
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        ops.gemm_nt(torch.zeros(64, 64, dtype=torch.bfloat16), torch.zeros(64, 64, dtype=torch.bfloat16))
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under rnagan_b200/ may import or execute it."""
+    pkg = os.path.join(ROOT, "rnagan_b200")
+    pat = re.compile(r"^\s*(from|import)\s+\.*oracle\b|importlib.*oracle|ref_oracle", re.M)
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert not pat.search(open(os.path.join(pkg, fn)).read()), fn
+
+
+def test_state_dict_layout_matches_reference_layout():
+    from oracle import ref_oracle as O
+    from rnagan_b200 import dcgan
+    from rnagan_b200.betaVAE import betaVAE
+    pairs = [(dcgan.DCGANGenerator(2048, 64, 3, 64), O.OracleGenerator(2048, 64, 3, 64)),
+             (dcgan.DCGANDiscriminator(64, 3, 64), O.OracleCritic(64, 3, 64)),
+             (dcgan.DCGANUpGenerator(2048, 32, 3, 64), O.OracleUpGenerator(2048, 32, 3, 64)),
+             (betaVAE(100, 2048, [6000, 4000, 2048], [4000, 6000]), O.OracleVAE(100))]
+    for mine, ref in pairs:
+        a, b = mine.state_dict(), ref.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, k
+    # SURVEY.md Appendix D spot checks
+    sd = dcgan.DCGANGenerator(2048, 256, 3, 64).state_dict()
+    assert tuple(sd["model.0.0.weight"].shape) == (2048, 2048, 4, 4)
+    assert tuple(sd["model.6.0.weight"].shape) == (64, 3, 4, 4) and tuple(sd["model.6.0.bias"].shape) == (3,)
+    sd = dcgan.DCGANDiscriminator(256, 3, 64).state_dict()
+    assert tuple(sd["model.5.0.weight"].shape) == (2048, 1024, 4, 4) and tuple(sd["disc.0.weight"].shape) == (1, 2048, 4, 4)
+
+
+def test_reference_constructor_errors():
+    from rnagan_b200 import dcgan
+    for cls in (dcgan.DCGANGenerator, dcgan.DCGANUpGenerator):
+        with pytest.raises(Exception, match="Target Image Size must be at least 16\\*16 and an exact power of 2"):
+            cls(out_size=24)
+    with pytest.raises(Exception, match="at least 16\\*16 and an exact power of 2"):
+        dcgan.DCGANDiscriminator(in_size=8)
+
+
+def test_trainer_binds_train_ops_by_parameter_name():
+    from rnagan_b200 import wgan_loss
+    from rnagan_b200.trainer import Trainer
+    import inspect
+    g = list(inspect.signature(wgan_loss.WassersteinGeneratorLossVAE.train_ops).parameters)
+    d = list(inspect.signature(wgan_loss.WassersteinDiscriminatorLossVAE.train_ops).parameters)
+    p = list(inspect.signature(wgan_loss.WassersteinGradientPenaltyVAE.train_ops).parameters)
+    assert g == ["self", "generator", "discriminator", "optimizer_generator", "device", "batch_size", "real_inputs", "labels"]
+    assert d == p == ["self", "generator", "discriminator", "optimizer_discriminator", "real_inputs", "device", "labels"]
+
+    calls = []
+
+    class FakeG(wgan_loss.GeneratorLoss):
+        def train_ops(self, generator, optimizer_generator, real_inputs, labels=None):
+            calls.append(("g", generator, optimizer_generator, real_inputs))
+            return 1.0
+
+    class FakeD(wgan_loss.DiscriminatorLoss):
+        def train_ops(self, discriminator, device, batch_size):
+            calls.append(("d", discriminator, str(device), batch_size))
+            return 2.0
+
+    net = {"generator": {"name": torch.nn.Linear, "args": {"in_features": 2, "out_features": 2},
+                         "optimizer": {"name": torch.optim.Adam, "args": {"lr": 1e-3}}},
+           "discriminator": {"name": torch.nn.Linear, "args": {"in_features": 2, "out_features": 1},
+                             "optimizer": {"name": torch.optim.Adam, "args": {"lr": 1e-3}}}}
+    tr = Trainer(net, [FakeG(), FakeD()], device="cpu", devices=[0])
+    tr.real_inputs, tr.batch_size = {"image": torch.zeros(3, 1)}, 3
+    out = tr.train_iter()
+    assert out == {"FakeG": 1.0, "FakeD": 2.0}
+    assert calls[0][0] == "g" and calls[0][1] is tr.generator and calls[1] == ("d", tr.discriminator, "cpu", 3)
+    assert tr.devices == [0]                      # unknown kwargs become attributes, like torchgan
+    assert tr.loss_information["generator_iters"] == 1 and tr.loss_information["discriminator_iters"] == 1
+
+
+def test_shard_range_partitions_units():
+    from rnagan_b200.parallel import shard_range
+    for n, w in [(100000, 8), (10, 3), (5, 8), (0, 2)]:
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from rnagan_b200.parallel import allreduce_mean_, init_from_env
+rank, world = init_from_env(backend="gloo")
+torch.manual_seed(rank)
+ts = [torch.full((5,), float(rank + 1)), torch.full((3, 2), float(10 * (rank + 1))), torch.arange(4.0) * (rank + 1)]
+allreduce_mean_(ts, bucket_bytes=40)       # tiny buckets: exercises the multi-bucket path
+exp = [torch.full((5,), 1.5), torch.full((3, 2), 15.0), torch.arange(4.0) * 1.5]
+ok = all(torch.allclose(a, b) for a, b in zip(ts, exp))
+dist.barrier(); dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_gradient_allreduce_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)))
+             for r in range(2)]
+    codes = [p.wait(timeout=180) for p in procs]
+    assert codes == [0, 0]

@@ -1,0 +1,150 @@
+"""GPU parity of the drop-in modules (forward only), the encoder, checkpoint round trips and error behaviour."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("size,B", [(32, 8), (64, 4), (128, 2)])
+def test_generator_and_critic_forward(cuda_dev, size, B):
+    from rnagan_b200 import dcgan
+    lrelu, tanh = torch.nn.LeakyReLU(0.2), torch.nn.Tanh()
+    oG = O.OracleGenerator(2048, size, 3, 64, nonlinearity=lrelu, last_nonlinearity=tanh)
+    oD = O.OracleCritic(size, 3, 64, nonlinearity=lrelu, last_nonlinearity=lrelu)
+    O.reinit_(oG, 1); O.reinit_(oD, 2)
+    G = dcgan.DCGANGenerator(2048, size, 3, 64, nonlinearity=torch.nn.LeakyReLU(0.2),
+                             last_nonlinearity=torch.nn.Tanh()).to(cuda_dev)
+    D = dcgan.DCGANDiscriminator(size, 3, 64, nonlinearity=torch.nn.LeakyReLU(0.2),
+                                 last_nonlinearity=torch.nn.LeakyReLU(0.2)).to(cuda_dev)
+    G.load_state_dict(oG.state_dict()); D.load_state_dict(oD.state_dict())
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(B, 2048, generator=g)
+    x = torch.rand(B, 3, size, size, generator=g) * 2 - 1
+    for mode in ("train", "eval"):
+        getattr(oG, mode)(); getattr(oD, mode)(); getattr(G, mode)(); getattr(D, mode)()
+        with torch.no_grad():
+            ref_img, ref_out = oG(z), oD(x)
+        img, out = G(z.to(cuda_dev)), D(x.to(cuda_dev))
+        assert img.shape == ref_img.shape and img.dtype == torch.float32
+        assert _rel(img, ref_img) <= 3e-2, mode
+        assert (out.cpu() - ref_out).abs().max().item() <= 0.03 + 0.03 * ref_out.abs().max().item(), mode
+    # train-mode forwards updated the running statistics like the reference's modules do
+    for (n, bo), (_, bm) in zip(oG.named_buffers(), G.named_buffers()):
+        if n.endswith("num_batches_tracked"):
+            assert int(bo) == int(bm) == 1
+        else:
+            assert _rel(bm.float(), bo.float()) <= 2e-2, n
+    feat = D(x.to(cuda_dev), feature_matching=True)
+    with torch.no_grad():
+        assert feat.shape == oD(x, feature_matching=True).shape
+
+
+def test_encoder_matches_oracle(cuda_dev):
+    from rnagan_b200.betaVAE import betaVAE
+    feats, B = 300, 16
+    oV = O.OracleVAE(feats, beta=0.005).eval()
+    O.reinit_(oV, 23)
+    vae = betaVAE(feats, 2048, [6000, 4000, 2048], [4000, 6000], beta=0.005)
+    vae.load_state_dict(oV.state_dict())
+    vae = vae.to(cuda_dev).eval()
+    x = torch.randn(B, feats, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        zm, zl, h = oV.encode(x)
+    gm, gl, gh = vae.encode(x.to(cuda_dev))
+    assert _rel(gm, zm) <= 2e-2 and _rel(gl, zl) <= 2e-2 and _rel(gh, h) <= 2e-2
+    vae.train()
+    with pytest.raises(NotImplementedError):
+        vae.encode(x.to(cuda_dev))
+
+
+def test_latent_prep_matches_reference_formula(cuda_dev):
+    from rnagan_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    noise = torch.rand(16, 2048, generator=g) * 0.6 - 0.3
+    z = torch.randn(16, 2048, generator=g)
+    ref = O.latent_prep(noise, z)
+    lat = torch.empty(16, 2048, device=cuda_dev)
+    ops.latent_prep(noise.to(cuda_dev), z.to(cuda_dev), lat_f32=lat)
+    assert (lat.cpu() - ref).abs().max().item() <= 2e-5
+    # single profile broadcast (generate_images): conditioning cancels, SURVEY.md section 3.3
+    ref1 = O.latent_prep(noise, z[:1])
+    ops.latent_prep(noise.to(cuda_dev), z[:1].contiguous().to(cuda_dev), lat_f32=lat)
+    assert (lat.cpu() - ref1).abs().max().item() <= 2e-5
+    # B == 1 gives NaN like the reference (unbiased std of one sample)
+    one = torch.empty(1, 2048, device=cuda_dev)
+    ops.latent_prep(noise[:1].contiguous().to(cuda_dev), z[:1].contiguous().to(cuda_dev), lat_f32=one)
+    assert torch.isnan(one).all()
+
+
+def test_adam_matches_torch(cuda_dev):
+    from rnagan_b200.optim import adam_step
+    g = torch.Generator().manual_seed(1)
+    shapes = [(2048, 64, 4, 4), (1000,), (3,), (77, 5)]
+    ps = [torch.nn.Parameter(torch.randn(s, generator=g).to(cuda_dev)) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    o1 = torch.optim.Adam(ps, lr=4e-4, betas=(0.5, 0.999))
+    o2 = torch.optim.Adam(qs, lr=4e-4, betas=(0.5, 0.999))
+    for _ in range(3):
+        for p, q in zip(ps, qs):
+            gr = torch.randn(p.shape, generator=g).to(cuda_dev)
+            p.grad = gr.clone(); q.grad = gr.clone()
+        adam_step(o1)
+        o2.step()
+    for p, q in zip(ps, qs):
+        assert (p - q).abs().max().item() <= 1e-6
+    sd = o1.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 3.0
+
+
+def test_checkpoint_roundtrip_and_errors(cuda_dev):
+    from rnagan_b200 import dcgan, wgan_loss
+    from rnagan_b200.trainer import Trainer
+    feats = 64
+    oV = O.OracleVAE(feats).eval()
+    d = tempfile.mkdtemp()
+    ckpt = os.path.join(d, "vae.pt")
+    torch.save(oV.state_dict(), ckpt)
+    net = {
+        "generator": {"name": dcgan.DCGANGenerator, "args": {"encoding_dims": 2048, "out_size": 32, "step_channels": 64},
+                      "optimizer": {"name": torch.optim.Adam, "args": {"lr": 1e-4, "betas": (0.5, 0.999)}}},
+        "discriminator": {"name": dcgan.DCGANDiscriminator, "args": {"in_size": 32, "step_channels": 64},
+                          "optimizer": {"name": torch.optim.Adam, "args": {"lr": 4e-4, "betas": (0.5, 0.999)}}},
+    }
+    mk = lambda: [wgan_loss.WassersteinGeneratorLossVAE(ckpt, feats), wgan_loss.WassersteinDiscriminatorLossVAE(ckpt, feats),
+                  wgan_loss.WassersteinGradientPenaltyVAE(ckpt, feats)]
+    tr = Trainer(net, mk(), device=cuda_dev, checkpoints=os.path.join(d, "gan"), epochs=1, devices=[0])
+    data = O.make_batch(8, feats, 32, 1)
+    tr.real_inputs = data
+    vals = tr.train_iter()
+    assert list(vals) == ["WassersteinGeneratorLossVAE", "WassersteinDiscriminatorLossVAE", "WassersteinGradientPenaltyVAE"]
+    assert all(np.isfinite(v) for v in vals.values())
+    path = tr.save_model(0)
+    saved = torch.load(path, weights_only=False)
+    for k in ("epoch", "loss_information", "loss_objects", "generator", "discriminator", "optimizer_generator",
+              "optimizer_discriminator"):
+        assert k in saved
+    tr2 = Trainer(net, mk(), device=cuda_dev, checkpoints=os.path.join(d, "gan"), epochs=1)
+    tr2.load_model(load_path=path)
+    for (n, a), (_, b) in zip(tr.generator.state_dict().items(), tr2.generator.state_dict().items()):
+        assert torch.equal(a, b), n
+    assert tr2.start_epoch == 1
+    # same batch, same RNG -> the restored trainer continues identically (deterministic kernels)
+    tr.real_inputs = tr2.real_inputs = data
+    torch.manual_seed(3); v1 = tr.train_iter()
+    torch.manual_seed(3); v2 = tr2.train_iter()
+    assert list(v1.values()) == list(v2.values())
+    # reference error behaviour
+    tr.generator.label_type = "required"
+    with pytest.raises(Exception, match="GAN model requires labels for training"):
+        tr.train_iter()
