@@ -14,7 +14,9 @@
  *               nn.ConvTranspose2d(Cp->Cs,4,2,1) has weight [Cin=Cp][Cout=Cs][4][4] (generator, src/dcgan.py:52)
  *               so both directions of both networks are the same three contractions: DOWN, UP, WGRAD.
  *   w_down      bf16 [Cp][16*Cs]      k = (kh*4+kw)*Cs + s
+ *               (rg_conv_up reads the same buffer as an MN-major B operand: one packed copy per link)
  *   w_up        bf16 [4][Cs_pad][4*Cp] phase = (y&1)*2+(x&1), k = tap*Cp + p, Cs_pad = max(Cs,16) rounded to 16
+ *               (only for the <=8-channel image variant rg_conv_up_img)
  *   activations bf16 NHWC; images fp32 NCHW (the reference's tensor layout at the module boundary).
  */
 #ifndef RNAGAN_B200_H
@@ -60,7 +62,10 @@ int rg_cast_pad_bf16(const float* src, void* dst, int rows, int cols, int cols_p
 int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int W, int Cs, int Cp, rg_stream_t st);
 /* hi[b,y,x,s] = sum lo[b,i,j,p] * W[p,s,kh,kw] over y=2i-1+kh, x=2j-1+kw
  * generator forward nn.ConvTranspose2d(4,2,1) (src/dcgan.py:52) and critic dgrad. */
-int rg_conv_up(const void* lo, const void* w_up, void* hi, int B, int H, int W, int Cp, int Cs, rg_stream_t st);
+/* w: either w_up (w_is_down=0; K-major B, best for Cs <= 128 where the extra packed copy is tiny) or w_down
+ * (w_is_down=1; read as an MN-major B operand, so large layers keep a single packed copy). */
+int rg_conv_up(const void* lo, const void* w, int w_is_down, void* hi, int B, int H, int W, int Cp, int Cs,
+               rg_stream_t st);
 /* same as rg_conv_up for Cs<=16 image channels, fp32 NCHW output, optional bias + tanh
  * (generator last layer, src/dcgan.py:82; critic layer-0 dgrad). */
 int rg_conv_up_img(const void* lo, const void* w_up, float* img, const float* bias, int act_tanh, int B, int H,

@@ -27,7 +27,7 @@ SIGNATURES = {
     "rg_pack_edge": (_i, [_vp, _vp, _i, _i, _vp]),
     "rg_cast_pad_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rg_conv_down": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "rg_conv_up": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rg_conv_up": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "rg_conv_up_img": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rg_conv_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "rg_conv_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _f, _vp, _f, _vp]),

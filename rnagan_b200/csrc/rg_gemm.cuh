@@ -26,7 +26,7 @@ constexpr int kStages = 4;
 constexpr int kAStageBytes = 128 * 128;      // 16 KiB
 constexpr int kBStageBytes = 256 * 128;      // 32 KiB
 constexpr int kStageBytes = kAStageBytes + kBStageBytes;
-constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*epilogue affine*/;
 constexpr int kGemmThreads = 192;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;              // TMEM columns per accumulator stage
@@ -35,7 +35,7 @@ struct Tap {
   int8_t map;   // which A-view (parity map) this tap reads
   int8_t dh;    // row offset added to the tile's first row
   int8_t dw;    // column offset
-  int8_t rsv;
+  int8_t wtap;  // kernel position kh*4+kw this tap multiplies (used when B is read MN-major from w_down)
 };
 
 struct GemmMaps {
@@ -54,12 +54,14 @@ struct FwdArgs {
   int num_phases;         // 1, or 4 for the transposed (upsampling) form
   int n_total, block_n, n_tiles;
   int b_phase_rows;       // row offset between phases in the packed weight matrix
+  int b_mn;               // 1: B operand is read MN-major from w_down[Cp][16*Cs] (K rows = p, N contiguous = s)
+  int b_tap_cols;         // b_mn: column stride between kernel positions in w_down (= Cs)
   Tap taps[4][16];
   void* out;
   const float* col_scale;   // optional per-output-column scale (folded eval BatchNorm1d)
   const float* col_shift;   // optional per-output-column shift / bias
-  float slope;              // LeakyReLU slope applied after scale/shift (1.0f = identity)
-  int act_tanh;             // 1: tanh instead of LeakyReLU
+  float slope;              // LeakyReLU slope in [0,1] applied after scale/shift (1.0f = identity)
+  int act_tanh;             // OUT_F32_NCHW only: tanh instead of LeakyReLU
   int OH, OW, OC;           // output tensor dims
   int sy, sx;               // output pixel = (i*sy + oy[phase], j*sx + ox[phase])
   int n_valid;              // columns >= n_valid are not stored
@@ -85,6 +87,8 @@ struct PipeSmem {
   uint64_t* tfull;
   uint64_t* tempty;
   uint32_t* tmem_slot;
+  float* s_scale;   // [256] per-column epilogue scale of the current tile
+  float* s_shift;   // [256]
 };
 
 __device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
@@ -97,6 +101,8 @@ __device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
   s.tfull = bars + 2 * kStages;
   s.tempty = bars + 2 * kStages + 2;
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  s.s_scale = reinterpret_cast<float*>(base + kStages * kStageBytes + 256);
+  s.s_shift = s.s_scale + 256;
   return s;
 }
 
@@ -166,7 +172,14 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
           uint8_t* sb = sa + kAStageBytes;
           mbar_expect_tx(&s.full[stage], stage_tx);
           tma_load_4d(&maps.a[t.map], &s.full[stage], sa, chunk * kBlockK, j0 + t.dw, i0 + t.dh, b0);
-          tma_load_2d(&maps.b, &s.full[stage], sb, kb * kBlockK, brow);
+          if (p.b_mn) {
+            // B^T slabs [64 k-rows = p][64 n = s] straight out of w_down: no second packed copy of the weights
+            const int col0 = t.wtap * p.b_tap_cols + n_tile * p.block_n;
+            for (int sl = 0; sl < (p.block_n >> 6); ++sl)
+              tma_load_2d(&maps.b, &s.full[stage], sb + sl * 8192, col0 + sl * 64, chunk * kBlockK);
+          } else {
+            tma_load_2d(&maps.b, &s.full[stage], sb, kb * kBlockK, brow);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -174,7 +187,9 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
   } else if (warp == 1) {
     // ===================================================== MMA issuer (one elected lane)
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, p.b_mn);
+      const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
+      const uint32_t b_kstep = p.b_mn ? 128u : 2u;   // (>>4) address advance per UMMA_K: 16 rows x 128 B, or 32 B
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -190,11 +205,11 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
           const uint32_t sa = smem_u32(s.stages + stage * kStageBytes);
           const uint32_t sb = sa + kAStageBytes;
           const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 bytes per UMMA_K inside the 128-byte swizzle row => +2 in the (>>4) address field
-            umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_d, da + 2u * k, db + b_kstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&s.empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -210,6 +225,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
     const int ii = (row / p.bw) % p.bh;
     const int bbi = row / (p.bw * p.bh);
     int iter = 0;
+    int staged_n_tile = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1u;
@@ -224,6 +240,22 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
       const bool row_ok = (b < p.nB) && (i < p.H) && (j < p.W);
       const int y = i * p.sy + p.oy[ph], x = j * p.sx + p.ox[ph];
       const int n0 = n_tile * p.block_n;
+
+      // per-column scale / shift of this tile -> smem (one broadcast read per element instead of global loads)
+      const bool affine = (p.col_scale != nullptr) || (p.col_shift != nullptr);
+      if (affine && n_tile != staged_n_tile) {                 // reload only when the column range changes
+        const int et = threadIdx.x - 64;                       // 0..127 among the epilogue warps
+        asm volatile("bar.sync 1, 128;" ::: "memory");        // previous tile's readers are done
+        for (int cc = et; cc < p.block_n; cc += 128) {
+          const int col = n0 + cc;
+          const bool ok = col < p.n_valid;
+          s.s_scale[cc] = (ok && p.col_scale) ? __ldg(p.col_scale + col) : 1.0f;
+          s.s_shift[cc] = (ok && p.col_shift) ? __ldg(p.col_shift + col) : 0.0f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        staged_n_tile = n_tile;
+      }
+      const bool lrelu = p.slope != 1.0f;
 
       mbar_wait(&s.tfull[acc], acc_phase);
       tc_fence_after();
@@ -241,19 +273,19 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
         }
         tmem_ld_wait();
         const int ncols = min(32, p.block_n - c);
-        // optional per-column affine + activation
-        if (p.col_scale != nullptr || p.col_shift != nullptr || p.slope != 1.0f || p.act_tanh) {
+        if (affine) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            v[e] = __float_as_uint(fmaf(__uint_as_float(v[e]), s.s_scale[(c + e) & 255], s.s_shift[(c + e) & 255]));
+        }
+        if (OUT == OUT_F32_NCHW && p.act_tanh) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __float_as_uint(tanhf(__uint_as_float(v[e])));
+        } else if (lrelu) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const int col = n0 + c + e;
-            float f = __uint_as_float(v[e]);
-            if (e < ncols && col < p.n_valid) {
-              if (p.col_scale) f *= __ldg(p.col_scale + col);
-              if (p.col_shift) f += __ldg(p.col_shift + col);
-              if (p.act_tanh) f = tanhf(f);
-              else f = f > 0.0f ? f : f * p.slope;
-            }
-            v[e] = __float_as_uint(f);
+            const float f = __uint_as_float(v[e]);
+            v[e] = __float_as_uint(fmaxf(f, f * p.slope));
           }
         }
         if (row_ok) {

@@ -204,10 +204,21 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// Split-K factor: minimise waves x (k-blocks per unit + per-unit epilogue cost); favours unit counts that fill whole
+// waves of the persistent grid (e.g. 64 tiles x 9 splits = 576 units = 3.9 waves instead of 192 = 1.3 waves).
 static void choose_splits(int units, int num_pb, int& splits, int& pb_per_split) {
-  splits = std::max(1, std::min(num_pb, ceil_div(num_sms(), units)));
+  const int sms = num_sms();
+  double best = 1e30;
+  int best_s = 1;
+  for (int sp = 1; sp <= std::min(num_pb, 4 * sms); ++sp) {
+    const int per = ceil_div(num_pb, sp);
+    const int eff = ceil_div(num_pb, per);
+    if (eff != sp) continue;
+    const double cost = static_cast<double>(ceil_div(units * sp, sms)) * (per + 4) + 0.05 * sp;
+    if (cost < best) { best = cost; best_s = sp; }
+  }
+  splits = best_s;
   pb_per_split = ceil_div(num_pb, splits);
-  splits = ceil_div(num_pb, pb_per_split);
 }
 
 struct WgradGeom {
@@ -424,7 +435,7 @@ int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int
       t.map = static_cast<int8_t>(kDownPar[kh] * 2 + kDownPar[kw]);
       t.dh = static_cast<int8_t>(kDownOff[kh]);
       t.dw = static_cast<int8_t>(kDownOff[kw]);
-      t.rsv = 0;
+      t.wtap = static_cast<int8_t>(kh * 4 + kw);
       a.taps[0][kh * 4 + kw] = t;
     }
   a.n_total = Cp;
@@ -439,9 +450,9 @@ int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int
   return launch_fwd(maps, a, OUT_BF16_NHWC, st);
 }
 
-static int conv_up_common(const void* lo, const void* w_up, void* out, const float* bias, int act_tanh, int B, int H,
-                          int W, int Cp, int Cs, int out_kind, cudaStream_t st) {
-  RG_CHECK_ARG(lo && w_up && out, "rg_conv_up: null pointer");
+static int conv_up_common(const void* lo, const void* w, void* out, const float* bias, int act_tanh, int B, int H,
+                          int W, int Cp, int Cs, int out_kind, bool w_is_down, cudaStream_t st) {
+  RG_CHECK_ARG(lo && w && out, "rg_conv_up: null pointer");
   RG_CHECK_ARG(B > 0 && is_pow2(H) && is_pow2(W), "rg_conv_up: H, W must be powers of two (got %d x %d)", H, W);
   RG_CHECK_ARG(Cp % 64 == 0, "rg_conv_up: need Cp %% 64 == 0 (Cp=%d)", Cp);
   const int Cs_pad = std::max(16, (Cs + 15) / 16 * 16);
@@ -465,7 +476,7 @@ static int conv_up_common(const void* lo, const void* w_up, void* out, const flo
           t.map = 0;
           t.dh = static_cast<int8_t>(kUpOff[rh][th]);
           t.dw = static_cast<int8_t>(kUpOff[rw][tw]);
-          t.rsv = 0;
+          t.wtap = static_cast<int8_t>(kUpK[rh][th] * 4 + kUpK[rw][tw]);
           a.taps[ph][th * 2 + tw] = t;
         }
     }
@@ -473,7 +484,14 @@ static int conv_up_common(const void* lo, const void* w_up, void* out, const flo
   a.block_n = pick_block_n(Cs_pad, a.m_tiles * 4);
   a.n_tiles = ceil_div(Cs_pad, a.block_n);
   a.b_phase_rows = Cs_pad;
-  rc = encode_map_2d(&maps.b, w_up, 4ull * Cp, 4ull * Cs_pad, 4ull * Cp, 64, a.block_n);
+  if (w_is_down) {
+    // B is read MN-major straight from w_down[Cp][16*Cs]: 64x64 slabs at column tap*Cs + n, row p
+    a.b_mn = 1;
+    a.b_tap_cols = Cs;
+    rc = encode_map_2d(&maps.b, w, 16ull * Cs, Cp, 16ull * Cs, 64, 64);
+  } else {
+    rc = encode_map_2d(&maps.b, w, 4ull * Cp, 4ull * Cs_pad, 4ull * Cp, 64, a.block_n);
+  }
   if (rc) return rc;
   a.out = out;
   a.OH = 2 * H; a.OW = 2 * W; a.OC = Cs;
@@ -484,15 +502,19 @@ static int conv_up_common(const void* lo, const void* w_up, void* out, const flo
   return launch_fwd(maps, a, out_kind, st);
 }
 
-int rg_conv_up(const void* lo, const void* w_up, void* hi, int B, int H, int W, int Cp, int Cs, rg_stream_t st_) {
-  RG_CHECK_ARG(Cs % 16 == 0, "rg_conv_up: need Cs %% 16 == 0 (Cs=%d); use rg_conv_up_img for image channels", Cs);
-  return conv_up_common(lo, w_up, hi, nullptr, 0, B, H, W, Cp, Cs, OUT_BF16_NHWC, static_cast<cudaStream_t>(st_));
+int rg_conv_up(const void* lo, const void* w, int w_is_down, void* hi, int B, int H, int W, int Cp, int Cs,
+               rg_stream_t st_) {
+  RG_CHECK_ARG(Cs % (w_is_down ? 64 : 16) == 0,
+               "rg_conv_up: need Cs %% 64 == 0 with w_down, %% 16 with w_up (Cs=%d); use rg_conv_up_img for images", Cs);
+  return conv_up_common(lo, w, hi, nullptr, 0, B, H, W, Cp, Cs, OUT_BF16_NHWC, w_is_down != 0,
+                        static_cast<cudaStream_t>(st_));
 }
 
 int rg_conv_up_img(const void* lo, const void* w_up, float* img, const float* bias, int act_tanh, int B, int H, int W,
                    int Cp, int Cimg, rg_stream_t st_) {
   RG_CHECK_ARG(Cimg >= 1 && Cimg <= 8, "rg_conv_up_img: 1..8 image channels supported (got %d)", Cimg);
-  return conv_up_common(lo, w_up, img, bias, act_tanh, B, H, W, Cp, Cimg, OUT_F32_NCHW, static_cast<cudaStream_t>(st_));
+  return conv_up_common(lo, w_up, img, bias, act_tanh, B, H, W, Cp, Cimg, OUT_F32_NCHW, false,
+                        static_cast<cudaStream_t>(st_));
 }
 
 int rg_gemm_nt(const void* A, const void* Bw, void* C, int M, int N, int K, int ldc, const float* col_scale,
@@ -550,7 +572,7 @@ int rg_conv_wgrad(const void* lo, const void* hi, float* dW, void* ws, size_t ws
       t.map = static_cast<int8_t>(kDownPar[kh] * 2 + kDownPar[kw]);
       t.dh = static_cast<int8_t>(kDownOff[kh]);
       t.dw = static_cast<int8_t>(kDownOff[kw]);
-      t.rsv = 0;
+      t.wtap = static_cast<int8_t>(kh * 4 + kw);
       taps[kh * 4 + kw] = t;
     }
   return launch_wgrad(maps, w, taps, B, H, W, Cp, Cs, dW, ws, ws_bytes, alpha, alpha_dev, beta, st);

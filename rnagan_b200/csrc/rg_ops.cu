@@ -36,6 +36,10 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const Vec8& r) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+__device__ __forceinline__ uint32_t pack_bf16x2_ops(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ Vec8 ldf8(const float* p) {
   Vec8 r;
   const float4 a = *reinterpret_cast<const float4*>(p);
@@ -418,56 +422,51 @@ __global__ void latent_prep_kernel(const float* __restrict__ noise, const float*
 // im2col of a fp32 NCHW image [B][Cimg<=4][S][S] for the 4x4 stride-2 pad-1 conv: col[pix][k], k = (kh*4+kw)*4 + c.
 // mode 0: v = x*mul ; mode 1: v = (eps*x + (1-eps)*y)*mul (GP interpolation, src/wgan_loss.py:377);
 // mode 2: v = x*(1 - y*y)*mul (tanh backward with y = tanh output).  eps_dev/mul_dev are device scalars (optional).
-__global__ void im2col_img_kernel(const float* __restrict__ x, const float* __restrict__ y, int mode,
-                                  const float* __restrict__ eps_dev, const float* __restrict__ mul_dev, int B, int Cimg,
-                                  int S, __nv_bfloat16* __restrict__ col, float* __restrict__ mixed_out) {
-  const int Ho = S / 2;
-  const size_t npix = static_cast<size_t>(B) * Ho * Ho;
+// One block per output row (b, ho): the four input rows are staged in shared memory with the pointwise transform
+// applied once per input element (coalesced reads), then written out as whole 128-byte col rows (coalesced writes).
+__global__ void __launch_bounds__(256) im2col_img_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                         int mode, const float* __restrict__ eps_dev,
+                                                         const float* __restrict__ mul_dev, int B, int Cimg, int S,
+                                                         __nv_bfloat16* __restrict__ col,
+                                                         float* __restrict__ mixed_out) {
+  extern __shared__ float rows[];   // [Cimg][4][S + 2], one zero column on each side
+  const int Ho = S / 2, Wp = S + 2;
+  const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
   const float eps = eps_dev ? __ldg(eps_dev) : 0.0f;
   const float mul = mul_dev ? __ldg(mul_dev) : 1.0f;
-  // one thread per (pixel, kh): writes 4 taps x 4 channels = 16 bf16 = 32 bytes
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < npix * 4;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    // index order (b, ho, kh, wo): neighbouring threads read neighbouring input pixels of the same row
-    const int wo = static_cast<int>(i % Ho);
-    const int kh = static_cast<int>((i / Ho) & 3);
-    const int ho = static_cast<int>((i / (4 * static_cast<size_t>(Ho))) % Ho);
-    const int b = static_cast<int>(i / (4 * static_cast<size_t>(Ho) * Ho));
-    const size_t pix = (static_cast<size_t>(b) * Ho + ho) * Ho + wo;
-    const int yy = 2 * ho - 1 + kh;
-    uint32_t packed[8];
-#pragma unroll
-    for (int kw = 0; kw < 4; ++kw) {
-      const int xx = 2 * wo - 1 + kw;
-      float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      if (yy >= 0 && yy < S && xx >= 0 && xx < S) {
-        for (int c = 0; c < Cimg; ++c) {
-          const size_t o = ((static_cast<size_t>(b) * Cimg + c) * S + yy) * S + xx;
-          float t = __ldg(x + o);
-          if (mode == 1) t = eps * t + (1.0f - eps) * __ldg(y + o);
-          else if (mode == 2) { const float th = __ldg(y + o); t = t * (1.0f - th * th); }
-          v[c] = t * mul;
-        }
-      }
-      packed[kw * 2] = (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16(v[1]))) << 16) |
-                       __bfloat16_as_ushort(__float2bfloat16(v[0]));
-      packed[kw * 2 + 1] = (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16(v[3]))) << 16) |
-                           __bfloat16_as_ushort(__float2bfloat16(v[2]));
+  for (int idx = threadIdx.x; idx < Cimg * 4 * S; idx += blockDim.x) {
+    const int xx = idx % S;
+    const int r = (idx / S) & 3;
+    const int c = idx / (4 * S);
+    const int yy = 2 * ho - 1 + r;
+    float t = 0.0f;
+    if (yy >= 0 && yy < S) {
+      const size_t o = ((static_cast<size_t>(b) * Cimg + c) * S + yy) * S + xx;
+      t = __ldg(x + o);
+      if (mode == 1) t = eps * t + (1.0f - eps) * __ldg(y + o);
+      else if (mode == 2) { const float th = __ldg(y + o); t = t * (1.0f - th * th); }
+      t *= mul;
+      if (mixed_out && (r == 1 || r == 2)) mixed_out[o] = t;   // rows 2ho, 2ho+1 are owned by this block
     }
-    uint4* dst = reinterpret_cast<uint4*>(col + pix * 64 + kh * 16);
-    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    rows[(c * 4 + r) * Wp + xx + 1] = t;
   }
-  // optional: materialise the mixed image itself (fp32 NCHW) for callers that need it
-  if (mixed_out) {
-    const size_t n = static_cast<size_t>(B) * Cimg * S * S;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-      float t = x[i];
-      if (mode == 1) t = eps * t + (1.0f - eps) * y[i];
-      else if (mode == 2) t = t * (1.0f - y[i] * y[i]);
-      mixed_out[i] = t * mul;
+  for (int idx = threadIdx.x; idx < Cimg * 4 * 2; idx += blockDim.x)
+    rows[(idx >> 1) * Wp + ((idx & 1) ? S + 1 : 0)] = 0.0f;
+  __syncthreads();
+  const size_t pix0 = (static_cast<size_t>(b) * Ho + ho) * Ho;
+  for (int idx = threadIdx.x; idx < Ho * 8; idx += blockDim.x) {
+    const int wo = idx >> 3, part = idx & 7;
+    const int kh = part >> 1, kw0 = (part & 1) * 2;
+    uint32_t packed[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const int sx = 2 * wo + kw0 + k;            // smem column of input x = 2*wo - 1 + kw
+      for (int c = 0; c < Cimg; ++c) v[c] = rows[(c * 4 + kh) * Wp + sx];
+      packed[k * 2] = pack_bf16x2_ops(v[0], v[1]);
+      packed[k * 2 + 1] = pack_bf16x2_ops(v[2], v[3]);
     }
+    *reinterpret_cast<uint4*>(col + (pix0 + wo) * 64 + part * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
 }
 
@@ -876,10 +875,10 @@ int rg_im2col_img(const float* x, const float* y, int mode, const float* eps_dev
                   int Cimg, int S, void* col, float* mixed_out, rg_stream_t st) {
   RG_CHECK_ARG(x && col && B > 0 && Cimg >= 1 && Cimg <= 4 && S >= 2 && S % 2 == 0, "rg_im2col_img: bad arguments");
   RG_CHECK_ARG(mode == 0 || y, "rg_im2col_img: mode %d needs a second image", mode);
-  const size_t work = static_cast<size_t>(B) * (S / 2) * (S / 2) * 4;
-  const int grid = static_cast<int>(std::min<size_t>((work + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  im2col_img_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(x, y, mode, eps_dev, mul_dev, B, Cimg, S,
-                                                                     static_cast<bf16*>(col), mixed_out);
+  const size_t smem = static_cast<size_t>(Cimg) * 4 * (S + 2) * sizeof(float);
+  RG_CHECK_ARG(smem <= 48 * 1024, "rg_im2col_img: image side %d too large for the row-staging buffer", S);
+  im2col_img_kernel<<<B * (S / 2), 256, smem, static_cast<cudaStream_t>(st)>>>(x, y, mode, eps_dev, mul_dev, B, Cimg, S,
+                                                                               static_cast<bf16*>(col), mixed_out);
   RG_LAUNCH_CHECK("rg_im2col_img");
   return 0;
 }

@@ -137,11 +137,13 @@ class GeneratorEngine:
         self.size = 4 * (2 ** (self.n + 1))
         # packed bf16 operands (derived, non-persistent)
         self.w_proj = torch.empty(16 * self.C0, self.E, dtype=BF16, device=dev)
-        self.w_up, self.w_down = [], []
+        # one packed copy per link (w_down: K-major B for rg_conv_down, MN-major B for rg_conv_up); layers with
+        # Cs <= 128 also keep the tiny K-major w_up copy, which is faster for narrow N tiles
+        self.w_down, self.w_upk = [], []
         for c in self.convs:
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
-            self.w_up.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev))
             self.w_down.append(torch.empty(Cp, 16 * Cs, dtype=BF16, device=dev))
+            self.w_upk.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev) if Cs <= 128 else None)
         self.w_colT_last = torch.zeros(16 * self.Cimg, self.Cn, dtype=BF16, device=dev)
         self.w_col_last = torch.empty(self.Cn, 64, dtype=BF16, device=dev)
         self.pack()
@@ -149,8 +151,8 @@ class GeneratorEngine:
     def pack(self):
         """Refresh the bf16 operand copies from the fp32 master weights (after load_state_dict / optimizer step)."""
         ops.pack_proj(self.conv0.weight.detach(), self.w_proj)
-        for c, wu, wd in zip(self.convs, self.w_up, self.w_down):
-            ops.pack_link(c.weight.detach(), wd, wu)
+        for c, wd, wu in zip(self.convs, self.w_down, self.w_upk):
+            ops.pack_link(c.weight.detach(), wd, wu, want_up=wu is not None)
         ops.pack_edge_t(self.conv_last.weight.detach(), self.w_colT_last)
         ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
 
@@ -166,7 +168,7 @@ class GeneratorEngine:
         for l, (c, bn) in enumerate(zip(self.convs, self.bns), start=1):
             Cs = c.weight.shape[1]
             a = g(f"{tag}.a{l}", (B, 2 * H, 2 * H, Cs))
-            ops.conv_up(h, self.w_up[l - 1], Cs, out=a)
+            ops.conv_up(h, self.w_upk[l - 1] if self.w_upk[l - 1] is not None else self.w_down[l - 1], Cs, out=a)
             H *= 2
             h = g(f"{tag}.h{l}", (B, H, H, Cs))
             bn.forward(a, h, B * H * H, training, tag=tag)
@@ -245,11 +247,11 @@ class CriticEngine:
             raise NotImplementedError("channel counts must be multiples of 64 on the sm_100a path")
         self.w_col0 = torch.empty(self.C0, 64, dtype=BF16, device=dev)
         self.w_colT0 = torch.zeros(16 * self.Cimg, self.C0, dtype=BF16, device=dev)
-        self.w_down, self.w_up = [], []
+        self.w_down, self.w_upk = [], []
         for c in self.convs:
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
             self.w_down.append(torch.empty(Cp, 16 * Cs, dtype=BF16, device=dev))
-            self.w_up.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev))
+            self.w_upk.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev) if Cs <= 128 else None)
         self.w_head = torch.empty(16 * self.Cn, dtype=F32, device=dev)
         self.tmpC = torch.zeros(max([self.C0] + [c.weight.shape[0] for c in self.convs]), dtype=F32, device=dev)
         self.gp_partial = torch.zeros(1024, dtype=F32, device=dev)
@@ -259,9 +261,12 @@ class CriticEngine:
     def pack(self):
         ops.pack_edge(self.conv0.weight.detach(), self.w_col0)
         ops.pack_edge_t(self.conv0.weight.detach(), self.w_colT0)
-        for c, wd, wu in zip(self.convs, self.w_down, self.w_up):
-            ops.pack_link(c.weight.detach(), wd, wu)
+        for c, wd, wu in zip(self.convs, self.w_down, self.w_upk):
+            ops.pack_link(c.weight.detach(), wd, wu, want_up=wu is not None)
         ops.pack_head(self.head.weight.detach(), self.w_head)
+
+    def _wup(self, l):
+        return self.w_upk[l - 1] if self.w_upk[l - 1] is not None else self.w_down[l - 1]
 
     # ------------------------------------------------------------------ forward
     def forward(self, x=None, tag="d", training=True, col=None):
@@ -317,7 +322,7 @@ class CriticEngine:
                 ops.conv_wgrad(da, hprev, _grad_of(c.weight), beta=acc)
             H *= 2
             dh = g(f"{tag}.dh{l - 1}", (B, H, H, Cs))
-            ops.conv_up(da, self.w_up[l - 1], Cs, out=dh)
+            ops.conv_up(da, self._wup(l), Cs, out=dh)
         h0 = g(f"{tag}.h0", (B, H, H, self.C0))
         da0 = g(f"{tag}.da0", (B, H, H, self.C0))
         npix = B * H * H
@@ -397,7 +402,7 @@ class CriticEngine:
             ops.conv_wgrad(T, hprev, _grad_of(c.weight), beta=1.0)
             H *= 2
             A_h = g(f"{tag}.Ah{l - 1}", (B, H, H, Cs))
-            ops.conv_up(T, self.w_up[l - 1], Cs, out=A_h)
+            ops.conv_up(T, self._wup(l), Cs, out=A_h)
             if l - 1 >= 1:
                 bnp = self.bns[l - 2]
                 a = g(f"{tag}.a{l - 1}", (B, H, H, Cs))

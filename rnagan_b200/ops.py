@@ -116,14 +116,15 @@ def conv_down(hi, w_down, out=None):
     return out
 
 
-def conv_up(lo, w_up, Cs, out=None):
-    """lo bf16 [B, H, W, Cp], w_up bf16 [4, Cs_pad, 4*Cp] -> hi bf16 [B, 2H, 2W, Cs]."""
-    _chk(lo, BF16, "lo"); _chk(w_up, BF16, "w_up")
+def conv_up(lo, w, Cs, out=None):
+    """lo bf16 [B, H, W, Cp] -> hi bf16 [B, 2H, 2W, Cs].  w: w_down bf16 [Cp, 16*Cs] (2-D; read MN-major) or
+    w_up bf16 [4, Cs_pad, 4*Cp] (3-D; K-major)."""
+    _chk(lo, BF16, "lo"); _chk(w, BF16, "w")
     B, H, W, Cp = lo.shape
     if out is None:
         out = torch.empty(B, 2 * H, 2 * W, Cs, dtype=BF16, device=lo.device)
     _prof("conv_up", 2.0 * B * H * W * Cp * 16 * Cs, lambda: _lib.check(
-        _lib.lib().rg_conv_up(_p(lo), _p(w_up), _p(out), B, H, W, Cp, Cs, _st()), "rg_conv_up"))
+        _lib.lib().rg_conv_up(_p(lo), _p(w), int(w.dim() == 2), _p(out), B, H, W, Cp, Cs, _st()), "rg_conv_up"))
     return out
 
 

@@ -80,10 +80,11 @@ def test_conv_up(cuda_dev, B, H, W, Cp, Cs):
     x = _bf(torch.randn(B, Cp, H, W, generator=g)).to(cuda_dev)
     Wt = _bf(torch.randn(Cp, Cs, 4, 4, generator=g) * 0.05).to(cuda_dev)
     ref = F.conv_transpose2d(x, Wt, stride=2, padding=1)
-    _, w_up = ops.pack_link(Wt, want_down=False)
-    out = ops.conv_up(_nhwc(x), w_up, Cs)
-    assert out.shape == (B, 2 * H, 2 * W, Cs)
-    assert _rel(_nchw(out), ref) < 8e-3
+    w_down, w_up = ops.pack_link(Wt)
+    for w in (w_down, w_up):      # MN-major read of w_down, and the K-major w_up copy
+        out = ops.conv_up(_nhwc(x), w, Cs)
+        assert out.shape == (B, 2 * H, 2 * W, Cs)
+        assert _rel(_nchw(out), ref) < 8e-3
 
 
 @pytest.mark.parametrize("B,H,W,Cp", [(4, 32, 32, 64), (2, 128, 128, 64)])
