@@ -146,7 +146,6 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
     from rnagan_b200 import _lib, ops, steps
-    from rnagan_b200.parallel import allreduce_mean_
 
     device = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(device)
@@ -158,10 +157,6 @@ def run_ours(args, rank, world, local_rank):
     G, D = tr.generator, tr.discriminator
     vae = tr.losses["WassersteinGeneratorLossVAE"]._encoder(device)
     names = list(tr.losses.keys())
-
-    def allreduce(module):
-        if world > 1:
-            allreduce_mean_([p.grad for p in module.parameters() if p.grad is not None])
 
     def barrier():
         if world > 1:
@@ -188,10 +183,9 @@ def run_ours(args, rank, world, local_rank):
     def resident_step(i):
         j = i & 1
         z = vae.encode_mean(rna_d[j])                      # encoder runs once per iteration (same batch for 3 steps)
-        l1 = steps.g_step(G, D, tr.optimizer_generator, noise_all[i, 0], z, allreduce=allreduce)
-        l2 = steps.critic_step(G, D, tr.optimizer_discriminator, noise_all[i, 1], z, real_d[j], allreduce=allreduce)
-        l3 = steps.gp_step(G, D, tr.optimizer_discriminator, noise_all[i, 2], z, real_d[j], eps_all[i],
-                           allreduce=allreduce)
+        l1 = steps.g_step(G, D, tr.optimizer_generator, noise_all[i, 0], z)
+        l2 = steps.critic_step(G, D, tr.optimizer_discriminator, noise_all[i, 1], z, real_d[j])
+        l3 = steps.gp_step(G, D, tr.optimizer_discriminator, noise_all[i, 2], z, real_d[j], eps_all[i])
         loss_log[i, 0:1].copy_(l1)
         loss_log[i, 1:2].copy_(l2)
         loss_log[i, 2:3].copy_(l3[0:1])
@@ -385,8 +379,7 @@ def run_reference(args, rank, world):
     for _ in range(K):
         O.train_iter(G, D, og, od, vae, data)
     dt = (time.perf_counter() - t0) / K
-    value = (sb / dt) / args.batch * world      # 64-sample steps per second; replicas are not run on the CPU
-    value = (sb / dt) / args.batch
+    value = (sb / dt) / args.batch              # 64-sample steps per second on the host cores (rank 0 only)
     line = {
         "impl": "reference", "metric": "wgan_gd_train_steps_per_s", "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1000.0 / value, "higher_is_better": True,

@@ -160,8 +160,9 @@ int rg_gp_norm(const float* g, size_t n, float lambd, float* partial_ws, int par
 int rg_adam_table_bytes(int num_chunks);
 int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms, void* const* vs, const int64_t* sizes,
                         int num_tensors, int chunk_elems, void* table_host, int max_chunks);
+/* grad_scale multiplies every gradient first (1/world_size after a SUM all-reduce; 1.0 otherwise) */
 int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, float beta2, float eps, int step,
-                 int do_clamp, float clamp_lo, float clamp_hi, rg_stream_t st);
+                 int do_clamp, float clamp_lo, float clamp_hi, float grad_scale, rg_stream_t st);
 int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st);
 /* (x+1)/2 and NCHW -> NHWC fp32 (src/gan_utils.py:236-241) */
 int rg_tiles_to_unit_nhwc(const float* img, float* out, int B, int C, int S, rg_stream_t st);

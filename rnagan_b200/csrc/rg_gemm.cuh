@@ -274,9 +274,16 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
         tmem_ld_wait();
         const int ncols = min(32, p.block_n - c);
         if (affine) {
+          const float4* sc4 = reinterpret_cast<const float4*>(s.s_scale + (c & 255));
+          const float4* sh4 = reinterpret_cast<const float4*>(s.s_shift + (c & 255));
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            v[e] = __float_as_uint(fmaf(__uint_as_float(v[e]), s.s_scale[(c + e) & 255], s.s_shift[(c + e) & 255]));
+          for (int g4 = 0; g4 < 8; ++g4) {
+            const float4 a4 = sc4[g4], b4 = sh4[g4];
+            v[g4 * 4 + 0] = __float_as_uint(fmaf(__uint_as_float(v[g4 * 4 + 0]), a4.x, b4.x));
+            v[g4 * 4 + 1] = __float_as_uint(fmaf(__uint_as_float(v[g4 * 4 + 1]), a4.y, b4.y));
+            v[g4 * 4 + 2] = __float_as_uint(fmaf(__uint_as_float(v[g4 * 4 + 2]), a4.z, b4.z));
+            v[g4 * 4 + 3] = __float_as_uint(fmaf(__uint_as_float(v[g4 * 4 + 3]), a4.w, b4.w));
+          }
         }
         if (OUT == OUT_F32_NCHW && p.act_tanh) {
 #pragma unroll

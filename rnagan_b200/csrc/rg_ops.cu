@@ -695,7 +695,7 @@ struct AdamChunk {
 //   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__ chunks, float lr, float b1, float b2,
                                                    float eps, float bc1, float bc2_sqrt, float clamp_lo, float clamp_hi,
-                                                   int do_clamp) {
+                                                   int do_clamp, float gscale) {
   const AdamChunk ch = chunks[blockIdx.x];
   const float step = lr / bc1;
   const float ob1 = 1.0f - b1, ob2 = 1.0f - b2;
@@ -707,7 +707,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
   float4* v4 = reinterpret_cast<float4*>(ch.v);
   for (int i = threadIdx.x; i < n4; i += blockDim.x) {
     float4 p = p4[i], m = m4[i], v = v4[i];
-    const float4 g = g4[i];
+    float4 g = g4[i];
+    g.x *= gscale; g.y *= gscale; g.z *= gscale; g.w *= gscale;
     float* pp = reinterpret_cast<float*>(&p);
     float* mm = reinterpret_cast<float*>(&m);
     float* vv = reinterpret_cast<float*>(&v);
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
     p4[i] = p; m4[i] = m; v4[i] = v;
   }
   for (int i = n4 * 4 + threadIdx.x; i < ch.n; i += blockDim.x) {
-    const float g = ch.g[i];
+    const float g = ch.g[i] * gscale;
     const float m = b1 * ch.m[i] + ob1 * g;
     const float v = b2 * ch.v[i] + ob2 * g * g;
     ch.m[i] = m;
@@ -1003,13 +1004,13 @@ int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms
 }
 
 int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, float beta2, float eps, int step,
-                 int do_clamp, float clamp_lo, float clamp_hi, rg_stream_t st) {
+                 int do_clamp, float clamp_lo, float clamp_hi, float grad_scale, rg_stream_t st) {
   RG_CHECK_ARG(table_dev && num_chunks > 0 && step >= 1, "rg_adam_step: bad arguments");
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   adam_kernel<<<num_chunks, 256, 0, static_cast<cudaStream_t>(st)>>>(static_cast<const AdamChunk*>(table_dev), lr, beta1,
                                                                      beta2, eps, bc1, sqrtf(bc2), clamp_lo, clamp_hi,
-                                                                     do_clamp);
+                                                                     do_clamp, grad_scale);
   RG_LAUNCH_CHECK("rg_adam_step");
   return 0;
 }

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .parallel import GradSync
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -146,6 +147,7 @@ class GeneratorEngine:
             self.w_upk.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev) if Cs <= 128 else None)
         self.w_colT_last = torch.zeros(16 * self.Cimg, self.Cn, dtype=BF16, device=dev)
         self.w_col_last = torch.empty(self.Cn, 64, dtype=BF16, device=dev)
+        self.sync = GradSync(module)
         self.pack()
 
     def pack(self):
@@ -192,6 +194,7 @@ class GeneratorEngine:
         dcol = g("bwd.dcol", (self.Cn, 64), F32)
         ops.gemm_tn(hn.view(npix, self.Cn), col, out=dcol)
         ops.unpack_edge_grad(dcol, _grad_of(self.conv_last.weight), acc=0.0)
+        self.sync.layer_done(self.conv_last.weight, self.conv_last.bias)
         dh = g(f"bwd.dh{n}", (B, H, H, self.Cn))
         ops.gemm_nt(col, self.w_col_last, out=dh.view(npix, self.Cn))
         for l in range(n, 0, -1):
@@ -203,12 +206,14 @@ class GeneratorEngine:
             H //= 2
             hprev = g(f"{tag}.h{l - 1}", (B, H, H, Cp))
             ops.conv_wgrad(hprev, da, _grad_of(c.weight))
+            self.sync.layer_done(c.weight, bn.mod.weight, bn.mod.bias)
             dh = g(f"bwd.dh{l - 1}", (B, H, H, Cp))
             ops.conv_down(da, self.w_down[l - 1], out=dh)
         a0 = g(f"{tag}.a0", (B, 4, 4, self.C0))
         da0 = g("bwd.da0", (B, 4, 4, self.C0))
         self.bn0.backward(dh, a0, da0, B * 16, param_grads=True, tag=tag)
         ops.proj_wgrad(lat, da0, _grad_of(self.conv0.weight))
+        self.sync.layer_done(self.conv0.weight, self.bn0.mod.weight, self.bn0.mod.bias)
 
 
 # ====================================================================================================== critic
@@ -256,6 +261,7 @@ class CriticEngine:
         self.tmpC = torch.zeros(max([self.C0] + [c.weight.shape[0] for c in self.convs]), dtype=F32, device=dev)
         self.gp_partial = torch.zeros(1024, dtype=F32, device=dev)
         self.gp_out = torch.zeros(3, dtype=F32, device=dev)
+        self.sync = GradSync(module)
         self.pack()
 
     def pack(self):
@@ -294,7 +300,7 @@ class CriticEngine:
         return out
 
     # ------------------------------------------------------------------ first-order backward
-    def backward(self, B, dout_const, tag="d", params=False, acc=0.0, want_dimg=False, keep_du=False):
+    def backward(self, B, dout_const, tag="d", params=False, acc=0.0, want_dimg=False, keep_du=False, final=False):
         """Backward of sum_b dout_const * out[b] through the pass saved under `tag`.
 
         params: also produce parameter gradients (acc=1.0 accumulates onto existing .grad).
@@ -310,6 +316,8 @@ class CriticEngine:
         ops.head_bwd_data(a6, dout_const, self.w_head, B, 16 * self.Cn, SLOPE, da6, dh)
         if params:
             ops.head_wgrad(da6, hn, B, 16 * self.Cn, self.Cn, _grad_of(self.head.weight), acc)
+            if final:
+                self.sync.layer_done(self.head.weight)
         for l in range(n, 0, -1):
             c, bn = self.convs[l - 1], self.bns[l - 1]
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
@@ -320,6 +328,8 @@ class CriticEngine:
             hprev = g(f"{tag}.h{l - 1}", (B, 2 * H, 2 * H, Cs))
             if params:
                 ops.conv_wgrad(da, hprev, _grad_of(c.weight), beta=acc)
+                if final:
+                    self.sync.layer_done(c.weight, bn.mod.weight, bn.mod.bias)
             H *= 2
             dh = g(f"{tag}.dh{l - 1}", (B, H, H, Cs))
             ops.conv_up(da, self._wup(l), Cs, out=dh)
@@ -333,6 +343,8 @@ class CriticEngine:
             dcol = g("bwd.dcol", (self.C0, 64), F32)
             ops.gemm_tn(da0.view(npix, self.C0), col, out=dcol)
             ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=acc)
+            if final:
+                self.sync.layer_done(self.conv0.weight, self.conv0.bias)
         if want_dimg:
             dimg = g(f"{tag}.dimg", (B, self.Cimg, 2 * H, 2 * H), F32)
             colimg = g("bwd.colimg", (npix, 16 * self.Cimg), F32)
@@ -391,6 +403,7 @@ class CriticEngine:
                             Cp, A_dh, A_a, _grad_of(bn.mod.weight), 0.0)
         da6 = g(f"{tag}.da6", (B,), F32)
         ops.head_wgrad(da6, A_dh, B, 16 * self.Cn, self.Cn, _grad_of(self.head.weight), 0.0)
+        self.sync.layer_done(self.head.weight)
         # step 4: ordinary backward over the forward graph, seeded by the A_a terms
         T = g(f"{tag}.Aa{n}", (B, 4, 4, self.Cn))
         _grad_of(self.bns[n - 1].mod.bias).zero_()
@@ -400,6 +413,8 @@ class CriticEngine:
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
             hprev = g(f"{tag}.h{l - 1}", (B, 2 * H, 2 * H, Cs))
             ops.conv_wgrad(T, hprev, _grad_of(c.weight), beta=1.0)
+            # conv_l's weight is final now; BN_l's gamma/beta were finalised by step 3 (l = n) or the previous turn
+            self.sync.layer_done(c.weight, self.bns[l - 1].mod.weight, self.bns[l - 1].mod.bias)
             H *= 2
             A_h = g(f"{tag}.Ah{l - 1}", (B, H, H, Cs))
             ops.conv_up(T, self._wup(l), Cs, out=A_h)
@@ -417,6 +432,7 @@ class CriticEngine:
                 ops.gemm_tn(A_a0.view(npix0, self.C0), col_x, out=dcol)
                 ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=1.0)
                 ops.col_sum(A_a0, npix0, self.C0, self.tmpC, _grad_of(self.conv0.bias), 0.0)
+                self.sync.layer_done(self.conv0.weight, self.conv0.bias)
         return self.gp_out
 
 

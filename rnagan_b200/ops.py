@@ -367,8 +367,8 @@ class AdamTable:
         self.keep = (params, grads, ms, vs)
         self.ptrs = tuple(t.data_ptr() for ts in self.keep for t in ts)
 
-    def step(self, lr, beta1, beta2, eps, step, clamp=None):
+    def step(self, lr, beta1, beta2, eps, step, clamp=None, grad_scale=1.0):
         lo, hi = (clamp if clamp is not None else (0.0, 0.0))
         _lib.check(_lib.lib().rg_adam_step(_p(self.table), self.num_chunks, float(lr), float(beta1), float(beta2),
-                                           float(eps), int(step), int(clamp is not None), float(lo), float(hi), _st()),
-                   "rg_adam_step")
+                                           float(eps), int(step), int(clamp is not None), float(lo), float(hi),
+                                           float(grad_scale), _st()), "rg_adam_step")

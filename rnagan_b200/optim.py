@@ -19,8 +19,9 @@ def _ensure_state(opt, p):
     return st
 
 
-def adam_step(opt, clamp=None):
-    """One Adam step over every parameter of ``opt`` that has a gradient. Returns nothing; asynchronous."""
+def adam_step(opt, clamp=None, grad_scale=1.0):
+    """One Adam step over every parameter of ``opt`` that has a gradient (gradients are multiplied by grad_scale
+    first: 1/world_size after a SUM all-reduce). Returns nothing; asynchronous."""
     if not isinstance(opt, torch.optim.Adam):
         raise NotImplementedError(f"only torch.optim.Adam is implemented on the sm_100a path (got {type(opt).__name__})")
     tables = opt.__dict__.setdefault("_rg_tables", {})
@@ -45,4 +46,4 @@ def adam_step(opt, clamp=None):
             s["step"] += 1
         step = int(states[0]["step"].item()) if states[0]["step"].device.type == "cpu" else int(states[0]["step"])
         b1, b2 = group["betas"]
-        ent[1].step(group["lr"], b1, b2, group["eps"], step, clamp=clamp)
+        ent[1].step(group["lr"], b1, b2, group["eps"], step, clamp=clamp, grad_scale=grad_scale)

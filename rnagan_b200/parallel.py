@@ -54,3 +54,82 @@ def shard_range(n, rank, world):
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GradSync:
+    """Flat fp32 gradient buffer of one network (every ``p.grad`` is a view into it) + overlapped all-reduce.
+
+    ``layer_done(*params)`` is called by the engines as soon as a layer's gradients are final: the layer's slice of
+    the flat buffer is all-reduced (SUM) asynchronously on NCCL's stream while the rest of backward keeps running;
+    ``finish()`` reduces whatever was not announced, waits for the handles and returns the scale (1/world) that
+    the fused Adam applies to the gradients.  With a single process everything is a no-op and the scale is 1.
+    """
+
+    def __init__(self, module):
+        params = [p for p in module.parameters()]
+        self.params = params
+        offs, off = {}, 0
+        for p in params:
+            offs[id(p)] = (off, p.numel())
+            off += (p.numel() + 3) // 4 * 4            # keep every tensor 16-byte aligned for the vectorised Adam
+        self.offs = offs
+        self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=params[0].device)
+        for p in params:
+            o, n = offs[id(p)]
+            p.grad = self.flat[o:o + n].view_as(p)
+        self._pending = []
+        self._done = set()
+
+    @staticmethod
+    def world():
+        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _owns(self, p):
+        o, n = self.offs[id(p)]
+        return p.grad is not None and p.grad.data_ptr() == self.flat.data_ptr() + 4 * o
+
+    def layer_done(self, *params):
+        if self.world() == 1:
+            return
+        params = [p for p in params if p is not None and id(p) not in self._done]
+        if not params:
+            return
+        if all(self._owns(p) for p in params):
+            lo = min(self.offs[id(p)][0] for p in params)
+            hi = max(self.offs[id(p)][0] + self.offs[id(p)][1] for p in params)
+            # the slice may only cover tensors that are final: require the announced set to be contiguous
+            covered = sum((self.offs[id(p)][1] + 3) // 4 * 4 for p in params)
+            if covered >= hi - lo:
+                self._pending.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+                self._done.update(id(p) for p in params)
+                return
+        for p in params:
+            self._pending.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True))
+            self._done.add(id(p))
+
+    def finish(self):
+        w = self.world()
+        if w == 1:
+            return 1.0
+        rest = [p for p in self.params if id(p) not in self._done and p.grad is not None]
+        # merge contiguous leftovers into as few collectives as possible
+        run = []
+        for p in rest + [None]:
+            if p is not None and self._owns(p) and (not run or self.offs[id(run[-1])][0] + (self.offs[id(run[-1])][1] + 3) // 4 * 4
+                                                      == self.offs[id(p)][0]):
+                run.append(p)
+                continue
+            if run:
+                lo = self.offs[id(run[0])][0]
+                hi = self.offs[id(run[-1])][0] + self.offs[id(run[-1])][1]
+                self._pending.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+                run = []
+            if p is not None:
+                if self._owns(p):
+                    run = [p]
+                else:
+                    self._pending.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True))
+        for h in self._pending:
+            h.wait()
+        self._pending, self._done = [], set()
+        return 1.0 / w

@@ -24,7 +24,7 @@ def _loss_buf(ge, name):
     return ge.bufs.get(name, (1,), F32)
 
 
-def g_step(generator, discriminator, opt_g, noise_d, z, allreduce=None):
+def g_step(generator, discriminator, opt_g, noise_d, z):
     """WassersteinGeneratorLossVAE.train_ops body (src/wgan_loss.py:100-128). Returns the device loss tensor [1]."""
     ge, de = generator._engine(), discriminator._engine()
     B = noise_d.shape[0]
@@ -35,14 +35,12 @@ def g_step(generator, discriminator, opt_g, noise_d, z, allreduce=None):
     ops.wgan_loss(out, -1.0, loss)                                   # mean(-D(G(z)))
     d_img = de.backward(B, -1.0 / B, tag="gstep", params=False, want_dimg=True)
     ge.backward(lat, d_img, fake, tag="g")
-    if allreduce is not None:
-        allreduce(generator)
-    adam_step(opt_g)
+    adam_step(opt_g, grad_scale=ge.sync.finish())       # gradients averaged over ranks (no-op single-process)
     ge.pack()
     return loss
 
 
-def critic_step(generator, discriminator, opt_d, noise_d, z, real, clip=None, allreduce=None):
+def critic_step(generator, discriminator, opt_d, noise_d, z, real, clip=None):
     """WassersteinDiscriminatorLossVAE.train_ops body (src/wgan_loss.py:213-262)."""
     ge, de = generator._engine(), discriminator._engine()
     if clip is not None:                                             # src/wgan_loss.py:213-215
@@ -57,22 +55,18 @@ def critic_step(generator, discriminator, opt_d, noise_d, z, real, clip=None, al
     loss = _loss_buf(ge, "loss_d")
     ops.wgan_loss(out_fake, 1.0, loss, b=out_real, sign_b=-1.0)      # mean(D(G(z)) - D(x))
     de.backward(B, -1.0 / B, tag="real", params=True, acc=0.0)
-    de.backward(B, 1.0 / B, tag="fake", params=True, acc=1.0)
-    if allreduce is not None:
-        allreduce(discriminator)
-    adam_step(opt_d)
+    de.backward(B, 1.0 / B, tag="fake", params=True, acc=1.0, final=True)
+    adam_step(opt_d, grad_scale=de.sync.finish())
     de.pack()
     return loss
 
 
-def gp_step(generator, discriminator, opt_d, noise_d, z, real, eps_d, lambd=10.0, allreduce=None):
+def gp_step(generator, discriminator, opt_d, noise_d, z, real, eps_d, lambd=10.0):
     """WassersteinGradientPenaltyVAE.train_ops body (src/wgan_loss.py:357-388). Returns device [P, seed, ||g||]."""
     ge, de = generator._engine(), discriminator._engine()
     lat = latent(ge, noise_d, z)
     fake = ge.forward(lat, tag="g", training=generator.training)
     out3 = de.gradient_penalty(real, fake, eps_d, lambd=lambd)
-    if allreduce is not None:
-        allreduce(discriminator)
-    adam_step(opt_d)
+    adam_step(opt_d, grad_scale=de.sync.finish())
     de.pack()
     return out3

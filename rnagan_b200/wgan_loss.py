@@ -156,7 +156,7 @@ class WassersteinGeneratorLossVAE(_VAEConditioned, GeneratorLoss):
     def train_ops(self, generator, discriminator, optimizer_generator, device, batch_size, real_inputs, labels=None):
         _check_labels(labels, generator)
         noise_d, z = self._inputs(generator, real_inputs, device)
-        loss = steps.g_step(generator, discriminator, optimizer_generator, noise_d, z, allreduce=_allreduce_grads)
+        loss = steps.g_step(generator, discriminator, optimizer_generator, noise_d, z)
         return loss.item()
 
 
@@ -173,8 +173,7 @@ class WassersteinDiscriminatorLossVAE(_VAEConditioned, DiscriminatorLoss):
         _check_labels(labels, generator, discriminator)
         noise_d, z = self._inputs(generator, real_inputs, device)
         real = self._real(real_inputs, device)
-        loss = steps.critic_step(generator, discriminator, optimizer_discriminator, noise_d, z, real, clip=self.clip,
-                                 allreduce=_allreduce_grads)
+        loss = steps.critic_step(generator, discriminator, optimizer_discriminator, noise_d, z, real, clip=self.clip)
         return loss.item()
 
 
@@ -197,17 +196,7 @@ class WassersteinGradientPenaltyVAE(_VAEConditioned, DiscriminatorLoss):
         eps_d = discriminator._engine().bufs.get("eps", (1,), F32)
         eps_d.copy_(eps)
         out3 = steps.gp_step(generator, discriminator, optimizer_discriminator, noise_d, z, real, eps_d,
-                             lambd=self.lambd, allreduce=_allreduce_grads)
+                             lambd=self.lambd)
         return out3[0].item()
 
 
-# ------------------------------------------------------------------------------------------------ data parallel
-def _allreduce_grads(module):
-    """Batch-sharded training: average parameter gradients over ranks with NCCL when a process
-    group is initialised; single-process runs skip it."""
-    import torch.distributed as dist
-
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return
-    from .parallel import allreduce_mean_
-    allreduce_mean_([p.grad for p in module.parameters() if p.grad is not None])
