@@ -84,10 +84,19 @@ int rg_proj_wgrad(const void* z, const void* da0, float* dW, void* ws, size_t ws
  * generator layer 0 (src/dcgan.py:38-40), image-side im2col GEMMs. */
 int rg_gemm_nt(const void* A, const void* Bw, void* C, int M, int N, int K, int ldc, const float* col_scale,
                const float* col_shift, float slope, int out_f32, rg_stream_t st);
+/* same with explicit leading dimensions (K, N arbitrary: TMA zero-fills the k tail) */
+int rg_gemm_nt_ld(const void* A, int lda, const void* Bw, int ldb, void* C, int M, int N, int K, int ldc,
+                  const float* col_scale, const float* col_shift, float slope, int out_f32, rg_stream_t st);
+/* C[M,N] = act((A[M,K] . Bw[K,N]) * col_scale + col_shift) with Bw row-major [K][N]: the input gradient of an
+ * nn.Linear whose weight is [out=K][in=N] (autograd of src/betaVAE.py:31,76,86; betaVAE training, config 5). */
+int rg_gemm_nn(const void* A, int lda, const void* Bw, int ldb, void* C, int M, int N, int K, int ldc,
+               const float* col_scale, const float* col_shift, float slope, int out_f32, rg_stream_t st);
 /* C[M,N] (fp32, row-major) = beta*C + alpha*(*alpha_dev) * sum_r A[r,M]^T B[r,N]; A,B bf16 row-major [R][M],[R][N]. */
 size_t rg_gemm_tn_ws_bytes(int R, int M, int N);
 int rg_gemm_tn(const void* A, const void* Bm, float* C, void* ws, size_t ws_bytes, int R, int M, int N, float alpha,
                const float* alpha_dev, float beta, rg_stream_t st);
+int rg_gemm_tn_ld(const void* A, int lda, const void* Bm, int ldb, float* C, void* ws, size_t ws_bytes, int R, int M,
+                  int N, float alpha, const float* alpha_dev, float beta, rg_stream_t st);
 
 /* ---- HBM-bound kernels (rg_ops.cu) ----------------------------------------------------------------------- */
 /* Activations are bf16 NHWC viewed as [M rows][C channels]; per-channel vectors are fp32 [C].  Reductions need a
@@ -166,6 +175,24 @@ int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, f
 int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st);
 /* (x+1)/2 and NCHW -> NHWC fp32 (src/gan_utils.py:236-241) */
 int rg_tiles_to_unit_nhwc(const float* img, float* out, int B, int C, int S, rg_stream_t st);
+
+/* ---- betaVAE training step (config 5; src/betaVAE.py:96-115, 145-162, 216-236) ---------------------------- */
+/* dst = bf16(src * mul * scale), zero pad columns: train-mode Dropout(0.5) with the caller's keep mask (mul may be NULL) */
+int rg_mul_cast_pad_bf16(const float* src, const float* mul, float scale, void* dst, int rows, int cols, int cols_pad,
+                         rg_stream_t st);
+/* mulv fp32 [B][2Z] = (z_mean | z_logvar): z = mu + eps*exp(lv/2) (bf16); partial sums of 1+lv-mu^2-exp(lv).
+ * Returns the number of partials written (>0) or a negative error. */
+int rg_vae_reparam(const float* mulv, const float* eps, int B, int Z, void* z, float* partial, int partial_len,
+                   rg_stream_t st);
+/* out = tanh(pre); d_pre = gscale*(out-x)*(1-out^2) (bf16 [B][ldp]); partial sums of (out-x)^2; returns #partials */
+int rg_vae_recon(const float* pre, int ldp, const float* x, int B, int F, float gscale, void* dpre, float* partial,
+                 int partial_len, rg_stream_t st);
+/* dcat bf16 [B][2Z] = (dz + kscale*mu | dz*eps*0.5*exp(lv/2) - 0.5*kscale*(1-exp(lv))), kscale = beta/B */
+int rg_vae_latent_grad(const void* dz, const float* mulv, const float* eps, int B, int Z, float kscale, void* dcat,
+                       rg_stream_t st);
+/* out3 = {total, reconstruction, kl}: MSE + beta * mean_b(-0.5*sum_j(...)) (betaVAEloss) */
+int rg_vae_loss_finalize(const float* p_sse, int n1, const float* p_kld, int n2, int B, int F, float beta, float* out3,
+                         rg_stream_t st);
 
 #ifdef __cplusplus
 }

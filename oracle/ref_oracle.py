@@ -208,6 +208,23 @@ def vae_train_step(vae, optimizer, x, beta):
     return {k: v.item() for k, v in losses.items()}
 
 
+def vae_train_step_explicit(vae, optimizer, x, beta, keep_mask, eps):
+    """Same step with the two random draws made explicit (Dropout keep mask, reparametrisation noise), so that a
+    device implementation with its own RNG can be compared on identical randomness.  Equals vae_train_step when
+    keep_mask / eps are the tensors F.dropout / randn_like would have drawn."""
+    optimizer.zero_grad(set_to_none=True)
+    p = vae.encoder.encoder[0][0].p
+    h = x * keep_mask / (1.0 - p)
+    for blk in list(vae.encoder.encoder)[1:]:
+        h = blk(h)
+    mu, logvar = vae.z_mu(h), vae.z_logvar(h)
+    recon = vae.decoder(mu + eps * torch.exp(0.5 * logvar))
+    losses = vae_loss(x, recon, mu, logvar, beta, training=True)
+    losses["total_loss"].backward()
+    optimizer.step()
+    return {k: v.item() for k, v in losses.items()}
+
+
 # ------------------------------------------------------------------------------------------------ step logic
 def draw_noise(batch, dims):
     """CPU uniform(-0.3, 0.3) draw from the global generator, src/wgan_loss.py:100."""

@@ -34,6 +34,9 @@ SIGNATURES = {
     "rg_proj_wgrad_ws_bytes": (_sz, [_i, _i, _i]),
     "rg_proj_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp, _f, _vp]),
     "rg_gemm_nt": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp]),
+    "rg_gemm_nt_ld": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp]),
+    "rg_gemm_nn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp]),
+    "rg_gemm_tn_ld": (_i, [_vp, _i, _vp, _i, _vp, _vp, _sz, _i, _i, _i, _f, _vp, _f, _vp]),
     "rg_gemm_tn_ws_bytes": (_sz, [_i, _i, _i]),
     "rg_gemm_tn": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp, _f, _vp]),
     "rg_reduce_ws_bytes": (_sz, [_i, _i]),
@@ -64,6 +67,11 @@ SIGNATURES = {
     "rg_adam_step": (_i, [_vp, _i, _f, _f, _f, _f, _i, _i, _f, _f, _f, _vp]),
     "rg_clamp": (_i, [_vp, _sz, _f, _f, _vp]),
     "rg_tiles_to_unit_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "rg_mul_cast_pad_bf16": (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _vp]),
+    "rg_vae_reparam": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "rg_vae_recon": (_i, [_vp, _i, _vp, _i, _i, _f, _vp, _vp, _i, _vp]),
+    "rg_vae_latent_grad": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
+    "rg_vae_loss_finalize": (_i, [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp]),
 }
 
 _lib = None

@@ -60,13 +60,29 @@ class betaVAE(nn.Module):
         if eng is None or eng.device != p0.device:
             eng = _engine.EncoderEngine(self)
             self.__dict__["_rg_engine"] = eng
-        elif vers != self.__dict__.get("_rg_versions"):
-            eng.refresh()
+        elif vers != self.__dict__.get("_rg_versions") or self.__dict__.get("_rg_dirty", False):
+            eng.refresh()            # weights changed (load_state_dict / a fused training step)
         self.__dict__["_rg_versions"] = vers
+        self.__dict__["_rg_dirty"] = False
+        return eng
+
+    def _train_engine(self):
+        p0 = next(self.parameters())
+        if p0.device.type != "cuda":
+            raise RuntimeError("betaVAE training runs only on a CUDA (sm_100a) device: there is no CPU fallback")
+        eng = self.__dict__.get("_rg_train_engine")
+        vers = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if eng is None or eng.device != p0.device:
+            eng = _engine.VAETrainEngine(self)
+            self.__dict__["_rg_train_engine"] = eng
+        elif vers != self.__dict__.get("_rg_train_versions"):
+            eng.pack()
+        self.__dict__["_rg_train_versions"] = vers
         return eng
 
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.pop("_rg_engine", None)
+        self.__dict__.pop("_rg_train_engine", None)
         return super()._apply(fn, *args, **kwargs)
 
     # -- reference API -----------------------------------------------------------------------------------------
@@ -103,3 +119,40 @@ def betaVAEloss(x, x_recons, z_mean, z_logvar, beta, kld_weight=0.005, training=
     kld_loss = torch.mean(-0.5 * torch.sum(1 + z_logvar - z_mean ** 2 - z_logvar.exp(), dim=1), dim=0)
     total_loss = recons_loss + beta * kld_loss if training else recons_loss
     return {"total_loss": total_loss, "reconstruction_loss": recons_loss, "kl_loss": kld_loss}
+
+
+def train_step(model, optimizer, x, beta, keep_mask=None, eps=None):
+    """One betaVAE optimisation step on the sm_100a kernels: the body of the batch loop of ``train_betaVAE``
+    (src/betaVAE.py:221-235: zero_grad, forward, betaVAEloss, backward, optimizer.step()).
+
+    x: fp32 [B, in_channels].  keep_mask / eps: optional explicit Dropout keep mask (fp32 0/1 [B, in_channels]) and
+    reparametrisation noise (fp32 [B, z_dim]); drawn on the device when omitted.
+    Returns a device tensor [total_loss, reconstruction_loss, kl_loss] (no host synchronisation)."""
+    from .optim import adam_step
+    if not model.training:
+        raise RuntimeError("train_step needs model.train() (BatchNorm batch statistics, Dropout)")
+    eng = model._train_engine()
+    x = x.to(device=eng.device, dtype=torch.float32).contiguous()
+    out3 = eng.step(x, beta, keep_mask=keep_mask, eps=eps)
+    adam_step(optimizer, grad_scale=eng.sync.finish())
+    eng.pack()
+    model.__dict__["_rg_dirty"] = True
+    return out3
+
+
+def train_betaVAE(model, optimizer, dataloader, beta, num_epochs=1, scheduler=None, log_interval=None):
+    """Minimal epoch loop around ``train_step`` with the call order of the reference's train phase
+    (src/betaVAE.py:205-247): per batch step, then ``scheduler.step()``; returns the per-epoch mean losses."""
+    history = []
+    model.train()
+    for _ in range(num_epochs):
+        acc, n = torch.zeros(3, device=next(model.parameters()).device), 0
+        for batch in dataloader:
+            x = batch["rna_data"] if isinstance(batch, dict) else batch
+            acc += train_step(model, optimizer, x, beta)
+            n += 1
+            if scheduler is not None:
+                scheduler.step()
+        mean = (acc / max(n, 1)).tolist()
+        history.append({"total_loss": mean[0], "reconstruction_loss": mean[1], "kl_loss": mean[2]})
+    return history

@@ -174,18 +174,21 @@ static int encode_parity_maps(GemmMaps& maps, const void* hi, int B, int H, int 
 // ------------------------------------------------------------------------------------------------ reduce kernel
 template <int TAPS>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dW,
-                                                           int splits, int Cp, int Cs, float alpha,
+                                                           int splits, int Cp, int Cs, int Cs_out, float alpha,
                                                            const float* __restrict__ alpha_dev, float beta) {
-  const size_t n = static_cast<size_t>(Cp) * Cs;
+  // ws: [splits][TAPS][Cp][Cs] partials; dW: [Cp][Cs_out][TAPS] (Cs_out < Cs only for the padded plain-GEMM case)
+  const size_t n_out = static_cast<size_t>(Cp) * Cs_out;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
+  if (idx >= n_out) return;
+  const size_t n = static_cast<size_t>(Cp) * Cs;
+  const size_t src = (Cs_out == Cs) ? idx : (idx / Cs_out) * Cs + (idx % Cs_out);
   const float a = alpha * (alpha_dev ? __ldg(alpha_dev) : 1.0f);
   float acc[TAPS];
 #pragma unroll
   for (int t = 0; t < TAPS; ++t) acc[t] = 0.0f;
   for (int sp = 0; sp < splits; ++sp) {
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) acc[t] += ws[(static_cast<size_t>(sp) * TAPS + t) * n + idx];
+    for (int t = 0; t < TAPS; ++t) acc[t] += ws[(static_cast<size_t>(sp) * TAPS + t) * n + src];
   }
   float* o = dW + idx * TAPS;
   if (TAPS % 4 == 0) {
@@ -230,7 +233,7 @@ static WgradGeom wgrad_geom(int B, int H, int W, int Cp, int Cs, int taps) {
   w.g = make_boxing(B, H, W, 64);
   w.num_pb = w.g.tw * w.g.th * w.g.tb;
   w.m_tiles = ceil_div(Cp, 128);
-  w.chunks_s = Cs / 64;
+  w.chunks_s = ceil_div(Cs, 64);
   w.taps = taps;
   const int num_slabs = taps * w.chunks_s;
   w.slabs_per_tile = (num_slabs % 4 == 0) ? 4 : ((num_slabs % 2 == 0) ? 2 : 1);
@@ -241,7 +244,8 @@ static WgradGeom wgrad_geom(int B, int H, int W, int Cp, int Cs, int taps) {
 
 static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* taps, int B, int H, int W, int Cp, int Cs,
                         float* dW, void* ws, size_t ws_bytes, float alpha, const float* alpha_dev, float beta,
-                        cudaStream_t st) {
+                        cudaStream_t st, int Cs_out = -1) {
+  if (Cs_out < 0) Cs_out = Cs;
   int rc = ensure_attrs();
   if (rc) return rc;
   const size_t need = static_cast<size_t>(w.splits) * w.taps * Cp * Cs * sizeof(float);
@@ -263,13 +267,13 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
   const int grid = std::min(units, num_sms());
   gemm_wgrad_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
   RG_LAUNCH_CHECK("gemm_wgrad_kernel");
-  const size_t n = static_cast<size_t>(Cp) * Cs;
+  const size_t n = static_cast<size_t>(Cp) * Cs_out;
   if (w.taps == 16)
-    wgrad_reduce_kernel<16><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, alpha,
-                                                                                    alpha_dev, beta);
+    wgrad_reduce_kernel<16><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out,
+                                                                                    alpha, alpha_dev, beta);
   else
-    wgrad_reduce_kernel<1><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, alpha,
-                                                                                   alpha_dev, beta);
+    wgrad_reduce_kernel<1><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out,
+                                                                                   alpha, alpha_dev, beta);
   RG_LAUNCH_CHECK("wgrad_reduce_kernel");
   return 0;
 }
@@ -517,26 +521,37 @@ int rg_conv_up_img(const void* lo, const void* w_up, float* img, const float* bi
                         static_cast<cudaStream_t>(st_));
 }
 
-int rg_gemm_nt(const void* A, const void* Bw, void* C, int M, int N, int K, int ldc, const float* col_scale,
-               const float* col_shift, float slope, int out_f32, rg_stream_t st_) {
-  cudaStream_t st = static_cast<cudaStream_t>(st_);
-  RG_CHECK_ARG(A && Bw && C, "rg_gemm_nt: null pointer");
-  RG_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 64 == 0, "rg_gemm_nt: K must be a positive multiple of 64 (K=%d)", K);
-  RG_CHECK_ARG(ldc >= N && (out_f32 ? ldc % 4 == 0 : ldc % 8 == 0), "rg_gemm_nt: bad ldc %d", ldc);
+static int gemm_plain(const void* A, int lda, const void* Bw, int ldb, bool b_is_kn, void* C, int M, int N, int K,
+                      int ldc, const float* col_scale, const float* col_shift, float slope, int out_f32,
+                      cudaStream_t st, const char* name) {
+  RG_CHECK_ARG(A && Bw && C, "%s: null pointer", name);
+  RG_CHECK_ARG(M > 0 && N > 0 && K > 0 && lda >= K && lda % 8 == 0 && ldb % 8 == 0,
+               "%s: need lda >= K and lda, ldb multiples of 8 elements (M=%d N=%d K=%d lda=%d ldb=%d)", name, M, N, K,
+               lda, ldb);
+  RG_CHECK_ARG(ldc >= N && (out_f32 ? ldc % 4 == 0 : ldc % 8 == 0), "%s: bad ldc %d", name, ldc);
   GemmMaps maps;
   FwdArgs a;
   fill_common(a, M, 1, 1);
-  int rc = encode_map_4d(&maps.a[0], A, K, 1, 1, M, K, K, K, 64, 1, 1, kBlockM);
+  // K need not be a multiple of 64: the tensor maps carry the true K and TMA zero-fills the tail of the last k-block
+  int rc = encode_map_4d(&maps.a[0], A, K, 1, 1, M, lda, lda, lda, 64, 1, 1, kBlockM);
   if (rc) return rc;
   maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
   a.num_taps = 1;
-  a.chunks = K / 64;
+  a.chunks = ceil_div(K, 64);
   Tap t = {0, 0, 0, 0};
   a.taps[0][0] = t;
   a.n_total = N;
   a.block_n = pick_block_n(N, a.m_tiles);
+  if (b_is_kn && a.block_n < 64) a.block_n = 64;
   a.n_tiles = ceil_div(N, a.block_n);
-  rc = encode_map_2d(&maps.b, Bw, K, N, K, 64, a.block_n);
+  if (b_is_kn) {
+    // Bw is [K][N] row-major (e.g. an nn.Linear weight [out=K][in=N] used for its input gradient): MN-major B slabs
+    a.b_mn = 1;
+    a.b_tap_cols = 0;
+    rc = encode_map_2d(&maps.b, Bw, N, K, ldb, 64, 64);
+  } else {
+    rc = encode_map_2d(&maps.b, Bw, K, N, ldb, 64, a.block_n);
+  }
   if (rc) return rc;
   a.out = C;
   a.OH = 1; a.OW = 1; a.OC = ldc;
@@ -545,6 +560,24 @@ int rg_gemm_nt(const void* A, const void* Bw, void* C, int M, int N, int K, int 
   a.col_shift = col_shift;
   a.slope = slope;
   return launch_fwd(maps, a, out_f32 ? OUT_F32_NHWC : OUT_BF16_NHWC, st);
+}
+
+int rg_gemm_nt(const void* A, const void* Bw, void* C, int M, int N, int K, int ldc, const float* col_scale,
+               const float* col_shift, float slope, int out_f32, rg_stream_t st_) {
+  return gemm_plain(A, K, Bw, K, false, C, M, N, K, ldc, col_scale, col_shift, slope, out_f32,
+                    static_cast<cudaStream_t>(st_), "rg_gemm_nt");
+}
+
+int rg_gemm_nt_ld(const void* A, int lda, const void* Bw, int ldb, void* C, int M, int N, int K, int ldc,
+                  const float* col_scale, const float* col_shift, float slope, int out_f32, rg_stream_t st_) {
+  return gemm_plain(A, lda, Bw, ldb, false, C, M, N, K, ldc, col_scale, col_shift, slope, out_f32,
+                    static_cast<cudaStream_t>(st_), "rg_gemm_nt_ld");
+}
+
+int rg_gemm_nn(const void* A, int lda, const void* Bw, int ldb, void* C, int M, int N, int K, int ldc,
+               const float* col_scale, const float* col_shift, float slope, int out_f32, rg_stream_t st_) {
+  return gemm_plain(A, lda, Bw, ldb, true, C, M, N, K, ldc, col_scale, col_shift, slope, out_f32,
+                    static_cast<cudaStream_t>(st_), "rg_gemm_nn");
 }
 
 size_t rg_conv_wgrad_ws_bytes(int B, int H, int W, int Cp, int Cs) {
@@ -607,25 +640,38 @@ int rg_proj_wgrad(const void* z, const void* da0, float* dW, void* ws, size_t ws
 }
 
 size_t rg_gemm_tn_ws_bytes(int R, int M, int N) {
-  if (R <= 0 || M <= 0 || N < 64) return 0;
-  WgradGeom w = wgrad_geom(R, 1, 1, M, N, 1);
-  return static_cast<size_t>(w.splits) * M * N * sizeof(float);
+  if (R <= 0 || M <= 0 || N < 1) return 0;
+  const int Nw = (N + 3) / 4 * 4;
+  WgradGeom w = wgrad_geom(R, 1, 1, M, Nw, 1);
+  return static_cast<size_t>(w.splits) * M * Nw * sizeof(float);
+}
+
+static int gemm_tn_impl(const void* A, int lda, const void* Bm, int ldb, float* C, void* ws, size_t ws_bytes, int R,
+                        int M, int N, float alpha, const float* alpha_dev, float beta, cudaStream_t st) {
+  RG_CHECK_ARG(A && Bm && C, "rg_gemm_tn: null pointer");
+  RG_CHECK_ARG(R > 0 && M > 0 && N > 0 && lda % 8 == 0 && ldb % 8 == 0 && lda >= M && ldb >= N,
+               "rg_gemm_tn: need lda >= M, ldb >= N, both multiples of 8 (M=%d N=%d lda=%d ldb=%d)", M, N, lda, ldb);
+  const int Nw = (N + 3) / 4 * 4;     // partials use a 16-byte aligned row stride; the final reduce writes N columns
+  WgradGeom w = wgrad_geom(R, 1, 1, M, Nw, 1);
+  GemmMaps maps;
+  int rc = encode_map_4d(&maps.a[0], Bm, N, 1, 1, R, ldb, ldb, ldb, 64, 1, 1, 64);
+  if (rc) return rc;
+  maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+  rc = encode_map_4d(&maps.b, A, M, 1, 1, R, lda, lda, lda, 64, 1, 1, 64);
+  if (rc) return rc;
+  Tap taps[1] = {{0, 0, 0, 0}};
+  return launch_wgrad(maps, w, taps, R, 1, 1, M, Nw, C, ws, ws_bytes, alpha, alpha_dev, beta, st, N);
 }
 
 int rg_gemm_tn(const void* A, const void* Bm, float* C, void* ws, size_t ws_bytes, int R, int M, int N, float alpha,
                const float* alpha_dev, float beta, rg_stream_t st_) {
-  cudaStream_t st = static_cast<cudaStream_t>(st_);
-  RG_CHECK_ARG(A && Bm && C, "rg_gemm_tn: null pointer");
-  RG_CHECK_ARG(R > 0 && M % 8 == 0 && N % 64 == 0, "rg_gemm_tn: need M %% 8 == 0, N %% 64 == 0 (M=%d N=%d)", M, N);
-  WgradGeom w = wgrad_geom(R, 1, 1, M, N, 1);
-  GemmMaps maps;
-  int rc = encode_map_4d(&maps.a[0], Bm, N, 1, 1, R, N, N, N, 64, 1, 1, 64);
-  if (rc) return rc;
-  maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
-  rc = encode_map_4d(&maps.b, A, M, 1, 1, R, M, M, M, 64, 1, 1, 64);
-  if (rc) return rc;
-  Tap taps[1] = {{0, 0, 0, 0}};
-  return launch_wgrad(maps, w, taps, R, 1, 1, M, N, C, ws, ws_bytes, alpha, alpha_dev, beta, st);
+  return gemm_tn_impl(A, M, Bm, N, C, ws, ws_bytes, R, M, N, alpha, alpha_dev, beta, static_cast<cudaStream_t>(st_));
+}
+
+int rg_gemm_tn_ld(const void* A, int lda, const void* Bm, int ldb, float* C, void* ws, size_t ws_bytes, int R, int M,
+                  int N, float alpha, const float* alpha_dev, float beta, rg_stream_t st_) {
+  return gemm_tn_impl(A, lda, Bm, ldb, C, ws, ws_bytes, R, M, N, alpha, alpha_dev, beta,
+                      static_cast<cudaStream_t>(st_));
 }
 
 }  // extern "C"

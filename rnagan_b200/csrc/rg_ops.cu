@@ -759,6 +759,110 @@ __global__ void nchw_to_unit_nhwc_kernel(const float* __restrict__ img, float* _
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ betaVAE training
+// dst[r][c] = bf16(src[r][c] * mul[r][c] * scale) for c < cols, 0 for the pad columns (Dropout(0.5) in train mode,
+// src/betaVAE.py:26-27, with the caller's mask; mul == nullptr -> plain cast)
+__global__ void mul_cast_pad_kernel(const float* __restrict__ src, const float* __restrict__ mul, float scale,
+                                    __nv_bfloat16* __restrict__ dst, int rows, int cols, int cols_pad) {
+  const size_t n = static_cast<size_t>(rows) * cols_pad;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / cols_pad;
+    const int c = static_cast<int>(i - r * cols_pad);
+    float v = 0.0f;
+    if (c < cols) {
+      v = src[r * cols + c] * scale;
+      if (mul) v *= mul[r * cols + c];
+    }
+    dst[i] = __float2bfloat16(v);
+  }
+}
+__device__ __forceinline__ float block_sum_256(float s, float* sm) {
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sm[threadIdx.x] += sm[threadIdx.x + w];
+    __syncthreads();
+  }
+  return sm[0];
+}
+// z = mu + eps*exp(lv/2) (src/betaVAE.py:96-100); partial[block] = sum(1 + lv - mu^2 - exp(lv)) (src/betaVAE.py:148)
+__global__ void __launch_bounds__(256) vae_reparam_kernel(const float* __restrict__ mulv, const float* __restrict__ eps,
+                                                          int B, int Z, __nv_bfloat16* __restrict__ z,
+                                                          float* __restrict__ partial) {
+  __shared__ float sm[256];
+  const size_t n = static_cast<size_t>(B) * Z;
+  float s = 0.0f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / Z;
+    const int j = static_cast<int>(i - b * Z);
+    const float mu = mulv[b * 2 * Z + j], lv = mulv[b * 2 * Z + Z + j];
+    const float e = expf(lv);
+    z[i] = __float2bfloat16(mu + eps[i] * expf(0.5f * lv));
+    s += 1.0f + lv - mu * mu - e;
+  }
+  const float t = block_sum_256(s, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+// out = tanh(pre); d_pre = gscale*(out - x)*(1 - out^2) (bf16, pad columns zero); partial[block] = sum (out - x)^2
+__global__ void __launch_bounds__(256) vae_recon_kernel(const float* __restrict__ pre, int ldp,
+                                                        const float* __restrict__ x, int B, int F, float gscale,
+                                                        __nv_bfloat16* __restrict__ dpre, float* __restrict__ partial) {
+  __shared__ float sm[256];
+  const size_t n = static_cast<size_t>(B) * ldp;
+  float s = 0.0f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / ldp;
+    const int j = static_cast<int>(i - b * ldp);
+    float d = 0.0f;
+    if (j < F) {
+      const float o = tanhf(pre[i]);
+      const float e = o - x[b * F + j];
+      s += e * e;
+      d = gscale * e * (1.0f - o * o);
+    }
+    dpre[i] = __float2bfloat16(d);
+  }
+  const float t = block_sum_256(s, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+// d_mu = dz + kscale*mu ; d_lv = dz*eps*0.5*exp(lv/2) - 0.5*kscale*(1 - exp(lv)), kscale = beta/B
+__global__ void vae_latent_grad_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ mulv,
+                                       const float* __restrict__ eps, int B, int Z, float kscale,
+                                       __nv_bfloat16* __restrict__ dcat) {
+  const size_t n = static_cast<size_t>(B) * Z;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / Z;
+    const int j = static_cast<int>(i - b * Z);
+    const float mu = mulv[b * 2 * Z + j], lv = mulv[b * 2 * Z + Z + j];
+    const float g = __bfloat162float(dz[i]);
+    dcat[b * 2 * Z + j] = __float2bfloat16(g + kscale * mu);
+    dcat[b * 2 * Z + Z + j] = __float2bfloat16(g * eps[i] * 0.5f * expf(0.5f * lv) - 0.5f * kscale * (1.0f - expf(lv)));
+  }
+}
+// out3 = {total, recon, kld}: recon = sse/(B*F); kld = -0.5*sum/B; total = recon + beta*kld (src/betaVAE.py:145-162)
+__global__ void __launch_bounds__(256) vae_loss_finalize_kernel(const float* __restrict__ p_sse, int n1,
+                                                                const float* __restrict__ p_kld, int n2, float inv_bf,
+                                                                float inv_b, float beta, float* __restrict__ out3) {
+  __shared__ float sm[256];
+  float a = 0.0f, b = 0.0f;
+  for (int i = threadIdx.x; i < n1; i += blockDim.x) a += p_sse[i];
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) b += p_kld[i];
+  const float sse = block_sum_256(a, sm);
+  __syncthreads();
+  const float ks = block_sum_256(b, sm);
+  if (threadIdx.x == 0) {
+    const float recon = sse * inv_bf, kld = -0.5f * ks * inv_b;
+    out3[0] = recon + beta * kld;
+    out3[1] = recon;
+    out3[2] = kld;
+  }
+}
+
 }  // namespace rg
 
 using namespace rg;
@@ -1029,6 +1133,57 @@ int rg_tiles_to_unit_nhwc(const float* img, float* out, int B, int C, int S, rg_
   const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   nchw_to_unit_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(img, out, B, C, S);
   RG_LAUNCH_CHECK("rg_tiles_to_unit_nhwc");
+  return 0;
+}
+
+
+int rg_mul_cast_pad_bf16(const float* src, const float* mul, float scale, void* dst, int rows, int cols, int cols_pad,
+                         rg_stream_t st) {
+  RG_CHECK_ARG(src && dst && rows > 0 && cols > 0 && cols_pad >= cols, "rg_mul_cast_pad_bf16: bad arguments");
+  const size_t n = static_cast<size_t>(rows) * cols_pad;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  mul_cast_pad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(src, mul, scale, static_cast<bf16*>(dst), rows,
+                                                                       cols, cols_pad);
+  RG_LAUNCH_CHECK("rg_mul_cast_pad_bf16");
+  return 0;
+}
+
+int rg_vae_reparam(const float* mulv, const float* eps, int B, int Z, void* z, float* partial, int partial_len,
+                   rg_stream_t st) {
+  RG_CHECK_ARG(mulv && eps && z && partial && partial_len >= 1, "rg_vae_reparam: bad arguments");
+  const int grid = std::min(partial_len, 256);
+  vae_reparam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(mulv, eps, B, Z, static_cast<bf16*>(z), partial);
+  RG_LAUNCH_CHECK("rg_vae_reparam");
+  return grid;
+}
+
+int rg_vae_recon(const float* pre, int ldp, const float* x, int B, int F, float gscale, void* dpre, float* partial,
+                 int partial_len, rg_stream_t st) {
+  RG_CHECK_ARG(pre && x && dpre && partial && partial_len >= 1 && ldp >= F, "rg_vae_recon: bad arguments");
+  const int grid = std::min(partial_len, 256);
+  vae_recon_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(pre, ldp, x, B, F, gscale, static_cast<bf16*>(dpre),
+                                                                    partial);
+  RG_LAUNCH_CHECK("rg_vae_recon");
+  return grid;
+}
+
+int rg_vae_latent_grad(const void* dz, const float* mulv, const float* eps, int B, int Z, float kscale, void* dcat,
+                       rg_stream_t st) {
+  RG_CHECK_ARG(dz && mulv && eps && dcat, "rg_vae_latent_grad: bad arguments");
+  const size_t n = static_cast<size_t>(B) * Z;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  vae_latent_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(static_cast<const bf16*>(dz), mulv, eps, B, Z,
+                                                                          kscale, static_cast<bf16*>(dcat));
+  RG_LAUNCH_CHECK("rg_vae_latent_grad");
+  return 0;
+}
+
+int rg_vae_loss_finalize(const float* p_sse, int n1, const float* p_kld, int n2, int B, int F, float beta, float* out3,
+                         rg_stream_t st) {
+  RG_CHECK_ARG(p_sse && p_kld && out3 && B > 0 && F > 0, "rg_vae_loss_finalize: bad arguments");
+  vae_loss_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(st)>>>(
+      p_sse, n1, p_kld, n2, 1.0f / (static_cast<float>(B) * static_cast<float>(F)), 1.0f / B, beta, out3);
+  RG_LAUNCH_CHECK("rg_vae_loss_finalize");
   return 0;
 }
 

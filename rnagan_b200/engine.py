@@ -59,10 +59,11 @@ class _BNState:
 class _BN:
     """One BatchNorm2d layer: parameter references + per-channel work vectors keyed by pass tag."""
 
-    def __init__(self, mod, device):
+    def __init__(self, mod, device, slope=SLOPE):
         self.mod = mod
         self.C = mod.num_features
         self.device = device
+        self.slope = slope
         self._states = {}
 
     def st(self, tag):
@@ -84,16 +85,16 @@ class _BN:
                 s.rstd.copy_((m.running_var + m.eps).rsqrt())
                 s.scale.copy_(m.weight * s.rstd)
                 s.shift.copy_(m.bias - s.mean * s.scale)
-        ops.bn_act(a, s.scale, s.shift, SLOPE, h, M, self.C)
+        ops.bn_act(a, s.scale, s.shift, self.slope, h, M, self.C)
 
     def backward(self, dh, a, da, M, param_grads=False, acc_gamma=0.0, acc_beta=0.0, add=None, du_out=None, tag=""):
         """da = d(loss)/d(a) from dh = d(loss)/d(h); optionally (accumulating) gamma/beta gradients."""
         s = self.st(tag)
-        ops.bn_bwd_reduce(dh, a, s.mean, s.rstd, s.scale, s.shift, SLOPE, M, self.C, s.bsums)
+        ops.bn_bwd_reduce(dh, a, s.mean, s.rstd, s.scale, s.shift, self.slope, M, self.C, s.bsums)
         if param_grads:
             ops.bn_param_grads(s.bsums, _grad_of(self.mod.weight), _grad_of(self.mod.bias), self.C, acc_gamma,
                                acc_beta)
-        ops.bn_bwd_apply(dh, a, add, s.mean, s.rstd, s.scale, s.shift, SLOPE, s.bsums, M, self.C, da, du_out)
+        ops.bn_bwd_apply(dh, a, add, s.mean, s.rstd, s.scale, s.shift, self.slope, s.bsums, M, self.C, da, du_out)
 
 
 def _check_act(mod, slope, what):
@@ -491,3 +492,123 @@ class EncoderEngine:
         lv = g("zlv", (B, self.w_lv.shape[0]), F32)
         ops.gemm_nt(h, self.w_lv, out=lv, col_shift=self.b_lv)
         return z, lv, h[:, :self.layers[-1][4]].float()
+
+
+# ====================================================================================================== VAE training
+class VAETrainEngine:
+    """betaVAE training step (BASELINE config 5; inner step of train_betaVAE, src/betaVAE.py:216-236):
+    Dropout -> 3x[Linear, BatchNorm1d(train), LeakyReLU(0.01)] -> (z_mu | z_logvar) -> reparametrise ->
+    2x[Linear, BN1d, LeakyReLU] -> Linear + Tanh; loss = MSE + beta * KLD (betaVAEloss, :145-162); backward; gradients
+    land in the flat buffer for the fused Adam.  Every Linear is a tcgen05 GEMM (forward NT, input gradient NN read
+    MN-major from the same bf16 weight copy, weight gradient TN with split-K); BN1d reuses the BN2d kernels with M = B."""
+
+    def __init__(self, vae):
+        dev = next(vae.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("VAETrainEngine needs the betaVAE on a CUDA device (there is no CPU path)")
+        self.vae, self.device = vae, dev
+        self.bufs = _Bufs(dev)
+        enc = list(vae.encoder.encoder)[1:]
+        dec = list(vae.decoder)
+        self.p_drop = vae.encoder.encoder[0][0].p
+        self.blocks = []                      # (linear, _BN) for the 3 encoder + 2 decoder hidden blocks
+        for blk in enc + dec[:-1]:
+            self.blocks.append((blk[0], _BN(blk[1], dev, slope=blk[2].negative_slope)))
+        self.n_enc = len(enc)
+        self.last = dec[-1][0]
+        self.F = self.last.weight.shape[0]
+        self.Z = vae.z_mu.weight.shape[0]
+        self.Fp = (self.F + 7) // 8 * 8
+        self.w = [torch.empty(l.weight.shape[0], (l.weight.shape[1] + 7) // 8 * 8, dtype=BF16, device=dev)
+                  for l, _ in self.blocks]
+        self.w_last = torch.empty(self.F, self.last.weight.shape[1], dtype=BF16, device=dev)
+        self.w_cat = torch.empty(2 * self.Z, self.Z, dtype=BF16, device=dev)
+        self.b_cat = torch.empty(2 * self.Z, dtype=F32, device=dev)
+        self.partial = torch.zeros(2, 256, dtype=F32, device=dev)
+        self.out3 = torch.zeros(3, dtype=F32, device=dev)
+        self.sync = GradSync(vae)
+        self.pack()
+
+    def pack(self):
+        for (l, _), w in zip(self.blocks, self.w):
+            ops.cast_pad_bf16(l.weight.detach(), w.shape[1], out=w)
+        ops.cast_pad_bf16(self.last.weight.detach(), self.w_last.shape[1], out=self.w_last)
+        ops.cast_pad_bf16(self.vae.z_mu.weight.detach(), self.Z, out=self.w_cat[:self.Z])
+        ops.cast_pad_bf16(self.vae.z_logvar.weight.detach(), self.Z, out=self.w_cat[self.Z:])
+        with torch.no_grad():
+            self.b_cat[:self.Z].copy_(self.vae.z_mu.bias)
+            self.b_cat[self.Z:].copy_(self.vae.z_logvar.bias)
+
+    def step(self, x, beta, keep_mask=None, eps=None):
+        """Forward + backward of one batch x fp32 [B, F] (device).  keep_mask: fp32 0/1 [B, F] dropout keep mask,
+        eps: fp32 [B, Z] reparametrisation noise (both drawn with torch's device RNG when omitted).
+        Returns the device tensor [total, reconstruction, kl]; gradients are in p.grad (flat buffer)."""
+        g = self.bufs.get
+        B, F, Z = x.shape[0], self.F, self.Z
+        if keep_mask is None:
+            keep_mask = (torch.rand(B, F, device=self.device) >= self.p_drop).float()
+        if eps is None:
+            eps = torch.randn(B, Z, device=self.device)
+        # ---------------- forward
+        xd = g("xd", (B, self.Fp))
+        ops.mul_cast_pad_bf16(x, xd, mul=keep_mask, scale=1.0 / (1.0 - self.p_drop))
+        h, hs, As = xd, [xd], []
+        for i, ((lin, bn), w) in enumerate(zip(self.blocks, self.w)):
+            if i == self.n_enc:                 # latent sits between encoder and decoder
+                mulv = g("mulv", (B, 2 * Z), F32)
+                ops.gemm_nt(h, self.w_cat, out=mulv, col_shift=self.b_cat)
+                z = g("z", (B, Z))
+                n_kld = ops.vae_reparam(mulv, eps, z, self.partial[1])
+                h_lat, h = h, z
+                hs.append(z)
+            N, K = lin.weight.shape
+            a = g(f"a{i}", (B, N))
+            ops.gemm_nt(h, w, out=a, col_shift=lin.bias.detach(), K=K)
+            hn = g(f"h{i}", (B, N))
+            bn.forward(a, hn, B, training=True, tag="vae")
+            As.append(a)
+            h = hn
+            hs.append(hn)
+        pre = g("pre", (B, self.Fp), F32)
+        ops.gemm_nt(h, self.w_last, out=pre, col_shift=self.last.bias.detach(), N=F)
+        dpre = g("dpre", (B, self.Fp))
+        n_sse = ops.vae_recon(pre, x, 2.0 / (B * F), dpre, self.partial[0])
+        ops.vae_loss_finalize(self.partial[0], n_sse, self.partial[1], n_kld, B, F, beta, self.out3)
+        # ---------------- backward
+        tmp = g("tmpcols", (max(self.Fp, 2 * Z, 8192),), F32)
+        ops.gemm_tn(dpre, h, out=_grad_of(self.last.weight), M=F)
+        ops.col_sum(dpre, B, self.Fp, tmp, tmp, 0.0)
+        with torch.no_grad():
+            _grad_of(self.last.bias).copy_(tmp[:F])
+        dh = g("dh_last", (B, self.last.weight.shape[1]))
+        ops.gemm_nn(dpre, self.w_last, out=dh, K=F)
+        self.sync.layer_done(self.last.weight, self.last.bias)
+        hidx = len(hs) - 2                       # hs[hidx] is the input of the block being differentiated
+        for i in range(len(self.blocks) - 1, -1, -1):
+            (lin, bn), w = self.blocks[i], self.w[i]
+            N, K = lin.weight.shape
+            da = g(f"da{i}", (B, N))
+            bn.backward(dh, As[i], da, B, param_grads=True, tag="vae")
+            hin = hs[hidx]
+            ops.gemm_tn(da, hin, out=_grad_of(lin.weight), N=K)
+            ops.col_sum(da, B, N, tmp, _grad_of(lin.bias), 0.0)
+            self.sync.layer_done(lin.weight, lin.bias, bn.mod.weight, bn.mod.bias)
+            if i > 0:
+                dh = g(f"dh{i}", (B, K))
+                ops.gemm_nn(da, w, out=dh, N=K)
+            hidx -= 1
+            if i == self.n_enc:                 # crossing the latent: dz -> (d_mu | d_logvar) -> encoder output
+                dcat = g("dcat", (B, 2 * Z))
+                ops.vae_latent_grad(dh, mulv, eps, beta / B, dcat)
+                ops.gemm_tn(dcat[:, :Z], h_lat, out=_grad_of(self.vae.z_mu.weight))
+                ops.gemm_tn(dcat[:, Z:], h_lat, out=_grad_of(self.vae.z_logvar.weight))
+                ops.col_sum(dcat, B, 2 * Z, tmp, tmp, 0.0)
+                with torch.no_grad():
+                    _grad_of(self.vae.z_mu.bias).copy_(tmp[:Z])
+                    _grad_of(self.vae.z_logvar.bias).copy_(tmp[Z:2 * Z])
+                self.sync.layer_done(self.vae.z_mu.weight, self.vae.z_mu.bias, self.vae.z_logvar.weight,
+                                     self.vae.z_logvar.bias)
+                dh = g("dh_lat", (B, Z))
+                ops.gemm_nn(dcat, self.w_cat, out=dh)
+                hidx -= 1
+        return self.out3

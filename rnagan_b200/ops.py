@@ -17,12 +17,15 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def _chk(t, dtype, name):
+def _chk(t, dtype, name, rows_strided=False):
     if t.device.type != "cuda":
         raise ValueError(f"{name} must be a CUDA tensor (no CPU fallback)")
     if t.dtype != dtype:
         raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
-    if not t.is_contiguous():
+    if rows_strided:
+        if t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError(f"{name} must be a 2-D tensor with unit column stride")
+    elif not t.is_contiguous():
         raise ValueError(f"{name} must be contiguous")
 
 
@@ -168,33 +171,50 @@ def proj_wgrad(z, da0, dW, alpha=1.0, alpha_dev=None, beta=0.0):
     return dW
 
 
-def gemm_nt(A, Bw, out=None, col_scale=None, col_shift=None, slope=1.0, out_f32=False, N=None):
-    """C[M, N] = lrelu((A[M, K] @ Bw[N, K]^T) * col_scale + col_shift)."""
-    _chk(A, BF16, "A"); _chk(Bw, BF16, "Bw")
-    M, K = A.shape
+def gemm_nt(A, Bw, out=None, col_scale=None, col_shift=None, slope=1.0, out_f32=False, N=None, K=None):
+    """C[M, N] = lrelu((A[M, K] @ Bw[N, K]^T) * col_scale + col_shift); rows of A / Bw / out may be strided."""
+    _chk(A, BF16, "A", True); _chk(Bw, BF16, "Bw", True)
+    M = A.shape[0]
+    K = A.shape[1] if K is None else K
     N = Bw.shape[0] if N is None else N
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32 if out_f32 else BF16, device=A.device)
-    ldc = out.stride(0)
     _prof("gemm_nt", 2.0 * M * N * K, lambda: _lib.check(
-        _lib.lib().rg_gemm_nt(_p(A), _p(Bw), _p(out), M, N, K, ldc, _p(col_scale), _p(col_shift), float(slope),
-                              int(out.dtype == torch.float32), _st()), "rg_gemm_nt"))
+        _lib.lib().rg_gemm_nt_ld(_p(A), A.stride(0), _p(Bw), Bw.stride(0), _p(out), M, N, K, out.stride(0),
+                                 _p(col_scale), _p(col_shift), float(slope), int(out.dtype == torch.float32), _st()),
+        "rg_gemm_nt_ld"))
     return out
 
 
-def gemm_tn(A, Bm, out=None, alpha=1.0, alpha_dev=None, beta=0.0):
-    """C[M, N] fp32 = beta*C + alpha * A[R, M]^T @ Bm[R, N]."""
-    _chk(A, BF16, "A"); _chk(Bm, BF16, "Bm")
-    R, M = A.shape
-    N = Bm.shape[1]
+def gemm_nn(A, Bw, out=None, col_scale=None, col_shift=None, slope=1.0, out_f32=False, N=None, K=None):
+    """C[M, N] = A[M, K] @ Bw[K, N] with Bw row-major (the input gradient of an nn.Linear with weight [K, N])."""
+    _chk(A, BF16, "A", True); _chk(Bw, BF16, "Bw", True)
+    M = A.shape[0]
+    K = A.shape[1] if K is None else K
+    N = Bw.shape[1] if N is None else N
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32 if out_f32 else BF16, device=A.device)
+    _prof("gemm_nn", 2.0 * M * N * K, lambda: _lib.check(
+        _lib.lib().rg_gemm_nn(_p(A), A.stride(0), _p(Bw), Bw.stride(0), _p(out), M, N, K, out.stride(0),
+                              _p(col_scale), _p(col_shift), float(slope), int(out.dtype == torch.float32), _st()),
+        "rg_gemm_nn"))
+    return out
+
+
+def gemm_tn(A, Bm, out=None, alpha=1.0, alpha_dev=None, beta=0.0, M=None, N=None):
+    """C[M, N] fp32 (dense) = beta*C + alpha * A[R, M]^T @ Bm[R, N]; rows of A / Bm may be strided."""
+    _chk(A, BF16, "A", True); _chk(Bm, BF16, "Bm", True)
+    R = A.shape[0]
+    M = A.shape[1] if M is None else M
+    N = Bm.shape[1] if N is None else N
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=A.device)
     L = _lib.lib()
     nbytes = L.rg_gemm_tn_ws_bytes(R, M, N)
     ws = _workspace(nbytes, A.device)
     _prof("gemm_tn", 2.0 * R * M * N, lambda: _lib.check(
-        L.rg_gemm_tn(_p(A), _p(Bm), _p(out), _p(ws), ws.numel() * 4, R, M, N, float(alpha), _p(alpha_dev),
-                     float(beta), _st()), "rg_gemm_tn"))
+        L.rg_gemm_tn_ld(_p(A), A.stride(0), _p(Bm), Bm.stride(0), _p(out), _p(ws), ws.numel() * 4, R, M, N,
+                        float(alpha), _p(alpha_dev), float(beta), _st()), "rg_gemm_tn_ld"))
     return out
 
 
@@ -372,3 +392,39 @@ class AdamTable:
         _lib.check(_lib.lib().rg_adam_step(_p(self.table), self.num_chunks, float(lr), float(beta1), float(beta2),
                                            float(eps), int(step), int(clamp is not None), float(lo), float(hi),
                                            float(grad_scale), _st()), "rg_adam_step")
+
+
+# ------------------------------------------------------------------------------------------------ betaVAE training
+def mul_cast_pad_bf16(src, out, mul=None, scale=1.0):
+    rows, cols = src.shape
+    _lib.check(_lib.lib().rg_mul_cast_pad_bf16(_p(src), _p(mul), float(scale), _p(out), rows, cols, out.shape[1],
+                                               _st()), "rg_mul_cast_pad_bf16")
+    return out
+
+
+def vae_reparam(mulv, eps, z, partial):
+    B, Z = eps.shape
+    n = _lib.lib().rg_vae_reparam(_p(mulv), _p(eps), B, Z, _p(z), _p(partial), partial.numel(), _st())
+    if n <= 0:
+        _lib.check(n if n < 0 else -1, "rg_vae_reparam")
+    return n
+
+
+def vae_recon(pre, x, gscale, dpre, partial):
+    B, F = x.shape
+    n = _lib.lib().rg_vae_recon(_p(pre), pre.stride(0), _p(x), B, F, float(gscale), _p(dpre), _p(partial),
+                                partial.numel(), _st())
+    if n <= 0:
+        _lib.check(n if n < 0 else -1, "rg_vae_recon")
+    return n
+
+
+def vae_latent_grad(dz, mulv, eps, kscale, dcat):
+    B, Z = eps.shape
+    _lib.check(_lib.lib().rg_vae_latent_grad(_p(dz), _p(mulv), _p(eps), B, Z, float(kscale), _p(dcat), _st()),
+               "rg_vae_latent_grad")
+
+
+def vae_loss_finalize(p_sse, n1, p_kld, n2, B, F, beta, out3):
+    _lib.check(_lib.lib().rg_vae_loss_finalize(_p(p_sse), n1, _p(p_kld), n2, B, F, float(beta), _p(out3), _st()),
+               "rg_vae_loss_finalize")

@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _rel(a, b):
-    a = a.float()
-    b = b.float()
+    a = a.float().cpu()
+    b = b.float().cpu()
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
 
@@ -196,3 +196,29 @@ def test_img_channel_sum_and_im2col(cuda_dev):
     got = col.float().view(5, 32 * 32, 16, 4)
     assert (got[..., :3] - _bf(unf)).abs().max().item() < 1e-6
     assert got[..., 3].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 6000, 19198), (128, 2048, 4000), (32, 300, 6000), (128, 4000, 2048)])
+def test_gemm_nn_and_ragged_k(cuda_dev, M, N, K):
+    """C = A[M,K] @ W[K,N] with W row-major (nn.Linear input gradient), K and N not multiples of 64."""
+    from rnagan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp)
+    A[:, :K] = _bf(torch.randn(M, K, generator=g))
+    Np = (N + 7) // 8 * 8
+    W = torch.zeros(K, Np)
+    W[:, :N] = _bf(torch.randn(K, N, generator=g) * 0.05)
+    ref = A[:, :K] @ W[:, :N]
+    out = ops.gemm_nn(A.to(cuda_dev).to(torch.bfloat16), W.to(cuda_dev).to(torch.bfloat16), out_f32=True, N=N, K=K)
+    assert _rel(out, ref) < 2e-3
+    # NT with ragged K (true K in the tensor map, zero-filled tail)
+    Wt = torch.zeros(N, Kp)
+    Wt[:, :K] = _bf(torch.randn(N, K, generator=g) * 0.05)
+    out2 = ops.gemm_nt(A.to(cuda_dev).to(torch.bfloat16), Wt.to(cuda_dev).to(torch.bfloat16), out_f32=True, K=K)
+    assert _rel(out2, A[:, :K] @ Wt[:, :K].t()) < 2e-3
+    # TN with a ragged N (weight gradient [M_out, N_in] with N_in = K here)
+    dY = _bf(torch.randn(M, 200, generator=g)).to(cuda_dev).to(torch.bfloat16)
+    dW = ops.gemm_tn(dY, A.to(cuda_dev).to(torch.bfloat16), N=K)
+    assert dW.shape == (200, K)
+    assert _rel(dW, dY.float().t() @ A[:, :K].to(cuda_dev)) < 2e-3

@@ -148,3 +148,50 @@ def test_checkpoint_roundtrip_and_errors(cuda_dev):
     tr.generator.label_type = "required"
     with pytest.raises(Exception, match="GAN model requires labels for training"):
         tr.train_iter()
+
+
+def test_vae_train_step_matches_oracle(cuda_dev):
+    """betaVAE training step (config 5) vs the oracle on identical Dropout mask / reparametrisation noise:
+    losses within 2e-2 relative, per-parameter gradient cosine >= 0.98 (bf16 operands), BN1d running stats, and the
+    frozen-encoder path sees the updated weights afterwards."""
+    from rnagan_b200 import betaVAE as bv
+    feats, B, beta = 300, 32, 0.0005
+    oV = O.OracleVAE(feats, beta=beta)
+    O.reinit_(oV, 23)
+    oV.train()
+    vae = bv.betaVAE(feats, 2048, [6000, 4000, 2048], [4000, 6000], beta=beta)
+    vae.load_state_dict(oV.state_dict())
+    vae = vae.to(cuda_dev).train()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, feats, generator=g)
+    keep = (torch.rand(B, feats, generator=g) >= 0.5).float()
+    eps = torch.randn(B, 2048, generator=g)
+    oo = torch.optim.Adam(oV.parameters(), lr=5e-5)
+    om = torch.optim.Adam(vae.parameters(), lr=5e-5)
+    ref = O.vae_train_step_explicit(oV, oo, x, beta, keep, eps)
+    out3 = bv.train_step(vae, om, x.to(cuda_dev), beta, keep_mask=keep.to(cuda_dev), eps=eps.to(cuda_dev)).cpu()
+    for got, key in zip(out3.tolist(), ("total_loss", "reconstruction_loss", "kl_loss")):
+        assert abs(got - ref[key]) <= 2e-2 * abs(ref[key]) + 1e-4, key
+    for (n, po), (_, pm) in zip(oV.named_parameters(), vae.named_parameters()):
+        a, b = pm.grad.double().flatten().cpu(), po.grad.double().flatten()
+        if n.endswith(".0.bias") and not n.startswith("decoder.2"):
+            # bias of a Linear that feeds BatchNorm: its exact gradient is 0 (BN removes the mean); both sides only
+            # hold rounding noise, so compare magnitudes instead of directions
+            assert b.norm().item() <= 1e-4 and a.norm().item() <= 1e-3, n
+            continue
+        if b.norm() < 1e-12:
+            continue
+        cos = (a @ b / (a.norm() * b.norm())).item()
+        assert cos >= 0.98, f"{n}: cosine {cos:.4f}"
+        assert _rel(pm.data, po.data) <= 1e-2, n
+    for (n, bo), (_, bm) in zip(oV.named_buffers(), vae.named_buffers()):
+        if n.endswith("num_batches_tracked"):
+            assert int(bo) == int(bm)
+        else:
+            assert _rel(bm.float(), bo.float()) <= 2e-2, n
+    # a second step with internally drawn randomness runs and stays finite; eval-mode encode uses the new weights
+    out = bv.train_step(vae, om, x.to(cuda_dev), beta)
+    assert torch.isfinite(out).all()
+    vae.eval(); oV.eval()
+    zm = vae.encode(x.to(cuda_dev))[0]
+    assert torch.isfinite(zm).all()
