@@ -287,6 +287,37 @@ def run_ours(args, rank, world, local_rank):
                  "frac_of_bf16_sustained": FLOP_PER_TILE * S / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
                  "note": "one synthetic RNA profile per row, train-mode BN over the chunk, latent prep included"}
 
+    # ------------------------------------------------------------------ betaVAE training (config 5 shape)
+    vae_train = None
+    if args.vae_steps > 0:
+        from rnagan_b200 import betaVAE as bv
+        torch.manual_seed(7)
+        vmod = bv.betaVAE(GENES, LATENT, [6000, 4000, 2048], [4000, 6000], beta=0.0005)
+        for m in vmod.modules():                       # init_weights_xavier (src/utils.py:12-15)
+            if isinstance(m, torch.nn.Linear):
+                torch.nn.init.xavier_uniform_(m.weight)
+                m.bias.data.fill_(0.01)
+        vmod = vmod.to(device).train()
+        vopt = torch.optim.Adam(vmod.parameters(), lr=5e-5, weight_decay=0)
+        VB = 128
+        xs = torch.randn(VB, GENES, generator=torch.Generator().manual_seed(11 + rank)).to(device)
+        for _ in range(3):
+            bv.train_step(vmod, vopt, xs, 0.0005)
+        barrier()
+        e0.record()
+        for _ in range(args.vae_steps):
+            out3 = bv.train_step(vmod, vopt, xs, 0.0005)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / args.vae_steps
+        nparam = sum(p.numel() for p in vmod.parameters())
+        # algorithmic HBM bytes per step: Adam 28 B/param + bf16 weight read x2 (fwd, dgrad) + fp32 grad write + repack 6 B
+        algo = nparam * (28 + 4 + 4 + 6)
+        vae_train = {"steps_per_s": world * 1000.0 / ms, "ms_per_step": ms, "batch": VB, "params": nparam,
+                     "hbm_gbs_algorithmic": algo / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": algo / (ms * 1e-3) / 1e9 / peaks["hbm"],
+                     "losses": [float(v) for v in out3.cpu()], "device_resident": True}
+        del vmod, vopt
+
     # ------------------------------------------------------------------ CPU baseline (oracle port) on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -304,7 +335,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2_policy": "working set per step (>1 GB of activations) exceeds the 126 MB L2",
                        "precision": "bf16 operands / fp32 accumulate, fp32 master weights, stats, losses"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "synthesis": synth, "losses_finite": finite,
+            "cpu_baseline": cpu, "synthesis": synth, "vae_train": vae_train, "losses_finite": finite,
             "last_losses": [float(x) for x in losses_host[-1]],
         }
         print(json.dumps(line), flush=True)
@@ -406,6 +437,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (config 2: 64)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--synth-chunk", type=int, default=1024, help="0 disables the synthesis measurement")
+    ap.add_argument("--vae-steps", type=int, default=20, help="betaVAE (config 5) training steps to time; 0 disables")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

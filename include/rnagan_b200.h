@@ -194,6 +194,29 @@ int rg_vae_latent_grad(const void* dz, const float* mulv, const float* eps, int 
 int rg_vae_loss_finalize(const float* p_sse, int n1, const float* p_kld, int n2, int B, int F, float beta, float* out3,
                          rg_stream_t st);
 
+/* ---- resize-conv generator DCGANUpGenerator (src/dcgan.py:8-99) -------------------------------------------- */
+/* nn.Upsample(x2, bilinear, align_corners=False) + nn.ReflectionPad2d(1) (src/dcgan.py:48-49,78-79) and its adjoint:
+ * bf16 NHWC [B,H,W,C] <-> [B,2H+2,2W+2,C] */
+int rg_upsample2x_reflectpad(const void* h, void* u, int B, int H, int W, int C, rg_stream_t st);
+int rg_upsample2x_reflectpad_bwd(const void* du, void* dh, int B, int H, int W, int C, rg_stream_t st);
+/* nn.Conv2d(Cin, Cout, 3, 1, 0) on the padded tensor u [B,Ho+2,Wo+2,Cin] (src/dcgan.py:50-51,80-81):
+ * w3 bf16 [Cout_pad][9*Cin] from rg_pack_conv3; forward (+bias), image-channel forward (fp32 NCHW), input gradient on
+ * the padded grid (weights read MN-major from w3), weight gradient in the torch layout. */
+int rg_pack_conv3(const float* W, void* w3, int Cout, int Cin, int rows, rg_stream_t st);
+int rg_conv3x3(const void* u, const void* w3, void* out, const float* bias, int B, int Ho, int Wo, int Cin, int Cout,
+               rg_stream_t st);
+int rg_conv3x3_img(const void* u, const void* w3, float* img, const float* bias, int B, int Ho, int Wo, int Cin,
+                   int Cimg, rg_stream_t st);
+int rg_conv3x3_dgrad(const void* da, const void* w3, void* du, int B, int Ho, int Wo, int Cin, int Cout, rg_stream_t st);
+size_t rg_conv3x3_wgrad_ws_bytes(int B, int Ho, int Wo, int Cin, int Cout);
+int rg_conv3x3_wgrad(const void* da, const void* u, float* dW, void* ws, size_t ws_bytes, int B, int Ho, int Wo,
+                     int Cin, int Cout, float beta, rg_stream_t st);
+/* backward of the last Conv2d(64, 3, 3) of the resize-conv generator: dW fp32 [Cimg][64][3][3] and (optional) du bf16
+ * [B,S+2,S+2,64] from dout fp32 NCHW [B,Cimg,S,S]; ws of rg_upg_last_ws_bytes() bytes */
+size_t rg_upg_last_ws_bytes(int B, int S, int C, int Cimg);
+int rg_upg_last_bwd(const void* u, const float* dout, const float* W, int B, int S, int C, int Cimg, float* dW, void* du,
+                    void* ws, size_t ws_bytes, rg_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif

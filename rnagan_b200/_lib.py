@@ -67,6 +67,16 @@ SIGNATURES = {
     "rg_adam_step": (_i, [_vp, _i, _f, _f, _f, _f, _i, _i, _f, _f, _f, _vp]),
     "rg_clamp": (_i, [_vp, _sz, _f, _f, _vp]),
     "rg_tiles_to_unit_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "rg_upsample2x_reflectpad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "rg_upsample2x_reflectpad_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "rg_pack_conv3": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "rg_conv3x3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rg_conv3x3_img": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rg_conv3x3_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rg_conv3x3_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "rg_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _f, _vp]),
+    "rg_upg_last_ws_bytes": (_sz, [_i, _i, _i, _i]),
+    "rg_upg_last_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "rg_mul_cast_pad_bf16": (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _vp]),
     "rg_vae_reparam": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "rg_vae_recon": (_i, [_vp, _i, _vp, _i, _i, _f, _vp, _vp, _i, _vp]),

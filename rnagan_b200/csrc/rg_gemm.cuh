@@ -47,7 +47,8 @@ enum OutKind { OUT_BF16_NHWC = 0, OUT_F32_NHWC = 1, OUT_F32_NCHW = 2 };
 
 struct FwdArgs {
   int nB, H, W;        // M index space: pixels of the low-resolution grid (plain GEMM: H=W=1, nB=M)
-  int bw, bh, bb;      // TMA box (pixels) per M tile; bw*bh*bb == 128
+  int bw, bh, bb;      // TMA box (pixels) per M tile; bw*bh*bb <= 128 (== 128 for power-of-two grids)
+  int rows_valid;      // bw*bh*bb: accumulator rows beyond it are never stored
   int tw, th, tb;      // boxes per dimension
   int m_tiles;
   int num_taps, chunks;   // k-blocks per tile = num_taps * chunks (chunks = C_A / 64)
@@ -146,7 +147,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
 
   const int num_kb = p.num_taps * p.chunks;
   const int total_tiles = p.m_tiles * p.n_tiles * p.num_phases;
-  const uint32_t stage_tx = kAStageBytes + static_cast<uint32_t>(p.block_n) * 128u;
+  const uint32_t stage_tx = static_cast<uint32_t>(p.rows_valid) * 128u + static_cast<uint32_t>(p.block_n) * 128u;
 
   if (warp == 0) {
     // ===================================================== TMA producer (one elected lane)
@@ -237,7 +238,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
       const int it = (m_tile / p.tw) % p.th;
       const int bt = m_tile / (p.tw * p.th);
       const int b = bt * p.bb + bbi, i = it * p.bh + ii, j = jt * p.bw + jj;
-      const bool row_ok = (b < p.nB) && (i < p.H) && (j < p.W);
+      const bool row_ok = (row < p.rows_valid) && (b < p.nB) && (i < p.H) && (j < p.W);
       const int y = i * p.sy + p.oy[ph], x = j * p.sx + p.ox[ph];
       const int n0 = n_tile * p.block_n;
 

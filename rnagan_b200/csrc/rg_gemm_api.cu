@@ -92,9 +92,20 @@ struct Boxing {
 };
 static Boxing make_boxing(int B, int H, int W, int rows) {
   Boxing g;
-  g.bw = std::min(W, rows);
-  g.bh = std::min(H, rows / g.bw);
-  g.bb = rows / (g.bw * g.bh);
+  if (is_pow2(W) && is_pow2(H)) {
+    g.bw = std::min(W, rows);
+    g.bh = std::min(H, rows / g.bw);
+    g.bb = rows / (g.bw * g.bh);
+  } else {
+    // general grids (the reflect-padded 2H+2 x 2W+2 grid of the resize-conv generator): widest divisor of W that
+    // fits, as many rows / images as fit; the tile then has bw*bh*bb <= rows valid rows (the rest is masked)
+    g.bw = W;
+    if (W > rows)
+      for (int d = rows; d >= 1; --d)
+        if (W % d == 0) { g.bw = d; break; }
+    g.bh = std::max(1, std::min(H, rows / g.bw));
+    g.bb = std::max(1, std::min(B, rows / (g.bw * g.bh)));
+  }
   g.tw = ceil_div(W, g.bw);
   g.th = ceil_div(H, g.bh);
   g.tb = ceil_div(B, g.bb);
@@ -151,6 +162,7 @@ static void fill_common(FwdArgs& a, int B, int H, int W) {
   Boxing g = make_boxing(B, H, W, kBlockM);
   a.nB = B; a.H = H; a.W = W;
   a.bw = g.bw; a.bh = g.bh; a.bb = g.bb;
+  a.rows_valid = g.bw * g.bh * g.bb;
   a.tw = g.tw; a.th = g.th; a.tb = g.tb;
   a.m_tiles = g.tw * g.th * g.tb;
   a.slope = 1.0f;
@@ -271,6 +283,9 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
   if (w.taps == 16)
     wgrad_reduce_kernel<16><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out,
                                                                                     alpha, alpha_dev, beta);
+  else if (w.taps == 9)
+    wgrad_reduce_kernel<9><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out,
+                                                                                   alpha, alpha_dev, beta);
   else
     wgrad_reduce_kernel<1><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out,
                                                                                    alpha, alpha_dev, beta);
@@ -343,6 +358,16 @@ __global__ void pack_edge_kernel(const float* __restrict__ W, __nv_bfloat16* __r
   const int p = idx >> 6, k = idx & 63, tap = k >> 2, c = k & 3;
   const float v = c < Cimg ? W[(static_cast<size_t>(p) * Cimg + c) * 16 + tap] : 0.0f;
   out[idx] = __float2bfloat16(v);
+}
+__global__ void pack_conv3_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
+                                  int rows) {
+  const size_t n = static_cast<size_t>(rows) * 9 * Cin;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int co = static_cast<int>(i / (9 * Cin));
+  const int k = static_cast<int>(i - static_cast<size_t>(co) * 9 * Cin);
+  const int tap = k / Cin, c = k - tap * Cin;
+  out[i] = __float2bfloat16(co < Cout ? W[(static_cast<size_t>(co) * Cin + c) * 9 + tap] : 0.0f);
 }
 __global__ void cast_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols,
                                 int cols_pad) {
@@ -578,6 +603,127 @@ int rg_gemm_nn(const void* A, int lda, const void* Bw, int ldb, void* C, int M, 
                const float* col_scale, const float* col_shift, float slope, int out_f32, rg_stream_t st_) {
   return gemm_plain(A, lda, Bw, ldb, true, C, M, N, K, ldc, col_scale, col_shift, slope, out_f32,
                     static_cast<cudaStream_t>(st_), "rg_gemm_nn");
+}
+
+// ------------------------------------------------------------------------------------------------ 3x3 stride-1 conv
+// u: reflect-padded, 2x-upsampled activation bf16 [B][Ho+2][Wo+2][Cin]; w3: bf16 [Cout_pad][9*Cin], k = tap*Cin + c.
+static int conv3_common(const void* u, const void* w3, void* out, const float* bias, int B, int Ho, int Wo, int Cin,
+                        int Cout, int out_kind, cudaStream_t st) {
+  RG_CHECK_ARG(u && w3 && out, "rg_conv3x3: null pointer");
+  RG_CHECK_ARG(B > 0 && is_pow2(Ho) && is_pow2(Wo) && Cin % 64 == 0, "rg_conv3x3: need power-of-two Ho, Wo and Cin %% 64 == 0");
+  const int Cout_pad = std::max(16, (Cout + 15) / 16 * 16);
+  GemmMaps maps;
+  FwdArgs a;
+  fill_common(a, B, Ho, Wo);
+  const uint64_t Wp = Wo + 2, Hp = Ho + 2;
+  int rc = encode_map_4d(&maps.a[0], u, Cin, Wp, Hp, B, Cin, Wp * Cin, Hp * Wp * Cin, 64, a.bw, a.bh, a.bb);
+  if (rc) return rc;
+  maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+  a.num_taps = 9;
+  a.chunks = Cin / 64;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      Tap t = {0, static_cast<int8_t>(kh), static_cast<int8_t>(kw), static_cast<int8_t>(kh * 3 + kw)};
+      a.taps[0][kh * 3 + kw] = t;
+    }
+  a.n_total = Cout_pad;
+  a.block_n = pick_block_n(Cout_pad, a.m_tiles);
+  a.n_tiles = ceil_div(Cout_pad, a.block_n);
+  rc = encode_map_2d(&maps.b, w3, 9ull * Cin, Cout_pad, 9ull * Cin, 64, a.block_n);
+  if (rc) return rc;
+  a.out = out;
+  a.OH = Ho; a.OW = Wo; a.OC = Cout;
+  a.n_valid = Cout;
+  a.col_shift = bias;
+  return launch_fwd(maps, a, out_kind, st);
+}
+
+int rg_conv3x3(const void* u, const void* w3, void* out, const float* bias, int B, int Ho, int Wo, int Cin, int Cout,
+               rg_stream_t st) {
+  RG_CHECK_ARG(Cout % 8 == 0, "rg_conv3x3: need Cout %% 8 == 0 (use rg_conv3x3_img for image channels)");
+  return conv3_common(u, w3, out, bias, B, Ho, Wo, Cin, Cout, OUT_BF16_NHWC, static_cast<cudaStream_t>(st));
+}
+
+int rg_conv3x3_img(const void* u, const void* w3, float* img, const float* bias, int B, int Ho, int Wo, int Cin,
+                   int Cimg, rg_stream_t st) {
+  RG_CHECK_ARG(Cimg >= 1 && Cimg <= 8, "rg_conv3x3_img: 1..8 image channels supported");
+  return conv3_common(u, w3, img, bias, B, Ho, Wo, Cin, Cimg, OUT_F32_NCHW, static_cast<cudaStream_t>(st));
+}
+
+// du[b,y,x,ci] = sum_{kh,kw,co} da[b,y-kh,x-kw,co] * W[co,ci,kh,kw] on the padded (Ho+2)x(Wo+2) grid; the weights
+// are read MN-major from the same w3 buffer.
+int rg_conv3x3_dgrad(const void* da, const void* w3, void* du, int B, int Ho, int Wo, int Cin, int Cout,
+                     rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(da && w3 && du, "rg_conv3x3_dgrad: null pointer");
+  RG_CHECK_ARG(B > 0 && Cout % 64 == 0 && Cin % 64 == 0, "rg_conv3x3_dgrad: need Cin, Cout %% 64 == 0");
+  GemmMaps maps;
+  FwdArgs a;
+  fill_common(a, B, Ho + 2, Wo + 2);
+  int rc = encode_map_4d(&maps.a[0], da, Cout, Wo, Ho, B, Cout, 1ull * Wo * Cout, 1ull * Ho * Wo * Cout, 64, a.bw, a.bh,
+                         a.bb);
+  if (rc) return rc;
+  maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+  a.num_taps = 9;
+  a.chunks = Cout / 64;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      Tap t = {0, static_cast<int8_t>(-kh), static_cast<int8_t>(-kw), static_cast<int8_t>(kh * 3 + kw)};
+      a.taps[0][kh * 3 + kw] = t;
+    }
+  a.n_total = Cin;
+  a.block_n = std::max(64, pick_block_n(Cin, a.m_tiles));
+  a.n_tiles = ceil_div(Cin, a.block_n);
+  a.b_mn = 1;
+  a.b_tap_cols = Cin;
+  rc = encode_map_2d(&maps.b, w3, 9ull * Cin, Cout, 9ull * Cin, 64, 64);
+  if (rc) return rc;
+  a.out = du;
+  a.OH = Ho + 2; a.OW = Wo + 2; a.OC = Cin;
+  a.n_valid = Cin;
+  return launch_fwd(maps, a, OUT_BF16_NHWC, st);
+}
+
+size_t rg_conv3x3_wgrad_ws_bytes(int B, int Ho, int Wo, int Cin, int Cout) {
+  if (B <= 0 || Ho <= 0 || Wo <= 0 || Cin < 64 || Cout <= 0) return 0;
+  WgradGeom w = wgrad_geom(B, Ho, Wo, Cout, Cin, 9);
+  return static_cast<size_t>(w.splits) * 9 * Cout * Cin * sizeof(float);
+}
+
+// dW[co,ci,kh,kw] = sum_{b,y,x} da[b,y,x,co] * u[b,y+kh,x+kw,ci]
+int rg_conv3x3_wgrad(const void* da, const void* u, float* dW, void* ws, size_t ws_bytes, int B, int Ho, int Wo,
+                     int Cin, int Cout, float beta, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(da && u && dW, "rg_conv3x3_wgrad: null pointer");
+  RG_CHECK_ARG(B > 0 && is_pow2(Ho) && is_pow2(Wo) && Cin % 64 == 0 && Cout % 8 == 0,
+               "rg_conv3x3_wgrad: need power-of-two Ho, Wo, Cin %% 64 == 0, Cout %% 8 == 0");
+  WgradGeom w = wgrad_geom(B, Ho, Wo, Cout, Cin, 9);
+  GemmMaps maps;
+  const uint64_t Wp = Wo + 2, Hp = Ho + 2;
+  int rc = encode_map_4d(&maps.a[0], u, Cin, Wp, Hp, B, Cin, Wp * Cin, Hp * Wp * Cin, 64, w.g.bw, w.g.bh, w.g.bb);
+  if (rc) return rc;
+  maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+  rc = encode_map_4d(&maps.b, da, Cout, Wo, Ho, B, Cout, 1ull * Wo * Cout, 1ull * Ho * Wo * Cout, 64, w.g.bw, w.g.bh,
+                     w.g.bb);
+  if (rc) return rc;
+  Tap taps[16];
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      Tap t = {0, static_cast<int8_t>(kh), static_cast<int8_t>(kw), static_cast<int8_t>(kh * 3 + kw)};
+      taps[kh * 3 + kw] = t;
+    }
+  return launch_wgrad(maps, w, taps, B, Ho, Wo, Cout, Cin, dW, ws, ws_bytes, 1.0f, nullptr, beta, st);
+}
+
+// W[Cout][Cin][3][3] fp32 -> w3[Cout_pad][9*Cin] bf16 (rows >= Cout zero)
+int rg_pack_conv3(const float* W, void* w3, int Cout, int Cin, int rows, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(W && w3 && rows >= Cout, "rg_pack_conv3: bad arguments");
+  const size_t n = static_cast<size_t>(rows) * 9 * Cin;
+  pack_conv3_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(w3), Cout,
+                                                                            Cin, rows);
+  RG_LAUNCH_CHECK("rg_pack_conv3");
+  return 0;
 }
 
 size_t rg_conv_wgrad_ws_bytes(int B, int H, int W, int Cp, int Cs) {

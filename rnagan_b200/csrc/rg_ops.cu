@@ -863,6 +863,190 @@ __global__ void __launch_bounds__(256) vae_loss_finalize_kernel(const float* __r
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ resize-conv generator
+// nn.Upsample(scale_factor=2, mode='bilinear') [align_corners=False] followed by nn.ReflectionPad2d(1)
+// (src/dcgan.py:48-49,78-79; index rules of SURVEY.md Appendix B.11), bf16 NHWC [B,H,W,C] -> [B,2H+2,2W+2,C].
+__device__ __forceinline__ void up_taps(int d, int n, int& i0, int& i1, float& w1) {
+  // source coordinate of up-sampled index d: max(0, (d + 0.5)/2 - 0.5); i1 clamped to n-1
+  const float src = fmaxf(0.0f, (d + 0.5f) * 0.5f - 0.5f);
+  i0 = static_cast<int>(src);
+  w1 = src - i0;
+  i1 = min(i0 + 1, n - 1);
+}
+__device__ __forceinline__ int reflect_idx(int p, int n) {   // padded index p in [-1, n] -> [0, n)
+  return p < 0 ? -p : (p >= n ? 2 * n - 2 - p : p);
+}
+struct UpPadF {
+  const __nv_bfloat16* h;
+  __nv_bfloat16* u;
+  int H, W, C;
+  __device__ void operator()(size_t row, int c0) const {
+    const int Wp = 2 * W + 2, Hp = 2 * H + 2;
+    const int px = static_cast<int>(row % Wp);
+    const int py = static_cast<int>((row / Wp) % Hp);
+    const size_t b = row / (static_cast<size_t>(Wp) * Hp);
+    const int yy = reflect_idx(py - 1, 2 * H), xx = reflect_idx(px - 1, 2 * W);
+    int y0, y1, x0, x1;
+    float wy, wx;
+    up_taps(yy, H, y0, y1, wy);
+    up_taps(xx, W, x0, x1, wx);
+    const __nv_bfloat16* base = h + b * H * W * C + c0;
+    const Vec8 a = ld8(base + (static_cast<size_t>(y0) * W + x0) * C), bq = ld8(base + (static_cast<size_t>(y0) * W + x1) * C);
+    const Vec8 c = ld8(base + (static_cast<size_t>(y1) * W + x0) * C), d = ld8(base + (static_cast<size_t>(y1) * W + x1) * C);
+    Vec8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float top = a.v[e] + wx * (bq.v[e] - a.v[e]);
+      const float bot = c.v[e] + wx * (d.v[e] - c.v[e]);
+      o.v[e] = top + wy * (bot - top);
+    }
+    st8(u + row * C + c0, o);
+  }
+};
+// adjoint: dh[b,i,j,:] = sum over the padded up-sampled pixels that read (i,j), weights as in the forward
+struct UpPadBwdF {
+  const __nv_bfloat16* du;
+  __nv_bfloat16* dh;
+  int H, W, C;
+  // gradient of the un-padded up-sampled pixel (yy,xx): its own padded position plus the reflected border copies
+  __device__ __forceinline__ void gather(size_t b, int yy, int xx, int c0, float wgt, Vec8& acc) const {
+    const int Wp = 2 * W + 2, Hp = 2 * H + 2, H2 = 2 * H, W2 = 2 * W;
+    int ys[2], xs[2], ny = 1, nx = 1;
+    ys[0] = yy + 1; xs[0] = xx + 1;
+    if (yy == 1) ys[ny++] = 0; else if (yy == H2 - 2) ys[ny++] = Hp - 1;
+    if (xx == 1) xs[nx++] = 0; else if (xx == W2 - 2) xs[nx++] = Wp - 1;
+    for (int a = 0; a < ny; ++a)
+      for (int q = 0; q < nx; ++q) {
+        const Vec8 v = ld8(du + ((b * Hp + ys[a]) * Wp + xs[q]) * C + c0);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc.v[e] += wgt * v.v[e];
+      }
+  }
+  __device__ void operator()(size_t row, int c0) const {
+    const int j = static_cast<int>(row % W);
+    const int i = static_cast<int>((row / W) % H);
+    const size_t b = row / (static_cast<size_t>(W) * H);
+    Vec8 acc;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc.v[e] = 0.0f;
+    // up-sampled rows yy in [2i-1, 2i+2] can read input row i; recompute their taps to get the exact weights
+    for (int yy = max(0, 2 * i - 1); yy <= min(2 * H - 1, 2 * i + 2); ++yy) {
+      int y0, y1; float wy;
+      up_taps(yy, H, y0, y1, wy);
+      const float cy = (y0 == i ? 1.0f - wy : 0.0f) + (y1 == i ? wy : 0.0f);
+      if (cy == 0.0f) continue;
+      for (int xx = max(0, 2 * j - 1); xx <= min(2 * W - 1, 2 * j + 2); ++xx) {
+        int x0, x1; float wx;
+        up_taps(xx, W, x0, x1, wx);
+        const float cx = (x0 == j ? 1.0f - wx : 0.0f) + (x1 == j ? wx : 0.0f);
+        if (cx == 0.0f) continue;
+        gather(b, yy, xx, c0, cy * cx, acc);
+      }
+    }
+    st8(dh + row * C + c0, acc);
+  }
+};
+
+// last layer of the resize-conv generator (Conv2d(C,3,3) on the padded tensor): backward on CUDA cores.
+// dW[co][ci][kh][kw] partials: one block per pixel chunk, thread = (ci) x (co,tap split); deterministic 2-stage.
+__global__ void __launch_bounds__(256) upg_last_wgrad_stage1(const __nv_bfloat16* __restrict__ u,
+                                                             const float* __restrict__ dout, int B, int S, int C,
+                                                             int Cimg, int pix_per_block, float* __restrict__ partial) {
+  // partial[block][co*9+tap][ci]; requires C == 64 (4 groups of 64 threads split the 9 taps)
+  extern __shared__ float sd[];   // dout values of the current pixel batch: [Cimg][batch]
+  const int ci = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int Sp = S + 2;
+  const size_t npix = static_cast<size_t>(B) * S * S;
+  const size_t p0 = static_cast<size_t>(blockIdx.x) * pix_per_block;
+  const size_t p1 = min(npix, p0 + pix_per_block);
+  float acc[3][3];    // [co][tap slot]: this group handles taps grp, grp+4, grp+8
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int t = 0; t < 3; ++t) acc[a][t] = 0.0f;
+  for (size_t pb = p0; pb < p1; pb += 64) {
+    const int nb = static_cast<int>((p1 - pb) < 64 ? (p1 - pb) : 64);
+    __syncthreads();
+    for (int e = threadIdx.x; e < Cimg * nb; e += blockDim.x) {
+      const int co = e / nb, q = e - co * nb;
+      const size_t pix = pb + q;
+      const size_t b = pix / (static_cast<size_t>(S) * S);
+      const size_t yx = pix - b * S * S;
+      sd[co * 64 + q] = dout[(b * Cimg + co) * S * S + yx];
+    }
+    __syncthreads();
+    for (int q = 0; q < nb; ++q) {
+      const size_t pix = pb + q;
+      const int x = static_cast<int>(pix % S), y = static_cast<int>((pix / S) % S);
+      const size_t b = pix / (static_cast<size_t>(S) * S);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int tap = grp + 4 * t;
+        if (tap < 9) {
+          const int kh = tap / 3, kw = tap - kh * 3;
+          const float uv = __bfloat162float(u[((b * Sp + y + kh) * Sp + x + kw) * C + ci]);
+          for (int co = 0; co < Cimg; ++co) acc[co][t] = fmaf(sd[co * 64 + q], uv, acc[co][t]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int tap = grp + 4 * t;
+    if (tap < 9)
+      for (int co = 0; co < Cimg; ++co)
+        partial[(static_cast<size_t>(blockIdx.x) * (Cimg * 9) + co * 9 + tap) * C + ci] = acc[co][t];
+  }
+}
+__global__ void upg_last_wgrad_stage2(const float* __restrict__ partial, int nblocks, int C, int Cimg,
+                                      float* __restrict__ dW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;    // over (co, tap, ci)
+  if (i >= Cimg * 9 * C) return;
+  float s = 0.0f;
+  for (int b = 0; b < nblocks; ++b) s += partial[static_cast<size_t>(b) * Cimg * 9 * C + i];
+  const int ci = i % C, ct = i / C, tap = ct % 9, co = ct / 9;
+  dW[(static_cast<size_t>(co) * C + ci) * 9 + tap] = s;
+}
+// du[b,y',x',ci] = sum_{co,kh,kw} dout[b,co,y'-kh,x'-kw] * W[co][ci][kh][kw]  on the padded grid
+__global__ void __launch_bounds__(256) upg_last_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ W,
+                                                             int B, int S, int C, int Cimg,
+                                                             __nv_bfloat16* __restrict__ du) {
+  extern __shared__ float sw[];   // W as [co][tap][ci]
+  for (int e = threadIdx.x; e < Cimg * 9 * C; e += blockDim.x) {
+    const int ci = e % C, ct = e / C, tap = ct % 9, co = ct / 9;
+    sw[e] = W[(static_cast<size_t>(co) * C + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const int Sp = S + 2, cgs = C / 8;
+  const size_t nvec = static_cast<size_t>(B) * Sp * Sp * cgs;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cgs);
+    const size_t pix = i / cgs;
+    const int px = static_cast<int>(pix % Sp), py = static_cast<int>((pix / Sp) % Sp);
+    const size_t b = pix / (static_cast<size_t>(Sp) * Sp);
+    Vec8 acc;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc.v[e] = 0.0f;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int y = py - kh;
+      if (y < 0 || y >= S) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int x = px - kw;
+        if (x < 0 || x >= S) continue;
+        for (int co = 0; co < Cimg; ++co) {
+          const float g = __ldg(dout + ((b * Cimg + co) * S + y) * S + x);
+          const float* wr = sw + (co * 9 + kh * 3 + kw) * C + cg * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc.v[e] = fmaf(g, wr[e], acc.v[e]);
+        }
+      }
+    }
+    st8(du + pix * C + cg * 8, acc);
+  }
+}
+
 }  // namespace rg
 
 using namespace rg;
@@ -1184,6 +1368,52 @@ int rg_vae_loss_finalize(const float* p_sse, int n1, const float* p_kld, int n2,
   vae_loss_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(st)>>>(
       p_sse, n1, p_kld, n2, 1.0f / (static_cast<float>(B) * static_cast<float>(F)), 1.0f / B, beta, out3);
   RG_LAUNCH_CHECK("rg_vae_loss_finalize");
+  return 0;
+}
+
+
+int rg_upsample2x_reflectpad(const void* h, void* u, int B, int H, int W, int C, rg_stream_t st) {
+  RG_CHECK_ARG(h && u && H >= 2 && W >= 2, "rg_upsample2x_reflectpad: bad arguments");
+  UpPadF f{static_cast<const bf16*>(h), static_cast<bf16*>(u), H, W, C};
+  return run_ew(f, B * (2 * H + 2) * (2 * W + 2), C, static_cast<cudaStream_t>(st), "rg_upsample2x_reflectpad");
+}
+
+int rg_upsample2x_reflectpad_bwd(const void* du, void* dh, int B, int H, int W, int C, rg_stream_t st) {
+  RG_CHECK_ARG(du && dh && H >= 2 && W >= 2, "rg_upsample2x_reflectpad_bwd: bad arguments");
+  UpPadBwdF f{static_cast<const bf16*>(du), static_cast<bf16*>(dh), H, W, C};
+  return run_ew(f, B * H * W, C, static_cast<cudaStream_t>(st), "rg_upsample2x_reflectpad_bwd");
+}
+
+size_t rg_upg_last_ws_bytes(int B, int S, int C, int Cimg) {
+  const size_t npix = static_cast<size_t>(B) * S * S;
+  const int blocks = static_cast<int>(std::min<size_t>((npix + 1023) / 1024, static_cast<size_t>(num_sms()) * 4));
+  return static_cast<size_t>(blocks) * Cimg * 9 * C * sizeof(float);
+}
+
+int rg_upg_last_bwd(const void* u, const float* dout, const float* W, int B, int S, int C, int Cimg, float* dW, void* du,
+                    void* ws, size_t ws_bytes, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(u && dout && W && dW && C == 64 && Cimg >= 1 && Cimg <= 3, "rg_upg_last_bwd: needs C == 64, Cimg <= 3");
+  const size_t npix = static_cast<size_t>(B) * S * S;
+  const int blocks = static_cast<int>(std::min<size_t>((npix + 1023) / 1024, static_cast<size_t>(num_sms()) * 4));
+  const int ppb = static_cast<int>((npix + blocks - 1) / blocks);
+  const size_t need = static_cast<size_t>(blocks) * Cimg * 9 * C * sizeof(float);
+  if (!ws || ws_bytes < need) {
+    set_error("rg_upg_last_bwd: workspace too small (need %zu, have %zu)", need, ws_bytes);
+    return RG_EWORKSPACE;
+  }
+  upg_last_wgrad_stage1<<<blocks, 256, 3 * 64 * sizeof(float), st>>>(static_cast<const bf16*>(u), dout, B, S, C, Cimg,
+                                                                     ppb, static_cast<float*>(ws));
+  RG_LAUNCH_CHECK("rg_upg_last_bwd(wgrad1)");
+  upg_last_wgrad_stage2<<<ceil_div(Cimg * 9 * C, 256), 256, 0, st>>>(static_cast<const float*>(ws), blocks, C, Cimg, dW);
+  RG_LAUNCH_CHECK("rg_upg_last_bwd(wgrad2)");
+  if (du) {
+    const size_t nvec = static_cast<size_t>(B) * (S + 2) * (S + 2) * (C / 8);
+    const int grid = static_cast<int>(std::min<size_t>((nvec + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+    upg_last_dgrad_kernel<<<grid, 256, Cimg * 9 * C * sizeof(float), st>>>(dout, W, B, S, C, Cimg,
+                                                                           static_cast<bf16*>(du));
+    RG_LAUNCH_CHECK("rg_upg_last_bwd(dgrad)");
+  }
   return 0;
 }
 

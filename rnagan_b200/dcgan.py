@@ -5,7 +5,7 @@ Same constructor keywords, attributes (``encoding_dims``, ``label_type``, ``samp
 
   * torchgan==0.1.0 ``DCGANGenerator`` / ``DCGANDiscriminator`` -- the classes the reference actually instantiates
     (src/histopathology_gan.py:176-192, src/gan_utils.py:255-271); structure per SURVEY.md Appendix A/D, and
-  * the reference's own ``DCGANUpGenerator`` (src/dcgan.py:8-99).
+  * the reference's own ``DCGANUpGenerator`` (src/dcgan.py:8-99), the resize-conv variant.
 
 The ``nn`` layers inside ``self.model`` are PARAMETER CONTAINERS (fp32 masters, checkpoint layout); ``forward`` never
 calls them -- it runs rnagan_b200.engine on the CUDA kernels and raises when the module is not on a B200.
@@ -177,12 +177,13 @@ class DCGANDiscriminator(_EngineMixin, Discriminator):
         return out.clone()
 
 
-class DCGANUpGenerator(Generator):
-    """Resize-convolution generator of src/dcgan.py:8-99 (bilinear x2 -> ReflectionPad2d(1) -> Conv2d 3x3; no Tanh).
+class DCGANUpGenerator(_EngineMixin, Generator):
+    """Resize-convolution generator of src/dcgan.py:8-99 (bilinear x2 -> ReflectionPad2d(1) -> Conv2d 3x3; the
+    ``last_nonlinearity`` is built but NOT applied, src/dcgan.py:32,82).  Same constructor and state_dict layout as the
+    reference class; ``forward`` runs rnagan_b200.engine.UpGeneratorEngine.  The reference imports this class
+    (src/histopathology_gan.py:24) but its drivers instantiate the transposed-conv DCGANGenerator."""
 
-    Parameter layout / state_dict keys match the reference.  It is imported but never instantiated by the reference's
-    drivers (src/histopathology_gan.py:24,176); its kernel schedule is not built yet, so ``forward`` fails loudly
-    instead of silently running a non-native path."""
+    _engine_cls = _engine.UpGeneratorEngine
 
     def __init__(self, encoding_dims=100, out_size=32, out_channels=3, step_channels=64, batchnorm=True,
                  nonlinearity=None, last_nonlinearity=None, label_type="none"):
@@ -209,6 +210,9 @@ class DCGANUpGenerator(Generator):
         self.model = nn.Sequential(*layers)
         self._weight_initializer()
 
+    @torch.no_grad()
     def forward(self, x, feature_matching=False):
-        raise NotImplementedError("DCGANUpGenerator: the resize-conv kernel schedule (SURVEY.md K5) is not built in "
-                                  "this round; use DCGANGenerator (what the reference drivers instantiate)")
+        eng = self._engine()
+        x = x.view(-1, x.size(1)).to(device=eng.device, dtype=torch.float32).contiguous()
+        lat = _ops.cast_pad_bf16(x, x.size(1))
+        return eng.forward(lat, tag="module", training=self.training).clone()

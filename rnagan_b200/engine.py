@@ -217,6 +217,111 @@ class GeneratorEngine:
         self.sync.layer_done(self.conv0.weight, self.bn0.mod.weight, self.bn0.mod.bias)
 
 
+# ====================================================================================================== resize-conv G
+class UpGeneratorEngine:
+    """Kernel schedule for DCGANUpGenerator (src/dcgan.py:8-99): G.0 projection + BN + LeakyReLU, then per block
+    bilinear x2 + reflect-pad (rg_upsample2x_reflectpad) -> 3x3 conv as a 9-tap implicit GEMM (rg_conv3x3, bias in the
+    epilogue) -> BN + LeakyReLU; last block ends in a bias-only Conv2d(64, 3, 3) with NO Tanh (src/dcgan.py:76-84)."""
+
+    def __init__(self, module):
+        blocks = list(module.model)
+        self.module = module
+        dev = next(module.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("UpGeneratorEngine needs the module on a CUDA device (there is no CPU path)")
+        self.device = dev
+        self.bufs = _Bufs(dev)
+        first = blocks[0]
+        if len(first) != 3 or not isinstance(first[1], nn.BatchNorm2d):
+            raise NotImplementedError("resize-conv generator without BatchNorm is not implemented on the sm_100a path")
+        self.conv0, self.bn0 = first[0], _BN(first[1], dev)
+        _check_act(first[2], SLOPE, "generator")
+        self.E, self.C0 = self.conv0.weight.shape[0], self.conv0.weight.shape[1]
+        self.convs, self.bns = [], []
+        for blk in blocks[1:-1]:
+            if len(blk) != 5 or not isinstance(blk[2], nn.Conv2d) or not isinstance(blk[3], nn.BatchNorm2d):
+                raise NotImplementedError("unexpected resize-conv block layout")
+            _check_act(blk[4], SLOPE, "generator")
+            self.convs.append(blk[2])
+            self.bns.append(_BN(blk[3], dev))
+        self.conv_last = blocks[-1][2]
+        self.Cimg, self.Cn = self.conv_last.weight.shape[0], self.conv_last.weight.shape[1]
+        if self.Cn != 64 or self.Cimg > 3:
+            raise NotImplementedError("resize-conv generator: last layer must be Conv2d(64, <=3, 3) (step_channels=64)")
+        self.n = len(self.convs)
+        self.size = 4 * (2 ** (self.n + 1))
+        self.w_proj = torch.empty(16 * self.C0, self.E, dtype=BF16, device=dev)
+        self.w3 = [torch.empty(max(16, c.weight.shape[0]), 9 * c.weight.shape[1], dtype=BF16, device=dev)
+                   for c in self.convs]
+        self.w3_last = torch.zeros(16, 9 * self.Cn, dtype=BF16, device=dev)
+        self.tmpC = torch.zeros(max(c.weight.shape[0] for c in self.convs), dtype=F32, device=dev)
+        self.sync = GradSync(module)
+        self.pack()
+
+    def pack(self):
+        ops.pack_proj(self.conv0.weight.detach(), self.w_proj)
+        for c, w in zip(self.convs, self.w3):
+            ops.pack_conv3(c.weight.detach(), w)
+        ops.pack_conv3(self.conv_last.weight.detach(), self.w3_last)
+
+    def forward(self, lat, tag="g", training=True, out=None):
+        B = lat.shape[0]
+        g = self.bufs.get
+        a = g(f"{tag}.a0", (B, 4, 4, self.C0))
+        h = g(f"{tag}.h0", (B, 4, 4, self.C0))
+        ops.gemm_nt(lat, self.w_proj, out=a.view(B, 16 * self.C0))
+        self.bn0.forward(a, h, B * 16, training, tag=tag)
+        H = 4
+        for l, (c, bn) in enumerate(zip(self.convs, self.bns), start=1):
+            Cout, Cin = c.weight.shape[0], c.weight.shape[1]
+            u = g(f"{tag}.u{l}", (B, 2 * H + 2, 2 * H + 2, Cin))
+            ops.upsample2x_reflectpad(h, u)
+            H *= 2
+            a = g(f"{tag}.a{l}", (B, H, H, Cout))
+            ops.conv3x3(u, self.w3[l - 1], a, bias=c.bias.detach())
+            h = g(f"{tag}.h{l}", (B, H, H, Cout))
+            bn.forward(a, h, B * H * H, training, tag=tag)
+        u = g(f"{tag}.ulast", (B, 2 * H + 2, 2 * H + 2, self.Cn))
+        ops.upsample2x_reflectpad(h, u)
+        if out is None:
+            out = g(f"{tag}.img", (B, self.Cimg, 2 * H, 2 * H), F32)
+        ops.conv3x3(u, self.w3_last, out, bias=self.conv_last.bias.detach())
+        return out
+
+    def backward(self, lat, d_img, img, tag="g"):
+        B = lat.shape[0]
+        g = self.bufs.get
+        n, S = self.n, self.size
+        H = S // 2
+        u = g(f"{tag}.ulast", (B, S + 2, S + 2, self.Cn))
+        du = g("bwd.dulast", (B, S + 2, S + 2, self.Cn))
+        ops.upg_last_bwd(u, d_img, self.conv_last.weight.detach(), _grad_of(self.conv_last.weight), du)
+        ops.img_channel_sum(d_img, _grad_of(self.conv_last.bias), mode=0, acc=0.0)
+        self.sync.layer_done(self.conv_last.weight, self.conv_last.bias)
+        dh = g(f"bwd.dh{n}", (B, H, H, self.Cn))
+        ops.upsample2x_reflectpad_bwd(du, dh)
+        for l in range(n, 0, -1):
+            c, bn = self.convs[l - 1], self.bns[l - 1]
+            Cout, Cin = c.weight.shape[0], c.weight.shape[1]
+            a = g(f"{tag}.a{l}", (B, H, H, Cout))
+            da = g(f"bwd.da{l}", (B, H, H, Cout))
+            bn.backward(dh, a, da, B * H * H, param_grads=True, tag=tag)
+            u = g(f"{tag}.u{l}", (B, H + 2, H + 2, Cin))
+            ops.conv3x3_wgrad(da, u, _grad_of(c.weight))
+            ops.col_sum(da, B * H * H, Cout, self.tmpC, _grad_of(c.bias), 0.0)
+            self.sync.layer_done(c.weight, c.bias, bn.mod.weight, bn.mod.bias)
+            du = g(f"bwd.du{l}", (B, H + 2, H + 2, Cin))
+            ops.conv3x3_dgrad(da, self.w3[l - 1], du)
+            H //= 2
+            dh = g(f"bwd.dh{l - 1}", (B, H, H, Cin))
+            ops.upsample2x_reflectpad_bwd(du, dh)
+        a0 = g(f"{tag}.a0", (B, 4, 4, self.C0))
+        da0 = g("bwd.da0", (B, 4, 4, self.C0))
+        self.bn0.backward(dh, a0, da0, B * 16, param_grads=True, tag=tag)
+        ops.proj_wgrad(lat, da0, _grad_of(self.conv0.weight))
+        self.sync.layer_done(self.conv0.weight, self.bn0.mod.weight, self.bn0.mod.bias)
+
+
 # ====================================================================================================== critic
 class CriticEngine:
     """Kernel schedule for torchgan-style DCGANDiscriminator (batchnorm=True, LeakyReLU(0.2) everywhere)."""

@@ -428,3 +428,66 @@ def vae_latent_grad(dz, mulv, eps, kscale, dcat):
 def vae_loss_finalize(p_sse, n1, p_kld, n2, B, F, beta, out3):
     _lib.check(_lib.lib().rg_vae_loss_finalize(_p(p_sse), n1, _p(p_kld), n2, B, F, float(beta), _p(out3), _st()),
                "rg_vae_loss_finalize")
+
+
+# ------------------------------------------------------------------------------------------------ resize-conv generator
+def upsample2x_reflectpad(h, out):
+    B, H, W, C = h.shape
+    _lib.check(_lib.lib().rg_upsample2x_reflectpad(_p(h), _p(out), B, H, W, C, _st()), "rg_upsample2x_reflectpad")
+    return out
+
+
+def upsample2x_reflectpad_bwd(du, out):
+    B, H, W, C = out.shape
+    _lib.check(_lib.lib().rg_upsample2x_reflectpad_bwd(_p(du), _p(out), B, H, W, C, _st()),
+               "rg_upsample2x_reflectpad_bwd")
+    return out
+
+
+def pack_conv3(W, out):
+    Cout, Cin = W.shape[0], W.shape[1]
+    _lib.check(_lib.lib().rg_pack_conv3(_p(W), _p(out), Cout, Cin, out.shape[0], _st()), "rg_pack_conv3")
+    return out
+
+
+def conv3x3(u, w3, out, bias=None):
+    """u bf16 [B, Ho+2, Wo+2, Cin] -> out bf16 NHWC [B, Ho, Wo, Cout] or fp32 NCHW [B, Cimg, Ho, Wo]."""
+    B, Hp, Wp, Cin = u.shape
+    Ho, Wo = Hp - 2, Wp - 2
+    if out.dtype == torch.float32:
+        Cimg = out.shape[1]
+        _prof("conv3x3", 2.0 * B * Ho * Wo * Cimg * 9 * Cin, lambda: _lib.check(
+            _lib.lib().rg_conv3x3_img(_p(u), _p(w3), _p(out), _p(bias), B, Ho, Wo, Cin, Cimg, _st()), "rg_conv3x3_img"))
+    else:
+        Cout = out.shape[3]
+        _prof("conv3x3", 2.0 * B * Ho * Wo * Cout * 9 * Cin, lambda: _lib.check(
+            _lib.lib().rg_conv3x3(_p(u), _p(w3), _p(out), _p(bias), B, Ho, Wo, Cin, Cout, _st()), "rg_conv3x3"))
+    return out
+
+
+def conv3x3_dgrad(da, w3, du):
+    B, Ho, Wo, Cout = da.shape
+    Cin = du.shape[3]
+    _prof("conv3x3_dgrad", 2.0 * B * Ho * Wo * Cout * 9 * Cin, lambda: _lib.check(
+        _lib.lib().rg_conv3x3_dgrad(_p(da), _p(w3), _p(du), B, Ho, Wo, Cin, Cout, _st()), "rg_conv3x3_dgrad"))
+    return du
+
+
+def conv3x3_wgrad(da, u, dW, beta=0.0):
+    B, Ho, Wo, Cout = da.shape
+    Cin = u.shape[3]
+    L = _lib.lib()
+    ws = _workspace(L.rg_conv3x3_wgrad_ws_bytes(B, Ho, Wo, Cin, Cout), da.device)
+    _prof("conv3x3_wgrad", 2.0 * B * Ho * Wo * Cout * 9 * Cin, lambda: _lib.check(
+        L.rg_conv3x3_wgrad(_p(da), _p(u), _p(dW), _p(ws), ws.numel() * 4, B, Ho, Wo, Cin, Cout, float(beta), _st()),
+        "rg_conv3x3_wgrad"))
+    return dW
+
+
+def upg_last_bwd(u, dout, W, dW, du):
+    B, Cimg, S, _ = dout.shape
+    C = u.shape[3]
+    L = _lib.lib()
+    ws = _workspace(L.rg_upg_last_ws_bytes(B, S, C, Cimg), u.device)
+    _lib.check(L.rg_upg_last_bwd(_p(u), _p(dout), _p(W), B, S, C, Cimg, _p(dW), _p(du), _p(ws), ws.numel() * 4, _st()),
+               "rg_upg_last_bwd")

@@ -195,3 +195,73 @@ def test_vae_train_step_matches_oracle(cuda_dev):
     vae.eval(); oV.eval()
     zm = vae.encode(x.to(cuda_dev))[0]
     assert torch.isfinite(zm).all()
+
+
+def test_up_generator_forward_matches_reference_golden(cuda_dev):
+    """DCGANUpGenerator (src/dcgan.py:8-99) forward against the output of the reference's own class (golden) and the
+    oracle, train-mode BN, same weights and latent."""
+    from rnagan_b200 import dcgan
+    from tests import _util as U
+    gold = U.load_golden("modules.npz")
+    oU = O.OracleUpGenerator(2048, 32, 3, 64, nonlinearity=torch.nn.LeakyReLU(0.2), last_nonlinearity=torch.nn.Tanh())
+    O.reinit_(oU, 21)
+    oU.train()
+    G = dcgan.DCGANUpGenerator(2048, 32, 3, 64, nonlinearity=torch.nn.LeakyReLU(0.2),
+                               last_nonlinearity=torch.nn.Tanh()).to(cuda_dev)
+    G.load_state_dict(oU.state_dict())
+    G.train()
+    z = torch.randn(6, 2048, generator=torch.Generator().manual_seed(22))
+    with torch.no_grad():
+        ref = oU(z)
+    out = G(z.to(cuda_dev))
+    assert out.shape == ref.shape
+    assert _rel(out, ref) <= 3e-2
+    got = U.sample_of(out, 4096)
+    assert U.rel_l2(got, gold["upgen/out_sample"]) <= 3e-2
+
+
+@pytest.mark.parametrize("size,B", [(32, 8), (64, 4)])
+def test_up_generator_g_step_matches_oracle(cuda_dev, size, B):
+    """G step (src/wgan_loss.py:82-129) with the resize-conv generator: loss and generator gradients vs the oracle."""
+    import copy
+    import os
+    import tempfile
+    from torch.optim import Adam
+    from rnagan_b200 import dcgan, wgan_loss
+    feats = 128
+    lrelu, tanh = torch.nn.LeakyReLU(0.2), torch.nn.Tanh()
+    oG = O.OracleUpGenerator(2048, size, 3, 64, nonlinearity=lrelu, last_nonlinearity=tanh).train()
+    oD = O.OracleCritic(size, 3, 64, nonlinearity=lrelu, last_nonlinearity=lrelu).train()
+    oV = O.OracleVAE(feats, beta=0.005).eval()
+    O.reinit_(oV, 13); O.reinit_(oG, 31); O.reinit_(oD, 12)
+    ckpt = os.path.join(tempfile.mkdtemp(), "vae.pt")
+    torch.save(oV.state_dict(), ckpt)
+    G = dcgan.DCGANUpGenerator(2048, size, 3, 64, nonlinearity=torch.nn.LeakyReLU(0.2),
+                               last_nonlinearity=torch.nn.Tanh()).to(cuda_dev).train()
+    D = dcgan.DCGANDiscriminator(size, 3, 64, nonlinearity=torch.nn.LeakyReLU(0.2),
+                                 last_nonlinearity=torch.nn.LeakyReLU(0.2)).to(cuda_dev).train()
+    G.load_state_dict(oG.state_dict()); D.load_state_dict(oD.state_dict())
+    loss = wgan_loss.WassersteinGeneratorLossVAE(ckpt, feats)
+    data = O.make_batch(B, feats, size, 14)
+    # torch's own bf16 deviation as the yardstick
+    aG, aD = copy.deepcopy(oG), copy.deepcopy(oD)
+    torch.manual_seed(99)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        O.g_step(aG, aD, Adam(aG.parameters(), lr=0.0), oV, data)
+    torch.manual_seed(99)
+    v_ref = O.g_step(oG, oD, Adam(oG.parameters(), lr=0.0), oV, data)
+    torch.manual_seed(99)
+    opt = Adam(G.parameters(), lr=0.0)
+    v = loss.train_ops(G, D, opt, cuda_dev, B, data)
+    assert abs(v - v_ref) <= 0.02 + 0.02 * abs(v_ref)
+    c_bf16, pairs = 1.0, []
+    for (n, po), (_, pm), (_, pa) in zip(oG.named_parameters(), G.named_parameters(), aG.named_parameters()):
+        a, b, c = pm.grad.double().flatten().cpu(), po.grad.double().flatten(), pa.grad.double().flatten()
+        cos = lambda u, w: (u @ w / (u.norm() * w.norm()).clamp_min(1e-30)).item()
+        if b.norm() < 1e-7 * max(1.0, b.numel() ** 0.5):      # conv biases feeding BatchNorm: exact gradient is 0
+            continue
+        c_bf16 = min(c_bf16, cos(c, b))
+        pairs.append((n, cos(a, b)))
+    bound = 1.0 - 2.0 * (1.0 - c_bf16) - 0.01
+    for n, cs in pairs:
+        assert cs >= bound, f"{n}: cosine {cs:.4f} < {bound:.4f} (torch-bf16 worst {c_bf16:.4f})"
