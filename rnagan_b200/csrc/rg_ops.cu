@@ -41,9 +41,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2_ops(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ Vec8 ldf8(const float* p) {
+  // per-channel parameter vectors are read-only for the kernel's lifetime: ld.global.nc lets the compiler hoist
+  // these loads out of the row loops when the channel group is loop-invariant
   Vec8 r;
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
   r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
   return r;
@@ -69,8 +71,16 @@ __global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int r
     for (int k = 0; k < K; ++k)
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[k][e] = 0.0f;
-    if (active)
-      for (int r = r0 + rl; r < r1; r += lanes) f(static_cast<size_t>(r), cg * 8, acc);
+    if (active) {
+      int r = r0 + rl;
+      for (; r + 3 * lanes < r1; r += 4 * lanes) {     // 4 independent rows in flight per thread
+        f(static_cast<size_t>(r), cg * 8, acc);
+        f(static_cast<size_t>(r + lanes), cg * 8, acc);
+        f(static_cast<size_t>(r + 2 * lanes), cg * 8, acc);
+        f(static_cast<size_t>(r + 3 * lanes), cg * 8, acc);
+      }
+      for (; r < r1; r += lanes) f(static_cast<size_t>(r), cg * 8, acc);
+    }
     if (lanes == 1) {
 #pragma unroll
       for (int k = 0; k < K; ++k)
@@ -121,8 +131,8 @@ static ReducePlan plan_reduce(int M, int C, int K) {
   ReducePlan p;
   const int cgs = C / 8;
   const int lanes = cgs >= 256 ? 1 : 256 / cgs;
-  int target = num_sms() * 2;
-  int rpb = std::max(lanes * 4, ceil_div(M, target));
+  int target = num_sms() * 6;
+  int rpb = std::max(lanes * 8, ceil_div(M, target));
   rpb = ceil_div(rpb, lanes) * lanes;
   p.rows_per_block = rpb;
   p.blocks = ceil_div(M, rpb);
@@ -137,8 +147,8 @@ static size_t reduce_ws_floats(int M, int C, int K) {
 template <class F>
 static int run_colreduce(F f, int M, int C, float* ws, size_t ws_bytes, float* out, cudaStream_t st, const char* name) {
   constexpr int K = F::K;
-  if (C % 8 != 0 || C < 8 || C > 8192 || M <= 0) {
-    set_error("%s: need C %% 8 == 0, 8 <= C <= 8192, M > 0 (M=%d C=%d)", name, M, C);
+  if (C % 8 != 0 || C < 8 || C > 65536 || M <= 0) {
+    set_error("%s: need C %% 8 == 0, 8 <= C <= 65536, M > 0 (M=%d C=%d)", name, M, C);
     return RG_EINVAL;
   }
   ReducePlan p = plan_reduce(M, C, K);
@@ -164,12 +174,24 @@ static int run_colreduce(F f, int M, int C, float* ws, size_t ws_bytes, float* o
 // ------------------------------------------------------------------------------------------------ elementwise driver
 // Functor: __device__ void operator()(size_t row, int c0) const  -- processes 8 channels of one row
 template <class F>
-__global__ void __launch_bounds__(256) ew_kernel(F f, size_t nvec, int cgs) {
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t row = i / cgs;
-    const int cg = static_cast<int>(i - row * cgs);
-    f(row, cg * 8);
+__global__ void __launch_bounds__(256) ew_kernel(F f, unsigned nvec, int cgs, int cg_shift) {
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg_shift >= 0) {
+    // cgs is a power of two and divides the stride: this thread's channel group never changes, so the per-channel
+    // parameter loads inside f are loop-invariant and there is no integer division
+    const int c0 = static_cast<int>(i0 & static_cast<unsigned>(cgs - 1)) * 8;
+    unsigned i = i0;
+    for (; i + stride < nvec && i + stride > i; i += 2 * stride) {    // two independent rows in flight
+      f(static_cast<size_t>(i >> cg_shift), c0);
+      f(static_cast<size_t>((i + stride) >> cg_shift), c0);
+    }
+    if (i < nvec) f(static_cast<size_t>(i >> cg_shift), c0);
+  } else {
+    for (unsigned i = i0; i < nvec; i += stride) {
+      const unsigned row = i / static_cast<unsigned>(cgs);
+      f(static_cast<size_t>(row), static_cast<int>(i - row * cgs) * 8);
+    }
   }
 }
 template <class F>
@@ -179,8 +201,20 @@ static int run_ew(F f, int M, int C, cudaStream_t st, const char* name) {
     return RG_EINVAL;
   }
   const size_t nvec = static_cast<size_t>(M) * (C / 8);
-  const int grid = static_cast<int>(std::min<size_t>((nvec + 255) / 256, static_cast<size_t>(num_sms()) * 8));
-  ew_kernel<F><<<grid, 256, 0, st>>>(f, nvec, C / 8);
+  if (nvec >= (1ull << 31)) {
+    set_error("%s: tensor too large for 32-bit vector indexing (%zu vectors)", name, nvec);
+    return RG_EINVAL;
+  }
+  const int cgs = C / 8;
+  int grid = static_cast<int>(std::min<size_t>((nvec + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  int shift = -1;
+  if (is_pow2(cgs)) {
+    const int mult = std::max(1, cgs / 256);             // stride = grid*256 must be a multiple of cgs
+    grid = std::max(mult, grid / mult * mult);
+    shift = 0;
+    while ((1 << shift) < cgs) ++shift;
+  }
+  ew_kernel<F><<<grid, 256, 0, st>>>(f, static_cast<unsigned>(nvec), cgs, shift);
   RG_LAUNCH_CHECK(name);
   return 0;
 }
@@ -431,13 +465,14 @@ __global__ void __launch_bounds__(256) im2col_img_kernel(const float* __restrict
                                                          float* __restrict__ mixed_out) {
   extern __shared__ float rows[];   // [Cimg][4][S + 2], one zero column on each side
   const int Ho = S / 2, Wp = S + 2;
-  const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
+  const int b = blockIdx.x >> (31 - __clz(Ho)), ho = blockIdx.x & (Ho - 1);
   const float eps = eps_dev ? __ldg(eps_dev) : 0.0f;
   const float mul = mul_dev ? __ldg(mul_dev) : 1.0f;
+  const int ls = 31 - __clz(S);                 // S is a power of two (checked by the host wrapper)
   for (int idx = threadIdx.x; idx < Cimg * 4 * S; idx += blockDim.x) {
-    const int xx = idx % S;
-    const int r = (idx / S) & 3;
-    const int c = idx / (4 * S);
+    const int xx = idx & (S - 1);
+    const int r = (idx >> ls) & 3;
+    const int c = idx >> (ls + 2);
     const int yy = 2 * ho - 1 + r;
     float t = 0.0f;
     if (yy >= 0 && yy < S) {
@@ -517,12 +552,12 @@ __global__ void __launch_bounds__(256) col2im_img_kernel(const float* __restrict
                                                          const float* __restrict__ bias, int act_tanh, int B, int Cimg,
                                                          int H, int W, float* __restrict__ img) {
   const int OH = 2 * H, OW = 2 * W;
-  const size_t n = static_cast<size_t>(B) * OH * OW;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(i % OW);
-    const int y = static_cast<int>((i / OW) % OH);
-    const int b = static_cast<int>(i / (static_cast<size_t>(OW) * OH));
+  const unsigned n = static_cast<unsigned>(B) * OH * OW;
+  const int lw = 31 - __clz(OW), lh = 31 - __clz(OH);    // power-of-two image sides (checked by the host wrapper)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int x = static_cast<int>(i & (OW - 1));
+    const int y = static_cast<int>((i >> lw) & (OH - 1));
+    const int b = static_cast<int>(i >> (lw + lh));
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     // y = 2*ii - 1 + kh  ->  kh has the parity of (y + 1); two candidates each for rows and columns
 #pragma unroll
@@ -536,13 +571,18 @@ __global__ void __launch_bounds__(256) col2im_img_kernel(const float* __restrict
         const int jj = (x + 1 - kw) >> 1;
         if (jj < 0 || jj >= W) continue;
         const float* src = col + ((static_cast<size_t>(b) * H + ii) * W + jj) * ldc + (kh * 4 + kw) * Cimg;
-        for (int c = 0; c < Cimg; ++c) acc[c] += __ldg(src + c);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < Cimg) acc[c] += __ldg(src + c);
       }
     }
-    for (int c = 0; c < Cimg; ++c) {
-      float v = acc[c] + (bias ? __ldg(bias + c) : 0.0f);
-      if (act_tanh) v = tanhf(v);
-      img[((static_cast<size_t>(b) * Cimg + c) * OH + y) * OW + x] = v;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < Cimg) {
+        float v = acc[c] + (bias ? __ldg(bias + c) : 0.0f);
+        if (act_tanh) v = tanhf(v);
+        img[((static_cast<size_t>(b) * Cimg + c) * OH + y) * OW + x] = v;
+      }
     }
   }
 }
@@ -986,7 +1026,9 @@ __global__ void __launch_bounds__(256) upg_last_wgrad_stage1(const __nv_bfloat16
         if (tap < 9) {
           const int kh = tap / 3, kw = tap - kh * 3;
           const float uv = __bfloat162float(u[((b * Sp + y + kh) * Sp + x + kw) * C + ci]);
-          for (int co = 0; co < Cimg; ++co) acc[co][t] = fmaf(sd[co * 64 + q], uv, acc[co][t]);
+#pragma unroll
+          for (int co = 0; co < 3; ++co)
+            if (co < Cimg) acc[co][t] = fmaf(sd[co * 64 + q], uv, acc[co][t]);
         }
       }
     }
@@ -994,9 +1036,11 @@ __global__ void __launch_bounds__(256) upg_last_wgrad_stage1(const __nv_bfloat16
 #pragma unroll
   for (int t = 0; t < 3; ++t) {
     const int tap = grp + 4 * t;
-    if (tap < 9)
-      for (int co = 0; co < Cimg; ++co)
-        partial[(static_cast<size_t>(blockIdx.x) * (Cimg * 9) + co * 9 + tap) * C + ci] = acc[co][t];
+    if (tap < 9) {
+#pragma unroll
+      for (int co = 0; co < 3; ++co)
+        if (co < Cimg) partial[(static_cast<size_t>(blockIdx.x) * (Cimg * 9) + co * 9 + tap) * C + ci] = acc[co][t];
+    }
   }
 }
 __global__ void upg_last_wgrad_stage2(const float* __restrict__ partial, int nblocks, int C, int Cimg,
@@ -1162,7 +1206,8 @@ int rg_latent_prep(const float* noise, const float* z, int B, int E, int z_rows,
 
 int rg_im2col_img(const float* x, const float* y, int mode, const float* eps_dev, const float* mul_dev, int B,
                   int Cimg, int S, void* col, float* mixed_out, rg_stream_t st) {
-  RG_CHECK_ARG(x && col && B > 0 && Cimg >= 1 && Cimg <= 4 && S >= 2 && S % 2 == 0, "rg_im2col_img: bad arguments");
+  RG_CHECK_ARG(x && col && B > 0 && Cimg >= 1 && Cimg <= 4 && S >= 4 && is_pow2(S),
+               "rg_im2col_img: need 1..4 channels and a power-of-two image side (S=%d)", S);
   RG_CHECK_ARG(mode == 0 || y, "rg_im2col_img: mode %d needs a second image", mode);
   const size_t smem = static_cast<size_t>(Cimg) * 4 * (S + 2) * sizeof(float);
   RG_CHECK_ARG(smem <= 48 * 1024, "rg_im2col_img: image side %d too large for the row-staging buffer", S);
@@ -1187,7 +1232,8 @@ int rg_img_channel_sum(const float* x, const float* y, int mode, int B, int Cimg
 
 int rg_col2im_img(const float* col, int ldc, const float* bias, int act_tanh, int B, int Cimg, int H, int W, float* img,
                   rg_stream_t st) {
-  RG_CHECK_ARG(col && img && Cimg >= 1 && Cimg <= 4 && ldc >= 16 * Cimg, "rg_col2im_img: bad arguments");
+  RG_CHECK_ARG(col && img && Cimg >= 1 && Cimg <= 4 && ldc >= 16 * Cimg && is_pow2(H) && is_pow2(W),
+               "rg_col2im_img: need power-of-two H, W and ldc >= 16*Cimg");
   const size_t n = static_cast<size_t>(B) * 4 * H * W;
   const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   col2im_img_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(col, ldc, bias, act_tanh, B, Cimg, H, W, img);

@@ -78,6 +78,26 @@ def main(filt=""):
         da0 = torch.randn(B, 4, 4, 2048, device=dev).to(BF)
         dW = torch.empty(2048, 2048, 4, 4, device=dev)
         report("proj_wgrad", timeit(lambda: ops.proj_wgrad(z, da0, dW)), 2.0 * B * 2048 * 32768, dW.numel() * 4)
+    if filt in "ew im2col":
+        img = torch.rand(B, 3, 256, 256, device=dev) * 2 - 1
+        img2 = torch.rand(B, 3, 256, 256, device=dev) * 2 - 1
+        col = torch.empty(M, 64, dtype=BF, device=dev)
+        eps = torch.tensor([0.3], device=dev)
+        report("im2col mode0", timeit(lambda: ops.im2col_img(img, col)), 0, img.numel() * 4 + M * 128)
+        report("im2col mode1 (interp)", timeit(lambda: ops.im2col_img(img, col, y=img2, mode=1, eps_dev=eps)), 0, img.numel() * 8 + M * 128)
+        colf = torch.randn(M, 48, device=dev)
+        out = torch.empty(B, 3, 256, 256, device=dev)
+        bias3 = torch.zeros(3, device=dev)
+        from rnagan_b200 import _lib
+        report("col2im (+bias+tanh)", timeit(lambda: _lib.check(_lib.lib().rg_col2im_img(colf.data_ptr(), 48, bias3.data_ptr(), 1, B, 3, 128, 128, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "x")), 0, M * 192 + out.numel() * 4)
+        a = torch.randn(M, 64, device=dev).to(BF)
+        h = torch.empty_like(a)
+        sums = torch.zeros(2, 64, device=dev)
+        sc, sh = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+        report("bn_stats [1M,64]", timeit(lambda: ops.bn_stats(a, M, 64, sums)), 0, M * 128)
+        report("bn_act [1M,64]", timeit(lambda: ops.bn_act(a, sc, sh, 0.2, h, M, 64)), 0, M * 256)
+        report("bn_bwd_reduce [1M,64]", timeit(lambda: ops.bn_bwd_reduce(h, a, sh, sc, sc, sh, 0.2, M, 64, sums)), 0, M * 256)
+        report("bn_bwd_apply [1M,64]", timeit(lambda: ops.bn_bwd_apply(h, a, None, sh, sc, sc, sh, 0.2, sums, M, 64, h)), 0, M * 384)
     if filt in "encoder":
         x = torch.randn(B, 19200, device=dev).to(BF)
         W1 = (torch.randn(6000, 19200, device=dev) * 0.01).to(BF)
