@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librnagan_b200.so")
+LIB_PATH = os.environ.get("RG_LIB_PATH") or os.path.join(_HERE, "librnagan_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["rg_gemm_api.cu", "rg_ops.cu"]
 

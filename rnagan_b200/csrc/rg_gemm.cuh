@@ -78,7 +78,24 @@ struct WgradArgs {
   int Cp, Cs, num_taps;
   Tap taps[16];
   float* ws;           // [splits][num_taps][Cp][Cs] fp32 partials
+  // splits == 1 with 16 taps: the epilogue writes the torch layout dW[p][s][kh][kw] directly (no partials, no reduce)
+  float* direct_out;
+  const float* alpha_dev;
+  float alpha, beta;
 };
+
+// slab sl of N-tile nt -> (kernel position, 64-channel chunk).  For 4x4 kernels a tile holds the four kw of one kh
+// and one chunk, so an epilogue thread owns 4 consecutive floats (16 B) of dW[p][s][kh][0..3].
+__device__ __forceinline__ void wgrad_slab(const WgradArgs& p, int nt, int sl, int& tap, int& chunk) {
+  if (p.num_taps == 16 && p.slabs_per_tile == 4) {
+    chunk = nt >> 2;
+    tap = (nt & 3) * 4 + sl;
+  } else {
+    const int qd = nt * p.slabs_per_tile + sl;
+    tap = qd / p.chunks_s;
+    chunk = qd - tap * p.chunks_s;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ shared setup
 struct PipeSmem {
@@ -395,9 +412,8 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
           tma_load_4d(&maps.b, &s.full[stage], sa + 8192, m_tile * 128 + 64, j0, i0, b0);
           // MMA-B operand: one slab per (tap, 64-channel chunk) of the high-resolution tensor
           for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
-            const int qd = n_tile * p.slabs_per_tile + sl;
-            const int tap = qd / p.chunks_s;
-            const int chunk = qd - tap * p.chunks_s;
+            int tap, chunk;
+            wgrad_slab(p, n_tile, sl, tap, chunk);
             const Tap t = p.taps[tap];
             tma_load_4d(&maps.a[t.map], &s.full[stage], sb + sl * 8192, chunk * 64, j0 + t.dw, i0 + t.dh, b0);
           }
@@ -455,23 +471,53 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
       mbar_wait(&s.tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
-        const int qd = n_tile * p.slabs_per_tile + sl;
-        const int tap = qd / p.chunks_s;
-        const int chunk = qd - tap * p.chunks_s;
-        float* o = p.ws + ((static_cast<size_t>(split) * p.num_taps + tap) * p.Cp + prow) * p.Cs + chunk * 64;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + sl * 64 + h * 32, v);
+      if (p.direct_out != nullptr) {
+        // direct write: dW[p][s][kh][kw] = beta*dW + alpha * acc; this tile = (kh, chunk), slabs = kw 0..3
+        const int chunk = n_tile >> 2, kh = n_tile & 3;
+        const float a = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {
+          uint32_t v0[16], v1[16], v2[16], v3[16];
+          tmem_ld_32x16(taddr + 0 * 64 + h * 16, v0);
+          tmem_ld_32x16(taddr + 1 * 64 + h * 16, v1);
+          tmem_ld_32x16(taddr + 2 * 64 + h * 16, v2);
+          tmem_ld_32x16(taddr + 3 * 64 + h * 16, v3);
           tmem_ld_wait();
           if (row_ok) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              if (chunk * 64 + h * 32 + g * 4 + 4 <= p.Cs) {
-                float4 f = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
-                                       __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
-                *reinterpret_cast<float4*>(o + h * 32 + g * 4) = f;
+            for (int e = 0; e < 16; ++e) {
+              const int sidx = chunk * 64 + h * 16 + e;
+              if (sidx < p.Cs) {
+                float* o = p.direct_out + (static_cast<size_t>(prow) * p.Cs + sidx) * 16 + kh * 4;
+                float4 f = make_float4(a * __uint_as_float(v0[e]), a * __uint_as_float(v1[e]),
+                                       a * __uint_as_float(v2[e]), a * __uint_as_float(v3[e]));
+                if (p.beta != 0.0f) {
+                  const float4 old = *reinterpret_cast<const float4*>(o);
+                  f.x += p.beta * old.x; f.y += p.beta * old.y; f.z += p.beta * old.z; f.w += p.beta * old.w;
+                }
+                *reinterpret_cast<float4*>(o) = f;
+              }
+            }
+          }
+        }
+      } else {
+        for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
+          int tap, chunk;
+          wgrad_slab(p, n_tile, sl, tap, chunk);
+          float* o = p.ws + ((static_cast<size_t>(split) * p.num_taps + tap) * p.Cp + prow) * p.Cs + chunk * 64;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + sl * 64 + h * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (chunk * 64 + h * 32 + g * 4 + 4 <= p.Cs) {
+                  float4 f = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
+                                         __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+                  *reinterpret_cast<float4*>(o + h * 32 + g * 4) = f;
+                }
               }
             }
           }

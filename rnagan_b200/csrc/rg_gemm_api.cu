@@ -1,5 +1,6 @@
 // rg_gemm_api.cu -- C-ABI entry points for the tcgen05 tile engine (rg_gemm.cuh) and the weight packers.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <atomic>
 #include "rg_gemm.cuh"
@@ -184,16 +185,20 @@ static int encode_parity_maps(GemmMaps& maps, const void* hi, int B, int H, int 
 }
 
 // ------------------------------------------------------------------------------------------------ reduce kernel
-template <int TAPS>
+template <int TAPS, bool PADDED>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dW,
                                                            int splits, int Cp, int Cs, int Cs_out, float alpha,
                                                            const float* __restrict__ alpha_dev, float beta) {
-  // ws: [splits][TAPS][Cp][Cs] partials; dW: [Cp][Cs_out][TAPS] (Cs_out < Cs only for the padded plain-GEMM case)
-  const size_t n_out = static_cast<size_t>(Cp) * Cs_out;
-  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // ws: [splits][TAPS][Cp][Cs] partials; dW: [Cp][Cs_out][TAPS] (PADDED: Cs_out < Cs, the ragged plain-GEMM case)
+  const unsigned n_out = static_cast<unsigned>(Cp) * Cs_out;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_out) return;
   const size_t n = static_cast<size_t>(Cp) * Cs;
-  const size_t src = (Cs_out == Cs) ? idx : (idx / Cs_out) * Cs + (idx % Cs_out);
+  unsigned src = idx;
+  if (PADDED) {
+    const unsigned r = idx / static_cast<unsigned>(Cs_out);
+    src = r * Cs + (idx - r * Cs_out);
+  }
   const float a = alpha * (alpha_dev ? __ldg(alpha_dev) : 1.0f);
   float acc[TAPS];
 #pragma unroll
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) acc[t] += ws[(static_cast<size_t>(sp) * TAPS + t) * n + src];
   }
-  float* o = dW + idx * TAPS;
+  float* o = dW + static_cast<size_t>(idx) * TAPS;
   if (TAPS % 4 == 0) {
 #pragma unroll
     for (int t = 0; t < TAPS; t += 4) {
@@ -260,8 +265,14 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
   if (Cs_out < 0) Cs_out = Cs;
   int rc = ensure_attrs();
   if (rc) return rc;
+  // measured on B200: inside the full training step the direct epilogue LOSES ~1.2 ms/step to the split-K + reduce
+  // path (16-byte read-modify-write pieces at a 64-byte stride when accumulating), so it is opt-in for experiments
+  static const bool allow_direct = [] { const char* e = getenv("RG_WGRAD_DIRECT"); return e && e[0] == '1'; }();
+  // direct 16-byte stores at a 64-byte stride pay off while dW stays L2-sized; the 268 MB projection gradient does not
+  const bool direct = allow_direct && (w.splits == 1 && w.taps == 16 && w.slabs_per_tile == 4 && Cs_out == Cs) &&
+                      static_cast<size_t>(Cp) * Cs * 64 <= (160u << 20);
   const size_t need = static_cast<size_t>(w.splits) * w.taps * Cp * Cs * sizeof(float);
-  if (ws_bytes < need || ws == nullptr) {
+  if (!direct && (ws_bytes < need || ws == nullptr)) {
     set_error("wgrad workspace too small: need %zu bytes, have %zu", need, ws_bytes);
     return RG_EWORKSPACE;
   }
@@ -275,20 +286,27 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
   a.Cp = Cp; a.Cs = Cs; a.num_taps = w.taps;
   for (int t = 0; t < w.taps; ++t) a.taps[t] = taps[t];
   a.ws = static_cast<float*>(ws);
+  if (direct) {
+    a.direct_out = dW;
+    a.alpha = alpha;
+    a.alpha_dev = alpha_dev;
+    a.beta = beta;
+  }
   const int units = w.m_tiles * w.n_tiles * w.splits;
   const int grid = std::min(units, num_sms());
   gemm_wgrad_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
   RG_LAUNCH_CHECK("gemm_wgrad_kernel");
+  if (direct) return 0;
   const size_t n = static_cast<size_t>(Cp) * Cs_out;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   if (w.taps == 16)
-    wgrad_reduce_kernel<16><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out,
-                                                                                    alpha, alpha_dev, beta);
+    wgrad_reduce_kernel<16, false><<<blocks, 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out, alpha, alpha_dev, beta);
   else if (w.taps == 9)
-    wgrad_reduce_kernel<9><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out,
-                                                                                   alpha, alpha_dev, beta);
+    wgrad_reduce_kernel<9, false><<<blocks, 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out, alpha, alpha_dev, beta);
+  else if (Cs_out != Cs)
+    wgrad_reduce_kernel<1, true><<<blocks, 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out, alpha, alpha_dev, beta);
   else
-    wgrad_reduce_kernel<1><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out,
-                                                                                   alpha, alpha_dev, beta);
+    wgrad_reduce_kernel<1, false><<<blocks, 256, 0, st>>>(a.ws, dW, w.splits, Cp, Cs, Cs_out, alpha, alpha_dev, beta);
   RG_LAUNCH_CHECK("wgrad_reduce_kernel");
   return 0;
 }

@@ -18,6 +18,7 @@ def timeit(fn, reps=8):
     ts = []
     for _ in range(reps):
         flush.zero_()
+        torch.cuda._sleep(400000)      # ~0.2 ms of GPU idle-spin: the host enqueues fn() behind it
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record()
         torch.cuda.synchronize()
