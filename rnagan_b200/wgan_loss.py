@@ -116,21 +116,47 @@ class _VAEConditioned:
 
     def _inputs(self, generator, real_inputs, device):
         """z = encode(rna) (once per batch) and this step's CPU uniform(-0.3, 0.3) noise draw, both on the device
-        (src/wgan_loss.py:96-101)."""
+        (src/wgan_loss.py:96-101).  The first step that sees a batch also starts the host->device copy of its images
+        on a side stream, so the critic / GP steps (which need them, :238, :364) do not wait for PCIe."""
         B = real_inputs["image"].size(0)
         rna = real_inputs["rna_data"]
         vae = self._encoder(device)
         z = _CACHE.get("z", rna, device, lambda: vae.encode_mean(rna.to(device, non_blocking=True)))
-        noise = torch.FloatTensor(B, generator.encoding_dims).uniform_(-0.3, 0.3)
-        noise_d = generator._engine().bufs.get("noise", (B, generator.encoding_dims), F32)
-        noise_d.copy_(noise, non_blocking=False)
+        self._prefetch_real(real_inputs, device)
+        eng = generator._engine()
+        E = generator.encoding_dims
+        stage = eng.bufs.__dict__.setdefault("_noise_pinned", {})
+        pinned = stage.get((B, E))
+        if pinned is None:
+            pinned = torch.empty(B, E, dtype=F32).pin_memory()
+            stage[(B, E)] = pinned
+        pinned.uniform_(-0.3, 0.3)                 # same CPU generator stream as torch.FloatTensor(B, E).uniform_()
+        noise_d = eng.bufs.get("noise", (B, E), F32)
+        noise_d.copy_(pinned, non_blocking=True)   # every train_ops ends with .item(): the copy is done before reuse
         return noise_d, z
 
     @staticmethod
-    def _real(real_inputs, device):
+    def _prefetch_real(real_inputs, device):
         img = real_inputs["image"]
-        return _CACHE.get("image", img, device,
-                          lambda: img.to(device=device, dtype=F32, non_blocking=True).contiguous())
+
+        def start():
+            if img.device.type == "cuda":
+                return (img.to(dtype=F32).contiguous(), None)
+            side = _CACHE.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=device))
+            with torch.cuda.stream(side):
+                dst = img.to(device=device, dtype=F32, non_blocking=True).contiguous()
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return (dst, ev)
+
+        return _CACHE.get("image", img, device, start)
+
+    @staticmethod
+    def _real(real_inputs, device):
+        dst, ev = _VAEConditioned._prefetch_real(real_inputs, device)
+        if ev is not None:
+            torch.cuda.current_stream(device).wait_event(ev)
+        return dst
 
 
 def _check_labels(labels, *nets):
