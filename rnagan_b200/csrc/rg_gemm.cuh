@@ -55,6 +55,9 @@ struct FwdArgs {
   int num_phases;         // 1, or 4 for the transposed (upsampling) form
   int n_total, block_n, n_tiles;
   int b_phase_rows;       // row offset between phases in the packed weight matrix
+  int a_2d;               // 1: maps.a[0] is a rank-2 [rows][K] view (plain GEMMs): cheaper for the TMA unit than 4-D
+  int mc;                 // 1: launched as 2-CTA clusters; the two CTAs take neighbouring M tiles of the same N tile
+                          //    and each fetches half of the B tile with TMA multicast (halves the L2->SM B traffic)
   int b_mn;               // 1: B operand is read MN-major from w_down[Cp][16*Cs] (K rows = p, N contiguous = s)
   int b_tap_cols;         // b_mn: column stride between kernel positions in w_down (= Cs)
   Tap taps[4][16];
@@ -82,6 +85,7 @@ struct WgradArgs {
   float* direct_out;
   const float* alpha_dev;
   float alpha, beta;
+  int msub;            // 128-row accumulators per unit: 1, or 2 (256-row M tile sharing every B slab)
 };
 
 // slab sl of N-tile nt -> (kernel position, 64-channel chunk).  For 4x4 kernels a tile holds the four kw of one kh
@@ -124,12 +128,12 @@ __device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
   return s;
 }
 
-__device__ __forceinline__ uint32_t pipeline_prologue(const PipeSmem& s, int warp) {
+__device__ __forceinline__ uint32_t pipeline_prologue(const PipeSmem& s, int warp, int cluster_size = 1) {
   if (warp == 1) {
     if (elect_one()) {
       for (int i = 0; i < kStages; ++i) {
         mbar_init(&s.full[i], 1);
-        mbar_init(&s.empty[i], 1);
+        mbar_init(&s.empty[i], cluster_size);   // a stage is free when EVERY CTA that multicasts into it released it
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s.tfull[i], 1);
@@ -143,6 +147,7 @@ __device__ __forceinline__ uint32_t pipeline_prologue(const PipeSmem& s, int war
   }
   tc_fence_before();
   __syncthreads();
+  if (cluster_size > 1) cluster_sync_all();     // peers' barriers exist before any remote arrive / multicast
   tc_fence_after();
   return *reinterpret_cast<volatile uint32_t*>(s.tmem_slot);
 }
@@ -160,10 +165,15 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
   }
-  const uint32_t tmem_base = pipeline_prologue(s, warp);
+  const int csize = p.mc ? 2 : 1;
+  const int crank = p.mc ? static_cast<int>(cluster_ctarank()) : 0;
+  const uint32_t tmem_base = pipeline_prologue(s, warp, csize);
 
   const int num_kb = p.num_taps * p.chunks;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.num_phases;
+  // tile loop: one "slot" = csize neighbouring M tiles (one per CTA of the cluster) of the same (N tile, phase)
+  const int mslots = (p.m_tiles + csize - 1) / csize;
+  const int total_tiles = mslots * p.n_tiles * p.num_phases;
+  const int tile0 = blockIdx.x / csize, tile_step = gridDim.x / csize;
   const uint32_t stage_tx = static_cast<uint32_t>(p.rows_valid) * 128u + static_cast<uint32_t>(p.block_n) * 128u;
 
   if (warp == 0) {
@@ -171,9 +181,9 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile % p.m_tiles;
-        const int rest = tile / p.m_tiles;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int m_tile = (tile % mslots) * csize + crank;    // may be >= m_tiles for the odd tail: loads zero-fill
+        const int rest = tile / mslots;
         const int n_tile = rest % p.n_tiles;
         const int ph = rest / p.n_tiles;
         const int jt = m_tile % p.tw;
@@ -189,12 +199,22 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
           uint8_t* sa = s.stages + stage * kStageBytes;
           uint8_t* sb = sa + kAStageBytes;
           mbar_expect_tx(&s.full[stage], stage_tx);
-          tma_load_4d(&maps.a[t.map], &s.full[stage], sa, chunk * kBlockK, j0 + t.dw, i0 + t.dh, b0);
+          if (p.a_2d) tma_load_2d(&maps.a[0], &s.full[stage], sa, chunk * kBlockK, b0);
+          else tma_load_4d(&maps.a[t.map], &s.full[stage], sa, chunk * kBlockK, j0 + t.dw, i0 + t.dh, b0);
           if (p.b_mn) {
             // B^T slabs [64 k-rows = p][64 n = s] straight out of w_down: no second packed copy of the weights
             const int col0 = t.wtap * p.b_tap_cols + n_tile * p.block_n;
-            for (int sl = 0; sl < (p.block_n >> 6); ++sl)
-              tma_load_2d(&maps.b, &s.full[stage], sb + sl * 8192, col0 + sl * 64, chunk * kBlockK);
+            const int ns = p.block_n >> 6;
+            if (p.mc) {       // this CTA fetches half of the slabs for both CTAs
+              for (int sl = crank * (ns >> 1); sl < (crank + 1) * (ns >> 1); ++sl)
+                tma_load_2d_mc(&maps.b, &s.full[stage], sb + sl * 8192, col0 + sl * 64, chunk * kBlockK, 3);
+            } else {
+              for (int sl = 0; sl < ns; ++sl)
+                tma_load_2d(&maps.b, &s.full[stage], sb + sl * 8192, col0 + sl * 64, chunk * kBlockK);
+            }
+          } else if (p.mc) {  // half of the B rows (box = block_n/2 rows) for both CTAs
+            const int half = p.block_n >> 1;
+            tma_load_2d_mc(&maps.b, &s.full[stage], sb + crank * half * 128, kb * kBlockK, brow + crank * half, 3);
           } else {
             tma_load_2d(&maps.b, &s.full[stage], sb, kb * kBlockK, brow);
           }
@@ -211,7 +231,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1u;
         mbar_wait(&s.tempty[acc], acc_phase ^ 1u);
@@ -229,7 +249,8 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
             // +32 bytes per UMMA_K inside the 128-byte swizzle row => +2 in the (>>4) address field
             umma_bf16(tmem_d, da + 2u * k, db + b_kstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&s.empty[stage]);
+          if (p.mc) umma_commit_mc(&s.empty[stage], 3);   // both producers write into this stage of my smem
+          else umma_commit(&s.empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&s.tfull[acc]);
@@ -244,18 +265,18 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
     const int bbi = row / (p.bw * p.bh);
     int iter = 0;
     int staged_n_tile = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1u;
-      const int m_tile = tile % p.m_tiles;
-      const int rest = tile / p.m_tiles;
+      const int m_tile = (tile % mslots) * csize + crank;
+      const int rest = tile / mslots;
       const int n_tile = rest % p.n_tiles;
       const int ph = rest / p.n_tiles;
       const int jt = m_tile % p.tw;
       const int it = (m_tile / p.tw) % p.th;
       const int bt = m_tile / (p.tw * p.th);
       const int b = bt * p.bb + bbi, i = it * p.bh + ii, j = jt * p.bw + jj;
-      const bool row_ok = (row < p.rows_valid) && (b < p.nB) && (i < p.H) && (j < p.W);
+      const bool row_ok = (m_tile < p.m_tiles) && (row < p.rows_valid) && (b < p.nB) && (i < p.H) && (j < p.W);
       const int y = i * p.sy + p.oy[ph], x = j * p.sx + p.ox[ph];
       const int n0 = n_tile * p.block_n;
 
@@ -367,10 +388,15 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
 
   tc_fence_before();
   __syncthreads();
+  if (p.mc) cluster_sync_all();   // the peer may still multicast into this CTA's smem / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
+// Measured on B200 (profiles/r1_wgrad_whatif.txt): with both operands streamed once from HBM this kernel is bound by
+// bytes in flight per SM (smem ring / DRAM latency), not by the tensor pipe -- removing every MMA changes its time by
+// < 10 %.  msub = 2 therefore processes a 256-row M tile per unit (two 128-row accumulators sharing every B slab):
+// 1.5x the FLOPs per byte of smem ring at the price of the accumulator double-buffering (all 512 TMEM columns).
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ WgradArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -384,8 +410,12 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
   }
   const uint32_t tmem_base = pipeline_prologue(s, warp);
 
+  const int msub = p.msub;                                    // 128-row accumulators per unit (1 or 2)
+  const int a_bytes = msub * 16384;                           // msub * 2 slabs of [64 px][64 ch]
+  const int stage_bytes = a_bytes + 32768;
+  const int nstages = msub == 2 ? 3 : 4;                      // 3 x 64 KiB or 4 x 48 KiB
   const int total_units = p.m_tiles * p.n_tiles * p.splits;
-  const uint32_t stage_tx = static_cast<uint32_t>(2 + p.slabs_per_tile) * 8192u;
+  const uint32_t stage_tx = static_cast<uint32_t>(2 * msub + p.slabs_per_tile) * 8192u;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -404,12 +434,12 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
           const int bt = pb / (p.tw * p.th);
           const int j0 = jt * p.bw, i0 = it * p.bh, b0 = bt * p.bb;
           mbar_wait(&s.empty[stage], phase ^ 1u);
-          uint8_t* sa = s.stages + stage * kStageBytes;
-          uint8_t* sb = sa + kAStageBytes;
+          uint8_t* sa = s.stages + stage * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
           mbar_expect_tx(&s.full[stage], stage_tx);
-          // MMA-A operand: two 64-channel slabs of the low-resolution tensor (channels beyond Cp zero-fill)
-          tma_load_4d(&maps.b, &s.full[stage], sa, m_tile * 128, j0, i0, b0);
-          tma_load_4d(&maps.b, &s.full[stage], sa + 8192, m_tile * 128 + 64, j0, i0, b0);
+          // MMA-A operand: 64-channel slabs of the low-resolution tensor (channels beyond Cp zero-fill)
+          for (int sl = 0; sl < 2 * msub; ++sl)
+            tma_load_4d(&maps.b, &s.full[stage], sa + sl * 8192, m_tile * 128 * msub + sl * 64, j0, i0, b0);
           // MMA-B operand: one slab per (tap, 64-channel chunk) of the high-resolution tensor
           for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
             int tap, chunk;
@@ -417,7 +447,7 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
             const Tap t = p.taps[tap];
             tma_load_4d(&maps.a[t.map], &s.full[stage], sb + sl * 8192, chunk * 64, j0 + t.dw, i0 + t.dh, b0);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -431,26 +461,28 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
         const int split = u / (p.m_tiles * p.n_tiles);
         const int pb0 = split * p.pb_per_split;
         const int pb1 = min(p.num_pb, pb0 + p.pb_per_split);
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1u;
+        // msub == 2 owns all 512 TMEM columns: a single accumulator stage
+        const int acc = msub == 2 ? 0 : (iter & 1);
+        const uint32_t acc_phase = msub == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
         mbar_wait(&s.tempty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
         for (int pb = pb0; pb < pb1; ++pb) {
           mbar_wait(&s.full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(s.stages + stage * kStageBytes);
-          const uint32_t sb = sa + kAStageBytes;
+          const uint32_t sa = smem_u32(s.stages + stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
           // MN-major SWIZZLE_128B: LBO = stride between 64-element MN slabs (8 KiB),
           // SBO = stride between 8-row K groups (1 KiB); one UMMA_K = 16 pixel rows = 2 KiB.
-          const uint64_t da = make_smem_desc_sw128(sa, 8192, 1024);
           const uint64_t db = make_smem_desc_sw128(sb, 8192, 1024);
+          for (int ms = 0; ms < msub; ++ms) {
+            const uint64_t da = make_smem_desc_sw128(sa + ms * 16384, 8192, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16(tmem_d, da + 128u * k, db + 128u * k, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_d + ms * kAccStride, da + 128u * k, db + 128u * k, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&s.empty[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&s.tfull[acc]);
       }
@@ -460,63 +492,65 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
     const int row = q * 32 + lane;
     int iter = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++iter) {
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (iter >> 1) & 1u;
+      const int acc = msub == 2 ? 0 : (iter & 1);
+      const uint32_t acc_phase = msub == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
       const int m_tile = u % p.m_tiles;
       const int rest = u / p.m_tiles;
       const int n_tile = rest % p.n_tiles;
       const int split = rest / p.n_tiles;
-      const int prow = m_tile * 128 + row;
-      const bool row_ok = prow < p.Cp;
       mbar_wait(&s.tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      if (p.direct_out != nullptr) {
-        // direct write: dW[p][s][kh][kw] = beta*dW + alpha * acc; this tile = (kh, chunk), slabs = kw 0..3
-        const int chunk = n_tile >> 2, kh = n_tile & 3;
-        const float a = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
+      for (int ms = 0; ms < msub; ++ms) {
+        const int prow = (m_tile * msub + ms) * 128 + row;
+        const bool row_ok = prow < p.Cp;
+        const uint32_t taddr = tmem_base + (acc + ms) * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+        if (p.direct_out != nullptr) {
+          // direct write: dW[p][s][kh][kw] = beta*dW + alpha * acc; this tile = (kh, chunk), slabs = kw 0..3
+          const int chunk = n_tile >> 2, kh = n_tile & 3;
+          const float a = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
 #pragma unroll 1
-        for (int h = 0; h < 4; ++h) {
-          uint32_t v0[16], v1[16], v2[16], v3[16];
-          tmem_ld_32x16(taddr + 0 * 64 + h * 16, v0);
-          tmem_ld_32x16(taddr + 1 * 64 + h * 16, v1);
-          tmem_ld_32x16(taddr + 2 * 64 + h * 16, v2);
-          tmem_ld_32x16(taddr + 3 * 64 + h * 16, v3);
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int sidx = chunk * 64 + h * 16 + e;
-              if (sidx < p.Cs) {
-                float* o = p.direct_out + (static_cast<size_t>(prow) * p.Cs + sidx) * 16 + kh * 4;
-                float4 f = make_float4(a * __uint_as_float(v0[e]), a * __uint_as_float(v1[e]),
-                                       a * __uint_as_float(v2[e]), a * __uint_as_float(v3[e]));
-                if (p.beta != 0.0f) {
-                  const float4 old = *reinterpret_cast<const float4*>(o);
-                  f.x += p.beta * old.x; f.y += p.beta * old.y; f.z += p.beta * old.z; f.w += p.beta * old.w;
-                }
-                *reinterpret_cast<float4*>(o) = f;
-              }
-            }
-          }
-        }
-      } else {
-        for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
-          int tap, chunk;
-          wgrad_slab(p, n_tile, sl, tap, chunk);
-          float* o = p.ws + ((static_cast<size_t>(split) * p.num_taps + tap) * p.Cp + prow) * p.Cs + chunk * 64;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + sl * 64 + h * 32, v);
+          for (int h = 0; h < 4; ++h) {
+            uint32_t v0[16], v1[16], v2[16], v3[16];
+            tmem_ld_32x16(taddr + 0 * 64 + h * 16, v0);
+            tmem_ld_32x16(taddr + 1 * 64 + h * 16, v1);
+            tmem_ld_32x16(taddr + 2 * 64 + h * 16, v2);
+            tmem_ld_32x16(taddr + 3 * 64 + h * 16, v3);
             tmem_ld_wait();
             if (row_ok) {
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                if (chunk * 64 + h * 32 + g * 4 + 4 <= p.Cs) {
-                  float4 f = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
-                                         __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
-                  *reinterpret_cast<float4*>(o + h * 32 + g * 4) = f;
+              for (int e = 0; e < 16; ++e) {
+                const int sidx = chunk * 64 + h * 16 + e;
+                if (sidx < p.Cs) {
+                  float* o = p.direct_out + (static_cast<size_t>(prow) * p.Cs + sidx) * 16 + kh * 4;
+                  float4 f = make_float4(a * __uint_as_float(v0[e]), a * __uint_as_float(v1[e]),
+                                         a * __uint_as_float(v2[e]), a * __uint_as_float(v3[e]));
+                  if (p.beta != 0.0f) {
+                    const float4 old = *reinterpret_cast<const float4*>(o);
+                    f.x += p.beta * old.x; f.y += p.beta * old.y; f.z += p.beta * old.z; f.w += p.beta * old.w;
+                  }
+                  *reinterpret_cast<float4*>(o) = f;
+                }
+              }
+            }
+          }
+        } else {
+          for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
+            int tap, chunk;
+            wgrad_slab(p, n_tile, sl, tap, chunk);
+            float* o = p.ws + ((static_cast<size_t>(split) * p.num_taps + tap) * p.Cp + prow) * p.Cs + chunk * 64;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t v[32];
+              tmem_ld_32x32(taddr + sl * 64 + h * 32, v);
+              tmem_ld_wait();
+              if (row_ok) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  if (chunk * 64 + h * 32 + g * 4 + 4 <= p.Cs) {
+                    float4 f = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
+                                           __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+                    *reinterpret_cast<float4*>(o + h * 32 + g * 4) = f;
+                  }
                 }
               }
             }

@@ -143,19 +143,47 @@ static int ensure_attrs() {
   return 0;
 }
 
+// 2-CTA clusters with TMA multicast of the B tile (see FwdArgs::mc): worth it when the tile is wide enough to split
+static bool want_mc(const FwdArgs& a) {
+  // measured on B200 (same box A/B, full training step): neutral (17.38 vs 17.36 ms/step) -- these kernels are not
+  // L2-bandwidth bound -- so the simpler non-cluster launch stays the default; RG_MC=1 enables the multicast path
+  static const bool allow = [] { const char* e = getenv("RG_MC"); return e && e[0] == '1'; }();
+  return allow && a.block_n >= 128 && a.m_tiles >= 2;
+}
+
+template <int OUT>
+static int launch_fwd_t(const GemmMaps& maps, const FwdArgs& a, cudaStream_t st) {
+  const int csize = a.mc ? 2 : 1;
+  const int slots = ceil_div(a.m_tiles, csize) * a.n_tiles * a.num_phases;
+  const int grid = std::min(slots, num_sms() / csize) * csize;
+  if (!a.mc) {
+    gemm_fwd_kernel<OUT><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = kGemmSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RG_CUDA(cudaLaunchKernelEx(&cfg, gemm_fwd_kernel<OUT>, maps, a));
+  }
+  RG_LAUNCH_CHECK("gemm_fwd_kernel");
+  return 0;
+}
+
 static int launch_fwd(const GemmMaps& maps, const FwdArgs& a, int out_kind, cudaStream_t st) {
   int rc = ensure_attrs();
   if (rc) return rc;
-  const int total = a.m_tiles * a.n_tiles * a.num_phases;
-  const int grid = std::min(total, num_sms());
-  if (out_kind == OUT_BF16_NHWC)
-    gemm_fwd_kernel<OUT_BF16_NHWC><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
-  else if (out_kind == OUT_F32_NHWC)
-    gemm_fwd_kernel<OUT_F32_NHWC><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
-  else
-    gemm_fwd_kernel<OUT_F32_NCHW><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
-  RG_LAUNCH_CHECK("gemm_fwd_kernel");
-  return 0;
+  if (out_kind == OUT_BF16_NHWC) return launch_fwd_t<OUT_BF16_NHWC>(maps, a, st);
+  if (out_kind == OUT_F32_NHWC) return launch_fwd_t<OUT_F32_NHWC>(maps, a, st);
+  return launch_fwd_t<OUT_F32_NCHW>(maps, a, st);
 }
 
 static void fill_common(FwdArgs& a, int B, int H, int W) {
@@ -243,13 +271,16 @@ static void choose_splits(int units, int num_pb, int& splits, int& pb_per_split)
 
 struct WgradGeom {
   Boxing g;
-  int num_pb, m_tiles, chunks_s, slabs_per_tile, n_tiles, splits, pb_per_split, taps;
+  int num_pb, m_tiles, chunks_s, slabs_per_tile, n_tiles, splits, pb_per_split, taps, msub;
 };
 static WgradGeom wgrad_geom(int B, int H, int W, int Cp, int Cs, int taps) {
   WgradGeom w;
   w.g = make_boxing(B, H, W, 64);
   w.num_pb = w.g.tw * w.g.th * w.g.tb;
-  w.m_tiles = ceil_div(Cp, 128);
+  static const bool allow256 = [] { const char* e = getenv("RG_WGRAD_M256"); return !(e && e[0] == '0'); }();
+  // 256-row units give up the accumulator double-buffering: only worth it when a unit runs many pixel blocks
+  w.msub = (allow256 && Cp % 256 == 0 && w.num_pb >= 64) ? 2 : 1;
+  w.m_tiles = ceil_div(Cp, 128 * w.msub);
   w.chunks_s = ceil_div(Cs, 64);
   w.taps = taps;
   const int num_slabs = taps * w.chunks_s;
@@ -286,6 +317,7 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
   a.Cp = Cp; a.Cs = Cs; a.num_taps = w.taps;
   for (int t = 0; t < w.taps; ++t) a.taps[t] = taps[t];
   a.ws = static_cast<float*>(ws);
+  a.msub = w.msub;
   if (direct) {
     a.direct_out = dW;
     a.alpha = alpha;
@@ -489,7 +521,8 @@ int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int
   a.block_n = pick_block_n(Cp, a.m_tiles);
   a.n_tiles = ceil_div(Cp, a.block_n);
   a.b_phase_rows = 0;
-  rc = encode_map_2d(&maps.b, w_down, 16ull * Cs, Cp, 16ull * Cs, 64, a.block_n);
+  a.mc = want_mc(a) ? 1 : 0;
+  rc = encode_map_2d(&maps.b, w_down, 16ull * Cs, Cp, 16ull * Cs, 64, a.mc ? a.block_n / 2 : a.block_n);
   if (rc) return rc;
   a.out = lo;
   a.OH = H; a.OW = W; a.OC = Cp;
@@ -531,13 +564,14 @@ static int conv_up_common(const void* lo, const void* w, void* out, const float*
   a.block_n = pick_block_n(Cs_pad, a.m_tiles * 4);
   a.n_tiles = ceil_div(Cs_pad, a.block_n);
   a.b_phase_rows = Cs_pad;
+  a.mc = (out_kind == OUT_BF16_NHWC && want_mc(a)) ? 1 : 0;
   if (w_is_down) {
     // B is read MN-major straight from w_down[Cp][16*Cs]: 64x64 slabs at column tap*Cs + n, row p
     a.b_mn = 1;
     a.b_tap_cols = Cs;
     rc = encode_map_2d(&maps.b, w, 16ull * Cs, Cp, 16ull * Cs, 64, 64);
   } else {
-    rc = encode_map_2d(&maps.b, w, 4ull * Cp, 4ull * Cs_pad, 4ull * Cp, 64, a.block_n);
+    rc = encode_map_2d(&maps.b, w, 4ull * Cp, 4ull * Cs_pad, 4ull * Cp, 64, a.mc ? a.block_n / 2 : a.block_n);
   }
   if (rc) return rc;
   a.out = out;
@@ -576,7 +610,14 @@ static int gemm_plain(const void* A, int lda, const void* Bw, int ldb, bool b_is
   FwdArgs a;
   fill_common(a, M, 1, 1);
   // K need not be a multiple of 64: the tensor maps carry the true K and TMA zero-fills the tail of the last k-block
-  int rc = encode_map_4d(&maps.a[0], A, K, 1, 1, M, lda, lda, lda, 64, 1, 1, kBlockM);
+  static const bool a2d = [] { const char* e = getenv("RG_A2D"); return !(e && e[0] == '0'); }();
+  int rc;
+  if (a2d) {
+    rc = encode_map_2d(&maps.a[0], A, K, M, lda, 64, kBlockM);
+    a.a_2d = 1;
+  } else {
+    rc = encode_map_4d(&maps.a[0], A, K, 1, 1, M, lda, lda, lda, 64, 1, 1, kBlockM);
+  }
   if (rc) return rc;
   maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
   a.num_taps = 1;
