@@ -42,6 +42,9 @@ const char* rg_last_error(void);
 int rg_check_device(void);
 /* number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches) */
 long long rg_launch_count(void);
+/* profiling aid (tools/gemm_prof.py): when non-NULL, forward tile-engine launches write per-CTA clock64 totals of
+ * their producer / MMA / epilogue roles into buf[grid][12]; NULL (the default) disables it. */
+void rg_debug_set_prof(long long* buf);
 
 /* ---- weight packing (after every optimizer step) --------------------------------------------------------- */
 /* fp32 W[Cp][Cs][4][4] -> bf16 w_down and/or w_up (either may be NULL).  Replaces nothing in the reference: it is
@@ -59,13 +62,20 @@ int rg_cast_pad_bf16(const float* src, void* dst, int rows, int cols, int cols_p
 /* lo[b,i,j,p] = sum_{kh,kw,s} hi[b,2i-1+kh,2j-1+kw,s] * W[p,s,kh,kw]
  * critic forward nn.Conv2d(4,2,1) (torchgan DCGANDiscriminator; args src/histopathology_gan.py:186-192) and
  * generator dgrad (autograd of src/dcgan.py:52). */
-int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int W, int Cs, int Cp, rg_stream_t st);
+/* stats_ws (all three bf16 convolutions; may be NULL): fp32 [rg_stats_parts()][2][C_out] of rg_stats_ws_bytes(C_out)
+ * bytes.  When given, the epilogue also accumulates per-channel sums and sums of squares of the STORED (bf16-rounded)
+ * outputs, one row per CTA in a fixed order (deterministic) -- the nn.BatchNorm2d batch statistics
+ * without a second pass over the activation; finish with rg_bn_finalize_partials.  Needs C_out % 64 == 0. */
+size_t rg_stats_ws_bytes(int C);
+int rg_stats_parts(void);
+int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int W, int Cs, int Cp, float* stats_ws,
+                 rg_stream_t st);
 /* hi[b,y,x,s] = sum lo[b,i,j,p] * W[p,s,kh,kw] over y=2i-1+kh, x=2j-1+kw
  * generator forward nn.ConvTranspose2d(4,2,1) (src/dcgan.py:52) and critic dgrad. */
 /* w: either w_up (w_is_down=0; K-major B, best for Cs <= 128 where the extra packed copy is tiny) or w_down
  * (w_is_down=1; read as an MN-major B operand, so large layers keep a single packed copy). */
 int rg_conv_up(const void* lo, const void* w, int w_is_down, void* hi, int B, int H, int W, int Cp, int Cs,
-               rg_stream_t st);
+               float* stats_ws, rg_stream_t st);
 /* same as rg_conv_up for Cs<=16 image channels, fp32 NCHW output, optional bias + tanh
  * (generator last layer, src/dcgan.py:82; critic layer-0 dgrad). */
 int rg_conv_up_img(const void* lo, const void* w_up, float* img, const float* bias, int act_tanh, int B, int H,
@@ -108,6 +118,11 @@ int rg_bn_stats(const void* a, int M, int C, void* ws, size_t ws_bytes, float* s
 int rg_bn_finalize(const float* sums, const float* gamma, const float* beta, int M, int C, float eps, float momentum,
                    float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean, float* rstd,
                    float* scale, float* shift, rg_stream_t st);
+/* same from the per-CTA partial sums a convolution epilogue left in stats_ws (fixed-order reduction over the
+ * rg_stats_parts() rows); sums_out (optional) receives sums[0][C], sums[1][C] */
+int rg_bn_finalize_partials(const float* stats_ws, const float* gamma, const float* beta, int M, int C, float eps,
+                            float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                            float* sums_out, float* mean, float* rstd, float* scale, float* shift, rg_stream_t st);
 /* h = LeakyReLU(scale*a + shift) */
 int rg_bn_act(const void* a, const float* scale, const float* shift, float slope, void* h, int M, int C,
               rg_stream_t st);
@@ -204,7 +219,7 @@ int rg_upsample2x_reflectpad_bwd(const void* du, void* dh, int B, int H, int W, 
  * the padded grid (weights read MN-major from w3), weight gradient in the torch layout. */
 int rg_pack_conv3(const float* W, void* w3, int Cout, int Cin, int rows, rg_stream_t st);
 int rg_conv3x3(const void* u, const void* w3, void* out, const float* bias, int B, int Ho, int Wo, int Cin, int Cout,
-               rg_stream_t st);
+               float* stats_ws, rg_stream_t st);
 int rg_conv3x3_img(const void* u, const void* w3, float* img, const float* bias, int B, int Ho, int Wo, int Cin,
                    int Cimg, rg_stream_t st);
 int rg_conv3x3_dgrad(const void* da, const void* w3, void* du, int B, int Ho, int Wo, int Cin, int Cout, rg_stream_t st);

@@ -22,12 +22,15 @@ SIGNATURES = {
     "rg_last_error": (_c.c_char_p, []),
     "rg_check_device": (_i, []),
     "rg_launch_count": (_c.c_longlong, []),
+    "rg_debug_set_prof": (None, [_vp]),
     "rg_pack_link": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "rg_pack_proj": (_i, [_vp, _vp, _i, _i, _vp]),
     "rg_pack_edge": (_i, [_vp, _vp, _i, _i, _vp]),
     "rg_cast_pad_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "rg_conv_down": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "rg_conv_up": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rg_stats_ws_bytes": (_sz, [_i]),
+    "rg_stats_parts": (_i, []),
+    "rg_conv_down": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rg_conv_up": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rg_conv_up_img": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rg_conv_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "rg_conv_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _f, _vp, _f, _vp]),
@@ -42,6 +45,7 @@ SIGNATURES = {
     "rg_reduce_ws_bytes": (_sz, [_i, _i]),
     "rg_bn_stats": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp]),
     "rg_bn_finalize": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rg_bn_finalize_partials": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rg_bn_act": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _vp]),
     "rg_bn_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _sz, _vp, _vp]),
     "rg_bn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp, _vp, _vp]),
@@ -70,7 +74,7 @@ SIGNATURES = {
     "rg_upsample2x_reflectpad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rg_upsample2x_reflectpad_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rg_pack_conv3": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "rg_conv3x3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rg_conv3x3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rg_conv3x3_img": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rg_conv3x3_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rg_conv3x3_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),

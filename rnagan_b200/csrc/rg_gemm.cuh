@@ -22,14 +22,19 @@ namespace rg {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                  // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kStages = 4;
-constexpr int kAStageBytes = 128 * 128;      // 16 KiB
-constexpr int kBStageBytes = 256 * 128;      // 32 KiB
-constexpr int kStageBytes = kAStageBytes + kBStageBytes;
-constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*epilogue affine*/;
+constexpr int kMaxStages = 8;
+constexpr int kAStageBytes = 128 * 128;      // 16 KiB: 128 pixel rows x 64 channels
+constexpr int kStagingBytes = 128 * 128;     // one 64-column bf16 slab of the output tile (epilogue -> TMA store)
+constexpr int kBarBytes = 256;
+constexpr int kAffineBytes = 2048;           // per-column scale / shift of the current tile (2 x 256 floats)
+constexpr int kStatBytes = 2048;             // per-warp column sums of one slab (4 warps x 2 x 64 floats)
+constexpr int kSmemFixedBytes = kBarBytes + kAffineBytes + kStatBytes + 1024 /*alignment slack*/;
+constexpr int kSmemMaxBytes = 232448;        // 227 KiB: the sm_100 per-CTA dynamic shared memory limit
 constexpr int kGemmThreads = 192;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;              // TMEM columns per accumulator stage
+// weight-gradient kernel: fixed ring (4 x 48 KiB, or 3 x 64 KiB for 256-row units)
+constexpr int kWgradSmemBytes = 4 * (kAStageBytes + 256 * 128) + kSmemFixedBytes;
 
 struct Tap {
   int8_t map;   // which A-view (parity map) this tap reads
@@ -41,6 +46,7 @@ struct Tap {
 struct GemmMaps {
   CUtensorMap a[4];
   CUtensorMap b;
+  CUtensorMap o[4];   // per-phase output views (bf16 NHWC through the TMA-store epilogue)
 };
 
 enum OutKind { OUT_BF16_NHWC = 0, OUT_F32_NHWC = 1, OUT_F32_NCHW = 2 };
@@ -56,10 +62,17 @@ struct FwdArgs {
   int n_total, block_n, n_tiles;
   int b_phase_rows;       // row offset between phases in the packed weight matrix
   int a_2d;               // 1: maps.a[0] is a rank-2 [rows][K] view (plain GEMMs): cheaper for the TMA unit than 4-D
-  int mc;                 // 1: launched as 2-CTA clusters; the two CTAs take neighbouring M tiles of the same N tile
-                          //    and each fetches half of the B tile with TMA multicast (halves the L2->SM B traffic)
   int b_mn;               // 1: B operand is read MN-major from w_down[Cp][16*Cs] (K rows = p, N contiguous = s)
   int b_tap_cols;         // b_mn: column stride between kernel positions in w_down (= Cs)
+  int nstages;            // smem ring depth (host-planned from block_n and the CTA-pair mode)
+  int b_stage_bytes;      // bytes of the B operand one CTA holds per stage ((block_n / CG) * 128)
+  int tma_store;          // OUT_BF16_NHWC: tile leaves through swizzled smem slabs + TMA stores (whole 128-byte lines)
+  int nbuf;               // staging slabs (1 or 2)
+  int whatif;             // profiling experiments (RG_WHATIF): 1 no MMA, 2 no epilogue work, 4 no A loads, 8 no B loads
+  long long* prof;        // optional [gridDim.x][12] clock64 totals per role (tools/gemm_prof.py); null in production
+  float* stats;           // optional [gridDim.x][2][n_total]: per-CTA column sums / sums of squares of the STORED
+                          // (bf16-rounded) outputs, accumulated in a fixed order -> BatchNorm statistics without
+                          // re-reading the activation (finalised by rg_bn_finalize_partials)
   Tap taps[4][16];
   void* out;
   const float* col_scale;   // optional per-output-column scale (folded eval BatchNorm1d)
@@ -104,6 +117,7 @@ __device__ __forceinline__ void wgrad_slab(const WgradArgs& p, int nt, int sl, i
 // ------------------------------------------------------------------------------------------------ shared setup
 struct PipeSmem {
   uint8_t* stages;
+  uint8_t* staging;
   uint64_t* full;
   uint64_t* empty;
   uint64_t* tfull;
@@ -111,179 +125,283 @@ struct PipeSmem {
   uint32_t* tmem_slot;
   float* s_scale;   // [256] per-column epilogue scale of the current tile
   float* s_shift;   // [256]
+  float* s_stat;    // [4 warps][2][64]
 };
 
-__device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
+// layout: [ring: ring_bytes][staging: staging_bytes][barriers 256][affine 2048][stat 2048], ring 1024-byte aligned
+__device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw, int ring_bytes, int staging_bytes) {
   PipeSmem s;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
   s.stages = base;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kStages * kStageBytes);
+  s.staging = base + ring_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + ring_bytes + staging_bytes);
   s.full = bars;
-  s.empty = bars + kStages;
-  s.tfull = bars + 2 * kStages;
-  s.tempty = bars + 2 * kStages + 2;
-  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  s.s_scale = reinterpret_cast<float*>(base + kStages * kStageBytes + 256);
+  s.empty = bars + kMaxStages;
+  s.tfull = bars + 2 * kMaxStages;
+  s.tempty = bars + 2 * kMaxStages + 2;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  s.s_scale = reinterpret_cast<float*>(base + ring_bytes + staging_bytes + kBarBytes);
   s.s_shift = s.s_scale + 256;
+  s.s_stat = s.s_shift + 256;
+  uint32_t dyn;
+  asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+  if (reinterpret_cast<uint8_t*>(s.s_stat) + kStatBytes > raw + dyn) __trap();   // host under-provisioned the launch
   return s;
 }
 
-__device__ __forceinline__ uint32_t pipeline_prologue(const PipeSmem& s, int warp, int cluster_size = 1) {
+// CG = CTAs per MMA group (1, or 2 = tcgen05 cta_group::2 pair launched as a 2-CTA cluster)
+template <int CG>
+__device__ __forceinline__ uint32_t pipeline_prologue(const PipeSmem& s, int warp, int nstages) {
   if (warp == 1) {
     if (elect_one()) {
-      for (int i = 0; i < kStages; ++i) {
+      for (int i = 0; i < nstages; ++i) {
         mbar_init(&s.full[i], 1);
-        mbar_init(&s.empty[i], cluster_size);   // a stage is free when EVERY CTA that multicasts into it released it
+        mbar_init(&s.empty[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s.tfull[i], 1);
-        mbar_init(&s.tempty[i], 4);   // one arrival per epilogue warp
+        mbar_init(&s.tempty[i], 4 * CG);   // one arrival per epilogue warp of every CTA in the group
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(s.tmem_slot, kTmemCols);
-    tmem_relinquish();
+    tmem_alloc_cg<CG>(s.tmem_slot, kTmemCols);
+    tmem_relinquish_cg<CG>();
   }
   tc_fence_before();
   __syncthreads();
-  if (cluster_size > 1) cluster_sync_all();     // peers' barriers exist before any remote arrive / multicast
+  if (CG > 1) cluster_sync_all();     // the peer's barriers exist before any remote arrive / paired TMA load
   tc_fence_after();
   return *reinterpret_cast<volatile uint32_t*>(s.tmem_slot);
 }
 
+// Column sums over the 32 lanes of a warp of a 32-register row fragment: lane l returns sum_lanes x[l].
+// Butterfly transpose-reduce: 31 shuffles for 32 columns, fixed summation order (deterministic).
+__device__ __forceinline__ float warp_colsum32(const float (&x)[32], int lane) {
+  float a16[16], a8[8], a4[4], a2[2];
+  const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0, h2 = (lane & 2) != 0,
+             h1 = (lane & 1) != 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float keep = h16 ? x[16 + i] : x[i], send = h16 ? x[i] : x[16 + i];
+    a16[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = h8 ? a16[8 + i] : a16[i], send = h8 ? a16[i] : a16[8 + i];
+    a8[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h4 ? a8[4 + i] : a8[i], send = h4 ? a8[i] : a8[4 + i];
+    a4[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = h2 ? a4[2 + i] : a4[i], send = h2 ? a4[i] : a4[2 + i];
+    a2[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 2);
+  }
+  const float keep = h1 ? a2[1] : a2[0], send = h1 ? a2[0] : a2[1];
+  return keep + __shfl_xor_sync(0xFFFFFFFFu, send, 1);
+}
+
+__device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(__float2bfloat16(f)); }
+
 // ------------------------------------------------------------------------------------------------ forward / dgrad
-template <int OUT>
+// Tile order: phase fastest, then M slot, then N tile -- CTAs running at the same time share the A tiles of an M slot
+// across the four output phases of the transposed form (L2 hits) and a persistent CTA keeps its N tile for long runs
+// (statistics accumulate in registers and reach memory only when the N tile changes).
+template <int OUT, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ FwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  const PipeSmem s = carve_smem(smem_raw);
+  const int stage_bytes = kAStageBytes + p.b_stage_bytes;
+  const PipeSmem s = carve_smem(smem_raw, p.nstages * stage_bytes, p.nbuf * kStagingBytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
+    if (OUT == OUT_BF16_NHWC && p.tma_store) tma_prefetch_desc(&maps.o[0]);
   }
-  const int csize = p.mc ? 2 : 1;
-  const int crank = p.mc ? static_cast<int>(cluster_ctarank()) : 0;
-  const uint32_t tmem_base = pipeline_prologue(s, warp, csize);
+  const int crank = CG > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const uint32_t tmem_base = pipeline_prologue<CG>(s, warp, p.nstages);
 
   const int num_kb = p.num_taps * p.chunks;
-  // tile loop: one "slot" = csize neighbouring M tiles (one per CTA of the cluster) of the same (N tile, phase)
-  const int mslots = (p.m_tiles + csize - 1) / csize;
+  const int nstages = p.nstages;
+  const int mslots = (p.m_tiles + CG - 1) / CG;     // one slot = the M tiles of one MMA group
   const int total_tiles = mslots * p.n_tiles * p.num_phases;
-  const int tile0 = blockIdx.x / csize, tile_step = gridDim.x / csize;
-  const uint32_t stage_tx = static_cast<uint32_t>(p.rows_valid) * 128u + static_cast<uint32_t>(p.block_n) * 128u;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
+  // bytes landing per stage on the (leader's) full barrier: A box + this CTA's share of B, from every CTA of the group
+  const uint32_t stage_tx = (((p.whatif & 4) ? 0u : static_cast<uint32_t>(p.rows_valid) * 128u) +
+                             ((p.whatif & 8) ? 0u : static_cast<uint32_t>(p.b_stage_bytes))) * CG;
+  const int bn_cta = p.block_n / CG;                // B rows (N columns) this CTA fetches
 
   if (warp == 0) {
-    // ===================================================== TMA producer (one elected lane)
+    // ===================================================== TMA producer (one elected lane, in every CTA of the group)
+    // This single thread paces the whole pipeline: everything loop-invariant lives in registers (the asm memory
+    // clobbers would otherwise make the compiler re-read kernel parameters every k-block), there is no integer
+    // division in the k loop (taps outer, channel chunks inner) and shared addresses are plain 32-bit integers.
     if (elect_one()) {
+      const int chunks = p.chunks, num_taps = p.num_taps, num_phases = p.num_phases;
+      const int tw = p.tw, th = p.th, bw = p.bw, bh = p.bh, bb = p.bb;
+      const int block_n = p.block_n, b_phase_rows = p.b_phase_rows, b_tap_cols = p.b_tap_cols;
+      const bool a_2d = p.a_2d != 0, b_mn = p.b_mn != 0;
+      const bool skip_a = (p.whatif & 4) != 0, skip_b = (p.whatif & 8) != 0;
+      const bool prof = p.prof != nullptr;
+      const int ns = bn_cta >> 6;
+      const uint32_t ring0 = smem_u32(s.stages);
+      const uint32_t full0 = smem_u32(&s.full[0]), empty0 = smem_u32(&s.empty[0]);
+      const uint32_t full0_tx = CG > 1 ? (full0 & kPeerBitMask) : full0;     // the barrier the TMA bytes count on
+      const uint64_t desc_b = reinterpret_cast<uint64_t>(&maps.b);
+      const uint64_t desc_a0 = reinterpret_cast<uint64_t>(&maps.a[0]);
       int stage = 0;
       uint32_t phase = 0;
+      long long t_wait = 0, t_issue = 0;
+      const long long t_begin = clock64();
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-        const int m_tile = (tile % mslots) * csize + crank;    // may be >= m_tiles for the odd tail: loads zero-fill
-        const int rest = tile / mslots;
-        const int n_tile = rest % p.n_tiles;
-        const int ph = rest / p.n_tiles;
-        const int jt = m_tile % p.tw;
-        const int it = (m_tile / p.tw) % p.th;
-        const int bt = m_tile / (p.tw * p.th);
-        const int j0 = jt * p.bw, i0 = it * p.bh, b0 = bt * p.bb;
-        const int brow = ph * p.b_phase_rows + n_tile * p.block_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.chunks;
-          const int chunk = kb - tap * p.chunks;
+        const int ph = tile % num_phases;
+        const int rest = tile / num_phases;
+        const int m_tile = (rest % mslots) * CG + crank;      // may be >= m_tiles for an odd tail: loads zero-fill
+        const int n_tile = rest / mslots;
+        const int jt = m_tile % tw;
+        const int it = (m_tile / tw) % th;
+        const int bt = m_tile / (tw * th);
+        const int j0 = jt * bw, i0 = it * bh, b0 = bt * bb;
+        const int ncol0 = n_tile * block_n + crank * bn_cta;
+        const int brow = ph * b_phase_rows + ncol0;
+        int kcol = 0;                                          // kb * 64: K coordinate of a K-major B
+        for (int tap = 0; tap < num_taps; ++tap) {
           const Tap t = p.taps[ph][tap];
-          mbar_wait(&s.empty[stage], phase ^ 1u);
-          uint8_t* sa = s.stages + stage * kStageBytes;
-          uint8_t* sb = sa + kAStageBytes;
-          mbar_expect_tx(&s.full[stage], stage_tx);
-          if (p.a_2d) tma_load_2d(&maps.a[0], &s.full[stage], sa, chunk * kBlockK, b0);
-          else tma_load_4d(&maps.a[t.map], &s.full[stage], sa, chunk * kBlockK, j0 + t.dw, i0 + t.dh, b0);
-          if (p.b_mn) {
-            // B^T slabs [64 k-rows = p][64 n = s] straight out of w_down: no second packed copy of the weights
-            const int col0 = t.wtap * p.b_tap_cols + n_tile * p.block_n;
-            const int ns = p.block_n >> 6;
-            if (p.mc) {       // this CTA fetches half of the slabs for both CTAs
-              for (int sl = crank * (ns >> 1); sl < (crank + 1) * (ns >> 1); ++sl)
-                tma_load_2d_mc(&maps.b, &s.full[stage], sb + sl * 8192, col0 + sl * 64, chunk * kBlockK, 3);
-            } else {
-              for (int sl = 0; sl < ns; ++sl)
-                tma_load_2d(&maps.b, &s.full[stage], sb + sl * 8192, col0 + sl * 64, chunk * kBlockK);
+          const uint64_t desc_a = desc_a0 + static_cast<uint64_t>(t.map) * sizeof(CUtensorMap);
+          const int cj = j0 + t.dw, ci = i0 + t.dh;
+          const int bcol = t.wtap * b_tap_cols + ncol0;
+          for (int chunk = 0; chunk < chunks; ++chunk, kcol += kBlockK) {
+            const long long c0 = prof ? clock64() : 0;
+            mbar_wait_raw(empty0 + stage * 8, phase ^ 1u);
+            const long long c1 = prof ? clock64() : 0;
+            const uint32_t sa = ring0 + stage * stage_bytes;
+            const uint32_t sb = sa + kAStageBytes;
+            const uint32_t fb = full0_tx + stage * 8;
+            if (crank == 0) mbar_expect_tx_raw(full0 + stage * 8, stage_tx);
+            if (!skip_a) {
+              if (a_2d) tma_ld_2d_raw<CG>(desc_a0, fb, sa, chunk * kBlockK, b0);
+              else tma_ld_4d_raw<CG>(desc_a, fb, sa, chunk * kBlockK, cj, ci, b0);
             }
-          } else if (p.mc) {  // half of the B rows (box = block_n/2 rows) for both CTAs
-            const int half = p.block_n >> 1;
-            tma_load_2d_mc(&maps.b, &s.full[stage], sb + crank * half * 128, kb * kBlockK, brow + crank * half, 3);
-          } else {
-            tma_load_2d(&maps.b, &s.full[stage], sb, kb * kBlockK, brow);
+            if (!skip_b) {
+              if (b_mn) {
+                // B^T slabs [64 k-rows = p][64 n = s] straight out of w_down: no second packed copy of the weights
+                for (int sl = 0; sl < ns; ++sl)
+                  tma_ld_2d_raw<CG>(desc_b, fb, sb + sl * 8192, bcol + sl * 64, chunk * kBlockK);
+              } else {
+                tma_ld_2d_raw<CG>(desc_b, fb, sb, kcol, brow);
+              }
+            }
+            if (prof) { t_wait += c1 - c0; t_issue += clock64() - c1; }
+            if (++stage == nstages) { stage = 0; phase ^= 1u; }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+      }
+      if (prof) {
+        long long* o = p.prof + static_cast<size_t>(blockIdx.x) * 12;
+        o[0] = clock64() - t_begin; o[1] = t_wait; o[2] = t_issue;
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one elected lane)
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, p.b_mn);
+    // ===================================================== MMA issuer (one elected lane of the leader CTA)
+    if (crank == 0 && elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM * CG, p.block_n, 0, p.b_mn);
       const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
       const uint32_t b_kstep = p.b_mn ? 128u : 2u;   // (>>4) address advance per UMMA_K: 16 rows x 128 B, or 32 B
+      const bool skip_mma = (p.whatif & 1) != 0, prof = p.prof != nullptr;
+      const uint32_t ring0 = smem_u32(s.stages);
+      const uint32_t full0 = smem_u32(&s.full[0]);
+      // descriptor templates: only the 14-bit start-address field changes per stage / k step
+      const uint64_t da0 = make_smem_desc_sw128(0, 16, 1024);
+      const uint64_t db0 = make_smem_desc_sw128(0, b_lbo, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
+      long long t_wfull = 0, t_wtempty = 0;
+      const long long t_begin = clock64();
       for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1u;
+        const long long c0 = prof ? clock64() : 0;
         mbar_wait(&s.tempty[acc], acc_phase ^ 1u);
+        if (prof) t_wtempty += clock64() - c0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&s.full[stage], phase);
+          const long long c1 = prof ? clock64() : 0;
+          mbar_wait_raw(full0 + stage * 8, phase);
+          if (prof) t_wfull += clock64() - c1;
           tc_fence_after();
-          const uint32_t sa = smem_u32(s.stages + stage * kStageBytes);
-          const uint32_t sb = sa + kAStageBytes;
-          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb, b_lbo, 1024);
+          const uint32_t sa = ring0 + stage * stage_bytes;
+          const uint64_t da = da0 | static_cast<uint64_t>((sa >> 4) & 0x3FFF);
+          const uint64_t db = db0 | static_cast<uint64_t>(((sa + kAStageBytes) >> 4) & 0x3FFF);
+          if (!skip_mma) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +32 bytes per UMMA_K inside the 128-byte swizzle row => +2 in the (>>4) address field
-            umma_bf16(tmem_d, da + 2u * k, db + b_kstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // +32 bytes per UMMA_K inside the 128-byte swizzle row => +2 in the (>>4) address field
+              umma_bf16_cg<CG>(tmem_d, da + 2u * k, db + b_kstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
-          if (p.mc) umma_commit_mc(&s.empty[stage], 3);   // both producers write into this stage of my smem
-          else umma_commit(&s.empty[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          umma_commit_cg<CG>(&s.empty[stage]);        // frees this stage in every CTA of the group
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&s.tfull[acc]);
+        umma_commit_cg<CG>(&s.tfull[acc]);
+      }
+      if (prof) {
+        long long* o = p.prof + static_cast<size_t>(blockIdx.x) * 12;
+        o[3] = clock64() - t_begin; o[4] = t_wfull; o[5] = t_wtempty;
       }
     }
   } else {
     // ===================================================== epilogue warps (TMEM lanes 32*(warp%4) ...)
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;                         // 0..127 among the epilogue warps
     const int jj = row % p.bw;
     const int ii = (row / p.bw) % p.bh;
     const int bbi = row / (p.bw * p.bh);
+    const bool affine = (p.col_scale != nullptr) || (p.col_shift != nullptr);
+    const bool lrelu = p.slope != 1.0f;
+    const bool use_tma = (OUT == OUT_BF16_NHWC) && p.tma_store;
+    const bool do_stats = use_tma && (p.stats != nullptr);
+    // the tempty barrier lives in the leader CTA
+    const uint32_t tempty_addr0 = CG > 1 ? mapa_rank(smem_u32(&s.tempty[0]), 0) : smem_u32(&s.tempty[0]);
+    // statistics: thread et owns (quantity k = et >> 6, column (et & 63) of every slab) of this CTA's partial row
+    const int st_k = et >> 6, st_c = et & 63;
+    float st_acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float* st_row = do_stats ? p.stats + (static_cast<size_t>(blockIdx.x) * 2 + st_k) * p.n_total : nullptr;
+    if (do_stats)
+      for (int c = st_c; c < p.n_total; c += 64) st_row[c] = 0.0f;
+    int st_ntile = -1;
+    int store_count = 0;
     int iter = 0;
     int staged_n_tile = -1;
+    long long t_wtfull = 0, t_wstore = 0;
+    const long long t_begin = clock64();
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1u;
-      const int m_tile = (tile % mslots) * csize + crank;
-      const int rest = tile / mslots;
-      const int n_tile = rest % p.n_tiles;
-      const int ph = rest / p.n_tiles;
+      const int ph = tile % p.num_phases;
+      const int rest = tile / p.num_phases;
+      const int m_tile = (rest % mslots) * CG + crank;
+      const int n_tile = rest / mslots;
       const int jt = m_tile % p.tw;
       const int it = (m_tile / p.tw) % p.th;
       const int bt = m_tile / (p.tw * p.th);
       const int b = bt * p.bb + bbi, i = it * p.bh + ii, j = jt * p.bw + jj;
-      const bool row_ok = (m_tile < p.m_tiles) && (row < p.rows_valid) && (b < p.nB) && (i < p.H) && (j < p.W);
+      const bool tile_ok = m_tile < p.m_tiles;
+      const bool row_ok = tile_ok && (row < p.rows_valid) && (b < p.nB) && (i < p.H) && (j < p.W);
       const int y = i * p.sy + p.oy[ph], x = j * p.sx + p.ox[ph];
       const int n0 = n_tile * p.block_n;
 
       // per-column scale / shift of this tile -> smem (one broadcast read per element instead of global loads)
-      const bool affine = (p.col_scale != nullptr) || (p.col_shift != nullptr);
       if (affine && n_tile != staged_n_tile) {                 // reload only when the column range changes
-        const int et = threadIdx.x - 64;                       // 0..127 among the epilogue warps
         asm volatile("bar.sync 1, 128;" ::: "memory");        // previous tile's readers are done
         for (int cc = et; cc < p.block_n; cc += 128) {
           const int col = n0 + cc;
@@ -294,12 +412,129 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
         asm volatile("bar.sync 1, 128;" ::: "memory");
         staged_n_tile = n_tile;
       }
-      const bool lrelu = p.slope != 1.0f;
+      if (do_stats && n_tile != st_ntile) {                    // flush the register accumulators of the old N tile
+        if (st_ntile >= 0) {
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            const int c = st_ntile * p.block_n + sl * 64 + st_c;
+            if (sl * 64 < p.block_n && c < p.n_total) st_row[c] += st_acc[sl];
+            st_acc[sl] = 0.0f;
+          }
+        }
+        st_ntile = n_tile;
+      }
 
+      const long long cw0 = p.prof ? clock64() : 0;
       mbar_wait(&s.tfull[acc], acc_phase);
+      if (p.prof) t_wtfull += clock64() - cw0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
+      if (p.whatif & 2) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG > 1) mbar_arrive_cluster(tempty_addr0 + acc * 8);
+          else mbar_arrive(&s.tempty[acc]);
+        }
+        continue;
+      }
+      if (use_tma) {
+        // ------------------------------------------------- bf16 NHWC through swizzled smem slabs + TMA stores
+        const int nslabs = p.block_n >> 6;
+        const int j0 = jt * p.bw, i0 = it * p.bh, b0 = bt * p.bb;
+#pragma unroll 1
+        for (int sl = 0; sl < nslabs; ++sl, ++store_count) {
+          uint8_t* buf = s.staging + (p.nbuf == 2 ? (store_count & 1) : 0) * kStagingBytes;
+          // the TMA store that last read this slab buffer has finished reading it
+          if (et == 0) {
+            const long long cs0 = p.prof ? clock64() : 0;
+            if (p.nbuf == 2) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+            if (p.prof) t_wstore += clock64() - cs0;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float csum[2] = {0.0f, 0.0f}, csq[2] = {0.0f, 0.0f};
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int c = sl * 64 + hh * 32;
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c, v);
+            tmem_ld_wait();
+            if (affine) {
+              const float4* sc4 = reinterpret_cast<const float4*>(s.s_scale + c);
+              const float4* sh4 = reinterpret_cast<const float4*>(s.s_shift + c);
+#pragma unroll
+              for (int g4 = 0; g4 < 8; ++g4) {
+                const float4 a4 = sc4[g4], b4 = sh4[g4];
+                v[g4 * 4 + 0] = __float_as_uint(fmaf(__uint_as_float(v[g4 * 4 + 0]), a4.x, b4.x));
+                v[g4 * 4 + 1] = __float_as_uint(fmaf(__uint_as_float(v[g4 * 4 + 1]), a4.y, b4.y));
+                v[g4 * 4 + 2] = __float_as_uint(fmaf(__uint_as_float(v[g4 * 4 + 2]), a4.z, b4.z));
+                v[g4 * 4 + 3] = __float_as_uint(fmaf(__uint_as_float(v[g4 * 4 + 3]), a4.w, b4.w));
+              }
+            }
+            if (lrelu) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const float f = __uint_as_float(v[e]);
+                v[e] = __float_as_uint(fmaxf(f, f * p.slope));
+              }
+            }
+            // pack to bf16 and write this row's 64 bytes: 16-byte chunk index XOR (row & 7) = the SWIZZLE_128B
+            // pattern the output tensor map expects (and conflict-free: 8 rows cover all 8 chunk positions)
+            uint8_t* rowp = buf + row * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+              u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+              u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+              u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+              const int chunk = hh * 4 + g;
+              *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = u;
+            }
+            if (do_stats) {
+              float xs[32];
+#pragma unroll
+              for (int e = 0; e < 32; ++e) xs[e] = row_ok ? bf16_round(__uint_as_float(v[e])) : 0.0f;
+              csum[hh] = warp_colsum32(xs, lane);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) xs[e] *= xs[e];
+              csq[hh] = warp_colsum32(xs, lane);
+            }
+          }
+          if (sl == nslabs - 1) {          // accumulator drained: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG > 1) mbar_arrive_cluster(tempty_addr0 + acc * 8);
+              else mbar_arrive(&s.tempty[acc]);
+            }
+          }
+          if (do_stats) {
+            float* ss = s.s_stat + q * 128;
+            ss[lane] = csum[0]; ss[32 + lane] = csum[1];
+            ss[64 + lane] = csq[0]; ss[96 + lane] = csq[1];
+          }
+          fence_proxy_async();             // generic-proxy smem writes -> visible to the TMA (async proxy)
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0 && tile_ok) {
+            tma_store_4d(&maps.o[ph], buf, n0 + sl * 64, j0, i0, b0);
+            bulk_commit();
+          }
+          if (do_stats) {                  // fixed-order sum of the four warps' partial column sums
+            const float* ss = s.s_stat + st_k * 64 + st_c;
+            const float t = ((ss[0] + ss[128]) + ss[256]) + ss[384];
+            if (sl == 0) st_acc[0] += t;
+            else if (sl == 1) st_acc[1] += t;
+            else if (sl == 2) st_acc[2] += t;
+            else st_acc[3] += t;
+          }
+        }
+        continue;
+      }
+
+      // ------------------------------------------------- direct stores (fp32 outputs, narrow bf16 tiles)
       for (int c = 0; c < p.block_n; c += 32) {
         uint32_t v[32];
         if (p.block_n >= 32) {
@@ -382,14 +617,29 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+      if (lane == 0) {
+        if (CG > 1) mbar_arrive_cluster(tempty_addr0 + acc * 8);
+        else mbar_arrive(&s.tempty[acc]);
+      }
+    }
+    if (do_stats && st_ntile >= 0) {
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const int c = st_ntile * p.block_n + sl * 64 + st_c;
+        if (sl * 64 < p.block_n && c < p.n_total) st_row[c] += st_acc[sl];
+      }
+    }
+    if (use_tma && et == 0) bulk_wait_read<0>();     // smem must outlive the last store's reads
+    if (p.prof && et == 0) {
+      long long* o = p.prof + static_cast<size_t>(blockIdx.x) * 12;
+      o[6] = clock64() - t_begin; o[7] = t_wtfull; o[8] = t_wstore; o[9] = iter;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (p.mc) cluster_sync_all();   // the peer may still multicast into this CTA's smem / arrive on its barriers
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (CG > 1) cluster_sync_all();   // the peer may still arrive on this CTA's barriers / its MMAs read this smem
+  if (warp == 1) tmem_dealloc_cg<CG>(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
@@ -400,7 +650,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ WgradArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  const PipeSmem s = carve_smem(smem_raw);
+  const PipeSmem s = carve_smem(smem_raw, 4 * (kAStageBytes + 256 * 128), 0);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -408,7 +658,7 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
   }
-  const uint32_t tmem_base = pipeline_prologue(s, warp);
+  const uint32_t tmem_base = pipeline_prologue<1>(s, warp, 4);
 
   const int msub = p.msub;                                    // 128-row accumulators per unit (1 or 2)
   const int a_bytes = msub * 16384;                           // msub * 2 slabs of [64 px][64 ch]
@@ -418,42 +668,66 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
   const uint32_t stage_tx = static_cast<uint32_t>(2 * msub + p.slabs_per_tile) * 8192u;
 
   if (warp == 0) {
+    // Producer: one thread paces the pipeline, so the pixel-block loop holds no division, no parameter re-reads and
+    // no per-slab tap decoding (all hoisted per unit into registers).
     if (elect_one()) {
+      const int m_tiles = p.m_tiles, n_tiles = p.n_tiles, pb_per_split = p.pb_per_split, num_pb = p.num_pb;
+      const int tw = p.tw, th = p.th, bw = p.bw, bh = p.bh, bb = p.bb;
+      const int spt = p.slabs_per_tile;
+      const uint32_t ring0 = smem_u32(s.stages);
+      const uint32_t full0 = smem_u32(&s.full[0]), empty0 = smem_u32(&s.empty[0]);
+      const uint64_t desc_lo = reinterpret_cast<uint64_t>(&maps.b);
+      const uint64_t desc_hi0 = reinterpret_cast<uint64_t>(&maps.a[0]);
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const int m_tile = u % p.m_tiles;
-        const int rest = u / p.m_tiles;
-        const int n_tile = rest % p.n_tiles;
-        const int split = rest / p.n_tiles;
-        const int pb0 = split * p.pb_per_split;
-        const int pb1 = min(p.num_pb, pb0 + p.pb_per_split);
-        for (int pb = pb0; pb < pb1; ++pb) {
-          const int jt = pb % p.tw;
-          const int it = (pb / p.tw) % p.th;
-          const int bt = pb / (p.tw * p.th);
-          const int j0 = jt * p.bw, i0 = it * p.bh, b0 = bt * p.bb;
-          mbar_wait(&s.empty[stage], phase ^ 1u);
-          uint8_t* sa = s.stages + stage * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
-          mbar_expect_tx(&s.full[stage], stage_tx);
-          // MMA-A operand: 64-channel slabs of the low-resolution tensor (channels beyond Cp zero-fill)
-          for (int sl = 0; sl < 2 * msub; ++sl)
-            tma_load_4d(&maps.b, &s.full[stage], sa + sl * 8192, m_tile * 128 * msub + sl * 64, j0, i0, b0);
-          // MMA-B operand: one slab per (tap, 64-channel chunk) of the high-resolution tensor
-          for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
+        const int m_tile = u % m_tiles;
+        const int rest = u / m_tiles;
+        const int n_tile = rest % n_tiles;
+        const int split = rest / n_tiles;
+        const int pb0 = split * pb_per_split;
+        const int pb1 = min(num_pb, pb0 + pb_per_split);
+        uint64_t sdesc[4];
+        int sdw[4], sdh[4], scol[4];
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          sdesc[sl] = desc_hi0; sdw[sl] = 0; sdh[sl] = 0; scol[sl] = 0;
+          if (sl < spt) {
             int tap, chunk;
             wgrad_slab(p, n_tile, sl, tap, chunk);
             const Tap t = p.taps[tap];
-            tma_load_4d(&maps.a[t.map], &s.full[stage], sb + sl * 8192, chunk * 64, j0 + t.dw, i0 + t.dh, b0);
+            sdesc[sl] = desc_hi0 + static_cast<uint64_t>(t.map) * sizeof(CUtensorMap);
+            sdw[sl] = t.dw; sdh[sl] = t.dh; scol[sl] = chunk * 64;
           }
+        }
+        const int mcol = m_tile * 128 * msub;
+        int jt = pb0 % tw, it = (pb0 / tw) % th, bt = pb0 / (tw * th);
+        for (int pb = pb0; pb < pb1; ++pb) {
+          const int j0 = jt * bw, i0 = it * bh, b0 = bt * bb;
+          mbar_wait_raw(empty0 + stage * 8, phase ^ 1u);
+          const uint32_t sa = ring0 + stage * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+          const uint32_t fb = full0 + stage * 8;
+          mbar_expect_tx_raw(fb, stage_tx);
+          // MMA-A operand: 64-channel slabs of the low-resolution tensor (channels beyond Cp zero-fill)
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl)
+            if (sl < 2 * msub) tma_ld_4d_raw<1>(desc_lo, fb, sa + sl * 8192, mcol + sl * 64, j0, i0, b0);
+          // MMA-B operand: one slab per (tap, 64-channel chunk) of the high-resolution tensor
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl)
+            if (sl < spt) tma_ld_4d_raw<1>(sdesc[sl], fb, sb + sl * 8192, scol[sl], j0 + sdw[sl], i0 + sdh[sl], b0);
           if (++stage == nstages) { stage = 0; phase ^= 1u; }
+          if (++jt == tw) { jt = 0; if (++it == th) { it = 0; ++bt; } }
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(kBlockM, 64 * p.slabs_per_tile, 1, 1);
+      const uint32_t ring0 = smem_u32(s.stages);
+      const uint32_t full0 = smem_u32(&s.full[0]);
+      const uint64_t d0 = make_smem_desc_sw128(0, 8192, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -468,15 +742,15 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
         for (int pb = pb0; pb < pb1; ++pb) {
-          mbar_wait(&s.full[stage], phase);
+          mbar_wait_raw(full0 + stage * 8, phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(s.stages + stage * stage_bytes);
+          const uint32_t sa = ring0 + stage * stage_bytes;
           const uint32_t sb = sa + a_bytes;
           // MN-major SWIZZLE_128B: LBO = stride between 64-element MN slabs (8 KiB),
           // SBO = stride between 8-row K groups (1 KiB); one UMMA_K = 16 pixel rows = 2 KiB.
-          const uint64_t db = make_smem_desc_sw128(sb, 8192, 1024);
+          const uint64_t db = d0 | static_cast<uint64_t>((sb >> 4) & 0x3FFF);
           for (int ms = 0; ms < msub; ++ms) {
-            const uint64_t da = make_smem_desc_sw128(sa + ms * 16384, 8192, 1024);
+            const uint64_t da = d0 | static_cast<uint64_t>(((sa + ms * 16384) >> 4) & 0x3FFF);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(tmem_d + ms * kAccStride, da + 128u * k, db + 128u * k, idesc, (pb > pb0 || k > 0) ? 1u : 0u);

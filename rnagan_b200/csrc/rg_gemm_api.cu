@@ -22,6 +22,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   return static_cast<int>(e);
 }
 static std::atomic<long long> g_launches{0};
+static long long* g_prof = nullptr;   // tools/gemm_prof.py: per-CTA role clocks of the next forward launches
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 int num_sms() {
@@ -120,70 +121,134 @@ static const int kDownPar[4] = {1, 0, 1, 0};
 static const int kUpOff[2][2] = {{0, -1}, {0, 1}};
 static const int kUpK[2][2] = {{1, 3}, {2, 0}};
 
-static int pick_block_n(int n_total, int tiles_per_n) {
+static bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  if (!e || !e[0]) return dflt;
+  return e[0] != '0';
+}
+
+// CTA pairs (tcgen05 cta_group::2): the two SMs of a TPC share one 256-row tile, each fetching half of the B rows, so
+// an SM ingests 1.5x fewer operand bytes per FLOP than with two independent 128 x 256 tiles -- the L2 -> SM path, not
+// the tensor pipe, bounds the single-CTA kernel (profiles/r1_ncu_gemm.txt: 52 B/clk/SM at 55 % tensor peak).
+static bool pair_allowed(const FwdArgs& a, int out_kind) {
+  static const bool allow = env_flag("RG_CG2", true);
+  return allow && out_kind == OUT_BF16_NHWC && a.m_tiles >= 2;
+}
+static int pick_block_n(int n_total, int tiles_per_n, int cg = 1) {
   int bn = 256;
   while ((bn >> 1) >= n_total && bn > 16) bn >>= 1;   // smallest power of two >= n_total (rows beyond zero-fill)
-  const int target = (num_sms() * 4) / 5;
-  while (bn > 64 && ceil_div(n_total, bn) * tiles_per_n < target) bn >>= 1;
+  const int target = (num_sms() / cg * 4) / 5;
+  const int units_per_n = ceil_div(tiles_per_n, cg);
+  while (bn > 64 && ceil_div(n_total, bn) * units_per_n < target) bn >>= 1;
   return bn;
+}
+static int pick_cg(const FwdArgs& a, int out_kind) {
+  if (!pair_allowed(a, out_kind)) return 1;
+  if (a.block_n < 32 || a.block_n % 16 != 0) return 1;
+  if (a.b_mn && a.block_n % 128 != 0) return 1;       // MN-major B arrives in 64-column slabs: each CTA needs >= 1
+  return 2;
 }
 
 static int ensure_attrs() {
   static bool done = false;
   if (!done) {
-    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_BF16_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kGemmSmemBytes));
-    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_F32_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kGemmSmemBytes));
-    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_F32_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kGemmSmemBytes));
-    RG_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_BF16_NHWC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSmemMaxBytes));
+    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_BF16_NHWC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSmemMaxBytes));
+    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_F32_NHWC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSmemMaxBytes));
+    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_F32_NCHW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSmemMaxBytes));
+    RG_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBytes));
     done = true;
   }
   return 0;
 }
 
-// 2-CTA clusters with TMA multicast of the B tile (see FwdArgs::mc): worth it when the tile is wide enough to split
-static bool want_mc(const FwdArgs& a) {
-  // measured on B200 (same box A/B, full training step): neutral (17.38 vs 17.36 ms/step) -- these kernels are not
-  // L2-bandwidth bound -- so the simpler non-cluster launch stays the default; RG_MC=1 enables the multicast path
-  static const bool allow = [] { const char* e = getenv("RG_MC"); return e && e[0] == '1'; }();
-  return allow && a.block_n >= 128 && a.m_tiles >= 2;
-}
-
-template <int OUT>
-static int launch_fwd_t(const GemmMaps& maps, const FwdArgs& a, cudaStream_t st) {
-  const int csize = a.mc ? 2 : 1;
-  const int slots = ceil_div(a.m_tiles, csize) * a.n_tiles * a.num_phases;
-  const int grid = std::min(slots, num_sms() / csize) * csize;
-  if (!a.mc) {
-    gemm_fwd_kernel<OUT><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
+template <int OUT, int CG>
+static int launch_fwd_t(const GemmMaps& maps, const FwdArgs& a, int grid, size_t smem, cudaStream_t st) {
+  if (CG == 1) {
+    gemm_fwd_kernel<OUT, CG><<<grid, kGemmThreads, smem, st>>>(maps, a);
   } else {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = kGemmSmemBytes;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RG_CUDA(cudaLaunchKernelEx(&cfg, gemm_fwd_kernel<OUT>, maps, a));
+    RG_CUDA(cudaLaunchKernelEx(&cfg, gemm_fwd_kernel<OUT, CG>, maps, a));
   }
   RG_LAUNCH_CHECK("gemm_fwd_kernel");
   return 0;
 }
 
-static int launch_fwd(const GemmMaps& maps, const FwdArgs& a, int out_kind, cudaStream_t st) {
+size_t stats_ws_floats(int C) { return static_cast<size_t>(num_sms()) * 2 * C; }
+
+// cg: the CTA-group size the caller encoded the B map for (pick_cg).  stats_ws: optional [num_sms][2][n_total] fp32.
+static int launch_fwd(GemmMaps& maps, FwdArgs& a, int out_kind, int cg, float* stats_ws, cudaStream_t st) {
   int rc = ensure_attrs();
   if (rc) return rc;
-  if (out_kind == OUT_BF16_NHWC) return launch_fwd_t<OUT_BF16_NHWC>(maps, a, st);
-  if (out_kind == OUT_F32_NHWC) return launch_fwd_t<OUT_F32_NHWC>(maps, a, st);
-  return launch_fwd_t<OUT_F32_NCHW>(maps, a, st);
+  static const bool allow_tma_store = env_flag("RG_TMA_STORE", true);
+  a.tma_store = (allow_tma_store && out_kind == OUT_BF16_NHWC && a.block_n % 64 == 0 && a.OC % 8 == 0 &&
+                 (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) ? 1 : 0;
+  if (stats_ws && !(a.tma_store && a.n_total % 64 == 0)) {
+    set_error("fused statistics need a bf16 output with a multiple of 64 channels (n_total=%d block_n=%d)", a.n_total,
+              a.block_n);
+    return RG_EINVAL;
+  }
+  a.stats = stats_ws;
+  {
+    const char* e = getenv("RG_WHATIF");    // read per call: the profiling tool flips it between launches
+    a.whatif = e ? atoi(e) : 0;
+  }
+  a.prof = g_prof;
+  // shared-memory plan: ring of (A 16 KiB + this CTA's share of B) stages, then the epilogue staging slabs
+  a.b_stage_bytes = (a.block_n / cg) * 128;
+  const int stage = kAStageBytes + a.b_stage_bytes;
+  const int avail = kSmemMaxBytes - kSmemFixedBytes;
+  a.nbuf = a.tma_store ? 2 : 0;
+  int ns = (avail - a.nbuf * kStagingBytes) / stage;
+  if (a.tma_store && ns < 4) {
+    a.nbuf = 1;
+    ns = (avail - kStagingBytes) / stage;
+  }
+  a.nstages = std::min(ns, kMaxStages);
+  const size_t smem = static_cast<size_t>(a.nstages) * stage + a.nbuf * kStagingBytes + kSmemFixedBytes;
+  if (a.tma_store) {
+    // per-phase output views: pixel (b, i*sy + oy, j*sx + ox), channels [0, n_valid); TMA clips what lies outside
+    const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(a.out);
+    for (int ph = 0; ph < a.num_phases; ++ph) {
+      const __nv_bfloat16* b0 = base + (static_cast<size_t>(a.oy[ph]) * a.OW + a.ox[ph]) * a.OC;
+      rc = encode_map_4d(&maps.o[ph], b0, a.n_valid, a.W, a.H, a.nB, static_cast<uint64_t>(a.sx) * a.OC,
+                         static_cast<uint64_t>(a.sy) * a.OW * a.OC, static_cast<uint64_t>(a.OH) * a.OW * a.OC, 64, a.bw,
+                         a.bh, a.bb);
+      if (rc) return rc;
+    }
+  }
+  const int slots = ceil_div(a.m_tiles, cg) * a.n_tiles * a.num_phases;
+  const int grid = std::min(slots, num_sms() / cg) * cg;
+  if (stats_ws && grid < num_sms()) {
+    const size_t row = 2ull * a.n_total * sizeof(float);
+    RG_CUDA(cudaMemsetAsync(stats_ws + static_cast<size_t>(grid) * 2 * a.n_total, 0, (num_sms() - grid) * row, st));
+  }
+  if (out_kind == OUT_BF16_NHWC) {
+    if (cg == 2) return launch_fwd_t<OUT_BF16_NHWC, 2>(maps, a, grid, smem, st);
+    return launch_fwd_t<OUT_BF16_NHWC, 1>(maps, a, grid, smem, st);
+  }
+  if (cg != 1) {
+    set_error("internal: CTA pairs are only instantiated for bf16 outputs");
+    return RG_EINVAL;
+  }
+  if (out_kind == OUT_F32_NHWC) return launch_fwd_t<OUT_F32_NHWC, 1>(maps, a, grid, smem, st);
+  return launch_fwd_t<OUT_F32_NCHW, 1>(maps, a, grid, smem, st);
 }
 
 static void fill_common(FwdArgs& a, int B, int H, int W) {
@@ -326,7 +391,7 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
   }
   const int units = w.m_tiles * w.n_tiles * w.splits;
   const int grid = std::min(units, num_sms());
-  gemm_wgrad_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(maps, a);
+  gemm_wgrad_kernel<<<grid, kGemmThreads, kWgradSmemBytes, st>>>(maps, a);
   RG_LAUNCH_CHECK("gemm_wgrad_kernel");
   if (direct) return 0;
   const size_t n = static_cast<size_t>(Cp) * Cs_out;
@@ -452,6 +517,10 @@ int rg_check_device(void) {
   return 0;
 }
 
+void rg_debug_set_prof(long long* buf) { g_prof = buf; }
+size_t rg_stats_ws_bytes(int C) { return C > 0 ? stats_ws_floats(C) * sizeof(float) : 0; }
+int rg_stats_parts(void) { return num_sms(); }
+
 int rg_pack_link(const float* W, void* w_down, void* w_up, int Cp, int Cs, rg_stream_t st_) {
   cudaStream_t st = static_cast<cudaStream_t>(st_);
   RG_CHECK_ARG(W && Cp > 0 && Cs > 0, "rg_pack_link: bad arguments");
@@ -496,7 +565,8 @@ int rg_cast_pad_bf16(const float* src, void* dst, int rows, int cols, int cols_p
   return 0;
 }
 
-int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int W, int Cs, int Cp, rg_stream_t st_) {
+int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int W, int Cs, int Cp, float* stats_ws,
+                 rg_stream_t st_) {
   cudaStream_t st = static_cast<cudaStream_t>(st_);
   RG_CHECK_ARG(hi && w_down && lo, "rg_conv_down: null pointer");
   RG_CHECK_ARG(B > 0 && is_pow2(H) && is_pow2(W), "rg_conv_down: H, W must be powers of two (got %d x %d)", H, W);
@@ -518,20 +588,20 @@ int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int
       a.taps[0][kh * 4 + kw] = t;
     }
   a.n_total = Cp;
-  a.block_n = pick_block_n(Cp, a.m_tiles);
+  a.block_n = pick_block_n(Cp, a.m_tiles, pair_allowed(a, OUT_BF16_NHWC) ? 2 : 1);
   a.n_tiles = ceil_div(Cp, a.block_n);
   a.b_phase_rows = 0;
-  a.mc = want_mc(a) ? 1 : 0;
-  rc = encode_map_2d(&maps.b, w_down, 16ull * Cs, Cp, 16ull * Cs, 64, a.mc ? a.block_n / 2 : a.block_n);
+  const int cg = pick_cg(a, OUT_BF16_NHWC);
+  rc = encode_map_2d(&maps.b, w_down, 16ull * Cs, Cp, 16ull * Cs, 64, a.block_n / cg);
   if (rc) return rc;
   a.out = lo;
   a.OH = H; a.OW = W; a.OC = Cp;
   a.n_valid = Cp;
-  return launch_fwd(maps, a, OUT_BF16_NHWC, st);
+  return launch_fwd(maps, a, OUT_BF16_NHWC, cg, stats_ws, st);
 }
 
 static int conv_up_common(const void* lo, const void* w, void* out, const float* bias, int act_tanh, int B, int H,
-                          int W, int Cp, int Cs, int out_kind, bool w_is_down, cudaStream_t st) {
+                          int W, int Cp, int Cs, int out_kind, bool w_is_down, float* stats_ws, cudaStream_t st) {
   RG_CHECK_ARG(lo && w && out, "rg_conv_up: null pointer");
   RG_CHECK_ARG(B > 0 && is_pow2(H) && is_pow2(W), "rg_conv_up: H, W must be powers of two (got %d x %d)", H, W);
   RG_CHECK_ARG(Cp % 64 == 0, "rg_conv_up: need Cp %% 64 == 0 (Cp=%d)", Cp);
@@ -561,17 +631,17 @@ static int conv_up_common(const void* lo, const void* w, void* out, const float*
         }
     }
   a.n_total = Cs_pad;
-  a.block_n = pick_block_n(Cs_pad, a.m_tiles * 4);
+  a.block_n = pick_block_n(Cs_pad, a.m_tiles * 4, pair_allowed(a, out_kind) ? 2 : 1);
   a.n_tiles = ceil_div(Cs_pad, a.block_n);
   a.b_phase_rows = Cs_pad;
-  a.mc = (out_kind == OUT_BF16_NHWC && want_mc(a)) ? 1 : 0;
+  a.b_mn = w_is_down ? 1 : 0;
+  const int cg = pick_cg(a, out_kind);
   if (w_is_down) {
     // B is read MN-major straight from w_down[Cp][16*Cs]: 64x64 slabs at column tap*Cs + n, row p
-    a.b_mn = 1;
     a.b_tap_cols = Cs;
     rc = encode_map_2d(&maps.b, w, 16ull * Cs, Cp, 16ull * Cs, 64, 64);
   } else {
-    rc = encode_map_2d(&maps.b, w, 4ull * Cp, 4ull * Cs_pad, 4ull * Cp, 64, a.mc ? a.block_n / 2 : a.block_n);
+    rc = encode_map_2d(&maps.b, w, 4ull * Cp, 4ull * Cs_pad, 4ull * Cp, 64, a.block_n / cg);
   }
   if (rc) return rc;
   a.out = out;
@@ -580,21 +650,21 @@ static int conv_up_common(const void* lo, const void* w, void* out, const float*
   a.n_valid = Cs;
   a.col_shift = bias;
   a.act_tanh = act_tanh;
-  return launch_fwd(maps, a, out_kind, st);
+  return launch_fwd(maps, a, out_kind, cg, stats_ws, st);
 }
 
 int rg_conv_up(const void* lo, const void* w, int w_is_down, void* hi, int B, int H, int W, int Cp, int Cs,
-               rg_stream_t st_) {
+               float* stats_ws, rg_stream_t st_) {
   RG_CHECK_ARG(Cs % (w_is_down ? 64 : 16) == 0,
                "rg_conv_up: need Cs %% 64 == 0 with w_down, %% 16 with w_up (Cs=%d); use rg_conv_up_img for images", Cs);
-  return conv_up_common(lo, w, hi, nullptr, 0, B, H, W, Cp, Cs, OUT_BF16_NHWC, w_is_down != 0,
+  return conv_up_common(lo, w, hi, nullptr, 0, B, H, W, Cp, Cs, OUT_BF16_NHWC, w_is_down != 0, stats_ws,
                         static_cast<cudaStream_t>(st_));
 }
 
 int rg_conv_up_img(const void* lo, const void* w_up, float* img, const float* bias, int act_tanh, int B, int H, int W,
                    int Cp, int Cimg, rg_stream_t st_) {
   RG_CHECK_ARG(Cimg >= 1 && Cimg <= 8, "rg_conv_up_img: 1..8 image channels supported (got %d)", Cimg);
-  return conv_up_common(lo, w_up, img, bias, act_tanh, B, H, W, Cp, Cimg, OUT_F32_NCHW, false,
+  return conv_up_common(lo, w_up, img, bias, act_tanh, B, H, W, Cp, Cimg, OUT_F32_NCHW, false, nullptr,
                         static_cast<cudaStream_t>(st_));
 }
 
@@ -624,17 +694,19 @@ static int gemm_plain(const void* A, int lda, const void* Bw, int ldb, bool b_is
   a.chunks = ceil_div(K, 64);
   Tap t = {0, 0, 0, 0};
   a.taps[0][0] = t;
+  const int out_kind = out_f32 ? OUT_F32_NHWC : OUT_BF16_NHWC;
   a.n_total = N;
-  a.block_n = pick_block_n(N, a.m_tiles);
+  a.block_n = pick_block_n(N, a.m_tiles, pair_allowed(a, out_kind) ? 2 : 1);
   if (b_is_kn && a.block_n < 64) a.block_n = 64;
   a.n_tiles = ceil_div(N, a.block_n);
+  a.b_mn = b_is_kn ? 1 : 0;
+  const int cg = pick_cg(a, out_kind);
   if (b_is_kn) {
     // Bw is [K][N] row-major (e.g. an nn.Linear weight [out=K][in=N] used for its input gradient): MN-major B slabs
-    a.b_mn = 1;
     a.b_tap_cols = 0;
     rc = encode_map_2d(&maps.b, Bw, N, K, ldb, 64, 64);
   } else {
-    rc = encode_map_2d(&maps.b, Bw, K, N, ldb, 64, a.block_n);
+    rc = encode_map_2d(&maps.b, Bw, K, N, ldb, 64, a.block_n / cg);
   }
   if (rc) return rc;
   a.out = C;
@@ -643,7 +715,7 @@ static int gemm_plain(const void* A, int lda, const void* Bw, int ldb, bool b_is
   a.col_scale = col_scale;
   a.col_shift = col_shift;
   a.slope = slope;
-  return launch_fwd(maps, a, out_f32 ? OUT_F32_NHWC : OUT_BF16_NHWC, st);
+  return launch_fwd(maps, a, out_kind, cg, nullptr, st);
 }
 
 int rg_gemm_nt(const void* A, const void* Bw, void* C, int M, int N, int K, int ldc, const float* col_scale,
@@ -667,7 +739,7 @@ int rg_gemm_nn(const void* A, int lda, const void* Bw, int ldb, void* C, int M, 
 // ------------------------------------------------------------------------------------------------ 3x3 stride-1 conv
 // u: reflect-padded, 2x-upsampled activation bf16 [B][Ho+2][Wo+2][Cin]; w3: bf16 [Cout_pad][9*Cin], k = tap*Cin + c.
 static int conv3_common(const void* u, const void* w3, void* out, const float* bias, int B, int Ho, int Wo, int Cin,
-                        int Cout, int out_kind, cudaStream_t st) {
+                        int Cout, int out_kind, float* stats_ws, cudaStream_t st) {
   RG_CHECK_ARG(u && w3 && out, "rg_conv3x3: null pointer");
   RG_CHECK_ARG(B > 0 && is_pow2(Ho) && is_pow2(Wo) && Cin % 64 == 0, "rg_conv3x3: need power-of-two Ho, Wo and Cin %% 64 == 0");
   const int Cout_pad = std::max(16, (Cout + 15) / 16 * 16);
@@ -686,27 +758,28 @@ static int conv3_common(const void* u, const void* w3, void* out, const float* b
       a.taps[0][kh * 3 + kw] = t;
     }
   a.n_total = Cout_pad;
-  a.block_n = pick_block_n(Cout_pad, a.m_tiles);
+  a.block_n = pick_block_n(Cout_pad, a.m_tiles, pair_allowed(a, out_kind) ? 2 : 1);
   a.n_tiles = ceil_div(Cout_pad, a.block_n);
-  rc = encode_map_2d(&maps.b, w3, 9ull * Cin, Cout_pad, 9ull * Cin, 64, a.block_n);
+  const int cg = pick_cg(a, out_kind);
+  rc = encode_map_2d(&maps.b, w3, 9ull * Cin, Cout_pad, 9ull * Cin, 64, a.block_n / cg);
   if (rc) return rc;
   a.out = out;
   a.OH = Ho; a.OW = Wo; a.OC = Cout;
   a.n_valid = Cout;
   a.col_shift = bias;
-  return launch_fwd(maps, a, out_kind, st);
+  return launch_fwd(maps, a, out_kind, cg, stats_ws, st);
 }
 
 int rg_conv3x3(const void* u, const void* w3, void* out, const float* bias, int B, int Ho, int Wo, int Cin, int Cout,
-               rg_stream_t st) {
+               float* stats_ws, rg_stream_t st) {
   RG_CHECK_ARG(Cout % 8 == 0, "rg_conv3x3: need Cout %% 8 == 0 (use rg_conv3x3_img for image channels)");
-  return conv3_common(u, w3, out, bias, B, Ho, Wo, Cin, Cout, OUT_BF16_NHWC, static_cast<cudaStream_t>(st));
+  return conv3_common(u, w3, out, bias, B, Ho, Wo, Cin, Cout, OUT_BF16_NHWC, stats_ws, static_cast<cudaStream_t>(st));
 }
 
 int rg_conv3x3_img(const void* u, const void* w3, float* img, const float* bias, int B, int Ho, int Wo, int Cin,
                    int Cimg, rg_stream_t st) {
   RG_CHECK_ARG(Cimg >= 1 && Cimg <= 8, "rg_conv3x3_img: 1..8 image channels supported");
-  return conv3_common(u, w3, img, bias, B, Ho, Wo, Cin, Cimg, OUT_F32_NCHW, static_cast<cudaStream_t>(st));
+  return conv3_common(u, w3, img, bias, B, Ho, Wo, Cin, Cimg, OUT_F32_NCHW, nullptr, static_cast<cudaStream_t>(st));
 }
 
 // du[b,y,x,ci] = sum_{kh,kw,co} da[b,y-kh,x-kw,co] * W[co,ci,kh,kw] on the padded (Ho+2)x(Wo+2) grid; the weights
@@ -731,16 +804,17 @@ int rg_conv3x3_dgrad(const void* da, const void* w3, void* du, int B, int Ho, in
       a.taps[0][kh * 3 + kw] = t;
     }
   a.n_total = Cin;
-  a.block_n = std::max(64, pick_block_n(Cin, a.m_tiles));
+  a.block_n = std::max(64, pick_block_n(Cin, a.m_tiles, pair_allowed(a, OUT_BF16_NHWC) ? 2 : 1));
   a.n_tiles = ceil_div(Cin, a.block_n);
   a.b_mn = 1;
   a.b_tap_cols = Cin;
+  const int cg = pick_cg(a, OUT_BF16_NHWC);
   rc = encode_map_2d(&maps.b, w3, 9ull * Cin, Cout, 9ull * Cin, 64, 64);
   if (rc) return rc;
   a.out = du;
   a.OH = Ho + 2; a.OW = Wo + 2; a.OC = Cin;
   a.n_valid = Cin;
-  return launch_fwd(maps, a, OUT_BF16_NHWC, st);
+  return launch_fwd(maps, a, OUT_BF16_NHWC, cg, nullptr, st);
 }
 
 size_t rg_conv3x3_wgrad_ws_bytes(int B, int Ho, int Wo, int Cin, int Cout) {

@@ -104,21 +104,31 @@ __global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int r
     }
   }
 }
-// Stage 2: out[k][c] = sum_blocks partial[block][k][c]; 32 columns x 8 block-lanes per CTA, summed in a fixed order
-__global__ void __launch_bounds__(256) colreduce_stage2(const float* __restrict__ partial, int nblocks, int KC,
-                                                        float* __restrict__ out) {
-  __shared__ float sm[8][33];
+// Stage 2: out[k][c] = sum_blocks partial[block][k][c]; 32 columns x 32 block-lanes per CTA (narrow layers have few
+// columns, so the parallelism has to come from the block dimension), four loads in flight per thread, lanes summed
+// in a fixed order
+__global__ void __launch_bounds__(1024) colreduce_stage2(const float* __restrict__ partial, int nblocks, int KC,
+                                                         float* __restrict__ out) {
+  __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + cx;
-  float s = 0.0f;
-  if (i < KC)
-    for (int b = g; b < nblocks; b += 8) s += partial[static_cast<size_t>(b) * KC + i];
-  sm[g][cx] = s;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  if (i < KC) {
+    int b = g;
+    for (; b + 96 < nblocks; b += 128) {
+      s0 += partial[static_cast<size_t>(b) * KC + i];
+      s1 += partial[static_cast<size_t>(b + 32) * KC + i];
+      s2 += partial[static_cast<size_t>(b + 64) * KC + i];
+      s3 += partial[static_cast<size_t>(b + 96) * KC + i];
+    }
+    for (; b < nblocks; b += 32) s0 += partial[static_cast<size_t>(b) * KC + i];
+  }
+  sm[g][cx] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (g == 0 && i < KC) {
     float t = sm[0][cx];
 #pragma unroll
-    for (int l = 1; l < 8; ++l) t += sm[l][cx];
+    for (int l = 1; l < 32; ++l) t += sm[l][cx];
     out[i] = t;
   }
 }
@@ -131,7 +141,7 @@ static ReducePlan plan_reduce(int M, int C, int K) {
   ReducePlan p;
   const int cgs = C / 8;
   const int lanes = cgs >= 256 ? 1 : 256 / cgs;
-  int target = num_sms() * 6;
+  int target = num_sms() * 4;
   int rpb = std::max(lanes * 8, ceil_div(M, target));
   rpb = ceil_div(rpb, lanes) * lanes;
   p.rows_per_block = rpb;
@@ -166,7 +176,7 @@ static int run_colreduce(F f, int M, int C, float* ws, size_t ws_bytes, float* o
   }
   colreduce_stage1<F><<<p.blocks, 256, p.smem, st>>>(f, M, C, p.rows_per_block, ws);
   RG_LAUNCH_CHECK(name);
-  colreduce_stage2<<<ceil_div(K * C, 32), 256, 0, st>>>(ws, p.blocks, K * C, out);
+  colreduce_stage2<<<ceil_div(K * C, 32), 1024, 0, st>>>(ws, p.blocks, K * C, out);
   RG_LAUNCH_CHECK(name);
   return 0;
 }
@@ -401,6 +411,49 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
   if (c >= C) return;
   const float m = sums[c] * invM;
   const float var = fmaxf(sums[C + c] * invM - m * m, 0.0f);
+  const float r = rsqrtf(var + eps);
+  mean[c] = m;
+  rstd[c] = r;
+  const float sc = gamma[c] * r;
+  scale[c] = sc;
+  shift[c] = beta[c] - m * sc;
+  if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * m;
+  if (running_var) running_var[c] = (1.0f - momentum) * running_var[c] + momentum * var * unbias;
+}
+
+// Same as bn_finalize_kernel, starting from the per-CTA partial sums a convolution epilogue wrote
+// (partial[part][2][C]): 32 channels x 8 part-lanes per block, lanes and then parts summed in a fixed order.
+__global__ void __launch_bounds__(256) bn_finalize_partials_kernel(
+    const float* __restrict__ partial, int nparts, const float* __restrict__ gamma, const float* __restrict__ beta,
+    int C, float invM, float unbias, float eps, float momentum, float* running_mean, float* running_var,
+    long long* nbt, float* sums_out, float* mean, float* rstd, float* scale, float* shift) {
+  __shared__ float sm[2][8][33];
+  const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s0 = 0.0f, s1 = 0.0f;
+  if (c < C) {
+    for (int b = g; b < nparts; b += 8) {
+      s0 += partial[(static_cast<size_t>(b) * 2 + 0) * C + c];
+      s1 += partial[(static_cast<size_t>(b) * 2 + 1) * C + c];
+    }
+  }
+  sm[0][g][cx] = s0;
+  sm[1][g][cx] = s1;
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
+  if (g != 0 || c >= C) return;
+  float t0 = sm[0][0][cx], t1 = sm[1][0][cx];
+#pragma unroll
+  for (int l = 1; l < 8; ++l) {
+    t0 += sm[0][l][cx];
+    t1 += sm[1][l][cx];
+  }
+  if (sums_out) {
+    sums_out[c] = t0;
+    sums_out[C + c] = t1;
+  }
+  const float m = t0 * invM;
+  const float var = fmaxf(t1 * invM - m * m, 0.0f);
   const float r = rsqrtf(var + eps);
   mean[c] = m;
   rstd[c] = r;
@@ -1114,6 +1167,19 @@ int rg_bn_finalize(const float* sums, const float* gamma, const float* beta, int
       sums, gamma, beta, C, 1.0f / M, unbias, eps, momentum, running_mean, running_var,
       reinterpret_cast<long long*>(num_batches_tracked), mean, rstd, scale, shift);
   RG_LAUNCH_CHECK("rg_bn_finalize");
+  return 0;
+}
+
+int rg_bn_finalize_partials(const float* stats_ws, const float* gamma, const float* beta, int M, int C, float eps,
+                            float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                            float* sums_out, float* mean, float* rstd, float* scale, float* shift, rg_stream_t st) {
+  RG_CHECK_ARG(stats_ws && gamma && beta && mean && rstd && scale && shift && M > 0 && C > 0,
+               "rg_bn_finalize_partials: bad arguments");
+  const float unbias = M > 1 ? static_cast<float>(M) / static_cast<float>(M - 1) : 1.0f;
+  bn_finalize_partials_kernel<<<ceil_div(C, 32), 256, 0, static_cast<cudaStream_t>(st)>>>(
+      stats_ws, num_sms(), gamma, beta, C, 1.0f / M, unbias, eps, momentum, running_mean, running_var,
+      reinterpret_cast<long long*>(num_batches_tracked), sums_out, mean, rstd, scale, shift);
+  RG_LAUNCH_CHECK("rg_bn_finalize_partials");
   return 0;
 }
 

@@ -130,6 +130,60 @@ __device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* m, uint64_t* b
       : "memory");
 }
 
+// ---------------------------------------------------------------- TMA stores (shared -> global, bulk async group)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// In a 2-CTA cluster the shared::cluster address of CTA rank r carries r in bit 24: clearing it names the same
+// offset in the even (leader) CTA -- the barrier a paired TMA load must signal.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of one CTA of a pair: data lands in THIS CTA's smem, the bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t* bar, void* smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* m, uint64_t* bar, void* smem, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+      "[%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_ld_2d(const CUtensorMap* m, uint64_t* bar, void* smem, int c0, int c1) {
+  if (CG == 2) tma_load_2d_pair(m, bar, smem, c0, c1);
+  else tma_load_2d(m, bar, smem, c0, c1);
+}
+template <int CG>
+__device__ __forceinline__ void tma_ld_4d(const CUtensorMap* m, uint64_t* bar, void* smem, int c0, int c1, int c2,
+                                          int c3) {
+  if (CG == 2) tma_load_4d_pair(m, bar, smem, c0, c1, c2, c3);
+  else tma_load_4d(m, bar, smem, c0, c1, c2, c3);
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
@@ -195,6 +249,110 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+
+// ---------------------------------------------------------------- raw-address variants for the producer hot loop
+// (32-bit shared addresses and a 64-bit descriptor address kept in registers: no per-iteration conversions)
+__device__ __forceinline__ uint32_t mbar_try_wait_raw(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_raw(uint32_t bar, uint32_t parity) {
+#if RG_HANG_GUARD
+  uint32_t spins = 0;
+  while (!mbar_try_wait_raw(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+#else
+  while (!mbar_try_wait_raw(bar, parity)) {
+  }
+#endif
+}
+__device__ __forceinline__ void mbar_expect_tx_raw(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bar: for CG == 2 the caller passes the LEADER's barrier address (own address & kPeerBitMask)
+template <int CG>
+__device__ __forceinline__ void tma_ld_2d_raw(uint64_t desc, uint32_t bar, uint32_t dst, int c0, int c1) {
+  if (CG == 2)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_ld_4d_raw(uint64_t desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                              int c3) {
+  if (CG == 2)
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+        "[%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// ---------------------------------------------------------------- cta_group-generic tcgen05 wrappers
+template <int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t* smem_dst, uint32_t ncols) {
+  if (CG == 2)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols) : "memory");
+  else
+    tmem_alloc(smem_dst, ncols);
+}
+template <int CG>
+__device__ __forceinline__ void tmem_relinquish_cg() {
+  if (CG == 2) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  else tmem_relinquish();
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t ncols) {
+  if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else tmem_dealloc(taddr, ncols);
+}
+// CG == 2: one instruction drives both SMs of the pair: D rows 0..127 live in the leader's TMEM, 128..255 in the
+// peer's; each CTA supplies its own 128 A rows and its half of the B rows from the same smem offsets.
+template <int CG>
+__device__ __forceinline__ void umma_bf16_cg(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  if (CG == 2) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+  }
+}
+// CG == 2: the arrival is multicast to the barrier at this offset in BOTH CTAs of the pair
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+  if (CG == 2) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+        : "memory");
+  } else {
+    umma_commit(bar);
+  }
 }
 
 // ---------------------------------------------------------------- UMMA descriptors

@@ -14,6 +14,8 @@ Backward uses the same engine with the roles swapped (dgrad of a conv is the tra
 wgrad is rg_conv_wgrad); the gradient penalty's double backward follows SURVEY.md Appendix C and is checked
 against autograd in tests/test_gp_math_cpu.py.  Activations are bf16 NHWC, parameters/gradients/statistics fp32.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -23,6 +25,8 @@ from .parallel import GradSync
 BF16 = torch.bfloat16
 F32 = torch.float32
 SLOPE = 0.2
+# BatchNorm batch statistics accumulated in the epilogue of the producing convolution (RG_FUSED_STATS=0: separate pass)
+FUSED_STATS = os.environ.get("RG_FUSED_STATS", "1") != "0"
 
 
 def _grad_of(p):
@@ -73,9 +77,18 @@ class _BN:
             self._states[tag] = s
         return s
 
-    def forward(self, a, h, M, training=True, tag=""):
+    def stats_ws(self, training=True):
+        """Scratch for the statistics the producing convolution accumulates in its epilogue (None: separate pass)."""
+        if not training or self.C % 64 != 0 or not FUSED_STATS:
+            return None
+        return ops.stats_ws(self.C, self.device)
+
+    def forward(self, a, h, M, training=True, tag="", stats=None):
         m, s = self.mod, self.st(tag)
-        if training:
+        if training and stats is not None:
+            ops.bn_finalize_partials(stats, m.weight, m.bias, M, self.C, m.eps, m.momentum, m.running_mean,
+                                     m.running_var, m.num_batches_tracked, s.sums, s.mean, s.rstd, s.scale, s.shift)
+        elif training:
             ops.bn_stats(a, M, self.C, s.sums)
             ops.bn_finalize(s.sums, m.weight, m.bias, M, self.C, m.eps, m.momentum, m.running_mean, m.running_var,
                             m.num_batches_tracked, s.mean, s.rstd, s.scale, s.shift)
@@ -171,10 +184,12 @@ class GeneratorEngine:
         for l, (c, bn) in enumerate(zip(self.convs, self.bns), start=1):
             Cs = c.weight.shape[1]
             a = g(f"{tag}.a{l}", (B, 2 * H, 2 * H, Cs))
-            ops.conv_up(h, self.w_upk[l - 1] if self.w_upk[l - 1] is not None else self.w_down[l - 1], Cs, out=a)
+            sws = bn.stats_ws(training)
+            ops.conv_up(h, self.w_upk[l - 1] if self.w_upk[l - 1] is not None else self.w_down[l - 1], Cs, out=a,
+                        stats=sws)
             H *= 2
             h = g(f"{tag}.h{l}", (B, H, H, Cs))
-            bn.forward(a, h, B * H * H, training, tag=tag)
+            bn.forward(a, h, B * H * H, training, tag=tag, stats=sws)
         if out is None:
             out = g(f"{tag}.img", (B, self.Cimg, 2 * H, 2 * H), F32)
         col = g("fwd.colimg", (B * H * H, 16 * self.Cimg), F32)
@@ -278,9 +293,10 @@ class UpGeneratorEngine:
             ops.upsample2x_reflectpad(h, u)
             H *= 2
             a = g(f"{tag}.a{l}", (B, H, H, Cout))
-            ops.conv3x3(u, self.w3[l - 1], a, bias=c.bias.detach())
+            sws = bn.stats_ws(training)
+            ops.conv3x3(u, self.w3[l - 1], a, bias=c.bias.detach(), stats=sws)
             h = g(f"{tag}.h{l}", (B, H, H, Cout))
-            bn.forward(a, h, B * H * H, training, tag=tag)
+            bn.forward(a, h, B * H * H, training, tag=tag, stats=sws)
         u = g(f"{tag}.ulast", (B, 2 * H + 2, 2 * H + 2, self.Cn))
         ops.upsample2x_reflectpad(h, u)
         if out is None:
@@ -397,9 +413,10 @@ class CriticEngine:
             Cp = c.weight.shape[0]
             H //= 2
             a = g(f"{tag}.a{l}", (B, H, H, Cp))
-            ops.conv_down(h, self.w_down[l - 1], out=a)
+            sws = bn.stats_ws(training)
+            ops.conv_down(h, self.w_down[l - 1], out=a, stats=sws)
             h = g(f"{tag}.h{l}", (B, H, H, Cp))
-            bn.forward(a, h, B * H * H, training, tag=tag)
+            bn.forward(a, h, B * H * H, training, tag=tag, stats=sws)
         a6 = g(f"{tag}.a6", (B,), F32)
         out = g(f"{tag}.out", (B,), F32)
         ops.head_fwd(h, self.w_head, B, 16 * self.Cn, SLOPE, a6, out)

@@ -106,8 +106,21 @@ def cast_pad_bf16(src, cols_pad=None, out=None):
 
 
 # ------------------------------------------------------------------------------------------------ contractions
-def conv_down(hi, w_down, out=None):
-    """hi bf16 [B, 2H, 2W, Cs], w_down bf16 [Cp, 16*Cs] -> lo bf16 [B, H, W, Cp]."""
+_stats_cache = {}
+
+
+def stats_ws(C, device, slot=0):
+    """fp32 [parts, 2, C] scratch a convolution epilogue fills with per-CTA channel sums / sums of squares."""
+    key = (device.index, C, slot)
+    t = _stats_cache.get(key)
+    if t is None:
+        t = torch.zeros(_lib.lib().rg_stats_parts(), 2, C, dtype=torch.float32, device=device)
+        _stats_cache[key] = t
+    return t
+
+
+def conv_down(hi, w_down, out=None, stats=None):
+    """hi bf16 [B, 2H, 2W, Cs], w_down bf16 [Cp, 16*Cs] -> lo bf16 [B, H, W, Cp] (+ fused BN statistics)."""
     _chk(hi, BF16, "hi"); _chk(w_down, BF16, "w_down")
     B, H2, W2, Cs = hi.shape
     Cp = w_down.shape[0]
@@ -115,11 +128,11 @@ def conv_down(hi, w_down, out=None):
     if out is None:
         out = torch.empty(B, H, W, Cp, dtype=BF16, device=hi.device)
     _prof("conv_down", 2.0 * B * H * W * Cp * 16 * Cs, lambda: _lib.check(
-        _lib.lib().rg_conv_down(_p(hi), _p(w_down), _p(out), B, H, W, Cs, Cp, _st()), "rg_conv_down"))
+        _lib.lib().rg_conv_down(_p(hi), _p(w_down), _p(out), B, H, W, Cs, Cp, _p(stats), _st()), "rg_conv_down"))
     return out
 
 
-def conv_up(lo, w, Cs, out=None):
+def conv_up(lo, w, Cs, out=None, stats=None):
     """lo bf16 [B, H, W, Cp] -> hi bf16 [B, 2H, 2W, Cs].  w: w_down bf16 [Cp, 16*Cs] (2-D; read MN-major) or
     w_up bf16 [4, Cs_pad, 4*Cp] (3-D; K-major)."""
     _chk(lo, BF16, "lo"); _chk(w, BF16, "w")
@@ -127,7 +140,8 @@ def conv_up(lo, w, Cs, out=None):
     if out is None:
         out = torch.empty(B, 2 * H, 2 * W, Cs, dtype=BF16, device=lo.device)
     _prof("conv_up", 2.0 * B * H * W * Cp * 16 * Cs, lambda: _lib.check(
-        _lib.lib().rg_conv_up(_p(lo), _p(w), int(w.dim() == 2), _p(out), B, H, W, Cp, Cs, _st()), "rg_conv_up"))
+        _lib.lib().rg_conv_up(_p(lo), _p(w), int(w.dim() == 2), _p(out), B, H, W, Cp, Cs, _p(stats), _st()),
+        "rg_conv_up"))
     return out
 
 
@@ -235,6 +249,12 @@ def bn_finalize(sums, gamma, beta, M, C, eps, momentum, rmean, rvar, nbt, mean, 
     _lib.check(_lib.lib().rg_bn_finalize(_p(sums), _p(gamma), _p(beta), M, C, float(eps), float(momentum), _p(rmean),
                                          _p(rvar), _p(nbt), _p(mean), _p(rstd), _p(scale), _p(shift), _st()),
                "rg_bn_finalize")
+
+
+def bn_finalize_partials(stats, gamma, beta, M, C, eps, momentum, rmean, rvar, nbt, sums, mean, rstd, scale, shift):
+    _lib.check(_lib.lib().rg_bn_finalize_partials(_p(stats), _p(gamma), _p(beta), M, C, float(eps), float(momentum),
+                                                  _p(rmean), _p(rvar), _p(nbt), _p(sums), _p(mean), _p(rstd),
+                                                  _p(scale), _p(shift), _st()), "rg_bn_finalize_partials")
 
 
 def bn_act(a, scale, shift, slope, h, M, C):
@@ -450,7 +470,7 @@ def pack_conv3(W, out):
     return out
 
 
-def conv3x3(u, w3, out, bias=None):
+def conv3x3(u, w3, out, bias=None, stats=None):
     """u bf16 [B, Ho+2, Wo+2, Cin] -> out bf16 NHWC [B, Ho, Wo, Cout] or fp32 NCHW [B, Cimg, Ho, Wo]."""
     B, Hp, Wp, Cin = u.shape
     Ho, Wo = Hp - 2, Wp - 2
@@ -461,7 +481,8 @@ def conv3x3(u, w3, out, bias=None):
     else:
         Cout = out.shape[3]
         _prof("conv3x3", 2.0 * B * Ho * Wo * Cout * 9 * Cin, lambda: _lib.check(
-            _lib.lib().rg_conv3x3(_p(u), _p(w3), _p(out), _p(bias), B, Ho, Wo, Cin, Cout, _st()), "rg_conv3x3"))
+            _lib.lib().rg_conv3x3(_p(u), _p(w3), _p(out), _p(bias), B, Ho, Wo, Cin, Cout, _p(stats), _st()),
+            "rg_conv3x3"))
     return out
 
 

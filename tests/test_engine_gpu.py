@@ -222,3 +222,61 @@ def test_gemm_nn_and_ragged_k(cuda_dev, M, N, K):
     dW = ops.gemm_tn(dY, A.to(cuda_dev).to(torch.bfloat16), N=K)
     assert dW.shape == (200, K)
     assert _rel(dW, dY.float().t() @ A[:, :K].to(cuda_dev)) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cs,Cp", [(16, 16, 16, 256, 512), (4, 64, 64, 64, 128), (3, 8, 8, 64, 128),
+                                         (8, 4, 4, 128, 64), (5, 16, 16, 128, 256)])
+def test_conv_fused_stats(cuda_dev, B, H, W, Cs, Cp):
+    """The per-CTA channel sums / sums of squares a convolution epilogue leaves in stats_ws (BatchNorm batch
+    statistics without a second pass) equal the sums over the stored bf16 output; odd tile counts and batches that
+    do not fill a tile included.  Also checks the output itself on these shapes (CTA-pair path with an odd M tail)."""
+    from rnagan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B + H + Cs + Cp + 5)
+    Wt = _bf(torch.randn(Cp, Cs, 4, 4, generator=g) * 0.05).to(cuda_dev)
+    w_down, w_up = ops.pack_link(Wt)
+    # down
+    x = _bf(torch.randn(B, Cs, 2 * H, 2 * W, generator=g)).to(cuda_dev)
+    ws = ops.stats_ws(Cp, cuda_dev, slot=7)
+    ws.fill_(float("nan"))          # every row must be (re)written
+    out = ops.conv_down(_nhwc(x), w_down, stats=ws)
+    assert _rel(_nchw(out), F.conv2d(x, Wt, stride=2, padding=1)) < 8e-3
+    o = out.float().view(-1, Cp)
+    got = ws.sum(0)
+    assert _rel(got[0], o.sum(0)) < 1e-4 and _rel(got[1], (o * o).sum(0)) < 1e-4
+    # up (both weight layouts)
+    y = _bf(torch.randn(B, Cp, H, W, generator=g)).to(cuda_dev)
+    ws2 = ops.stats_ws(Cs, cuda_dev, slot=7)
+    for w in (w_down, w_up):
+        ws2.fill_(float("nan"))
+        out = ops.conv_up(_nhwc(y), w, Cs, stats=ws2)
+        assert _rel(_nchw(out), F.conv_transpose2d(y, Wt, stride=2, padding=1)) < 8e-3
+        o = out.float().view(-1, Cs)
+        got = ws2.sum(0)
+        assert _rel(got[0], o.sum(0)) < 1e-4 and _rel(got[1], (o * o).sum(0)) < 1e-4
+
+
+def test_bn_finalize_partials(cuda_dev):
+    from rnagan_b200 import ops
+    C, M = 128, 4096
+    g = torch.Generator(device="cpu").manual_seed(3)
+    a = (torch.randn(M, C, generator=g) * 2 + 0.5).to(torch.bfloat16).to(cuda_dev)
+    parts = ops.stats_ws(C, cuda_dev, slot=8)
+    P = parts.shape[0]
+    af = a.float()
+    with torch.no_grad():
+        rows = torch.arange(M, device=cuda_dev) % P
+        parts.zero_()
+        parts[:, 0].index_add_(0, rows, af)
+        parts[:, 1].index_add_(0, rows, af * af)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(cuda_dev)
+    beta = torch.randn(C, generator=g).to(cuda_dev)
+    rm, rv = torch.zeros(C, device=cuda_dev), torch.ones(C, device=cuda_dev)
+    nbt = torch.zeros((), dtype=torch.int64, device=cuda_dev)
+    f = lambda *s: torch.zeros(*s, device=cuda_dev)
+    sums, mean, rstd, scale, shift = f(2, C), f(C), f(C), f(C), f(C)
+    ops.bn_finalize_partials(parts, gamma, beta, M, C, 1e-5, 0.1, rm, rv, nbt, sums, mean, rstd, scale, shift)
+    m_ref, v_ref = af.mean(0), af.var(0, unbiased=False)
+    assert _rel(mean, m_ref) < 1e-4 and _rel(rstd, (v_ref + 1e-5).rsqrt()) < 1e-3
+    assert _rel(scale, gamma * (v_ref + 1e-5).rsqrt()) < 1e-3
+    assert _rel(rm, 0.1 * m_ref) < 1e-4 and _rel(rv, 0.9 + 0.1 * af.var(0, unbiased=True)) < 1e-3
+    assert int(nbt.item()) == 1 and _rel(sums[0], af.sum(0)) < 1e-4

@@ -52,7 +52,9 @@ def main(filt=""):
         if filt in f"down {name}":
             report(f"conv_down {name} {Cs}->{Cp} @{h}", timeit(lambda: ops.conv_down(hi, wd, out=out_lo)), fl, by)
         if filt in f"up {name}":
-            report(f"conv_up   {name} {Cp}->{Cs} @{h}", timeit(lambda: ops.conv_up(lo, wd, Cs, out=out_hi)), fl, by)
+            report(f"conv_up   {name} {Cp}->{Cs} @{h} (w_down, MN-major B)", timeit(lambda: ops.conv_up(lo, wd, Cs, out=out_hi)), fl, by)
+            if Cs <= 128:
+                report(f"conv_up   {name} {Cp}->{Cs} @{h} (w_up, K-major B)", timeit(lambda: ops.conv_up(lo, wu, Cs, out=out_hi)), fl, by)
         if filt in f"wgrad {name}":
             report(f"conv_wgrad {name}", timeit(lambda: ops.conv_wgrad(lo, hi, dW)), fl, by + W.numel() * 2)
     # image-side / projection GEMMs
