@@ -53,6 +53,8 @@ int rg_pack_link(const float* W, void* w_down, void* w_up, int Cp, int Cs, rg_st
 /* generator layer 0, nn.ConvTranspose2d(E, C0, 4, 1, 0) weight [E][C0][4][4] (src/dcgan.py:38-40)
  * -> bf16 [16*C0][E]  (row = tap*C0 + co), the B operand of rg_gemm_nt. */
 int rg_pack_proj(const float* W, void* w_proj, int E, int C0, rg_stream_t st);
+/* bf16 w_down[Cp][16*Cs] -> bf16 w_up[4][Cs_pad][4*Cp] (the K-major copy narrow layers keep for rg_conv_up) */
+int rg_pack_up_from_down(const void* w_down, void* w_up, int Cp, int Cs, rg_stream_t st);
 /* image-side (3-channel) link, K padded to 64: bf16 w_col[Cp][64], k = (kh*4+kw)*4 + c. */
 int rg_pack_edge(const float* W, void* w_col, int Cp, int Cimg, rg_stream_t st);
 /* fp32 [rows][cols] -> bf16 [rows][cols_pad] (zero padded), nn.Linear weights (src/betaVAE.py:31,76). */
@@ -80,15 +82,18 @@ int rg_conv_up(const void* lo, const void* w, int w_is_down, void* hi, int B, in
  * (generator last layer, src/dcgan.py:82; critic layer-0 dgrad). */
 int rg_conv_up_img(const void* lo, const void* w_up, float* img, const float* bias, int act_tanh, int B, int H,
                    int W, int Cp, int Cimg, rg_stream_t st);
-/* dW[p,s,kh,kw] = beta*dW + alpha*(*alpha_dev)*sum_{b,i,j} lo[b,i,j,p] * hi[b,2i-1+kh,2j-1+kw,s]  (fp32, torch layout)
- * autograd wgrad of both conv kinds.  ws: fp32 scratch of at least rg_conv_wgrad_ws_bytes(). alpha_dev may be NULL. */
+/* dW[p,s,kh,kw] = beta*dW + alpha*(*alpha_dev)*sum_{b,i,j} lo[b,i,j,p] * hi[b,2i-1+kh,2j-1+kw,s]  (fp32)
+ * autograd wgrad of both conv kinds.  ws: fp32 scratch of at least rg_conv_wgrad_ws_bytes(). alpha_dev may be NULL.
+ * native_layout = 0: dW is a contiguous torch tensor [Cp][Cs][4][4]; 1: dW is the physical memory of a
+ * torch.channels_last tensor of that shape, i.e. [Cp][kh][kw][Cs] -- the engine's own layout (one coalesced store per
+ * accumulator row, no split-K scratch when the pixel count fits one unit, and the same element order as w_down). */
 size_t rg_conv_wgrad_ws_bytes(int B, int H, int W, int Cp, int Cs);
 int rg_conv_wgrad(const void* lo, const void* hi, float* dW, void* ws, size_t ws_bytes, int B, int H, int W, int Cp,
-                  int Cs, float alpha, const float* alpha_dev, float beta, rg_stream_t st);
+                  int Cs, float alpha, const float* alpha_dev, float beta, int native_layout, rg_stream_t st);
 /* generator layer 0 wgrad: dW[e,c,kh,kw] = sum_b z[b,e] * da0[b,kh,kw,c]. */
 size_t rg_proj_wgrad_ws_bytes(int B, int E, int C0);
 int rg_proj_wgrad(const void* z, const void* da0, float* dW, void* ws, size_t ws_bytes, int B, int E, int C0,
-                  float alpha, const float* alpha_dev, float beta, rg_stream_t st);
+                  float alpha, const float* alpha_dev, float beta, int native_layout, rg_stream_t st);
 /* C[M,N] = act((A[M,K] . Bw[N,K]^T) * col_scale + col_shift); A, Bw bf16 row-major (K multiple of 64), C bf16 or
  * fp32 with leading dimension ldc.  nn.Linear(+eval BatchNorm1d+LeakyReLU) of the encoder (src/betaVAE.py:29-36),
  * generator layer 0 (src/dcgan.py:38-40), image-side im2col GEMMs. */
@@ -182,8 +187,12 @@ int rg_gp_norm(const float* g, size_t n, float lambd, float* partial_ws, int par
  * with the optional WGAN weight clamp (src/wgan_loss.py:213-215) fused in.  rg_adam_build_table fills a HOST table
  * and returns the number of chunks (>0); copy it to the device and pass it to rg_adam_step. */
 int rg_adam_table_bytes(int num_chunks);
-int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms, void* const* vs, const int64_t* sizes,
-                        int num_tensors, int chunk_elems, void* table_host, int max_chunks);
+/* shadows (may be NULL, entries may be NULL): per tensor a bf16 buffer of the same element count that receives the
+ * updated parameters in the same element order -- for a channels_last conv weight that IS the packed w_down operand,
+ * so the optimiser step re-emits the GEMM operands and no pack kernel runs afterwards. */
+int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms, void* const* vs,
+                        void* const* shadows, const int64_t* sizes, int num_tensors, int chunk_elems, void* table_host,
+                        int max_chunks);
 /* grad_scale multiplies every gradient first (1/world_size after a SUM all-reduce; 1.0 otherwise) */
 int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, float beta2, float eps, int step,
                  int do_clamp, float clamp_lo, float clamp_hi, float grad_scale, rg_stream_t st);

@@ -25,6 +25,7 @@ SIGNATURES = {
     "rg_debug_set_prof": (None, [_vp]),
     "rg_pack_link": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "rg_pack_proj": (_i, [_vp, _vp, _i, _i, _vp]),
+    "rg_pack_up_from_down": (_i, [_vp, _vp, _i, _i, _vp]),
     "rg_pack_edge": (_i, [_vp, _vp, _i, _i, _vp]),
     "rg_cast_pad_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rg_stats_ws_bytes": (_sz, [_i]),
@@ -33,9 +34,9 @@ SIGNATURES = {
     "rg_conv_up": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rg_conv_up_img": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rg_conv_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "rg_conv_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _f, _vp, _f, _vp]),
+    "rg_conv_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _f, _vp, _f, _i, _vp]),
     "rg_proj_wgrad_ws_bytes": (_sz, [_i, _i, _i]),
-    "rg_proj_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp, _f, _vp]),
+    "rg_proj_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp, _f, _i, _vp]),
     "rg_gemm_nt": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp]),
     "rg_gemm_nt_ld": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp]),
     "rg_gemm_nn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp]),
@@ -67,7 +68,7 @@ SIGNATURES = {
     "rg_wgan_loss": (_i, [_vp, _f, _vp, _f, _i, _vp, _vp]),
     "rg_gp_norm": (_i, [_vp, _sz, _f, _vp, _i, _vp, _vp]),
     "rg_adam_table_bytes": (_i, [_i]),
-    "rg_adam_build_table": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i]),
+    "rg_adam_build_table": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i]),
     "rg_adam_step": (_i, [_vp, _i, _f, _f, _f, _f, _i, _i, _f, _f, _f, _vp]),
     "rg_clamp": (_i, [_vp, _sz, _f, _f, _vp]),
     "rg_tiles_to_unit_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),

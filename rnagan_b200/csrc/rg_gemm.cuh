@@ -96,6 +96,9 @@ struct WgradArgs {
   float* ws;           // [splits][num_taps][Cp][Cs] fp32 partials
   // splits == 1 with 16 taps: the epilogue writes the torch layout dW[p][s][kh][kw] directly (no partials, no reduce)
   float* direct_out;
+  // splits == 1: the epilogue writes the NATIVE layout dW[p][tap][s] (= a channels_last [Cp][Cs][kh][kw] tensor): each
+  // thread stores whole 128-byte lines, beta/alpha applied in place, no partials and no reduce pass
+  float* native_out;
   const float* alpha_dev;
   float alpha, beta;
   int msub;            // 128-row accumulators per unit: 1, or 2 (256-row M tile sharing every B slab)
@@ -778,7 +781,36 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
         const int prow = (m_tile * msub + ms) * 128 + row;
         const bool row_ok = prow < p.Cp;
         const uint32_t taddr = tmem_base + (acc + ms) * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-        if (p.direct_out != nullptr) {
+        if (p.native_out != nullptr) {
+          const float a = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
+          const float beta = p.beta;
+          for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
+            int tap, chunk;
+            wgrad_slab(p, n_tile, sl, tap, chunk);
+            float* o = p.native_out + (static_cast<size_t>(prow) * p.num_taps + tap) * p.Cs + chunk * 64;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t v[32];
+              tmem_ld_32x32(taddr + sl * 64 + h * 32, v);
+              tmem_ld_wait();
+              if (row_ok) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  if (chunk * 64 + h * 32 + g * 4 + 4 <= p.Cs) {
+                    float4 f = make_float4(a * __uint_as_float(v[g * 4 + 0]), a * __uint_as_float(v[g * 4 + 1]),
+                                           a * __uint_as_float(v[g * 4 + 2]), a * __uint_as_float(v[g * 4 + 3]));
+                    float4* dst = reinterpret_cast<float4*>(o + h * 32 + g * 4);
+                    if (beta != 0.0f) {
+                      const float4 old = *dst;
+                      f.x += beta * old.x; f.y += beta * old.y; f.z += beta * old.z; f.w += beta * old.w;
+                    }
+                    *dst = f;
+                  }
+                }
+              }
+            }
+          }
+        } else if (p.direct_out != nullptr) {
           // direct write: dW[p][s][kh][kw] = beta*dW + alpha * acc; this tile = (kh, chunk), slabs = kw 0..3
           const int chunk = n_tile >> 2, kh = n_tile & 3;
           const float a = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);

@@ -317,6 +317,35 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// ws: [splits][taps][Cp][Cs] partials -> NATIVE dW[p][tap][s] (channels_last weight gradient): float4 in, float4 out
+__global__ void __launch_bounds__(256) wgrad_reduce_native_kernel(const float* __restrict__ ws, float* __restrict__ dW,
+                                                                  int splits, int taps, int Cp, int Cs, float alpha,
+                                                                  const float* __restrict__ alpha_dev, float beta) {
+  const int cs4 = Cs >> 2;
+  const size_t n4 = static_cast<size_t>(taps) * Cp * cs4;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // over [p][tap][s4]
+  if (idx >= n4) return;
+  const int s4 = static_cast<int>(idx % cs4);
+  const size_t r = idx / cs4;
+  const int tap = static_cast<int>(r % taps);
+  const int prow = static_cast<int>(r / taps);
+  const float a = alpha * (alpha_dev ? __ldg(alpha_dev) : 1.0f);
+  const size_t plane = static_cast<size_t>(Cp) * Cs;
+  const float* src = ws + (static_cast<size_t>(tap) * Cp + prow) * Cs + s4 * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sp = 0; sp < splits; ++sp) {
+    const float4 v = *reinterpret_cast<const float4*>(src + static_cast<size_t>(sp) * taps * plane);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float4* dst = reinterpret_cast<float4*>(dW) + idx;
+  float4 o = make_float4(a * acc.x, a * acc.y, a * acc.z, a * acc.w);
+  if (beta != 0.0f) {
+    const float4 old = *dst;
+    o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w;
+  }
+  *dst = o;
+}
+
 // Split-K factor: minimise waves x (k-blocks per unit + per-unit epilogue cost); favours unit counts that fill whole
 // waves of the persistent grid (e.g. 64 tiles x 9 splits = 576 units = 3.9 waves instead of 192 = 1.3 waves).
 static void choose_splits(int units, int num_pb, int& splits, int& pb_per_split) {
@@ -357,16 +386,22 @@ static WgradGeom wgrad_geom(int B, int H, int W, int Cp, int Cs, int taps) {
 
 static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* taps, int B, int H, int W, int Cp, int Cs,
                         float* dW, void* ws, size_t ws_bytes, float alpha, const float* alpha_dev, float beta,
-                        cudaStream_t st, int Cs_out = -1) {
+                        cudaStream_t st, int Cs_out = -1, bool native = false) {
   if (Cs_out < 0) Cs_out = Cs;
+  if (native && (Cs_out != Cs || Cs % 4 != 0)) {
+    set_error("native weight-gradient layout needs Cs %% 4 == 0 and no column padding (Cs=%d)", Cs);
+    return RG_EINVAL;
+  }
   int rc = ensure_attrs();
   if (rc) return rc;
   // measured on B200: inside the full training step the direct epilogue LOSES ~1.2 ms/step to the split-K + reduce
   // path (16-byte read-modify-write pieces at a 64-byte stride when accumulating), so it is opt-in for experiments
   static const bool allow_direct = [] { const char* e = getenv("RG_WGRAD_DIRECT"); return e && e[0] == '1'; }();
   // direct 16-byte stores at a 64-byte stride pay off while dW stays L2-sized; the 268 MB projection gradient does not
-  const bool direct = allow_direct && (w.splits == 1 && w.taps == 16 && w.slabs_per_tile == 4 && Cs_out == Cs) &&
-                      static_cast<size_t>(Cp) * Cs * 64 <= (160u << 20);
+  const bool native_direct = native && w.splits == 1;
+  const bool direct = native_direct ||
+                      (!native && allow_direct && (w.splits == 1 && w.taps == 16 && w.slabs_per_tile == 4 && Cs_out == Cs) &&
+                       static_cast<size_t>(Cp) * Cs * 64 <= (160u << 20));
   const size_t need = static_cast<size_t>(w.splits) * w.taps * Cp * Cs * sizeof(float);
   if (!direct && (ws_bytes < need || ws == nullptr)) {
     set_error("wgrad workspace too small: need %zu bytes, have %zu", need, ws_bytes);
@@ -384,7 +419,8 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
   a.ws = static_cast<float*>(ws);
   a.msub = w.msub;
   if (direct) {
-    a.direct_out = dW;
+    if (native_direct) a.native_out = dW;
+    else a.direct_out = dW;
     a.alpha = alpha;
     a.alpha_dev = alpha_dev;
     a.beta = beta;
@@ -394,6 +430,13 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
   gemm_wgrad_kernel<<<grid, kGemmThreads, kWgradSmemBytes, st>>>(maps, a);
   RG_LAUNCH_CHECK("gemm_wgrad_kernel");
   if (direct) return 0;
+  if (native) {
+    const size_t n4 = static_cast<size_t>(w.taps) * Cp * (Cs / 4);
+    wgrad_reduce_native_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(a.ws, dW, w.splits, w.taps, Cp,
+                                                                                         Cs, alpha, alpha_dev, beta);
+    RG_LAUNCH_CHECK("wgrad_reduce_native_kernel");
+    return 0;
+  }
   const size_t n = static_cast<size_t>(Cp) * Cs_out;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   if (w.taps == 16)
@@ -447,6 +490,29 @@ __global__ void pack_up_kernel(const float* __restrict__ W, __nv_bfloat16* __res
     const int phase = rh * 2 + rw, t = th * 2 + tw;
     out[(static_cast<size_t>(phase) * Cs_pad + s0 + sl) * (4 * static_cast<size_t>(Cp)) + static_cast<size_t>(t) * Cp + p0 + pl] =
         __float2bfloat16(sm[pl][sl * 16 + tap16]);
+  }
+}
+// w_down[p][tap16*Cs + s] bf16 -> w_up[phase][s][t*Cp + p] bf16: per kernel position a [p][s] -> [s][p] transpose.
+// grid (ceil(Cs/32), ceil(Cp/32), 16), block 256.
+__global__ void pack_up_from_down_kernel(const __nv_bfloat16* __restrict__ wd, __nv_bfloat16* __restrict__ out, int Cp,
+                                         int Cs, int Cs_pad) {
+  __shared__ __nv_bfloat16 sm[32][34];
+  const int tap16 = blockIdx.z;
+  const int p0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (p0 + r < Cp && s0 + tx < Cs)
+      sm[r][tx] = wd[static_cast<size_t>(p0 + r) * 16 * Cs + static_cast<size_t>(tap16) * Cs + s0 + tx];
+  __syncthreads();
+  const int kh = tap16 >> 2, kw = tap16 & 3;
+  const int rh = (kh == 1 || kh == 3) ? 0 : 1, th = (kh == 1 || kh == 2) ? 0 : 1;
+  const int rw = (kw == 1 || kw == 3) ? 0 : 1, tw = (kw == 1 || kw == 2) ? 0 : 1;
+  const int phase = rh * 2 + rw, t = th * 2 + tw;
+  for (int r = ty; r < 32; r += 8) {
+    const int sidx = s0 + r;
+    if (sidx < Cs && p0 + tx < Cp)
+      out[(static_cast<size_t>(phase) * Cs_pad + sidx) * (4 * static_cast<size_t>(Cp)) + static_cast<size_t>(t) * Cp + p0 + tx] =
+          sm[tx][r];
   }
 }
 // W[E][C0*16] fp32 -> out[(tap*C0 + co)][E] bf16 : 32x32 tile transpose
@@ -535,6 +601,17 @@ int rg_pack_link(const float* W, void* w_down, void* w_up, int Cp, int Cs, rg_st
     pack_up_kernel<<<grid, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(w_up), Cp, Cs, Cs_pad);
     RG_LAUNCH_CHECK("pack_up_kernel");
   }
+  return 0;
+}
+
+int rg_pack_up_from_down(const void* w_down, void* w_up, int Cp, int Cs, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(w_down && w_up && Cp > 0 && Cs > 0, "rg_pack_up_from_down: bad arguments");
+  const int Cs_pad = std::max(16, (Cs + 15) / 16 * 16);
+  dim3 grid(ceil_div(Cs, 32), ceil_div(Cp, 32), 16);
+  pack_up_from_down_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(w_down),
+                                                 static_cast<__nv_bfloat16*>(w_up), Cp, Cs, Cs_pad);
+  RG_LAUNCH_CHECK("pack_up_from_down_kernel");
   return 0;
 }
 
@@ -866,7 +943,7 @@ size_t rg_conv_wgrad_ws_bytes(int B, int H, int W, int Cp, int Cs) {
 }
 
 int rg_conv_wgrad(const void* lo, const void* hi, float* dW, void* ws, size_t ws_bytes, int B, int H, int W, int Cp,
-                  int Cs, float alpha, const float* alpha_dev, float beta, rg_stream_t st_) {
+                  int Cs, float alpha, const float* alpha_dev, float beta, int native_layout, rg_stream_t st_) {
   cudaStream_t st = static_cast<cudaStream_t>(st_);
   RG_CHECK_ARG(lo && hi && dW, "rg_conv_wgrad: null pointer");
   RG_CHECK_ARG(B > 0 && is_pow2(H) && is_pow2(W), "rg_conv_wgrad: H, W must be powers of two (got %d x %d)", H, W);
@@ -887,7 +964,8 @@ int rg_conv_wgrad(const void* lo, const void* hi, float* dW, void* ws, size_t ws
       t.wtap = static_cast<int8_t>(kh * 4 + kw);
       taps[kh * 4 + kw] = t;
     }
-  return launch_wgrad(maps, w, taps, B, H, W, Cp, Cs, dW, ws, ws_bytes, alpha, alpha_dev, beta, st);
+  return launch_wgrad(maps, w, taps, B, H, W, Cp, Cs, dW, ws, ws_bytes, alpha, alpha_dev, beta, st, -1,
+                      native_layout != 0);
 }
 
 size_t rg_proj_wgrad_ws_bytes(int B, int E, int C0) {
@@ -897,7 +975,7 @@ size_t rg_proj_wgrad_ws_bytes(int B, int E, int C0) {
 }
 
 int rg_proj_wgrad(const void* z, const void* da0, float* dW, void* ws, size_t ws_bytes, int B, int E, int C0,
-                  float alpha, const float* alpha_dev, float beta, rg_stream_t st_) {
+                  float alpha, const float* alpha_dev, float beta, int native_layout, rg_stream_t st_) {
   cudaStream_t st = static_cast<cudaStream_t>(st_);
   RG_CHECK_ARG(z && da0 && dW, "rg_proj_wgrad: null pointer");
   RG_CHECK_ARG(B > 0 && E % 8 == 0 && C0 % 64 == 0, "rg_proj_wgrad: need E %% 8 == 0, C0 %% 64 == 0 (E=%d C0=%d)", E, C0);
@@ -915,7 +993,8 @@ int rg_proj_wgrad(const void* z, const void* da0, float* dW, void* ws, size_t ws
       Tap t = {0, static_cast<int8_t>(kh), static_cast<int8_t>(kw), 0};
       taps[kh * 4 + kw] = t;
     }
-  return launch_wgrad(maps, w, taps, B, 1, 1, E, C0, dW, ws, ws_bytes, alpha, alpha_dev, beta, st);
+  return launch_wgrad(maps, w, taps, B, 1, 1, E, C0, dW, ws, ws_bytes, alpha, alpha_dev, beta, st, -1,
+                      native_layout != 0);
 }
 
 size_t rg_gemm_tn_ws_bytes(int R, int M, int N) {

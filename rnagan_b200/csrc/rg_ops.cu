@@ -782,6 +782,8 @@ struct AdamChunk {
   const float* g;
   float* m;
   float* v;
+  __nv_bfloat16* shadow;   // optional bf16 copy of the updated parameters in the same element order (the packed GEMM
+                           // operand of a channels_last weight): the optimiser step re-emits it, no pack kernel
   int n;
 };
 // torch.optim.Adam (no amsgrad, no weight decay), src/histopathology_gan.py:252,257:
@@ -798,6 +800,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
   const float4* g4 = reinterpret_cast<const float4*>(ch.g);
   float4* m4 = reinterpret_cast<float4*>(ch.m);
   float4* v4 = reinterpret_cast<float4*>(ch.v);
+  uint2* s4 = (ch.shadow != nullptr && (reinterpret_cast<uintptr_t>(ch.shadow) & 7) == 0)
+                  ? reinterpret_cast<uint2*>(ch.shadow) : nullptr;
   for (int i = threadIdx.x; i < n4; i += blockDim.x) {
     float4 p = p4[i], m = m4[i], v = v4[i];
     float4 g = g4[i];
@@ -815,7 +819,10 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
       pp[e] = q;
     }
     p4[i] = p; m4[i] = m; v4[i] = v;
+    if (s4) s4[i] = make_uint2(pack_bf16x2_ops(p.x, p.y), pack_bf16x2_ops(p.z, p.w));
   }
+  if (ch.shadow != nullptr && s4 == nullptr)
+    for (int i = threadIdx.x; i < n4 * 4; i += blockDim.x) ch.shadow[i] = __float2bfloat16(ch.p[i]);
   for (int i = n4 * 4 + threadIdx.x; i < ch.n; i += blockDim.x) {
     const float g = ch.g[i] * gscale;
     const float m = b1 * ch.m[i] + ob1 * g;
@@ -825,6 +832,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
     float p = ch.p[i] - step * (m / (sqrtf(v) / bc2_sqrt + eps));
     if (do_clamp) p = fminf(fmaxf(p, clamp_lo), clamp_hi);
     ch.p[i] = p;
+    if (ch.shadow) ch.shadow[i] = __float2bfloat16(p);
   }
 }
 __global__ void clamp_kernel(float* p, size_t n, float lo, float hi) {
@@ -1381,8 +1389,9 @@ int rg_adam_table_bytes(int num_chunks) { return static_cast<int>(sizeof(AdamChu
 
 // chunks_host: arrays of num_tensors pointers / sizes; table_dev: device buffer for the chunk table (filled here with
 // a synchronous-with-stream async copy from the caller's pinned or pageable host staging buffer table_host).
-int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms, void* const* vs, const int64_t* sizes,
-                        int num_tensors, int chunk_elems, void* table_host, int max_chunks) {
+int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms, void* const* vs,
+                        void* const* shadows, const int64_t* sizes, int num_tensors, int chunk_elems, void* table_host,
+                        int max_chunks) {
   RG_CHECK_ARG(params && grads && ms && vs && sizes && table_host && chunk_elems > 0, "rg_adam_build_table: bad arguments");
   AdamChunk* t = static_cast<AdamChunk*>(table_host);
   int n = 0;
@@ -1396,6 +1405,7 @@ int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms
       t[n].g = static_cast<const float*>(grads[i]) + off;
       t[n].m = static_cast<float*>(ms[i]) + off;
       t[n].v = static_cast<float*>(vs[i]) + off;
+      t[n].shadow = (shadows && shadows[i]) ? static_cast<__nv_bfloat16*>(shadows[i]) + off : nullptr;
       t[n].n = static_cast<int>(std::min<int64_t>(chunk_elems, sizes[i] - off));
       ++n;
     }

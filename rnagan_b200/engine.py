@@ -30,9 +30,24 @@ FUSED_STATS = os.environ.get("RG_FUSED_STATS", "1") != "0"
 
 
 def _grad_of(p):
-    if p.grad is None or p.grad.dtype != F32 or not p.grad.is_contiguous():
-        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    if p.grad is None or p.grad.dtype != F32 or p.grad.stride() != p.stride():
+        p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
     return p.grad
+
+
+def _to_native(params):
+    """Store 4x4 conv weights [Cp, Cs, 4, 4] channels_last, i.e. physically [Cp][kh][kw][Cs]: the element order of the
+    packed w_down operand and of the wgrad accumulator rows.  Shapes, values, state_dict keys and every torch op on
+    the parameter are unchanged; Adam then re-emits the bf16 GEMM operand while it updates the fp32 master (no pack
+    kernel) and the weight gradient is stored in whole 128-byte lines without a layout-changing reduce pass.
+    Returns the parameters whose storage was replaced."""
+    changed = []
+    for p in params:
+        if not ops.is_native4(p):
+            with torch.no_grad():
+                p.data = p.data.contiguous(memory_format=torch.channels_last)
+            changed.append(p)
+    return changed
 
 
 class _Bufs:
@@ -150,25 +165,38 @@ class GeneratorEngine:
             raise NotImplementedError("channel counts must be multiples of 64 on the sm_100a path")
         self.n = len(self.convs)
         self.size = 4 * (2 ** (self.n + 1))
-        # packed bf16 operands (derived, non-persistent)
-        self.w_proj = torch.empty(16 * self.C0, self.E, dtype=BF16, device=dev)
+        self._native_params = [self.conv0.weight] + [c.weight for c in self.convs]
+        _to_native(self._native_params)
+        # packed bf16 operands (derived, non-persistent).  G.0: [E][16*C0] = the bf16 image of the native weight, read
+        # as an MN-major B operand by rg_gemm_nn (column n = tap*C0 + co)
+        self.w_projkn = torch.empty(self.E, 16 * self.C0, dtype=BF16, device=dev)
+        self.conv0.weight._rg_shadow = self.w_projkn
         # one packed copy per link (w_down: K-major B for rg_conv_down, MN-major B for rg_conv_up); layers with
         # Cs <= 128 also keep the tiny K-major w_up copy, which is faster for narrow N tiles
         self.w_down, self.w_upk = [], []
         for c in self.convs:
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
             self.w_down.append(torch.empty(Cp, 16 * Cs, dtype=BF16, device=dev))
+            c.weight._rg_shadow = self.w_down[-1]        # re-emitted by the fused Adam step
             self.w_upk.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev) if Cs <= 128 else None)
         self.w_colT_last = torch.zeros(16 * self.Cimg, self.Cn, dtype=BF16, device=dev)
         self.w_col_last = torch.empty(self.Cn, 64, dtype=BF16, device=dev)
         self.sync = GradSync(module)
         self.pack()
 
-    def pack(self):
-        """Refresh the bf16 operand copies from the fp32 master weights (after load_state_dict / optimizer step)."""
-        ops.pack_proj(self.conv0.weight.detach(), self.w_proj)
+    def pack(self, full=True):
+        """Refresh the bf16 operand copies.  full=True (load_state_dict, external weight edits): everything from the
+        fp32 masters.  full=False (right after the fused Adam step, which already re-emitted w_down / w_projkn): only
+        the derived copies Adam does not write."""
+        if full:
+            for p in _to_native(self._native_params):
+                self.sync.rebind(p)
+            ops.cast_pad_bf16(ops.phys2d(self.conv0.weight.detach()), out=self.w_projkn)
+            for c, wd in zip(self.convs, self.w_down):
+                ops.cast_pad_bf16(ops.phys2d(c.weight.detach()), out=wd)
         for c, wd, wu in zip(self.convs, self.w_down, self.w_upk):
-            ops.pack_link(c.weight.detach(), wd, wu, want_up=wu is not None)
+            if wu is not None:
+                ops.pack_up_from_down(wd, wu, c.weight.shape[1])
         ops.pack_edge_t(self.conv_last.weight.detach(), self.w_colT_last)
         ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
 
@@ -178,7 +206,7 @@ class GeneratorEngine:
         g = self.bufs.get
         a = g(f"{tag}.a0", (B, 4, 4, self.C0))
         h = g(f"{tag}.h0", (B, 4, 4, self.C0))
-        ops.gemm_nt(lat, self.w_proj, out=a.view(B, 16 * self.C0))
+        ops.gemm_nn(lat, self.w_projkn, out=a.view(B, 16 * self.C0))
         self.bn0.forward(a, h, B * 16, training, tag=tag)
         H = 4
         for l, (c, bn) in enumerate(zip(self.convs, self.bns), start=1):
@@ -273,7 +301,7 @@ class UpGeneratorEngine:
         self.sync = GradSync(module)
         self.pack()
 
-    def pack(self):
+    def pack(self, full=True):
         ops.pack_proj(self.conv0.weight.detach(), self.w_proj)
         for c, w in zip(self.convs, self.w3):
             ops.pack_conv3(c.weight.detach(), w)
@@ -375,9 +403,12 @@ class CriticEngine:
         self.w_col0 = torch.empty(self.C0, 64, dtype=BF16, device=dev)
         self.w_colT0 = torch.zeros(16 * self.Cimg, self.C0, dtype=BF16, device=dev)
         self.w_down, self.w_upk = [], []
+        self._native_params = [c.weight for c in self.convs]
+        _to_native(self._native_params)
         for c in self.convs:
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
             self.w_down.append(torch.empty(Cp, 16 * Cs, dtype=BF16, device=dev))
+            c.weight._rg_shadow = self.w_down[-1]        # re-emitted by the fused Adam step
             self.w_upk.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev) if Cs <= 128 else None)
         self.w_head = torch.empty(16 * self.Cn, dtype=F32, device=dev)
         self.tmpC = torch.zeros(max([self.C0] + [c.weight.shape[0] for c in self.convs]), dtype=F32, device=dev)
@@ -386,11 +417,18 @@ class CriticEngine:
         self.sync = GradSync(module)
         self.pack()
 
-    def pack(self):
+    def pack(self, full=True):
+        """See GeneratorEngine.pack: full=False right after the fused Adam step (w_down already re-emitted)."""
         ops.pack_edge(self.conv0.weight.detach(), self.w_col0)
         ops.pack_edge_t(self.conv0.weight.detach(), self.w_colT0)
+        if full:
+            for p in _to_native(self._native_params):
+                self.sync.rebind(p)
+            for c, wd in zip(self.convs, self.w_down):
+                ops.cast_pad_bf16(ops.phys2d(c.weight.detach()), out=wd)
         for c, wd, wu in zip(self.convs, self.w_down, self.w_upk):
-            ops.pack_link(c.weight.detach(), wd, wu, want_up=wu is not None)
+            if wu is not None:
+                ops.pack_up_from_down(wd, wu, c.weight.shape[1])
         ops.pack_head(self.head.weight.detach(), self.w_head)
 
     def _wup(self, l):
@@ -651,7 +689,7 @@ class VAETrainEngine:
         self.sync = GradSync(vae)
         self.pack()
 
-    def pack(self):
+    def pack(self, full=True):
         for (l, _), w in zip(self.blocks, self.w):
             ops.cast_pad_bf16(l.weight.detach(), w.shape[1], out=w)
         ops.cast_pad_bf16(self.last.weight.detach(), self.w_last.shape[1], out=self.w_last)

@@ -75,6 +75,35 @@ def pack_link(W, w_down=None, w_up=None, want_down=True, want_up=True):
     return w_down, w_up
 
 
+def is_native4(t):
+    """True when a 4-D tensor [N, C, H, W] is stored channels_last, i.e. physically [N][H][W][C] -- the engine's
+    native weight layout (same element order as the packed w_down operand and as the wgrad accumulator rows)."""
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+
+
+def phys2d(W):
+    """[Cp, 16*Cs] view of the physical memory of a native (channels_last) weight [Cp, Cs, 4, 4]."""
+    return W.permute(0, 2, 3, 1).reshape(W.shape[0], -1)
+
+
+def _wgrad_layout(dW):
+    if dW.dtype != torch.float32 or dW.device.type != "cuda":
+        raise ValueError("dW must be a CUDA fp32 tensor")
+    if dW.is_contiguous():
+        return 0
+    if is_native4(dW):
+        return 1
+    raise ValueError("dW must be contiguous or channels_last")
+
+
+def pack_up_from_down(w_down, w_up, Cs):
+    """bf16 w_down [Cp, 16*Cs] -> bf16 w_up [4, Cs_pad, 4*Cp]."""
+    _chk(w_down, BF16, "w_down"); _chk(w_up, BF16, "w_up")
+    _lib.check(_lib.lib().rg_pack_up_from_down(_p(w_down), _p(w_up), w_down.shape[0], Cs, _st()),
+               "rg_pack_up_from_down")
+    return w_up
+
+
 def pack_proj(W, out=None):
     """W: fp32 [E, C0, 4, 4] -> bf16 [16*C0, E]."""
     _chk(W, torch.float32, "W")
@@ -158,8 +187,9 @@ def conv_up_img(lo, w_up, Cimg, bias=None, act_tanh=False, out=None):
 
 
 def conv_wgrad(lo, hi, dW, alpha=1.0, alpha_dev=None, beta=0.0):
-    """dW fp32 [Cp, Cs, 4, 4] = beta*dW + alpha * sum lo (x) hi@tap."""
-    _chk(lo, BF16, "lo"); _chk(hi, BF16, "hi"); _chk(dW, torch.float32, "dW")
+    """dW fp32 [Cp, Cs, 4, 4] (contiguous or channels_last) = beta*dW + alpha * sum lo (x) hi@tap."""
+    _chk(lo, BF16, "lo"); _chk(hi, BF16, "hi")
+    native = _wgrad_layout(dW)
     B, H, W, Cp = lo.shape
     Cs = hi.shape[3]
     L = _lib.lib()
@@ -167,13 +197,14 @@ def conv_wgrad(lo, hi, dW, alpha=1.0, alpha_dev=None, beta=0.0):
     ws = _workspace(nbytes, lo.device)
     _prof("conv_wgrad", 2.0 * B * H * W * Cp * 16 * Cs, lambda: _lib.check(
         L.rg_conv_wgrad(_p(lo), _p(hi), _p(dW), _p(ws), ws.numel() * 4, B, H, W, Cp, Cs, float(alpha), _p(alpha_dev),
-                        float(beta), _st()), "rg_conv_wgrad"))
+                        float(beta), native, _st()), "rg_conv_wgrad"))
     return dW
 
 
 def proj_wgrad(z, da0, dW, alpha=1.0, alpha_dev=None, beta=0.0):
-    """dW fp32 [E, C0, 4, 4] = sum_b z[b, e] * da0[b, kh, kw, c]."""
-    _chk(z, BF16, "z"); _chk(da0, BF16, "da0"); _chk(dW, torch.float32, "dW")
+    """dW fp32 [E, C0, 4, 4] (contiguous or channels_last) = sum_b z[b, e] * da0[b, kh, kw, c]."""
+    _chk(z, BF16, "z"); _chk(da0, BF16, "da0")
+    native = _wgrad_layout(dW)
     B, E = z.shape
     C0 = da0.shape[-1]
     L = _lib.lib()
@@ -181,7 +212,7 @@ def proj_wgrad(z, da0, dW, alpha=1.0, alpha_dev=None, beta=0.0):
     ws = _workspace(nbytes, z.device)
     _prof("proj_wgrad", 2.0 * B * E * 16 * C0, lambda: _lib.check(
         L.rg_proj_wgrad(_p(z), _p(da0), _p(dW), _p(ws), ws.numel() * 4, B, E, C0, float(alpha), _p(alpha_dev),
-                        float(beta), _st()), "rg_proj_wgrad"))
+                        float(beta), native, _st()), "rg_proj_wgrad"))
     return dW
 
 
@@ -390,21 +421,24 @@ class AdamTable:
 
     CHUNK = 1 << 16
 
-    def __init__(self, params, grads, ms, vs):
+    def __init__(self, params, grads, ms, vs, shadows=None):
         import ctypes
         L = _lib.lib()
         n = len(params)
+        shadows = list(shadows) if shadows is not None else [None] * n
         sizes = [p.numel() for p in params]
         max_chunks = sum((s + self.CHUNK - 1) // self.CHUNK for s in sizes)
         arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
         host = torch.empty(L.rg_adam_table_bytes(max_chunks), dtype=torch.uint8).pin_memory()
-        nch = L.rg_adam_build_table(arr(params), arr(grads), arr(ms), arr(vs), (ctypes.c_int64 * n)(*sizes), n,
+        sh = (ctypes.c_void_p * n)(*[None if t is None else t.data_ptr() for t in shadows])
+        nch = L.rg_adam_build_table(arr(params), arr(grads), arr(ms), arr(vs), sh, (ctypes.c_int64 * n)(*sizes), n,
                                     self.CHUNK, host.data_ptr(), max_chunks)
         if nch <= 0:
             _lib.check(nch if nch < 0 else -1, "rg_adam_build_table")
         self.num_chunks = nch
         self.table = host.to(params[0].device, non_blocking=False)
         self.keep = (params, grads, ms, vs)
+        self.shadows = shadows
         self.ptrs = tuple(t.data_ptr() for ts in self.keep for t in ts)
 
     def step(self, lr, beta1, beta2, eps, step, clamp=None, grad_scale=1.0):

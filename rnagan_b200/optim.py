@@ -14,9 +14,20 @@ def _ensure_state(opt, p):
     st = opt.state[p]
     if len(st) == 0:
         st["step"] = torch.tensor(0.0, dtype=torch.float32)
-        st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-        st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+    for k in ("exp_avg", "exp_avg_sq"):
+        # the kernel walks physical memory: moments must share the parameter's layout (a state loaded from an upstream
+        # checkpoint is contiguous while the engine keeps conv weights channels_last) -- converted once
+        if st[k].stride() != p.stride() or st[k].device != p.device or st[k].dtype != p.dtype:
+            new = torch.empty_like(p, memory_format=torch.preserve_format)
+            new.copy_(st[k])
+            st[k] = new
     return st
+
+
+def _dense(t):
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
 
 
 def adam_step(opt, clamp=None, grad_scale=1.0):
@@ -33,13 +44,15 @@ def adam_step(opt, clamp=None, grad_scale=1.0):
             continue
         states = [_ensure_state(opt, p) for p in params]
         for p in params:
-            if p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
-                raise NotImplementedError("fused Adam needs contiguous fp32 parameters and gradients")
-        key = tuple(t.data_ptr() for p, s in zip(params, states) for t in (p, p.grad, s["exp_avg"], s["exp_avg_sq"]))
+            if p.dtype != torch.float32 or not _dense(p) or p.grad.stride() != p.stride():
+                raise NotImplementedError("fused Adam needs dense fp32 parameters with gradients in the same layout")
+        shadows = [getattr(p, "_rg_shadow", None) for p in params]
+        key = tuple(t.data_ptr() for p, s in zip(params, states) for t in (p, p.grad, s["exp_avg"], s["exp_avg_sq"])) + \
+            tuple(0 if t is None else t.data_ptr() for t in shadows)
         ent = tables.get(gi)
         if ent is None or ent[0] != key:
             tab = ops.AdamTable([p.detach() for p in params], [p.grad for p in params],
-                                [s["exp_avg"] for s in states], [s["exp_avg_sq"] for s in states])
+                                [s["exp_avg"] for s in states], [s["exp_avg_sq"] for s in states], shadows)
             ent = (key, tab)
             tables[gi] = ent
         for s in states:

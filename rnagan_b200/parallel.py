@@ -76,9 +76,23 @@ class GradSync:
         self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=params[0].device)
         for p in params:
             o, n = offs[id(p)]
-            p.grad = self.flat[o:o + n].view_as(p)
+            p.grad = self._view(o, n, p)
         self._pending = []
         self._done = set()
+
+    def _view(self, o, n, p):
+        """Gradient view with the parameter's own memory layout (conv weights the engines keep channels_last get a
+        channels_last gradient: the wgrad kernels write it natively and Adam walks all four tensors in lockstep)."""
+        seg = self.flat[o:o + n]
+        if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+            N, C, H, W = p.shape
+            return seg.view(N, H, W, C).permute(0, 3, 1, 2)
+        return seg.view_as(p)
+
+    def rebind(self, p):
+        """Re-create the gradient view of one parameter after its layout changed."""
+        o, n = self.offs[id(p)]
+        p.grad = self._view(o, n, p)
 
     @staticmethod
     def world():

@@ -36,7 +36,7 @@ def g_step(generator, discriminator, opt_g, noise_d, z):
     d_img = de.backward(B, -1.0 / B, tag="gstep", params=False, want_dimg=True)
     ge.backward(lat, d_img, fake, tag="g")
     adam_step(opt_g, grad_scale=ge.sync.finish())       # gradients averaged over ranks (no-op single-process)
-    ge.pack()
+    ge.pack(full=False)                                 # Adam re-emitted the bf16 GEMM operands itself
     return loss
 
 
@@ -57,7 +57,7 @@ def critic_step(generator, discriminator, opt_d, noise_d, z, real, clip=None):
     de.backward(B, -1.0 / B, tag="real", params=True, acc=0.0)
     de.backward(B, 1.0 / B, tag="fake", params=True, acc=1.0, final=True)
     adam_step(opt_d, grad_scale=de.sync.finish())
-    de.pack()
+    de.pack(full=False)
     return loss
 
 
@@ -68,5 +68,5 @@ def gp_step(generator, discriminator, opt_d, noise_d, z, real, eps_d, lambd=10.0
     fake = ge.forward(lat, tag="g", training=generator.training)
     out3 = de.gradient_penalty(real, fake, eps_d, lambd=lambd)
     adam_step(opt_d, grad_scale=de.sync.finish())
-    de.pack()
+    de.pack(full=False)
     return out3

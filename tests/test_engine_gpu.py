@@ -119,6 +119,13 @@ def test_conv_wgrad(cuda_dev, B, H, W, Cs, Cp):
     scale = torch.tensor([0.5], device=cuda_dev)
     ops.conv_wgrad(_nhwc(lo), _nhwc(hi), dW, alpha=2.0, alpha_dev=scale, beta=1.0)
     assert _rel(dW, 2 * ref) < 2e-3
+    # native (channels_last) gradient layout: what the engines use -- direct epilogue or native split-K reduce
+    dWn = torch.empty(Cp, Cs, 4, 4, device=cuda_dev).contiguous(memory_format=torch.channels_last)
+    assert ops.is_native4(dWn)
+    ops.conv_wgrad(_nhwc(lo), _nhwc(hi), dWn)
+    assert _rel(dWn, ref) < 2e-3
+    ops.conv_wgrad(_nhwc(lo), _nhwc(hi), dWn, alpha=2.0, alpha_dev=scale, beta=1.0)
+    assert _rel(dWn, 2 * ref) < 2e-3
 
 
 def test_proj_wgrad_and_fwd(cuda_dev):
@@ -280,3 +287,31 @@ def test_bn_finalize_partials(cuda_dev):
     assert _rel(scale, gamma * (v_ref + 1e-5).rsqrt()) < 1e-3
     assert _rel(rm, 0.1 * m_ref) < 1e-4 and _rel(rv, 0.9 + 0.1 * af.var(0, unbiased=True)) < 1e-3
     assert int(nbt.item()) == 1 and _rel(sums[0], af.sum(0)) < 1e-4
+
+
+def test_pack_up_from_down_and_adam_shadow(cuda_dev):
+    """The K-major w_up copy derived from the bf16 w_down equals the one packed from the fp32 weight, and the fused
+    Adam step re-emits the bf16 image of a channels_last weight (= w_down) while updating the fp32 master."""
+    from rnagan_b200 import ops
+    Cp, Cs = 128, 64
+    g = torch.Generator(device="cpu").manual_seed(21)
+    Wt = _bf(torch.randn(Cp, Cs, 4, 4, generator=g) * 0.05).to(cuda_dev)
+    w_down, w_up = ops.pack_link(Wt)
+    w_up2 = torch.zeros_like(w_up)
+    ops.pack_up_from_down(w_down, w_up2, Cs)
+    assert torch.equal(w_up, w_up2)
+    Wn = Wt.contiguous(memory_format=torch.channels_last)
+    assert torch.equal(ops.cast_pad_bf16(ops.phys2d(Wn)), w_down)
+    # Adam with a shadow
+    p = (torch.randn(Cp, Cs, 4, 4, generator=g) * 0.05).to(cuda_dev).contiguous(memory_format=torch.channels_last)
+    gr = torch.randn(Cp, Cs, 4, 4, generator=g).to(cuda_dev).contiguous(memory_format=torch.channels_last)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    shadow = torch.zeros(Cp, 16 * Cs, dtype=torch.bfloat16, device=cuda_dev)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-3, betas=(0.5, 0.999))
+    pr.grad = gr.clone()
+    opt.step()
+    tab = ops.AdamTable([p], [gr], [m], [v], [shadow])
+    tab.step(1e-3, 0.5, 0.999, 1e-8, 1)
+    assert _rel(p, pr.detach()) < 1e-5
+    assert torch.equal(shadow, ops.cast_pad_bf16(ops.phys2d(p)))
