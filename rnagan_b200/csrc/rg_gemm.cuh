@@ -30,7 +30,7 @@ constexpr int kAffineBytes = 2048;           // per-column scale / shift of the 
 constexpr int kStatBytes = 2048;             // per-warp column sums of one slab (4 warps x 2 x 64 floats)
 constexpr int kSmemFixedBytes = kBarBytes + kAffineBytes + kStatBytes + 1024 /*alignment slack*/;
 constexpr int kSmemMaxBytes = 232448;        // 227 KiB: the sm_100 per-CTA dynamic shared memory limit
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 224;            // warps: 0 A-producer, 1 MMA issuer, 2-5 epilogue, 6 B-producer
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;              // TMEM columns per accumulator stage
 // weight-gradient kernel: fixed ring (4 x 48 KiB, or 3 x 64 KiB for 256-row units)
@@ -241,8 +241,10 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
                              ((p.whatif & 8) ? 0u : static_cast<uint32_t>(p.b_stage_bytes))) * CG;
   const int bn_cta = p.block_n / CG;                // B rows (N columns) this CTA fetches
 
-  if (warp == 0) {
-    // ===================================================== TMA producer (one elected lane, in every CTA of the group)
+  if (warp == 0 || warp == 6) {
+    // ===================================================== TMA producers (one elected lane each, in every CTA of the
+    // group): warp 0 announces the stage's bytes and fetches the A tile, warp 6 fetches the B tile.  Issuing a TMA
+    // costs its thread ~100 cycles, so two issuers halve the per-k-block cost that bounds the narrow layers.
     // This single thread paces the whole pipeline: everything loop-invariant lives in registers (the asm memory
     // clobbers would otherwise make the compiler re-read kernel parameters every k-block), there is no integer
     // division in the k loop (taps outer, channel chunks inner) and shared addresses are plain 32-bit integers.
@@ -251,8 +253,8 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
       const int tw = p.tw, th = p.th, bw = p.bw, bh = p.bh, bb = p.bb;
       const int block_n = p.block_n, b_phase_rows = p.b_phase_rows, b_tap_cols = p.b_tap_cols;
       const bool a_2d = p.a_2d != 0, b_mn = p.b_mn != 0;
-      const bool skip_a = (p.whatif & 4) != 0, skip_b = (p.whatif & 8) != 0;
-      const bool prof = p.prof != nullptr;
+      const bool do_a = warp == 0 && (p.whatif & 4) == 0, do_b = warp == 6 && (p.whatif & 8) == 0;
+      const bool prof = p.prof != nullptr && warp == 0;
       const int ns = bn_cta >> 6;
       const uint32_t ring0 = smem_u32(s.stages);
       const uint32_t full0 = smem_u32(&s.full[0]), empty0 = smem_u32(&s.empty[0]);
@@ -287,12 +289,12 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
             const uint32_t sa = ring0 + stage * stage_bytes;
             const uint32_t sb = sa + kAStageBytes;
             const uint32_t fb = full0_tx + stage * 8;
-            if (crank == 0) mbar_expect_tx_raw(full0 + stage * 8, stage_tx);
-            if (!skip_a) {
+            if (warp == 0 && crank == 0) mbar_expect_tx_raw(full0 + stage * 8, stage_tx);
+            if (do_a) {
               if (a_2d) tma_ld_2d_raw<CG>(desc_a0, fb, sa, chunk * kBlockK, b0);
               else tma_ld_4d_raw<CG>(desc_a, fb, sa, chunk * kBlockK, cj, ci, b0);
             }
-            if (!skip_b) {
+            if (do_b) {
               if (b_mn) {
                 // B^T slabs [64 k-rows = p][64 n = s] straight out of w_down: no second packed copy of the weights
                 for (int sl = 0; sl < ns; ++sl)
@@ -670,8 +672,8 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
   const int total_units = p.m_tiles * p.n_tiles * p.splits;
   const uint32_t stage_tx = static_cast<uint32_t>(2 * msub + p.slabs_per_tile) * 8192u;
 
-  if (warp == 0) {
-    // Producer: one thread paces the pipeline, so the pixel-block loop holds no division, no parameter re-reads and
+  if (warp == 0 || warp == 6) {
+    // Producers (warp 0: stage bytes + the low-resolution slabs, warp 6: the high-resolution slabs): one thread each paces the pipeline, so the pixel-block loop holds no division, no parameter re-reads and
     // no per-slab tap decoding (all hoisted per unit into registers).
     if (elect_one()) {
       const int m_tiles = p.m_tiles, n_tiles = p.n_tiles, pb_per_split = p.pb_per_split, num_pb = p.num_pb;
@@ -711,15 +713,15 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
           const uint32_t sa = ring0 + stage * stage_bytes;
           const uint32_t sb = sa + a_bytes;
           const uint32_t fb = full0 + stage * 8;
-          mbar_expect_tx_raw(fb, stage_tx);
+          if (warp == 0) mbar_expect_tx_raw(fb, stage_tx);
           // MMA-A operand: 64-channel slabs of the low-resolution tensor (channels beyond Cp zero-fill)
 #pragma unroll
           for (int sl = 0; sl < 4; ++sl)
-            if (sl < 2 * msub) tma_ld_4d_raw<1>(desc_lo, fb, sa + sl * 8192, mcol + sl * 64, j0, i0, b0);
+            if (warp == 0 && sl < 2 * msub) tma_ld_4d_raw<1>(desc_lo, fb, sa + sl * 8192, mcol + sl * 64, j0, i0, b0);
           // MMA-B operand: one slab per (tap, 64-channel chunk) of the high-resolution tensor
 #pragma unroll
           for (int sl = 0; sl < 4; ++sl)
-            if (sl < spt) tma_ld_4d_raw<1>(sdesc[sl], fb, sb + sl * 8192, scol[sl], j0 + sdw[sl], i0 + sdh[sl], b0);
+            if (warp == 6 && sl < spt) tma_ld_4d_raw<1>(sdesc[sl], fb, sb + sl * 8192, scol[sl], j0 + sdw[sl], i0 + sdh[sl], b0);
           if (++stage == nstages) { stage = 0; phase ^= 1u; }
           if (++jt == tw) { jt = 0; if (++it == th) { it = 0; ++bt; } }
         }

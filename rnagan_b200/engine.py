@@ -56,8 +56,34 @@ class _Bufs:
     def __init__(self, device):
         self.device = device
         self._d = {}
+        self._alias = {}
+
+    def pair(self, name_a, name_b):
+        """Make `name_a` / `name_b` the two halves of ONE allocation [2, *shape]: two passes (real / fake, or the two
+        operand sets of the gradient penalty) then feed a single weight-gradient or input-gradient launch over the
+        concatenated batch instead of two launches with an accumulating epilogue."""
+        group = ("pair", name_a, name_b)
+        self._alias.setdefault(name_a, (group, 0))
+        self._alias.setdefault(name_b, (group, 1))
+
+    def joint(self, name_a, shape, dtype=BF16):
+        """The whole [2*B, ...] tensor whose first half is `name_a` (which must have been paired)."""
+        group, _ = self._alias[name_a]
+        t = self._pair_tensor(group, shape, dtype)
+        return t.view(2 * shape[0], *shape[1:])
+
+    def _pair_tensor(self, group, shape, dtype):
+        key = (group, tuple(shape), dtype)
+        t = self._d.get(key)
+        if t is None:
+            t = torch.zeros((2,) + tuple(shape), dtype=dtype, device=self.device)
+            self._d[key] = t
+        return t
 
     def get(self, name, shape, dtype=BF16, zero=False):
+        al = self._alias.get(name)
+        if al is not None:
+            return self._pair_tensor(al[0], shape, dtype)[al[1]]
         key = (name, tuple(shape), dtype)
         t = self._d.get(key)
         if t is None:
@@ -415,6 +441,19 @@ class CriticEngine:
         self.gp_partial = torch.zeros(1024, dtype=F32, device=dev)
         self.gp_out = torch.zeros(3, dtype=F32, device=dev)
         self.sync = GradSync(module)
+        # critic step: real / fake passes share their weight- and input-gradient launches (see backward_pair)
+        self.bufs.pair("real.col", "fake.col")
+        self.bufs.pair("real.da0", "fake.da0")
+        for l in range(0, self.n + 1):
+            self.bufs.pair(f"real.h{l}", f"fake.h{l}")
+            self.bufs.pair(f"real.dh{l}", f"fake.dh{l}")
+            if l >= 1:
+                self.bufs.pair(f"real.da{l}", f"fake.da{l}")
+        # gradient penalty: the two weight-gradient terms of layer l, (da_l (x) A_dh_{l-1}) + (T_l (x) h_{l-1}), are one
+        # contraction over the concatenated pixel axis
+        for l in range(1, self.n + 1):
+            self.bufs.pair(f"gp.da{l}", f"gp.Aa{l}" if l == self.n else f"gp.T{l}")
+            self.bufs.pair(f"gp.Adh{l - 1}", f"gp.h{l - 1}")
         self.pack()
 
     def pack(self, full=True):
@@ -513,6 +552,49 @@ class CriticEngine:
             return dimg
         return None
 
+    def backward_pair(self, B, passes=(("real", -1.0), ("fake", 1.0))):
+        """Critic-step backward of sum_b c_real*out_real[b] + c_fake*out_fake[b] (passes = ((tag, c*B), ...)) with
+        parameter gradients (overwriting .grad): BatchNorm backward runs per pass (its statistics are per pass), the
+        weight gradient and the input gradient of every conv layer run ONCE over the concatenated 2B batch."""
+        g = self.bufs.get
+        n = self.n
+        (ta, _), (tb, _) = passes
+        H = 4
+        for i, (tag, c) in enumerate(passes):
+            hn = g(f"{tag}.h{n}", (B, H, H, self.Cn))
+            a6 = g(f"{tag}.a6", (B,), F32)
+            da6 = g(f"{tag}.da6", (B,), F32)
+            dh = g(f"{tag}.dh{n}", (B, H, H, self.Cn))
+            ops.head_bwd_data(a6, c / B, self.w_head, B, 16 * self.Cn, SLOPE, da6, dh)
+            ops.head_wgrad(da6, hn, B, 16 * self.Cn, self.Cn, _grad_of(self.head.weight), float(i > 0))
+        self.sync.layer_done(self.head.weight)
+        for l in range(n, 0, -1):
+            c_, bn = self.convs[l - 1], self.bns[l - 1]
+            Cp, Cs = c_.weight.shape[0], c_.weight.shape[1]
+            for i, (tag, _) in enumerate(passes):
+                a = g(f"{tag}.a{l}", (B, H, H, Cp))
+                da = g(f"{tag}.da{l}", (B, H, H, Cp))
+                dh = g(f"{tag}.dh{l}", (B, H, H, Cp))
+                bn.backward(dh, a, da, B * H * H, param_grads=True, acc_gamma=float(i > 0), acc_beta=float(i > 0), tag=tag)
+            da2 = self.bufs.joint(f"{ta}.da{l}", (B, H, H, Cp))
+            hprev2 = self.bufs.joint(f"{ta}.h{l - 1}", (B, 2 * H, 2 * H, Cs))
+            ops.conv_wgrad(da2, hprev2, _grad_of(c_.weight))
+            self.sync.layer_done(c_.weight, bn.mod.weight, bn.mod.bias)
+            H *= 2
+            dh2 = self.bufs.joint(f"{ta}.dh{l - 1}", (B, H, H, Cs))
+            ops.conv_up(da2, self._wup(l), Cs, out=dh2)
+        npix = B * H * H
+        h0 = self.bufs.joint(f"{ta}.h0", (B, H, H, self.C0))
+        dh0 = self.bufs.joint(f"{ta}.dh0", (B, H, H, self.C0))
+        da0 = self.bufs.joint(f"{ta}.da0", (B, H, H, self.C0))
+        ops.lrelu_bwd(dh0, h0, SLOPE, da0, 2 * npix, self.C0)
+        ops.col_sum(da0, 2 * npix, self.C0, self.tmpC, _grad_of(self.conv0.bias), 0.0)
+        col = self.bufs.joint(f"{ta}.col", (npix, 64))
+        dcol = g("bwd.dcol", (self.C0, 64), F32)
+        ops.gemm_tn(da0.view(2 * npix, self.C0), col, out=dcol)
+        ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=0.0)
+        self.sync.layer_done(self.conv0.weight, self.conv0.bias)
+
     # ------------------------------------------------------------------ gradient penalty
     def gradient_penalty(self, real, fake, eps_dev, lambd=10.0, tag="gp"):
         """WassersteinGradientPenaltyVAE core (src/wgan_loss.py:32-44, 376-388): writes d(lambda*P)/d(theta_D)
@@ -552,7 +634,7 @@ class CriticEngine:
             da = g(f"{tag}.da{l}", (B, H, H, Cp))
             du = g(f"{tag}.du{l}", (B, H, H, Cp))
             a = g(f"{tag}.a{l}", (B, H, H, Cp))
-            ops.conv_wgrad(da, A_dh, _grad_of(c.weight), beta=0.0)
+            # (the da_l (x) A_dh_{l-1} weight-gradient term is contracted in step 4, jointly with T_l (x) h_{l-1})
             ggI = g(f"{tag}.ggI{l}", (B, H, H, Cp))
             ops.conv_down(A_dh, self.w_down[l - 1], out=ggI)
             # bn.bsums still holds S(du), S(du*xhat) of THIS layer from step 2
@@ -572,8 +654,9 @@ class CriticEngine:
         for l in range(n, 0, -1):
             c = self.convs[l - 1]
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
-            hprev = g(f"{tag}.h{l - 1}", (B, 2 * H, 2 * H, Cs))
-            ops.conv_wgrad(T, hprev, _grad_of(c.weight), beta=1.0)
+            lo2 = self.bufs.joint(f"{tag}.da{l}", (B, H, H, Cp))                  # [da_l ; T_l]
+            hi2 = self.bufs.joint(f"{tag}.Adh{l - 1}", (B, 2 * H, 2 * H, Cs))     # [A_dh_{l-1} ; h_{l-1}]
+            ops.conv_wgrad(lo2, hi2, _grad_of(c.weight))
             # conv_l's weight is final now; BN_l's gamma/beta were finalised by step 3 (l = n) or the previous turn
             self.sync.layer_done(c.weight, self.bns[l - 1].mod.weight, self.bns[l - 1].mod.bias)
             H *= 2

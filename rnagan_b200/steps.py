@@ -54,8 +54,7 @@ def critic_step(generator, discriminator, opt_d, noise_d, z, real, clip=None):
     out_fake = de.forward(fake, tag="fake", training=discriminator.training)
     loss = _loss_buf(ge, "loss_d")
     ops.wgan_loss(out_fake, 1.0, loss, b=out_real, sign_b=-1.0)      # mean(D(G(z)) - D(x))
-    de.backward(B, -1.0 / B, tag="real", params=True, acc=0.0)
-    de.backward(B, 1.0 / B, tag="fake", params=True, acc=1.0, final=True)
+    de.backward_pair(B, (("real", -1.0), ("fake", 1.0)))     # one wgrad / dgrad launch per layer over both passes
     adam_step(opt_d, grad_scale=de.sync.finish())
     de.pack(full=False)
     return loss

@@ -56,7 +56,10 @@ def main(filt=""):
             if Cs <= 128:
                 report(f"conv_up   {name} {Cp}->{Cs} @{h} (w_up, K-major B)", timeit(lambda: ops.conv_up(lo, wu, Cs, out=out_hi)), fl, by)
         if filt in f"wgrad {name}":
-            report(f"conv_wgrad {name}", timeit(lambda: ops.conv_wgrad(lo, hi, dW)), fl, by + W.numel() * 2)
+            report(f"conv_wgrad {name} (torch layout)", timeit(lambda: ops.conv_wgrad(lo, hi, dW)), fl, by + W.numel() * 2)
+            dWn = torch.empty_like(W).contiguous(memory_format=torch.channels_last)
+            report(f"conv_wgrad {name} (native layout)", timeit(lambda: ops.conv_wgrad(lo, hi, dWn)), fl, by + W.numel() * 2)
+            report(f"conv_wgrad {name} (native, beta=1)", timeit(lambda: ops.conv_wgrad(lo, hi, dWn, beta=1.0)), fl, by + W.numel() * 6)
     # image-side / projection GEMMs
     M = B * 128 * 128
     A = torch.randn(M, 64, device=dev).to(BF)
