@@ -52,12 +52,54 @@ __device__ __forceinline__ Vec8 ldf8(const float* p) {
 }
 
 // ------------------------------------------------------------------------------------------------ column reduce
-// Stage 1: partial[block][k][c] = sum over the block's rows of f_k(row, c).  Functor F: static K, and
-//   __device__ void operator()(size_t row, int c0, float (&acc)[K][8]) const   (accumulates 8 channels)
+// Stage 1: partial[block][k][c] = sum over the block's rows of f_k(row, c).  Functor F: static K, a register struct
+// F::In, `In load(row, c0)` (global loads only) and `void acc(const In&, c0, float (&acc)[K][8])` (math only).
+// The split keeps FOUR rows of loads in flight per thread before any arithmetic: written as one call per row the
+// compiler interleaved load / compute and the kernels ran latency-bound at 38-48 % of HBM peak.
+__device__ __forceinline__ Vec8 unpack8(const uint4& u) {
+  Vec8 r;
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+// streaming 16-byte load; `asm volatile` keeps the batch of loads a thread issues ahead of its arithmetic in program
+// order (ptxas otherwise sinks each load next to its first use, leaving one row in flight per thread)
+__device__ __forceinline__ uint4 ldu4(const __nv_bfloat16* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kRedRows = 4;                       // rows per batch per thread
+constexpr int kRedStageBytes = 2 * kRedRows * 256 * 16;   // per input tensor: double-buffered, 16 B per thread per row
+
+// Functor F: static K (sums), static NT (input tensors), `const bf16* ptr(int t)`, and
+// `void acc(const uint4 (&d)[NT], int c0, float (&acc)[K][8])`.
+// Loads go global -> shared with cp.async into thread-private slots, a batch of kRedRows rows ahead of the arithmetic
+// (double-buffered): every thread keeps 2 x NT x 4 x 16 bytes in flight without holding them in registers.  (Plain
+// register loads were sunk next to their uses by ptxas -- one row in flight per thread, 38-48 % of HBM peak.)
 template <class F>
 __global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int rows_per_block, float* __restrict__ partial) {
   constexpr int K = F::K;
-  extern __shared__ float sm[];   // [lanes][K][8*cgs_in_flight] only used when lanes > 1
+  constexpr int NT = F::NT;
+  constexpr int R = kRedRows;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  float* sm = reinterpret_cast<float*>(smraw);   // after the row loop: [lanes][K][C] cross-lane reduction scratch
   const int cgs = C >> 3;
   const int lanes = cgs >= 256 ? 1 : 256 / cgs;            // row lanes per block iteration
   const int rl = cgs >= 256 ? 0 : threadIdx.x / cgs;
@@ -65,6 +107,10 @@ __global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int r
   const bool active = cgs >= 256 ? true : (threadIdx.x < lanes * cgs);
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
+  // slot(buf, j, t) for this thread
+  auto slot = [&](int buf, int j, int t) -> uint4* {
+    return reinterpret_cast<uint4*>(smraw + (static_cast<size_t>((t * 2 + buf) * R + j) * 256 + threadIdx.x) * 16);
+  };
   for (int cg = cg0; cg < cgs; cg += 256) {
     float acc[K][8];
 #pragma unroll
@@ -72,15 +118,38 @@ __global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int r
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[k][e] = 0.0f;
     if (active) {
-      int r = r0 + rl;
-      for (; r + 3 * lanes < r1; r += 4 * lanes) {     // 4 independent rows in flight per thread
-        f(static_cast<size_t>(r), cg * 8, acc);
-        f(static_cast<size_t>(r + lanes), cg * 8, acc);
-        f(static_cast<size_t>(r + 2 * lanes), cg * 8, acc);
-        f(static_cast<size_t>(r + 3 * lanes), cg * 8, acc);
+      const int c0 = cg * 8;
+      const int step = R * lanes;
+      int rb = r0 + rl;                      // first row of the batch being fetched
+      auto fetch = [&](int buf, int row0) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int r = row0 + j * lanes;
+          if (r < r1) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) cp_async16(slot(buf, j, t), f.ptr(t) + static_cast<size_t>(r) * C + c0);
+          }
+        }
+        cp_async_commit();
+      };
+      fetch(0, rb);
+      int buf = 0;
+      for (int r = rb; r < r1; r += step, buf ^= 1) {
+        fetch(buf ^ 1, r + step);            // next batch (possibly empty) while this one is consumed
+        cp_async_wait<1>();
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          if (r + j * lanes < r1) {
+            uint4 d[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) d[t] = *slot(buf, j, t);
+            f.acc(d, c0, acc);
+          }
+        }
       }
-      for (; r < r1; r += lanes) f(static_cast<size_t>(r), cg * 8, acc);
+      cp_async_wait<0>();
     }
+    if (lanes > 1) __syncthreads();          // staging slots are reused as reduction scratch below
     if (lanes == 1) {
 #pragma unroll
       for (int k = 0; k < K; ++k)
@@ -104,6 +173,7 @@ __global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int r
     }
   }
 }
+
 // Stage 2: out[k][c] = sum_blocks partial[block][k][c]; 32 columns x 32 block-lanes per CTA (narrow layers have few
 // columns, so the parallelism has to come from the block dimension), four loads in flight per thread, lanes summed
 // in a fixed order
@@ -137,17 +207,19 @@ struct ReducePlan {
   int blocks, rows_per_block;
   size_t smem;
 };
-static ReducePlan plan_reduce(int M, int C, int K) {
+static ReducePlan plan_reduce(int M, int C, int K, int NT = 1) {
   ReducePlan p;
   const int cgs = C / 8;
   const int lanes = cgs >= 256 ? 1 : 256 / cgs;
-  int target = num_sms() * 4;
+  // one wave of resident CTAs: the cp.async staging (NT x 32 KiB) limits residency to 4 / 3 / 2 CTAs per SM.
+  // (NT = 1 yields the most blocks: the workspace query uses it as the upper bound.)
+  int target = num_sms() * (NT <= 1 ? 4 : (NT == 2 ? 3 : 2));
   int rpb = std::max(lanes * 8, ceil_div(M, target));
   rpb = ceil_div(rpb, lanes) * lanes;
   p.rows_per_block = rpb;
   p.blocks = ceil_div(M, rpb);
-  p.smem = lanes > 1 ? static_cast<size_t>(lanes) * K * C * sizeof(float) : 0;
-  return p;
+  p.smem = lanes > 1 ? static_cast<size_t>(lanes) * K * C * sizeof(float) : 0;   // cross-lane scratch; run_colreduce
+  return p;                                                                       // adds the cp.async staging
 }
 static size_t reduce_ws_floats(int M, int C, int K) {
   ReducePlan p = plan_reduce(M, C, K);
@@ -161,20 +233,21 @@ static int run_colreduce(F f, int M, int C, float* ws, size_t ws_bytes, float* o
     set_error("%s: need C %% 8 == 0, 8 <= C <= 65536, M > 0 (M=%d C=%d)", name, M, C);
     return RG_EINVAL;
   }
-  ReducePlan p = plan_reduce(M, C, K);
+  ReducePlan p = plan_reduce(M, C, K, F::NT);
   const size_t need = static_cast<size_t>(p.blocks) * K * C * sizeof(float);
   if (!ws || ws_bytes < need) {
     set_error("%s: reduction workspace too small (need %zu, have %zu)", name, need, ws_bytes);
     return RG_EWORKSPACE;
   }
-  if (p.smem > 48 * 1024) {
+  const size_t smem = std::max(p.smem, static_cast<size_t>(F::NT) * kRedStageBytes);
+  if (smem > 48 * 1024) {
     static bool attr_done = false;   // per instantiation
     if (!attr_done) {
-      RG_CUDA(cudaFuncSetAttribute(colreduce_stage1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      RG_CUDA(cudaFuncSetAttribute(colreduce_stage1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr_done = true;
     }
   }
-  colreduce_stage1<F><<<p.blocks, 256, p.smem, st>>>(f, M, C, p.rows_per_block, ws);
+  colreduce_stage1<F><<<p.blocks, 256, smem, st>>>(f, M, C, p.rows_per_block, ws);
   RG_LAUNCH_CHECK(name);
   colreduce_stage2<<<ceil_div(K * C, 32), 1024, 0, st>>>(ws, p.blocks, K * C, out);
   RG_LAUNCH_CHECK(name);
@@ -229,13 +302,79 @@ static int run_ew(F f, int M, int C, cudaStream_t st, const char* name) {
   return 0;
 }
 
+// Same driver for functors with the load / apply split (`In load(row, c0)`, `void apply(const In&, row, c0)`):
+// four rows of loads are issued before the first store.
+template <class F>
+__global__ void __launch_bounds__(256) ew_split_kernel(F f, unsigned nvec, int cgs, int cg_shift) {
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg_shift >= 0) {
+    const int c0 = static_cast<int>(i0 & static_cast<unsigned>(cgs - 1)) * 8;
+    unsigned i = i0;
+    for (; static_cast<unsigned long long>(i) + 3ull * stride < nvec; i += 4 * stride) {
+      const size_t ra = i >> cg_shift, rb = (i + stride) >> cg_shift, rc = (i + 2 * stride) >> cg_shift,
+                   rd = (i + 3 * stride) >> cg_shift;
+      const typename F::In d0 = f.load(ra, c0);
+      const typename F::In d1 = f.load(rb, c0);
+      const typename F::In d2 = f.load(rc, c0);
+      const typename F::In d3 = f.load(rd, c0);
+      f.apply(d0, ra, c0);
+      f.apply(d1, rb, c0);
+      f.apply(d2, rc, c0);
+      f.apply(d3, rd, c0);
+    }
+    for (; i < nvec && i >= i0; i += stride) {
+      const size_t ra = i >> cg_shift;
+      const typename F::In d0 = f.load(ra, c0);
+      f.apply(d0, ra, c0);
+      if (i + stride < i) break;   // 32-bit wrap
+    }
+  } else {
+    for (unsigned i = i0; i < nvec; i += stride) {
+      const unsigned row = i / static_cast<unsigned>(cgs);
+      const int c0 = static_cast<int>(i - row * cgs) * 8;
+      const typename F::In d0 = f.load(static_cast<size_t>(row), c0);
+      f.apply(d0, static_cast<size_t>(row), c0);
+      if (i + stride < i) break;
+    }
+  }
+}
+template <class F>
+static int run_ew_split(F f, int M, int C, cudaStream_t st, const char* name) {
+  if (C % 8 != 0 || M <= 0) {
+    set_error("%s: need C %% 8 == 0 and M > 0 (M=%d C=%d)", name, M, C);
+    return RG_EINVAL;
+  }
+  const size_t nvec = static_cast<size_t>(M) * (C / 8);
+  if (nvec >= (1ull << 31)) {
+    set_error("%s: tensor too large for 32-bit vector indexing (%zu vectors)", name, nvec);
+    return RG_EINVAL;
+  }
+  const int cgs = C / 8;
+  // 4 rows per thread per trip: a grid of ~4 CTAs per SM still covers the tensor in a few trips
+  int grid = static_cast<int>(std::min<size_t>((nvec + 1023) / 1024, static_cast<size_t>(num_sms()) * 8));
+  grid = std::max(grid, 1);
+  int shift = -1;
+  if (is_pow2(cgs)) {
+    const int mult = std::max(1, cgs / 256);             // stride = grid*256 must be a multiple of cgs
+    grid = std::max(mult, grid / mult * mult);
+    shift = 0;
+    while ((1 << shift) < cgs) ++shift;
+  }
+  ew_split_kernel<F><<<grid, 256, 0, st>>>(f, static_cast<unsigned>(nvec), cgs, shift);
+  RG_LAUNCH_CHECK(name);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ BN functors
 struct StatsF {   // sum a, sum a^2
   static constexpr int K = 2;
+  static constexpr int NT = 1;
   const __nv_bfloat16* a;
   int C;
-  __device__ void operator()(size_t row, int c0, float (&acc)[2][8]) const {
-    const Vec8 x = ld8(a + row * C + c0);
+  __device__ __forceinline__ const __nv_bfloat16* ptr(int) const { return a; }
+  __device__ __forceinline__ void acc(const uint4 (&d)[1], int, float (&acc)[2][8]) const {
+    const Vec8 x = unpack8(d[0]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       acc[0][e] += x.v[e];
@@ -245,14 +384,16 @@ struct StatsF {   // sum a, sum a^2
 };
 
 struct BnActF {   // h = lrelu(scale*a + shift)
+  struct In { uint4 x; };
   const __nv_bfloat16* a;
   __nv_bfloat16* h;
   const float* scale;
   const float* shift;
   float slope;
   int C;
-  __device__ void operator()(size_t row, int c0) const {
-    const Vec8 x = ld8(a + row * C + c0);
+  __device__ __forceinline__ In load(size_t row, int c0) const { return In{ldu4(a + row * C + c0)}; }
+  __device__ __forceinline__ void apply(const In& d, size_t row, int c0) const {
+    const Vec8 x = unpack8(d.x);
     const Vec8 sc = ldf8(scale + c0), sh = ldf8(shift + c0);
     Vec8 o;
 #pragma unroll
@@ -267,13 +408,15 @@ struct BnActF {   // h = lrelu(scale*a + shift)
 // du = dh * lrelu'(u), u = scale*a + shift, xhat = (a - mean) * rstd
 struct BwdReduceF {   // S(du), S(du*xhat)
   static constexpr int K = 2;
+  static constexpr int NT = 2;
   const __nv_bfloat16* dh;
   const __nv_bfloat16* a;
   const float *mean, *rstd, *scale, *shift;
   float slope;
   int C;
-  __device__ void operator()(size_t row, int c0, float (&acc)[2][8]) const {
-    const Vec8 g = ld8(dh + row * C + c0), x = ld8(a + row * C + c0);
+  __device__ __forceinline__ const __nv_bfloat16* ptr(int t) const { return t == 0 ? dh : a; }
+  __device__ __forceinline__ void acc(const uint4 (&d)[2], int c0, float (&acc)[2][8]) const {
+    const Vec8 g = unpack8(d[0]), x = unpack8(d[1]);
     const Vec8 mu = ldf8(mean + c0), rs = ldf8(rstd + c0), sc = ldf8(scale + c0), sh = ldf8(shift + c0);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -286,6 +429,7 @@ struct BwdReduceF {   // S(du), S(du*xhat)
 };
 
 struct BwdApplyF {   // da = scale*(du - s1/M - xhat*s2/M) (+ add); optional du output
+  struct In { uint4 g, x, ad; };
   const __nv_bfloat16* dh;
   const __nv_bfloat16* a;
   const __nv_bfloat16* add;
@@ -294,9 +438,17 @@ struct BwdApplyF {   // da = scale*(du - s1/M - xhat*s2/M) (+ add); optional du 
   const float *mean, *rstd, *scale, *shift, *sums;   // sums[0][C] = S(du), sums[1][C] = S(du*xhat)
   float slope, invM;
   int C;
-  __device__ void operator()(size_t row, int c0) const {
+  __device__ __forceinline__ In load(size_t row, int c0) const {
     const size_t off = row * C + c0;
-    const Vec8 g = ld8(dh + off), x = ld8(a + off);
+    In d;
+    d.g = ldu4(dh + off);
+    d.x = ldu4(a + off);
+    d.ad = add ? ldu4(add + off) : make_uint4(0u, 0u, 0u, 0u);
+    return d;
+  }
+  __device__ __forceinline__ void apply(const In& in, size_t row, int c0) const {
+    const size_t off = row * C + c0;
+    const Vec8 g = unpack8(in.g), x = unpack8(in.x), ad = unpack8(in.ad);
     const Vec8 mu = ldf8(mean + c0), rs = ldf8(rstd + c0), sc = ldf8(scale + c0), sh = ldf8(shift + c0);
     const Vec8 s1 = ldf8(sums + c0), s2 = ldf8(sums + C + c0);
     Vec8 o, d;
@@ -306,12 +458,7 @@ struct BwdApplyF {   // da = scale*(du - s1/M - xhat*s2/M) (+ add); optional du 
       const float du = u > 0.0f ? g.v[e] : g.v[e] * slope;
       const float xh = (x.v[e] - mu.v[e]) * rs.v[e];
       d.v[e] = du;
-      o.v[e] = sc.v[e] * (du - s1.v[e] * invM - xh * s2.v[e] * invM);
-    }
-    if (add) {
-      const Vec8 ad = ld8(add + off);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o.v[e] += ad.v[e];
+      o.v[e] = sc.v[e] * (du - s1.v[e] * invM - xh * s2.v[e] * invM) + ad.v[e];
     }
     st8(da + off, o);
     if (du_out) st8(du_out + off, d);
@@ -319,27 +466,32 @@ struct BwdApplyF {   // da = scale*(du - s1/M - xhat*s2/M) (+ add); optional du 
 };
 
 struct LreluBwdF {   // da = dh * lrelu'(h)   (layer without BatchNorm: mask from the stored activation)
+  struct In { uint4 g, x; };
   const __nv_bfloat16* dh;
   const __nv_bfloat16* h;
   __nv_bfloat16* da;
   float slope;
   int C;
-  __device__ void operator()(size_t row, int c0) const {
-    const size_t off = row * C + c0;
-    const Vec8 g = ld8(dh + off), x = ld8(h + off);
+  __device__ __forceinline__ In load(size_t row, int c0) const {
+    return In{ldu4(dh + row * C + c0), ldu4(h + row * C + c0)};
+  }
+  __device__ __forceinline__ void apply(const In& in, size_t row, int c0) const {
+    const Vec8 g = unpack8(in.g), x = unpack8(in.x);
     Vec8 o;
 #pragma unroll
     for (int e = 0; e < 8; ++e) o.v[e] = x.v[e] > 0.0f ? g.v[e] : g.v[e] * slope;
-    st8(da + off, o);
+    st8(da + row * C + c0, o);
   }
 };
 
 struct ColSumF {   // S(x)
   static constexpr int K = 1;
+  static constexpr int NT = 1;
   const __nv_bfloat16* x;
   int C;
-  __device__ void operator()(size_t row, int c0, float (&acc)[1][8]) const {
-    const Vec8 v = ld8(x + row * C + c0);
+  __device__ __forceinline__ const __nv_bfloat16* ptr(int) const { return x; }
+  __device__ __forceinline__ void acc(const uint4 (&d)[1], int, float (&acc)[1][8]) const {
+    const Vec8 v = unpack8(d[0]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[0][e] += v.v[e];
   }
@@ -348,14 +500,15 @@ struct ColSumF {   // S(x)
 // gradient-penalty double backward through BatchNorm: ggI = adjoint of da, gO = du
 struct GpReduceF {   // S(ggI), S(ggI*xhat), S(ggI*gO)
   static constexpr int K = 3;
+  static constexpr int NT = 3;
   const __nv_bfloat16* ggI;
   const __nv_bfloat16* a;
   const __nv_bfloat16* gO;
   const float *mean, *rstd;
   int C;
-  __device__ void operator()(size_t row, int c0, float (&acc)[3][8]) const {
-    const size_t off = row * C + c0;
-    const Vec8 gi = ld8(ggI + off), x = ld8(a + off), go = ld8(gO + off);
+  __device__ __forceinline__ const __nv_bfloat16* ptr(int t) const { return t == 0 ? ggI : (t == 1 ? a : gO); }
+  __device__ __forceinline__ void acc(const uint4 (&d)[3], int c0, float (&acc)[3][8]) const {
+    const Vec8 gi = unpack8(d[0]), x = unpack8(d[1]), go = unpack8(d[2]);
     const Vec8 mu = ldf8(mean + c0), rs = ldf8(rstd + c0);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -369,6 +522,7 @@ struct GpReduceF {   // S(ggI), S(ggI*xhat), S(ggI*gO)
 struct GpApplyF {
   // A_dh = lrelu'(u) * gamma*r/M*(M*ggI - q1 - xhat*q2)
   // A_a  = gamma*r^2/M * [ xhat*(q1*s1/M - q3 + 3*s2*q2/M) + q2*(s1/M - gO) + s2*(q1/M - ggI) ]
+  struct In { uint4 gi, x, go; };
   const __nv_bfloat16* ggI;
   const __nv_bfloat16* a;
   const __nv_bfloat16* gO;
@@ -377,9 +531,13 @@ struct GpApplyF {
   const float *mean, *rstd, *gamma, *scale, *shift, *s, *q;   // s[2][C], q[3][C]
   float slope, invM;
   int C;
-  __device__ void operator()(size_t row, int c0) const {
+  __device__ __forceinline__ In load(size_t row, int c0) const {
     const size_t off = row * C + c0;
-    const Vec8 gi = ld8(ggI + off), x = ld8(a + off), go = ld8(gO + off);
+    return In{ldu4(ggI + off), ldu4(a + off), ldu4(gO + off)};
+  }
+  __device__ __forceinline__ void apply(const In& in, size_t row, int c0) const {
+    const size_t off = row * C + c0;
+    const Vec8 gi = unpack8(in.gi), x = unpack8(in.x), go = unpack8(in.go);
     const Vec8 mu = ldf8(mean + c0), rs = ldf8(rstd + c0), ga = ldf8(gamma + c0), sc = ldf8(scale + c0),
                sh = ldf8(shift + c0);
     const Vec8 s1 = ldf8(s + c0), s2 = ldf8(s + C + c0);
@@ -1195,7 +1353,7 @@ int rg_bn_act(const void* a, const float* scale, const float* shift, float slope
               rg_stream_t st) {
   RG_CHECK_ARG(a && scale && shift && h, "rg_bn_act: null pointer");
   BnActF f{static_cast<const bf16*>(a), static_cast<bf16*>(h), scale, shift, slope, C};
-  return run_ew(f, M, C, static_cast<cudaStream_t>(st), "rg_bn_act");
+  return run_ew_split(f, M, C, static_cast<cudaStream_t>(st), "rg_bn_act");
 }
 
 int rg_bn_bwd_reduce(const void* dh, const void* a, const float* mean, const float* rstd, const float* scale,
@@ -1213,7 +1371,7 @@ int rg_bn_bwd_apply(const void* dh, const void* a, const void* add, const float*
   RG_CHECK_ARG(dh && a && mean && rstd && scale && shift && sums && da, "rg_bn_bwd_apply: null pointer");
   BwdApplyF f{static_cast<const bf16*>(dh), static_cast<const bf16*>(a), static_cast<const bf16*>(add),
               static_cast<bf16*>(da), static_cast<bf16*>(du_out), mean, rstd, scale, shift, sums, slope, 1.0f / M, C};
-  return run_ew(f, M, C, static_cast<cudaStream_t>(st), "rg_bn_bwd_apply");
+  return run_ew_split(f, M, C, static_cast<cudaStream_t>(st), "rg_bn_bwd_apply");
 }
 
 int rg_bn_param_grads(const float* sums, float* dgamma, float* dbeta, int C, float acc_gamma, float acc_beta,
@@ -1228,7 +1386,7 @@ int rg_bn_param_grads(const float* sums, float* dgamma, float* dbeta, int C, flo
 int rg_lrelu_bwd(const void* dh, const void* h, float slope, void* da, int M, int C, rg_stream_t st) {
   RG_CHECK_ARG(dh && h && da, "rg_lrelu_bwd: null pointer");
   LreluBwdF f{static_cast<const bf16*>(dh), static_cast<const bf16*>(h), static_cast<bf16*>(da), slope, C};
-  return run_ew(f, M, C, static_cast<cudaStream_t>(st), "rg_lrelu_bwd");
+  return run_ew_split(f, M, C, static_cast<cudaStream_t>(st), "rg_lrelu_bwd");
 }
 
 int rg_col_sum(const void* x, int M, int C, void* ws, size_t ws_bytes, float* tmp, float* out, float acc,
@@ -1260,7 +1418,7 @@ int rg_bn_gp_apply(const void* ggI, const void* a, const void* gO, const float* 
   GpApplyF f{static_cast<const bf16*>(ggI), static_cast<const bf16*>(a), static_cast<const bf16*>(gO),
              static_cast<bf16*>(A_dh), static_cast<bf16*>(A_a), mean, rstd, gamma, scale, shift, s, q, slope,
              1.0f / M, C};
-  int rc = run_ew(f, M, C, st, "rg_bn_gp_apply");
+  int rc = run_ew_split(f, M, C, st, "rg_bn_gp_apply");
   if (rc) return rc;
   if (dgamma) {
     bn_gp_dgamma_kernel<<<ceil_div(C, 256), 256, 0, st>>>(s, q, rstd, dgamma, C, 1.0f / M, dgamma_acc);
