@@ -46,8 +46,24 @@ def measured_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(family):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None when absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        key = "gemm_fwd_kernel" if family == "fwd_dgrad" else "gemm_wgrad_kernel"
+        for name, v in d.get("kernels", {}).items():
+            if key in name:
+                return v.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -63,7 +79,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                                          "-lms", "50", "-i", str(self.idx)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -243,7 +259,7 @@ def run_ours(args, rank, world, local_rank):
         d[1] += a.elapsed_time(b)
         d[2] += 1
     fam = {"fwd_dgrad": ("conv_down", "conv_up"), "wgrad": ("conv_wgrad",),
-           "edge_hbm_bound": ("conv_up_img", "gemm_nt", "gemm_tn", "proj_wgrad")}
+           "edge_hbm_bound": ("conv_up_img", "gemm_nt", "gemm_nn", "gemm_tn", "proj_wgrad")}
     fam_stats = {}
     for name, kinds in fam.items():
         fl = sum(agg[k][0] for k in kinds if k in agg)
@@ -257,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "tensor",
                 "kernel": "rg::gemm_fwd_kernel (conv fprop/dgrad)" if dom == "fwd_dgrad" else "rg::gemm_wgrad_kernel",
                 "achieved": ds["tflops"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": ds["tflops"] / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["source"],
+                "frac": ds["tflops"] / peaks["bf16_sustained"], "traffic": ncu_traffic(dom), "peak_source": peaks["source"],
                 "avg_launch_ms": ds["ms_per_step"] / ds["launches_per_step"],
                 "algorithmic_gflop_per_launch": ds["gflop_per_launch"], "share_of_step": ds["ms_per_step"] / ms_step,
                 "families": fam_stats,

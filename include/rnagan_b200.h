@@ -95,7 +95,8 @@ size_t rg_proj_wgrad_ws_bytes(int B, int E, int C0);
 int rg_proj_wgrad(const void* z, const void* da0, float* dW, void* ws, size_t ws_bytes, int B, int E, int C0,
                   float alpha, const float* alpha_dev, float beta, int native_layout, rg_stream_t st);
 /* C[M,N] = act((A[M,K] . Bw[N,K]^T) * col_scale + col_shift); A, Bw bf16 row-major (K multiple of 64), C bf16 or
- * fp32 with leading dimension ldc.  nn.Linear(+eval BatchNorm1d+LeakyReLU) of the encoder (src/betaVAE.py:29-36),
+ * fp32 with leading dimension ldc.  out_f32 is a flag word: bit 0 = fp32 output, bit 1 = tanh instead of LeakyReLU
+ * (fp32 output only; the betaVAE decoder's Linear + Tanh, src/betaVAE.py:92).  nn.Linear(+eval BatchNorm1d+LeakyReLU) of the encoder (src/betaVAE.py:29-36),
  * generator layer 0 (src/dcgan.py:38-40), image-side im2col GEMMs. */
 int rg_gemm_nt(const void* A, const void* Bw, void* C, int M, int N, int K, int ldc, const float* col_scale,
                const float* col_shift, float slope, int out_f32, rg_stream_t st);

@@ -80,9 +80,28 @@ class betaVAE(nn.Module):
         self.__dict__["_rg_train_versions"] = vers
         return eng
 
+    def _dec_engine(self):
+        p0 = next(self.parameters())
+        if p0.device.type != "cuda":
+            raise RuntimeError("betaVAE.decode runs only on a CUDA (sm_100a) device: there is no CPU fallback")
+        if self.training:
+            raise NotImplementedError("betaVAE.decode / forward / sample run in eval mode on the sm_100a path "
+                                      "(running BatchNorm statistics); training goes through betaVAE.train_step")
+        vers = tuple((p.data_ptr(), p._version) for p in self.decoder.state_dict().values())
+        eng = self.__dict__.get("_rg_dec_engine")
+        if eng is None or eng.device != p0.device:
+            eng = _engine.DecoderEngine(self)
+            self.__dict__["_rg_dec_engine"] = eng
+        elif vers != self.__dict__.get("_rg_dec_versions") or self.__dict__.get("_rg_dec_dirty", False):
+            eng.refresh()
+        self.__dict__["_rg_dec_versions"] = vers
+        self.__dict__["_rg_dec_dirty"] = False
+        return eng
+
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.pop("_rg_engine", None)
         self.__dict__.pop("_rg_train_engine", None)
+        self.__dict__.pop("_rg_dec_engine", None)
         return super()._apply(fn, *args, **kwargs)
 
     # -- reference API -----------------------------------------------------------------------------------------
@@ -103,14 +122,27 @@ class betaVAE(nn.Module):
         std = torch.exp(0.5 * z_log_var)
         return z_mean + torch.randn_like(std) * std
 
+    @torch.no_grad()
     def decode(self, x):
-        raise NotImplementedError("betaVAE decoder (config 5, VAE training/sampling) is not on the sm_100a path yet")
+        """src/betaVAE.py:142-143 (eval mode): tanh(decoder(x)) on the tcgen05 GEMMs."""
+        eng = self._dec_engine()
+        return eng.decode(x.to(device=eng.device, dtype=torch.float32))
 
+    @torch.no_grad()
     def forward(self, x):
-        raise NotImplementedError("betaVAE.forward (config 5, VAE training) is not on the sm_100a path yet")
+        """src/betaVAE.py:109-115 (eval mode): (decoder(reparametrize(z_mean, z_log_var)), z_mean, z_log_var)."""
+        z_mean, z_log_var, _ = self.encode(x)
+        z = self.reparametrize(z_mean, z_log_var)
+        return self.decode(z), z_mean, z_log_var
 
+    @torch.no_grad()
     def sample(self, num_samples, current_device, interpolation=None, alpha=1.0):
-        raise NotImplementedError("betaVAE.sample is not on the sm_100a path yet")
+        """src/betaVAE.py:117-140: decode CPU-drawn N(0, I) latents (+ alpha * interpolation)."""
+        z = torch.randn(num_samples, self.z_dim)
+        z = z.to(current_device)
+        if interpolation is not None:
+            z = z + torch.from_numpy(alpha * interpolation).float().to(current_device)
+        return self.decode(z)
 
 
 def betaVAEloss(x, x_recons, z_mean, z_logvar, beta, kld_weight=0.005, training=True):
@@ -137,6 +169,7 @@ def train_step(model, optimizer, x, beta, keep_mask=None, eps=None):
     adam_step(optimizer, grad_scale=eng.sync.finish())
     eng.pack()
     model.__dict__["_rg_dirty"] = True
+    model.__dict__["_rg_dec_dirty"] = True
     return out3
 
 

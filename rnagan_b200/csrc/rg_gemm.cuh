@@ -567,6 +567,9 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
         if (OUT == OUT_F32_NCHW && p.act_tanh) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = __float_as_uint(tanhf(__uint_as_float(v[e])));
+        } else if (OUT == OUT_F32_NHWC && p.act_tanh) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(tanhf(__uint_as_float(v[e])));
         } else if (lrelu) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {

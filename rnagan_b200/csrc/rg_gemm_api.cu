@@ -771,6 +771,9 @@ static int gemm_plain(const void* A, int lda, const void* Bw, int ldb, bool b_is
   a.chunks = ceil_div(K, 64);
   Tap t = {0, 0, 0, 0};
   a.taps[0][0] = t;
+  const int out_tanh = (out_f32 & 2) ? 1 : 0;     // out_f32 is a flag word: bit 0 fp32 output, bit 1 tanh (fp32 only)
+  out_f32 &= 1;
+  RG_CHECK_ARG(!out_tanh || out_f32, "%s: the tanh epilogue needs an fp32 output", name);
   const int out_kind = out_f32 ? OUT_F32_NHWC : OUT_BF16_NHWC;
   a.n_total = N;
   a.block_n = pick_block_n(N, a.m_tiles, pair_allowed(a, out_kind) ? 2 : 1);
@@ -792,6 +795,7 @@ static int gemm_plain(const void* A, int lda, const void* Bw, int ldb, bool b_is
   a.col_scale = col_scale;
   a.col_shift = col_shift;
   a.slope = slope;
+  a.act_tanh = out_tanh;
   return launch_fwd(maps, a, out_kind, cg, nullptr, st);
 }
 

@@ -737,6 +737,54 @@ class EncoderEngine:
         return z, lv, h[:, :self.layers[-1][4]].float()
 
 
+# ====================================================================================================== decoder
+class DecoderEngine:
+    """Eval-mode betaVAE decoder (src/betaVAE.py:80-92, used by decode / forward / sample, :109-143):
+    [Linear + eval BatchNorm1d + LeakyReLU(0.01)] per hidden layer folded into GEMM epilogues, then Linear + Tanh
+    (tanh in the fp32 epilogue)."""
+
+    def __init__(self, vae):
+        dev = next(vae.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("DecoderEngine needs the betaVAE on a CUDA device (there is no CPU path)")
+        self.device, self.vae = dev, vae
+        self.bufs = _Bufs(dev)
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        blocks = list(self.vae.decoder)
+        self.layers = []
+        for blk in blocks[:-1]:
+            lin, bn = blk[0], blk[1]
+            Kp = (lin.weight.shape[1] + 63) // 64 * 64
+            w = ops.cast_pad_bf16(lin.weight.detach().contiguous(), Kp)
+            scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+            shift = ((lin.bias - bn.running_mean) * scale + bn.bias).float().contiguous()
+            self.layers.append((w, scale, shift, blk[2].negative_slope, lin.weight.shape[0], Kp))
+        last = blocks[-1][0]
+        self.F = last.weight.shape[0]
+        self.Fp = (self.F + 3) // 4 * 4
+        self.w_last = ops.cast_pad_bf16(last.weight.detach().contiguous(), (last.weight.shape[1] + 63) // 64 * 64)
+        self.b_last = last.bias.detach().float().contiguous()
+
+    def decode(self, z):
+        """z: fp32 [B, z_dim] on the device -> tanh(decoder(z)) fp32 [B, in_channels]."""
+        B = z.shape[0]
+        g = self.bufs.get
+        K0 = self.layers[0][5] if self.layers else self.w_last.shape[1]
+        h = g("z", (B, K0), zero=True)
+        ops.cast_pad_bf16(z.contiguous(), K0, out=h)
+        for i, (w, scale, shift, slope, N, Kp) in enumerate(self.layers):
+            Np = (N + 63) // 64 * 64
+            o = g(f"h{i}", (B, Np), zero=True)
+            ops.gemm_nt(h, w, out=o, col_scale=scale, col_shift=shift, slope=slope, N=N)
+            h = o
+        out = g("out", (B, self.Fp), F32)
+        ops.gemm_nt(h, self.w_last, out=out, col_shift=self.b_last, N=self.F, tanh=True)
+        return out[:, :self.F].clone()
+
+
 # ====================================================================================================== VAE training
 class VAETrainEngine:
     """betaVAE training step (BASELINE config 5; inner step of train_betaVAE, src/betaVAE.py:216-236):

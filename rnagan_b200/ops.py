@@ -216,7 +216,7 @@ def proj_wgrad(z, da0, dW, alpha=1.0, alpha_dev=None, beta=0.0):
     return dW
 
 
-def gemm_nt(A, Bw, out=None, col_scale=None, col_shift=None, slope=1.0, out_f32=False, N=None, K=None):
+def gemm_nt(A, Bw, out=None, col_scale=None, col_shift=None, slope=1.0, out_f32=False, N=None, K=None, tanh=False):
     """C[M, N] = lrelu((A[M, K] @ Bw[N, K]^T) * col_scale + col_shift); rows of A / Bw / out may be strided."""
     _chk(A, BF16, "A", True); _chk(Bw, BF16, "Bw", True)
     M = A.shape[0]
@@ -226,7 +226,8 @@ def gemm_nt(A, Bw, out=None, col_scale=None, col_shift=None, slope=1.0, out_f32=
         out = torch.empty(M, N, dtype=torch.float32 if out_f32 else BF16, device=A.device)
     _prof("gemm_nt", 2.0 * M * N * K, lambda: _lib.check(
         _lib.lib().rg_gemm_nt_ld(_p(A), A.stride(0), _p(Bw), Bw.stride(0), _p(out), M, N, K, out.stride(0),
-                                 _p(col_scale), _p(col_shift), float(slope), int(out.dtype == torch.float32), _st()),
+                                 _p(col_scale), _p(col_shift), float(slope),
+                                 int(out.dtype == torch.float32) | (2 if tanh else 0), _st()),
         "rg_gemm_nt_ld"))
     return out
 

@@ -53,26 +53,50 @@ class Trainer:
             setattr(self, k, v)
 
     def _call(self, name):
+        """Run one loss object's optimiser step.  Loss objects of this package expose ``device_ops`` (train_ops minus
+        the ``.item()``): their losses stay on the device and the whole iteration is read back with one
+        synchronisation in train_iter; any other loss object goes through the reference's ``train_ops`` -> float."""
         loss = self.losses[name]
-        return loss.train_ops(**{a: getattr(self, a) for a in self.loss_arg_maps[name]})
+        kwargs = {a: getattr(self, a) for a in self.loss_arg_maps[name]}
+        fn = getattr(loss, "device_ops", None)
+        return fn(**kwargs) if fn is not None else loss.train_ops(**kwargs)
+
+    def _read_back(self, pending):
+        """{name: device tensor [1] | float} -> {name: float} with a single device->host copy + synchronisation."""
+        dev = [(n, v) for n, v in pending.items() if torch.is_tensor(v)]
+        out = {n: v for n, v in pending.items() if not torch.is_tensor(v)}
+        if dev:
+            if getattr(self, "_loss_pinned", None) is None or self._loss_pinned.numel() < len(dev):
+                self._loss_pinned = torch.empty(max(8, len(dev)), dtype=torch.float32).pin_memory()
+            for i, (_, v) in enumerate(dev):
+                self._loss_pinned[i:i + 1].copy_(v.reshape(1), non_blocking=True)
+            torch.cuda.current_stream(dev[0][1].device).synchronize()
+            for i, (n, _) in enumerate(dev):
+                out[n] = float(self._loss_pinned[i])
+        return out
 
     def train_iter(self):
         lgen = ldis = 0.0
         gen_iter = dis_iter = 0
-        values = {}
+        pending, kinds = {}, {}
         for name, loss in self.losses.items():
             if isinstance(loss, GeneratorLoss):
                 if self.loss_information["discriminator_iters"] % self.ncritic == 0:
-                    v = self._call(name)
-                    lgen += v
-                    gen_iter += 1
-                    values[name] = v
+                    pending[name] = self._call(name)
+                    kinds[name] = "g"
             elif isinstance(loss, DiscriminatorLoss):
-                v = self._call(name)
+                pending[name] = self._call(name)
+                kinds[name] = "d"
+        values = self._read_back(pending)
+        for name in self.losses:
+            v = values.get(name)
+            if kinds.get(name) == "g":
+                lgen += v
+                gen_iter += 1
+            elif kinds.get(name) == "d":
                 ldis += v
                 dis_iter += 1
-                values[name] = v
-            self.loss_logs.setdefault(name, []).append(values.get(name))
+            self.loss_logs.setdefault(name, []).append(v)
         self.loss_information["generator_losses"] += lgen
         self.loss_information["discriminator_losses"] += ldis
         self.loss_information["generator_iters"] += gen_iter

@@ -125,14 +125,17 @@ class _VAEConditioned:
         self._prefetch_real(real_inputs, device)
         eng = generator._engine()
         E = generator.encoding_dims
+        # one pinned staging buffer and one device buffer PER LOSS OBJECT: Trainer.train_iter defers the three host
+        # synchronisations of an iteration to its end, so a step's asynchronous copy may still be in flight when the
+        # next step draws its noise; the same object runs again only after that end-of-iteration synchronisation
         stage = eng.bufs.__dict__.setdefault("_noise_pinned", {})
-        pinned = stage.get((B, E))
+        pinned = stage.get((id(self), B, E))
         if pinned is None:
             pinned = torch.empty(B, E, dtype=F32).pin_memory()
-            stage[(B, E)] = pinned
+            stage[(id(self), B, E)] = pinned
         pinned.uniform_(-0.3, 0.3)                 # same CPU generator stream as torch.FloatTensor(B, E).uniform_()
-        noise_d = eng.bufs.get("noise", (B, E), F32)
-        noise_d.copy_(pinned, non_blocking=True)   # every train_ops ends with .item(): the copy is done before reuse
+        noise_d = eng.bufs.get(f"noise.{type(self).__name__}", (B, E), F32)
+        noise_d.copy_(pinned, non_blocking=True)
         return noise_d, z
 
     @staticmethod
@@ -180,10 +183,15 @@ class WassersteinGeneratorLossVAE(_VAEConditioned, GeneratorLoss):
         return wasserstein_generator_loss_vae(fgz, self.reduction)
 
     def train_ops(self, generator, discriminator, optimizer_generator, device, batch_size, real_inputs, labels=None):
+        return self.device_ops(generator, discriminator, optimizer_generator, device, batch_size, real_inputs,
+                               labels).item()
+
+    def device_ops(self, generator, discriminator, optimizer_generator, device, batch_size, real_inputs, labels=None):
+        """train_ops without the host read-back: returns the loss as a device tensor [1] (Trainer.train_iter reads
+        the three losses of an iteration with ONE synchronisation at its end)."""
         _check_labels(labels, generator)
         noise_d, z = self._inputs(generator, real_inputs, device)
-        loss = steps.g_step(generator, discriminator, optimizer_generator, noise_d, z)
-        return loss.item()
+        return steps.g_step(generator, discriminator, optimizer_generator, noise_d, z)
 
 
 class WassersteinDiscriminatorLossVAE(_VAEConditioned, DiscriminatorLoss):
@@ -196,11 +204,13 @@ class WassersteinDiscriminatorLossVAE(_VAEConditioned, DiscriminatorLoss):
         return wasserstein_discriminator_loss_vae(fx, fgz, self.reduction)
 
     def train_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
+        return self.device_ops(generator, discriminator, optimizer_discriminator, real_inputs, device, labels).item()
+
+    def device_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
         _check_labels(labels, generator, discriminator)
         noise_d, z = self._inputs(generator, real_inputs, device)
         real = self._real(real_inputs, device)
-        loss = steps.critic_step(generator, discriminator, optimizer_discriminator, noise_d, z, real, clip=self.clip)
-        return loss.item()
+        return steps.critic_step(generator, discriminator, optimizer_discriminator, noise_d, z, real, clip=self.clip)
 
 
 class WassersteinGradientPenaltyVAE(_VAEConditioned, DiscriminatorLoss):
@@ -215,6 +225,9 @@ class WassersteinGradientPenaltyVAE(_VAEConditioned, DiscriminatorLoss):
                                   "(hand-scheduled double backward); there is no autograd graph to differentiate")
 
     def train_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
+        return self.device_ops(generator, discriminator, optimizer_discriminator, real_inputs, device, labels).item()
+
+    def device_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
         _check_labels(labels, generator, discriminator)
         noise_d, z = self._inputs(generator, real_inputs, device)
         real = self._real(real_inputs, device)
@@ -223,6 +236,6 @@ class WassersteinGradientPenaltyVAE(_VAEConditioned, DiscriminatorLoss):
         eps_d.copy_(eps)
         out3 = steps.gp_step(generator, discriminator, optimizer_discriminator, noise_d, z, real, eps_d,
                              lambd=self.lambd)
-        return out3[0].item()
+        return out3[0:1]
 
 
