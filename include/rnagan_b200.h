@@ -76,8 +76,12 @@ int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int
  * generator forward nn.ConvTranspose2d(4,2,1) (src/dcgan.py:52) and critic dgrad. */
 /* w: either w_up (w_is_down=0; K-major B, best for Cs <= 128 where the extra packed copy is tiny) or w_down
  * (w_is_down=1; read as an MN-major B operand, so large layers keep a single packed copy). */
+/* w_is_down = 2: w is the merged-phase operand of rg_pack_up9_from_down (Cs == 64, at least two 128-pixel M tiles): one
+ * tile then contracts all four output phases, fetching the 9 distinct shifted input tiles once instead of 16 times. */
 int rg_conv_up(const void* lo, const void* w, int w_is_down, void* hi, int B, int H, int W, int Cp, int Cs,
                float* stats_ws, rg_stream_t st);
+size_t rg_up9_elems(int Cp);
+int rg_pack_up9_from_down(const void* w_down, void* w_up9, int Cp, int Cs, rg_stream_t st);
 /* same as rg_conv_up for Cs<=16 image channels, fp32 NCHW output, optional bias + tanh
  * (generator last layer, src/dcgan.py:82; critic layer-0 dgrad). */
 int rg_conv_up_img(const void* lo, const void* w_up, float* img, const float* bias, int act_tanh, int B, int H,

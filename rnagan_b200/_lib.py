@@ -26,6 +26,8 @@ SIGNATURES = {
     "rg_pack_link": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "rg_pack_proj": (_i, [_vp, _vp, _i, _i, _vp]),
     "rg_pack_up_from_down": (_i, [_vp, _vp, _i, _i, _vp]),
+    "rg_up9_elems": (_sz, [_i]),
+    "rg_pack_up9_from_down": (_i, [_vp, _vp, _i, _i, _vp]),
     "rg_pack_edge": (_i, [_vp, _vp, _i, _i, _vp]),
     "rg_cast_pad_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rg_stats_ws_bytes": (_sz, [_i]),

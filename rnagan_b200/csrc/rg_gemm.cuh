@@ -68,6 +68,10 @@ struct FwdArgs {
   int b_stage_bytes;      // bytes of the B operand one CTA holds per stage ((block_n / CG) * 128)
   int tma_store;          // OUT_BF16_NHWC: tile leaves through swizzled smem slabs + TMA stores (whole 128-byte lines)
   int nbuf;               // staging slabs (1 or 2)
+  int merged;             // transposed form with ALL FOUR output phases in one tile (Cs == 64, CTA pairs): the 9 distinct
+                          // shifted A tiles of an M tile are fetched once instead of 16 times; TMEM slab q = phase q
+  int8_t mg_nph[9];       // merged: how many phases tap t9 = (dh+1)*3 + (dw+1) feeds (1, 2 or 4) ...
+  int8_t mg_phase[9][4];  // ... and which ones; their B slabs sit in this order in the stage (packed by rg_pack_up9)
   int whatif;             // profiling experiments (RG_WHATIF): 1 no MMA, 2 no epilogue work, 4 no A loads, 8 no B loads
   long long* prof;        // optional [gridDim.x][12] clock64 totals per role (tools/gemm_prof.py); null in production
   float* stats;           // optional [gridDim.x][2][n_total]: per-CTA column sums / sums of squares of the STORED
@@ -240,6 +244,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
   const uint32_t stage_tx = (((p.whatif & 4) ? 0u : static_cast<uint32_t>(p.rows_valid) * 128u) +
                              ((p.whatif & 8) ? 0u : static_cast<uint32_t>(p.b_stage_bytes))) * CG;
   const int bn_cta = p.block_n / CG;                // B rows (N columns) this CTA fetches
+  const int mg_rows = 64 / CG;                      // merged: rows of one phase's B slab held by this CTA
 
   if (warp == 0 || warp == 6) {
     // ===================================================== TMA producers (one elected lane each, in every CTA of the
@@ -252,7 +257,8 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
       const int chunks = p.chunks, num_taps = p.num_taps, num_phases = p.num_phases;
       const int tw = p.tw, th = p.th, bw = p.bw, bh = p.bh, bb = p.bb;
       const int block_n = p.block_n, b_phase_rows = p.b_phase_rows, b_tap_cols = p.b_tap_cols;
-      const bool a_2d = p.a_2d != 0, b_mn = p.b_mn != 0;
+      const bool a_2d = p.a_2d != 0, b_mn = p.b_mn != 0, merged = p.merged != 0;
+      const uint32_t a_tx = (p.whatif & 4) ? 0u : static_cast<uint32_t>(p.rows_valid) * 128u;
       const bool do_a = warp == 0 && (p.whatif & 4) == 0, do_b = warp == 6 && (p.whatif & 8) == 0;
       const bool prof = p.prof != nullptr && warp == 0;
       const int ns = bn_cta >> 6;
@@ -279,6 +285,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
         int kcol = 0;                                          // kb * 64: K coordinate of a K-major B
         for (int tap = 0; tap < num_taps; ++tap) {
           const Tap t = p.taps[ph][tap];
+          const int mg_n = merged ? p.mg_nph[tap] : 0;
           const uint64_t desc_a = desc_a0 + static_cast<uint64_t>(t.map) * sizeof(CUtensorMap);
           const int cj = j0 + t.dw, ci = i0 + t.dh;
           const int bcol = t.wtap * b_tap_cols + ncol0;
@@ -289,12 +296,18 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
             const uint32_t sa = ring0 + stage * stage_bytes;
             const uint32_t sb = sa + kAStageBytes;
             const uint32_t fb = full0_tx + stage * 8;
-            if (warp == 0 && crank == 0) mbar_expect_tx_raw(full0 + stage * 8, stage_tx);
+            if (warp == 0 && crank == 0)
+              mbar_expect_tx_raw(full0 + stage * 8, merged ? (a_tx + static_cast<uint32_t>(mg_n * mg_rows) * 128u) * CG
+                                                           : stage_tx);
             if (do_a) {
               if (a_2d) tma_ld_2d_raw<CG>(desc_a0, fb, sa, chunk * kBlockK, b0);
               else tma_ld_4d_raw<CG>(desc_a, fb, sa, chunk * kBlockK, cj, ci, b0);
             }
-            if (do_b) {
+            if (do_b && merged) {
+              // one box = the slabs of every phase this tap feeds (this CTA's half of their rows), contiguous in w_up9
+              const uint64_t d9 = mg_n == 4 ? desc_b : (mg_n == 2 ? desc_a0 + sizeof(CUtensorMap) : desc_a0 + 2 * sizeof(CUtensorMap));
+              tma_ld_2d_raw<CG>(d9, fb, sb, 0, ((tap * chunks + chunk) * CG + crank) * (4 * mg_rows));
+            } else if (do_b) {
               if (b_mn) {
                 // B^T slabs [64 k-rows = p][64 n = s] straight out of w_down: no second packed copy of the weights
                 for (int sl = 0; sl < ns; ++sl)
@@ -338,6 +351,35 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
         if (prof) t_wtempty += clock64() - c0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
+        if (p.merged) {
+          // 9 taps x chunks stages; each stage feeds 1, 2 or 4 phase accumulators (64 TMEM columns each)
+          const uint32_t idesc64 = make_idesc_bf16(kBlockM * CG, 64, 0, 0);
+          uint32_t used = 0;                    // phases that already hold a partial sum in this tile
+          for (int tap = 0; tap < p.num_taps; ++tap) {
+            const int nph = p.mg_nph[tap];
+            for (int chunk = 0; chunk < p.chunks; ++chunk) {
+              mbar_wait_raw(full0 + stage * 8, phase);
+              tc_fence_after();
+              const uint32_t sa = ring0 + stage * stage_bytes;
+              const uint64_t da = da0 | static_cast<uint64_t>((sa >> 4) & 0x3FFF);
+              for (int q = 0; q < nph; ++q) {
+                const int phq = p.mg_phase[tap][q];
+                const uint64_t db = db0 | static_cast<uint64_t>(((sa + kAStageBytes + q * mg_rows * 128) >> 4) & 0x3FFF);
+                const uint32_t first = (chunk == 0 && !((used >> phq) & 1u)) ? 1u : 0u;
+                if (!skip_mma) {
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma_bf16_cg<CG>(tmem_d + phq * 64, da + 2u * k, db + 2u * k, idesc64, (first && k == 0) ? 0u : 1u);
+                }
+              }
+              umma_commit_cg<CG>(&s.empty[stage]);
+              if (++stage == nstages) { stage = 0; phase ^= 1u; }
+            }
+            for (int q = 0; q < nph; ++q) used |= 1u << p.mg_phase[tap][q];
+          }
+          umma_commit_cg<CG>(&s.tfull[acc]);
+          continue;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           const long long c1 = prof ? clock64() : 0;
           mbar_wait_raw(full0 + stage * 8, phase);
@@ -524,13 +566,14 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
           fence_proxy_async();             // generic-proxy smem writes -> visible to the TMA (async proxy)
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (et == 0 && tile_ok) {
-            tma_store_4d(&maps.o[ph], buf, n0 + sl * 64, j0, i0, b0);
+            if (p.merged) tma_store_4d(&maps.o[sl], buf, 0, j0, i0, b0);      // slab = output phase, all 64 channels
+            else tma_store_4d(&maps.o[ph], buf, n0 + sl * 64, j0, i0, b0);
             bulk_commit();
           }
           if (do_stats) {                  // fixed-order sum of the four warps' partial column sums
             const float* ss = s.s_stat + st_k * 64 + st_c;
             const float t = ((ss[0] + ss[128]) + ss[256]) + ss[384];
-            if (sl == 0) st_acc[0] += t;
+            if (sl == 0 || p.merged) st_acc[0] += t;     // merged: the four slabs are four phases of the SAME channels
             else if (sl == 1) st_acc[1] += t;
             else if (sl == 2) st_acc[2] += t;
             else st_acc[3] += t;

@@ -225,7 +225,8 @@ static int launch_fwd(GemmMaps& maps, FwdArgs& a, int out_kind, int cg, float* s
   if (a.tma_store) {
     // per-phase output views: pixel (b, i*sy + oy, j*sx + ox), channels [0, n_valid); TMA clips what lies outside
     const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(a.out);
-    for (int ph = 0; ph < a.num_phases; ++ph) {
+    const int out_maps = a.merged ? 4 : a.num_phases;        // merged tiles store all four phase views
+    for (int ph = 0; ph < out_maps; ++ph) {
       const __nv_bfloat16* b0 = base + (static_cast<size_t>(a.oy[ph]) * a.OW + a.ox[ph]) * a.OC;
       rc = encode_map_4d(&maps.o[ph], b0, a.n_valid, a.W, a.H, a.nB, static_cast<uint64_t>(a.sx) * a.OC,
                          static_cast<uint64_t>(a.sy) * a.OW * a.OC, static_cast<uint64_t>(a.OH) * a.OW * a.OC, 64, a.bw,
@@ -346,17 +347,22 @@ __global__ void __launch_bounds__(256) wgrad_reduce_native_kernel(const float* _
   *dst = o;
 }
 
-// Split-K factor: minimise waves x (k-blocks per unit + per-unit epilogue cost); favours unit counts that fill whole
-// waves of the persistent grid (e.g. 64 tiles x 9 splits = 576 units = 3.9 waves instead of 192 = 1.3 waves).
-static void choose_splits(int units, int num_pb, int& splits, int& pb_per_split) {
+// Split-K factor: minimise waves x (k-blocks per unit + per-unit epilogue cost) + the cost of moving the fp32 partials
+// (every extra split writes and re-reads the whole gradient once).  Favours unit counts that fill whole waves of the
+// persistent grid without drowning a small-K layer in partial traffic (L3: 9 splits -> 151 MB of partials for an
+// 8 MB gradient; 4 splits run the MMAs 3 % longer and move 67 MB).
+static void choose_splits(int units, int num_pb, double out_bytes, int msub, int& splits, int& pb_per_split) {
   const int sms = num_sms();
+  // one pixel block = msub x 4 MMAs of 128x256x16 ~ msub x 0.34 us at the power-capped clock; partials stream at ~5 TB/s
+  const double pb_us = 0.34 * msub;
   double best = 1e30;
   int best_s = 1;
   for (int sp = 1; sp <= std::min(num_pb, 4 * sms); ++sp) {
     const int per = ceil_div(num_pb, sp);
     const int eff = ceil_div(num_pb, per);
     if (eff != sp) continue;
-    const double cost = static_cast<double>(ceil_div(units * sp, sms)) * (per + 4) + 0.05 * sp;
+    const double traffic_us = sp > 1 ? (2.0 * sp + 1.0) * out_bytes / 5.0e6 : 0.0;
+    const double cost = static_cast<double>(ceil_div(units * sp, sms)) * (per + 4) + traffic_us / pb_us + 0.05 * sp;
     if (cost < best) { best = cost; best_s = sp; }
   }
   splits = best_s;
@@ -380,7 +386,8 @@ static WgradGeom wgrad_geom(int B, int H, int W, int Cp, int Cs, int taps) {
   const int num_slabs = taps * w.chunks_s;
   w.slabs_per_tile = (num_slabs % 4 == 0) ? 4 : ((num_slabs % 2 == 0) ? 2 : 1);
   w.n_tiles = num_slabs / w.slabs_per_tile;
-  choose_splits(w.m_tiles * w.n_tiles, w.num_pb, w.splits, w.pb_per_split);
+  choose_splits(w.m_tiles * w.n_tiles, w.num_pb, static_cast<double>(taps) * Cp * Cs * sizeof(float), w.msub, w.splits,
+                w.pb_per_split);
   return w;
 }
 
@@ -515,6 +522,44 @@ __global__ void pack_up_from_down_kernel(const __nv_bfloat16* __restrict__ wd, _
           sm[tx][r];
   }
 }
+// Merged-phase operand of rg_conv_up (Cs == 64, CTA pairs): for every distinct input shift t9 = (dh+1)*3 + (dw+1) and
+// 64-channel chunk of Cp, the K-major slabs [64 s][64 p] of the output phases that shift feeds, split in two halves of
+// 32 output channels (one per CTA of the pair): out[t9][chunk][half][slot q][32 n][64 k], slots beyond the tap's phase
+// count zero.  Source: bf16 w_down[p][tap16*Cs + s].
+__global__ void pack_up9_kernel(const __nv_bfloat16* __restrict__ wd, __nv_bfloat16* __restrict__ out, int Cp, int Cs) {
+  const int chunks = Cp / 64;
+  const size_t total = static_cast<size_t>(9) * chunks * 2 * 4 * 32 * 64;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = static_cast<int>(idx & 63);
+  const int n = static_cast<int>((idx >> 6) & 31);
+  const int q = static_cast<int>((idx >> 11) & 3);
+  const int half = static_cast<int>((idx >> 13) & 1);
+  const int rest = static_cast<int>(idx >> 14);
+  const int chunk = rest % chunks, t9 = rest / chunks;
+  const int dh = t9 / 3 - 1, dw = t9 % 3 - 1;
+  // phases fed by this shift, in (rh, rw) order; row parity rh uses shift 0 (both) or -1 (rh = 0) / +1 (rh = 1)
+  int cnt = 0, rh_sel = -1, rw_sel = -1;
+  for (int rh = 0; rh < 2; ++rh)
+    for (int rw = 0; rw < 2; ++rw) {
+      const bool okh = dh == 0 || (dh == -1 && rh == 0) || (dh == 1 && rh == 1);
+      const bool okw = dw == 0 || (dw == -1 && rw == 0) || (dw == 1 && rw == 1);
+      if (okh && okw) {
+        if (cnt == q) { rh_sel = rh; rw_sel = rw; }
+        ++cnt;
+      }
+    }
+  float v = 0.0f;
+  __nv_bfloat16 o = __float2bfloat16(v);
+  if (rh_sel >= 0) {
+    // kernel index for (parity r, shift d): r = 0: d = 0 -> 1, d = -1 -> 3;  r = 1: d = 0 -> 2, d = +1 -> 0
+    const int kh = rh_sel == 0 ? (dh == 0 ? 1 : 3) : (dh == 0 ? 2 : 0);
+    const int kw = rw_sel == 0 ? (dw == 0 ? 1 : 3) : (dw == 0 ? 2 : 0);
+    const int prow = chunk * 64 + k, sidx = half * 32 + n;
+    o = wd[static_cast<size_t>(prow) * 16 * Cs + static_cast<size_t>(kh * 4 + kw) * Cs + sidx];
+  }
+  out[idx] = o;
+}
 // W[E][C0*16] fp32 -> out[(tap*C0 + co)][E] bf16 : 32x32 tile transpose
 __global__ void pack_proj_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int E, int C0) {
   __shared__ float sm[32][33];
@@ -615,6 +660,18 @@ int rg_pack_up_from_down(const void* w_down, void* w_up, int Cp, int Cs, rg_stre
   return 0;
 }
 
+size_t rg_up9_elems(int Cp) { return Cp > 0 && Cp % 64 == 0 ? static_cast<size_t>(9) * (Cp / 64) * 2 * 4 * 32 * 64 : 0; }
+
+int rg_pack_up9_from_down(const void* w_down, void* w_up9, int Cp, int Cs, rg_stream_t st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  RG_CHECK_ARG(w_down && w_up9 && Cp > 0 && Cp % 64 == 0 && Cs == 64, "rg_pack_up9_from_down: need Cs == 64, Cp %% 64 == 0");
+  const size_t total = rg_up9_elems(Cp);
+  pack_up9_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(w_down), static_cast<__nv_bfloat16*>(w_up9), Cp, Cs);
+  RG_LAUNCH_CHECK("pack_up9_kernel");
+  return 0;
+}
+
 int rg_pack_proj(const float* W, void* w_proj, int E, int C0, rg_stream_t st_) {
   cudaStream_t st = static_cast<cudaStream_t>(st_);
   RG_CHECK_ARG(W && w_proj && E > 0 && C0 > 0, "rg_pack_proj: bad arguments");
@@ -677,6 +734,57 @@ int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int
   return launch_fwd(maps, a, OUT_BF16_NHWC, cg, stats_ws, st);
 }
 
+// all four output phases of an M tile in one tile (weights packed by rg_pack_up9_from_down)
+static int conv_up_merged(const void* lo, const void* w9, void* out, int B, int H, int W, int Cp, int Cs,
+                          float* stats_ws, cudaStream_t st) {
+  RG_CHECK_ARG(Cs == 64 && Cp % 64 == 0, "rg_conv_up (merged phases): need Cs == 64, Cp %% 64 == 0");
+  GemmMaps maps;
+  FwdArgs a;
+  fill_common(a, B, H, W);
+  RG_CHECK_ARG(a.m_tiles >= 2 && pair_allowed(a, OUT_BF16_NHWC),
+               "rg_conv_up (merged phases) needs at least two M tiles (CTA pairs); use the w_up operand for tiny inputs");
+  int rc = encode_map_4d(&maps.a[0], lo, Cp, W, H, B, Cp, 1ull * W * Cp, 1ull * H * W * Cp, 64, a.bw, a.bh, a.bb);
+  if (rc) return rc;
+  const int chunks = Cp / 64;
+  const uint64_t rows9 = 9ull * chunks * 2 * 4 * 32;      // w_up9 as a [rows][64] matrix
+  rc = encode_map_2d(&maps.b, w9, 64, rows9, 64, 64, 4 * 32);          // taps feeding 4 phases
+  if (rc) return rc;
+  rc = encode_map_2d(&maps.a[1], w9, 64, rows9, 64, 64, 2 * 32);       // 2 phases
+  if (rc) return rc;
+  rc = encode_map_2d(&maps.a[2], w9, 64, rows9, 64, 64, 1 * 32);       // 1 phase
+  if (rc) return rc;
+  maps.a[3] = maps.a[0];
+  a.merged = 1;
+  a.num_taps = 9;
+  a.chunks = chunks;
+  a.num_phases = 1;
+  for (int t9 = 0; t9 < 9; ++t9) {
+    const int dh = t9 / 3 - 1, dw = t9 % 3 - 1;
+    Tap t = {0, static_cast<int8_t>(dh), static_cast<int8_t>(dw), 0};
+    a.taps[0][t9] = t;
+    int cnt = 0;
+    for (int rh = 0; rh < 2; ++rh)
+      for (int rw = 0; rw < 2; ++rw) {
+        const bool okh = dh == 0 || (dh == -1 && rh == 0) || (dh == 1 && rh == 1);
+        const bool okw = dw == 0 || (dw == -1 && rw == 0) || (dw == 1 && rw == 1);
+        if (okh && okw) a.mg_phase[t9][cnt++] = static_cast<int8_t>(rh * 2 + rw);
+      }
+    a.mg_nph[t9] = static_cast<int8_t>(cnt);
+  }
+  for (int ph = 0; ph < 4; ++ph) {
+    a.oy[ph] = static_cast<int8_t>(ph >> 1);
+    a.ox[ph] = static_cast<int8_t>(ph & 1);
+  }
+  a.n_total = Cs;
+  a.block_n = 256;               // TMEM columns of one tile: four 64-column phase slabs
+  a.n_tiles = 1;
+  a.out = out;
+  a.OH = 2 * H; a.OW = 2 * W; a.OC = Cs;
+  a.sy = a.sx = 2;
+  a.n_valid = Cs;
+  return launch_fwd(maps, a, OUT_BF16_NHWC, 2, stats_ws, st);
+}
+
 static int conv_up_common(const void* lo, const void* w, void* out, const float* bias, int act_tanh, int B, int H,
                           int W, int Cp, int Cs, int out_kind, bool w_is_down, float* stats_ws, cudaStream_t st) {
   RG_CHECK_ARG(lo && w && out, "rg_conv_up: null pointer");
@@ -732,6 +840,10 @@ static int conv_up_common(const void* lo, const void* w, void* out, const float*
 
 int rg_conv_up(const void* lo, const void* w, int w_is_down, void* hi, int B, int H, int W, int Cp, int Cs,
                float* stats_ws, rg_stream_t st_) {
+  if (w_is_down == 2) {
+    RG_CHECK_ARG(lo && w && hi && B > 0 && is_pow2(H) && is_pow2(W), "rg_conv_up: bad arguments");
+    return conv_up_merged(lo, w, hi, B, H, W, Cp, Cs, stats_ws, static_cast<cudaStream_t>(st_));
+  }
   RG_CHECK_ARG(Cs % (w_is_down ? 64 : 16) == 0,
                "rg_conv_up: need Cs %% 64 == 0 with w_down, %% 16 with w_up (Cs=%d); use rg_conv_up_img for images", Cs);
   return conv_up_common(lo, w, hi, nullptr, 0, B, H, W, Cp, Cs, OUT_BF16_NHWC, w_is_down != 0, stats_ws,

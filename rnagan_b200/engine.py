@@ -27,6 +27,8 @@ F32 = torch.float32
 SLOPE = 0.2
 # BatchNorm batch statistics accumulated in the epilogue of the producing convolution (RG_FUSED_STATS=0: separate pass)
 FUSED_STATS = os.environ.get("RG_FUSED_STATS", "1") != "0"
+# the Cs == 64 transposed convolutions contract all four output phases in one tile (RG_MERGED_UP=0: one phase per tile)
+MERGED_UP = os.environ.get("RG_MERGED_UP", "1") != "0"
 
 
 def _grad_of(p):
@@ -151,6 +153,14 @@ class _BN:
         ops.bn_bwd_apply(dh, a, add, s.mean, s.rstd, s.scale, s.shift, self.slope, s.bsums, M, self.C, da, du_out)
 
 
+def _up_operand(eng, l, npix):
+    """B operand of rg_conv_up for link l: the merged-phase w_up9 (Cs == 64 and at least two 128-pixel M tiles), the
+    K-major w_up copy of the narrow layers, else w_down itself read MN-major."""
+    if eng.w_up9[l - 1] is not None and npix >= 256 and MERGED_UP:
+        return eng.w_up9[l - 1]
+    return eng.w_upk[l - 1] if eng.w_upk[l - 1] is not None else eng.w_down[l - 1]
+
+
 def _check_act(mod, slope, what):
     if not isinstance(mod, nn.LeakyReLU) or abs(mod.negative_slope - slope) > 1e-12:
         raise NotImplementedError(f"{what}: only LeakyReLU({slope}) is implemented on the sm_100a path (got {mod!r})")
@@ -199,12 +209,13 @@ class GeneratorEngine:
         self.conv0.weight._rg_shadow = self.w_projkn
         # one packed copy per link (w_down: K-major B for rg_conv_down, MN-major B for rg_conv_up); layers with
         # Cs <= 128 also keep the tiny K-major w_up copy, which is faster for narrow N tiles
-        self.w_down, self.w_upk = [], []
+        self.w_down, self.w_upk, self.w_up9 = [], [], []
         for c in self.convs:
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
             self.w_down.append(torch.empty(Cp, 16 * Cs, dtype=BF16, device=dev))
             c.weight._rg_shadow = self.w_down[-1]        # re-emitted by the fused Adam step
             self.w_upk.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev) if Cs <= 128 else None)
+            self.w_up9.append(torch.zeros(9, Cp // 64, 2, 4, 32, 64, dtype=BF16, device=dev) if Cs == 64 else None)
         self.w_colT_last = torch.zeros(16 * self.Cimg, self.Cn, dtype=BF16, device=dev)
         self.w_col_last = torch.empty(self.Cn, 64, dtype=BF16, device=dev)
         self.sync = GradSync(module)
@@ -220,9 +231,11 @@ class GeneratorEngine:
             ops.cast_pad_bf16(ops.phys2d(self.conv0.weight.detach()), out=self.w_projkn)
             for c, wd in zip(self.convs, self.w_down):
                 ops.cast_pad_bf16(ops.phys2d(c.weight.detach()), out=wd)
-        for c, wd, wu in zip(self.convs, self.w_down, self.w_upk):
+        for c, wd, wu, w9 in zip(self.convs, self.w_down, self.w_upk, self.w_up9):
             if wu is not None:
                 ops.pack_up_from_down(wd, wu, c.weight.shape[1])
+            if w9 is not None:
+                ops.pack_up9_from_down(wd, c.weight.shape[1], out=w9)
         ops.pack_edge_t(self.conv_last.weight.detach(), self.w_colT_last)
         ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
 
@@ -239,8 +252,7 @@ class GeneratorEngine:
             Cs = c.weight.shape[1]
             a = g(f"{tag}.a{l}", (B, 2 * H, 2 * H, Cs))
             sws = bn.stats_ws(training)
-            ops.conv_up(h, self.w_upk[l - 1] if self.w_upk[l - 1] is not None else self.w_down[l - 1], Cs, out=a,
-                        stats=sws)
+            ops.conv_up(h, _up_operand(self, l, B * H * H), Cs, out=a, stats=sws)
             H *= 2
             h = g(f"{tag}.h{l}", (B, H, H, Cs))
             bn.forward(a, h, B * H * H, training, tag=tag, stats=sws)
@@ -428,7 +440,7 @@ class CriticEngine:
             raise NotImplementedError("channel counts must be multiples of 64 on the sm_100a path")
         self.w_col0 = torch.empty(self.C0, 64, dtype=BF16, device=dev)
         self.w_colT0 = torch.zeros(16 * self.Cimg, self.C0, dtype=BF16, device=dev)
-        self.w_down, self.w_upk = [], []
+        self.w_down, self.w_upk, self.w_up9 = [], [], []
         self._native_params = [c.weight for c in self.convs]
         _to_native(self._native_params)
         for c in self.convs:
@@ -436,6 +448,7 @@ class CriticEngine:
             self.w_down.append(torch.empty(Cp, 16 * Cs, dtype=BF16, device=dev))
             c.weight._rg_shadow = self.w_down[-1]        # re-emitted by the fused Adam step
             self.w_upk.append(torch.zeros(4, ops.up_pad(Cs), 4 * Cp, dtype=BF16, device=dev) if Cs <= 128 else None)
+            self.w_up9.append(torch.zeros(9, Cp // 64, 2, 4, 32, 64, dtype=BF16, device=dev) if Cs == 64 else None)
         self.w_head = torch.empty(16 * self.Cn, dtype=F32, device=dev)
         self.tmpC = torch.zeros(max([self.C0] + [c.weight.shape[0] for c in self.convs]), dtype=F32, device=dev)
         self.gp_partial = torch.zeros(1024, dtype=F32, device=dev)
@@ -465,13 +478,15 @@ class CriticEngine:
                 self.sync.rebind(p)
             for c, wd in zip(self.convs, self.w_down):
                 ops.cast_pad_bf16(ops.phys2d(c.weight.detach()), out=wd)
-        for c, wd, wu in zip(self.convs, self.w_down, self.w_upk):
+        for c, wd, wu, w9 in zip(self.convs, self.w_down, self.w_upk, self.w_up9):
             if wu is not None:
                 ops.pack_up_from_down(wd, wu, c.weight.shape[1])
+            if w9 is not None:
+                ops.pack_up9_from_down(wd, c.weight.shape[1], out=w9)
         ops.pack_head(self.head.weight.detach(), self.w_head)
 
-    def _wup(self, l):
-        return self.w_upk[l - 1] if self.w_upk[l - 1] is not None else self.w_down[l - 1]
+    def _wup(self, l, npix=0):
+        return _up_operand(self, l, npix)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x=None, tag="d", training=True, col=None):
@@ -532,7 +547,7 @@ class CriticEngine:
                     self.sync.layer_done(c.weight, bn.mod.weight, bn.mod.bias)
             H *= 2
             dh = g(f"{tag}.dh{l - 1}", (B, H, H, Cs))
-            ops.conv_up(da, self._wup(l), Cs, out=dh)
+            ops.conv_up(da, self._wup(l, da.shape[0] * da.shape[1] * da.shape[2]), Cs, out=dh)
         h0 = g(f"{tag}.h0", (B, H, H, self.C0))
         da0 = g(f"{tag}.da0", (B, H, H, self.C0))
         npix = B * H * H
@@ -582,7 +597,7 @@ class CriticEngine:
             self.sync.layer_done(c_.weight, bn.mod.weight, bn.mod.bias)
             H *= 2
             dh2 = self.bufs.joint(f"{ta}.dh{l - 1}", (B, H, H, Cs))
-            ops.conv_up(da2, self._wup(l), Cs, out=dh2)
+            ops.conv_up(da2, self._wup(l, da2.shape[0] * da2.shape[1] * da2.shape[2]), Cs, out=dh2)
         npix = B * H * H
         h0 = self.bufs.joint(f"{ta}.h0", (B, H, H, self.C0))
         dh0 = self.bufs.joint(f"{ta}.dh0", (B, H, H, self.C0))
@@ -661,7 +676,7 @@ class CriticEngine:
             self.sync.layer_done(c.weight, self.bns[l - 1].mod.weight, self.bns[l - 1].mod.bias)
             H *= 2
             A_h = g(f"{tag}.Ah{l - 1}", (B, H, H, Cs))
-            ops.conv_up(T, self._wup(l), Cs, out=A_h)
+            ops.conv_up(T, self._wup(l, T.shape[0] * T.shape[1] * T.shape[2]), Cs, out=A_h)
             if l - 1 >= 1:
                 bnp = self.bns[l - 2]
                 a = g(f"{tag}.a{l - 1}", (B, H, H, Cs))

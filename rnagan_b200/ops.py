@@ -104,6 +104,16 @@ def pack_up_from_down(w_down, w_up, Cs):
     return w_up
 
 
+def pack_up9_from_down(w_down, Cs, out=None):
+    """bf16 w_down [Cp, 16*Cs] (Cs == 64) -> merged-phase operand bf16 [9, Cp/64, 2, 4, 32, 64] of conv_up."""
+    _chk(w_down, BF16, "w_down")
+    Cp = w_down.shape[0]
+    if out is None:
+        out = torch.empty(9, Cp // 64, 2, 4, 32, 64, dtype=BF16, device=w_down.device)
+    _lib.check(_lib.lib().rg_pack_up9_from_down(_p(w_down), _p(out), Cp, Cs, _st()), "rg_pack_up9_from_down")
+    return out
+
+
 def pack_proj(W, out=None):
     """W: fp32 [E, C0, 4, 4] -> bf16 [16*C0, E]."""
     _chk(W, torch.float32, "W")
@@ -162,14 +172,14 @@ def conv_down(hi, w_down, out=None, stats=None):
 
 
 def conv_up(lo, w, Cs, out=None, stats=None):
-    """lo bf16 [B, H, W, Cp] -> hi bf16 [B, 2H, 2W, Cs].  w: w_down bf16 [Cp, 16*Cs] (2-D; read MN-major) or
-    w_up bf16 [4, Cs_pad, 4*Cp] (3-D; K-major)."""
+    """lo bf16 [B, H, W, Cp] -> hi bf16 [B, 2H, 2W, Cs].  w: w_down bf16 [Cp, 16*Cs] (2-D; read MN-major),
+    w_up bf16 [4, Cs_pad, 4*Cp] (3-D; K-major) or the merged-phase w_up9 (6-D; Cs == 64, >= 256 low-res pixels)."""
     _chk(lo, BF16, "lo"); _chk(w, BF16, "w")
     B, H, W, Cp = lo.shape
     if out is None:
         out = torch.empty(B, 2 * H, 2 * W, Cs, dtype=BF16, device=lo.device)
     _prof("conv_up", 2.0 * B * H * W * Cp * 16 * Cs, lambda: _lib.check(
-        _lib.lib().rg_conv_up(_p(lo), _p(w), int(w.dim() == 2), _p(out), B, H, W, Cp, Cs, _p(stats), _st()),
+        _lib.lib().rg_conv_up(_p(lo), _p(w), {2: 1, 3: 0, 6: 2}[w.dim()], _p(out), B, H, W, Cp, Cs, _p(stats), _st()),
         "rg_conv_up"))
     return out
 

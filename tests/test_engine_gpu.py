@@ -315,3 +315,25 @@ def test_pack_up_from_down_and_adam_shadow(cuda_dev):
     tab.step(1e-3, 0.5, 0.999, 1e-8, 1)
     assert _rel(p, pr.detach()) < 1e-5
     assert torch.equal(shadow, ops.cast_pad_bf16(ops.phys2d(p)))
+
+
+@pytest.mark.parametrize("B,H,W,Cp", [(4, 64, 64, 128), (2, 16, 16, 64), (3, 8, 8, 192), (16, 32, 32, 128)])
+def test_conv_up_merged_phases(cuda_dev, B, H, W, Cp):
+    """rg_conv_up with the merged-phase operand (Cs == 64: all four output phases in one tile) equals
+    conv_transpose2d, and its fused statistics equal the sums over the stored output."""
+    from rnagan_b200 import ops
+    Cs = 64
+    g = torch.Generator(device="cpu").manual_seed(B + H + Cp + 9)
+    x = _bf(torch.randn(B, Cp, H, W, generator=g)).to(cuda_dev)
+    Wt = _bf(torch.randn(Cp, Cs, 4, 4, generator=g) * 0.05).to(cuda_dev)
+    ref = F.conv_transpose2d(x, Wt, stride=2, padding=1)
+    w_down, _ = ops.pack_link(Wt, want_up=False)
+    w9 = ops.pack_up9_from_down(w_down, Cs)
+    ws = ops.stats_ws(Cs, cuda_dev, slot=9)
+    ws.fill_(float("nan"))
+    out = ops.conv_up(_nhwc(x), w9, Cs, stats=ws)
+    assert out.shape == (B, 2 * H, 2 * W, Cs)
+    assert _rel(_nchw(out), ref) < 8e-3
+    o = out.float().view(-1, Cs)
+    got = ws.sum(0)
+    assert _rel(got[0], o.sum(0)) < 1e-4 and _rel(got[1], (o * o).sum(0)) < 1e-4

@@ -55,6 +55,9 @@ def main(filt=""):
             report(f"conv_up   {name} {Cp}->{Cs} @{h} (w_down, MN-major B)", timeit(lambda: ops.conv_up(lo, wd, Cs, out=out_hi)), fl, by)
             if Cs <= 128:
                 report(f"conv_up   {name} {Cp}->{Cs} @{h} (w_up, K-major B)", timeit(lambda: ops.conv_up(lo, wu, Cs, out=out_hi)), fl, by)
+            if Cs == 64:
+                w9 = ops.pack_up9_from_down(wd, Cs)
+                report(f"conv_up   {name} {Cp}->{Cs} @{h} (w_up9, merged phases)", timeit(lambda: ops.conv_up(lo, w9, Cs, out=out_hi)), fl, by)
         if filt in f"wgrad {name}":
             report(f"conv_wgrad {name} (torch layout)", timeit(lambda: ops.conv_wgrad(lo, hi, dW)), fl, by + W.numel() * 2)
             dWn = torch.empty_like(W).contiguous(memory_format=torch.channels_last)
