@@ -445,6 +445,9 @@ def run_reference(args, rank, world):
 
 
 def main():
+    # rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION in this image) off it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -27,7 +27,7 @@ constexpr int kAStageBytes = 128 * 128;      // 16 KiB: 128 pixel rows x 64 chan
 constexpr int kStagingBytes = 128 * 128;     // one 64-column bf16 slab of the output tile (epilogue -> TMA store)
 constexpr int kBarBytes = 256;
 constexpr int kAffineBytes = 2048;           // per-column scale / shift of the current tile (2 x 256 floats)
-constexpr int kStatBytes = 2048;             // per-warp column sums of one slab (4 warps x 2 x 64 floats)
+constexpr int kStatBytes = 4096;             // per-warp column sums of one slab (4 warps x 2 x 64 floats), two slab parities
 constexpr int kSmemFixedBytes = kBarBytes + kAffineBytes + kStatBytes + 1024 /*alignment slack*/;
 constexpr int kSmemMaxBytes = 232448;        // 227 KiB: the sm_100 per-CTA dynamic shared memory limit
 constexpr int kGemmThreads = 224;            // warps: 0 A-producer, 1 MMA issuer, 2-5 epilogue, 6 B-producer
@@ -132,7 +132,7 @@ struct PipeSmem {
   uint32_t* tmem_slot;
   float* s_scale;   // [256] per-column epilogue scale of the current tile
   float* s_shift;   // [256]
-  float* s_stat;    // [4 warps][2][64]
+  float* s_stat;    // [2 slab parities][4 warps][2][64]
 };
 
 // layout: [ring: ring_bytes][staging: staging_bytes][barriers 256][affine 2048][stat 2048], ring 1024-byte aligned
@@ -493,21 +493,24 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
 #pragma unroll 1
         for (int sl = 0; sl < nslabs; ++sl, ++store_count) {
           uint8_t* buf = s.staging + (p.nbuf == 2 ? (store_count & 1) : 0) * kStagingBytes;
-          // the TMA store that last read this slab buffer has finished reading it
-          if (et == 0) {
-            const long long cs0 = p.prof ? clock64() : 0;
-            if (p.nbuf == 2) bulk_wait_read<1>();
-            else bulk_wait_read<0>();
-            if (p.prof) t_wstore += clock64() - cs0;
+          float* stat_buf = s.s_stat + (store_count & 1) * 512;
+          // Two staging slabs: ONE barrier per slab.  Before barrier B(s) the leader waits until store(s-1) has finished
+          // reading the other slab, so passing B(s) tells every thread both "slab s is written" (the leader may store
+          // it) and "the buffer of slab s+1 is free".  One staging slab (single-CTA 256-column tiles): wait + barrier
+          // before writing as well.
+          if (p.nbuf != 2) {
+            if (et == 0) bulk_wait_read<0>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
           float csum[2] = {0.0f, 0.0f}, csq[2] = {0.0f, 0.0f};
+          uint32_t vv[2][32];
+          tmem_ld_32x32(taddr + sl * 64, vv[0]);            // both halves in flight before the single wait
+          tmem_ld_32x32(taddr + sl * 64 + 32, vv[1]);
+          tmem_ld_wait();
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int c = sl * 64 + hh * 32;
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + c, v);
-            tmem_ld_wait();
+            uint32_t (&v)[32] = vv[hh];
             if (affine) {
               const float4* sc4 = reinterpret_cast<const float4*>(s.s_scale + c);
               const float4* sh4 = reinterpret_cast<const float4*>(s.s_shift + c);
@@ -559,11 +562,16 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
             }
           }
           if (do_stats) {
-            float* ss = s.s_stat + q * 128;
+            float* ss = stat_buf + q * 128;
             ss[lane] = csum[0]; ss[32 + lane] = csum[1];
             ss[64 + lane] = csq[0]; ss[96 + lane] = csq[1];
           }
           fence_proxy_async();             // generic-proxy smem writes -> visible to the TMA (async proxy)
+          if (p.nbuf == 2 && et == 0) {
+            const long long cs0 = p.prof ? clock64() : 0;
+            bulk_wait_read<0>();           // store(s-1) no longer reads the slab that slab s+1 will overwrite
+            if (p.prof) t_wstore += clock64() - cs0;
+          }
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (et == 0 && tile_ok) {
             if (p.merged) tma_store_4d(&maps.o[sl], buf, 0, j0, i0, b0);      // slab = output phase, all 64 channels
@@ -571,7 +579,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
             bulk_commit();
           }
           if (do_stats) {                  // fixed-order sum of the four warps' partial column sums
-            const float* ss = s.s_stat + st_k * 64 + st_c;
+            const float* ss = stat_buf + st_k * 64 + st_c;
             const float t = ((ss[0] + ss[128]) + ss[256]) + ss[384];
             if (sl == 0 || p.merged) st_acc[0] += t;     // merged: the four slabs are four phases of the SAME channels
             else if (sl == 1) st_acc[1] += t;
