@@ -344,3 +344,40 @@ def make_batch(batch, rna_features, size, seed):
         "rna_data": torch.randn(batch, rna_features, generator=g),
         "labels": torch.zeros(batch),
     }
+
+
+# ------------------------------------------------------------------------------------------------ un-conditioned WGAN
+# torchgan's own WassersteinGeneratorLoss / WassersteinDiscriminatorLoss(clip) / WassersteinGradientPenalty default
+# train_ops [tg] (used by `--loss_type wgan`, src/histopathology_gan.py:267-272).  torchgan is absent from the reference
+# tree: restated from the package's published source; parity at this boundary is UNPINNED.  The device-RNG noise draw
+# is an explicit argument here (the tests draw it on the GPU with a fixed seed and hand the same values to both sides).
+def plain_g_step(G, D, opt_g, noise):
+    opt_g.zero_grad()
+    loss = torch.mean(-1.0 * D(G(noise)))
+    loss.backward()
+    opt_g.step()
+    return loss.item()
+
+
+def plain_critic_step(G, D, opt_d, noise, real, clip=None):
+    if clip is not None:
+        for p in D.parameters():
+            p.data.clamp_(clip[0], clip[1])
+    opt_d.zero_grad()
+    dx = D(real)
+    dgz = D(G(noise).detach())
+    loss = torch.mean(dgz - dx)
+    loss.backward()
+    opt_d.step()
+    return loss.item()
+
+
+def plain_gp_step(G, D, opt_d, noise, real, lambd=10.0):
+    fake = G(noise)
+    opt_d.zero_grad()
+    eps = torch.rand(1).item()
+    interp = eps * real + (1 - eps) * fake
+    loss = gradient_penalty(interp, D(interp))
+    (lambd * loss).backward()
+    opt_d.step()
+    return loss.item()

@@ -13,10 +13,14 @@ BF16 = torch.bfloat16
 
 
 def latent(ge, noise_d, z):
-    """standardise_0(noise + z) -> bf16 [B, E] (src/wgan_loss.py:105-106)."""
+    """standardise_0(noise + z) -> bf16 [B, E] (src/wgan_loss.py:105-106); z=None (the un-conditioned `wgan` losses,
+    src/histopathology_gan.py:267-272): the N(0, I) noise itself, cast to bf16."""
     B, E = noise_d.shape
     lat = ge.bufs.get("lat", (B, E), BF16)
-    ops.latent_prep(noise_d, z, lat_bf16=lat)
+    if z is None:
+        ops.cast_pad_bf16(noise_d, E, out=lat)
+    else:
+        ops.latent_prep(noise_d, z, lat_bf16=lat)
     return lat
 
 

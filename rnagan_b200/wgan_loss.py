@@ -239,3 +239,68 @@ class WassersteinGradientPenaltyVAE(_VAEConditioned, DiscriminatorLoss):
         return out3[0:1]
 
 
+
+
+# ------------------------------------------------------------------------------------------------ un-conditioned WGAN
+# The README's comparison model (`--loss_type wgan`, src/histopathology_gan.py:267-272) uses torchgan's own
+# WassersteinGeneratorLoss / WassersteinDiscriminatorLoss(clip=(-0.01, 0.01)) / WassersteinGradientPenalty [tg]: the same
+# three steps without the betaVAE conditioning -- latent = randn(batch, encoding_dims, device=device) as is -- plus the
+# critic weight clamp before the critic step.  Same kernels (steps.py with z=None).
+def _images_of(real_inputs, device):
+    img = real_inputs["image"] if isinstance(real_inputs, dict) else real_inputs
+    return img.to(device=device, dtype=F32, non_blocking=True).contiguous()
+
+
+class WassersteinGeneratorLoss(GeneratorLoss):
+    def forward(self, fgz):
+        return reduce_vae(-1.0 * fgz, self.reduction)
+
+    def train_ops(self, generator, discriminator, optimizer_generator, device, batch_size, labels=None):
+        return self.device_ops(generator, discriminator, optimizer_generator, device, batch_size, labels).item()
+
+    def device_ops(self, generator, discriminator, optimizer_generator, device, batch_size, labels=None):
+        _check_labels(labels, generator)
+        noise = torch.randn(batch_size, generator.encoding_dims, device=device)       # torchgan: device RNG [tg]
+        return steps.g_step(generator, discriminator, optimizer_generator, noise, None)
+
+
+class WassersteinDiscriminatorLoss(DiscriminatorLoss):
+    def __init__(self, reduction="mean", clip=None, override_train_ops=None):
+        super().__init__(reduction, override_train_ops)
+        self.clip = clip if isinstance(clip, (tuple, list)) and len(clip) > 1 else None
+
+    def forward(self, fx, fgz):
+        return reduce_vae(fgz - fx, self.reduction)
+
+    def train_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
+        return self.device_ops(generator, discriminator, optimizer_discriminator, real_inputs, device, labels).item()
+
+    def device_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
+        _check_labels(labels, generator, discriminator)
+        real = _images_of(real_inputs, device)
+        noise = torch.randn(real.size(0), generator.encoding_dims, device=device)
+        return steps.critic_step(generator, discriminator, optimizer_discriminator, noise, None, real, clip=self.clip)
+
+
+class WassersteinGradientPenalty(DiscriminatorLoss):
+    def __init__(self, reduction="mean", lambd=10.0, override_train_ops=None):
+        super().__init__(reduction, override_train_ops)
+        self.lambd = lambd
+
+    def forward(self, interpolate, d_interpolate):
+        raise NotImplementedError("the penalty is computed inside train_ops by CriticEngine.gradient_penalty "
+                                  "(hand-scheduled double backward); there is no autograd graph to differentiate")
+
+    def train_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
+        return self.device_ops(generator, discriminator, optimizer_discriminator, real_inputs, device, labels).item()
+
+    def device_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
+        _check_labels(labels, generator, discriminator)
+        real = _images_of(real_inputs, device)
+        noise = torch.randn(real.size(0), generator.encoding_dims, device=device)
+        eps = torch.rand(1)                                                # CPU draw, like torchgan's .item() [tg]
+        eps_d = discriminator._engine().bufs.get("eps", (1,), F32)
+        eps_d.copy_(eps)
+        out3 = steps.gp_step(generator, discriminator, optimizer_discriminator, noise, None, real, eps_d,
+                             lambd=self.lambd)
+        return out3[0:1]

@@ -198,3 +198,60 @@ def test_synthesis_after_golden_training_state(cuda_dev):
     sample = flat[U.sample_idx(flat.size, 4096)]
     assert U.rel_l2(sample, gold["tiles/sample"]) <= 3e-2
     assert np.abs(sample - gold["tiles/sample"]).max() <= 0.12
+
+
+def test_plain_wgan_steps_match_oracle(cuda_dev):
+    """The un-conditioned `wgan` losses (torchgan WassersteinGeneratorLoss / WassersteinDiscriminatorLoss(clip) /
+    WassersteinGradientPenalty, src/histopathology_gan.py:267-272) through Trainer.train_iter vs the oracle's
+    restatement; the device-RNG noise of each step is reproduced by re-seeding the CUDA generator."""
+    from rnagan_b200 import dcgan, wgan_loss
+    from rnagan_b200.trainer import Trainer
+    size, batch = 32, 8
+    lrelu, tanh = torch.nn.LeakyReLU(0.2), torch.nn.Tanh()
+    oG = O.OracleGenerator(2048, size, 3, 64, nonlinearity=lrelu, last_nonlinearity=tanh).train()
+    oD = O.OracleCritic(size, 3, 64, nonlinearity=lrelu, last_nonlinearity=lrelu).train()
+    O.reinit_(oG, U.SEED_G); O.reinit_(oD, U.SEED_D)
+    net = {
+        "generator": {"name": dcgan.DCGANGenerator,
+                      "args": {"encoding_dims": 2048, "out_channels": 3, "step_channels": 64, "out_size": size,
+                               "nonlinearity": torch.nn.LeakyReLU(0.2), "last_nonlinearity": torch.nn.Tanh()},
+                      "optimizer": {"name": Adam, "args": {"lr": 0.0001, "betas": (0.5, 0.999)}}},
+        "discriminator": {"name": dcgan.DCGANDiscriminator,
+                          "args": {"in_size": size, "in_channels": 3, "step_channels": 64,
+                                   "nonlinearity": torch.nn.LeakyReLU(0.2),
+                                   "last_nonlinearity": torch.nn.LeakyReLU(0.2)},
+                          "optimizer": {"name": Adam, "args": {"lr": 0.0004, "betas": (0.5, 0.999)}}},
+    }
+    clip = (-0.05, 0.05)
+    losses = [wgan_loss.WassersteinGeneratorLoss(), wgan_loss.WassersteinDiscriminatorLoss(clip=clip),
+              wgan_loss.WassersteinGradientPenalty()]
+    tr = Trainer(net, losses, device=cuda_dev, sample_size=64, epochs=1, devices=[0])
+    tr.generator.train(); tr.discriminator.train()
+    real = O.make_batch(batch, 64, size, U.SEED_BATCH)["image"]
+    tr.real_inputs, tr.batch_size = real, batch
+    og = Adam(oG.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    od = Adam(oD.parameters(), lr=4e-4, betas=(0.5, 0.999))
+    names = list(tr.losses.keys())
+    torch.manual_seed(U.SEED_RUN)
+    for which in range(3):
+        _sync(tr, oG, oD, og, od)
+        torch.cuda.manual_seed(100 + which)
+        noise = torch.randn(batch, 2048, device=cuda_dev).cpu()      # what the product will draw
+        st = torch.get_rng_state()
+        if which == 0:
+            v_ref = O.plain_g_step(oG, oD, og, noise)
+        elif which == 1:
+            v_ref = O.plain_critic_step(oG, oD, od, noise, real, clip=clip)
+        else:
+            v_ref = O.plain_gp_step(oG, oD, od, noise, real)
+        st_after = torch.get_rng_state()
+        torch.set_rng_state(st)
+        torch.cuda.manual_seed(100 + which)
+        v = tr._call(names[which])
+        v = float(v.item()) if torch.is_tensor(v) else v
+        assert torch.equal(torch.get_rng_state(), st_after)          # CPU stream: only the GP step's eps
+        assert abs(v - v_ref) <= 0.02 + 0.02 * abs(v_ref), f"plain step{which}: {v} vs oracle {v_ref}"
+        onet, mnet = (oG, tr.generator) if which == 0 else (oD, tr.discriminator)
+        _check_state(f"plain step{which}", onet, mnet)
+    # the clamp ran before the critic step: every critic weight of the oracle was inside the clip range at that point
+    assert all(float(p.abs().max()) <= 0.06 for p in oD.parameters())
