@@ -172,7 +172,9 @@ int rg_img_channel_sum(const float* x, const float* y, int mode, int B, int Cimg
                        int partial_len, float* out, float acc, rg_stream_t st);
 /* image-side transposed conv in "dgrad form": col[pix][tap*Cimg+c] (fp32, from rg_gemm_nt with w_colT) is folded back
  * onto the 2x larger image: img[b,c,y,x] = act(bias[c] + sum of the 4 taps hitting (y,x)); fp32 NCHW output.
- * Generator last layer (ConvTranspose2d(64,3,4,2,1)+Tanh, src/dcgan.py:82) and the critic's layer-0 dgrad. */
+ * Generator last layer (ConvTranspose2d(64,3,4,2,1)+Tanh, src/dcgan.py:82) and the critic's layer-0 dgrad.
+ * act_tanh is a flag word: bit 0 = tanh, bit 1 = write the synthesis output instead, (v + 1) / 2 as fp32 NHWC
+ * [B, 2H, 2W, Cimg] (src/gan_utils.py:236-241), which saves the separate un-normalise + permute pass. */
 int rg_col2im_img(const float* col, int ldc, const float* bias, int act_tanh, int B, int Cimg, int H, int W, float* img,
                   rg_stream_t st);
 /* W[Cp][Cimg][4][4] -> bf16 w_colT[rows][Cp], row n = tap*Cimg + c (rows beyond 16*Cimg zero) */

@@ -99,10 +99,13 @@ class betaVAE(nn.Module):
         return eng
 
     def _apply(self, fn, *args, **kwargs):
-        self.__dict__.pop("_rg_engine", None)
-        self.__dict__.pop("_rg_train_engine", None)
-        self.__dict__.pop("_rg_dec_engine", None)
-        return super()._apply(fn, *args, **kwargs)
+        before = [p.data_ptr() for p in self.parameters()]
+        out = super()._apply(fn, *args, **kwargs)
+        if before != [p.data_ptr() for p in self.parameters()]:      # .to()/.cuda()/.float() really moved the storage
+            self.__dict__.pop("_rg_engine", None)
+            self.__dict__.pop("_rg_train_engine", None)
+            self.__dict__.pop("_rg_dec_engine", None)
+        return out
 
     # -- reference API -----------------------------------------------------------------------------------------
     @torch.no_grad()

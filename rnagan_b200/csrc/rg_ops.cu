@@ -644,31 +644,41 @@ __global__ void vec_axpby_kernel(const float* __restrict__ x, float* y, int n, f
 }
 
 // latent = standardise_0(noise + z) with unbiased std (src/wgan_loss.py:105-106); one thread per feature column
-__global__ void latent_prep_kernel(const float* __restrict__ noise, const float* __restrict__ z, int B, int E, int zB,
-                                   __nv_bfloat16* __restrict__ lat_bf16, float* __restrict__ lat_f32) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
+// 32 feature columns x 8 row lanes per block: each lane walks rows lane, lane+8, ... (coalesced 128-byte rows), the
+// lanes are combined in shared memory in a fixed order.  Three passes (mean, unbiased variance, write) like the
+// reference's two-pass formula; large synthesis batches (B = 1024) no longer run one thread per column.
+__global__ void __launch_bounds__(256) latent_prep_kernel(const float* __restrict__ noise, const float* __restrict__ z,
+                                                          int B, int E, int zB, __nv_bfloat16* __restrict__ lat_bf16,
+                                                          float* __restrict__ lat_f32) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + cx;
+  const bool ok = e < E;
+  auto val = [&](int b) { return noise[static_cast<size_t>(b) * E + e] + z[static_cast<size_t>(zB == 1 ? 0 : b) * E + e]; };
   float s = 0.0f;
-  for (int b = 0; b < B; ++b) s += noise[static_cast<size_t>(b) * E + e] + z[static_cast<size_t>(zB == 1 ? 0 : b) * E + e];
-  const float m = s / B;
+  if (ok) for (int b = g; b < B; b += 8) s += val(b);
+  sm[g][cx] = s;
+  __syncthreads();
+  float tot = 0.0f;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) tot += sm[l][cx];
+  const float m = tot / B;
+  __syncthreads();
   float ss = 0.0f;
-  for (int b = 0; b < B; ++b) {
-    const float d = noise[static_cast<size_t>(b) * E + e] + z[static_cast<size_t>(zB == 1 ? 0 : b) * E + e] - m;
-    ss += d * d;
-  }
-  const float sd = sqrtf(ss / (B - 1));   // B == 1 -> NaN, like the reference
-  for (int b = 0; b < B; ++b) {
-    const float v = (noise[static_cast<size_t>(b) * E + e] + z[static_cast<size_t>(zB == 1 ? 0 : b) * E + e] - m) / sd;
+  if (ok) for (int b = g; b < B; b += 8) { const float d = val(b) - m; ss += d * d; }
+  sm[g][cx] = ss;
+  __syncthreads();
+  float tss = 0.0f;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) tss += sm[l][cx];
+  const float sd = sqrtf(tss / (B - 1));   // B == 1 -> NaN, like the reference
+  if (!ok) return;
+  for (int b = g; b < B; b += 8) {
+    const float v = (val(b) - m) / sd;
     if (lat_bf16) lat_bf16[static_cast<size_t>(b) * E + e] = __float2bfloat16(v);
     if (lat_f32) lat_f32[static_cast<size_t>(b) * E + e] = v;
   }
 }
-
-// im2col of a fp32 NCHW image [B][Cimg<=4][S][S] for the 4x4 stride-2 pad-1 conv: col[pix][k], k = (kh*4+kw)*4 + c.
-// mode 0: v = x*mul ; mode 1: v = (eps*x + (1-eps)*y)*mul (GP interpolation, src/wgan_loss.py:377);
-// mode 2: v = x*(1 - y*y)*mul (tanh backward with y = tanh output).  eps_dev/mul_dev are device scalars (optional).
-// One block per output row (b, ho): the four input rows are staged in shared memory with the pointwise transform
-// applied once per input element (coalesced reads), then written out as whole 128-byte col rows (coalesced writes).
 __global__ void __launch_bounds__(256) im2col_img_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                          int mode, const float* __restrict__ eps_dev,
                                                          const float* __restrict__ mul_dev, int B, int Cimg, int S,
@@ -791,8 +801,11 @@ __global__ void __launch_bounds__(256) col2im_img_kernel(const float* __restrict
     for (int c = 0; c < 4; ++c) {
       if (c < Cimg) {
         float v = acc[c] + (bias ? __ldg(bias + c) : 0.0f);
-        if (act_tanh) v = tanhf(v);
-        img[((static_cast<size_t>(b) * Cimg + c) * OH + y) * OW + x] = v;
+        if (act_tanh & 1) v = tanhf(v);
+        if (act_tanh & 2)     // synthesis output (src/gan_utils.py:236-241): (x + 1) / 2, NHWC
+          img[((static_cast<size_t>(b) * OH + y) * OW + x) * Cimg + c] = (v + 1.0f) * 0.5f;
+        else
+          img[((static_cast<size_t>(b) * Cimg + c) * OH + y) * OW + x] = v;
       }
     }
   }
@@ -1430,7 +1443,7 @@ int rg_bn_gp_apply(const void* ggI, const void* a, const void* gO, const float* 
 int rg_latent_prep(const float* noise, const float* z, int B, int E, int z_rows, void* lat_bf16, float* lat_f32,
                    rg_stream_t st) {
   RG_CHECK_ARG(noise && z && B > 0 && E > 0 && (z_rows == B || z_rows == 1), "rg_latent_prep: bad arguments");
-  latent_prep_kernel<<<ceil_div(E, 128), 128, 0, static_cast<cudaStream_t>(st)>>>(noise, z, B, E, z_rows,
+  latent_prep_kernel<<<ceil_div(E, 32), 256, 0, static_cast<cudaStream_t>(st)>>>(noise, z, B, E, z_rows,
                                                                                   static_cast<bf16*>(lat_bf16), lat_f32);
   RG_LAUNCH_CHECK("rg_latent_prep");
   return 0;

@@ -98,8 +98,11 @@ class _EngineMixin:
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _apply(self, fn, *args, **kwargs):   # .to()/.cuda()/.float(): storage moves invalidate the engine
-        self.__dict__.pop("_rg_engine", None)
-        return super()._apply(fn, *args, **kwargs)
+        before = [p.data_ptr() for p in self.parameters()]
+        out = super()._apply(fn, *args, **kwargs)
+        if before != [p.data_ptr() for p in self.parameters()]:
+            self.__dict__.pop("_rg_engine", None)
+        return out
 
 
 class DCGANGenerator(_EngineMixin, Generator):

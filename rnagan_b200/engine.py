@@ -239,8 +239,9 @@ class GeneratorEngine:
         ops.pack_edge_t(self.conv_last.weight.detach(), self.w_colT_last)
         ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
 
-    def forward(self, lat, tag="g", training=True, out=None):
-        """lat: bf16 [B, E] -> fp32 NCHW image [B, Cimg, S, S]; keeps activations under `tag` for backward."""
+    def forward(self, lat, tag="g", training=True, out=None, unit_nhwc=False):
+        """lat: bf16 [B, E] -> fp32 NCHW image [B, Cimg, S, S]; keeps activations under `tag` for backward.
+        unit_nhwc (synthesis): `out` [B, S, S, Cimg] receives (image + 1) / 2 in NHWC straight from the last kernel."""
         B = lat.shape[0]
         g = self.bufs.get
         a = g(f"{tag}.a0", (B, 4, 4, self.C0))
@@ -257,9 +258,10 @@ class GeneratorEngine:
             h = g(f"{tag}.h{l}", (B, H, H, Cs))
             bn.forward(a, h, B * H * H, training, tag=tag, stats=sws)
         if out is None:
-            out = g(f"{tag}.img", (B, self.Cimg, 2 * H, 2 * H), F32)
+            out = g(f"{tag}.img", (B, 2 * H, 2 * H, self.Cimg) if unit_nhwc else (B, self.Cimg, 2 * H, 2 * H), F32)
         col = g("fwd.colimg", (B * H * H, 16 * self.Cimg), F32)
-        ops.conv_up_img_col(h, self.w_colT_last, self.Cimg, col, out, bias=self.conv_last.bias.detach(), act_tanh=True)
+        ops.conv_up_img_col(h, self.w_colT_last, self.Cimg, col, out, bias=self.conv_last.bias.detach(), act_tanh=True,
+                            unit_nhwc=unit_nhwc)
         return out
 
     def backward(self, lat, d_img, img, tag="g"):

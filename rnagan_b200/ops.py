@@ -375,14 +375,15 @@ def pack_edge_t(W, out):
     return out
 
 
-def conv_up_img_col(lo, w_colT, Cimg, col, out, bias=None, act_tanh=False):
+def conv_up_img_col(lo, w_colT, Cimg, col, out, bias=None, act_tanh=False, unit_nhwc=False):
     """Image-side transposed conv as GEMM (K = Cp only, each input pixel read once) + col2im:
-    lo bf16 [B, H, W, Cp] -> out fp32 NCHW [B, Cimg, 2H, 2W]; col: fp32 scratch [B*H*W, 16*Cimg]."""
+    lo bf16 [B, H, W, Cp] -> out fp32 NCHW [B, Cimg, 2H, 2W]; col: fp32 scratch [B*H*W, 16*Cimg].
+    unit_nhwc: out is instead the synthesis result (x + 1) / 2 as fp32 NHWC [B, 2H, 2W, Cimg]."""
     B, H, W, Cp = lo.shape
     N = 16 * Cimg
     gemm_nt(lo.view(B * H * W, Cp), w_colT, out=col, N=N)
-    _lib.check(_lib.lib().rg_col2im_img(_p(col), col.stride(0), _p(bias), int(act_tanh), B, Cimg, H, W, _p(out),
-                                        _st()), "rg_col2im_img")
+    _lib.check(_lib.lib().rg_col2im_img(_p(col), col.stride(0), _p(bias), int(act_tanh) | (2 if unit_nhwc else 0), B,
+                                        Cimg, H, W, _p(out), _st()), "rg_col2im_img")
     return out
 
 
