@@ -64,6 +64,25 @@ int rg_cast_pad_bf16(const float* src, void* dst, int rows, int cols, int cols_p
 /* lo[b,i,j,p] = sum_{kh,kw,s} hi[b,2i-1+kh,2j-1+kw,s] * W[p,s,kh,kw]
  * critic forward nn.Conv2d(4,2,1) (torchgan DCGANDiscriminator; args src/histopathology_gan.py:186-192) and
  * generator dgrad (autograd of src/dcgan.py:52). */
+/* Optional fused elementwise backward in the epilogue of an input-gradient contraction (rg_conv_down / rg_conv_up /
+ * rg_gemm_nt_ld with a bf16 output; pass NULL for none): `aux` is a bf16 tensor with the layout of the output.
+ *   mode 1  the layer below has no BatchNorm: out = acc * LeakyReLU'(aux), aux = its stored activation h
+ *           (autograd of nn.LeakyReLU(0.2) after the critic's first Conv2d [tg])
+ *   mode 2  BatchNorm2d + LeakyReLU below: aux = the pre-BN activation a; out = du = acc * LeakyReLU'(scale*a + shift),
+ *           and with stats_ws the per-CTA partials become S(du), S(du * xhat) with xhat = (a - mean) * rstd, i.e.
+ *           rg_bn_bwd_reduce without a pass over dh and a; finish with rg_reduce_partials + rg_bn_bwd_apply(du_in=1). */
+typedef struct rg_epilogue_aux {
+  const void* aux;
+  int mode;
+  const float* mean;
+  const float* rstd;
+  const float* scale;
+  const float* shift;
+  float slope;
+} rg_epilogue_aux;
+/* out[k][c] = sum over the rg_stats_parts() rows of stats_ws[part][k][c] (fixed order), KC = K*C values */
+int rg_reduce_partials(const float* stats_ws, int KC, float* out, rg_stream_t st);
+
 /* stats_ws (all three bf16 convolutions; may be NULL): fp32 [rg_stats_parts()][2][C_out] of rg_stats_ws_bytes(C_out)
  * bytes.  When given, the epilogue also accumulates per-channel sums and sums of squares of the STORED (bf16-rounded)
  * outputs, one row per CTA in a fixed order (deterministic) -- the nn.BatchNorm2d batch statistics
@@ -71,7 +90,7 @@ int rg_cast_pad_bf16(const float* src, void* dst, int rows, int cols, int cols_p
 size_t rg_stats_ws_bytes(int C);
 int rg_stats_parts(void);
 int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int W, int Cs, int Cp, float* stats_ws,
-                 rg_stream_t st);
+                 const rg_epilogue_aux* aux, rg_stream_t st);
 /* hi[b,y,x,s] = sum lo[b,i,j,p] * W[p,s,kh,kw] over y=2i-1+kh, x=2j-1+kw
  * generator forward nn.ConvTranspose2d(4,2,1) (src/dcgan.py:52) and critic dgrad. */
 /* w: either w_up (w_is_down=0; K-major B, best for Cs <= 128 where the extra packed copy is tiny) or w_down
@@ -79,7 +98,7 @@ int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int
 /* w_is_down = 2: w is the merged-phase operand of rg_pack_up9_from_down (Cs == 64, at least two 128-pixel M tiles): one
  * tile then contracts all four output phases, fetching the 9 distinct shifted input tiles once instead of 16 times. */
 int rg_conv_up(const void* lo, const void* w, int w_is_down, void* hi, int B, int H, int W, int Cp, int Cs,
-               float* stats_ws, rg_stream_t st);
+               float* stats_ws, const rg_epilogue_aux* aux, rg_stream_t st);
 size_t rg_up9_elems(int Cp);
 int rg_pack_up9_from_down(const void* w_down, void* w_up9, int Cp, int Cs, rg_stream_t st);
 /* same as rg_conv_up for Cs<=16 image channels, fp32 NCHW output, optional bias + tanh
@@ -107,6 +126,10 @@ int rg_gemm_nt(const void* A, const void* Bw, void* C, int M, int N, int K, int 
 /* same with explicit leading dimensions (K, N arbitrary: TMA zero-fills the k tail) */
 int rg_gemm_nt_ld(const void* A, int lda, const void* Bw, int ldb, void* C, int M, int N, int K, int ldc,
                   const float* col_scale, const float* col_shift, float slope, int out_f32, rg_stream_t st);
+/* bf16 C[M,N] = A[M,K] . Bw[N,K]^T with fused statistics and / or the fused elementwise backward (see rg_epilogue_aux):
+ * the generator's image-side input gradient feeding its last BatchNorm (autograd of src/dcgan.py:82). */
+int rg_gemm_nt_bwd(const void* A, int lda, const void* Bw, int ldb, void* C, int M, int N, int K, int ldc,
+                   float* stats_ws, const rg_epilogue_aux* aux, rg_stream_t st);
 /* C[M,N] = act((A[M,K] . Bw[K,N]) * col_scale + col_shift) with Bw row-major [K][N]: the input gradient of an
  * nn.Linear whose weight is [out=K][in=N] (autograd of src/betaVAE.py:31,76,86; betaVAE training, config 5). */
 int rg_gemm_nn(const void* A, int lda, const void* Bw, int ldb, void* C, int M, int N, int K, int ldc,

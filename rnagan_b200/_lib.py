@@ -32,8 +32,10 @@ SIGNATURES = {
     "rg_cast_pad_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rg_stats_ws_bytes": (_sz, [_i]),
     "rg_stats_parts": (_i, []),
-    "rg_conv_down": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
-    "rg_conv_up": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rg_conv_down": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rg_conv_up": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rg_gemm_nt_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rg_reduce_partials": (_i, [_vp, _i, _vp, _vp]),
     "rg_conv_up_img": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rg_conv_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "rg_conv_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _f, _vp, _f, _i, _vp]),
@@ -90,6 +92,13 @@ SIGNATURES = {
     "rg_vae_latent_grad": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
     "rg_vae_loss_finalize": (_i, [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp]),
 }
+
+
+class EpilogueAux(ctypes.Structure):
+    """rg_epilogue_aux of include/rnagan_b200.h."""
+    _fields_ = [("aux", _vp), ("mode", _i), ("mean", _vp), ("rstd", _vp), ("scale", _vp), ("shift", _vp),
+                ("slope", _f)]
+
 
 _lib = None
 

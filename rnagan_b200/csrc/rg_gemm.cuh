@@ -26,7 +26,8 @@ constexpr int kMaxStages = 8;
 constexpr int kAStageBytes = 128 * 128;      // 16 KiB: 128 pixel rows x 64 channels
 constexpr int kStagingBytes = 128 * 128;     // one 64-column bf16 slab of the output tile (epilogue -> TMA store)
 constexpr int kBarBytes = 256;
-constexpr int kAffineBytes = 2048;           // per-column scale / shift of the current tile (2 x 256 floats)
+constexpr int kAffineBytes = 4096;           // per-column vectors of the current tile: scale, shift (+ mean, rstd for the
+                                             // fused BatchNorm backward), 4 x 256 floats
 constexpr int kStatBytes = 4096;             // per-warp column sums of one slab (4 warps x 2 x 64 floats), two slab parities
 constexpr int kSmemFixedBytes = kBarBytes + kAffineBytes + kStatBytes + 1024 /*alignment slack*/;
 constexpr int kSmemMaxBytes = 232448;        // 227 KiB: the sm_100 per-CTA dynamic shared memory limit
@@ -72,6 +73,18 @@ struct FwdArgs {
                           // shifted A tiles of an M tile are fetched once instead of 16 times; TMEM slab q = phase q
   int8_t mg_nph[9];       // merged: how many phases tap t9 = (dh+1)*3 + (dw+1) feeds (1, 2 or 4) ...
   int8_t mg_phase[9][4];  // ... and which ones; their B slabs sit in this order in the stage (packed by rg_pack_up9)
+  // Fused elementwise backward of the layer this GEMM's output is the input gradient of (TMA-store epilogue only):
+  // aux has the layout of `out`.  mode 1 (no BatchNorm): out = acc * lrelu'(aux), aux = the stored activation h.
+  // mode 2 (BatchNorm + LeakyReLU): aux = the pre-BN activation a; out = du = acc * lrelu'(scale*a + shift) and, with
+  // `stats`, the per-CTA partial sums are S(du) and S(du * xhat), xhat = (a - mean) * rstd -- rg_bn_bwd_reduce without
+  // a pass over dh and a.
+  const __nv_bfloat16* aux;
+  int aux_mode;
+  const float* aux_mean;
+  const float* aux_rstd;
+  const float* aux_scale;
+  const float* aux_shift;
+  float aux_slope;
   int whatif;             // profiling experiments (RG_WHATIF): 1 no MMA, 2 no epilogue work, 4 no A loads, 8 no B loads
   long long* prof;        // optional [gridDim.x][12] clock64 totals per role (tools/gemm_prof.py); null in production
   float* stats;           // optional [gridDim.x][2][n_total]: per-CTA column sums / sums of squares of the STORED
@@ -132,6 +145,8 @@ struct PipeSmem {
   uint32_t* tmem_slot;
   float* s_scale;   // [256] per-column epilogue scale of the current tile
   float* s_shift;   // [256]
+  float* s_mean;    // [256] fused BatchNorm backward only
+  float* s_rstd;    // [256]
   float* s_stat;    // [2 slab parities][4 warps][2][64]
 };
 
@@ -149,7 +164,9 @@ __device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw, int ring_bytes, int
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
   s.s_scale = reinterpret_cast<float*>(base + ring_bytes + staging_bytes + kBarBytes);
   s.s_shift = s.s_scale + 256;
-  s.s_stat = s.s_shift + 256;
+  s.s_mean = s.s_scale + 512;
+  s.s_rstd = s.s_scale + 768;
+  s.s_stat = s.s_scale + 1024;
   uint32_t dyn;
   asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
   if (reinterpret_cast<uint8_t*>(s.s_stat) + kStatBytes > raw + dyn) __trap();   // host under-provisioned the launch
@@ -218,7 +235,8 @@ __device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(_
 // Tile order: phase fastest, then M slot, then N tile -- CTAs running at the same time share the A tiles of an M slot
 // across the four output phases of the transposed form (L2 hits) and a persistent CTA keeps its N tile for long runs
 // (statistics accumulate in registers and reach memory only when the N tile changes).
-template <int OUT, int CG>
+// AUX: compile the fused elementwise-backward epilogue (rg_epilogue_aux) in; the plain instantiation carries none of it
+template <int OUT, int CG, bool AUX = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ FwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -417,6 +435,8 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
     const bool lrelu = p.slope != 1.0f;
     const bool use_tma = (OUT == OUT_BF16_NHWC) && p.tma_store;
     const bool do_stats = use_tma && (p.stats != nullptr);
+    const bool aux_on = AUX && use_tma && p.aux != nullptr && p.aux_mode != 0;
+    const bool aux_bn = aux_on && p.aux_mode == 2;
     // the tempty barrier lives in the leader CTA
     const uint32_t tempty_addr0 = CG > 1 ? mapa_rank(smem_u32(&s.tempty[0]), 0) : smem_u32(&s.tempty[0]);
     // statistics: thread et owns (quantity k = et >> 6, column (et & 63) of every slab) of this CTA's partial row
@@ -448,13 +468,20 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
       const int n0 = n_tile * p.block_n;
 
       // per-column scale / shift of this tile -> smem (one broadcast read per element instead of global loads)
-      if (affine && n_tile != staged_n_tile) {                 // reload only when the column range changes
+      if ((affine || aux_bn) && n_tile != staged_n_tile) {     // reload only when the column range changes
         asm volatile("bar.sync 1, 128;" ::: "memory");        // previous tile's readers are done
         for (int cc = et; cc < p.block_n; cc += 128) {
           const int col = n0 + cc;
           const bool ok = col < p.n_valid;
-          s.s_scale[cc] = (ok && p.col_scale) ? __ldg(p.col_scale + col) : 1.0f;
-          s.s_shift[cc] = (ok && p.col_shift) ? __ldg(p.col_shift + col) : 0.0f;
+          if (aux_bn) {
+            s.s_scale[cc] = ok ? __ldg(p.aux_scale + col) : 1.0f;
+            s.s_shift[cc] = ok ? __ldg(p.aux_shift + col) : 0.0f;
+            s.s_mean[cc] = ok ? __ldg(p.aux_mean + col) : 0.0f;
+            s.s_rstd[cc] = ok ? __ldg(p.aux_rstd + col) : 0.0f;
+          } else {
+            s.s_scale[cc] = (ok && p.col_scale) ? __ldg(p.col_scale + col) : 1.0f;
+            s.s_shift[cc] = (ok && p.col_shift) ? __ldg(p.col_shift + col) : 0.0f;
+          }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         staged_n_tile = n_tile;
@@ -503,6 +530,16 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
             asm volatile("bar.sync 1, 128;" ::: "memory");
           }
           float csum[2] = {0.0f, 0.0f}, csq[2] = {0.0f, 0.0f};
+          uint4 ax[8];                                      // this row's 64 aux values of the slab (fused backward)
+          if (aux_on) {
+            // merged tiles: slab = output phase, so the pixel changes per slab and the channels start at 0
+            const int ys = p.merged ? i * p.sy + p.oy[sl] : y, xs_ = p.merged ? j * p.sx + p.ox[sl] : x;
+            const __nv_bfloat16* ap = p.aux + (static_cast<size_t>(b * p.OH + ys) * p.OW + xs_) * p.OC +
+                                      (p.merged ? 0 : n0 + sl * 64);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              ax[g] = row_ok ? *reinterpret_cast<const uint4*>(ap + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+          }
           uint32_t vv[2][32];
           tmem_ld_32x32(taddr + sl * 64, vv[0]);            // both halves in flight before the single wait
           tmem_ld_32x32(taddr + sl * 64 + 32, vv[1]);
@@ -530,6 +567,30 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
                 v[e] = __float_as_uint(fmaxf(f, f * p.slope));
               }
             }
+            float xh[32];                                   // mode 2: normalised activation of each element
+            if (aux_on) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&ax[hh * 4 + g]);
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  const float2 av = __bfloat1622float2(h2[e2]);
+                  const int e = g * 8 + e2 * 2;
+                  if (aux_bn) {
+                    const int pc = (p.merged ? hh * 32 : c) + e;   // merged: every slab holds the SAME 64 channels
+                    const float u0 = fmaf(av.x, s.s_scale[pc], s.s_shift[pc]);
+                    const float u1 = fmaf(av.y, s.s_scale[pc + 1], s.s_shift[pc + 1]);
+                    if (!(u0 > 0.0f)) v[e] = __float_as_uint(__uint_as_float(v[e]) * p.aux_slope);
+                    if (!(u1 > 0.0f)) v[e + 1] = __float_as_uint(__uint_as_float(v[e + 1]) * p.aux_slope);
+                    xh[e] = (av.x - s.s_mean[pc]) * s.s_rstd[pc];
+                    xh[e + 1] = (av.y - s.s_mean[pc + 1]) * s.s_rstd[pc + 1];
+                  } else {
+                    if (!(av.x > 0.0f)) v[e] = __float_as_uint(__uint_as_float(v[e]) * p.aux_slope);
+                    if (!(av.y > 0.0f)) v[e + 1] = __float_as_uint(__uint_as_float(v[e + 1]) * p.aux_slope);
+                  }
+                }
+              }
+            }
             // pack to bf16 and write this row's 64 bytes: 16-byte chunk index XOR (row & 7) = the SWIZZLE_128B
             // pattern the output tensor map expects (and conflict-free: 8 rows cover all 8 chunk positions)
             uint8_t* rowp = buf + row * 128;
@@ -548,8 +609,13 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
 #pragma unroll
               for (int e = 0; e < 32; ++e) xs[e] = row_ok ? bf16_round(__uint_as_float(v[e])) : 0.0f;
               csum[hh] = warp_colsum32(xs, lane);
+              if (aux_bn) {
 #pragma unroll
-              for (int e = 0; e < 32; ++e) xs[e] *= xs[e];
+                for (int e = 0; e < 32; ++e) xs[e] *= xh[e];          // S(du * xhat)
+              } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) xs[e] *= xs[e];          // S(a^2)
+              }
               csq[hh] = warp_colsum32(xs, lane);
             }
           }

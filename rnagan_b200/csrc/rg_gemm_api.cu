@@ -156,6 +156,10 @@ static int ensure_attrs() {
                                  kSmemMaxBytes));
     RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_BF16_NHWC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kSmemMaxBytes));
+    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_BF16_NHWC, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSmemMaxBytes));
+    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_BF16_NHWC, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSmemMaxBytes));
     RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_F32_NHWC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kSmemMaxBytes));
     RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_F32_NCHW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -166,10 +170,10 @@ static int ensure_attrs() {
   return 0;
 }
 
-template <int OUT, int CG>
+template <int OUT, int CG, bool AUX = false>
 static int launch_fwd_t(const GemmMaps& maps, const FwdArgs& a, int grid, size_t smem, cudaStream_t st) {
   if (CG == 1) {
-    gemm_fwd_kernel<OUT, CG><<<grid, kGemmThreads, smem, st>>>(maps, a);
+    gemm_fwd_kernel<OUT, CG, AUX><<<grid, kGemmThreads, smem, st>>>(maps, a);
   } else {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -184,7 +188,7 @@ static int launch_fwd_t(const GemmMaps& maps, const FwdArgs& a, int grid, size_t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RG_CUDA(cudaLaunchKernelEx(&cfg, gemm_fwd_kernel<OUT, CG>, maps, a));
+    RG_CUDA(cudaLaunchKernelEx(&cfg, gemm_fwd_kernel<OUT, CG, AUX>, maps, a));
   }
   RG_LAUNCH_CHECK("gemm_fwd_kernel");
   return 0;
@@ -193,12 +197,35 @@ static int launch_fwd_t(const GemmMaps& maps, const FwdArgs& a, int grid, size_t
 size_t stats_ws_floats(int C) { return static_cast<size_t>(num_sms()) * 2 * C; }
 
 // cg: the CTA-group size the caller encoded the B map for (pick_cg).  stats_ws: optional [num_sms][2][n_total] fp32.
-static int launch_fwd(GemmMaps& maps, FwdArgs& a, int out_kind, int cg, float* stats_ws, cudaStream_t st) {
+static int launch_fwd(GemmMaps& maps, FwdArgs& a, int out_kind, int cg, float* stats_ws, cudaStream_t st,
+                      const rg_epilogue_aux* aux = nullptr) {
   int rc = ensure_attrs();
   if (rc) return rc;
+  if (aux && aux->aux && aux->mode != 0) {
+    if (aux->mode != 1 && aux->mode != 2) {
+      set_error("rg_epilogue_aux: mode must be 0, 1 or 2 (got %d)", aux->mode);
+      return RG_EINVAL;
+    }
+    if (aux->mode == 2 && !(aux->mean && aux->rstd && aux->scale && aux->shift)) {
+      set_error("rg_epilogue_aux: mode 2 needs mean, rstd, scale and shift");
+      return RG_EINVAL;
+    }
+    if ((reinterpret_cast<uintptr_t>(aux->aux) & 15) != 0 || a.col_scale || a.col_shift || a.slope != 1.0f) {
+      set_error("rg_epilogue_aux: aux must be 16-byte aligned and excludes the affine / activation epilogue");
+      return RG_EINVAL;
+    }
+    a.aux = static_cast<const __nv_bfloat16*>(aux->aux);
+    a.aux_mode = aux->mode;
+    a.aux_mean = aux->mean; a.aux_rstd = aux->rstd; a.aux_scale = aux->scale; a.aux_shift = aux->shift;
+    a.aux_slope = aux->slope;
+  }
   static const bool allow_tma_store = env_flag("RG_TMA_STORE", true);
   a.tma_store = (allow_tma_store && out_kind == OUT_BF16_NHWC && a.block_n % 64 == 0 && a.OC % 8 == 0 &&
                  (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) ? 1 : 0;
+  if (a.aux_mode != 0 && !(a.tma_store && a.n_total % 64 == 0 && a.n_valid == a.n_total)) {
+    set_error("the fused elementwise backward needs a bf16 output with a multiple of 64 channels (n=%d)", a.n_total);
+    return RG_EINVAL;
+  }
   if (stats_ws && !(a.tma_store && a.n_total % 64 == 0)) {
     set_error("fused statistics need a bf16 output with a multiple of 64 channels (n_total=%d block_n=%d)", a.n_total,
               a.block_n);
@@ -241,6 +268,10 @@ static int launch_fwd(GemmMaps& maps, FwdArgs& a, int out_kind, int cg, float* s
     RG_CUDA(cudaMemsetAsync(stats_ws + static_cast<size_t>(grid) * 2 * a.n_total, 0, (num_sms() - grid) * row, st));
   }
   if (out_kind == OUT_BF16_NHWC) {
+    if (a.aux_mode != 0) {
+      if (cg == 2) return launch_fwd_t<OUT_BF16_NHWC, 2, true>(maps, a, grid, smem, st);
+      return launch_fwd_t<OUT_BF16_NHWC, 1, true>(maps, a, grid, smem, st);
+    }
     if (cg == 2) return launch_fwd_t<OUT_BF16_NHWC, 2>(maps, a, grid, smem, st);
     return launch_fwd_t<OUT_BF16_NHWC, 1>(maps, a, grid, smem, st);
   }
@@ -700,7 +731,7 @@ int rg_cast_pad_bf16(const float* src, void* dst, int rows, int cols, int cols_p
 }
 
 int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int W, int Cs, int Cp, float* stats_ws,
-                 rg_stream_t st_) {
+                 const rg_epilogue_aux* aux, rg_stream_t st_) {
   cudaStream_t st = static_cast<cudaStream_t>(st_);
   RG_CHECK_ARG(hi && w_down && lo, "rg_conv_down: null pointer");
   RG_CHECK_ARG(B > 0 && is_pow2(H) && is_pow2(W), "rg_conv_down: H, W must be powers of two (got %d x %d)", H, W);
@@ -731,12 +762,12 @@ int rg_conv_down(const void* hi, const void* w_down, void* lo, int B, int H, int
   a.out = lo;
   a.OH = H; a.OW = W; a.OC = Cp;
   a.n_valid = Cp;
-  return launch_fwd(maps, a, OUT_BF16_NHWC, cg, stats_ws, st);
+  return launch_fwd(maps, a, OUT_BF16_NHWC, cg, stats_ws, st, aux);
 }
 
 // all four output phases of an M tile in one tile (weights packed by rg_pack_up9_from_down)
 static int conv_up_merged(const void* lo, const void* w9, void* out, int B, int H, int W, int Cp, int Cs,
-                          float* stats_ws, cudaStream_t st) {
+                          float* stats_ws, const rg_epilogue_aux* aux, cudaStream_t st) {
   RG_CHECK_ARG(Cs == 64 && Cp % 64 == 0, "rg_conv_up (merged phases): need Cs == 64, Cp %% 64 == 0");
   GemmMaps maps;
   FwdArgs a;
@@ -782,11 +813,12 @@ static int conv_up_merged(const void* lo, const void* w9, void* out, int B, int 
   a.OH = 2 * H; a.OW = 2 * W; a.OC = Cs;
   a.sy = a.sx = 2;
   a.n_valid = Cs;
-  return launch_fwd(maps, a, OUT_BF16_NHWC, 2, stats_ws, st);
+  return launch_fwd(maps, a, OUT_BF16_NHWC, 2, stats_ws, st, aux);
 }
 
 static int conv_up_common(const void* lo, const void* w, void* out, const float* bias, int act_tanh, int B, int H,
-                          int W, int Cp, int Cs, int out_kind, bool w_is_down, float* stats_ws, cudaStream_t st) {
+                          int W, int Cp, int Cs, int out_kind, bool w_is_down, float* stats_ws, cudaStream_t st,
+                          const rg_epilogue_aux* aux = nullptr) {
   RG_CHECK_ARG(lo && w && out, "rg_conv_up: null pointer");
   RG_CHECK_ARG(B > 0 && is_pow2(H) && is_pow2(W), "rg_conv_up: H, W must be powers of two (got %d x %d)", H, W);
   RG_CHECK_ARG(Cp % 64 == 0, "rg_conv_up: need Cp %% 64 == 0 (Cp=%d)", Cp);
@@ -835,19 +867,19 @@ static int conv_up_common(const void* lo, const void* w, void* out, const float*
   a.n_valid = Cs;
   a.col_shift = bias;
   a.act_tanh = act_tanh;
-  return launch_fwd(maps, a, out_kind, cg, stats_ws, st);
+  return launch_fwd(maps, a, out_kind, cg, stats_ws, st, aux);
 }
 
 int rg_conv_up(const void* lo, const void* w, int w_is_down, void* hi, int B, int H, int W, int Cp, int Cs,
-               float* stats_ws, rg_stream_t st_) {
+               float* stats_ws, const rg_epilogue_aux* aux, rg_stream_t st_) {
   if (w_is_down == 2) {
     RG_CHECK_ARG(lo && w && hi && B > 0 && is_pow2(H) && is_pow2(W), "rg_conv_up: bad arguments");
-    return conv_up_merged(lo, w, hi, B, H, W, Cp, Cs, stats_ws, static_cast<cudaStream_t>(st_));
+    return conv_up_merged(lo, w, hi, B, H, W, Cp, Cs, stats_ws, aux, static_cast<cudaStream_t>(st_));
   }
   RG_CHECK_ARG(Cs % (w_is_down ? 64 : 16) == 0,
                "rg_conv_up: need Cs %% 64 == 0 with w_down, %% 16 with w_up (Cs=%d); use rg_conv_up_img for images", Cs);
   return conv_up_common(lo, w, hi, nullptr, 0, B, H, W, Cp, Cs, OUT_BF16_NHWC, w_is_down != 0, stats_ws,
-                        static_cast<cudaStream_t>(st_));
+                        static_cast<cudaStream_t>(st_), aux);
 }
 
 int rg_conv_up_img(const void* lo, const void* w_up, float* img, const float* bias, int act_tanh, int B, int H, int W,
@@ -859,7 +891,8 @@ int rg_conv_up_img(const void* lo, const void* w_up, float* img, const float* bi
 
 static int gemm_plain(const void* A, int lda, const void* Bw, int ldb, bool b_is_kn, void* C, int M, int N, int K,
                       int ldc, const float* col_scale, const float* col_shift, float slope, int out_f32,
-                      cudaStream_t st, const char* name) {
+                      cudaStream_t st, const char* name, float* stats_ws = nullptr,
+                      const rg_epilogue_aux* aux = nullptr) {
   RG_CHECK_ARG(A && Bw && C, "%s: null pointer", name);
   RG_CHECK_ARG(M > 0 && N > 0 && K > 0 && lda >= K && lda % 8 == 0 && ldb % 8 == 0,
                "%s: need lda >= K and lda, ldb multiples of 8 elements (M=%d N=%d K=%d lda=%d ldb=%d)", name, M, N, K,
@@ -908,7 +941,7 @@ static int gemm_plain(const void* A, int lda, const void* Bw, int ldb, bool b_is
   a.col_shift = col_shift;
   a.slope = slope;
   a.act_tanh = out_tanh;
-  return launch_fwd(maps, a, out_kind, cg, nullptr, st);
+  return launch_fwd(maps, a, out_kind, cg, stats_ws, st, aux);
 }
 
 int rg_gemm_nt(const void* A, const void* Bw, void* C, int M, int N, int K, int ldc, const float* col_scale,
@@ -921,6 +954,12 @@ int rg_gemm_nt_ld(const void* A, int lda, const void* Bw, int ldb, void* C, int 
                   const float* col_scale, const float* col_shift, float slope, int out_f32, rg_stream_t st_) {
   return gemm_plain(A, lda, Bw, ldb, false, C, M, N, K, ldc, col_scale, col_shift, slope, out_f32,
                     static_cast<cudaStream_t>(st_), "rg_gemm_nt_ld");
+}
+
+int rg_gemm_nt_bwd(const void* A, int lda, const void* Bw, int ldb, void* C, int M, int N, int K, int ldc,
+                   float* stats_ws, const rg_epilogue_aux* aux, rg_stream_t st_) {
+  return gemm_plain(A, lda, Bw, ldb, false, C, M, N, K, ldc, nullptr, nullptr, 1.0f, 0, static_cast<cudaStream_t>(st_),
+                    "rg_gemm_nt_bwd", stats_ws, aux);
 }
 
 int rg_gemm_nn(const void* A, int lda, const void* Bw, int ldb, void* C, int M, int N, int K, int ldc,

@@ -1362,6 +1362,13 @@ int rg_bn_finalize_partials(const float* stats_ws, const float* gamma, const flo
   return 0;
 }
 
+int rg_reduce_partials(const float* stats_ws, int KC, float* out, rg_stream_t st) {
+  RG_CHECK_ARG(stats_ws && out && KC > 0, "rg_reduce_partials: bad arguments");
+  colreduce_stage2<<<ceil_div(KC, 32), 1024, 0, static_cast<cudaStream_t>(st)>>>(stats_ws, num_sms(), KC, out);
+  RG_LAUNCH_CHECK("rg_reduce_partials");
+  return 0;
+}
+
 int rg_bn_act(const void* a, const float* scale, const float* shift, float slope, void* h, int M, int C,
               rg_stream_t st) {
   RG_CHECK_ARG(a && scale && shift && h, "rg_bn_act: null pointer");

@@ -29,6 +29,12 @@ SLOPE = 0.2
 FUSED_STATS = os.environ.get("RG_FUSED_STATS", "1") != "0"
 # the Cs == 64 transposed convolutions contract all four output phases in one tile (RG_MERGED_UP=0: one phase per tile)
 MERGED_UP = os.environ.get("RG_MERGED_UP", "1") != "0"
+# the LeakyReLU / BatchNorm backward masks and the BatchNorm backward sums are computed in the epilogue of the
+# input-gradient contraction that produces dh (RG_FUSED_BWD=0: separate rg_bn_bwd_reduce / rg_lrelu_bwd passes)
+# Measured on B200 (profiles/r1_step_profile_fused_bwd.txt): OFF by default.  The fusion removes 22 of 30
+# rg_bn_bwd_reduce and 3 of 5 rg_lrelu_bwd launches (-0.87 ms/step) but the per-thread aux loads and the extra epilogue
+# arithmetic slow the contractions by 1.4 ms/step; it needs a TMA-staged aux tile to pay off.
+FUSED_BWD = os.environ.get("RG_FUSED_BWD", "0") != "0"
 
 
 def _grad_of(p):
@@ -143,14 +149,33 @@ class _BN:
                 s.shift.copy_(m.bias - s.mean * s.scale)
         ops.bn_act(a, s.scale, s.shift, self.slope, h, M, self.C)
 
-    def backward(self, dh, a, da, M, param_grads=False, acc_gamma=0.0, acc_beta=0.0, add=None, du_out=None, tag=""):
-        """da = d(loss)/d(a) from dh = d(loss)/d(h); optionally (accumulating) gamma/beta gradients."""
+    def bwd_ws(self, slot=1):
+        """Partial-sum scratch for the fused backward (None: unfused)."""
+        if not FUSED_BWD or self.C % 64 != 0:
+            return None
+        return ops.stats_ws(self.C, self.device, slot=slot)
+
+    def aux(self, a, tag=""):
+        """rg_epilogue_aux mode 2 descriptor: the contraction producing dh for THIS layer stores du and sums it."""
         s = self.st(tag)
-        ops.bn_bwd_reduce(dh, a, s.mean, s.rstd, s.scale, s.shift, self.slope, M, self.C, s.bsums)
+        return ("bn", a, s.mean, s.rstd, s.scale, s.shift, self.slope)
+
+    def backward(self, dh, a, da, M, param_grads=False, acc_gamma=0.0, acc_beta=0.0, add=None, du_out=None, tag="",
+                 fused=None):
+        """da = d(loss)/d(a) from dh = d(loss)/d(h); optionally (accumulating) gamma/beta gradients.
+        fused: per-CTA partial sums left by the contraction that produced `dh`, which then already holds
+        du = dh * lrelu'(u) (see aux): only the small fixed-order reduce of the partials remains."""
+        s = self.st(tag)
+        slope = self.slope
+        if fused is not None:
+            ops.reduce_partials(fused, s.bsums)
+            slope = 1.0                      # the mask is applied already: rg_bn_bwd_apply takes dh as du
+        else:
+            ops.bn_bwd_reduce(dh, a, s.mean, s.rstd, s.scale, s.shift, self.slope, M, self.C, s.bsums)
         if param_grads:
             ops.bn_param_grads(s.bsums, _grad_of(self.mod.weight), _grad_of(self.mod.bias), self.C, acc_gamma,
                                acc_beta)
-        ops.bn_bwd_apply(dh, a, add, s.mean, s.rstd, s.scale, s.shift, self.slope, s.bsums, M, self.C, da, du_out)
+        ops.bn_bwd_apply(dh, a, add, s.mean, s.rstd, s.scale, s.shift, slope, s.bsums, M, self.C, da, du_out)
 
 
 def _up_operand(eng, l, npix):
@@ -280,22 +305,31 @@ class GeneratorEngine:
         ops.unpack_edge_grad(dcol, _grad_of(self.conv_last.weight), acc=0.0)
         self.sync.layer_done(self.conv_last.weight, self.conv_last.bias)
         dh = g(f"bwd.dh{n}", (B, H, H, self.Cn))
-        ops.gemm_nt(col, self.w_col_last, out=dh.view(npix, self.Cn))
+        # every contraction that produces dh for a BatchNorm'd layer stores du = dh * lrelu'(u) and sums it (fused)
+        fused = self.bns[n - 1].bwd_ws()
+        if fused is not None:
+            ops.gemm_nt_bwd(col, self.w_col_last, dh.view(npix, self.Cn), stats=fused,
+                            aux=self.bns[n - 1].aux(g(f"{tag}.a{n}", (B, H, H, self.Cn)), tag))
+        else:
+            ops.gemm_nt(col, self.w_col_last, out=dh.view(npix, self.Cn))
         for l in range(n, 0, -1):
             c, bn = self.convs[l - 1], self.bns[l - 1]
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
             a = g(f"{tag}.a{l}", (B, H, H, Cs))
             da = g(f"bwd.da{l}", (B, H, H, Cs))
-            bn.backward(dh, a, da, B * H * H, param_grads=True, tag=tag)
+            bn.backward(dh, a, da, B * H * H, param_grads=True, tag=tag, fused=fused)
             H //= 2
             hprev = g(f"{tag}.h{l - 1}", (B, H, H, Cp))
             ops.conv_wgrad(hprev, da, _grad_of(c.weight))
             self.sync.layer_done(c.weight, bn.mod.weight, bn.mod.bias)
             dh = g(f"bwd.dh{l - 1}", (B, H, H, Cp))
-            ops.conv_down(da, self.w_down[l - 1], out=dh)
+            bnp = self.bns[l - 2] if l >= 2 else self.bn0
+            fused = bnp.bwd_ws()
+            aux = bnp.aux(g(f"{tag}.a{l - 1}", (B, H, H, Cp)), tag) if fused is not None else None
+            ops.conv_down(da, self.w_down[l - 1], out=dh, stats=fused, aux=aux)
         a0 = g(f"{tag}.a0", (B, 4, 4, self.C0))
         da0 = g("bwd.da0", (B, 4, 4, self.C0))
-        self.bn0.backward(dh, a0, da0, B * 16, param_grads=True, tag=tag)
+        self.bn0.backward(dh, a0, da0, B * 16, param_grads=True, tag=tag, fused=fused)
         ops.proj_wgrad(lat, da0, _grad_of(self.conv0.weight))
         self.sync.layer_done(self.conv0.weight, self.bn0.mod.weight, self.bn0.mod.bias)
 
@@ -535,25 +569,40 @@ class CriticEngine:
             ops.head_wgrad(da6, hn, B, 16 * self.Cn, self.Cn, _grad_of(self.head.weight), acc)
             if final:
                 self.sync.layer_done(self.head.weight)
+        fuse = FUSED_BWD and not keep_du     # the gradient-penalty pass keeps dh AND du of every layer: unfused
+        fused = None
         for l in range(n, 0, -1):
             c, bn = self.convs[l - 1], self.bns[l - 1]
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
             a = g(f"{tag}.a{l}", (B, H, H, Cp))
             da = g(f"{tag}.da{l}", (B, H, H, Cp))
             du = g(f"{tag}.du{l}", (B, H, H, Cp)) if keep_du else None
-            bn.backward(dh, a, da, B * H * H, param_grads=params, acc_gamma=acc, acc_beta=acc, du_out=du, tag=tag)
+            bn.backward(dh, a, da, B * H * H, param_grads=params, acc_gamma=acc, acc_beta=acc, du_out=du, tag=tag,
+                        fused=fused)
             hprev = g(f"{tag}.h{l - 1}", (B, 2 * H, 2 * H, Cs))
             if params:
                 ops.conv_wgrad(da, hprev, _grad_of(c.weight), beta=acc)
                 if final:
                     self.sync.layer_done(c.weight, bn.mod.weight, bn.mod.bias)
             H *= 2
-            dh = g(f"{tag}.dh{l - 1}", (B, H, H, Cs))
-            ops.conv_up(da, self._wup(l, da.shape[0] * da.shape[1] * da.shape[2]), Cs, out=dh)
+            fused, aux = None, None
+            if l >= 2:
+                dh = g(f"{tag}.dh{l - 1}", (B, H, H, Cs))
+                if fuse:
+                    fused = self.bns[l - 2].bwd_ws()
+                    if fused is not None:
+                        aux = self.bns[l - 2].aux(g(f"{tag}.a{l - 1}", (B, H, H, Cs)), tag)
+            elif fuse:       # layer 0 has no BatchNorm: the LeakyReLU mask goes into the epilogue, output is da0
+                dh = g(f"{tag}.da0", (B, H, H, self.C0))
+                aux = ("lrelu", g(f"{tag}.h0", (B, H, H, self.C0)), SLOPE)
+            else:
+                dh = g(f"{tag}.dh0", (B, H, H, Cs))
+            ops.conv_up(da, self._wup(l, da.shape[0] * da.shape[1] * da.shape[2]), Cs, out=dh, stats=fused, aux=aux)
         h0 = g(f"{tag}.h0", (B, H, H, self.C0))
         da0 = g(f"{tag}.da0", (B, H, H, self.C0))
         npix = B * H * H
-        ops.lrelu_bwd(dh, h0, SLOPE, da0, npix, self.C0)
+        if not fuse:
+            ops.lrelu_bwd(dh, h0, SLOPE, da0, npix, self.C0)
         if params:
             ops.col_sum(da0, npix, self.C0, self.tmpC, _grad_of(self.conv0.bias), acc)
             col = g(f"{tag}.col", (npix, 64))
@@ -576,6 +625,7 @@ class CriticEngine:
         g = self.bufs.get
         n = self.n
         (ta, _), (tb, _) = passes
+        fused = [None, None]
         H = 4
         for i, (tag, c) in enumerate(passes):
             hn = g(f"{tag}.h{n}", (B, H, H, self.Cn))
@@ -592,19 +642,37 @@ class CriticEngine:
                 a = g(f"{tag}.a{l}", (B, H, H, Cp))
                 da = g(f"{tag}.da{l}", (B, H, H, Cp))
                 dh = g(f"{tag}.dh{l}", (B, H, H, Cp))
-                bn.backward(dh, a, da, B * H * H, param_grads=True, acc_gamma=float(i > 0), acc_beta=float(i > 0), tag=tag)
+                bn.backward(dh, a, da, B * H * H, param_grads=True, acc_gamma=float(i > 0), acc_beta=float(i > 0), tag=tag,
+                            fused=fused[i])
             da2 = self.bufs.joint(f"{ta}.da{l}", (B, H, H, Cp))
             hprev2 = self.bufs.joint(f"{ta}.h{l - 1}", (B, 2 * H, 2 * H, Cs))
             ops.conv_wgrad(da2, hprev2, _grad_of(c_.weight))
             self.sync.layer_done(c_.weight, bn.mod.weight, bn.mod.bias)
             H *= 2
-            dh2 = self.bufs.joint(f"{ta}.dh{l - 1}", (B, H, H, Cs))
-            ops.conv_up(da2, self._wup(l, da2.shape[0] * da2.shape[1] * da2.shape[2]), Cs, out=dh2)
+            fused = [None, None]
+            bnp = self.bns[l - 2] if l >= 2 else None
+            if bnp is not None and bnp.bwd_ws() is not None:
+                # BatchNorm statistics are per pass: one input-gradient launch per pass, each storing du of its pass
+                # and summing it (the joint launch could not: its two halves normalise with different vectors)
+                for i, (tag, _) in enumerate(passes):
+                    fused[i] = bnp.bwd_ws(slot=1 + i)
+                    da_t = g(f"{tag}.da{l}", (B, H // 2, H // 2, Cp))
+                    ops.conv_up(da_t, self._wup(l, B * (H // 2) * (H // 2)), Cs, out=g(f"{tag}.dh{l - 1}", (B, H, H, Cs)),
+                                stats=fused[i], aux=bnp.aux(g(f"{tag}.a{l - 1}", (B, H, H, Cs)), tag))
+            elif l == 1 and FUSED_BWD:
+                # layer 0 has no BatchNorm: joint launch with the LeakyReLU mask in the epilogue, output is da0
+                ops.conv_up(da2, self._wup(l, da2.shape[0] * da2.shape[1] * da2.shape[2]), Cs,
+                            out=self.bufs.joint(f"{ta}.da0", (B, H, H, self.C0)),
+                            aux=("lrelu", self.bufs.joint(f"{ta}.h0", (B, H, H, self.C0)), SLOPE))
+            else:
+                dh2 = self.bufs.joint(f"{ta}.dh{l - 1}", (B, H, H, Cs))
+                ops.conv_up(da2, self._wup(l, da2.shape[0] * da2.shape[1] * da2.shape[2]), Cs, out=dh2)
         npix = B * H * H
         h0 = self.bufs.joint(f"{ta}.h0", (B, H, H, self.C0))
         dh0 = self.bufs.joint(f"{ta}.dh0", (B, H, H, self.C0))
         da0 = self.bufs.joint(f"{ta}.da0", (B, H, H, self.C0))
-        ops.lrelu_bwd(dh0, h0, SLOPE, da0, 2 * npix, self.C0)
+        if not FUSED_BWD:
+            ops.lrelu_bwd(dh0, h0, SLOPE, da0, 2 * npix, self.C0)
         ops.col_sum(da0, 2 * npix, self.C0, self.tmpC, _grad_of(self.conv0.bias), 0.0)
         col = self.bufs.joint(f"{ta}.col", (npix, 64))
         dcol = g("bwd.dcol", (self.C0, 64), F32)
@@ -677,19 +745,27 @@ class CriticEngine:
             # conv_l's weight is final now; BN_l's gamma/beta were finalised by step 3 (l = n) or the previous turn
             self.sync.layer_done(c.weight, self.bns[l - 1].mod.weight, self.bns[l - 1].mod.bias)
             H *= 2
-            A_h = g(f"{tag}.Ah{l - 1}", (B, H, H, Cs))
-            ops.conv_up(T, self._wup(l, T.shape[0] * T.shape[1] * T.shape[2]), Cs, out=A_h)
+            wup = self._wup(l, T.shape[0] * T.shape[1] * T.shape[2])
             if l - 1 >= 1:
                 bnp = self.bns[l - 2]
                 a = g(f"{tag}.a{l - 1}", (B, H, H, Cs))
+                A_h = g(f"{tag}.Ah{l - 1}", (B, H, H, Cs))
+                fused = bnp.bwd_ws()
+                ops.conv_up(T, wup, Cs, out=A_h, stats=fused, aux=bnp.aux(a, tag) if fused is not None else None)
                 A_a = g(f"{tag}.Aa{l - 1}", (B, H, H, Cs))
                 Tn = g(f"{tag}.T{l - 1}", (B, H, H, Cs))
                 # note: overwrites bnp.bsums (step-2 sums of layer l-1 were consumed in step 3 already)
-                bnp.backward(A_h, a, Tn, B * H * H, param_grads=True, acc_gamma=1.0, acc_beta=0.0, add=A_a, tag=tag)
+                bnp.backward(A_h, a, Tn, B * H * H, param_grads=True, acc_gamma=1.0, acc_beta=0.0, add=A_a, tag=tag,
+                             fused=fused)
                 T = Tn
             else:
                 A_a0 = g(f"{tag}.Aa0", (B, H, H, self.C0))
-                ops.lrelu_bwd(A_h, h0, SLOPE, A_a0, npix0, self.C0)
+                if FUSED_BWD:
+                    ops.conv_up(T, wup, Cs, out=A_a0, aux=("lrelu", h0, SLOPE))
+                else:
+                    A_h = g(f"{tag}.Ah{l - 1}", (B, H, H, Cs))
+                    ops.conv_up(T, wup, Cs, out=A_h)
+                    ops.lrelu_bwd(A_h, h0, SLOPE, A_a0, npix0, self.C0)
                 ops.gemm_tn(A_a0.view(npix0, self.C0), col_x, out=dcol)
                 ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=1.0)
                 ops.col_sum(A_a0, npix0, self.C0, self.tmpC, _grad_of(self.conv0.bias), 0.0)

@@ -158,7 +158,38 @@ def stats_ws(C, device, slot=0):
     return t
 
 
-def conv_down(hi, w_down, out=None, stats=None):
+def _aux(aux):
+    """aux: None, ("lrelu", h, slope) or ("bn", a, mean, rstd, scale, shift, slope) -> (ctypes pointer | None, keepalive)."""
+    if aux is None:
+        return None, None
+    import ctypes
+    if aux[0] == "lrelu":
+        st = _lib.EpilogueAux(aux[1].data_ptr(), 1, None, None, None, None, float(aux[2]))
+    else:
+        _, a, mean, rstd, scale, shift, slope = aux
+        st = _lib.EpilogueAux(a.data_ptr(), 2, mean.data_ptr(), rstd.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                              float(slope))
+    return ctypes.addressof(st), st
+
+
+def reduce_partials(stats, out):
+    """out[k, c] = sum over the per-CTA rows of stats [parts, K, C] (fixed order)."""
+    _lib.check(_lib.lib().rg_reduce_partials(_p(stats), out.numel(), _p(out), _st()), "rg_reduce_partials")
+
+
+def gemm_nt_bwd(A, Bw, out, stats=None, aux=None):
+    """bf16 out[M, N] = A[M, K] @ Bw[N, K]^T with fused statistics / elementwise backward (see rg_epilogue_aux)."""
+    _chk(A, BF16, "A", True); _chk(Bw, BF16, "Bw", True)
+    M, K = A.shape
+    N = Bw.shape[0]
+    ap, keep = _aux(aux)
+    _prof("gemm_nt", 2.0 * M * N * K, lambda: _lib.check(
+        _lib.lib().rg_gemm_nt_bwd(_p(A), A.stride(0), _p(Bw), Bw.stride(0), _p(out), M, N, K, out.stride(0), _p(stats),
+                                  ap, _st()), "rg_gemm_nt_bwd"))
+    return out
+
+
+def conv_down(hi, w_down, out=None, stats=None, aux=None):
     """hi bf16 [B, 2H, 2W, Cs], w_down bf16 [Cp, 16*Cs] -> lo bf16 [B, H, W, Cp] (+ fused BN statistics)."""
     _chk(hi, BF16, "hi"); _chk(w_down, BF16, "w_down")
     B, H2, W2, Cs = hi.shape
@@ -166,20 +197,23 @@ def conv_down(hi, w_down, out=None, stats=None):
     H, W = H2 // 2, W2 // 2
     if out is None:
         out = torch.empty(B, H, W, Cp, dtype=BF16, device=hi.device)
+    ap, keep = _aux(aux)
     _prof("conv_down", 2.0 * B * H * W * Cp * 16 * Cs, lambda: _lib.check(
-        _lib.lib().rg_conv_down(_p(hi), _p(w_down), _p(out), B, H, W, Cs, Cp, _p(stats), _st()), "rg_conv_down"))
+        _lib.lib().rg_conv_down(_p(hi), _p(w_down), _p(out), B, H, W, Cs, Cp, _p(stats), ap, _st()), "rg_conv_down"))
     return out
 
 
-def conv_up(lo, w, Cs, out=None, stats=None):
+def conv_up(lo, w, Cs, out=None, stats=None, aux=None):
     """lo bf16 [B, H, W, Cp] -> hi bf16 [B, 2H, 2W, Cs].  w: w_down bf16 [Cp, 16*Cs] (2-D; read MN-major),
     w_up bf16 [4, Cs_pad, 4*Cp] (3-D; K-major) or the merged-phase w_up9 (6-D; Cs == 64, >= 256 low-res pixels)."""
     _chk(lo, BF16, "lo"); _chk(w, BF16, "w")
     B, H, W, Cp = lo.shape
     if out is None:
         out = torch.empty(B, 2 * H, 2 * W, Cs, dtype=BF16, device=lo.device)
+    ap, keep = _aux(aux)
     _prof("conv_up", 2.0 * B * H * W * Cp * 16 * Cs, lambda: _lib.check(
-        _lib.lib().rg_conv_up(_p(lo), _p(w), {2: 1, 3: 0, 6: 2}[w.dim()], _p(out), B, H, W, Cp, Cs, _p(stats), _st()),
+        _lib.lib().rg_conv_up(_p(lo), _p(w), {2: 1, 3: 0, 6: 2}[w.dim()], _p(out), B, H, W, Cp, Cs, _p(stats), ap,
+                              _st()),
         "rg_conv_up"))
     return out
 

@@ -337,3 +337,62 @@ def test_conv_up_merged_phases(cuda_dev, B, H, W, Cp):
     o = out.float().view(-1, Cs)
     got = ws.sum(0)
     assert _rel(got[0], o.sum(0)) < 1e-4 and _rel(got[1], (o * o).sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,Cs,Cp", [(8, 16, 16, 128, 256), (4, 32, 32, 64, 128), (3, 8, 8, 64, 128)])
+def test_fused_bn_backward_epilogue(cuda_dev, B, H, W, Cs, Cp):
+    """rg_conv_down / rg_conv_up with rg_epilogue_aux mode 2: the stored output is du = dh * lrelu'(scale*a + shift)
+    and the partial sums are S(du), S(du * xhat) -- compared with the same quantities from torch ops."""
+    from rnagan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B + H + Cs + Cp + 13)
+    Wt = _bf(torch.randn(Cp, Cs, 4, 4, generator=g) * 0.05).to(cuda_dev)
+    w_down, w_up = ops.pack_link(Wt)
+    slope = 0.2
+
+    def check(out, dh_ref_nchw, a_nhwc, C, ws, mean, rstd, scale, shift):
+        dh = _nhwc(dh_ref_nchw).float().view(-1, C)
+        a = a_nhwc.float().view(-1, C)
+        u = a * scale + shift
+        du = torch.where(u > 0, dh, dh * slope)
+        o = out.float().view(-1, C)
+        assert _rel(o, du) < 1e-2
+        xhat = (a - mean) * rstd
+        got = ws.sum(0)
+        assert _rel(got[0], o.sum(0)) < 1e-3
+        assert _rel(got[1], (o * xhat).sum(0)) < 1e-3
+
+    def params(C):
+        mean = torch.randn(C, generator=g).to(cuda_dev) * 0.1
+        rstd = (torch.rand(C, generator=g) + 0.5).to(cuda_dev)
+        gamma = (torch.rand(C, generator=g) + 0.5).to(cuda_dev)
+        beta = torch.randn(C, generator=g).to(cuda_dev) * 0.1
+        scale = gamma * rstd
+        shift = beta - mean * scale
+        return mean, rstd, scale.contiguous(), shift.contiguous()
+
+    # down: out [B,H,W,Cp]
+    x = _bf(torch.randn(B, Cs, 2 * H, 2 * W, generator=g)).to(cuda_dev)
+    a = torch.randn(B, H, W, Cp, generator=g).to(cuda_dev).to(torch.bfloat16)
+    mean, rstd, scale, shift = params(Cp)
+    ws = ops.stats_ws(Cp, cuda_dev, slot=11)
+    ws.fill_(float("nan"))
+    out = ops.conv_down(_nhwc(x), w_down, stats=ws, aux=("bn", a, mean, rstd, scale, shift, slope))
+    check(out, F.conv2d(x, Wt, stride=2, padding=1), a, Cp, ws, mean, rstd, scale, shift)
+    # up: out [B,2H,2W,Cs] (K-major operand; merged-phase operand when Cs == 64 and the grid is large enough)
+    y = _bf(torch.randn(B, Cp, H, W, generator=g)).to(cuda_dev)
+    a2 = torch.randn(B, 2 * H, 2 * W, Cs, generator=g).to(cuda_dev).to(torch.bfloat16)
+    mean, rstd, scale, shift = params(Cs)
+    ws2 = ops.stats_ws(Cs, cuda_dev, slot=11)
+    ref_up = F.conv_transpose2d(y, Wt, stride=2, padding=1)
+    operands = [w_down] + ([w_up] if Cs <= 128 else [])
+    if Cs == 64 and B * H * W >= 256:
+        operands.append(ops.pack_up9_from_down(w_down, Cs))
+    for w in operands:
+        ws2.fill_(float("nan"))
+        out = ops.conv_up(_nhwc(y), w, Cs, stats=ws2, aux=("bn", a2, mean, rstd, scale, shift, slope))
+        check(out, ref_up, a2, Cs, ws2, mean, rstd, scale, shift)
+        # mode 1: plain LeakyReLU backward from the stored activation
+        out1 = ops.conv_up(_nhwc(y), w, Cs, aux=("lrelu", a2, slope))
+        dh = _nhwc(ref_up).float()
+        ref1 = torch.where(a2.float() > 0, dh, dh * slope)
+        assert _rel(out1.float(), ref1) < 1e-2
