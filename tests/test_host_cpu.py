@@ -163,3 +163,45 @@ def test_gradient_allreduce_gloo_world2(tmp_path):
              for r in range(2)]
     codes = [p.wait(timeout=180) for p in procs]
     assert codes == [0, 0]
+
+
+def test_native_weight_layout_plumbing_cpu():
+    """The engines keep 4x4 conv weights channels_last (physically [Cp][kh][kw][Cs]): values, shapes and state_dict
+    round trips are unchanged, the flat-buffer gradient view and the Adam moments share the parameter's strides, and a
+    contiguous optimiser state (an upstream checkpoint) is converted on first use."""
+    import torch
+    import torch.nn as nn
+
+    from rnagan_b200 import ops
+    from rnagan_b200.engine import _grad_of, _to_native
+    from rnagan_b200.optim import _ensure_state
+    from rnagan_b200.parallel import GradSync
+
+    torch.manual_seed(0)
+    m = nn.Sequential(nn.Conv2d(8, 16, 4, 2, 1, bias=False), nn.BatchNorm2d(16))
+    w = m[0].weight
+    ref = w.detach().clone()
+    assert len(_to_native([w])) == 1 and ops.is_native4(w) and torch.equal(w, ref)
+    assert len(_to_native([w])) == 0                      # idempotent
+    assert ops.phys2d(w.detach()).shape == (16, 16 * 8) and ops.phys2d(w.detach()).is_contiguous()
+    # physical order = [p][kh][kw][s]
+    assert torch.equal(ops.phys2d(w.detach()).view(16, 4, 4, 8), ref.permute(0, 2, 3, 1))
+    gs = GradSync(m)
+    assert w.grad.stride() == w.stride() and _grad_of(w).data_ptr() == w.grad.data_ptr()
+    w.grad.copy_(torch.arange(w.numel(), dtype=torch.float32).view_as(w))
+    o, n = gs.offs[id(w)]
+    assert torch.equal(gs.flat[o:o + n].view(16, 4, 4, 8).permute(0, 3, 1, 2), w.grad)
+    # state_dict round trip through a contiguous module and back keeps the native layout
+    m2 = nn.Sequential(nn.Conv2d(8, 16, 4, 2, 1, bias=False), nn.BatchNorm2d(16))
+    m2.load_state_dict(m.state_dict())
+    assert torch.equal(m2[0].weight, w) and m2[0].weight.is_contiguous()
+    m.load_state_dict(m2.state_dict())
+    assert ops.is_native4(m[0].weight) and torch.equal(m[0].weight, ref)
+    # Adam moments: created with the parameter's strides; a contiguous loaded state is converted, values kept
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    st = _ensure_state(opt, w)
+    assert st["exp_avg"].stride() == w.stride()
+    vals = torch.randn(16, 8, 4, 4)
+    opt.state[w]["exp_avg"] = vals.clone()                # contiguous, as torch.load of an upstream checkpoint gives
+    st = _ensure_state(opt, w)
+    assert st["exp_avg"].stride() == w.stride() and torch.equal(st["exp_avg"], vals)
