@@ -48,6 +48,7 @@ struct GemmMaps {
   CUtensorMap a[4];
   CUtensorMap b;
   CUtensorMap o[4];   // per-phase output views (bf16 NHWC through the TMA-store epilogue)
+  CUtensorMap x[4];   // the same views of the aux tensor of the fused elementwise backward (TMA-staged into smem)
 };
 
 enum OutKind { OUT_BF16_NHWC = 0, OUT_F32_NHWC = 1, OUT_F32_NCHW = 2 };
@@ -80,6 +81,7 @@ struct FwdArgs {
   // a pass over dh and a.
   const __nv_bfloat16* aux;
   int aux_mode;
+  int naux;                      // aux staging slabs in smem (2 when aux_mode != 0)
   const float* aux_mean;
   const float* aux_rstd;
   const float* aux_scale;
@@ -143,6 +145,8 @@ struct PipeSmem {
   uint64_t* tfull;
   uint64_t* tempty;
   uint32_t* tmem_slot;
+  uint64_t* auxbar;   // [2] "aux slab landed" barriers (fused elementwise backward)
+  uint8_t* auxstg;    // [2][16 KiB] aux slabs, same swizzled layout as the output staging slabs
   float* s_scale;   // [256] per-column epilogue scale of the current tile
   float* s_shift;   // [256]
   float* s_mean;    // [256] fused BatchNorm backward only
@@ -151,17 +155,20 @@ struct PipeSmem {
 };
 
 // layout: [ring: ring_bytes][staging: staging_bytes][barriers 256][affine 2048][stat 2048], ring 1024-byte aligned
-__device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw, int ring_bytes, int staging_bytes) {
+__device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw, int ring_bytes, int staging_bytes, int aux_bytes = 0) {
   PipeSmem s;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
   s.stages = base;
   s.staging = base + ring_bytes;
+  s.auxstg = base + ring_bytes + staging_bytes;
+  staging_bytes += aux_bytes;          // the fixed block follows the aux slabs
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + ring_bytes + staging_bytes);
   s.full = bars;
   s.empty = bars + kMaxStages;
   s.tfull = bars + 2 * kMaxStages;
   s.tempty = bars + 2 * kMaxStages + 2;
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  s.auxbar = bars + 2 * kMaxStages + 6;
   s.s_scale = reinterpret_cast<float*>(base + ring_bytes + staging_bytes + kBarBytes);
   s.s_shift = s.s_scale + 256;
   s.s_mean = s.s_scale + 512;
@@ -185,6 +192,7 @@ __device__ __forceinline__ uint32_t pipeline_prologue(const PipeSmem& s, int war
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s.tfull[i], 1);
         mbar_init(&s.tempty[i], 4 * CG);   // one arrival per epilogue warp of every CTA in the group
+        mbar_init(&s.auxbar[i], 1);
       }
       fence_barrier_init();
     }
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ FwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const int stage_bytes = kAStageBytes + p.b_stage_bytes;
-  const PipeSmem s = carve_smem(smem_raw, p.nstages * stage_bytes, p.nbuf * kStagingBytes);
+  const PipeSmem s = carve_smem(smem_raw, p.nstages * stage_bytes, p.nbuf * kStagingBytes, p.naux * kStagingBytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -451,6 +459,24 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
     int staged_n_tile = -1;
     long long t_wtfull = 0, t_wstore = 0;
     const long long t_begin = clock64();
+    // fused elementwise backward: the leader streams the aux slabs two slabs ahead of their use, in the (tile, slab)
+    // order the epilogue consumes them
+    int pf_tile = tile0, pf_sl = 0, pf_count = 0;
+    auto aux_prefetch = [&]() {
+      if (pf_tile >= total_tiles) return;
+      const int ph_ = pf_tile % p.num_phases;
+      const int rest_ = pf_tile / p.num_phases;
+      const int m_ = (rest_ % mslots) * CG + crank;
+      const int nt_ = rest_ / mslots;
+      const int j0_ = (m_ % p.tw) * p.bw, i0_ = ((m_ / p.tw) % p.th) * p.bh, b0_ = (m_ / (p.tw * p.th)) * p.bb;
+      uint64_t* bar = &s.auxbar[pf_count & 1];
+      mbar_expect_tx(bar, static_cast<uint32_t>(p.rows_valid) * 128u);
+      tma_load_4d(p.merged ? &maps.x[pf_sl] : &maps.x[ph_], bar, s.auxstg + (pf_count & 1) * kStagingBytes,
+                  p.merged ? 0 : nt_ * p.block_n + pf_sl * 64, j0_, i0_, b0_);
+      ++pf_count;
+      if (++pf_sl == (p.block_n >> 6)) { pf_sl = 0; pf_tile += tile_step; }
+    };
+    if (aux_on && et == 0) { aux_prefetch(); aux_prefetch(); }
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1u;
@@ -532,13 +558,12 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
           float csum[2] = {0.0f, 0.0f}, csq[2] = {0.0f, 0.0f};
           uint4 ax[8];                                      // this row's 64 aux values of the slab (fused backward)
           if (aux_on) {
-            // merged tiles: slab = output phase, so the pixel changes per slab and the channels start at 0
-            const int ys = p.merged ? i * p.sy + p.oy[sl] : y, xs_ = p.merged ? j * p.sx + p.ox[sl] : x;
-            const __nv_bfloat16* ap = p.aux + (static_cast<size_t>(b * p.OH + ys) * p.OW + xs_) * p.OC +
-                                      (p.merged ? 0 : n0 + sl * 64);
+            // the slab was TMA-loaded two slabs ago into auxstg[count & 1] (same swizzle as the output slab)
+            mbar_wait(&s.auxbar[store_count & 1], (store_count >> 1) & 1u);
+            const uint8_t* arow = s.auxstg + (store_count & 1) * kStagingBytes + row * 128;
 #pragma unroll
             for (int g = 0; g < 8; ++g)
-              ax[g] = row_ok ? *reinterpret_cast<const uint4*>(ap + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+              ax[g] = row_ok ? *reinterpret_cast<const uint4*>(arow + ((g ^ (row & 7)) << 4)) : make_uint4(0u, 0u, 0u, 0u);
           }
           uint32_t vv[2][32];
           tmem_ld_32x32(taddr + sl * 64, vv[0]);            // both halves in flight before the single wait
@@ -644,6 +669,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
             else tma_store_4d(&maps.o[ph], buf, n0 + sl * 64, j0, i0, b0);
             bulk_commit();
           }
+          if (aux_on && et == 0) aux_prefetch();   // every thread is past its reads of auxstg[count & 1]: refill it
           if (do_stats) {                  // fixed-order sum of the four warps' partial column sums
             const float* ss = stat_buf + st_k * 64 + st_c;
             const float t = ((ss[0] + ss[128]) + ss[256]) + ss[384];

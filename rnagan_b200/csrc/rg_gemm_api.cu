@@ -242,13 +242,18 @@ static int launch_fwd(GemmMaps& maps, FwdArgs& a, int out_kind, int cg, float* s
   const int stage = kAStageBytes + a.b_stage_bytes;
   const int avail = kSmemMaxBytes - kSmemFixedBytes;
   a.nbuf = a.tma_store ? 2 : 0;
-  int ns = (avail - a.nbuf * kStagingBytes) / stage;
-  if (a.tma_store && ns < 4) {
+  a.naux = a.aux_mode != 0 ? 2 : 0;
+  int ns = (avail - (a.nbuf + a.naux) * kStagingBytes) / stage;
+  if (a.tma_store && ns < 4 && a.naux == 0) {
     a.nbuf = 1;
     ns = (avail - kStagingBytes) / stage;
   }
+  if (ns < 2) {
+    set_error("internal: shared-memory plan leaves %d stages (block_n=%d cg=%d aux=%d)", ns, a.block_n, cg, a.aux_mode);
+    return RG_EINVAL;
+  }
   a.nstages = std::min(ns, kMaxStages);
-  const size_t smem = static_cast<size_t>(a.nstages) * stage + a.nbuf * kStagingBytes + kSmemFixedBytes;
+  const size_t smem = static_cast<size_t>(a.nstages) * stage + (a.nbuf + a.naux) * kStagingBytes + kSmemFixedBytes;
   if (a.tma_store) {
     // per-phase output views: pixel (b, i*sy + oy, j*sx + ox), channels [0, n_valid); TMA clips what lies outside
     const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(a.out);
@@ -259,6 +264,13 @@ static int launch_fwd(GemmMaps& maps, FwdArgs& a, int out_kind, int cg, float* s
                          static_cast<uint64_t>(a.sy) * a.OW * a.OC, static_cast<uint64_t>(a.OH) * a.OW * a.OC, 64, a.bw,
                          a.bh, a.bb);
       if (rc) return rc;
+      if (a.aux_mode != 0) {       // the aux tensor has the layout of the output: same views, other base
+        const __nv_bfloat16* x0 = a.aux + (static_cast<size_t>(a.oy[ph]) * a.OW + a.ox[ph]) * a.OC;
+        rc = encode_map_4d(&maps.x[ph], x0, a.n_valid, a.W, a.H, a.nB, static_cast<uint64_t>(a.sx) * a.OC,
+                           static_cast<uint64_t>(a.sy) * a.OW * a.OC, static_cast<uint64_t>(a.OH) * a.OW * a.OC, 64,
+                           a.bw, a.bh, a.bb);
+        if (rc) return rc;
+      }
     }
   }
   const int slots = ceil_div(a.m_tiles, cg) * a.n_tiles * a.num_phases;

@@ -32,8 +32,9 @@ MERGED_UP = os.environ.get("RG_MERGED_UP", "1") != "0"
 # the LeakyReLU / BatchNorm backward masks and the BatchNorm backward sums are computed in the epilogue of the
 # input-gradient contraction that produces dh (RG_FUSED_BWD=0: separate rg_bn_bwd_reduce / rg_lrelu_bwd passes)
 # Measured on B200 (profiles/r1_step_profile_fused_bwd.txt): OFF by default.  The fusion removes 22 of 30
-# rg_bn_bwd_reduce and 3 of 5 rg_lrelu_bwd launches (-0.87 ms/step) but the per-thread aux loads and the extra epilogue
-# arithmetic slow the contractions by 1.4 ms/step; it needs a TMA-staged aux tile to pay off.
+# rg_bn_bwd_reduce and 3 of 5 rg_lrelu_bwd launches (-0.87 ms/step) but slows the 25 contractions that carry it by
+# 1.07 ms/step (106 vs 67 us per launch) even with the aux tile TMA-staged two slabs ahead: four epilogue warps cannot
+# absorb the mask + normalise + second reduction arithmetic of the narrow, short-K layers under their mainloop.
 FUSED_BWD = os.environ.get("RG_FUSED_BWD", "0") != "0"
 
 
