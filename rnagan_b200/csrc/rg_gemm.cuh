@@ -72,8 +72,11 @@ struct FwdArgs {
   int nbuf;               // staging slabs (1 or 2)
   int merged;             // transposed form with ALL FOUR output phases in one tile (Cs == 64, CTA pairs): the 9 distinct
                           // shifted A tiles of an M tile are fetched once instead of 16 times; TMEM slab q = phase q
-  int8_t mg_nph[9];       // merged: how many phases tap t9 = (dh+1)*3 + (dw+1) feeds (1, 2 or 4) ...
-  int8_t mg_phase[9][4];  // ... and which ones; their B slabs sit in this order in the stage (packed by rg_pack_up9)
+  // merged: tap i of the list (centre shift first) feeds mg_nph[i] consecutive 64-column phase slabs starting at phase
+  // mg_col[i] with ONE MMA of N = 64 * mg_nph[i] per k-step (a phase the shift does not feed gets a zero B slab): an
+  // N = 64 tcgen05.mma costs ~94 cycles against 128 for N = 256 (measured), so wide instructions are what counts
+  int8_t mg_nph[9];
+  int8_t mg_col[9];
   // Fused elementwise backward of the layer this GEMM's output is the input gradient of (TMA-store epilogue only):
   // aux has the layout of `out`.  mode 1 (no BatchNorm): out = acc * lrelu'(aux), aux = the stored activation h.
   // mode 2 (BatchNorm + LeakyReLU): aux = the pre-BN activation a; out = du = acc * lrelu'(scale*a + shift) and, with
@@ -331,7 +334,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
             }
             if (do_b && merged) {
               // one box = the slabs of every phase this tap feeds (this CTA's half of their rows), contiguous in w_up9
-              const uint64_t d9 = mg_n == 4 ? desc_b : (mg_n == 2 ? desc_a0 + sizeof(CUtensorMap) : desc_a0 + 2 * sizeof(CUtensorMap));
+              const uint64_t d9 = mg_n == 4 ? desc_b : desc_a0 + static_cast<uint64_t>(mg_n == 2 ? 1 : (mg_n == 1 ? 2 : 3)) * sizeof(CUtensorMap);
               tma_ld_2d_raw<CG>(d9, fb, sb, 0, ((tap * chunks + chunk) * CG + crank) * (4 * mg_rows));
             } else if (do_b) {
               if (b_mn) {
@@ -378,30 +381,28 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
         if (p.merged) {
-          // 9 taps x chunks stages; each stage feeds 1, 2 or 4 phase accumulators (64 TMEM columns each)
-          const uint32_t idesc64 = make_idesc_bf16(kBlockM * CG, 64, 0, 0);
-          uint32_t used = 0;                    // phases that already hold a partial sum in this tile
+          // 9 shifts x chunks stages; one MMA per k-step covers every phase slab the shift feeds (N = 64..256).
+          // The centre shift comes first and feeds all four phases: its first MMA initialises the whole accumulator.
           for (int tap = 0; tap < p.num_taps; ++tap) {
-            const int nph = p.mg_nph[tap];
+            const int nsl = p.mg_nph[tap];
+            const uint32_t idesc_n = make_idesc_bf16(kBlockM * CG, 64 * nsl, 0, 0);
+            const uint32_t tmem_t = tmem_d + p.mg_col[tap] * 64;
             for (int chunk = 0; chunk < p.chunks; ++chunk) {
+              const long long c1 = prof ? clock64() : 0;
               mbar_wait_raw(full0 + stage * 8, phase);
+              if (prof) t_wfull += clock64() - c1;
               tc_fence_after();
               const uint32_t sa = ring0 + stage * stage_bytes;
               const uint64_t da = da0 | static_cast<uint64_t>((sa >> 4) & 0x3FFF);
-              for (int q = 0; q < nph; ++q) {
-                const int phq = p.mg_phase[tap][q];
-                const uint64_t db = db0 | static_cast<uint64_t>(((sa + kAStageBytes + q * mg_rows * 128) >> 4) & 0x3FFF);
-                const uint32_t first = (chunk == 0 && !((used >> phq) & 1u)) ? 1u : 0u;
-                if (!skip_mma) {
+              const uint64_t db = db0 | static_cast<uint64_t>(((sa + kAStageBytes) >> 4) & 0x3FFF);
+              if (!skip_mma) {
 #pragma unroll
-                  for (int k = 0; k < kBlockK / 16; ++k)
-                    umma_bf16_cg<CG>(tmem_d + phq * 64, da + 2u * k, db + 2u * k, idesc64, (first && k == 0) ? 0u : 1u);
-                }
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_bf16_cg<CG>(tmem_t, da + 2u * k, db + 2u * k, idesc_n, (tap | chunk | k) != 0 ? 1u : 0u);
               }
               umma_commit_cg<CG>(&s.empty[stage]);
               if (++stage == nstages) { stage = 0; phase ^= 1u; }
             }
-            for (int q = 0; q < nph; ++q) used |= 1u << p.mg_phase[tap][q];
           }
           umma_commit_cg<CG>(&s.tfull[acc]);
           continue;

@@ -565,11 +565,34 @@ __global__ void pack_up_from_down_kernel(const __nv_bfloat16* __restrict__ wd, _
           sm[tx][r];
   }
 }
-// Merged-phase operand of rg_conv_up (Cs == 64, CTA pairs): for every distinct input shift t9 = (dh+1)*3 + (dw+1) and
-// 64-channel chunk of Cp, the K-major slabs [64 s][64 p] of the output phases that shift feeds, split in two halves of
-// 32 output channels (one per CTA of the pair): out[t9][chunk][half][slot q][32 n][64 k], slots beyond the tap's phase
-// count zero.  Source: bf16 w_down[p][tap16*Cs + s].
-__global__ void pack_up9_kernel(const __nv_bfloat16* __restrict__ wd, __nv_bfloat16* __restrict__ out, int Cp, int Cs) {
+// Merged-phase operand of rg_conv_up (Cs == 64, CTA pairs).  The nine input shifts, centre first; shift i feeds
+// `nslots` consecutive phase slabs starting at phase col0 (phase = 2*rh + rw of the output pixel parity); a slot the shift
+// does not feed holds zeros so one MMA of N = 64 * nslots covers the span.
+struct Up9Tap {
+  int8_t dh, dw, nslots, col0;
+  int8_t phase[4];          // phase of each slot, -1 = zero slab
+};
+struct Up9Table {
+  Up9Tap t[9];
+};
+static Up9Table up9_table() {
+  static const Up9Table tab = {{
+      {0, 0, 4, 0, {0, 1, 2, 3}},
+      {-1, 0, 2, 0, {0, 1, -1, -1}},      // even output rows, both column parities
+      {1, 0, 2, 2, {2, 3, -1, -1}},       // odd output rows
+      {0, -1, 3, 0, {0, -1, 2, -1}},      // even output columns: phases 0 and 2, zero slab between
+      {0, 1, 3, 1, {1, -1, 3, -1}},       // odd output columns: phases 1 and 3
+      {-1, -1, 1, 0, {0, -1, -1, -1}},
+      {-1, 1, 1, 1, {1, -1, -1, -1}},
+      {1, -1, 1, 2, {2, -1, -1, -1}},
+      {1, 1, 1, 3, {3, -1, -1, -1}},
+  }};
+  return tab;
+}
+// out[shift i][chunk][CTA half][128 rows][64 k] bf16 from w_down[p][tap16*Cs + s] (K-major rows [column][p]; the first
+// 32 * nslots rows of a half are used)
+__global__ void pack_up9_kernel(const __nv_bfloat16* __restrict__ wd, __nv_bfloat16* __restrict__ out, int Cp, int Cs,
+                                const Up9Table tab) {
   const int chunks = Cp / 64;
   const size_t total = static_cast<size_t>(9) * chunks * 2 * 4 * 32 * 64;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -579,27 +602,25 @@ __global__ void pack_up9_kernel(const __nv_bfloat16* __restrict__ wd, __nv_bfloa
   const int q = static_cast<int>((idx >> 11) & 3);
   const int half = static_cast<int>((idx >> 13) & 1);
   const int rest = static_cast<int>(idx >> 14);
-  const int chunk = rest % chunks, t9 = rest / chunks;
-  const int dh = t9 / 3 - 1, dw = t9 % 3 - 1;
-  // phases fed by this shift, in (rh, rw) order; row parity rh uses shift 0 (both) or -1 (rh = 0) / +1 (rh = 1)
-  int cnt = 0, rh_sel = -1, rw_sel = -1;
-  for (int rh = 0; rh < 2; ++rh)
-    for (int rw = 0; rw < 2; ++rw) {
-      const bool okh = dh == 0 || (dh == -1 && rh == 0) || (dh == 1 && rh == 1);
-      const bool okw = dw == 0 || (dw == -1 && rw == 0) || (dw == 1 && rw == 1);
-      if (okh && okw) {
-        if (cnt == q) { rh_sel = rh; rw_sel = rw; }
-        ++cnt;
-      }
+  const int chunk = rest % chunks, ti = rest / chunks;
+  const Up9Tap t = tab.t[ti];
+  // cta_group::2 splits the N columns of ONE instruction between the CTAs: with N = 64 * nslots the leader supplies
+  // columns [0, N/2), the peer [N/2, N).  Row r of this CTA's box is therefore column c = half * N/2 + r of the span:
+  // slot c / 64 (a phase or a zero slab), output channel c % 64.
+  const int r = q * 32 + n;
+  const int half_cols = t.nslots * 32;
+  __nv_bfloat16 o = __float2bfloat16(0.0f);
+  if (r < half_cols) {
+    const int c = half * half_cols + r;
+    const int ph = t.phase[c >> 6];
+    if (ph >= 0) {
+      const int rh = ph >> 1, rw = ph & 1;
+      // kernel index for (parity r, shift d): r = 0: d = 0 -> 1, d = -1 -> 3;  r = 1: d = 0 -> 2, d = +1 -> 0
+      const int kh = rh == 0 ? (t.dh == 0 ? 1 : 3) : (t.dh == 0 ? 2 : 0);
+      const int kw = rw == 0 ? (t.dw == 0 ? 1 : 3) : (t.dw == 0 ? 2 : 0);
+      const int prow = chunk * 64 + k, sidx = c & 63;
+      o = wd[static_cast<size_t>(prow) * 16 * Cs + static_cast<size_t>(kh * 4 + kw) * Cs + sidx];
     }
-  float v = 0.0f;
-  __nv_bfloat16 o = __float2bfloat16(v);
-  if (rh_sel >= 0) {
-    // kernel index for (parity r, shift d): r = 0: d = 0 -> 1, d = -1 -> 3;  r = 1: d = 0 -> 2, d = +1 -> 0
-    const int kh = rh_sel == 0 ? (dh == 0 ? 1 : 3) : (dh == 0 ? 2 : 0);
-    const int kw = rw_sel == 0 ? (dw == 0 ? 1 : 3) : (dw == 0 ? 2 : 0);
-    const int prow = chunk * 64 + k, sidx = half * 32 + n;
-    o = wd[static_cast<size_t>(prow) * 16 * Cs + static_cast<size_t>(kh * 4 + kw) * Cs + sidx];
   }
   out[idx] = o;
 }
@@ -710,7 +731,7 @@ int rg_pack_up9_from_down(const void* w_down, void* w_up9, int Cp, int Cs, rg_st
   RG_CHECK_ARG(w_down && w_up9 && Cp > 0 && Cp % 64 == 0 && Cs == 64, "rg_pack_up9_from_down: need Cs == 64, Cp %% 64 == 0");
   const size_t total = rg_up9_elems(Cp);
   pack_up9_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(w_down), static_cast<__nv_bfloat16*>(w_up9), Cp, Cs);
+      static_cast<const __nv_bfloat16*>(w_down), static_cast<__nv_bfloat16*>(w_up9), Cp, Cs, up9_table());
   RG_LAUNCH_CHECK("pack_up9_kernel");
   return 0;
 }
@@ -790,29 +811,24 @@ static int conv_up_merged(const void* lo, const void* w9, void* out, int B, int 
   if (rc) return rc;
   const int chunks = Cp / 64;
   const uint64_t rows9 = 9ull * chunks * 2 * 4 * 32;      // w_up9 as a [rows][64] matrix
-  rc = encode_map_2d(&maps.b, w9, 64, rows9, 64, 64, 4 * 32);          // taps feeding 4 phases
+  rc = encode_map_2d(&maps.b, w9, 64, rows9, 64, 64, 4 * 32);          // box heights: 4, 2, 1, 3 slots of 32 rows
   if (rc) return rc;
-  rc = encode_map_2d(&maps.a[1], w9, 64, rows9, 64, 64, 2 * 32);       // 2 phases
+  rc = encode_map_2d(&maps.a[1], w9, 64, rows9, 64, 64, 2 * 32);
   if (rc) return rc;
-  rc = encode_map_2d(&maps.a[2], w9, 64, rows9, 64, 64, 1 * 32);       // 1 phase
+  rc = encode_map_2d(&maps.a[2], w9, 64, rows9, 64, 64, 1 * 32);
   if (rc) return rc;
-  maps.a[3] = maps.a[0];
+  rc = encode_map_2d(&maps.a[3], w9, 64, rows9, 64, 64, 3 * 32);
+  if (rc) return rc;
   a.merged = 1;
   a.num_taps = 9;
   a.chunks = chunks;
   a.num_phases = 1;
-  for (int t9 = 0; t9 < 9; ++t9) {
-    const int dh = t9 / 3 - 1, dw = t9 % 3 - 1;
-    Tap t = {0, static_cast<int8_t>(dh), static_cast<int8_t>(dw), 0};
-    a.taps[0][t9] = t;
-    int cnt = 0;
-    for (int rh = 0; rh < 2; ++rh)
-      for (int rw = 0; rw < 2; ++rw) {
-        const bool okh = dh == 0 || (dh == -1 && rh == 0) || (dh == 1 && rh == 1);
-        const bool okw = dw == 0 || (dw == -1 && rw == 0) || (dw == 1 && rw == 1);
-        if (okh && okw) a.mg_phase[t9][cnt++] = static_cast<int8_t>(rh * 2 + rw);
-      }
-    a.mg_nph[t9] = static_cast<int8_t>(cnt);
+  const Up9Table tab = up9_table();
+  for (int i = 0; i < 9; ++i) {
+    Tap t = {0, tab.t[i].dh, tab.t[i].dw, 0};
+    a.taps[0][i] = t;
+    a.mg_nph[i] = tab.t[i].nslots;
+    a.mg_col[i] = tab.t[i].col0;
   }
   for (int ph = 0; ph < 4; ++ph) {
     a.oy[ph] = static_cast<int8_t>(ph >> 1);

@@ -46,6 +46,11 @@ def main():
         run(f"conv_up L{i + 1} w_down", lambda: ops.conv_up(lo, wd, Cs, out=out_hi))
         if Cs <= 128:
             run(f"conv_up L{i + 1} w_up", lambda: ops.conv_up(lo, wu, Cs, out=out_hi))
+        if Cs == 64:
+            w9 = ops.pack_up9_from_down(wd, Cs)
+            run(f"conv_up L{i + 1} w_up9 (merged)", lambda: ops.conv_up(lo, w9, Cs, out=out_hi))
+            st = ops.stats_ws(Cs, dev, slot=3)
+            run(f"conv_up L{i + 1} w_up9 (merged) + stats", lambda: ops.conv_up(lo, w9, Cs, out=out_hi, stats=st))
 
 
 if __name__ == "__main__":
