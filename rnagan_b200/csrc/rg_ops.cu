@@ -682,19 +682,22 @@ __global__ void __launch_bounds__(256) latent_prep_kernel(const float* __restric
 __global__ void __launch_bounds__(256) im2col_img_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                          int mode, const float* __restrict__ eps_dev,
                                                          const float* __restrict__ mul_dev, int B, int Cimg, int S,
-                                                         __nv_bfloat16* __restrict__ col,
+                                                         int R, __nv_bfloat16* __restrict__ col,
                                                          float* __restrict__ mixed_out) {
-  extern __shared__ float rows[];   // [Cimg][4][S + 2], one zero column on each side
-  const int Ho = S / 2, Wp = S + 2;
-  const int b = blockIdx.x >> (31 - __clz(Ho)), ho = blockIdx.x & (Ho - 1);
+  // One block stages the 2R + 2 input rows that R consecutive output rows need (1 + 1/R reads per image row instead
+  // of 2) and emits R x (S/2) col rows of 128 bytes.
+  extern __shared__ float rows[];   // [Cimg][2R + 2][S + 2], one zero column on each side
+  const int Ho = S / 2, Wp = S + 2, NR = 2 * R + 2;
+  const int groups = Ho / R;                    // R divides Ho (host)
+  const int b = blockIdx.x / groups, ho0 = (blockIdx.x - b * groups) * R;
   const float eps = eps_dev ? __ldg(eps_dev) : 0.0f;
   const float mul = mul_dev ? __ldg(mul_dev) : 1.0f;
   const int ls = 31 - __clz(S);                 // S is a power of two (checked by the host wrapper)
-  for (int idx = threadIdx.x; idx < Cimg * 4 * S; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < Cimg * NR * S; idx += blockDim.x) {
     const int xx = idx & (S - 1);
-    const int r = (idx >> ls) & 3;
-    const int c = idx >> (ls + 2);
-    const int yy = 2 * ho - 1 + r;
+    const int cr = idx >> ls;
+    const int c = cr / NR, r = cr - c * NR;
+    const int yy = 2 * ho0 - 1 + r;
     float t = 0.0f;
     if (yy >= 0 && yy < S) {
       const size_t o = ((static_cast<size_t>(b) * Cimg + c) * S + yy) * S + xx;
@@ -702,27 +705,29 @@ __global__ void __launch_bounds__(256) im2col_img_kernel(const float* __restrict
       if (mode == 1) t = eps * t + (1.0f - eps) * __ldg(y + o);
       else if (mode == 2) { const float th = __ldg(y + o); t = t * (1.0f - th * th); }
       t *= mul;
-      if (mixed_out && (r == 1 || r == 2)) mixed_out[o] = t;   // rows 2ho, 2ho+1 are owned by this block
+      if (mixed_out && r >= 1 && r <= 2 * R) mixed_out[o] = t;   // rows 2ho0 .. 2ho0 + 2R - 1 are owned by this block
     }
-    rows[(c * 4 + r) * Wp + xx + 1] = t;
+    rows[(c * NR + r) * Wp + xx + 1] = t;
   }
-  for (int idx = threadIdx.x; idx < Cimg * 4 * 2; idx += blockDim.x)
+  for (int idx = threadIdx.x; idx < Cimg * NR * 2; idx += blockDim.x)
     rows[(idx >> 1) * Wp + ((idx & 1) ? S + 1 : 0)] = 0.0f;
   __syncthreads();
-  const size_t pix0 = (static_cast<size_t>(b) * Ho + ho) * Ho;
-  for (int idx = threadIdx.x; idx < Ho * 8; idx += blockDim.x) {
-    const int wo = idx >> 3, part = idx & 7;
+  for (int idx = threadIdx.x; idx < R * Ho * 8; idx += blockDim.x) {
+    const int part = idx & 7;
+    const int pw = idx >> 3;
+    const int lr = pw / Ho, wo = pw - lr * Ho;
     const int kh = part >> 1, kw0 = (part & 1) * 2;
     uint32_t packed[4];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       const int sx = 2 * wo + kw0 + k;            // smem column of input x = 2*wo - 1 + kw
-      for (int c = 0; c < Cimg; ++c) v[c] = rows[(c * 4 + kh) * Wp + sx];
+      for (int c = 0; c < Cimg; ++c) v[c] = rows[(c * NR + 2 * lr + kh) * Wp + sx];
       packed[k * 2] = pack_bf16x2_ops(v[0], v[1]);
       packed[k * 2 + 1] = pack_bf16x2_ops(v[2], v[3]);
     }
-    *reinterpret_cast<uint4*>(col + (pix0 + wo) * 64 + part * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    const size_t pix = (static_cast<size_t>(b) * Ho + ho0 + lr) * Ho + wo;
+    *reinterpret_cast<uint4*>(col + pix * 64 + part * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
 }
 
@@ -1461,10 +1466,13 @@ int rg_im2col_img(const float* x, const float* y, int mode, const float* eps_dev
   RG_CHECK_ARG(x && col && B > 0 && Cimg >= 1 && Cimg <= 4 && S >= 4 && is_pow2(S),
                "rg_im2col_img: need 1..4 channels and a power-of-two image side (S=%d)", S);
   RG_CHECK_ARG(mode == 0 || y, "rg_im2col_img: mode %d needs a second image", mode);
-  const size_t smem = static_cast<size_t>(Cimg) * 4 * (S + 2) * sizeof(float);
+  int R = 4;                                     // output rows per block: largest of 4, 2, 1 that divides S/2 and fits
+  while (R > 1 && ((S / 2) % R != 0 || static_cast<size_t>(Cimg) * (2 * R + 2) * (S + 2) * sizeof(float) > 48 * 1024))
+    R >>= 1;
+  const size_t smem = static_cast<size_t>(Cimg) * (2 * R + 2) * (S + 2) * sizeof(float);
   RG_CHECK_ARG(smem <= 48 * 1024, "rg_im2col_img: image side %d too large for the row-staging buffer", S);
-  im2col_img_kernel<<<B * (S / 2), 256, smem, static_cast<cudaStream_t>(st)>>>(x, y, mode, eps_dev, mul_dev, B, Cimg, S,
-                                                                               static_cast<bf16*>(col), mixed_out);
+  im2col_img_kernel<<<B * (S / 2 / R), 256, smem, static_cast<cudaStream_t>(st)>>>(x, y, mode, eps_dev, mul_dev, B, Cimg,
+                                                                                   S, R, static_cast<bf16*>(col), mixed_out);
   RG_LAUNCH_CHECK("rg_im2col_img");
   return 0;
 }
