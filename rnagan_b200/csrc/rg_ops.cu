@@ -1466,7 +1466,9 @@ int rg_im2col_img(const float* x, const float* y, int mode, const float* eps_dev
   RG_CHECK_ARG(x && col && B > 0 && Cimg >= 1 && Cimg <= 4 && S >= 4 && is_pow2(S),
                "rg_im2col_img: need 1..4 channels and a power-of-two image side (S=%d)", S);
   RG_CHECK_ARG(mode == 0 || y, "rg_im2col_img: mode %d needs a second image", mode);
-  int R = 4;                                     // output rows per block: largest of 4, 2, 1 that divides S/2 and fits
+  // output rows per block.  Measured on B200: R = 4 (1.25 instead of 2 reads per image row, 4x fewer blocks) is SLOWER
+  // (92 vs 86 us at B = 64, 256x256) -- the kernel is bound by its shared-memory gather, not by the image reads.
+  int R = 1;
   while (R > 1 && ((S / 2) % R != 0 || static_cast<size_t>(Cimg) * (2 * R + 2) * (S + 2) * sizeof(float) > 48 * 1024))
     R >>= 1;
   const size_t smem = static_cast<size_t>(Cimg) * (2 * R + 2) * (S + 2) * sizeof(float);
