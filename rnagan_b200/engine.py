@@ -36,6 +36,10 @@ MERGED_UP = os.environ.get("RG_MERGED_UP", "1") != "0"
 # 1.07 ms/step (106 vs 67 us per launch) even with the aux tile TMA-staged two slabs ahead: four epilogue warps cannot
 # absorb the mask + normalise + second reduction arithmetic of the narrow, short-K layers under their mainloop.
 FUSED_BWD = os.environ.get("RG_FUSED_BWD", "0") != "0"
+# the layer-0 LeakyReLU mask alone (rg_epilogue_aux mode 1: no statistics, no per-channel vectors) in the epilogue of the
+# contraction that produces dh0: ON -- measured -0.18 ms/step (3 of 5 rg_lrelu_bwd passes over 3 x 134 MB disappear, the
+# three merged-phase launches that carry the mask cost 0.04 ms more)
+FUSED_LRELU = os.environ.get("RG_FUSED_LRELU", "1") != "0"
 
 
 def _grad_of(p):
@@ -571,6 +575,7 @@ class CriticEngine:
             if final:
                 self.sync.layer_done(self.head.weight)
         fuse = FUSED_BWD and not keep_du     # the gradient-penalty pass keeps dh AND du of every layer: unfused
+        fuse0 = FUSED_LRELU and not keep_du
         fused = None
         for l in range(n, 0, -1):
             c, bn = self.convs[l - 1], self.bns[l - 1]
@@ -593,7 +598,7 @@ class CriticEngine:
                     fused = self.bns[l - 2].bwd_ws()
                     if fused is not None:
                         aux = self.bns[l - 2].aux(g(f"{tag}.a{l - 1}", (B, H, H, Cs)), tag)
-            elif fuse:       # layer 0 has no BatchNorm: the LeakyReLU mask goes into the epilogue, output is da0
+            elif fuse0:      # layer 0 has no BatchNorm: the LeakyReLU mask goes into the epilogue, output is da0
                 dh = g(f"{tag}.da0", (B, H, H, self.C0))
                 aux = ("lrelu", g(f"{tag}.h0", (B, H, H, self.C0)), SLOPE)
             else:
@@ -602,7 +607,7 @@ class CriticEngine:
         h0 = g(f"{tag}.h0", (B, H, H, self.C0))
         da0 = g(f"{tag}.da0", (B, H, H, self.C0))
         npix = B * H * H
-        if not fuse:
+        if not fuse0:
             ops.lrelu_bwd(dh, h0, SLOPE, da0, npix, self.C0)
         if params:
             ops.col_sum(da0, npix, self.C0, self.tmpC, _grad_of(self.conv0.bias), acc)
@@ -660,7 +665,7 @@ class CriticEngine:
                     da_t = g(f"{tag}.da{l}", (B, H // 2, H // 2, Cp))
                     ops.conv_up(da_t, self._wup(l, B * (H // 2) * (H // 2)), Cs, out=g(f"{tag}.dh{l - 1}", (B, H, H, Cs)),
                                 stats=fused[i], aux=bnp.aux(g(f"{tag}.a{l - 1}", (B, H, H, Cs)), tag))
-            elif l == 1 and FUSED_BWD:
+            elif l == 1 and FUSED_LRELU:
                 # layer 0 has no BatchNorm: joint launch with the LeakyReLU mask in the epilogue, output is da0
                 ops.conv_up(da2, self._wup(l, da2.shape[0] * da2.shape[1] * da2.shape[2]), Cs,
                             out=self.bufs.joint(f"{ta}.da0", (B, H, H, self.C0)),
@@ -672,7 +677,7 @@ class CriticEngine:
         h0 = self.bufs.joint(f"{ta}.h0", (B, H, H, self.C0))
         dh0 = self.bufs.joint(f"{ta}.dh0", (B, H, H, self.C0))
         da0 = self.bufs.joint(f"{ta}.da0", (B, H, H, self.C0))
-        if not FUSED_BWD:
+        if not FUSED_LRELU:
             ops.lrelu_bwd(dh0, h0, SLOPE, da0, 2 * npix, self.C0)
         ops.col_sum(da0, 2 * npix, self.C0, self.tmpC, _grad_of(self.conv0.bias), 0.0)
         col = self.bufs.joint(f"{ta}.col", (npix, 64))
@@ -761,7 +766,7 @@ class CriticEngine:
                 T = Tn
             else:
                 A_a0 = g(f"{tag}.Aa0", (B, H, H, self.C0))
-                if FUSED_BWD:
+                if FUSED_LRELU:
                     ops.conv_up(T, wup, Cs, out=A_a0, aux=("lrelu", h0, SLOPE))
                 else:
                     A_h = g(f"{tag}.Ah{l - 1}", (B, H, H, Cs))
