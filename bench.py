@@ -354,7 +354,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu, "synthesis": synth, "vae_train": vae_train, "losses_finite": finite,
             "last_losses": [float(x) for x in losses_host[-1]],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -441,13 +441,30 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_STDOUT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of this process, written to the real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
 
 
 def main():
-    # rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION in this image) off it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # Rank 0 prints exactly ONE line on stdout.  Native libraries write there too (NCCL prints its version banner on
+    # file descriptor 1 when a communicator is created): point fd 1 at stderr for the whole run and keep a private
+    # duplicate of the real stdout for the JSON line.
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
