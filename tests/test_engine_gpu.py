@@ -396,3 +396,43 @@ def test_fused_bn_backward_epilogue(cuda_dev, B, H, W, Cs, Cp):
         dh = _nhwc(ref_up).float()
         ref1 = torch.where(a2.float() > 0, dh, dh * slope)
         assert _rel(out1.float(), ref1) < 1e-2
+
+
+@pytest.mark.parametrize("layer", [1, 2, 3, 4, 5])
+def test_full_size_adjoint_identities(cuda_dev, layer):
+    """BASELINE config 2 layer shapes (B = 64, 256x256 images), where a CPU reference would take minutes: the three
+    contractions of a link must be mutually adjoint,
+        <conv_down(x; W), y> = <x, conv_up(y; W)>          (dgrad is the transpose of fprop)
+        <wgrad(y, x), V>     = <conv_down(x; V), y>        (wgrad is the derivative w.r.t. the weight)
+    for every weight layout the engines use (w_down K-major / MN-major, w_up, merged-phase w_up9, native gradient).
+    bf16 outputs round each element to 2^-9 relative; the inner products over >= 2M elements average that out."""
+    from rnagan_b200 import ops
+    B = 64
+    chans = [64, 128, 256, 512, 1024, 2048]
+    Cs, Cp = chans[layer - 1], chans[layer]
+    h = 128 >> layer
+    g = torch.Generator(device="cpu").manual_seed(40 + layer)
+    x = torch.randn(B, 2 * h, 2 * h, Cs, generator=g).to(cuda_dev).to(torch.bfloat16)      # hi side
+    y = torch.randn(B, h, h, Cp, generator=g).to(cuda_dev).to(torch.bfloat16)              # lo side
+    scale = (16 * Cs) ** -0.5
+    Wt = _bf(torch.randn(Cp, Cs, 4, 4, generator=g) * scale).to(cuda_dev)
+    V = _bf(torch.randn(Cp, Cs, 4, 4, generator=g) * scale).to(cuda_dev)
+    w_down, w_up = ops.pack_link(Wt, want_up=Cs <= 128)
+    v_down, _ = ops.pack_link(V, want_up=False)
+
+    def dot(a, b):
+        return (a.double() * b.double()).sum().item()
+
+    lhs = dot(ops.conv_down(x, w_down), y)
+    operands = [w_down] + ([w_up] if Cs <= 128 else []) + ([ops.pack_up9_from_down(w_down, Cs)] if Cs == 64 else [])
+    for w in operands:
+        rhs = dot(x, ops.conv_up(y, w, Cs))
+        assert abs(lhs - rhs) <= 2e-3 * (abs(lhs) + abs(rhs)) + 1e-2 * (x.numel() ** 0.5), (layer, w.dim(), lhs, rhs)
+    ref_w = dot(ops.conv_down(x, v_down), y)
+    dW = torch.empty(Cp, Cs, 4, 4, device=cuda_dev)
+    dWn = torch.empty(Cp, Cs, 4, 4, device=cuda_dev).contiguous(memory_format=torch.channels_last)
+    for d in (dW, dWn):
+        ops.conv_wgrad(y, x, d)
+        got = dot(d, V)
+        assert abs(got - ref_w) <= 2e-3 * (abs(got) + abs(ref_w)) + 1e-2 * (x.numel() ** 0.5), (layer, got, ref_w)
+    assert torch.equal(dW, dWn)          # both layouts come from the same fixed-order reduction

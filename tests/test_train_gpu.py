@@ -255,3 +255,32 @@ def test_plain_wgan_steps_match_oracle(cuda_dev):
         _check_state(f"plain step{which}", onet, mnet)
     # the clamp ran before the critic step: every critic weight of the oracle was inside the clip range at that point
     assert all(float(p.abs().max()) <= 0.06 for p in oD.parameters())
+
+
+def test_training_is_bitwise_deterministic(cuda_dev):
+    """cudnn.deterministic=True in the reference (src/histopathology_gan.py:289): every reduction on the sm_100a path
+    (split-K, fused BatchNorm statistics, column sums, gradient norm) has a fixed order, so two runs of the same two
+    iterations from the same state and seeds give bit-identical losses, weights, BatchNorm buffers and Adam moments."""
+    size, batch, feats, _ = U.CONFIGS["mini32"]
+    data = O.make_batch(batch, feats, size, U.SEED_BATCH)
+    results = []
+    for _ in range(2):
+        oG, oD, oV, tr = _build(size, feats, cuda_dev)
+        tr.generator.load_state_dict(oG.state_dict())
+        tr.discriminator.load_state_dict(oD.state_dict())
+        tr.real_inputs, tr.batch_size = data, batch
+        torch.manual_seed(U.SEED_RUN)
+        losses = [tuple(tr.train_iter().values()) for _ in range(2)]
+        torch.cuda.synchronize()
+        state = {f"G.{k}": v.detach().clone().cpu() for k, v in tr.generator.state_dict().items()}
+        state.update({f"D.{k}": v.detach().clone().cpu() for k, v in tr.discriminator.state_dict().items()})
+        for name, opt in (("og", tr.optimizer_generator), ("od", tr.optimizer_discriminator)):
+            for i, st in enumerate(opt.state.values()):
+                state[f"{name}.{i}.m"] = st["exp_avg"].detach().clone().cpu()
+                state[f"{name}.{i}.v"] = st["exp_avg_sq"].detach().clone().cpu()
+        results.append((losses, state))
+    (l0, s0), (l1, s1) = results
+    assert l0 == l1
+    assert s0.keys() == s1.keys()
+    for k in s0:
+        assert torch.equal(s0[k], s1[k]), f"{k} differs between two identical runs"
