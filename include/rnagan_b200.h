@@ -227,6 +227,11 @@ int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms
 int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, float beta2, float eps, int step,
                  int do_clamp, float clamp_lo, float clamp_hi, float grad_scale, rg_stream_t st);
 int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st);
+/* data path: uint8 HWC tiles [B][S][S][C] as the patch LMDBs hold them -> fp32 NCHW in [-1, 1];
+ * cv2 BGR->RGB (swap_rb), permute(2,0,1), ConvertImageDtype(float) and Normalize(0.5, 0.5) of src/read_data.py:341-343
+ * and src/histopathology_gan.py:106-109 in one pass, bit-identical to those CPU transforms.  Moving uint8 instead of
+ * fp32 over PCIe cuts the per-batch host->device bytes by 4. */
+int rg_tiles_u8_to_nchw(const void* tiles, float* img, int B, int C, int S, int swap_rb, rg_stream_t st);
 /* (x+1)/2 and NCHW -> NHWC fp32 (src/gan_utils.py:236-241) */
 int rg_tiles_to_unit_nhwc(const float* img, float* out, int B, int C, int S, rg_stream_t st);
 

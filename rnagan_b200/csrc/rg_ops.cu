@@ -1023,6 +1023,31 @@ __global__ void cast_f32_kernel(const float* __restrict__ src, float* __restrict
     if (dst16) dst16[i] = __float2bfloat16(src[i]);
   }
 }
+// uint8 HWC tiles (as stored in the patch LMDBs, src/read_data.py:336-343) -> fp32 NCHW in [-1, 1]:
+// cv2.cvtColor(BGR2RGB) + permute(2,0,1) + ConvertImageDtype(float) + Normalize(0.5, 0.5)
+// (src/read_data.py:341-343, src/histopathology_gan.py:106-109) in one pass, same fp32 operations (x / 255, then
+// (x - 0.5) / 0.5) so the result is bit-identical to the reference's CPU transforms.  One thread per 4 pixels of a row.
+__global__ void __launch_bounds__(256) tiles_u8_to_nchw_kernel(const uint8_t* __restrict__ tiles, float* __restrict__ img,
+                                                               int B, int C, int S, int swap_rb) {
+  const size_t nquad = static_cast<size_t>(B) * S * (S / 4);
+  for (size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < nquad;
+       q += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int xq = static_cast<int>(q % (S / 4));
+    const size_t by = q / (S / 4);                 // b * S + y
+    const size_t b = by / S;
+    const int y = static_cast<int>(by - b * S);
+    const uint8_t* src = tiles + (by * S + static_cast<size_t>(xq) * 4) * C;
+    for (int c = 0; c < C; ++c) {
+      const int cs = (swap_rb && C >= 3 && c < 3) ? 2 - c : c;
+      float4 o;
+      o.x = (__fdiv_rn(static_cast<float>(src[0 * C + cs]), 255.0f) - 0.5f) / 0.5f;
+      o.y = (__fdiv_rn(static_cast<float>(src[1 * C + cs]), 255.0f) - 0.5f) / 0.5f;
+      o.z = (__fdiv_rn(static_cast<float>(src[2 * C + cs]), 255.0f) - 0.5f) / 0.5f;
+      o.w = (__fdiv_rn(static_cast<float>(src[3 * C + cs]), 255.0f) - 0.5f) / 0.5f;
+      *reinterpret_cast<float4*>(img + ((b * C + c) * S + y) * S + static_cast<size_t>(xq) * 4) = o;
+    }
+  }
+}
 __global__ void nchw_to_unit_nhwc_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int C, int S) {
   // (x+1)/2 and NCHW -> NHWC (src/gan_utils.py:236-241)
   const size_t n = static_cast<size_t>(B) * C * S * S;
@@ -1618,6 +1643,17 @@ int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st) {
   const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 8));
   clamp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(p, n, lo, hi);
   RG_LAUNCH_CHECK("rg_clamp");
+  return 0;
+}
+
+int rg_tiles_u8_to_nchw(const void* tiles, float* img, int B, int C, int S, int swap_rb, rg_stream_t st) {
+  RG_CHECK_ARG(tiles && img && B > 0 && C >= 1 && C <= 4 && S >= 4 && S % 4 == 0,
+               "rg_tiles_u8_to_nchw: need 1..4 channels and an image side that is a multiple of 4 (S=%d)", S);
+  const size_t nquad = static_cast<size_t>(B) * S * (S / 4);
+  const int grid = static_cast<int>(std::min<size_t>((nquad + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  tiles_u8_to_nchw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(static_cast<const uint8_t*>(tiles), img, B, C,
+                                                                           S, swap_rb);
+  RG_LAUNCH_CHECK("rg_tiles_u8_to_nchw");
   return 0;
 }
 

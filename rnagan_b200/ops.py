@@ -453,6 +453,19 @@ def gp_norm(g, lambd, partial, out3):
                "rg_gp_norm")
 
 
+def tiles_u8_to_nchw(tiles, out=None, swap_rb=False):
+    """uint8 [B, S, S, C] (HWC, optionally BGR) on the device -> fp32 NCHW [B, C, S, S] in [-1, 1]."""
+    if tiles.device.type != "cuda" or tiles.dtype != torch.uint8 or not tiles.is_contiguous() or tiles.dim() != 4:
+        raise ValueError("tiles must be a contiguous CUDA uint8 tensor [B, S, S, C] (no CPU fallback)")
+    B, S, S2, C = tiles.shape
+    if S != S2:
+        raise ValueError("tiles must be square")
+    if out is None:
+        out = torch.empty(B, C, S, S, dtype=torch.float32, device=tiles.device)
+    _lib.check(_lib.lib().rg_tiles_u8_to_nchw(_p(tiles), _p(out), B, C, S, int(swap_rb), _st()), "rg_tiles_u8_to_nchw")
+    return out
+
+
 def tiles_to_unit_nhwc(img, out):
     B, C, S, _ = img.shape
     _lib.check(_lib.lib().rg_tiles_to_unit_nhwc(_p(img), _p(out), B, C, S, _st()), "rg_tiles_to_unit_nhwc")

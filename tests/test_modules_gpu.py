@@ -305,3 +305,30 @@ def test_up_generator_g_step_matches_oracle(cuda_dev, size, B):
     bound = 1.0 - 2.0 * (1.0 - c_bf16) - 0.01
     for n, cs in pairs:
         assert cs >= bound, f"{n}: cosine {cs:.4f} < {bound:.4f} (torch-bf16 worst {c_bf16:.4f})"
+
+
+def test_tiles_u8_normalise_bit_exact_and_prefetcher(cuda_dev):
+    """Data path: rg_tiles_u8_to_nchw equals the reference's CPU transforms bit for bit
+    (cv2 BGR->RGB, permute(2,0,1), ConvertImageDtype(float) = x / 255, Normalize(0.5, 0.5) = (x - 0.5) / 0.5;
+    src/read_data.py:341-343, src/histopathology_gan.py:106-109), and DevicePrefetcher yields device batches."""
+    from rnagan_b200 import data as D
+    g = torch.Generator().manual_seed(3)
+    tiles = torch.randint(0, 256, (5, 64, 64, 3), dtype=torch.uint8, generator=g)
+    tiles[0, 0, 0] = torch.tensor([0, 128, 255], dtype=torch.uint8)
+
+    def cpu_transform(t, bgr):
+        t = t.flip(-1) if bgr else t                       # BGR -> RGB swaps channels 0 and 2
+        x = t.permute(0, 3, 1, 2).to(torch.float32) / 255  # ConvertImageDtype(torch.float)
+        return (x - 0.5) / 0.5                             # Normalize(mean=0.5, std=0.5)
+
+    for bgr in (True, False):
+        got = D.normalise_tiles(tiles.to(cuda_dev), bgr=bgr)
+        ref = cpu_transform(tiles, bgr)
+        assert got.shape == (5, 3, 64, 64) and torch.equal(got.cpu(), ref)
+    rna = torch.randn(5, 40, generator=g)
+    loader = [{"image": tiles[:3], "rna_data": rna[:3], "labels": torch.zeros(3)},
+              {"image": tiles[3:], "rna_data": rna[3:], "labels": torch.zeros(2)}]
+    seen = list(D.DevicePrefetcher(loader, cuda_dev, bgr=True))
+    assert len(seen) == 2 and seen[0]["image"].device.type == "cuda" and seen[0]["image"].dtype == torch.float32
+    assert torch.equal(torch.cat([b["image"] for b in seen]).cpu(), cpu_transform(tiles, True))
+    assert torch.equal(torch.cat([b["rna_data"] for b in seen]).cpu(), rna)
