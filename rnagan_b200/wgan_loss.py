@@ -90,9 +90,17 @@ _CACHE = _StepCache()
 _SHARED_VAE = {}
 
 
+def strip_module_prefix(state):
+    """`model_dict_best.pt` written from an nn.DataParallel-wrapped betaVAE carries `module.`-prefixed keys; the
+    reference's `load_state_dict(torch.load(path))` (src/wgan_loss.py:68) only accepts the bare layout.  Accept both."""
+    if state and all(k.startswith("module.") for k in state):
+        return {k[len("module."):]: v for k, v in state.items()}
+    return state
+
+
 def _load_vae(checkpoint, rna_features, beta):
     vae = betaVAE(rna_features, 2048, [6000, 4000, 2048], [4000, 6000], beta=beta)
-    vae.load_state_dict(torch.load(checkpoint))
+    vae.load_state_dict(strip_module_prefix(torch.load(checkpoint, map_location="cpu")))
     vae.eval()
     return vae
 

@@ -205,3 +205,24 @@ def test_native_weight_layout_plumbing_cpu():
     opt.state[w]["exp_avg"] = vals.clone()                # contiguous, as torch.load of an upstream checkpoint gives
     st = _ensure_state(opt, w)
     assert st["exp_avg"].stride() == w.stride() and torch.equal(st["exp_avg"], vals)
+
+
+def test_vae_checkpoint_with_module_prefix_loads(tmp_path):
+    """Checkpoint interop: a betaVAE state_dict saved from an nn.DataParallel wrapper (`module.` keys)
+    loads into the loss objects exactly like the bare layout the reference writes (src/betaVAE.py:265-278)."""
+    import torch
+
+    from rnagan_b200 import wgan_loss
+    from rnagan_b200.betaVAE import betaVAE
+
+    torch.manual_seed(1)
+    vae = betaVAE(24, 2048, [6000, 4000, 2048], [4000, 6000], beta=0.005)
+    bare = tmp_path / "bare.pt"
+    wrapped = tmp_path / "wrapped.pt"
+    torch.save(vae.state_dict(), bare)
+    torch.save({"module." + k: v for k, v in vae.state_dict().items()}, wrapped)
+    a = wgan_loss.WassersteinGeneratorLossVAE(str(bare), 24).betavae
+    b = wgan_loss.WassersteinGeneratorLossVAE(str(wrapped), 24).betavae
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    assert not a.training and not b.training
