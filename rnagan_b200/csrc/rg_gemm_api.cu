@@ -31,6 +31,10 @@ int num_sms() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    // RG_NUM_SMS caps the persistent grids (even, >= 2): data-parallel runs can leave a few SMs to NCCL's all-reduce
+    // kernels, which cannot co-reside with a tile-engine CTA that owns the whole shared memory of its SM
+    const char* e = getenv("RG_NUM_SMS");
+    if (e && atoi(e) >= 2 && atoi(e) < sms) sms = atoi(e) & ~1;
   }
   return sms;
 }
