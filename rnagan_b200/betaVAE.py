@@ -170,7 +170,7 @@ def train_step(model, optimizer, x, beta, keep_mask=None, eps=None):
     x = x.to(device=eng.device, dtype=torch.float32).contiguous()
     out3 = eng.step(x, beta, keep_mask=keep_mask, eps=eps)
     adam_step(optimizer, grad_scale=eng.sync.finish())
-    eng.pack()
+    eng.pack(full=False)          # Adam re-emitted the unpadded bf16 operand copies itself
     model.__dict__["_rg_dirty"] = True
     model.__dict__["_rg_dec_dirty"] = True
     return out3

@@ -121,6 +121,8 @@ struct WgradArgs {
   // splits == 1: the epilogue writes the NATIVE layout dW[p][tap][s] (= a channels_last [Cp][Cs][kh][kw] tensor): each
   // thread stores whole 128-byte lines, beta/alpha applied in place, no partials and no reduce pass
   float* native_out;
+  int ld_out, n_out;   // native_out row pitch and valid columns per (row, tap): Cs, or the ragged N of a plain GEMM
+                       // (then rows are only 8-byte aligned and the epilogue stores float2)
   const float* alpha_dev;
   float alpha, beta;
   int msub;            // 128-row accumulators per unit: 1, or 2 (256-row M tile sharing every B slab)
@@ -936,16 +938,31 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
           for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
             int tap, chunk;
             wgrad_slab(p, n_tile, sl, tap, chunk);
-            float* o = p.native_out + (static_cast<size_t>(prow) * p.num_taps + tap) * p.Cs + chunk * 64;
+            float* o = p.native_out + (static_cast<size_t>(prow) * p.num_taps + tap) * p.ld_out + chunk * 64;
+            const bool vec4 = (p.ld_out & 3) == 0;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               uint32_t v[32];
               tmem_ld_32x32(taddr + sl * 64 + h * 32, v);
               tmem_ld_wait();
-              if (row_ok) {
+              if (row_ok && !vec4) {
+                // ragged row pitch (even, not a multiple of 4 floats): 8-byte stores
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                  if (chunk * 64 + h * 32 + g * 2 + 2 <= p.n_out) {
+                    float2 f = make_float2(a * __uint_as_float(v[g * 2 + 0]), a * __uint_as_float(v[g * 2 + 1]));
+                    float2* dst = reinterpret_cast<float2*>(o + h * 32 + g * 2);
+                    if (beta != 0.0f) {
+                      const float2 old = *dst;
+                      f.x += beta * old.x; f.y += beta * old.y;
+                    }
+                    *dst = f;
+                  }
+                }
+              } else if (row_ok) {
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
-                  if (chunk * 64 + h * 32 + g * 4 + 4 <= p.Cs) {
+                  if (chunk * 64 + h * 32 + g * 4 + 4 <= p.n_out) {
                     float4 f = make_float4(a * __uint_as_float(v[g * 4 + 0]), a * __uint_as_float(v[g * 4 + 1]),
                                            a * __uint_as_float(v[g * 4 + 2]), a * __uint_as_float(v[g * 4 + 3]));
                     float4* dst = reinterpret_cast<float4*>(o + h * 32 + g * 4);

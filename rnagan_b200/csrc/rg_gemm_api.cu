@@ -442,9 +442,16 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
                         float* dW, void* ws, size_t ws_bytes, float alpha, const float* alpha_dev, float beta,
                         cudaStream_t st, int Cs_out = -1, bool native = false) {
   if (Cs_out < 0) Cs_out = Cs;
-  if (native && (Cs_out != Cs || Cs % 4 != 0)) {
+  // native: rows of Cs_out floats per (p, tap).  Column padding (Cs_out < Cs) is only meaningful for one tap (the
+  // ragged plain GEMM), needs an even Cs_out (8-byte aligned rows) and the direct epilogue (the native reduce kernel
+  // walks unpadded float4 rows).
+  if (native && w.taps != 1 && (Cs_out != Cs || Cs % 4 != 0)) {
     set_error("native weight-gradient layout needs Cs %% 4 == 0 and no column padding (Cs=%d)", Cs);
     return RG_EINVAL;
+  }
+  if (native && w.taps == 1) {     // one tap: native == dense row-major, so falling back to the reduce path is safe
+    if (Cs_out != Cs && (Cs_out % 2 != 0 || w.splits != 1)) native = false;
+    if (Cs_out == Cs && Cs % 4 != 0) native = false;
   }
   int rc = ensure_attrs();
   if (rc) return rc;
@@ -472,6 +479,8 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
   for (int t = 0; t < w.taps; ++t) a.taps[t] = taps[t];
   a.ws = static_cast<float*>(ws);
   a.msub = w.msub;
+  a.ld_out = Cs_out;
+  a.n_out = Cs_out;
   if (direct) {
     if (native_direct) a.native_out = dW;
     else a.direct_out = dW;
@@ -1205,7 +1214,11 @@ static int gemm_tn_impl(const void* A, int lda, const void* Bm, int ldb, float* 
   rc = encode_map_4d(&maps.b, A, M, 1, 1, R, lda, lda, lda, 64, 1, 1, 64);
   if (rc) return rc;
   Tap taps[1] = {{0, 0, 0, 0}};
-  return launch_wgrad(maps, w, taps, R, 1, 1, M, Nw, C, ws, ws_bytes, alpha, alpha_dev, beta, st, N);
+  // With a single tap the native gradient layout [p][tap][s] IS the dense row-major C[M][N]: when N needs no column
+  // padding the epilogue stores C directly (alpha, beta in place) whenever one unit covers all R rows -- every
+  // nn.Linear weight gradient of the betaVAE step except the ragged 19198-column one -- instead of writing fp32
+  // partials and copying them (1.2 ms of the 5.0 ms step, tools/vae_profile.py).
+  return launch_wgrad(maps, w, taps, R, 1, 1, M, Nw, C, ws, ws_bytes, alpha, alpha_dev, beta, st, N, true);
 }
 
 int rg_gemm_tn(const void* A, const void* Bm, float* C, void* ws, size_t ws_bytes, int R, int M, int N, float alpha,

@@ -917,14 +917,29 @@ class VAETrainEngine:
         self.partial = torch.zeros(2, 256, dtype=F32, device=dev)
         self.out3 = torch.zeros(3, dtype=F32, device=dev)
         self.sync = GradSync(vae)
+        # nn.Linear weights whose bf16 operand copy has the SAME element order (no column padding): the fused Adam
+        # step re-emits the copy while it updates the fp32 master, so no cast pass follows the optimiser step
+        self._shadowed = set()
+        pairs = [(l.weight, w) for (l, _), w in zip(self.blocks, self.w)]
+        pairs += [(self.last.weight, self.w_last), (vae.z_mu.weight, self.w_cat[:self.Z]),
+                  (vae.z_logvar.weight, self.w_cat[self.Z:])]
+        for p, w in pairs:
+            if tuple(w.shape) == tuple(p.shape) and w.is_contiguous():
+                p._rg_shadow = w
+                self._shadowed.add(id(p))
         self.pack()
 
     def pack(self, full=True):
+        """full=False (right after the fused Adam step): only the copies Adam does not re-emit (padded layouts, the
+        concatenated head bias)."""
+        def cast(p, cols, out):
+            if full or id(p) not in self._shadowed:
+                ops.cast_pad_bf16(p.detach(), cols, out=out)
         for (l, _), w in zip(self.blocks, self.w):
-            ops.cast_pad_bf16(l.weight.detach(), w.shape[1], out=w)
-        ops.cast_pad_bf16(self.last.weight.detach(), self.w_last.shape[1], out=self.w_last)
-        ops.cast_pad_bf16(self.vae.z_mu.weight.detach(), self.Z, out=self.w_cat[:self.Z])
-        ops.cast_pad_bf16(self.vae.z_logvar.weight.detach(), self.Z, out=self.w_cat[self.Z:])
+            cast(l.weight, w.shape[1], w)
+        cast(self.last.weight, self.w_last.shape[1], self.w_last)
+        cast(self.vae.z_mu.weight, self.Z, self.w_cat[:self.Z])
+        cast(self.vae.z_logvar.weight, self.Z, self.w_cat[self.Z:])
         with torch.no_grad():
             self.b_cat[:self.Z].copy_(self.vae.z_mu.bias)
             self.b_cat[self.Z:].copy_(self.vae.z_logvar.bias)

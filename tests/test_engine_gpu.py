@@ -146,15 +146,27 @@ def test_proj_wgrad_and_fwd(cuda_dev):
     assert _rel(dW, refw) < 2e-3
 
 
-@pytest.mark.parametrize("R,M,N", [(4096, 64, 64), (100000, 64, 64), (64, 128, 256), (777, 256, 128)])
+@pytest.mark.parametrize("R,M,N", [(4096, 64, 64), (100000, 64, 64), (64, 128, 256), (777, 256, 128),
+                                   (128, 1024, 1998), (128, 1024, 199), (128, 512, 2048)])
 def test_gemm_tn(cuda_dev, R, M, N):
+    """C = A^T B (nn.Linear weight gradients, image-side wgrad): split-K + reduce, the direct epilogue (one unit covers
+    all rows; N = 1998: ragged 8-byte-aligned rows, float2 stores; N = 199: odd, falls back to the reduce path), and
+    alpha / beta accumulation in place."""
     from rnagan_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(R + M + N)
     A = _bf(torch.randn(R, M, generator=g)).to(cuda_dev)
     Bm = _bf(torch.randn(R, N, generator=g)).to(cuda_dev)
     ref = A.double().t() @ Bm.double()
-    out = ops.gemm_tn(A.to(torch.bfloat16), Bm.to(torch.bfloat16))
-    assert _rel(out.double(), ref) < 2e-3
+    Ab, Bb = A.to(torch.bfloat16), Bm.to(torch.bfloat16)
+    if N % 8:                      # rows of the bf16 operands need a pitch that is a multiple of 8 elements
+        Np = (N + 7) // 8 * 8
+        Bb = torch.zeros(R, Np, dtype=torch.bfloat16, device=cuda_dev)
+        Bb[:, :N] = Bm.to(torch.bfloat16)
+        Bb = Bb[:, :N]
+    out = ops.gemm_tn(Ab, Bb, N=N)
+    assert out.shape == (M, N) and _rel(out.double(), ref) < 2e-3
+    ops.gemm_tn(Ab, Bb, out=out, alpha=0.5, beta=1.0, N=N)
+    assert _rel(out.double(), 1.5 * ref) < 2e-3
 
 
 def test_pack_edge(cuda_dev):
