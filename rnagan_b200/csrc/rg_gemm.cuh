@@ -1,19 +1,25 @@
 // rg_gemm.cuh -- the tcgen05/TMEM/TMA implicit-GEMM tile engine shared by every dense contraction on the
 // RNA-GAN hot path:
 //
-//   * gemm_fwd_kernel   : D[M=128 pixels, N<=256] += A[pixels, K] * B[N, K]^T, both operands K-major.
-//                         The A tile of one k-block is a 4-D TMA box (64 channels x bw x bh x bb pixels) read at a
-//                         per-tap pixel offset from one of up to four strided views ("parity maps") of an NHWC
-//                         activation, so a stride-2 4x4 convolution (16 taps), its transposed form (4 output phases
-//                         x 4 taps) and a plain GEMM (1 tap, H=W=1) are the same kernel with different tap tables.
-//                         Out-of-image taps are zero-filled by TMA: no padding buffers, no im2col in HBM.
+//   * gemm_fwd_kernel   : D[M pixels, N<=256] += A[pixels, K] * B[N, K]^T.  The A tile of one k-block is a 4-D TMA box
+//                         (64 channels x bw x bh x bb pixels) read at a per-tap pixel offset from one of up to four
+//                         strided views ("parity maps") of an NHWC activation, so a stride-2 4x4 convolution (16
+//                         taps), its transposed form (4 output phases x 4 taps, or all four phases merged in one tile
+//                         for Cs = 64), a 3x3 convolution and a plain GEMM (1 tap, H=W=1) are the same kernel with
+//                         different tap tables.  Out-of-image taps are zero-filled by TMA: no padding buffers, no
+//                         im2col in HBM.  B is K-major or, straight from w_down, MN-major.
+//                         CG = 2: the two SMs of a TPC run one tcgen05.mma.cta_group::2 (M = 256) per k-step, each CTA
+//                         fetching its own 128 A rows and half of the B rows.
 //   * gemm_wgrad_kernel : dW[tap][p, s] = sum_pixels lo[pixel, p] * hi[pixel@tap, s]; both operands are the raw NHWC
-//                         tiles used as MN-major UMMA operands (reduction over pixel rows), split-K over pixel blocks
-//                         with fp32 partials reduced in a fixed order (deterministic, like cudnn.deterministic=True in
-//                         the reference, src/histopathology_gan.py:289).
+//                         tiles used as MN-major UMMA operands (reduction over pixel rows); output in the native
+//                         [p][tap][s] layout directly (one unit covers all pixels) or split-K over pixel blocks with
+//                         fp32 partials reduced in a fixed order (deterministic, like cudnn.deterministic=True in the
+//                         reference, src/histopathology_gan.py:289).
 //
-// Both are persistent, warp-specialised kernels: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
-// warps 2-5 = epilogue (TMEM -> registers -> HBM) overlapping the next tile's MMAs through a double-buffered
+// Both are persistent, warp-specialised kernels of 224 threads: warp 0 = TMA producer of the A operand (+ expect_tx),
+// warp 6 = TMA producer of the B operand, warp 1 = single-thread MMA issuer (+ TMEM owner), warps 2-5 = epilogue
+// (TMEM -> registers -> swizzled smem slab -> TMA store, with optional per-column affine / activation, fused BatchNorm
+// statistics and the opt-in fused elementwise backward) overlapping the next tile's MMAs through a double-buffered
 // accumulator (2 x 256 TMEM columns).
 #pragma once
 #include "rg_ptx.cuh"
