@@ -235,15 +235,18 @@ def run_ours(args, rank, world, local_rank):
         tr.train_iter()
     barrier()
     e0.record()
+    n_log0 = len(tr.loss_logs[names[0]])
     for i in range(Ke):
         tr.real_inputs = hb[i & 1]                          # alternate batches: the per-batch H2D/encoder cache misses
-        tr.train_iter()
+        tr.train_iter(defer=True)                           # what Trainer.train runs per batch: the host reads the
+    tr.flush()                                              # three losses of step i once step i+1 is queued
     e1.record()
+    assert len(tr.loss_logs[names[0]]) == n_log0 + Ke       # every step's losses reached the host inside the region
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / Ke
     h2d = B * 3 * SIZE * SIZE * 4 + B * GENES * 4 + 3 * B * LATENT * 4 + 4
     e2e = {"value": world * 1000.0 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
-           "ms_per_step": ms_e2e, "steps": Ke, "api": "rnagan_b200.trainer.Trainer.train_iter -> wgan_loss.*.train_ops"}
+           "ms_per_step": ms_e2e, "steps": Ke, "api": "rnagan_b200.trainer.Trainer.train_iter(defer=True) [the per-batch call of Trainer.train] -> wgan_loss.*.device_ops; losses read on the host one step late, all inside the timed region"}
 
     # ------------------------------------------------------------------ live per-kernel roofline (outside timing)
     peaks = measured_peaks()

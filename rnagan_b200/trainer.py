@@ -44,6 +44,7 @@ class Trainer:
         self.batch_size = None
         self.real_inputs = None
         self.labels = None
+        self._pending = []
         self.loss_information = {"generator_losses": 0.0, "discriminator_losses": 0.0, "generator_iters": 0,
                                  "discriminator_iters": 0}
         self.loss_logs, self.metric_logs = {}, {}
@@ -61,47 +62,103 @@ class Trainer:
         fn = getattr(loss, "device_ops", None)
         return fn(**kwargs) if fn is not None else loss.train_ops(**kwargs)
 
-    def _read_back(self, pending):
-        """{name: device tensor [1] | float} -> {name: float} with a single device->host copy + synchronisation."""
-        dev = [(n, v) for n, v in pending.items() if torch.is_tensor(v)]
-        out = {n: v for n, v in pending.items() if not torch.is_tensor(v)}
-        if dev:
-            if getattr(self, "_loss_pinned", None) is None or self._loss_pinned.numel() < len(dev):
-                self._loss_pinned = torch.empty(max(8, len(dev)), dtype=torch.float32).pin_memory()
-            for i, (_, v) in enumerate(dev):
-                self._loss_pinned[i:i + 1].copy_(v.reshape(1), non_blocking=True)
-            torch.cuda.current_stream(dev[0][1].device).synchronize()
-            for i, (n, _) in enumerate(dev):
-                out[n] = float(self._loss_pinned[i])
-        return out
+    # ---------------------------------------------------------------------------------------- loss read-back
+    # The reference's train_ops return Python floats (three `.item()` synchronisations per iteration, [tg]); here the
+    # losses stay on the device until the end of the iteration, are copied into a pinned ring slot asynchronously and
+    # folded into loss_logs / loss_information either at once (`train_iter()`, one synchronisation) or one iteration
+    # late (`train_iter(defer=True)`, what `train` uses): the host then waits on iteration i-1 while iteration i is
+    # already queued, so the device never drains.  Reading `loss_logs` / `loss_information` flushes what is pending.
+    _RING = 4
 
-    def train_iter(self):
+    def _enqueue(self, pending, kinds):
+        dev = [(n, v) for n, v in pending.items() if torch.is_tensor(v)]
+        entry = {"kinds": kinds, "host": {n: v for n, v in pending.items() if not torch.is_tensor(v)}, "dev": [],
+                 "event": None, "slot": None}
+        if dev:
+            if getattr(self, "_loss_pinned", None) is None or self._loss_pinned.size(1) < len(dev):
+                self.flush()
+                self._loss_pinned = torch.empty(self._RING, max(8, len(dev)), dtype=torch.float32).pin_memory()
+                self._loss_slot = 0
+            if len(self._pending) >= self._RING - 1:
+                self.flush()
+            slot = self._loss_pinned[self._loss_slot]
+            self._loss_slot = (self._loss_slot + 1) % self._RING
+            for i, (_, v) in enumerate(dev):
+                slot[i:i + 1].copy_(v.reshape(1), non_blocking=True)
+            entry["event"] = torch.cuda.Event()
+            entry["event"].record(torch.cuda.current_stream(dev[0][1].device))
+            entry["slot"], entry["dev"] = slot, [n for n, _ in dev]
+        self._pending.append(entry)
+        return entry
+
+    def _resolve(self, entry):
+        """Wait for one iteration's losses and fold them into the logs; returns {loss name: float}."""
+        values = dict(entry["host"])
+        if entry["event"] is not None:
+            entry["event"].synchronize()
+            for i, n in enumerate(entry["dev"]):
+                values[n] = float(entry["slot"][i])
         lgen = ldis = 0.0
-        gen_iter = dis_iter = 0
+        for name in self.losses:
+            v = values.get(name)
+            kind = entry["kinds"].get(name)
+            if kind == "g":
+                lgen += v
+            elif kind == "d":
+                ldis += v
+            self._loss_logs.setdefault(name, []).append(v)
+        self._loss_information["generator_losses"] += lgen
+        self._loss_information["discriminator_losses"] += ldis
+        return values
+
+    def flush(self, keep=0):
+        """Resolve pending iterations, oldest first, until at most `keep` remain."""
+        values = None
+        while len(self._pending) > keep:
+            values = self._resolve(self._pending.pop(0))
+        return values
+
+    @property
+    def loss_logs(self):
+        self.flush()
+        return self._loss_logs
+
+    @loss_logs.setter
+    def loss_logs(self, value):
+        self._pending = []
+        self._loss_logs = value
+
+    @property
+    def loss_information(self):
+        self.flush()
+        return self._loss_information
+
+    @loss_information.setter
+    def loss_information(self, value):
+        self._pending = []
+        self._loss_information = value
+
+    def train_iter(self, defer=False):
+        """One iteration = every loss object's optimiser step in list order (G loss, critic loss, gradient penalty).
+        Returns this iteration's {loss name: float}; with defer=True returns None and the values reach the logs when
+        the next iteration has been queued (or on the next read of the logs)."""
+        info = self._loss_information                      # iteration counters do not depend on the loss values
         pending, kinds = {}, {}
         for name, loss in self.losses.items():
             if isinstance(loss, GeneratorLoss):
-                if self.loss_information["discriminator_iters"] % self.ncritic == 0:
+                if info["discriminator_iters"] % self.ncritic == 0:
                     pending[name] = self._call(name)
                     kinds[name] = "g"
             elif isinstance(loss, DiscriminatorLoss):
                 pending[name] = self._call(name)
                 kinds[name] = "d"
-        values = self._read_back(pending)
-        for name in self.losses:
-            v = values.get(name)
-            if kinds.get(name) == "g":
-                lgen += v
-                gen_iter += 1
-            elif kinds.get(name) == "d":
-                ldis += v
-                dis_iter += 1
-            self.loss_logs.setdefault(name, []).append(v)
-        self.loss_information["generator_losses"] += lgen
-        self.loss_information["discriminator_losses"] += ldis
-        self.loss_information["generator_iters"] += gen_iter
-        self.loss_information["discriminator_iters"] += 1 if dis_iter else 0
-        return values
+        info["generator_iters"] += sum(1 for k in kinds.values() if k == "g")
+        info["discriminator_iters"] += 1 if "d" in kinds.values() else 0
+        self._enqueue(pending, kinds)
+        if defer:
+            self.flush(keep=1)
+            return None
+        return self.flush()
 
     def save_model(self, epoch, save_items=None):
         if self.last_retained_checkpoint == self.retain_checkpoints:
@@ -137,7 +194,8 @@ class Trainer:
                 self.real_inputs = data
                 if isinstance(data, dict) and "image" in data:
                     self.batch_size = data["image"].size(0)
-                self.train_iter()
+                self.train_iter(defer=True)
+            self.flush()
             self.save_model(epoch)
 
     def __call__(self, data_loader, **kwargs):

@@ -133,17 +133,25 @@ class _VAEConditioned:
         self._prefetch_real(real_inputs, device)
         eng = generator._engine()
         E = generator.encoding_dims
-        # one pinned staging buffer and one device buffer PER LOSS OBJECT: Trainer.train_iter defers the three host
-        # synchronisations of an iteration to its end, so a step's asynchronous copy may still be in flight when the
-        # next step draws its noise; the same object runs again only after that end-of-iteration synchronisation
+        # pinned staging PER LOSS OBJECT, two buffers used alternately: Trainer.train_iter defers the host
+        # synchronisation (to the end of the iteration, or by one more iteration in `train`), so a step's asynchronous
+        # copy may still be in flight when the same object draws its next noise; the event makes reuse safe at any lag
         stage = eng.bufs.__dict__.setdefault("_noise_pinned", {})
-        pinned = stage.get((id(self), B, E))
-        if pinned is None:
-            pinned = torch.empty(B, E, dtype=F32).pin_memory()
-            stage[(id(self), B, E)] = pinned
+        ring = stage.get((id(self), B, E))
+        if ring is None:
+            ring = {"i": 0, "slots": [[torch.empty(B, E, dtype=F32).pin_memory(), None] for _ in range(2)]}
+            stage[(id(self), B, E)] = ring
+        slot = ring["slots"][ring["i"]]
+        ring["i"] ^= 1
+        if slot[1] is not None:
+            slot[1].synchronize()
+        pinned = slot[0]
         pinned.uniform_(-0.3, 0.3)                 # same CPU generator stream as torch.FloatTensor(B, E).uniform_()
         noise_d = eng.bufs.get(f"noise.{type(self).__name__}", (B, E), F32)
         noise_d.copy_(pinned, non_blocking=True)
+        if slot[1] is None:
+            slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream(device))
         return noise_d, z
 
     @staticmethod

@@ -129,6 +129,14 @@ def test_trainer_binds_train_ops_by_parameter_name():
     assert calls[0][0] == "g" and calls[0][1] is tr.generator and calls[1] == ("d", tr.discriminator, "cpu", 3)
     assert tr.devices == [0]                      # unknown kwargs become attributes, like torchgan
     assert tr.loss_information["generator_iters"] == 1 and tr.loss_information["discriminator_iters"] == 1
+    # deferred read-back (what Trainer.train uses): at most one iteration stays pending, reading the logs flushes it,
+    # and nothing is lost or reordered
+    for _ in range(3):
+        assert tr.train_iter(defer=True) is None
+        assert len(tr._pending) == 1
+    assert tr.loss_logs == {"FakeG": [1.0] * 4, "FakeD": [2.0] * 4} and tr._pending == []
+    info = tr.loss_information
+    assert info == {"generator_losses": 4.0, "discriminator_losses": 8.0, "generator_iters": 4, "discriminator_iters": 4}
 
 
 def test_shard_range_partitions_units():

@@ -184,6 +184,22 @@ def test_checkpoint_roundtrip_and_errors(cuda_dev):
     torch.manual_seed(3); v1 = tr.train_iter()
     torch.manual_seed(3); v2 = tr2.train_iter()
     assert list(v1.values()) == list(v2.values())
+    # deferred read-back (Trainer.train's per-batch call) = the synchronous one, value for value, over fresh batches
+    batches = [O.make_batch(8, feats, 32, 10 + i) for i in range(4)]
+    torch.manual_seed(5)
+    sync_vals = []
+    for b in batches:
+        tr.real_inputs = b
+        sync_vals.append(list(tr.train_iter().values()))
+    torch.manual_seed(5)
+    n0 = len(tr2.loss_logs["WassersteinGeneratorLossVAE"])
+    for b in batches:
+        tr2.real_inputs = b
+        assert tr2.train_iter(defer=True) is None
+    logs = tr2.loss_logs
+    lag_vals = [[logs[k][n0 + i] for k in logs] for i in range(4)]
+    assert lag_vals == sync_vals
+    assert tr2.loss_information["discriminator_iters"] == tr.loss_information["discriminator_iters"]
     # reference error behaviour
     tr.generator.label_type = "required"
     with pytest.raises(Exception, match="GAN model requires labels for training"):
