@@ -271,6 +271,8 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
   }
   const int crank = CG > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const uint32_t tmem_base = pipeline_prologue<CG>(s, warp, p.nstages);
+  griddep_wait();        // PDL: everything above overlapped the previous kernel's tail; no global access before this
+  griddep_launch();
 
   const int num_kb = p.num_taps * p.chunks;
   const int nstages = p.nstages;
@@ -819,6 +821,8 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
     tma_prefetch_desc(&maps.b);
   }
   const uint32_t tmem_base = pipeline_prologue<1>(s, warp, 4);
+  griddep_wait();
+  griddep_launch();
 
   const int msub = p.msub;                                    // 128-row accumulators per unit (1 or 2)
   const int a_bytes = msub * 16384;                           // msub * 2 slabs of [64 px][64 ch]

@@ -39,6 +39,15 @@ int num_sms() {
   return sms;
 }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("RG_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 // ------------------------------------------------------------------------------------------------ tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -176,24 +185,7 @@ static int ensure_attrs() {
 
 template <int OUT, int CG, bool AUX = false>
 static int launch_fwd_t(const GemmMaps& maps, const FwdArgs& a, int grid, size_t smem, cudaStream_t st) {
-  if (CG == 1) {
-    gemm_fwd_kernel<OUT, CG, AUX><<<grid, kGemmThreads, smem, st>>>(maps, a);
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    RG_CUDA(cudaLaunchKernelEx(&cfg, gemm_fwd_kernel<OUT, CG, AUX>, maps, a));
-  }
+  RG_CUDA(launch_pdl(gemm_fwd_kernel<OUT, CG, AUX>, dim3(grid), dim3(kGemmThreads), smem, st, CG, maps, a));
   RG_LAUNCH_CHECK("gemm_fwd_kernel");
   return 0;
 }
@@ -490,7 +482,7 @@ static int launch_wgrad(const GemmMaps& maps, const WgradGeom& w, const Tap* tap
   }
   const int units = w.m_tiles * w.n_tiles * w.splits;
   const int grid = std::min(units, num_sms());
-  gemm_wgrad_kernel<<<grid, kGemmThreads, kWgradSmemBytes, st>>>(maps, a);
+  RG_CUDA(launch_pdl(gemm_wgrad_kernel, dim3(grid), dim3(kGemmThreads), kWgradSmemBytes, st, 1, maps, a));
   RG_LAUNCH_CHECK("gemm_wgrad_kernel");
   if (direct) return 0;
   if (native) {

@@ -9,6 +9,7 @@
 // src/histopathology_gan.py:289).
 #include <algorithm>
 #include "rg_host.cuh"
+#include "rg_ptx.cuh"
 #include <cuda_bf16.h>
 
 namespace rg {
@@ -95,6 +96,8 @@ constexpr int kRedStageBytes = 2 * kRedRows * 256 * 16;   // per input tensor: d
 // register loads were sunk next to their uses by ptxas -- one row in flight per thread, 38-48 % of HBM peak.)
 template <class F>
 __global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int rows_per_block, float* __restrict__ partial) {
+  griddep_wait();
+  griddep_launch();
   constexpr int K = F::K;
   constexpr int NT = F::NT;
   constexpr int R = kRedRows;
@@ -179,6 +182,8 @@ __global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int r
 // in a fixed order
 __global__ void __launch_bounds__(1024) colreduce_stage2(const float* __restrict__ partial, int nblocks, int KC,
                                                          float* __restrict__ out) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + cx;
@@ -247,9 +252,9 @@ static int run_colreduce(F f, int M, int C, float* ws, size_t ws_bytes, float* o
       attr_done = true;
     }
   }
-  colreduce_stage1<F><<<p.blocks, 256, smem, st>>>(f, M, C, p.rows_per_block, ws);
+  RG_CUDA(launch_pdl(colreduce_stage1<F>, dim3(p.blocks), dim3(256), smem, st, 1, f, M, C, p.rows_per_block, ws));
   RG_LAUNCH_CHECK(name);
-  colreduce_stage2<<<ceil_div(K * C, 32), 1024, 0, st>>>(ws, p.blocks, K * C, out);
+  RG_CUDA(launch_pdl(colreduce_stage2, dim3(ceil_div(K * C, 32)), dim3(1024), 0, st, 1, ws, p.blocks, K * C, out));
   RG_LAUNCH_CHECK(name);
   return 0;
 }
@@ -258,6 +263,8 @@ static int run_colreduce(F f, int M, int C, float* ws, size_t ws_bytes, float* o
 // Functor: __device__ void operator()(size_t row, int c0) const  -- processes 8 channels of one row
 template <class F>
 __global__ void __launch_bounds__(256) ew_kernel(F f, unsigned nvec, int cgs, int cg_shift) {
+  griddep_wait();
+  griddep_launch();
   const unsigned stride = gridDim.x * blockDim.x;
   const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (cg_shift >= 0) {
@@ -297,7 +304,7 @@ static int run_ew(F f, int M, int C, cudaStream_t st, const char* name) {
     shift = 0;
     while ((1 << shift) < cgs) ++shift;
   }
-  ew_kernel<F><<<grid, 256, 0, st>>>(f, static_cast<unsigned>(nvec), cgs, shift);
+  RG_CUDA(launch_pdl(ew_kernel<F>, dim3(grid), dim3(256), 0, st, 1, f, static_cast<unsigned>(nvec), cgs, shift));
   RG_LAUNCH_CHECK(name);
   return 0;
 }
@@ -306,6 +313,8 @@ static int run_ew(F f, int M, int C, cudaStream_t st, const char* name) {
 // four rows of loads are issued before the first store.
 template <class F>
 __global__ void __launch_bounds__(256) ew_split_kernel(F f, unsigned nvec, int cgs, int cg_shift) {
+  griddep_wait();
+  griddep_launch();
   const unsigned stride = gridDim.x * blockDim.x;
   const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (cg_shift >= 0) {
@@ -361,7 +370,7 @@ static int run_ew_split(F f, int M, int C, cudaStream_t st, const char* name) {
     shift = 0;
     while ((1 << shift) < cgs) ++shift;
   }
-  ew_split_kernel<F><<<grid, 256, 0, st>>>(f, static_cast<unsigned>(nvec), cgs, shift);
+  RG_CUDA(launch_pdl(ew_split_kernel<F>, dim3(grid), dim3(256), 0, st, 1, f, static_cast<unsigned>(nvec), cgs, shift));
   RG_LAUNCH_CHECK(name);
   return 0;
 }
@@ -585,6 +594,8 @@ __global__ void __launch_bounds__(256) bn_finalize_partials_kernel(
     const float* __restrict__ partial, int nparts, const float* __restrict__ gamma, const float* __restrict__ beta,
     int C, float invM, float unbias, float eps, float momentum, float* running_mean, float* running_var,
     long long* nbt, float* sums_out, float* mean, float* rstd, float* scale, float* shift) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float sm[2][8][33];
   const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -625,6 +636,8 @@ __global__ void __launch_bounds__(256) bn_finalize_partials_kernel(
 // dgamma (+)= S(du*xhat); dbeta (+)= S(du)
 __global__ void bn_param_grads_kernel(const float* __restrict__ sums, float* dgamma, float* dbeta, int C,
                                       float acc_gamma, float acc_beta) {
+  griddep_wait();
+  griddep_launch();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   dgamma[c] = (acc_gamma != 0.0f ? acc_gamma * dgamma[c] : 0.0f) + sums[C + c];
@@ -1385,9 +1398,9 @@ int rg_bn_finalize_partials(const float* stats_ws, const float* gamma, const flo
   RG_CHECK_ARG(stats_ws && gamma && beta && mean && rstd && scale && shift && M > 0 && C > 0,
                "rg_bn_finalize_partials: bad arguments");
   const float unbias = M > 1 ? static_cast<float>(M) / static_cast<float>(M - 1) : 1.0f;
-  bn_finalize_partials_kernel<<<ceil_div(C, 32), 256, 0, static_cast<cudaStream_t>(st)>>>(
-      stats_ws, num_sms(), gamma, beta, C, 1.0f / M, unbias, eps, momentum, running_mean, running_var,
-      reinterpret_cast<long long*>(num_batches_tracked), sums_out, mean, rstd, scale, shift);
+  RG_CUDA(launch_pdl(bn_finalize_partials_kernel, dim3(ceil_div(C, 32)), dim3(256), 0, static_cast<cudaStream_t>(st), 1,
+                     stats_ws, num_sms(), gamma, beta, C, 1.0f / M, unbias, eps, momentum, running_mean, running_var,
+                     reinterpret_cast<long long*>(num_batches_tracked), sums_out, mean, rstd, scale, shift));
   RG_LAUNCH_CHECK("rg_bn_finalize_partials");
   return 0;
 }
@@ -1427,8 +1440,8 @@ int rg_bn_bwd_apply(const void* dh, const void* a, const void* add, const float*
 int rg_bn_param_grads(const float* sums, float* dgamma, float* dbeta, int C, float acc_gamma, float acc_beta,
                       rg_stream_t st) {
   RG_CHECK_ARG(sums && dgamma && dbeta && C > 0, "rg_bn_param_grads: bad arguments");
-  bn_param_grads_kernel<<<ceil_div(C, 256), 256, 0, static_cast<cudaStream_t>(st)>>>(sums, dgamma, dbeta, C, acc_gamma,
-                                                                                     acc_beta);
+  RG_CUDA(launch_pdl(bn_param_grads_kernel, dim3(ceil_div(C, 256)), dim3(256), 0, static_cast<cudaStream_t>(st), 1, sums,
+                     dgamma, dbeta, C, acc_gamma, acc_beta));
   RG_LAUNCH_CHECK("rg_bn_param_grads");
   return 0;
 }

@@ -389,4 +389,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialisation attribute may
+// become resident while its predecessor in the stream is still running; griddep_wait() blocks until every
+// prerequisite grid has completed and its memory is visible, so everything before it (barrier init, TMEM allocation,
+// index arithmetic) overlaps the predecessor's tail and the launch latency.  griddep_launch() lets this grid's own
+// successor start staging.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace rg
