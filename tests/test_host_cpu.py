@@ -6,6 +6,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -234,3 +235,41 @@ def test_vae_checkpoint_with_module_prefix_loads(tmp_path):
     for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
         assert ka == kb and torch.equal(va, vb)
     assert not a.training and not b.training
+
+
+def test_rna_scaler_matches_reference_preprocessing():
+    """data.RNAScaler vs the reference's own preprocessing expressions (pandas `_get_log` + scikit-learn StandardScaler,
+    src/histopathology_gan.py:133-149; transform of a held-out table, src/read_data.py:495-496; inverse_transform,
+    src/betaVAE_sample.py:132) on a table with zero counts, an all-zero gene and a constant gene."""
+    pd = pytest.importorskip("pandas")
+    skp = pytest.importorskip("sklearn.preprocessing")
+    from rnagan_b200.data import RNAScaler, log_expression
+    rng = np.random.default_rng(0)
+    x = rng.gamma(2.0, 50.0, size=(37, 211))
+    x[rng.random(x.shape) < 0.2] = 0.0
+    x[:, 5] = 0.0
+    x[:, 7] = 3.0
+    held = rng.gamma(2.0, 50.0, size=(9, 211))
+    held[rng.random(held.shape) < 0.2] = 0.0
+
+    def _get_log(col):
+        col = np.log(col.replace(0, np.nan))
+        return col.replace(np.nan, 0)
+
+    cols = [f"rna_{i}" for i in range(x.shape[1])]
+    ref_log = pd.DataFrame(x, columns=cols).apply(_get_log).values
+    ref_held_log = pd.DataFrame(held, columns=cols).apply(_get_log).values
+    sk = skp.StandardScaler()
+    ref = sk.fit_transform(ref_log)
+    mine = RNAScaler()
+    got = mine.fit_transform(x)
+    assert np.array_equal(log_expression(x), ref_log)                     # the log step is exact
+    assert np.abs(got - ref).max() <= 1e-12 and np.abs(mine.scale_ - sk.scale_).max() <= 1e-12
+    assert np.array_equal(got.astype(np.float32)[:, 5], np.zeros(37, np.float32)) and mine.scale_[5] == 1.0
+    assert mine.scale_[7] == 1.0 and np.abs(got[:, 7]).max() <= 1e-12     # constant gene: scale 1, like scikit-learn
+    assert np.abs(mine.transform(held) - sk.transform(ref_held_log)).max() <= 1e-12
+    assert np.abs(mine.inverse_transform(got) - sk.inverse_transform(ref)).max() <= 1e-12
+    with pytest.raises(RuntimeError):
+        RNAScaler().transform(x)
+    with pytest.raises(ValueError):
+        mine.transform(x[:, :10])
