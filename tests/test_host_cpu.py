@@ -34,6 +34,50 @@ def test_library_exports_every_declared_symbol():
     assert lib.rg_launch_count() == 0          # loading launches nothing; no compute without a GPU
 
 
+def test_dependent_launch_kernels_wait_before_memory():
+    """Every kernel launched through `launch_pdl` (programmatic dependent launch, csrc/rg_host.cuh) may become resident
+    while its predecessor still runs: each of them must execute griddepcontrol.wait (SASS `ACQBULK`) -- and the sources
+    must place it before the kernel's first statement that can touch global memory (checked structurally: it is the
+    first statement of the body, or directly follows the tile engine's prologue).  Static check, no GPU."""
+    import shutil
+    from rnagan_b200 import _lib
+    if shutil.which("cuobjdump") is None or shutil.which("c++filt") is None:
+        pytest.skip("cuobjdump / c++filt not on PATH")
+    if _lib._needs_build():
+        _lib.build()
+    csrc = os.path.join(ROOT, "rnagan_b200", "csrc")
+    text = {f: open(os.path.join(csrc, f)).read() for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))}
+    kernels = set()
+    for t in text.values():
+        for head in re.findall(r"__global__([^;{]*)[;{]", t):
+            head = re.sub(r"__launch_bounds__\([^)]*\)", "", head)
+            m = re.search(r"([A-Za-z_0-9]+)\s*\(", head)
+            if m:
+                kernels.add(m.group(1))
+    launched = sorted({m for t in text.values() for m in re.findall(r"launch_pdl\(\s*([A-Za-z_0-9]+)", t)} & kernels)
+    assert "gemm_fwd_kernel" in launched and "ew_split_kernel" in launched and len(launched) >= 6
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)[1:]
+    mangled = [f.split("\n", 1)[0].strip() for f in funcs]
+    pretty = subprocess.run(["c++filt"] + mangled, capture_output=True, text=True, check=True).stdout.split("\n")
+    seen = set()
+    for name, body in zip(pretty, funcs):
+        for k in launched:
+            if re.search(r"\b" + k + r"\b", name.split("(")[0]):
+                seen.add(k)
+                assert "ACQBULK" in body, f"{name}: launched with the PDL attribute but has no griddepcontrol.wait"
+    assert seen == set(launched), f"PDL-launched kernels not found in the library: {set(launched) - seen}"
+    for k in launched:
+        defs = [m for t in text.values()
+                for m in re.finditer(r"__global__[^;{]*?\b" + k + r"\s*\([^{;]*\)\s*\{(.*?)griddep_wait\(\);", t, flags=re.S)]
+        assert defs, f"{k}: no griddep_wait() in its definition"
+        for m in defs:
+            before = m.group(1)
+            # nothing but declarations / the barrier+TMEM prologue may precede the wait: no global loads or stores
+            touches = r"\bld8\(|\bst8\(|__ldg|\[[^\]]*\]\s*=[^=]|tma_ld_\w*\(|tma_load_\w*\(|tma_store_\w*\(|tma_prefetch_4d\("
+            assert not re.search(touches, before), f"{k}: memory access before the wait"
+
+
 def test_size_queries_work_without_gpu():
     from rnagan_b200 import _lib
     lib = _lib.lib()
