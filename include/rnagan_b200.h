@@ -227,6 +227,11 @@ int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms
 int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, float beta2, float eps, int step,
                  int do_clamp, float clamp_lo, float clamp_hi, float grad_scale, rg_stream_t st);
 int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st);
+/* data-parallel gradient exchange (what DistributedDataParallel's all-reduce would do around the
+ * reference): out[i] = sum over r < nparts of src[r * stride + i], r ascending -- the reduction step of the peer-to-peer
+ * exchange, after every rank's copy of this rank's slice has been pulled into src by the copy engines.  Fixed order,
+ * so the result is identical on reruns and independent of arrival order.  n and stride in floats, multiples of 4. */
+int rg_slices_sum(const float* src, int nparts, size_t stride, size_t n, float* out, rg_stream_t st);
 /* data path: uint8 HWC tiles [B][S][S][C] as the patch LMDBs hold them -> fp32 NCHW in [-1, 1];
  * cv2 BGR->RGB (swap_rb), permute(2,0,1), ConvertImageDtype(float) and Normalize(0.5, 0.5) of src/read_data.py:341-343
  * and src/histopathology_gan.py:106-109 in one pass, bit-identical to those CPU transforms.  Moving uint8 instead of

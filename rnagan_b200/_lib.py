@@ -75,6 +75,7 @@ SIGNATURES = {
     "rg_adam_build_table": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i]),
     "rg_adam_step": (_i, [_vp, _i, _f, _f, _f, _f, _i, _i, _f, _f, _f, _vp]),
     "rg_clamp": (_i, [_vp, _sz, _f, _f, _vp]),
+    "rg_slices_sum": (_i, [_vp, _i, _sz, _sz, _vp, _vp]),
     "rg_tiles_u8_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rg_tiles_to_unit_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rg_upsample2x_reflectpad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

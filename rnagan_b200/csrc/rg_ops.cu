@@ -1029,6 +1029,30 @@ __global__ void clamp_kernel(float* p, size_t n, float lo, float hi) {
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     p[i] = fminf(fmaxf(p[i], lo), hi);
 }
+// out[i] = sum_{r < nparts} src[r * stride + i], r ascending (fixed order: every rank of a data-parallel job reduces a
+// slice with the same association, and a rerun reproduces it bit for bit).  float4 lanes, up to 8 parts in flight.
+__global__ void __launch_bounds__(256) slices_sum_kernel(const float* __restrict__ src, int nparts, size_t stride, size_t n4,
+                                                         float* __restrict__ out) {
+  const size_t step = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += step) {
+    float4 acc = reinterpret_cast<const float4*>(src)[i];
+    for (int r0 = 1; r0 < nparts; r0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (r0 + j < nparts) v[j] = reinterpret_cast<const float4*>(src + static_cast<size_t>(r0 + j) * stride)[i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (r0 + j < nparts) {
+          acc.x += v[j].x;
+          acc.y += v[j].y;
+          acc.z += v[j].z;
+          acc.w += v[j].w;
+        }
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+}
 __global__ void cast_f32_kernel(const float* __restrict__ src, float* __restrict__ dst32, __nv_bfloat16* dst16, size_t n) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -1656,6 +1680,17 @@ int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st) {
   const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 8));
   clamp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(p, n, lo, hi);
   RG_LAUNCH_CHECK("rg_clamp");
+  return 0;
+}
+
+int rg_slices_sum(const float* src, int nparts, size_t stride, size_t n, float* out, rg_stream_t st) {
+  RG_CHECK_ARG(src && out && nparts >= 1 && n > 0 && n % 4 == 0 && stride % 4 == 0 && stride >= n &&
+                   reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
+               "rg_slices_sum: need n and stride multiples of 4 floats, stride >= n, 16-byte aligned pointers");
+  const size_t n4 = n / 4;
+  const int grid = static_cast<int>(std::min<size_t>((n4 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  slices_sum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(src, nparts, stride, n4, out);
+  RG_LAUNCH_CHECK("rg_slices_sum");
   return 0;
 }
 

@@ -475,6 +475,13 @@ def clamp_(p, lo, hi):
     _lib.check(_lib.lib().rg_clamp(_p(p), p.numel(), float(lo), float(hi), _st()), "rg_clamp")
 
 
+def slices_sum(stage, nparts, n, out):
+    """out[:n] = sum_r stage[r, :n] in ascending r (stage: fp32 [nparts, stride] contiguous; n % 4 == 0)."""
+    _lib.check(_lib.lib().rg_slices_sum(_p(stage), int(nparts), int(stage.stride(0)), int(n), _p(out), _st()),
+               "rg_slices_sum")
+    return out
+
+
 class AdamTable:
     """Chunk table over a fixed list of (param, grad, exp_avg, exp_avg_sq) fp32 tensors for rg_adam_step."""
 

@@ -4,13 +4,14 @@ Training shards by batch: every rank runs the three steps
 BatchNorm / latent-standardisation / gradient-norm statistics (what wrapping the reference in DDP would do) and the
 parameter gradients are averaged before each optimiser step.  Tile synthesis needs no collective.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 
 def init_from_env(backend=None):
     """Initialise the default process group from RANK / WORLD_SIZE / MASTER_* (torchrun); returns (rank, world)."""
-    import os
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if world > 1 and not dist.is_initialized():
@@ -56,6 +57,108 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+# ------------------------------------------------------------------------------------------------ peer exchange
+# NCCL's all-reduce kernels need whole SMs for the ~1 ms they run, and a persistent tile-engine grid then executes the
+# CTAs they displaced as a second wave: the all-reduce is paid in full although it "overlaps".
+# PeerExchange moves the gradients with the COPY ENGINES instead: the flat gradient buffer lives in symmetric memory
+# (torch.distributed._symmetric_memory: every rank maps every peer's buffer over NVLink), and one all-reduce of a
+# bucket [lo, hi) is
+#     barrier | pull my slice of the bucket from every peer (DMA) | sum the world copies in rank order (one HBM-bound
+#     kernel, rg_slices_sum) | barrier | pull every peer's reduced slice (DMA) | barrier
+# on a side stream.  No SM is held while bytes move, the summation order is fixed (bit-reproducible, identical on all
+# ranks), and per GPU 2 (world-1)/world of the bucket crosses NVLink in each direction -- the same as a ring.
+def slice_bounds(n, world, align=4):
+    """Contiguous split of [0, n) into `world` slices with `align`-multiple lengths (trailing slices may be short or
+    empty); returns [(lo, hi)] per rank."""
+    per = ((n + align - 1) // align + world - 1) // world * align
+    return [(min(r * per, n), min((r + 1) * per, n)) for r in range(world)]
+
+
+def exchange_pull_reduce(rank, world, peers, stage, lo, n, copy, reduce):
+    """Phase 1 on `rank`: stage[r, :len] <- peer r's copy of this rank's slice of bucket [lo, lo+n), then
+    own[lo + slice] = sum_r stage[r] (ascending r).  `peers[r]` is rank r's flat buffer as seen from this rank."""
+    a, b = slice_bounds(n, world)[rank]
+    if b <= a:
+        return 0
+    for step in range(world):
+        r = (rank - step) % world                # start with the local copy, then walk the peers round-robin
+        copy(stage[r, :b - a], peers[r][lo + a:lo + b])
+    reduce(stage, world, b - a, peers[rank][lo + a:lo + b])
+    return b - a
+
+
+def exchange_gather(rank, world, peers, lo, n, copy):
+    """Phase 2 on `rank`: own[lo + slice_r] <- peer r's reduced slice, for every other rank r."""
+    own = peers[rank]
+    bounds = slice_bounds(n, world)
+    for step in range(1, world):
+        r = (rank - step) % world
+        a, b = bounds[r]
+        if b > a:
+            copy(own[lo + a:lo + b], peers[r][lo + a:lo + b])
+
+
+class _EventHandle:
+    def __init__(self, event, device):
+        self.event, self.device = event, device
+
+    def wait(self):
+        torch.cuda.current_stream(self.device).wait_event(self.event)
+
+
+class PeerExchange:
+    """SUM all-reduce of ranges of one flat fp32 buffer through peer-mapped memory and the copy engines (see above).
+    Opt-in (RG_DP_EXCHANGE=ce); every rank must issue the same sequence of `allreduce` calls."""
+
+    def __init__(self, numel, device, group=None):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("PeerExchange needs CUDA devices with peer access (there is no CPU path)")
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device, self.numel = device, int(numel)
+        self.flat = symm.empty(self.numel, dtype=torch.float32, device=device)
+        self.flat.zero_()
+        self.hdl = symm.rendezvous(self.flat, group)
+        self.peers = [self.flat if r == self.rank else self.hdl.get_buffer(r, (self.numel,), torch.float32, 0)
+                      for r in range(self.world)]
+        per = slice_bounds(self.numel, self.world)[0]
+        self.stage = torch.empty(self.world, max(per[1] - per[0], 4), dtype=torch.float32, device=device)
+        self.stream = torch.cuda.Stream(device=device)
+
+    @staticmethod
+    def _copy(dst, src):
+        dst.copy_(src, non_blocking=True)          # same dtype, contiguous: cudaMemcpyAsync -> copy engine
+
+    @staticmethod
+    def _reduce(stage, world, n, out):
+        from . import ops
+        ops.slices_sum(stage, world, n, out)
+
+    def allreduce(self, lo, hi):
+        """Asynchronous SUM over ranks of flat[lo:hi) (lo a multiple of 4 floats; hi is rounded up to one -- the
+        flat buffer is padded).  Returns a handle whose wait() orders the current stream after the exchange."""
+        hi = min((hi + 3) // 4 * 4, self.numel)
+        if lo % 4 != 0 or hi <= lo:
+            raise ValueError(f"PeerExchange.allreduce: bad range [{lo}, {hi})")
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.hdl.barrier(channel=0)            # every rank's bucket is final
+            exchange_pull_reduce(self.rank, self.world, self.peers, self.stage, lo, hi - lo, self._copy, self._reduce)
+            self.hdl.barrier(channel=0)            # every slice is reduced, nobody still reads un-reduced data
+            exchange_gather(self.rank, self.world, self.peers, lo, hi - lo, self._copy)
+            self.hdl.barrier(channel=0)            # nobody still reads this rank's slice: the buffer may be rewritten
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return _EventHandle(done, self.device)
+
+
+def exchange_mode():
+    """'nccl' (default) or 'ce' (RG_DP_EXCHANGE=ce: PeerExchange)."""
+    return os.environ.get("RG_DP_EXCHANGE", "nccl").lower()
+
+
 class GradSync:
     """Flat fp32 gradient buffer of one network (every ``p.grad`` is a view into it) + overlapped all-reduce.
 
@@ -73,7 +176,12 @@ class GradSync:
             offs[id(p)] = (off, p.numel())
             off += (p.numel() + 3) // 4 * 4            # keep every tensor 16-byte aligned for the vectorised Adam
         self.offs = offs
-        self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=params[0].device)
+        self.xchg = None
+        if self.world() > 1 and exchange_mode() == "ce" and params[0].device.type == "cuda":
+            self.xchg = PeerExchange(max(off, 4), params[0].device)
+            self.flat = self.xchg.flat
+        else:
+            self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=params[0].device)
         for p in params:
             o, n = offs[id(p)]
             p.grad = self._view(o, n, p)
@@ -98,6 +206,11 @@ class GradSync:
     def world():
         return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
 
+    def _reduce_range(self, lo, hi):
+        if self.xchg is not None:
+            return self.xchg.allreduce(lo, hi)
+        return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+
     def _owns(self, p):
         o, n = self.offs[id(p)]
         return p.grad is not None and p.grad.data_ptr() == self.flat.data_ptr() + 4 * o
@@ -114,7 +227,7 @@ class GradSync:
             # the slice may only cover tensors that are final: require the announced set to be contiguous
             covered = sum((self.offs[id(p)][1] + 3) // 4 * 4 for p in params)
             if covered >= hi - lo:
-                self._pending.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+                self._pending.append(self._reduce_range(lo, hi))
                 self._done.update(id(p) for p in params)
                 return
         for p in params:
@@ -136,7 +249,7 @@ class GradSync:
             if run:
                 lo = self.offs[id(run[0])][0]
                 hi = self.offs[id(run[-1])][0] + self.offs[id(run[-1])][1]
-                self._pending.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+                self._pending.append(self._reduce_range(lo, hi))
                 run = []
             if p is not None:
                 if self._owns(p):

@@ -20,3 +20,35 @@ def test_data_parallel_two_gpus(cuda_dev):
     sys.stdout.write(res.stdout[-3000:])
     sys.stderr.write(res.stderr[-3000:])
     assert res.returncode == 0
+
+
+# The copy-engine exchange (parallel.PeerExchange) was written after this round's GPU budget was spent: its GPU tests
+# are opt-in until they have been run once (RG_TEST_EXPERIMENTAL=1), so that the validated suite stays as measured.
+experimental = pytest.mark.skipif(os.environ.get("RG_TEST_EXPERIMENTAL", "0") != "1",
+                                  reason="unvalidated opt-in path: set RG_TEST_EXPERIMENTAL=1")
+
+
+@experimental
+def test_slices_sum_matches_ordered_sum(cuda_dev):
+    from rnagan_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    for world, n, stride in ((2, 4096, 4096), (8, 1000 * 4, 4100), (3, 4, 8), (8, 1 << 20, 1 << 20)):
+        stage = torch.randn(world, stride, generator=g).to(cuda_dev)
+        out = torch.full((n,), float("nan"), device=cuda_dev)
+        ops.slices_sum(stage, world, n, out)
+        want = stage[0, :n].clone()
+        for r in range(1, world):
+            want += stage[r, :n]
+        assert torch.equal(out, want)
+
+
+@experimental
+def test_data_parallel_two_gpus_peer_exchange(cuda_dev):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29578", os.path.join(ROOT, "tests", "dp_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, RG_DP_EXCHANGE="ce"))
+    sys.stdout.write(res.stdout[-3000:])
+    sys.stderr.write(res.stderr[-3000:])
+    assert res.returncode == 0

@@ -317,3 +317,42 @@ def test_rna_scaler_matches_reference_preprocessing():
         RNAScaler().transform(x)
     with pytest.raises(ValueError):
         mine.transform(x[:, :10])
+
+
+def test_peer_exchange_schedule_simulated():
+    """The copy-engine gradient exchange (parallel.PeerExchange, RG_DP_EXCHANGE=ce) as data movement only: W virtual
+    ranks share a list of flat buffers (what symmetric memory gives each rank), phase 1 (pull my slice from every peer,
+    sum in rank order) runs on every rank, then phase 2 (pull every peer's reduced slice).  Afterwards every rank holds
+    the SUM on the bucket -- bit-identical across ranks -- and nothing outside the bucket moved.  Ragged buckets, buckets
+    smaller than the world and world sizes 1..8."""
+    from rnagan_b200.parallel import exchange_gather, exchange_pull_reduce, slice_bounds
+
+    def copy(dst, src):
+        dst.copy_(src)
+
+    def reduce(stage, world, n, out):                   # stand-in for ops.slices_sum: ascending rank order
+        acc = stage[0, :n].clone()
+        for r in range(1, world):
+            acc += stage[r, :n]
+        out.copy_(acc)
+
+    g = torch.Generator().manual_seed(0)
+    for world in (1, 2, 3, 4, 8):
+        for numel, lo, n in ((4096, 0, 4096), (4096, 128, 1000), (4096, 4000, 96), (64, 8, 8), (64, 0, 4)):
+            b = slice_bounds(n, world)
+            assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+            assert all((hi - lo_) % 4 == 0 for lo_, hi in b[:-1]) and all(lo_ % 4 == 0 for lo_, hi in b if hi > lo_)
+            flats = [torch.randn(numel, generator=g) for _ in range(world)]
+            before = [f.clone() for f in flats]
+            want = torch.zeros(n)
+            for r in range(world):                      # the order rg_slices_sum uses
+                want = want + before[r][lo:lo + n] if r else before[r][lo:lo + n].clone()
+            per = max(b[0][1] - b[0][0], 4)
+            stages = [torch.full((world, per), float("nan")) for _ in range(world)]
+            for r in range(world):
+                exchange_pull_reduce(r, world, flats, stages[r], lo, n, copy, reduce)
+            for r in range(world):
+                exchange_gather(r, world, flats, lo, n, copy)
+            for r in range(world):
+                assert torch.equal(flats[r][lo:lo + n], want), (world, numel, lo, n, r)
+                assert torch.equal(flats[r][:lo], before[r][:lo]) and torch.equal(flats[r][lo + n:], before[r][lo + n:])
