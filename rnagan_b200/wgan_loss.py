@@ -174,8 +174,10 @@ class _VAEConditioned:
     def _real(real_inputs, device):
         dst, ev = _VAEConditioned._prefetch_real(real_inputs, device)
         if ev is not None:
-            torch.cuda.current_stream(device).wait_event(ev)
-        return dst
+            cur = torch.cuda.current_stream(device)
+            cur.wait_event(ev)
+            dst.record_stream(cur)     # allocated on the copy stream, read here: its block is not reused before this
+        return dst                     # stream is done with it (iterations are queued ahead of the host, Trainer.train)
 
 
 def _check_labels(labels, *nets):
