@@ -108,19 +108,25 @@ class DevicePrefetcher:
             ev.record(self.stream)
         return out, ev
 
+    def _hand_over(self, staged):
+        """Order the consumer's stream after the copies and tell the allocator who reads these blocks now."""
+        cur, ev = staged
+        stream = torch.cuda.current_stream(self.device)
+        stream.wait_event(ev)
+        for v in cur.values():
+            if torch.is_tensor(v) and v.device.type == "cuda":
+                v.record_stream(stream)
+        return cur
+
     def __iter__(self):
         nxt = None
         for batch in self.loader:
             staged = self._stage(batch)
             if nxt is not None:
-                cur, ev = nxt
-                torch.cuda.current_stream(self.device).wait_event(ev)
-                yield cur
+                yield self._hand_over(nxt)
             nxt = staged
         if nxt is not None:
-            cur, ev = nxt
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            yield cur
+            yield self._hand_over(nxt)
 
     def __len__(self):
         return len(self.loader)
