@@ -6,15 +6,18 @@
   * binds every loss object's ``train_ops`` parameters BY NAME to same-named trainer attributes;
   * ``train_iter`` runs the losses in list order (G loss, critic loss, gradient penalty; ncritic=1);
   * ``save_model`` / ``load_model`` use the torchgan checkpoint dictionary layout
-    (epoch, loss_information, loss_objects, metric_objects, loss_logs, metric_logs + one state_dict per model/optimizer).
+    (epoch, loss_information, loss_objects, metric_objects, loss_logs, metric_logs + one state_dict per model/optimizer);
+  * at the end of every epoch ``train`` checkpoints, switches the models to eval mode and writes the generator's sample
+    grid on a fixed ``test_noise`` to ``{recon}/epoch{N}_{model}.png`` (torchgan's end-of-epoch image log [tg]).
 
-Logging / visualisation (torchgan Logger, tensorboard, image grids) is out of scope.
+Console / tensorboard logging and metrics (torchgan Logger) are out of scope.
 """
 import inspect
 import os
 
 import torch
 
+from .image_grid import save_image_grid
 from .wgan_loss import DiscriminatorLoss, GeneratorLoss
 
 
@@ -41,6 +44,8 @@ class Trainer:
         self.retain_checkpoints = retain_checkpoints
         self.last_retained_checkpoint = 0
         self.recon = recon
+        self.nrow = nrow
+        self.test_noise = test_noise             # None: drawn once from each generator's sampler, then kept
         self.batch_size = None
         self.real_inputs = None
         self.labels = None
@@ -197,6 +202,24 @@ class Trainer:
                 self.train_iter(defer=True)
             self.flush()
             self.save_model(epoch)
+            for name in self.model_names:
+                getattr(self, name).eval()
+            self.sample_grids(epoch)
+
+    def sample_grids(self, epoch):
+        """Eval-mode sample grid of every generator-like model (one with a `sampler`) on the trainer's fixed test noise:
+        `{recon}/epoch{epoch+1}_{model}.png`, `nrow` tiles per row, min-max normalised.  Returns the written paths."""
+        if not self.recon:
+            return []
+        gens = [n for n in self.model_names if callable(getattr(getattr(self, n), "sampler", None))]
+        if self.test_noise is None:
+            self.test_noise = [getattr(self, n).sampler(self.sample_size, self.device) for n in gens]
+        paths = []
+        for n, noise in zip(gens, self.test_noise):
+            with torch.no_grad():
+                images = getattr(self, n)(*noise) if isinstance(noise, (list, tuple)) else getattr(self, n)(noise)
+            paths.append(save_image_grid(images, os.path.join(self.recon, f"epoch{epoch + 1}_{n}.png"), nrow=self.nrow))
+        return paths
 
     def __call__(self, data_loader, **kwargs):
         self.batch_size = getattr(data_loader, "batch_size", None)

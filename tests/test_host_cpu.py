@@ -356,3 +356,73 @@ def test_peer_exchange_schedule_simulated():
             for r in range(world):
                 assert torch.equal(flats[r][lo:lo + n], want), (world, numel, lo, n, r)
                 assert torch.equal(flats[r][:lo], before[r][:lo]) and torch.equal(flats[r][lo + n:], before[r][lo + n:])
+
+
+_GRID_SEEN = []
+
+
+class _GridTinyG(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.lin = torch.nn.Linear(4, 3 * 8 * 8)
+
+    def sampler(self, sample_size, device):
+        return [torch.randn(sample_size, 4, device=device)]
+
+    def forward(self, z):
+        _GRID_SEEN.append((self.training, z.clone()))
+        return torch.tanh(self.lin(z)).view(-1, 3, 8, 8)
+
+
+def _grid_losses():
+    """Picklable stand-in loss classes (save_model pickles the loss objects), created once at module level."""
+    from rnagan_b200 import wgan_loss
+    g = globals()
+    if "_GridFakeG" not in g:
+        class _GridFakeG(wgan_loss.GeneratorLoss):
+            def train_ops(self, generator, optimizer_generator):
+                return 1.0
+
+        class _GridFakeD(wgan_loss.DiscriminatorLoss):
+            def train_ops(self, discriminator, optimizer_discriminator):
+                return 2.0
+
+        for c in (_GridFakeG, _GridFakeD):
+            c.__qualname__ = c.__name__
+            g[c.__name__] = c
+    return g["_GridFakeG"], g["_GridFakeD"]
+
+
+def test_sample_grid_matches_torchvision_and_trainer_writes_it(tmp_path):
+    """image_grid (the per-epoch sample grid torchgan's Trainer writes to `recon` [tg]) reproduces
+    torchvision.utils.save_image(..., normalize=True) pixel for pixel, and Trainer.train writes
+    `{recon}/epoch{N}_{model}.png` from an eval-mode generator on a fixed test noise after the checkpoint."""
+    from rnagan_b200 import wgan_loss
+    from rnagan_b200.image_grid import save_image_grid
+    from rnagan_b200.trainer import Trainer
+    Image = pytest.importorskip("PIL.Image")
+    tv = pytest.importorskip("torchvision.utils")
+    g = torch.Generator().manual_seed(0)
+    for shape, nrow in (((64, 3, 32, 32), 8), ((10, 3, 16, 24), 8), ((5, 1, 8, 8), 3), ((1, 3, 4, 4), 8)):
+        x = torch.randn(shape, generator=g)
+        a, b = str(tmp_path / "a.png"), str(tmp_path / "b.png")
+        save_image_grid(x, a, nrow=nrow)
+        tv.save_image(x, b, nrow=nrow, normalize=True)
+        assert np.array_equal(np.array(Image.open(a)), np.array(Image.open(b))), shape
+
+    seen = _GRID_SEEN
+    seen.clear()
+    TinyG = _GridTinyG
+    FakeG, FakeD = _grid_losses()
+    net = {"generator": {"name": TinyG, "args": {}, "optimizer": {"name": torch.optim.Adam, "args": {"lr": 1e-3}}},
+           "discriminator": {"name": torch.nn.Linear, "args": {"in_features": 2, "out_features": 1},
+                             "optimizer": {"name": torch.optim.Adam, "args": {"lr": 1e-3}}}}
+    tr = Trainer(net, [FakeG(), FakeD()], device="cpu", epochs=2, sample_size=6, nrow=4,
+                 checkpoints=str(tmp_path / "ckpt" / "gan"), recon=str(tmp_path / "images"))
+    tr([{"image": torch.zeros(2, 3, 8, 8)}] * 3)
+    for e in (1, 2):
+        img = np.array(Image.open(tmp_path / "images" / f"epoch{e}_generator.png"))
+        assert img.shape == (2 * 10 + 2, 4 * 10 + 2, 3)              # 6 tiles, 4 per row, 2 px padding
+    assert os.path.exists(tmp_path / "ckpt" / "gan0.model") and os.path.exists(tmp_path / "ckpt" / "gan1.model")
+    assert len(seen) == 2 and not seen[0][0] and torch.equal(seen[0][1], seen[1][1])   # eval mode, same noise
+    assert tr.loss_logs["_GridFakeG"] == [1.0] * 6
