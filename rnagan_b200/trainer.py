@@ -17,6 +17,7 @@ import os
 
 import torch
 
+from . import compat
 from .image_grid import save_image_grid
 from .wgan_loss import DiscriminatorLoss, GeneratorLoss
 
@@ -181,7 +182,7 @@ class Trainer:
     def load_model(self, load_path="", load_items=None):
         if load_path == "":
             load_path = self.checkpoints + str(self.last_retained_checkpoint) + ".model"
-        ckpt = torch.load(load_path, map_location=self.device, weights_only=False)
+        ckpt = compat.load_checkpoint(load_path, map_location=self.device)   # also files the reference wrote
         self.start_epoch = ckpt["epoch"]
         self.loss_information = ckpt.get("loss_information", self.loss_information)
         self.loss_logs = ckpt.get("loss_logs", self.loss_logs)

@@ -112,6 +112,16 @@ class _VAEConditioned:
         self.betavae = _load_vae(checkpoint, rna_features, beta)
         self._ckpt_key = (str(checkpoint), int(rna_features))
 
+    def __setstate__(self, state):
+        """Instances pickled by the reference (inside a torchgan checkpoint's `loss_objects`, see compat.py) carry
+        `betavae`, `reduction`, `override_train_ops`, `arg_map` but none of this package's bookkeeping."""
+        super().__setstate__(state)
+        if "_ckpt_key" not in self.__dict__:
+            self._ckpt_key = ("unpickled", id(self))
+        vae = self._modules.get("betavae")
+        if vae is not None:
+            vae.eval()
+
     def _encoder(self, device):
         """All three loss objects load the SAME checkpoint (src/histopathology_gan.py:275-277): share one device copy."""
         key = self._ckpt_key + (str(device),)

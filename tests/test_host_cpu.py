@@ -426,3 +426,53 @@ def test_sample_grid_matches_torchvision_and_trainer_writes_it(tmp_path):
     assert os.path.exists(tmp_path / "ckpt" / "gan0.model") and os.path.exists(tmp_path / "ckpt" / "gan1.model")
     assert len(seen) == 2 and not seen[0][0] and torch.equal(seen[0][1], seen[1][1])   # eval mode, same noise
     assert tr.loss_logs["_GridFakeG"] == [1.0] * 6
+
+
+def test_reference_written_checkpoint_loads(tmp_path):
+    """a `{dir}{k}.model` in torchgan's save_model layout whose `loss_objects` are instances of the
+    REFERENCE's classes pickled under its top-level module names (`wgan_loss`, `betaVAE`; fixture written by
+    oracle/make_upstream_ckpt.py from the reference's own modules) loads through compat.load_checkpoint / Trainer.load_model
+    without the reference on the path: classes resolve to this package's, the instance state survives, the state_dicts
+    load strictly into this package's modules and into torch.optim.Adam."""
+    from rnagan_b200 import betaVAE as bv
+    from rnagan_b200 import compat, dcgan, wgan_loss
+    from rnagan_b200.trainer import Trainer
+    path = os.path.join(ROOT, "tests", "golden", "upstream_style_ckpt.model")
+    with pytest.raises(Exception):                 # plain torch.load cannot resolve the reference's module names
+        import importlib
+        if importlib.util.find_spec("wgan_loss") is not None:
+            raise ModuleNotFoundError("reference importable here: the negative check does not apply")
+        torch.load(path, weights_only=False)
+    ck = compat.load_checkpoint(path, map_location="cpu")
+    exp = ck["_expected"]
+    assert set(exp["loss_classes"].values()) == {"wgan_loss.WassersteinGeneratorLossVAE",
+                                                 "wgan_loss.WassersteinDiscriminatorLossVAE",
+                                                 "wgan_loss.WassersteinGradientPenaltyVAE"}
+    assert list(ck["loss_objects"]) == list(exp["loss_classes"])
+    for name, obj in ck["loss_objects"].items():
+        assert type(obj) is getattr(wgan_loss, name)
+        assert type(obj.betavae) is bv.betaVAE and type(obj.betavae.encoder) is bv.RNAEncoder
+        assert not obj.betavae.training and obj._ckpt_key[0] == "unpickled"
+        got = float(sum(p.double().sum() for p in obj.betavae.state_dict().values()))
+        assert abs(got - exp["vae_param_sum"]) <= 1e-9 * max(1.0, abs(exp["vae_param_sum"]))
+    g0 = ck["loss_objects"]["WassersteinGeneratorLossVAE"]
+    assert g0.reduction == exp["reduction_attr"] and g0.override_train_ops == exp["override_attr"] == exp["dims"]["feats"]
+    d = exp["dims"]
+    net = {
+        "generator": {"name": dcgan.DCGANGenerator,
+                      "args": {"encoding_dims": d["z"], "out_channels": 3, "step_channels": d["step"], "out_size": d["size"]},
+                      "optimizer": {"name": torch.optim.Adam, "args": {"lr": 1e-4, "betas": (0.5, 0.999)}}},
+        "discriminator": {"name": dcgan.DCGANDiscriminator,
+                          "args": {"in_size": d["size"], "in_channels": 3, "step_channels": d["step"]},
+                          "optimizer": {"name": torch.optim.Adam, "args": {"lr": 4e-4, "betas": (0.5, 0.999)}}},
+    }
+    tr = Trainer(net, list(ck["loss_objects"].values()), device="cpu", checkpoints=str(tmp_path / "gan"))
+    tr.load_model(load_path=path)
+    assert tr.start_epoch == 1 and tr.loss_information["generator_iters"] == 1
+    got = float(sum(p.double().sum() for p in tr.generator.state_dict().values()))
+    assert abs(got - exp["generator_param_sum"]) <= 1e-9 * max(1.0, abs(exp["generator_param_sum"]))
+    st = tr.optimizer_generator.state_dict()["state"]
+    assert len(st) == len(list(tr.generator.parameters())) and all(float(s["step"]) == 1.0 for s in st.values())
+    # and the round trip: what this package writes, it reads (loss objects included)
+    again = compat.load_checkpoint(tr.save_model(0), map_location="cpu")
+    assert type(again["loss_objects"]["WassersteinGradientPenaltyVAE"]) is wgan_loss.WassersteinGradientPenaltyVAE
