@@ -202,10 +202,18 @@ class Trainer:
                     self.batch_size = data["image"].size(0)
                 self.train_iter(defer=True)
             self.flush()
-            self.save_model(epoch)
+            main = self._is_main_process()       # data-parallel runs: replicas are identical, rank 0 writes the files
+            if main:
+                self.save_model(epoch)
             for name in self.model_names:
                 getattr(self, name).eval()
-            self.sample_grids(epoch)
+            if main:
+                self.sample_grids(epoch)
+
+    @staticmethod
+    def _is_main_process():
+        import torch.distributed as dist
+        return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
 
     def sample_grids(self, epoch):
         """Eval-mode sample grid of every generator-like model (one with a `sampler`) on the trainer's fixed test noise:
