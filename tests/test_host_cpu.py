@@ -476,3 +476,34 @@ def test_reference_written_checkpoint_loads(tmp_path):
     # and the round trip: what this package writes, it reads (loss objects included)
     again = compat.load_checkpoint(tr.save_model(0), map_location="cpu")
     assert type(again["loss_objects"]["WassersteinGradientPenaltyVAE"]) is wgan_loss.WassersteinGradientPenaltyVAE
+
+
+def test_partition_properties_hypothesis():
+    """Property tests of the two partitioners the multi-GPU paths rest on: parallel.shard_range (tile synthesis, whole
+    units) and parallel.slice_bounds (gradient exchange, 4-float aligned slices)."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    from rnagan_b200.parallel import shard_range, slice_bounds
+
+    @hyp.settings(max_examples=300, deadline=None)
+    @hyp.given(st.integers(0, 10 ** 7), st.integers(1, 64))
+    def shards(n, world):
+        spans = [shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+    @hyp.settings(max_examples=300, deadline=None)
+    @hyp.given(st.integers(1, 10 ** 7).map(lambda k: 4 * k), st.integers(1, 64))
+    def slices(n, world):
+        b = slice_bounds(n, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+        assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        lens = [hi - lo for lo, hi in b]
+        assert all(v % 4 == 0 for v in lens) and all(lo % 4 == 0 for lo, hi in b)
+        assert max(lens) == lens[0] and max(lens) - 4 * ((n // 4 + world - 1) // world) == 0
+        assert lens == sorted(lens, reverse=True)            # full slices first, then one short one, then empties
+
+    shards()
+    slices()
