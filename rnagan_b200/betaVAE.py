@@ -48,6 +48,11 @@ class betaVAE(nn.Module):
         self.z_dim = z_dim
 
     # -- engine plumbing ---------------------------------------------------------------------------------------
+    def __getstate__(self):
+        """Pickling (torchgan checkpoints hold the loss objects and, through them, this module) and deepcopy carry the
+        parameters and buffers only: the engines (`_rg_*`: device workspaces, bf16 operand copies) are rebuilt lazily."""
+        return {k: v for k, v in self.__dict__.items() if not k.startswith("_rg_")}
+
     def _engine(self):
         p0 = next(self.parameters())
         if p0.device.type != "cuda":

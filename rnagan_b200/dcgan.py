@@ -79,6 +79,10 @@ class _EngineMixin:
 
     _engine_cls = None
 
+    def __getstate__(self):
+        """pickle / deepcopy carry parameters and buffers only; the engine (`_rg_*`) is rebuilt lazily."""
+        return {k: v for k, v in self.__dict__.items() if not k.startswith("_rg_")}
+
     def _engine(self):
         eng = self.__dict__.get("_rg_engine")
         p0 = next(self.parameters())
