@@ -177,9 +177,15 @@ class GradSync:
             off += (p.numel() + 3) // 4 * 4            # keep every tensor 16-byte aligned for the vectorised Adam
         self.offs = offs
         self.xchg = None
+        # announced layers are merged into buckets of at least this many floats before they are exchanged (0: every
+        # announcement is reduced at once, the NCCL default).  The peer exchange costs three barriers and 2(world-1)
+        # copies per bucket whatever its size, and most layers are tiny: RG_DP_BUCKET_MB (default 16) in that mode.
+        self.bucket_floats = 0
+        self._open = None
         if self.world() > 1 and exchange_mode() == "ce" and params[0].device.type == "cuda":
             self.xchg = PeerExchange(max(off, 4), params[0].device)
             self.flat = self.xchg.flat
+            self.bucket_floats = int(float(os.environ.get("RG_DP_BUCKET_MB", "16")) * (1 << 20)) // 4
         else:
             self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=params[0].device)
         for p in params:
@@ -211,6 +217,28 @@ class GradSync:
             return self.xchg.allreduce(lo, hi)
         return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
 
+    def _flush_open(self):
+        if self._open is not None:
+            self._pending.append(self._reduce_range(*self._open))
+            self._open = None
+
+    def _submit(self, lo, hi):
+        """Reduce flat[lo:hi) now, or merge it into the open bucket when bucketing is on (adjacent ranges only: the
+        engines announce layers in backward order, i.e. in descending offsets)."""
+        if self.bucket_floats <= 0:
+            self._pending.append(self._reduce_range(lo, hi))
+            return
+        r4 = lambda v: (v + 3) // 4 * 4  # noqa: E731   (tensor offsets are padded to 4 floats)
+        if self._open is not None and r4(hi) == self._open[0]:
+            self._open[0] = lo
+        elif self._open is not None and r4(self._open[1]) == lo:
+            self._open[1] = hi
+        else:
+            self._flush_open()
+            self._open = [lo, hi]
+        if self._open[1] - self._open[0] >= self.bucket_floats:
+            self._flush_open()
+
     def _owns(self, p):
         o, n = self.offs[id(p)]
         return p.grad is not None and p.grad.data_ptr() == self.flat.data_ptr() + 4 * o
@@ -227,7 +255,7 @@ class GradSync:
             # the slice may only cover tensors that are final: require the announced set to be contiguous
             covered = sum((self.offs[id(p)][1] + 3) // 4 * 4 for p in params)
             if covered >= hi - lo:
-                self._pending.append(self._reduce_range(lo, hi))
+                self._submit(lo, hi)
                 self._done.update(id(p) for p in params)
                 return
         for p in params:
@@ -238,6 +266,7 @@ class GradSync:
         w = self.world()
         if w == 1:
             return 1.0
+        self._flush_open()
         rest = [p for p in self.params if id(p) not in self._done and p.grad is not None]
         # merge contiguous leftovers into as few collectives as possible
         run = []

@@ -507,3 +507,59 @@ def test_partition_properties_hypothesis():
 
     shards()
     slices()
+
+
+def test_gradsync_bucketing_merges_adjacent_layers():
+    """GradSync with bucketing on (the copy-engine exchange mode): layers announced in backward order are merged into
+    contiguous buckets of at least `bucket_floats`, every float of every gradient is reduced exactly once per step, and
+    nothing is reduced before its layer was announced.  The reductions are recorded instead of executed."""
+    from rnagan_b200.parallel import GradSync
+
+    class Rec(GradSync):
+        world = staticmethod(lambda: 2)
+
+        def _reduce_range(self, lo, hi):
+            self.calls.append((lo, hi))
+
+            class H:
+                def wait(self_inner):
+                    return None
+            return H()
+
+    sizes = [3, 130, 520, 2100, 8400, 33500, 31]             # layer sizes in the critic's proportions, first -> last
+    net = torch.nn.ModuleList([torch.nn.Linear(n, 1, bias=False) for n in sizes])
+    gs = Rec(net)
+    gs.calls = []
+    gs.bucket_floats = 4000
+    params = list(net.parameters())
+    for p in reversed(params):                                # backward order: last layer first
+        gs.layer_done(p)
+    assert gs.finish() == 0.5
+    total = gs.flat.numel()
+    covered = torch.zeros(total, dtype=torch.int32)
+    for lo, hi in gs.calls:
+        covered[lo:hi] += 1
+    for p in params:
+        o, n = gs.offs[id(p)]
+        assert bool((covered[o:o + n] == 1).all())
+    assert int(covered.max()) == 1
+    # [31 + 33500] reaches the threshold, 8400 alone does, the four small layers leave together at finish()
+    assert [hi - lo >= 4000 for lo, hi in gs.calls] == [True, True, False] and len(gs.calls) == 3
+    # second step, announcements out of order: non-adjacent ranges are not merged, still exactly-once coverage
+    gs.calls = []
+    for i in (6, 0, 5, 2, 1, 4, 3):
+        gs.layer_done(params[i])
+    gs.finish()
+    covered.zero_()
+    for lo, hi in gs.calls:
+        covered[lo:hi] += 1
+    for p in params:
+        o, n = gs.offs[id(p)]
+        assert bool((covered[o:o + n] == 1).all())
+    assert int(covered.max()) == 1
+    # bucketing off (the NCCL default): one reduction per announcement
+    gs.calls, gs.bucket_floats = [], 0
+    for p in reversed(params):
+        gs.layer_done(p)
+    gs.finish()
+    assert len(gs.calls) == len(params)
