@@ -1,0 +1,33 @@
+"""Worker for the gated B-resident test (tests/test_engine_gpu.py): runs rg_conv_down at the given shapes in a fresh
+process (RG_BRES is read once per process) and saves outputs + fused statistics + the B-resident launch count."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rnagan_b200 import _lib, ops  # noqa: E402
+
+
+def main(out_path):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    res = {}
+    # (B, H_hi, Cs, Cp): the lung L1 shape at a reduced batch, an odd number of M tiles for a CTA pair, and tiny cases
+    for i, (B, H2, Cs, Cp) in enumerate(((8, 128, 64, 128), (3, 48, 64, 128), (2, 16, 64, 64), (1, 8, 128, 64))):
+        hi = torch.randn(B, H2, H2, Cs, generator=g).to(dev).bfloat16()
+        W = (torch.randn(Cp, Cs, 4, 4, generator=g) * 0.05).to(dev)
+        w_down, _ = ops.pack_link(W, want_up=False)
+        ws = ops.stats_ws(Cp, dev, slot=i)
+        for rep in range(2):                      # twice: the second launch of a process reuses nothing stale
+            lo = ops.conv_down(hi, w_down, stats=ws)
+        torch.cuda.synchronize()
+        res[f"lo{i}"] = lo.float().cpu()
+        res[f"ws{i}"] = ws.float().cpu().clone()
+    res["bres_launches"] = int(_lib.lib().rg_bres_launch_count())
+    torch.save(res, out_path)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
