@@ -323,9 +323,20 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
         const uint32_t bar = smem_u32(&s.auxbar[0]);
         const uint32_t bar_tx = CG > 1 ? (bar & kPeerBitMask) : bar;
         if (crank == 0) mbar_expect_tx_raw(bar, static_cast<uint32_t>(p.bres_bytes) * CG);
-        const int brow0 = crank * bn_cta;                       // n_tiles == 1 and num_phases == 1
-        for (int kb = 0; kb < num_kb; ++kb)
-          tma_ld_2d_raw<CG>(desc_b, bar_tx, bres0 + kb * p.b_stage_bytes, kb * kBlockK, brow0);
+        if (merged) {
+          // merged phases: k-block (tap, chunk) holds mg_nph[tap] slabs of mg_rows rows, packed back to back
+          uint32_t off = 0;
+          for (int tap = 0; tap < num_taps; ++tap) {
+            const int mg_n = p.mg_nph[tap];
+            const uint64_t d9 = mg_n == 4 ? desc_b : desc_a0 + static_cast<uint64_t>(mg_n == 2 ? 1 : (mg_n == 1 ? 2 : 3)) * sizeof(CUtensorMap);
+            for (int chunk = 0; chunk < chunks; ++chunk, off += static_cast<uint32_t>(mg_n * mg_rows) * 128u)
+              tma_ld_2d_raw<CG>(d9, bar_tx, bres0 + off, 0, ((tap * chunks + chunk) * CG + crank) * (4 * mg_rows));
+          }
+        } else {
+          const int brow0 = crank * bn_cta;                     // n_tiles == 1 and num_phases == 1
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma_ld_2d_raw<CG>(desc_b, bar_tx, bres0 + kb * p.b_stage_bytes, kb * kBlockK, brow0);
+        }
       }
       for (int tile = (BRES && warp == 6) ? total_tiles : tile0; tile < total_tiles; tile += tile_step) {
         const int ph = tile % num_phases;
@@ -353,8 +364,8 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
             const uint32_t sb = sa + kAStageBytes;
             const uint32_t fb = full0_tx + stage * 8;
             if (warp == 0 && crank == 0)
-              mbar_expect_tx_raw(full0 + stage * 8, merged ? (a_tx + static_cast<uint32_t>(mg_n * mg_rows) * 128u) * CG
-                                                           : stage_tx);
+              mbar_expect_tx_raw(full0 + stage * 8,
+                                 (merged && !BRES) ? (a_tx + static_cast<uint32_t>(mg_n * mg_rows) * 128u) * CG : stage_tx);
             if (do_a) {
               if (a_2d) tma_ld_2d_raw<CG>(desc_a0, fb, sa, chunk * kBlockK, b0);
               else tma_ld_4d_raw<CG>(desc_a, fb, sa, chunk * kBlockK, cj, ci, b0);
@@ -415,6 +426,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
         if (p.merged) {
           // 9 shifts x chunks stages; one MMA per k-step covers every phase slab the shift feeds (N = 64..256).
           // The centre shift comes first and feeds all four phases: its first MMA initialises the whole accumulator.
+          uint32_t boff = 0;                                   // BRES: running offset into the resident B block
           for (int tap = 0; tap < p.num_taps; ++tap) {
             const int nsl = p.mg_nph[tap];
             const uint32_t idesc_n = make_idesc_bf16(kBlockM * CG, 64 * nsl, 0, 0);
@@ -426,7 +438,9 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
               tc_fence_after();
               const uint32_t sa = ring0 + stage * stage_bytes;
               const uint64_t da = da0 | static_cast<uint64_t>((sa >> 4) & 0x3FFF);
-              const uint64_t db = db0 | static_cast<uint64_t>(((sa + kAStageBytes) >> 4) & 0x3FFF);
+              const uint32_t sbk = BRES ? bres0 + boff : sa + kAStageBytes;
+              if (BRES) boff += static_cast<uint32_t>(nsl * mg_rows) * 128u;
+              const uint64_t db = db0 | static_cast<uint64_t>((sbk >> 4) & 0x3FFF);
               if (!skip_mma) {
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k)

@@ -260,13 +260,24 @@ static int launch_fwd(GemmMaps& maps, FwdArgs& a, int out_kind, int cg, float* s
   static const bool allow_bres = env_flag("RG_BRES", false);
   bool bres = false;
   a.bres_bytes = 0;
-  if (allow_bres && out_kind == OUT_BF16_NHWC && a.tma_store && !a.merged && !a.b_mn && a.num_phases == 1 &&
-      a.n_tiles == 1 && a.aux_mode == 0 && a.whatif == 0 && a.prof == nullptr) {
-    const int bres_bytes = a.num_taps * a.chunks * a.b_stage_bytes;
-    const int ns_a = (avail - a.nbuf * kStagingBytes - bres_bytes) / kAStageBytes;
+  static const int bres_level = [] { const char* e = getenv("RG_BRES"); return e ? atoi(e) : 0; }();
+  if (allow_bres && out_kind == OUT_BF16_NHWC && a.tma_store && !a.b_mn && a.num_phases == 1 && a.n_tiles == 1 &&
+      a.aux_mode == 0 && a.whatif == 0 && a.prof == nullptr && (!a.merged || (bres_level >= 2 && cg == 2))) {
+    int bres_bytes = a.num_taps * a.chunks * a.b_stage_bytes;
+    if (a.merged) {                       // RG_BRES=2: also the merged-phase transposed form (variable slabs per shift)
+      bres_bytes = 0;
+      for (int t = 0; t < a.num_taps; ++t) bres_bytes += a.chunks * a.mg_nph[t] * (64 / cg) * 128;
+    }
+    int nbuf = a.nbuf;
+    int ns_a = (avail - nbuf * kStagingBytes - bres_bytes) / kAStageBytes;
+    if (ns_a < 3 && nbuf == 2) {          // one staging slab instead of two buys the third A stage
+      nbuf = 1;
+      ns_a = (avail - kStagingBytes - bres_bytes) / kAStageBytes;
+    }
     if (bres_bytes > 0 && ns_a >= 3) {
       bres = true;
       a.bres_bytes = bres_bytes;
+      a.nbuf = nbuf;
       a.nstages = std::min(ns_a, kMaxStages);
       smem = static_cast<size_t>(a.nstages) * kAStageBytes + bres_bytes + a.nbuf * kStagingBytes + kSmemFixedBytes;
     }

@@ -25,6 +25,19 @@ def main(out_path):
         torch.cuda.synchronize()
         res[f"lo{i}"] = lo.float().cpu()
         res[f"ws{i}"] = ws.float().cpu().clone()
+    res["bres_down"] = int(_lib.lib().rg_bres_launch_count())
+    # merged-phase transposed convolution (Cs == 64, CTA pairs): resident only with RG_BRES=2
+    for i, (B, H, Cp) in enumerate(((8, 64, 128), (3, 24, 128), (2, 16, 64))):
+        lo = torch.randn(B, H, H, Cp, generator=g).to(dev).bfloat16()
+        W = (torch.randn(Cp, 64, 4, 4, generator=g) * 0.05).to(dev)
+        w_down, _ = ops.pack_link(W, want_up=False)
+        w9 = ops.pack_up9_from_down(w_down, 64)
+        ws = ops.stats_ws(64, dev, slot=8 + i)
+        for rep in range(2):
+            hi = ops.conv_up(lo, w9, 64, stats=ws)
+        torch.cuda.synchronize()
+        res[f"hi{i}"] = hi.float().cpu()
+        res[f"wsu{i}"] = ws.float().cpu().clone()
     res["bres_launches"] = int(_lib.lib().rg_bres_launch_count())
     torch.save(res, out_path)
 

@@ -463,13 +463,16 @@ def test_b_resident_plan_is_bit_identical(cuda_dev, tmp_path):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for flag in ("0", "1"):
+    for flag in ("0", "1", "2"):                 # 1: strided form only; 2: also the merged-phase transposed form
         path = str(tmp_path / f"bres{flag}.pt")
         res = subprocess.run([sys.executable, os.path.join(root, "tests", "bres_worker.py"), path],
                              env=dict(os.environ, RG_BRES=flag), capture_output=True, text=True, timeout=300)
         assert res.returncode == 0, res.stderr[-2000:]
         outs[flag] = torch.load(path)
-    assert outs["0"]["bres_launches"] == 0 and outs["1"]["bres_launches"] >= 6
-    for k, v in outs["0"].items():
-        if k != "bres_launches":
-            assert torch.equal(v, outs["1"][k]), k
+    assert outs["0"]["bres_launches"] == 0
+    assert outs["1"]["bres_down"] >= 6 and outs["1"]["bres_launches"] == outs["1"]["bres_down"]
+    assert outs["2"]["bres_down"] >= 6 and outs["2"]["bres_launches"] >= outs["2"]["bres_down"] + 4
+    for flag in ("1", "2"):
+        for k, v in outs["0"].items():
+            if not k.startswith("bres_"):
+                assert torch.equal(v, outs[flag][k]), (flag, k)
