@@ -1,8 +1,9 @@
 #!/bin/bash
 # First GPU call for the B-resident tile-engine plan (RG_BRES=1), one GPU:
 #   gpurun --timeout 420 -- 'bash tools/bres_ab.sh'
-# 1. the gated bit-identity test, 2. the conv micro-benchmarks with and without the plan (RG_BRES=1: strided L1; 2: also merged L1;
-# qualifies at the lung shapes), 3. A/B of the whole step.  Every leg under its own timeout: a barrier bug would hang.
+# 1. the gated bit-identity test, 2. the conv micro-benchmarks with and without the plan (RG_BRES=1: the strided L1
+# layer; RG_BRES=2: also the merged-phase transposed L1 layer -- the only ones that qualify at the lung shapes),
+# 3. A/B of the whole step.  Every leg runs under its own timeout: a barrier bug would hang.
 mkdir -p gpurun_out
 echo "== gated test"
 RG_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_engine_gpu.py -x -q -m gpu -k b_resident 2>&1 | tail -5
