@@ -563,3 +563,28 @@ def test_gradsync_bucketing_merges_adjacent_layers():
         gs.layer_done(p)
     gs.finish()
     assert len(gs.calls) == len(params)
+
+
+def test_frechet_distance_matches_reference_formula():
+    """fid.frechet_distance (symmetric eigen formulation) vs the reference's formula evaluated with scipy's general
+    matrix square root (src/fid.py:147-163), on full-rank, rank-deficient (N < D) and identical feature sets; and
+    activation_statistics vs np.mean / np.cov(rowvar=False) (src/fid.py:110-111)."""
+    linalg = pytest.importorskip("scipy.linalg")
+    from rnagan_b200.fid import activation_statistics, fid_from_features, frechet_distance
+    rng = np.random.default_rng(0)
+    for n1, n2, d in ((500, 400, 32), (40, 50, 64), (300, 300, 8)):
+        a = rng.normal(size=(n1, d)) @ rng.normal(size=(d, d)) * 0.3 + rng.normal(size=d)
+        b = rng.normal(size=(n2, d)) @ rng.normal(size=(d, d)) * 0.3
+        mu1, s1 = activation_statistics(a)
+        mu2, s2 = activation_statistics(b)
+        assert np.allclose(mu1, a.mean(0)) and np.allclose(s1, np.cov(a, rowvar=False))
+        covmean = linalg.sqrtm(s1.dot(s2))
+        covmean = covmean.real if np.iscomplexobj(covmean) else covmean
+        ref = (mu1 - mu2).dot(mu1 - mu2) + np.trace(s1) + np.trace(s2) - 2 * np.trace(covmean)
+        got = frechet_distance(mu1, s1, mu2, s2)
+        assert abs(got - ref) <= 1e-6 * max(1.0, abs(ref)), (n1, n2, d, got, ref)
+        assert abs(fid_from_features(b, a) - got) <= 1e-9 * max(1.0, abs(got))
+    same = frechet_distance(mu1, s1, mu1, s1)
+    assert abs(same) <= 1e-8 * np.trace(s1)
+    with pytest.raises(ValueError):
+        frechet_distance(mu1, s1, mu2[:-1], s2)
