@@ -42,8 +42,6 @@ const char* rg_last_error(void);
 int rg_check_device(void);
 /* number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches) */
 long long rg_launch_count(void);
-/* diagnostics: tile-engine launches that ran the B-resident plan (opt-in RG_BRES=1) */
-long long rg_bres_launch_count(void);
 /* profiling aid (tools/gemm_prof.py): when non-NULL, forward tile-engine launches write per-CTA clock64 totals of
  * their producer / MMA / epilogue roles into buf[grid][12]; NULL (the default) disables it. */
 void rg_debug_set_prof(long long* buf);

@@ -31,6 +31,8 @@ CONFIGS = {
     # name: (image size, batch, rna_features, iterations)
     "mini32": (32, 8, 256, 2),
     "mini64": (64, 4, 192, 1),
+    # BASELINE config-2 shapes (gan_run_lung.json: 256x256 tiles, 19198 protein-coding genes), one iteration
+    "full256": (256, 8, 19198, 1),
 }
 SEED_G, SEED_D, SEED_V, SEED_BATCH, SEED_RUN = 11, 12, 13, 14, 99
 
@@ -117,6 +119,8 @@ def run_config(name, size, batch, feats, iters):
     # generate_images hard-codes view(-1, 3, 256, 256) (src/gan_utils.py:224): pick sample sizes whose element
     # count is a multiple of 3*256*256 and store values in flat NCHW order, which is independent of that view.
     n_syn = (3 * 256 * 256) // (3 * size * size)
+    if size == 256:
+        n_syn = 12            # one full chunk of 10 + a ragged chunk of 2 (a single sample would make std() NaN)
     profile = batch_data["rna_data"][:1]
     tiles = gen_images(tr, gene_exp=profile, sample_size=n_syn, betavae=vae)
     flat = np.ascontiguousarray(tiles.transpose(0, 3, 1, 2)).astype(np.float64).reshape(-1)
@@ -182,6 +186,9 @@ def run_modules():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
+    only = sys.argv[1:]
     for cfg_name, cfg in CONFIGS.items():
-        run_config(cfg_name, *cfg)
-    run_modules()
+        if not only or cfg_name in only:
+            run_config(cfg_name, *cfg)
+    if not only or "modules" in only:
+        run_modules()

@@ -22,7 +22,6 @@ SIGNATURES = {
     "rg_last_error": (_c.c_char_p, []),
     "rg_check_device": (_i, []),
     "rg_launch_count": (_c.c_longlong, []),
-    "rg_bres_launch_count": (_c.c_longlong, []),
     "rg_debug_set_prof": (None, [_vp]),
     "rg_pack_link": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "rg_pack_proj": (_i, [_vp, _vp, _i, _i, _vp]),

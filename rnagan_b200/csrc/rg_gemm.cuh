@@ -111,7 +111,6 @@ struct FwdArgs {
   int sy, sx;               // output pixel = (i*sy + oy[phase], j*sx + ox[phase])
   int n_valid;              // columns >= n_valid are not stored
   int8_t oy[4], ox[4];
-  int bres_bytes;           // BRES instantiation: bytes of this CTA's B share over ALL k-blocks, resident behind the A ring
 };
 
 struct WgradArgs {
@@ -256,16 +255,12 @@ __device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(_
 // across the four output phases of the transposed form (L2 hits) and a persistent CTA keeps its N tile for long runs
 // (statistics accumulate in registers and reach memory only when the N tile changes).
 // AUX: compile the fused elementwise-backward epilogue (rg_epilogue_aux) in; the plain instantiation carries none of it
-// BRES ("B resident", opt-in RG_BRES=1, single N tile / single phase / K-major B): the CTA's share of the weight for ALL
-// k-blocks is loaded once behind the A ring and stays for the CTA's life; the ring then streams A tiles only.  For the
-// narrow strided layer (N = 128, K = 1024: 128 KiB per CTA of a pair) this takes the per-k-block L2->SM traffic from
-// 24 KiB to 16 KiB, i.e. from transfer-bound (545 clk at ~44 B/clk/SM) to MMA-issue-bound (376 clk).
-template <int OUT, int CG, bool AUX = false, bool BRES = false>
+template <int OUT, int CG, bool AUX = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ FwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  const int stage_bytes = BRES ? kAStageBytes : kAStageBytes + p.b_stage_bytes;
-  const PipeSmem s = carve_smem(smem_raw, p.nstages * stage_bytes + (BRES ? p.bres_bytes : 0), p.nbuf * kStagingBytes,
+  const int stage_bytes = kAStageBytes + p.b_stage_bytes;
+  const PipeSmem s = carve_smem(smem_raw, p.nstages * stage_bytes, p.nbuf * kStagingBytes,
                                 p.naux * kStagingBytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -287,7 +282,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
   // bytes landing per stage on the (leader's) full barrier: A box + this CTA's share of B, from every CTA of the group
   const uint32_t stage_tx = (((p.whatif & 4) ? 0u : static_cast<uint32_t>(p.rows_valid) * 128u) +
-                             ((BRES || (p.whatif & 8)) ? 0u : static_cast<uint32_t>(p.b_stage_bytes))) * CG;
+                             ((p.whatif & 8) ? 0u : static_cast<uint32_t>(p.b_stage_bytes))) * CG;
   const int bn_cta = p.block_n / CG;                // B rows (N columns) this CTA fetches
   const int mg_rows = 64 / CG;                      // merged: rows of one phase's B slab held by this CTA
 
@@ -316,29 +311,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
       uint32_t phase = 0;
       long long t_wait = 0, t_issue = 0;
       const long long t_begin = clock64();
-      if (BRES && warp == 6) {
-        // the whole B share of this CTA, once: k-block kb lands at bres0 + kb * b_stage_bytes; every CTA of the group
-        // counts its bytes on the leader's auxbar[0] (unused otherwise: BRES excludes AUX)
-        const uint32_t bres0 = ring0 + nstages * kAStageBytes;
-        const uint32_t bar = smem_u32(&s.auxbar[0]);
-        const uint32_t bar_tx = CG > 1 ? (bar & kPeerBitMask) : bar;
-        if (crank == 0) mbar_expect_tx_raw(bar, static_cast<uint32_t>(p.bres_bytes) * CG);
-        if (merged) {
-          // merged phases: k-block (tap, chunk) holds mg_nph[tap] slabs of mg_rows rows, packed back to back
-          uint32_t off = 0;
-          for (int tap = 0; tap < num_taps; ++tap) {
-            const int mg_n = p.mg_nph[tap];
-            const uint64_t d9 = mg_n == 4 ? desc_b : desc_a0 + static_cast<uint64_t>(mg_n == 2 ? 1 : (mg_n == 1 ? 2 : 3)) * sizeof(CUtensorMap);
-            for (int chunk = 0; chunk < chunks; ++chunk, off += static_cast<uint32_t>(mg_n * mg_rows) * 128u)
-              tma_ld_2d_raw<CG>(d9, bar_tx, bres0 + off, 0, ((tap * chunks + chunk) * CG + crank) * (4 * mg_rows));
-          }
-        } else {
-          const int brow0 = crank * bn_cta;                     // n_tiles == 1 and num_phases == 1
-          for (int kb = 0; kb < num_kb; ++kb)
-            tma_ld_2d_raw<CG>(desc_b, bar_tx, bres0 + kb * p.b_stage_bytes, kb * kBlockK, brow0);
-        }
-      }
-      for (int tile = (BRES && warp == 6) ? total_tiles : tile0; tile < total_tiles; tile += tile_step) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int ph = tile % num_phases;
         const int rest = tile / num_phases;
         const int m_tile = (rest % mslots) * CG + crank;      // may be >= m_tiles for an odd tail: loads zero-fill
@@ -365,7 +338,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
             const uint32_t fb = full0_tx + stage * 8;
             if (warp == 0 && crank == 0)
               mbar_expect_tx_raw(full0 + stage * 8,
-                                 (merged && !BRES) ? (a_tx + static_cast<uint32_t>(mg_n * mg_rows) * 128u) * CG : stage_tx);
+                                 merged ? (a_tx + static_cast<uint32_t>(mg_n * mg_rows) * 128u) * CG : stage_tx);
             if (do_a) {
               if (a_2d) tma_ld_2d_raw<CG>(desc_a0, fb, sa, chunk * kBlockK, b0);
               else tma_ld_4d_raw<CG>(desc_a, fb, sa, chunk * kBlockK, cj, ci, b0);
@@ -410,11 +383,6 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
       int iter = 0;
       long long t_wfull = 0, t_wtempty = 0;
       const long long t_begin = clock64();
-      const uint32_t bres0 = ring0 + nstages * kAStageBytes;
-      if (BRES && tile0 < total_tiles) {
-        mbar_wait_raw(smem_u32(&s.auxbar[0]), 0u);            // the resident B block has landed (in every CTA)
-        tc_fence_after();
-      }
       for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1u;
@@ -426,7 +394,6 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
         if (p.merged) {
           // 9 shifts x chunks stages; one MMA per k-step covers every phase slab the shift feeds (N = 64..256).
           // The centre shift comes first and feeds all four phases: its first MMA initialises the whole accumulator.
-          uint32_t boff = 0;                                   // BRES: running offset into the resident B block
           for (int tap = 0; tap < p.num_taps; ++tap) {
             const int nsl = p.mg_nph[tap];
             const uint32_t idesc_n = make_idesc_bf16(kBlockM * CG, 64 * nsl, 0, 0);
@@ -438,8 +405,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
               tc_fence_after();
               const uint32_t sa = ring0 + stage * stage_bytes;
               const uint64_t da = da0 | static_cast<uint64_t>((sa >> 4) & 0x3FFF);
-              const uint32_t sbk = BRES ? bres0 + boff : sa + kAStageBytes;
-              if (BRES) boff += static_cast<uint32_t>(nsl * mg_rows) * 128u;
+              const uint32_t sbk = sa + kAStageBytes;
               const uint64_t db = db0 | static_cast<uint64_t>((sbk >> 4) & 0x3FFF);
               if (!skip_mma) {
 #pragma unroll
@@ -460,7 +426,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
           tc_fence_after();
           const uint32_t sa = ring0 + stage * stage_bytes;
           const uint64_t da = da0 | static_cast<uint64_t>((sa >> 4) & 0x3FFF);
-          const uint32_t sbk = BRES ? bres0 + kb * p.b_stage_bytes : sa + kAStageBytes;
+          const uint32_t sbk = sa + kAStageBytes;
           const uint64_t db = db0 | static_cast<uint64_t>((sbk >> 4) & 0x3FFF);
           if (!skip_mma) {
 #pragma unroll

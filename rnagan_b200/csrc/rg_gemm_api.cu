@@ -22,7 +22,6 @@ int cuda_fail(cudaError_t e, const char* what) {
   return static_cast<int>(e);
 }
 static std::atomic<long long> g_launches{0};
-std::atomic<long long> g_bres_launches{0};
 static long long* g_prof = nullptr;   // tools/gemm_prof.py: per-CTA role clocks of the next forward launches
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
@@ -174,10 +173,6 @@ static int ensure_attrs() {
                                  kSmemMaxBytes));
     RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_BF16_NHWC, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kSmemMaxBytes));
-    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_BF16_NHWC, 1, false, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxBytes));
-    RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_BF16_NHWC, 2, false, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxBytes));
     RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_F32_NHWC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kSmemMaxBytes));
     RG_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<OUT_F32_NCHW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -188,9 +183,9 @@ static int ensure_attrs() {
   return 0;
 }
 
-template <int OUT, int CG, bool AUX = false, bool BRES = false>
+template <int OUT, int CG, bool AUX = false>
 static int launch_fwd_t(const GemmMaps& maps, const FwdArgs& a, int grid, size_t smem, cudaStream_t st) {
-  RG_CUDA(launch_pdl(gemm_fwd_kernel<OUT, CG, AUX, BRES>, dim3(grid), dim3(kGemmThreads), smem, st, CG, maps, a));
+  RG_CUDA(launch_pdl(gemm_fwd_kernel<OUT, CG, AUX>, dim3(grid), dim3(kGemmThreads), smem, st, CG, maps, a));
   RG_LAUNCH_CHECK("gemm_fwd_kernel");
   return 0;
 }
@@ -255,33 +250,6 @@ static int launch_fwd(GemmMaps& maps, FwdArgs& a, int out_kind, int cg, float* s
   }
   a.nstages = std::min(ns, kMaxStages);
   size_t smem = static_cast<size_t>(a.nstages) * stage + (a.nbuf + a.naux) * kStagingBytes + kSmemFixedBytes;
-  // B-resident plan (opt-in, RG_BRES=1): one N tile, one phase, K-major B, and the CTA's whole B share fits next to at
-  // least three A stages -> the ring holds A tiles only and B is fetched once per CTA instead of once per tile
-  static const bool allow_bres = env_flag("RG_BRES", false);
-  bool bres = false;
-  a.bres_bytes = 0;
-  static const int bres_level = [] { const char* e = getenv("RG_BRES"); return e ? atoi(e) : 0; }();
-  if (allow_bres && out_kind == OUT_BF16_NHWC && a.tma_store && !a.b_mn && a.num_phases == 1 && a.n_tiles == 1 &&
-      a.aux_mode == 0 && a.whatif == 0 && a.prof == nullptr && (!a.merged || (bres_level >= 2 && cg == 2))) {
-    int bres_bytes = a.num_taps * a.chunks * a.b_stage_bytes;
-    if (a.merged) {                       // RG_BRES=2: also the merged-phase transposed form (variable slabs per shift)
-      bres_bytes = 0;
-      for (int t = 0; t < a.num_taps; ++t) bres_bytes += a.chunks * a.mg_nph[t] * (64 / cg) * 128;
-    }
-    int nbuf = a.nbuf;
-    int ns_a = (avail - nbuf * kStagingBytes - bres_bytes) / kAStageBytes;
-    if (ns_a < 3 && nbuf == 2) {          // one staging slab instead of two buys the third A stage
-      nbuf = 1;
-      ns_a = (avail - kStagingBytes - bres_bytes) / kAStageBytes;
-    }
-    if (bres_bytes > 0 && ns_a >= 3) {
-      bres = true;
-      a.bres_bytes = bres_bytes;
-      a.nbuf = nbuf;
-      a.nstages = std::min(ns_a, kMaxStages);
-      smem = static_cast<size_t>(a.nstages) * kAStageBytes + bres_bytes + a.nbuf * kStagingBytes + kSmemFixedBytes;
-    }
-  }
   if (a.tma_store) {
     // per-phase output views: pixel (b, i*sy + oy, j*sx + ox), channels [0, n_valid); TMA clips what lies outside
     const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(a.out);
@@ -311,11 +279,6 @@ static int launch_fwd(GemmMaps& maps, FwdArgs& a, int out_kind, int cg, float* s
     if (a.aux_mode != 0) {
       if (cg == 2) return launch_fwd_t<OUT_BF16_NHWC, 2, true>(maps, a, grid, smem, st);
       return launch_fwd_t<OUT_BF16_NHWC, 1, true>(maps, a, grid, smem, st);
-    }
-    if (bres) {
-      g_bres_launches.fetch_add(1, std::memory_order_relaxed);
-      if (cg == 2) return launch_fwd_t<OUT_BF16_NHWC, 2, false, true>(maps, a, grid, smem, st);
-      return launch_fwd_t<OUT_BF16_NHWC, 1, false, true>(maps, a, grid, smem, st);
     }
     if (cg == 2) return launch_fwd_t<OUT_BF16_NHWC, 2>(maps, a, grid, smem, st);
     return launch_fwd_t<OUT_BF16_NHWC, 1>(maps, a, grid, smem, st);
@@ -720,7 +683,6 @@ extern "C" {
 
 int rg_version(void) { return 100; }
 long long rg_launch_count(void) { return rg::launch_count(); }
-long long rg_bres_launch_count(void) { return rg::g_bres_launches.load(std::memory_order_relaxed); }
 const char* rg_last_error(void) { return g_err; }
 
 int rg_check_device(void) {

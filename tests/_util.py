@@ -6,7 +6,9 @@ import torch
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SEED_G, SEED_D, SEED_V, SEED_BATCH, SEED_RUN = 11, 12, 13, 14, 99
-CONFIGS = {"mini32": (32, 8, 256, 2), "mini64": (64, 4, 192, 1)}
+CONFIGS = {"mini32": (32, 8, 256, 2), "mini64": (64, 4, 192, 1),
+           # BASELINE config-2 shapes (gan_run_lung.json): 256x256 tiles, 19198 genes
+           "full256": (256, 8, 19198, 1)}
 
 
 def load_golden(name):

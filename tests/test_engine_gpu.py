@@ -449,30 +449,3 @@ def test_full_size_adjoint_identities(cuda_dev, layer):
         got = dot(d, V)
         assert abs(got - ref_w) <= 2e-3 * (abs(got) + abs(ref_w)) + 1e-2 * (x.numel() ** 0.5), (layer, got, ref_w)
     assert torch.equal(dW, dWn)          # both layouts come from the same fixed-order reduction
-
-
-# The B-resident tile-engine plan (RG_BRES=1) was written after this round's GPU budget was spent:
-# opt-in until it has run once (RG_TEST_EXPERIMENTAL=1), so that the validated suite stays as measured.
-@pytest.mark.skipif(os.environ.get("RG_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="unvalidated opt-in path: set RG_TEST_EXPERIMENTAL=1")
-def test_b_resident_plan_is_bit_identical(cuda_dev, tmp_path):
-    """RG_BRES=1 changes where the B operand lives (resident block instead of the ring), not the arithmetic: same MMA
-    sequence per tile, so outputs and fused statistics must be BIT-identical to the default plan, and the plan must
-    actually have been taken (rg_bres_launch_count > 0).  Each plan runs in its own process (the flag is read once)."""
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = {}
-    for flag in ("0", "1", "2"):                 # 1: strided form only; 2: also the merged-phase transposed form
-        path = str(tmp_path / f"bres{flag}.pt")
-        res = subprocess.run([sys.executable, os.path.join(root, "tests", "bres_worker.py"), path],
-                             env=dict(os.environ, RG_BRES=flag), capture_output=True, text=True, timeout=300)
-        assert res.returncode == 0, res.stderr[-2000:]
-        outs[flag] = torch.load(path)
-    assert outs["0"]["bres_launches"] == 0
-    assert outs["1"]["bres_down"] >= 6 and outs["1"]["bres_launches"] == outs["1"]["bres_down"]
-    assert outs["2"]["bres_down"] >= 6 and outs["2"]["bres_launches"] >= outs["2"]["bres_down"] + 4
-    for flag in ("1", "2"):
-        for k, v in outs["0"].items():
-            if not k.startswith("bres_"):
-                assert torch.equal(v, outs[flag][k]), (flag, k)

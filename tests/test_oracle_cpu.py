@@ -44,7 +44,7 @@ def _cmp_named(gold, prefix, named, grads=False):
     assert n > 0
 
 
-@pytest.mark.parametrize("cfg", ["mini32", "mini64"])
+@pytest.mark.parametrize("cfg", ["mini32", "mini64", "full256"])
 def test_oracle_matches_reference_training(cfg):
     size, batch, feats, iters = U.CONFIGS[cfg]
     gold = U.load_golden(f"gan_{cfg}.npz")

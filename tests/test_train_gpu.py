@@ -114,7 +114,7 @@ def _check_state(tag, onet, mnet):
             assert _rel(bm.float(), bo.float()) <= 5e-2, f"{tag} buffer {n}"
 
 
-@pytest.mark.parametrize("cfg", ["mini32", "mini64"])
+@pytest.mark.parametrize("cfg", ["mini32", "mini64", "full256"])
 def test_train_steps_match_oracle(cuda_dev, cfg):
     size, batch, feats, iters = U.CONFIGS[cfg]
     gold = U.load_golden(f"gan_{cfg}.npz")
