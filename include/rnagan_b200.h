@@ -197,7 +197,10 @@ int rg_img_channel_sum(const float* x, const float* y, int mode, int B, int Cimg
  * onto the 2x larger image: img[b,c,y,x] = act(bias[c] + sum of the 4 taps hitting (y,x)); fp32 NCHW output.
  * Generator last layer (ConvTranspose2d(64,3,4,2,1)+Tanh, src/dcgan.py:82) and the critic's layer-0 dgrad.
  * act_tanh is a flag word: bit 0 = tanh, bit 1 = write the synthesis output instead, (v + 1) / 2 as fp32 NHWC
- * [B, 2H, 2W, Cimg] (src/gan_utils.py:236-241), which saves the separate un-normalise + permute pass. */
+ * [B, 2H, 2W, Cimg] (src/gan_utils.py:236-241), which saves the separate un-normalise + permute pass; bit 2 = write
+ * uint8 NHWC tiles trunc(255 * (v + 1) / 2) instead (`img` then points to B*2H*2W*Cimg bytes: what
+ * src/generate_tissue_images.py:127-129 computes on the host before cv2.imwrite), bit 3 = with bit 2, reversed channel
+ * order (cv2's BGR). */
 int rg_col2im_img(const float* col, int ldc, const float* bias, int act_tanh, int B, int Cimg, int H, int W, float* img,
                   rg_stream_t st);
 /* W[Cp][Cimg][4][4] -> bf16 w_colT[rows][Cp], row n = tap*Cimg + c (rows beyond 16*Cimg zero) */

@@ -820,7 +820,13 @@ __global__ void __launch_bounds__(256) col2im_img_kernel(const float* __restrict
       if (c < Cimg) {
         float v = acc[c] + (bias ? __ldg(bias + c) : 0.0f);
         if (act_tanh & 1) v = tanhf(v);
-        if (act_tanh & 2)     // synthesis output (src/gan_utils.py:236-241): (x + 1) / 2, NHWC
+        if (act_tanh & 4) {   // uint8 NHWC tile as the reference writes it to disk: trunc(255 * (x + 1) / 2)
+                              // (src/generate_tissue_images.py:127-129; bit 3: channel order reversed, cv2's BGR)
+          const float u = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
+          const int cc = (act_tanh & 8) ? Cimg - 1 - c : c;
+          reinterpret_cast<uint8_t*>(img)[((static_cast<size_t>(b) * OH + y) * OW + x) * Cimg + cc] =
+              static_cast<uint8_t>(__float2uint_rz(fminf(fmaxf(u, 0.0f), 255.0f)));
+        } else if (act_tanh & 2)     // synthesis output (src/gan_utils.py:236-241): (x + 1) / 2, NHWC
           img[((static_cast<size_t>(b) * OH + y) * OW + x) * Cimg + c] = (v + 1.0f) * 0.5f;
         else
           img[((static_cast<size_t>(b) * Cimg + c) * OH + y) * OW + x] = v;
@@ -960,7 +966,8 @@ __global__ void gp_finalize_kernel(const float* __restrict__ partial, int n, flo
   if (threadIdx.x == 0) {
     const float norm = sqrtf(static_cast<float>(sm[0]));
     out[0] = (norm - 1.0f) * (norm - 1.0f);
-    out[1] = lambd * 2.0f * (norm - 1.0f) / norm;
+    // torch.norm's backward gives the zero subgradient at norm == 0 (dead critic / all-zero input gradient)
+    out[1] = norm > 0.0f ? lambd * 2.0f * (norm - 1.0f) / norm : 0.0f;
     out[2] = norm;
   }
 }
@@ -1010,8 +1017,10 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
     p4[i] = p; m4[i] = m; v4[i] = v;
     if (s4) s4[i] = make_uint2(pack_bf16x2_ops(p.x, p.y), pack_bf16x2_ops(p.z, p.w));
   }
-  if (ch.shadow != nullptr && s4 == nullptr)
+  if (ch.shadow != nullptr && s4 == nullptr) {     // shadow not 8-byte aligned (offset views passed through the C ABI)
+    __syncthreads();                                // the elements below were written by other threads' float4 stores
     for (int i = threadIdx.x; i < n4 * 4; i += blockDim.x) ch.shadow[i] = __float2bfloat16(ch.p[i]);
+  }
   for (int i = n4 * 4 + threadIdx.x; i < ch.n; i += blockDim.x) {
     const float g = ch.g[i] * gscale;
     const float m = b1 * ch.m[i] + ob1 * g;

@@ -83,8 +83,13 @@ class _EngineMixin:
         """pickle / deepcopy carry parameters and buffers only; the engine (`_rg_*`) is rebuilt lazily."""
         return {k: v for k, v in self.__dict__.items() if not k.startswith("_rg_")}
 
-    def _engine(self):
+    def _engine(self, flush=True):
+        """The kernel schedule of this module.  flush: first apply an optimiser step that a data-parallel train step
+        deferred (steps.apply_update), so every outside reader sees the reference's post-step weights."""
         eng = self.__dict__.get("_rg_engine")
+        if flush and eng is not None and getattr(eng, "pending_update", None) is not None:
+            from .steps import apply_update
+            apply_update(eng)
         p0 = next(self.parameters())
         if p0.device.type != "cuda":
             raise RuntimeError(f"{type(self).__name__} runs only on a CUDA (sm_100a) device: there is no CPU fallback; "
@@ -100,6 +105,16 @@ class _EngineMixin:
 
     def _versions(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def state_dict(self, *args, **kwargs):
+        if self.__dict__.get("_rg_engine") is not None and next(self.parameters()).device.type == "cuda":
+            self._engine()                  # applies a deferred (data-parallel) optimiser step first
+        return super().state_dict(*args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        if self.__dict__.get("_rg_engine") is not None and next(self.parameters()).device.type == "cuda":
+            self._engine()                  # a deferred step must not land on top of the loaded weights
+        return super().load_state_dict(*args, **kwargs)
 
     def _apply(self, fn, *args, **kwargs):   # .to()/.cuda()/.float(): storage moves invalidate the engine
         before = [p.data_ptr() for p in self.parameters()]

@@ -269,9 +269,10 @@ class GeneratorEngine:
         ops.pack_edge_t(self.conv_last.weight.detach(), self.w_colT_last)
         ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
 
-    def forward(self, lat, tag="g", training=True, out=None, unit_nhwc=False):
+    def forward(self, lat, tag="g", training=True, out=None, unit_nhwc=False, u8=False, bgr=False):
         """lat: bf16 [B, E] -> fp32 NCHW image [B, Cimg, S, S]; keeps activations under `tag` for backward.
-        unit_nhwc (synthesis): `out` [B, S, S, Cimg] receives (image + 1) / 2 in NHWC straight from the last kernel."""
+        unit_nhwc (synthesis): `out` [B, S, S, Cimg] receives (image + 1) / 2 in NHWC straight from the last kernel;
+        u8: `out` is a uint8 [B, S, S, Cimg] tensor receiving trunc(255 * (image + 1) / 2) (bgr: reversed channels)."""
         B = lat.shape[0]
         g = self.bufs.get
         a = g(f"{tag}.a0", (B, 4, 4, self.C0))
@@ -291,7 +292,7 @@ class GeneratorEngine:
             out = g(f"{tag}.img", (B, 2 * H, 2 * H, self.Cimg) if unit_nhwc else (B, self.Cimg, 2 * H, 2 * H), F32)
         col = g("fwd.colimg", (B * H * H, 16 * self.Cimg), F32)
         ops.conv_up_img_col(h, self.w_colT_last, self.Cimg, col, out, bias=self.conv_last.bias.detach(), act_tanh=True,
-                            unit_nhwc=unit_nhwc)
+                            unit_nhwc=unit_nhwc, u8=u8, bgr=bgr)
         return out
 
     def backward(self, lat, d_img, img, tag="g"):

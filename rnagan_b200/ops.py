@@ -409,14 +409,16 @@ def pack_edge_t(W, out):
     return out
 
 
-def conv_up_img_col(lo, w_colT, Cimg, col, out, bias=None, act_tanh=False, unit_nhwc=False):
+def conv_up_img_col(lo, w_colT, Cimg, col, out, bias=None, act_tanh=False, unit_nhwc=False, u8=False, bgr=False):
     """Image-side transposed conv as GEMM (K = Cp only, each input pixel read once) + col2im:
     lo bf16 [B, H, W, Cp] -> out fp32 NCHW [B, Cimg, 2H, 2W]; col: fp32 scratch [B*H*W, 16*Cimg].
-    unit_nhwc: out is instead the synthesis result (x + 1) / 2 as fp32 NHWC [B, 2H, 2W, Cimg]."""
+    unit_nhwc: out is instead the synthesis result (x + 1) / 2 as fp32 NHWC [B, 2H, 2W, Cimg];
+    u8: out is the uint8 NHWC tile trunc(255 * (x + 1) / 2) (bgr: channel order reversed for cv2.imwrite)."""
     B, H, W, Cp = lo.shape
     N = 16 * Cimg
     gemm_nt(lo.view(B * H * W, Cp), w_colT, out=col, N=N)
-    _lib.check(_lib.lib().rg_col2im_img(_p(col), col.stride(0), _p(bias), int(act_tanh) | (2 if unit_nhwc else 0), B,
+    _lib.check(_lib.lib().rg_col2im_img(_p(col), col.stride(0), _p(bias),
+                                        int(act_tanh) | (2 if unit_nhwc else 0) | (4 if u8 else 0) | (8 if bgr else 0), B,
                                         Cimg, H, W, _p(out), _st()), "rg_col2im_img")
     return out
 

@@ -57,6 +57,9 @@ def adam_step(opt, clamp=None, grad_scale=1.0):
             tables[gi] = ent
         for s in states:
             s["step"] += 1
-        step = int(states[0]["step"].item()) if states[0]["step"].device.type == "cpu" else int(states[0]["step"])
+        step = int(states[0]["step"])
+        if len(states) > 1 and any(int(s["step"]) != step for s in states[1:]):
+            # one bias correction per launch: a partially populated / merged optimizer state would be stepped wrongly
+            raise NotImplementedError("fused Adam needs every parameter of a group at the same step count")
         b1, b2 = group["betas"]
         ent[1].step(group["lr"], b1, b2, group["eps"], step, clamp=clamp, grad_scale=grad_scale)

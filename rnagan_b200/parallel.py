@@ -262,10 +262,10 @@ class GradSync:
             self._pending.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True))
             self._done.add(id(p))
 
-    def finish(self):
-        w = self.world()
-        if w == 1:
-            return 1.0
+    def launch_rest(self):
+        """Submit (asynchronously) the reduction of everything the engines did not announce with layer_done."""
+        if self.world() == 1:
+            return
         self._flush_open()
         rest = [p for p in self.params if id(p) not in self._done and p.grad is not None]
         # merge contiguous leftovers into as few collectives as possible
@@ -285,7 +285,18 @@ class GradSync:
                     run = [p]
                 else:
                     self._pending.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True))
+        self._done.update(id(p) for p in rest)
+
+    def wait(self):
+        """Order the current stream after every submitted reduction; returns the gradient scale 1/world."""
+        w = self.world()
+        if w == 1:
+            return 1.0
         for h in self._pending:
             h.wait()
         self._pending, self._done = [], set()
         return 1.0 / w
+
+    def finish(self):
+        self.launch_rest()
+        return self.wait()

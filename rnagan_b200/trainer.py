@@ -46,7 +46,11 @@ class Trainer:
         self.last_retained_checkpoint = 0
         self.recon = recon
         self.nrow = nrow
-        self.test_noise = test_noise             # None: drawn once from each generator's sampler, then kept
+        # torchgan draws the fixed test noise of every generator-like model in __init__ [tg] (this consumes the device
+        # RNG stream before training starts, like upstream)
+        gens = [n for n in self.model_names if callable(getattr(getattr(self, n), "sampler", None))]
+        self.test_noise = [getattr(self, n).sampler(sample_size, self.device) if test_noise is None else test_noise
+                           for n in gens]
         self.batch_size = None
         self.real_inputs = None
         self.labels = None
@@ -152,7 +156,7 @@ class Trainer:
         pending, kinds = {}, {}
         for name, loss in self.losses.items():
             if isinstance(loss, GeneratorLoss):
-                if info["discriminator_iters"] % self.ncritic == 0:
+                if self.ncritic is None or info["discriminator_iters"] % self.ncritic == 0:
                     pending[name] = self._call(name)
                     kinds[name] = "g"
             elif isinstance(loss, DiscriminatorLoss):
@@ -197,12 +201,23 @@ class Trainer:
             for name in self.model_names:
                 getattr(self, name).train()
             for data in data_loader:
-                self.real_inputs = data
-                if isinstance(data, dict) and "image" in data:
-                    self.batch_size = data["image"].size(0)
+                if isinstance(data, (tuple, list)):          # (images, labels) loaders, as torchgan unpacks them [tg]
+                    self.real_inputs = data[0].to(self.device)
+                    self.labels = data[1].to(self.device)
+                    self.batch_size = self.real_inputs.size(0)
+                elif torch.is_tensor(data):
+                    self.real_inputs = data.to(self.device)
+                    self.batch_size = data.size(0)
+                else:
+                    self.real_inputs = data
+                    if isinstance(data, dict) and "image" in data:
+                        self.batch_size = data["image"].size(0)
                 self.train_iter(defer=True)
             self.flush()
-            main = self._is_main_process()       # data-parallel runs: replicas are identical, rank 0 writes the files
+            # data-parallel runs: parameters and optimiser state are bit-identical on every rank (averaged gradients);
+            # BatchNorm running statistics are rank-LOCAL (each rank saw its own shard, like DDP without SyncBN), so the
+            # checkpoint rank 0 writes carries rank 0's running statistics
+            main = self._is_main_process()
             if main:
                 self.save_model(epoch)
             for name in self.model_names:
@@ -221,8 +236,6 @@ class Trainer:
         if not self.recon:
             return []
         gens = [n for n in self.model_names if callable(getattr(getattr(self, n), "sampler", None))]
-        if self.test_noise is None:
-            self.test_noise = [getattr(self, n).sampler(self.sample_size, self.device) for n in gens]
         paths = []
         for n, noise in zip(gens, self.test_noise):
             with torch.no_grad():

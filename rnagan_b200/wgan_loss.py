@@ -16,6 +16,8 @@ BatchNorm everywhere, one scalar eps per GP step drawn after that step's noise, 
 lambda applied outside ``forward``, un-weighted penalty returned.  Work the reference wastes (encoder backward,
 critic wgrad in the G step, generator backward in the GP step) is simply not scheduled.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -77,8 +79,8 @@ class _StepCache:
         self.val = {}
         self.keep = {}
 
-    def get(self, what, src, device, make):
-        key = (id(src), src._version, tuple(src.shape), str(device))
+    def get(self, what, src, device, make, extra=()):
+        key = (id(src), src._version, tuple(src.shape), str(device)) + tuple(extra)
         if self.key.get(what) != key:
             self.val[what] = make()
             self.key[what] = key
@@ -110,7 +112,12 @@ class _VAEConditioned:
 
     def _init_vae(self, checkpoint, rna_features, beta):
         self.betavae = _load_vae(checkpoint, rna_features, beta)
-        self._ckpt_key = (str(checkpoint), int(rna_features))
+        try:
+            st = os.stat(checkpoint)
+            stamp = (st.st_size, st.st_mtime_ns)
+        except OSError:
+            stamp = ()
+        self._ckpt_key = (str(checkpoint), int(rna_features)) + stamp
 
     def __setstate__(self, state):
         """Instances pickled by the reference (inside a torchgan checkpoint's `loss_objects`, see compat.py) carry
@@ -123,7 +130,8 @@ class _VAEConditioned:
             vae.eval()
 
     def _encoder(self, device):
-        """All three loss objects load the SAME checkpoint (src/histopathology_gan.py:275-277): share one device copy."""
+        """All three loss objects load the SAME checkpoint (src/histopathology_gan.py:275-277): share one device copy
+        (keyed on path + size + mtime at load time, so a checkpoint re-saved at the same path is not confused)."""
         key = self._ckpt_key + (str(device),)
         vae = _SHARED_VAE.get(key)
         if vae is None:
@@ -139,9 +147,12 @@ class _VAEConditioned:
         B = real_inputs["image"].size(0)
         rna = real_inputs["rna_data"]
         vae = self._encoder(device)
-        z = _CACHE.get("z", rna, device, lambda: vae.encode_mean(rna.to(device, non_blocking=True)))
+        # keyed on the encoder too (its identity and parameter versions: another VAE / a reloaded checkpoint misses) and
+        # cloned, because encode_mean returns the encoder engine's reusable output buffer
+        vkey = (id(vae),) + tuple(p._version for p in vae.parameters())
+        z = _CACHE.get("z", rna, device, lambda: vae.encode_mean(rna.to(device, non_blocking=True)).clone(), extra=vkey)
         self._prefetch_real(real_inputs, device)
-        eng = generator._engine()
+        eng = generator._engine(flush=False)
         E = generator.encoding_dims
         # pinned staging PER LOSS OBJECT, two buffers used alternately: Trainer.train_iter defers the host
         # synchronisation (to the end of the iteration, or by one more iteration in `train`), so a step's asynchronous
@@ -188,6 +199,27 @@ class _VAEConditioned:
             cur.wait_event(ev)
             dst.record_stream(cur)     # allocated on the copy stream, read here: its block is not reused before this
         return dst                     # stream is done with it (iterations are queued ahead of the host, Trainer.train)
+
+
+def _eps_to_device(discriminator, eps):
+    """The GP step's scalar eps (one CPU draw, src/wgan_loss.py:376) -> device buffer through a pinned slot: an
+    asynchronous copy instead of the synchronous pageable one (the host stays ahead of the device, Trainer.train).
+    Four slots guarded by events, like the noise staging."""
+    eng = discriminator._engine(flush=False)
+    ring = eng.bufs.__dict__.setdefault("_eps_pinned", None)
+    if ring is None:
+        ring = {"i": 0, "buf": torch.empty(4, 1, dtype=F32).pin_memory(), "ev": [None] * 4}
+        eng.bufs.__dict__["_eps_pinned"] = ring
+    k = ring["i"] = (ring["i"] + 1) % 4
+    if ring["ev"][k] is not None:
+        ring["ev"][k].synchronize()
+    ring["buf"][k].copy_(eps)
+    eps_d = eng.bufs.get("eps", (1,), F32)
+    eps_d.copy_(ring["buf"][k], non_blocking=True)
+    if ring["ev"][k] is None:
+        ring["ev"][k] = torch.cuda.Event()
+    ring["ev"][k].record(torch.cuda.current_stream(eng.device))
+    return eps_d
 
 
 def _check_labels(labels, *nets):
@@ -260,8 +292,7 @@ class WassersteinGradientPenaltyVAE(_VAEConditioned, DiscriminatorLoss):
         noise_d, z = self._inputs(generator, real_inputs, device)
         real = self._real(real_inputs, device)
         eps = torch.rand(1)                                              # one scalar per step, src/wgan_loss.py:376
-        eps_d = discriminator._engine().bufs.get("eps", (1,), F32)
-        eps_d.copy_(eps)
+        eps_d = _eps_to_device(discriminator, eps)
         out3 = steps.gp_step(generator, discriminator, optimizer_discriminator, noise_d, z, real, eps_d,
                              lambd=self.lambd)
         return out3[0:1]
@@ -327,8 +358,7 @@ class WassersteinGradientPenalty(DiscriminatorLoss):
         real = _images_of(real_inputs, device)
         noise = torch.randn(real.size(0), generator.encoding_dims, device=device)
         eps = torch.rand(1)                                                # CPU draw, like torchgan's .item() [tg]
-        eps_d = discriminator._engine().bufs.get("eps", (1,), F32)
-        eps_d.copy_(eps)
+        eps_d = _eps_to_device(discriminator, eps)
         out3 = steps.gp_step(generator, discriminator, optimizer_discriminator, noise, None, real, eps_d,
                              lambd=self.lambd)
         return out3[0:1]

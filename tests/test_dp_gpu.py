@@ -1,5 +1,6 @@
-"""Multi-GPU (needs >= 2 B200s; skipped otherwise): batch-sharded data-parallel training over NCCL equals the oracle
-run per shard with averaged gradients, and all ranks hold identical weights after every optimiser step."""
+"""Multi-GPU (needs >= 2 B200s; skipped otherwise): batch-sharded data-parallel training equals the oracle run per shard
+with averaged gradients (within twice torch-bf16's own deviation), and all ranks hold bit-identical weights after every
+optimiser step -- over NCCL and over the copy-engine peer exchange (parallel.PeerExchange, RG_DP_EXCHANGE=ce)."""
 import os
 import subprocess
 import sys
@@ -22,13 +23,6 @@ def test_data_parallel_two_gpus(cuda_dev):
     assert res.returncode == 0
 
 
-# The copy-engine exchange (parallel.PeerExchange) was written after this round's GPU budget was spent: its GPU tests
-# are opt-in until they have been run once (RG_TEST_EXPERIMENTAL=1), so that the validated suite stays as measured.
-experimental = pytest.mark.skipif(os.environ.get("RG_TEST_EXPERIMENTAL", "0") != "1",
-                                  reason="unvalidated opt-in path: set RG_TEST_EXPERIMENTAL=1")
-
-
-@experimental
 def test_slices_sum_matches_ordered_sum(cuda_dev):
     from rnagan_b200 import ops
     g = torch.Generator().manual_seed(1)
@@ -42,7 +36,6 @@ def test_slices_sum_matches_ordered_sum(cuda_dev):
         assert torch.equal(out, want)
 
 
-@experimental
 def test_data_parallel_two_gpus_peer_exchange(cuda_dev):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

@@ -284,3 +284,45 @@ def test_training_is_bitwise_deterministic(cuda_dev):
     assert s0.keys() == s1.keys()
     for k in s0:
         assert torch.equal(s0[k], s1[k]), f"{k} differs between two identical runs"
+
+
+def test_uint8_tiles_and_synthesis_job(cuda_dev):
+    """uint8 tile output (what src/generate_tissue_images.py:127-129 computes on the host: `img *= 255;
+    img.astype(np.uint8)`, then RGB->BGR for cv2.imwrite) written by the generator's last kernel is BIT-EXACT against
+    that host arithmetic applied to the fp32 tiles of the same call, and the streaming job (gan_utils.synthesize_job,
+    BASELINE config 4) hands every tile of its range to the sink exactly once, in order, ragged last batch included."""
+    from rnagan_b200 import gan_utils
+    size, batch, feats, _ = U.CONFIGS["mini32"]
+    oG, oD, oV, tr = _build(size, feats, cuda_dev)
+    tr.generator.load_state_dict(oG.state_dict())
+    vae = tr.losses["WassersteinGeneratorLossVAE"]._encoder(cuda_dev)
+    profiles = torch.randn(7, feats, generator=torch.Generator().manual_seed(3))
+    n = 48
+    rows = profiles[torch.arange(n) % 7]
+    torch.manual_seed(21)
+    f32 = gan_utils.generate_tiles(tr.generator, vae, rows, n, chunk=n, device=cuda_dev).cpu().numpy()
+    for bgr in (False, True):
+        torch.manual_seed(21)
+        u8 = gan_utils.generate_tiles(tr.generator, vae, rows, n, chunk=n, device=cuda_dev, u8=True, bgr=bgr)
+        assert u8.dtype == torch.uint8 and u8.shape == (n, size, size, 3)
+        want = (f32 * np.float32(255)).astype(np.uint8)
+        if bgr:
+            want = want[..., ::-1]
+        assert np.array_equal(u8.cpu().numpy(), want)
+    # streaming job: tiles [5, 5 + 100) in batches of 32 (ragged tail of 4), profile row t % 7
+    got = {}
+
+    def sink(t0, tiles):
+        assert tiles.dtype == np.uint8 and tiles.shape[1:] == (size, size, 3)
+        got[t0] = tiles.copy()
+
+    torch.manual_seed(33)
+    done = gan_utils.synthesize_job(tr.generator, vae, profiles, 5, 105, batch=32, sink=sink)
+    assert done == 100 and sorted(got) == [5, 37, 69, 101] and [got[k].shape[0] for k in sorted(got)] == [32, 32, 32, 4]
+    # same RNG stream, same batches through generate_tiles
+    torch.manual_seed(33)
+    for t0 in sorted(got):
+        nb = got[t0].shape[0]
+        idx = torch.arange(t0, t0 + nb) % 7
+        ref = gan_utils.generate_tiles(tr.generator, vae, profiles[idx], nb, chunk=nb, device=cuda_dev, u8=True)
+        assert np.array_equal(ref.cpu().numpy(), got[t0]), t0
