@@ -203,6 +203,36 @@ int rg_img_channel_sum(const float* x, const float* y, int mode, int B, int Cimg
  * order (cv2's BGR). */
 int rg_col2im_img(const float* col, int ldc, const float* bias, int act_tanh, int B, int Cimg, int H, int W, float* img,
                   rg_stream_t st);
+/* ---- fused image-side convolutions (csrc/rg_img.cu): no materialised im2col / col2im buffer --------------------------
+ * The 64-channel side is bf16 NHWC [B][S/2][S/2][64]; the image side fp32 NCHW [B][Cimg][S][S] (Cimg <= 4); weights are
+ * the nn.Module parameters themselves, fp32 [64][Cimg][4][4] (Conv2d(Cimg,64).weight is [64][Cimg][4][4];
+ * ConvTranspose2d(64,Cimg).weight is [64][Cimg][4][4] too), read directly -- no packed copies.
+ *
+ * rg_img_conv_up: ConvTranspose2d(64, Cimg, 4, 2, 1) (+bias, Tanh) = the generator's output block (torchgan DCGANGenerator
+ * last block; src/dcgan.py:82 keeps the line as a comment) and the input gradient of the critic's first Conv2d
+ * (autograd.grad w.r.t. the interpolate, src/wgan_loss.py:34-41).  `flags` as rg_col2im_img: bit 0 tanh, bit 1 fp32 NHWC
+ * (v+1)/2 (src/gan_utils.py:236-241), bit 2 uint8 NHWC trunc(255*(v+1)/2) (src/generate_tissue_images.py:127-129),
+ * bit 3 reversed channel order with bit 2.  H, W: low-resolution side (powers of two >= 8). */
+int rg_img_conv_up(const void* lo, const float* W, const float* bias, int flags, int B, int H, int Wd, int Cp, int Cimg,
+                   void* out, rg_stream_t st);
+/* rg_img_conv_down: Conv2d(Cimg, 64, 4, 2, 1) (+bias, LeakyReLU(slope); slope 1 = none) = the critic's first block
+ * (torchgan DCGANDiscriminator) and the input gradient of the generator's output block.  The image operand is
+ * transformed while it is staged: mode 0: x * mul_dev[0] (mul_dev may be NULL); mode 1: eps_dev[0]*x + (1-eps_dev[0])*y,
+ * the gradient-penalty interpolate (src/wgan_loss.py:376-380); mode 2: x * (1 - y^2), the Tanh backward with y the
+ * generator output.  mask_src (optional, bf16 like out): out *= (mask_src > 0 ? 1 : mask_slope), the LeakyReLU backward
+ * mask of the double-backward sweep.  S: image side (power of two >= 16). */
+int rg_img_conv_down(const float* x, const float* y, int mode, const float* eps_dev, const float* mul_dev,
+                     const float* W, const float* bias, float slope, const void* mask_src, float mask_slope, int B,
+                     int Cimg, int S, int Cp, void* out, rg_stream_t st);
+/* rg_img_conv_wgrad: dW[p][c][kh][kw] = acc*dW + sum act[b,y,x,p] * img'[b,c,2y-1+kh,2x-1+kw] with img' the image
+ * operand transformed as in rg_img_conv_down -- the weight gradient of either layer (Conv2d: act = d(out);
+ * ConvTranspose2d: act = the layer input, img' = d(pre-activation)); dbias (optional, Cimg <= 3):
+ * dbias[p] = acc_bias*dbias + sum act[..,p] (the Conv2d bias gradient).  Two-stage, fixed order (bit-reproducible).
+ * ws: rg_img_conv_wgrad_ws_bytes() bytes of scratch. */
+size_t rg_img_conv_wgrad_ws_bytes(void);
+int rg_img_conv_wgrad(const void* act, const float* x, const float* y, int mode, const float* eps_dev,
+                      const float* mul_dev, int B, int Cimg, int S, int Cp, void* ws, size_t ws_bytes, float* dW,
+                      float acc, float* dbias, float acc_bias, rg_stream_t st);
 /* W[Cp][Cimg][4][4] -> bf16 w_colT[rows][Cp], row n = tap*Cimg + c (rows beyond 16*Cimg zero) */
 int rg_pack_edge_t(const float* W, void* w_colT, int Cp, int Cimg, int rows, rg_stream_t st);
 int rg_unpack_edge_grad(const float* dcol, float* dW, int Cp, int Cimg, float acc, rg_stream_t st);
@@ -230,6 +260,12 @@ int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms
 int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, float beta2, float eps, int step,
                  int do_clamp, float clamp_lo, float clamp_hi, float grad_scale, rg_stream_t st);
 int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st);
+/* data-parallel gradient exchange through NVSwitch multicast (NVLink SHARP): in place, over the MULTICAST mapping `mc` of
+ * a symmetric buffer (every rank's copy at the same offset), the calling rank reduces floats [offset, offset+n) --
+ * multimem.ld_reduce (fp32 sum inside the switch) then multimem.st (broadcast to every copy).  Ranks call it for disjoint
+ * slices between two barriers; replaces the NCCL all-reduce of G/D gradients (src/histopathology_gan.py runs one process;
+ * SURVEY.md 8e shards by batch).  max_ctas bounds the SMs it may take (0: 16). */
+int rg_nvls_allreduce(float* mc, size_t offset, size_t n, int max_ctas, rg_stream_t st);
 /* data-parallel gradient exchange (what DistributedDataParallel's all-reduce would do around the
  * reference): out[i] = sum over r < nparts of src[r * stride + i], r ascending -- the reduction step of the peer-to-peer
  * exchange, after every rank's copy of this rank's slice has been pulled into src by the copy engines.  Fixed order,

@@ -11,7 +11,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RG_LIB_PATH") or os.path.join(_HERE, "librnagan_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["rg_gemm_api.cu", "rg_ops.cu"]
+SOURCES = ["rg_gemm_api.cu", "rg_ops.cu", "rg_img.cu"]
 
 _c = ctypes
 _vp, _i, _f, _sz = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t
@@ -63,6 +63,10 @@ SIGNATURES = {
     "rg_im2col_img": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "rg_img_channel_sum": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _f, _vp]),
     "rg_col2im_img": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rg_img_conv_up": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rg_img_conv_down": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _f, _i, _i, _i, _i, _vp, _vp]),
+    "rg_img_conv_wgrad_ws_bytes": (_sz, []),
+    "rg_img_conv_wgrad": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _f, _vp, _f, _vp]),
     "rg_pack_edge_t": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rg_unpack_edge_grad": (_i, [_vp, _vp, _i, _i, _f, _vp]),
     "rg_pack_head": (_i, [_vp, _vp, _i, _vp]),
@@ -76,6 +80,7 @@ SIGNATURES = {
     "rg_adam_step": (_i, [_vp, _i, _f, _f, _f, _f, _i, _i, _f, _f, _f, _vp]),
     "rg_clamp": (_i, [_vp, _sz, _f, _f, _vp]),
     "rg_slices_sum": (_i, [_vp, _i, _sz, _sz, _vp, _vp]),
+    "rg_nvls_allreduce": (_i, [_vp, _sz, _sz, _i, _vp]),
     "rg_tiles_u8_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rg_tiles_to_unit_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rg_upsample2x_reflectpad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

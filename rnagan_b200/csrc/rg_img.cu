@@ -1,0 +1,540 @@
+// rg_img.cu -- the 3-channel image side of the DCGAN pair without a materialised im2col / col2im buffer:
+//
+//   rg_img_conv_up     ConvTranspose2d(64, Cimg, 4, 2, 1) (+bias, tanh): generator output layer (src/dcgan.py:82 /
+//                      torchgan DCGANGenerator last block) and the critic layer-0 input gradient
+//   rg_img_conv_down   Conv2d(Cimg, 64, 4, 2, 1) (+bias, LeakyReLU): critic layer 0 (torchgan DCGANDiscriminator first
+//                      block) on the fp32 NCHW image, with the gradient-penalty interpolation (src/wgan_loss.py:376-380)
+//                      or the tanh backward fused into the patch load; also the generator output layer's input gradient
+//   rg_img_conv_wgrad  the weight (and bias) gradient of either layer
+//
+// These layers carry 6 GFLOP per pass against 134 MB of activations: HBM-bound.  Each CTA stages a halo'd tile in shared
+// memory ONCE (the old path wrote and re-read a 134-201 MB `col` matrix per pass) and contracts it with warp-level
+// mma.sync.m16n8k16 bf16 fragments (fp32 accumulate) -- the tensor pipe is idle >90 % of the time here either way, so the
+// point of the MMA is only to keep the arithmetic off the critical path; tcgen05 / TMEM would buy nothing.
+#include <algorithm>
+#include "rg_host.cuh"
+#include "rg_ptx.cuh"
+#include <cuda_bf16.h>
+
+namespace rg {
+
+namespace {
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+// D (16x8 fp32) += A (16x16 bf16, row) * B (16x8 bf16, col)
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t bf2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// 16-byte global -> shared copy; bytes == 0 zero-fills (out-of-image halo)
+__device__ __forceinline__ void cp16_zfill(uint32_t sdst, const void* gsrc, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+constexpr int kTH = 16, kTW = 32;                 // low-resolution pixels per CTA tile (the 64-channel side)
+constexpr int kThreads = 256;                     // 8 warps: warp w owns tile rows 2w, 2w+1
+constexpr int kC = 64;                            // channels of the 64-channel side (step_channels)
+
+// ------------------------------------------------------------------------------------------------ image patch (fp32)
+// patch[c][r][x]: image rows 2*y0-1 .. 2*y0+2*kTH, columns 2*x0-1 .. 2*x0+2*kTW (zero outside the image), optionally
+// transformed while loading.  Row pitch 80 floats: the two patch rows a fragment load touches land 16 banks apart.
+constexpr int kPR = 2 * kTH + 2, kPC = 2 * kTW + 2, kPitch = 80;
+constexpr int kMaxCimg = 4;
+
+// mode 0: x * mul;  1: eps*x + (1-eps)*y (gradient-penalty interpolate);  2: x * (1 - y^2) (tanh backward, y = tanh)
+__device__ __forceinline__ void load_img_patch(float* patch, const float* __restrict__ x, const float* __restrict__ y,
+                                               int mode, float eps, float mul, int b, int Cimg, int S, int y0, int x0) {
+  const int rows = Cimg * kPR;
+  for (int idx = threadIdx.x; idx < rows * kPitch; idx += kThreads) {
+    const int cr = idx / kPitch, xx = idx - cr * kPitch;
+    const int c = cr / kPR, r = cr - c * kPR;
+    const int gy = 2 * y0 - 1 + r, gx = 2 * x0 - 1 + xx;
+    float t = 0.0f;
+    if (xx < kPC && gy >= 0 && gy < S && gx >= 0 && gx < S) {
+      const size_t o = ((static_cast<size_t>(b) * Cimg + c) * S + gy) * S + gx;
+      t = __ldg(x + o);
+      if (mode == 1) t = eps * t + (1.0f - eps) * __ldg(y + o);
+      else if (mode == 2) { const float th = __ldg(y + o); t = t * (1.0f - th * th); }
+      t *= mul;
+    }
+    patch[idx] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ activation tile (bf16)
+// tile[P][64 channels] with P = r * pw + c over a (ph x pw) pixel window whose top-left pixel is (ya, xa); 128-byte rows,
+// 16-byte chunk index XOR (P & 7): ldmatrix over 8 consecutive pixels is conflict-free.  Out-of-image pixels are zero.
+__device__ __forceinline__ void load_act_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ act, int b, int H, int W,
+                                              int ya, int xa, int ph, int pw) {
+  const uint32_t base = smem_u32(tile);
+  for (int idx = threadIdx.x; idx < ph * pw * 8; idx += kThreads) {
+    const int P = idx >> 3, ch = idx & 7;
+    const int r = P / pw, c = P - r * pw;
+    const int gy = ya + r, gx = xa + c;
+    const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    const __nv_bfloat16* src = act + ((static_cast<size_t>(b) * H + (ok ? gy : 0)) * W + (ok ? gx : 0)) * kC + ch * 8;
+    cp16_zfill(base + P * 128 + ((ch ^ (P & 7)) << 4), src, ok ? 16 : 0);
+  }
+}
+
+// =================================================================================================== conv_up (K2)
+// out[b, c, 2i+py, 2j+px] = bias[c] + sum_{dy,dx,p} lo[b, i+dy, j+dx, p] * W[p, c, py+1-2dy, px+1-2dx]
+// Per 16-pixel M tile and channel chunk: one A fragment per shift (dy,dx), two accumulator tiles (py = 0 / 1) whose 8
+// columns are (px, c) pairs; a shift with dy = -1 feeds only py = 0, dy = +1 only py = 1, dy = 0 both: 12 MMAs per chunk.
+constexpr int kUpPH = kTH + 2, kUpPW = kTW + 2;
+constexpr int kUpTileBytes = kUpPH * kUpPW * 128;            // 78336
+constexpr int kUpFragBytes = 12 * 4 * 32 * 8;                // (py, shift) x channel chunk x lane x {b0, b1}
+constexpr int kUpSmem = kUpTileBytes + kUpFragBytes;
+
+__global__ void __launch_bounds__(kThreads, 2)
+img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const float* __restrict__ Wt, const float* __restrict__ bias,
+                   void* __restrict__ out, int B, int H, int W, int Cimg, int flags) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* tile = smem;
+  uint2* bfrag = reinterpret_cast<uint2*>(smem + kUpTileBytes);
+  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, b = blockIdx.x / (tiles_x * tiles_y);
+  const int y0 = ty * kTH, x0 = tx * kTW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+
+  load_act_tile(tile, lo, b, H, W, y0 - 1, x0 - 1, kUpPH, kUpPW);
+  // B fragments: combo = py*6 + (dy - dymin(py))*3 + (dx+1); B[k = channel][n = px*Cimg + c]
+  for (int idx = threadIdx.x; idx < 12 * 4 * 32; idx += kThreads) {
+    const int l = idx & 31, kc = (idx >> 5) & 3, combo = idx >> 7;
+    const int py = combo / 6, rem = combo - py * 6;
+    const int dy = rem / 3 + (py == 0 ? -1 : 0), dx = rem % 3 - 1;
+    const int n = l >> 2, kq = l & 3;
+    const int px = n / Cimg, c = n - px * Cimg;
+    const int kh = py + 1 - 2 * dy, kw = px + 1 - 2 * dx;
+    float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (n < 2 * Cimg && kw >= 0 && kw <= 3) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int p = kc * 16 + kq * 2 + (e & 1) + (e >> 1) * 8;
+        v[e] = __ldg(Wt + ((static_cast<size_t>(p) * Cimg + c) * 4 + kh) * 4 + kw);
+      }
+    }
+    bfrag[idx] = make_uint2(bf2(v[0], v[1]), bf2(v[2], v[3]));
+  }
+  cp_commit_wait_all();
+  __syncthreads();
+
+  float acc[4][2][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[m][t][e] = 0.0f;
+  // ldmatrix row of this lane inside an M tile: pixel i = (lane & 7) + 8 * ((lane >> 3) & 1), k half = lane >> 4
+  const int li = (lane & 7) + ((lane >> 3) & 1) * 8, lk = lane >> 4;
+  const uint32_t tile_u32 = smem_u32(tile);
+  int P0[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) P0[m] = (2 * warp + (m >> 1) + 1) * kUpPW + (m & 1) * 16 + 1 + li;
+#pragma unroll 1
+  for (int kc = 0; kc < 4; ++kc) {
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        uint2 b0 = make_uint2(0u, 0u), b1 = make_uint2(0u, 0u);
+        if (dy <= 0) b0 = bfrag[(((dy + 1) * 3 + dx + 1) * 4 + kc) * 32 + lane];
+        if (dy >= 0) b1 = bfrag[((6 + dy * 3 + dx + 1) * 4 + kc) * 32 + lane];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int P = P0[m] + dy * kUpPW + dx;
+          uint32_t a[4];
+          ldsm_x4(a, tile_u32 + P * 128 + (((kc * 2 + lk) ^ (P & 7)) << 4));
+          if (dy <= 0) mma16816(acc[m][0], a, b0.x, b0.y);
+          if (dy >= 0) mma16816(acc[m][1], a, b1.x, b1.y);
+        }
+      }
+    }
+  }
+  __syncthreads();                       // the activation tile is dead: reuse it as the output staging buffer
+
+  // ---- epilogue: bias, tanh, layout / dtype of the output, staged so that global stores are whole 16-byte vectors
+  const int OH = 2 * H, OW = 2 * W;
+  const bool do_tanh = (flags & 1) != 0, unit = (flags & 2) != 0, u8 = (flags & 4) != 0, bgr = (flags & 8) != 0;
+  float* stf = reinterpret_cast<float*>(smem);
+  uint8_t* stb = smem;
+  float bv[kMaxCimg];
+#pragma unroll
+  for (int c = 0; c < kMaxCimg; ++c) bv[c] = (bias != nullptr && c < Cimg) ? __ldg(bias + c) : 0.0f;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int yl = 2 * warp + (m >> 1), xl0 = (m & 1) * 16;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = 2 * q + (e & 1);
+        if (n >= 2 * Cimg) continue;
+        const int px = n / Cimg, c = n - px * Cimg;
+        const int Yl = 2 * yl + t, Xl = 2 * (xl0 + g + (e >> 1) * 8) + px;
+        float v = acc[m][t][e] + bv[c];
+        if (do_tanh) v = tanhf(v);
+        if (u8) {
+          const float u = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
+          stb[(Yl * 64 + Xl) * Cimg + (bgr ? Cimg - 1 - c : c)] =
+              static_cast<uint8_t>(__float2uint_rz(fminf(fmaxf(u, 0.0f), 255.0f)));
+        } else if (unit) {
+          stf[(Yl * 64 + Xl) * Cimg + c] = (v + 1.0f) * 0.5f;
+        } else {
+          stf[(c * 32 + Yl) * 64 + Xl] = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int Y0 = 2 * y0, X0 = 2 * x0;
+  const int xvalid = min(64, OW - X0);           // multiple of 16 (W is a power of two >= 8)
+  if (u8) {
+    uint8_t* o = static_cast<uint8_t*>(out);
+    const int vec_row = 4 * Cimg;                // 16-byte vectors per staged row of 64*Cimg bytes
+    for (int idx = threadIdx.x; idx < 32 * vec_row; idx += kThreads) {
+      const int Yl = idx / vec_row, v = idx - Yl * vec_row;
+      if (Y0 + Yl >= OH || v * 16 >= xvalid * Cimg) continue;
+      *reinterpret_cast<uint4*>(o + (((static_cast<size_t>(b) * OH + Y0 + Yl) * OW + X0) * Cimg) + v * 16) =
+          *reinterpret_cast<const uint4*>(stb + Yl * 64 * Cimg + v * 16);
+    }
+  } else if (unit) {
+    float* o = static_cast<float*>(out);
+    const int vec_row = 16 * Cimg;
+    for (int idx = threadIdx.x; idx < 32 * vec_row; idx += kThreads) {
+      const int Yl = idx / vec_row, v = idx - Yl * vec_row;
+      if (Y0 + Yl >= OH || v * 4 >= xvalid * Cimg) continue;
+      *reinterpret_cast<float4*>(o + (((static_cast<size_t>(b) * OH + Y0 + Yl) * OW + X0) * Cimg) + v * 4) =
+          *reinterpret_cast<const float4*>(stf + Yl * 64 * Cimg + v * 4);
+    }
+  } else {
+    float* o = static_cast<float*>(out);
+    for (int idx = threadIdx.x; idx < Cimg * 32 * 16; idx += kThreads) {
+      const int v = idx & 15, Yl = (idx >> 4) & 31, c = idx >> 9;
+      if (Y0 + Yl >= OH || v * 4 >= xvalid) continue;
+      *reinterpret_cast<float4*>(o + ((static_cast<size_t>(b) * Cimg + c) * OH + Y0 + Yl) * OW + X0 + v * 4) =
+          *reinterpret_cast<const float4*>(stf + (c * 32 + Yl) * 64 + v * 4);
+    }
+  }
+}
+
+// =================================================================================================== conv_down (K1)
+// out[b, y, x, p] = act(bias[p] + sum_{c,kh,kw} img[b, c, 2y-1+kh, 2x-1+kw] * W[p, c, kh, kw])   (bf16 NHWC, 64 channels)
+// GEMM view: M = pixels, N = 64, K = Cimg*16 with one k16 step per image channel (k = kh*4 + kw): the A fragment of a lane
+// is four float2 loads of horizontally adjacent taps from the fp32 patch, the B fragments (the whole weight) live in
+// registers for the CTA's life.
+constexpr int kDownPatchBytes = kMaxCimg * kPR * kPitch * 4;          // 43520
+constexpr int kDownStageBytes = 8 * 16 * 128;                         // one 16-pixel x 64-channel bf16 tile per warp
+constexpr int kDownSmem = kDownPatchBytes + kDownStageBytes;
+
+__global__ void __launch_bounds__(kThreads, 2)
+img_conv_down_kernel(const float* __restrict__ x, const float* __restrict__ yimg, int mode,
+                     const float* __restrict__ eps_dev, const float* __restrict__ mul_dev, const float* __restrict__ Wt,
+                     const float* __restrict__ bias, float slope, const __nv_bfloat16* __restrict__ mask_src,
+                     float mask_slope, __nv_bfloat16* __restrict__ out, int B, int Cimg, int S) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* patch = reinterpret_cast<float*>(smem);
+  const int H = S / 2, W = S / 2;
+  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, b = blockIdx.x / (tiles_x * tiles_y);
+  const int y0 = ty * kTH, x0 = tx * kTW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const float eps = eps_dev ? __ldg(eps_dev) : 0.0f;
+  const float mul = mul_dev ? __ldg(mul_dev) : 1.0f;
+  load_img_patch(patch, x, yimg, mode, eps, mul, b, Cimg, S, y0, x0);
+  // B fragments: B[k = kh*4 + kw (channel c)][n = p]; lane holds k = 2q, 2q+1 (kh = q/2) and k + 8 (kh + 2), n = g
+  uint32_t breg[kMaxCimg][8][2];
+  const int kh0 = q >> 1, kw0 = (q & 1) * 2;
+#pragma unroll
+  for (int c = 0; c < kMaxCimg; ++c)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
+      if (c < Cimg) {
+        const float* wp = Wt + ((static_cast<size_t>(nt * 8 + g) * Cimg + c) * 4 + kh0) * 4 + kw0;
+        w0 = __ldg(wp); w1 = __ldg(wp + 1); w2 = __ldg(wp + 8); w3 = __ldg(wp + 9);
+      }
+      breg[c][nt][0] = bf2(w0, w1);
+      breg[c][nt][1] = bf2(w2, w3);
+    }
+  float bv[8][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    bv[nt][0] = bias ? __ldg(bias + nt * 8 + 2 * q) : 0.0f;
+    bv[nt][1] = bias ? __ldg(bias + nt * 8 + 2 * q + 1) : 0.0f;
+  }
+  __syncthreads();
+  uint8_t* stage = smem + kDownPatchBytes + warp * (16 * 128);
+#pragma unroll 1
+  for (int m = 0; m < 4; ++m) {
+    const int yl = 2 * warp + (m >> 1), xl0 = (m & 1) * 16;
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kMaxCimg; ++c) {
+      if (c < Cimg) {
+        const float* pr = patch + (c * kPR + 2 * yl + kh0) * kPitch + 2 * (xl0 + g) + kw0;
+        const float2 f0 = *reinterpret_cast<const float2*>(pr);                       // row g,     kh0
+        const float2 f1 = *reinterpret_cast<const float2*>(pr + 16);                  // row g + 8, kh0
+        const float2 f2 = *reinterpret_cast<const float2*>(pr + 2 * kPitch);          // row g,     kh0 + 2
+        const float2 f3 = *reinterpret_cast<const float2*>(pr + 2 * kPitch + 16);     // row g + 8, kh0 + 2
+        const uint32_t a[4] = {bf2(f0.x, f0.y), bf2(f1.x, f1.y), bf2(f2.x, f2.y), bf2(f3.x, f3.y)};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma16816(acc[nt], a, breg[c][nt][0], breg[c][nt][1]);
+      }
+    }
+    // epilogue: bias + LeakyReLU, bf16, swizzled per-warp staging (16 pixels x 128 B), then 16-byte global stores
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v0 = acc[nt][2 * h] + bv[nt][0], v1 = acc[nt][2 * h + 1] + bv[nt][1];
+        v0 = v0 > 0.0f ? v0 : v0 * slope;
+        v1 = v1 > 0.0f ? v1 : v1 * slope;
+        const int row = g + 8 * h;
+        *reinterpret_cast<uint32_t*>(stage + row * 128 + ((nt ^ (row & 7)) << 4) + q * 4) = bf2(v0, v1);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int vi = it * 32 + lane, row = vi >> 3, ch = vi & 7;
+      const int gy = y0 + yl, gx = x0 + xl0 + row;
+      if (gy < H && gx < W) {
+        uint4 v = *reinterpret_cast<const uint4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
+        const size_t o = ((static_cast<size_t>(b) * H + gy) * W + gx) * kC + ch * 8;
+        if (mask_src != nullptr) {          // LeakyReLU backward mask from a stored activation: out *= (m > 0 ? 1 : slope)
+          const uint4 mk = *reinterpret_cast<const uint4*>(mask_src + o);
+          const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk);
+          __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 mf = __bfloat1622float2(mh[e]);
+            float2 vf = __bfloat1622float2(vh[e]);
+            vf.x *= mf.x > 0.0f ? 1.0f : mask_slope;
+            vf.y *= mf.y > 0.0f ? 1.0f : mask_slope;
+            vh[e] = __floats2bfloat162_rn(vf.x, vf.y);
+          }
+        }
+        *reinterpret_cast<uint4*>(out + o) = v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// =================================================================================================== wgrad (K3)
+// part[cta][p][n] = sum over the CTA's tiles and pixels of act[b, y, x, p] * img'[b, c, 2y-1+kh, 2x-1+kw],
+// n = (c*2 + kh/2)*8 + (kh%2)*4 + kw; column 2*Cimg*8 holds sum act (the bias gradient of the 64-channel side).
+// GEMM view: M = p (64), N = taps, K = pixels.  A (p x pixel) comes transposed out of the activation tile with
+// ldmatrix.trans; B (pixel x tap) is gathered from the fp32 patch.  Warp w: pixel rows {w>>1, (w>>1)+4, ...} of the
+// tile, n tiles (w&1)*4 .. +3.  Fixed order everywhere: bit-reproducible.
+constexpr int kWgActBytes = kTH * kTW * 128;                   // 65536
+constexpr int kWgSmem = kWgActBytes + kDownPatchBytes;         // 109056
+constexpr int kWgN = 64;                                       // padded number of output columns
+
+__global__ void __launch_bounds__(kThreads, 2)
+img_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ x,
+                      const float* __restrict__ yimg, int mode, const float* __restrict__ eps_dev,
+                      const float* __restrict__ mul_dev, float* __restrict__ part, int B, int Cimg, int S) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* atile = smem;
+  float* patch = reinterpret_cast<float*>(smem + kWgActBytes);
+  const int H = S / 2, W = S / 2;
+  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
+  const int ntiles = B * tiles_x * tiles_y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int nh = warp & 1, kg = warp >> 1;
+  const float eps = eps_dev ? __ldg(eps_dev) : 0.0f;
+  const float mul = mul_dev ? __ldg(mul_dev) : 1.0f;
+  const int bias_nt = 2 * Cimg;                                 // n tile whose column 0 is the all-ones tap
+  float acc[4][4][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.0f;
+  const uint32_t atile_u32 = smem_u32(atile);
+  // ldmatrix.trans addressing: lanes 0-7 / 8-15 -> pixels 0-7, channel chunk 2m / 2m+1; lanes 16-31 -> pixels 8-15
+  const int lpx = (lane & 7) + (lane >> 4) * 8, lch = (lane >> 3) & 1;
+  const uint32_t one_bf2 = bf2(1.0f, 1.0f);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const int y0 = ty * kTH, x0 = tx * kTW;
+    __syncthreads();                                            // previous tile fully consumed
+    load_act_tile(atile, act, b, H, W, y0, x0, kTH, kTW);
+    load_img_patch(patch, x, yimg, mode, eps, mul, b, Cimg, S, y0, x0);
+    cp_commit_wait_all();
+    __syncthreads();
+#pragma unroll 1
+    for (int yl = kg; yl < kTH; yl += 4) {
+#pragma unroll 1
+      for (int xs = 0; xs < 2; ++xs) {
+        const int xl0 = xs * 16;
+        uint32_t a[4][4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int P = yl * kTW + xl0 + lpx;
+          ldsm_x4_trans(a[m], atile_u32 + P * 128 + (((2 * m + lch) ^ (P & 7)) << 4));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int nt = nh * 4 + j;
+          uint32_t b0, b1;
+          if (nt < bias_nt) {
+            const int c = nt >> 1, kh = (nt & 1) * 2 + (g >> 2), kw = g & 3;
+            const float* pr = patch + (c * kPR + 2 * yl + kh) * kPitch + 2 * (xl0 + 2 * q) + kw;
+            b0 = bf2(pr[0], pr[2]);                             // pixels xl0+2q, xl0+2q+1
+            b1 = bf2(pr[16], pr[18]);                           // pixels +8
+          } else if (nt == bias_nt) {
+            b0 = b1 = (g == 0) ? one_bf2 : 0u;
+          } else {
+            continue;
+          }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) mma16816(acc[m][j], a[m], b0, b1);
+        }
+      }
+    }
+  }
+  // cross-warp reduction over the four pixel groups (fixed order), then one [64][64] partial per CTA
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(smem);                  // [4 kg][64 p][64 n] = 64 KiB (the activation tile)
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int p = m * 16 + g + (e >> 1) * 8, n = (nh * 4 + j) * 8 + 2 * q + (e & 1);
+        red[(kg * 64 + p) * kWgN + n] = acc[m][j][e];
+      }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * kWgN; i += kThreads)
+    part[static_cast<size_t>(blockIdx.x) * 64 * kWgN + i] =
+        ((red[i] + red[64 * kWgN + i]) + red[2 * 64 * kWgN + i]) + red[3 * 64 * kWgN + i];
+}
+
+// dW[p][c][kh][kw] = acc*dW + sum_cta part;  dbias[p] = acc_b*dbias + sum_cta part[..][p][2*Cimg*8]
+__global__ void __launch_bounds__(256) img_wgrad_finish_kernel(const float* __restrict__ part, int nparts, int Cimg,
+                                                               float* __restrict__ dW, float acc,
+                                                               float* __restrict__ dbias, float acc_b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // over 64 * (Cimg*16 + 1)
+  const int per = Cimg * 16 + 1;
+  if (i >= 64 * per) return;
+  const int p = i / per, k = i - p * per;
+  int n;
+  if (k < Cimg * 16) {
+    const int c = k >> 4, kh = (k >> 2) & 3, kw = k & 3;
+    n = (c * 2 + (kh >> 1)) * 8 + (kh & 1) * 4 + kw;
+  } else {
+    n = 2 * Cimg * 8;
+    if (dbias == nullptr || n >= kWgN) return;
+  }
+  float s = 0.0f;
+  for (int r = 0; r < nparts; ++r) s += part[(static_cast<size_t>(r) * 64 + p) * kWgN + n];
+  if (k < Cimg * 16) dW[p * Cimg * 16 + k] = (acc != 0.0f ? acc * dW[p * Cimg * 16 + k] : 0.0f) + s;
+  else dbias[p] = (acc_b != 0.0f ? acc_b * dbias[p] : 0.0f) + s;
+}
+
+int ensure_img_attrs() {
+  static bool done = false;
+  if (!done) {
+    RG_CUDA(cudaFuncSetAttribute(img_conv_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
+    RG_CUDA(cudaFuncSetAttribute(img_conv_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDownSmem));
+    RG_CUDA(cudaFuncSetAttribute(img_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+    done = true;
+  }
+  return 0;
+}
+
+}  // namespace
+
+}  // namespace rg
+
+using namespace rg;
+
+extern "C" {
+
+int rg_img_conv_up(const void* lo, const float* W, const float* bias, int flags, int B, int H, int Wd, int Cp, int Cimg,
+                   void* out, rg_stream_t st) {
+  RG_CHECK_ARG(lo && W && out && B > 0 && Cp == kC && Cimg >= 1 && Cimg <= kMaxCimg && is_pow2(H) && is_pow2(Wd) &&
+                   H >= 8 && Wd >= 8,
+               "rg_img_conv_up: need 64 input channels, 1..4 image channels and power-of-two H, W >= 8 (Cp=%d Cimg=%d H=%d W=%d)",
+               Cp, Cimg, H, Wd);
+  if (int rc = ensure_img_attrs()) return rc;
+  const int grid = B * ceil_div(H, kTH) * ceil_div(Wd, kTW);
+  img_conv_up_kernel<<<grid, kThreads, kUpSmem, static_cast<cudaStream_t>(st)>>>(
+      static_cast<const __nv_bfloat16*>(lo), W, bias, out, B, H, Wd, Cimg, flags);
+  RG_LAUNCH_CHECK("rg_img_conv_up");
+  return 0;
+}
+
+int rg_img_conv_down(const float* x, const float* y, int mode, const float* eps_dev, const float* mul_dev,
+                     const float* W, const float* bias, float slope, const void* mask_src, float mask_slope, int B,
+                     int Cimg, int S, int Cp, void* out, rg_stream_t st) {
+  RG_CHECK_ARG(x && W && out && B > 0 && Cp == kC && Cimg >= 1 && Cimg <= kMaxCimg && is_pow2(S) && S >= 16 &&
+                   mode >= 0 && mode <= 2 && (mode == 0 || y != nullptr) && (mode != 1 || eps_dev != nullptr),
+               "rg_img_conv_down: need 64 output channels, 1..4 image channels, a power-of-two side >= 16, mode 0..2 "
+               "(Cp=%d Cimg=%d S=%d mode=%d)", Cp, Cimg, S, mode);
+  if (int rc = ensure_img_attrs()) return rc;
+  const int grid = B * ceil_div(S / 2, kTH) * ceil_div(S / 2, kTW);
+  img_conv_down_kernel<<<grid, kThreads, kDownSmem, static_cast<cudaStream_t>(st)>>>(
+      x, y, mode, eps_dev, mul_dev, W, bias, slope, static_cast<const __nv_bfloat16*>(mask_src), mask_slope,
+      static_cast<__nv_bfloat16*>(out), B, Cimg, S);
+  RG_LAUNCH_CHECK("rg_img_conv_down");
+  return 0;
+}
+
+size_t rg_img_conv_wgrad_ws_bytes(void) { return static_cast<size_t>(2 * num_sms()) * 64 * kWgN * sizeof(float); }
+
+int rg_img_conv_wgrad(const void* act, const float* x, const float* y, int mode, const float* eps_dev,
+                      const float* mul_dev, int B, int Cimg, int S, int Cp, void* ws, size_t ws_bytes, float* dW,
+                      float acc, float* dbias, float acc_bias, rg_stream_t st) {
+  RG_CHECK_ARG(act && x && dW && ws && B > 0 && Cp == kC && Cimg >= 1 && Cimg <= kMaxCimg && is_pow2(S) && S >= 16 &&
+                   mode >= 0 && mode <= 2 && (mode == 0 || y != nullptr) && (mode != 1 || eps_dev != nullptr) &&
+                   (dbias == nullptr || Cimg <= 3),
+               "rg_img_conv_wgrad: need 64 channels, 1..4 image channels (<= 3 with a fused bias gradient), a power-of-two "
+               "side >= 16, mode 0..2 (Cp=%d Cimg=%d S=%d mode=%d)", Cp, Cimg, S, mode);
+  if (int rc = ensure_img_attrs()) return rc;
+  const int ntiles = B * ceil_div(S / 2, kTH) * ceil_div(S / 2, kTW);
+  const int grid = std::min(ntiles, 2 * num_sms());
+  if (ws_bytes < static_cast<size_t>(grid) * 64 * kWgN * sizeof(float)) {
+    set_error("rg_img_conv_wgrad: workspace too small (need %zu bytes)", static_cast<size_t>(grid) * 64 * kWgN * 4);
+    return RG_EWORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(st);
+  img_conv_wgrad_kernel<<<grid, kThreads, kWgSmem, s>>>(static_cast<const __nv_bfloat16*>(act), x, y, mode, eps_dev,
+                                                        mul_dev, static_cast<float*>(ws), B, Cimg, S);
+  RG_LAUNCH_CHECK("rg_img_conv_wgrad");
+  img_wgrad_finish_kernel<<<ceil_div(64 * (Cimg * 16 + 1), 256), 256, 0, s>>>(static_cast<const float*>(ws), grid, Cimg,
+                                                                             dW, acc, dbias, acc_bias);
+  RG_LAUNCH_CHECK("rg_img_conv_wgrad(finish)");
+  return 0;
+}
+
+}  // extern "C"

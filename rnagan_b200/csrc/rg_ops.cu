@@ -1062,6 +1062,22 @@ __global__ void __launch_bounds__(256) slices_sum_kernel(const float* __restrict
     reinterpret_cast<float4*>(out)[i] = acc;
   }
 }
+// In-switch all-reduce of this rank's slice of a symmetric buffer through its MULTICAST address (NVLink SHARP):
+// multimem.ld_reduce returns the fp32 sum over every GPU's copy (reduced inside the NVSwitch), multimem.st writes the
+// result back into every GPU's copy.  Each element is reduced exactly once (by the rank that owns its slice) and then
+// broadcast, so all ranks end with bit-identical values.  Needs a barrier before (all contributions written) and
+// after (all stores landed); a handful of CTAs saturates the link, the rest of the GPU keeps computing.
+__global__ void __launch_bounds__(512) nvls_allreduce_kernel(float* mc, size_t n4) {
+  const size_t step = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += step) {
+    float* p = mc + i * 4;
+    float x, y, z, w;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "l"(p) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+  }
+}
 __global__ void cast_f32_kernel(const float* __restrict__ src, float* __restrict__ dst32, __nv_bfloat16* dst16, size_t n) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -1689,6 +1705,17 @@ int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st) {
   const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 8));
   clamp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(st)>>>(p, n, lo, hi);
   RG_LAUNCH_CHECK("rg_clamp");
+  return 0;
+}
+
+int rg_nvls_allreduce(float* mc, size_t offset, size_t n, int max_ctas, rg_stream_t st) {
+  RG_CHECK_ARG(mc && n > 0 && n % 4 == 0 && offset % 4 == 0 && reinterpret_cast<uintptr_t>(mc) % 16 == 0,
+               "rg_nvls_allreduce: need a 16-byte aligned multicast pointer and offset / n multiples of 4 floats");
+  const size_t n4 = n / 4;
+  const int cap = max_ctas > 0 ? max_ctas : 16;
+  const int grid = static_cast<int>(std::min<size_t>((n4 + 511) / 512, static_cast<size_t>(cap)));
+  nvls_allreduce_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(st)>>>(mc + offset, n4);
+  RG_LAUNCH_CHECK("rg_nvls_allreduce");
   return 0;
 }
 

@@ -40,6 +40,10 @@ FUSED_BWD = os.environ.get("RG_FUSED_BWD", "0") != "0"
 # contraction that produces dh0: ON -- measured -0.18 ms/step (3 of 5 rg_lrelu_bwd passes over 3 x 134 MB disappear, the
 # three merged-phase launches that carry the mask cost 0.04 ms more)
 FUSED_LRELU = os.environ.get("RG_FUSED_LRELU", "1") != "0"
+# the 3-channel image-side layers (critic layer 0, generator output layer) run as fused halo-tile kernels (csrc/rg_img.cu:
+# no materialised im2col / col2im buffers) whenever the wide side has 64 channels (step_channels = 64, every reference
+# config); RG_FUSED_IMG=0 keeps the im2col + GEMM + col2im path that other widths use
+FUSED_IMG = os.environ.get("RG_FUSED_IMG", "1") != "0"
 
 
 def _grad_of(p):
@@ -248,6 +252,7 @@ class GeneratorEngine:
             self.w_up9.append(torch.zeros(9, Cp // 64, 2, 4, 32, 64, dtype=BF16, device=dev) if Cs == 64 else None)
         self.w_colT_last = torch.zeros(16 * self.Cimg, self.Cn, dtype=BF16, device=dev)
         self.w_col_last = torch.empty(self.Cn, 64, dtype=BF16, device=dev)
+        self.fused_img = FUSED_IMG and self.Cn == 64 and self.Cimg <= 4 and self.size >= 16
         self.sync = GradSync(module)
         self.pack()
 
@@ -266,8 +271,9 @@ class GeneratorEngine:
                 ops.pack_up_from_down(wd, wu, c.weight.shape[1])
             if w9 is not None:
                 ops.pack_up9_from_down(wd, c.weight.shape[1], out=w9)
-        ops.pack_edge_t(self.conv_last.weight.detach(), self.w_colT_last)
-        ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
+        if not self.fused_img:               # the fused image-side kernels read the fp32 parameter itself
+            ops.pack_edge_t(self.conv_last.weight.detach(), self.w_colT_last)
+            ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
 
     def forward(self, lat, tag="g", training=True, out=None, unit_nhwc=False, u8=False, bgr=False):
         """lat: bf16 [B, E] -> fp32 NCHW image [B, Cimg, S, S]; keeps activations under `tag` for backward.
@@ -289,7 +295,12 @@ class GeneratorEngine:
             h = g(f"{tag}.h{l}", (B, H, H, Cs))
             bn.forward(a, h, B * H * H, training, tag=tag, stats=sws)
         if out is None:
-            out = g(f"{tag}.img", (B, 2 * H, 2 * H, self.Cimg) if unit_nhwc else (B, self.Cimg, 2 * H, 2 * H), F32)
+            out = g(f"{tag}.img", (B, 2 * H, 2 * H, self.Cimg) if (unit_nhwc or u8) else (B, self.Cimg, 2 * H, 2 * H),
+                    torch.uint8 if u8 else F32)
+        if self.fused_img:
+            ops.img_conv_up(h, self.conv_last.weight.detach(), out, bias=self.conv_last.bias.detach(), act_tanh=True,
+                            unit_nhwc=unit_nhwc, u8=u8, bgr=bgr)
+            return out
         col = g("fwd.colimg", (B * H * H, 16 * self.Cimg), F32)
         ops.conv_up_img_col(h, self.w_colT_last, self.Cimg, col, out, bias=self.conv_last.bias.detach(), act_tanh=True,
                             unit_nhwc=unit_nhwc, u8=u8, bgr=bgr)
@@ -302,22 +313,30 @@ class GeneratorEngine:
         n = self.n
         H = self.size // 2
         npix = B * H * H
-        col = g("bwd.col", (npix, 64))
-        ops.im2col_img(d_img, col, y=img, mode=2)                       # d(pre-tanh) in im2col form
         ops.img_channel_sum(d_img, _grad_of(self.conv_last.bias), y=img, mode=2, acc=0.0)
         hn = g(f"{tag}.h{n}", (B, H, H, self.Cn))
-        dcol = g("bwd.dcol", (self.Cn, 64), F32)
-        ops.gemm_tn(hn.view(npix, self.Cn), col, out=dcol)
-        ops.unpack_edge_grad(dcol, _grad_of(self.conv_last.weight), acc=0.0)
-        self.sync.layer_done(self.conv_last.weight, self.conv_last.bias)
         dh = g(f"bwd.dh{n}", (B, H, H, self.Cn))
         # every contraction that produces dh for a BatchNorm'd layer stores du = dh * lrelu'(u) and sums it (fused)
         fused = self.bns[n - 1].bwd_ws()
-        if fused is not None:
-            ops.gemm_nt_bwd(col, self.w_col_last, dh.view(npix, self.Cn), stats=fused,
-                            aux=self.bns[n - 1].aux(g(f"{tag}.a{n}", (B, H, H, self.Cn)), tag))
+        if self.fused_img and fused is None:
+            # d(pre-tanh) = d_img * (1 - img^2) is formed while the image patch is staged (mode 2)
+            ops.img_conv_wgrad(hn, d_img, _grad_of(self.conv_last.weight), y=img, mode=2)
+            self.sync.layer_done(self.conv_last.weight, self.conv_last.bias)
+            ops.img_conv_down(d_img, self.conv_last.weight.detach(), dh, y=img, mode=2)
         else:
-            ops.gemm_nt(col, self.w_col_last, out=dh.view(npix, self.Cn))
+            if self.fused_img:               # opt-in RG_FUSED_BWD needs the packed operands of the GEMM path
+                ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
+            col = g("bwd.col", (npix, 64))
+            ops.im2col_img(d_img, col, y=img, mode=2)                       # d(pre-tanh) in im2col form
+            dcol = g("bwd.dcol", (self.Cn, 64), F32)
+            ops.gemm_tn(hn.view(npix, self.Cn), col, out=dcol)
+            ops.unpack_edge_grad(dcol, _grad_of(self.conv_last.weight), acc=0.0)
+            self.sync.layer_done(self.conv_last.weight, self.conv_last.bias)
+            if fused is not None:
+                ops.gemm_nt_bwd(col, self.w_col_last, dh.view(npix, self.Cn), stats=fused,
+                                aux=self.bns[n - 1].aux(g(f"{tag}.a{n}", (B, H, H, self.Cn)), tag))
+            else:
+                ops.gemm_nt(col, self.w_col_last, out=dh.view(npix, self.Cn))
         for l in range(n, 0, -1):
             c, bn = self.convs[l - 1], self.bns[l - 1]
             Cp, Cs = c.weight.shape[0], c.weight.shape[1]
@@ -495,6 +514,8 @@ class CriticEngine:
         self.tmpC = torch.zeros(max([self.C0] + [c.weight.shape[0] for c in self.convs]), dtype=F32, device=dev)
         self.gp_partial = torch.zeros(1024, dtype=F32, device=dev)
         self.gp_out = torch.zeros(3, dtype=F32, device=dev)
+        self.fused_img = FUSED_IMG and self.C0 == 64 and self.Cimg <= 3 and self.size >= 16
+        self._img_in = {}            # tag -> (x, y, mode, eps_dev): the image operand of the pass, for the layer-0 wgrad
         self.sync = GradSync(module)
         # critic step: real / fake passes share their weight- and input-gradient launches (see backward_pair)
         self.bufs.pair("real.col", "fake.col")
@@ -513,8 +534,9 @@ class CriticEngine:
 
     def pack(self, full=True):
         """See GeneratorEngine.pack: full=False right after the fused Adam step (w_down already re-emitted)."""
-        ops.pack_edge(self.conv0.weight.detach(), self.w_col0)
-        ops.pack_edge_t(self.conv0.weight.detach(), self.w_colT0)
+        if not self.fused_img:               # the fused image-side kernels read the fp32 parameter itself
+            ops.pack_edge(self.conv0.weight.detach(), self.w_col0)
+            ops.pack_edge_t(self.conv0.weight.detach(), self.w_colT0)
         if full:
             for p in _to_native(self._native_params):
                 self.sync.rebind(p)
@@ -531,18 +553,26 @@ class CriticEngine:
         return _up_operand(self, l, npix)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x=None, tag="d", training=True, col=None):
-        """x: fp32 NCHW image [B, Cimg, S, S] (or a prebuilt im2col `col`) -> critic output fp32 [B]."""
+    def forward(self, x, tag="d", training=True, mix=None):
+        """x: fp32 NCHW image [B, Cimg, S, S] -> critic output fp32 [B].
+        mix = (y, eps_dev): run on the gradient-penalty interpolate eps*x + (1-eps)*y (src/wgan_loss.py:376-380), which is
+        formed while the first layer stages the image -- never materialised."""
         g = self.bufs.get
         S = self.size
-        B = x.shape[0] if x is not None else col.shape[0] // ((S // 2) ** 2)
+        B = x.shape[0]
         H = S // 2
         npix = B * H * H
-        if col is None:
-            col = g(f"{tag}.col", (npix, 64))
-            ops.im2col_img(x, col)
+        y, eps_dev = mix if mix is not None else (None, None)
+        mode = 1 if mix is not None else 0
+        self._img_in[tag] = (x, y, mode, eps_dev)
         h = g(f"{tag}.h0", (B, H, H, self.C0))
-        ops.gemm_nt(col, self.w_col0, out=h.view(npix, self.C0), col_shift=self.conv0.bias.detach(), slope=SLOPE)
+        if self.fused_img:
+            ops.img_conv_down(x, self.conv0.weight.detach(), h, y=y, mode=mode, eps_dev=eps_dev,
+                              bias=self.conv0.bias.detach(), slope=SLOPE)
+        else:
+            col = g(f"{tag}.col", (npix, 64))
+            ops.im2col_img(x, col, y=y, mode=mode, eps_dev=eps_dev)
+            ops.gemm_nt(col, self.w_col0, out=h.view(npix, self.C0), col_shift=self.conv0.bias.detach(), slope=SLOPE)
         for l, (c, bn) in enumerate(zip(self.convs, self.bns), start=1):
             Cp = c.weight.shape[0]
             H //= 2
@@ -611,19 +641,37 @@ class CriticEngine:
         if not fuse0:
             ops.lrelu_bwd(dh, h0, SLOPE, da0, npix, self.C0)
         if params:
-            ops.col_sum(da0, npix, self.C0, self.tmpC, _grad_of(self.conv0.bias), acc)
-            col = g(f"{tag}.col", (npix, 64))
-            dcol = g("bwd.dcol", (self.C0, 64), F32)
-            ops.gemm_tn(da0.view(npix, self.C0), col, out=dcol)
-            ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=acc)
+            self._wgrad0(da0, tag, acc, acc)
             if final:
                 self.sync.layer_done(self.conv0.weight, self.conv0.bias)
         if want_dimg:
             dimg = g(f"{tag}.dimg", (B, self.Cimg, 2 * H, 2 * H), F32)
-            colimg = g("bwd.colimg", (npix, 16 * self.Cimg), F32)
-            ops.conv_up_img_col(da0, self.w_colT0, self.Cimg, colimg, dimg)
+            if self.fused_img:
+                ops.img_conv_up(da0, self.conv0.weight.detach(), dimg)
+            else:
+                colimg = g("bwd.colimg", (npix, 16 * self.Cimg), F32)
+                ops.conv_up_img_col(da0, self.w_colT0, self.Cimg, colimg, dimg)
             return dimg
         return None
+
+    def _wgrad0(self, da0, tag, acc_w, acc_b, img=None):
+        """Layer-0 weight (+ bias, when acc_b is not None) gradient of the pass saved under `tag`:
+        conv0.weight.grad = acc_w * grad + da0 (x) image operand of that pass (or the explicit `img` tuple)."""
+        x, y, mode, eps_dev, mul_dev = (img if img is not None else self._img_in[tag] + (None,))
+        B, H = da0.shape[0], da0.shape[1]
+        npix = B * H * H
+        gb = _grad_of(self.conv0.bias) if acc_b is not None else None
+        if self.fused_img:
+            ops.img_conv_wgrad(da0, x, _grad_of(self.conv0.weight), y=y, mode=mode, eps_dev=eps_dev, mul_dev=mul_dev,
+                               acc=acc_w, dbias=gb, acc_bias=acc_b or 0.0)
+            return
+        if gb is not None:
+            ops.col_sum(da0, npix, self.C0, self.tmpC, gb, acc_b)
+        col = self.bufs.get("bwd.col0", (npix, 64))
+        ops.im2col_img(x, col, y=y, mode=mode, eps_dev=eps_dev, mul_dev=mul_dev)
+        dcol = self.bufs.get("bwd.dcol", (self.C0, 64), F32)
+        ops.gemm_tn(da0.view(npix, self.C0), col, out=dcol)
+        ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=acc_w)
 
     def backward_pair(self, B, passes=(("real", -1.0), ("fake", 1.0))):
         """Critic-step backward of sum_b c_real*out_real[b] + c_fake*out_fake[b] (passes = ((tag, c*B), ...)) with
@@ -680,11 +728,9 @@ class CriticEngine:
         da0 = self.bufs.joint(f"{ta}.da0", (B, H, H, self.C0))
         if not FUSED_LRELU:
             ops.lrelu_bwd(dh0, h0, SLOPE, da0, 2 * npix, self.C0)
-        ops.col_sum(da0, 2 * npix, self.C0, self.tmpC, _grad_of(self.conv0.bias), 0.0)
-        col = self.bufs.joint(f"{ta}.col", (npix, 64))
-        dcol = g("bwd.dcol", (self.C0, 64), F32)
-        ops.gemm_tn(da0.view(2 * npix, self.C0), col, out=dcol)
-        ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=0.0)
+        # layer-0 weight / bias gradient: one launch per pass (their image operands are different tensors)
+        for i, (tag, _) in enumerate(passes):
+            self._wgrad0(g(f"{tag}.da0", (B, H, H, self.C0)), tag, float(i > 0), float(i > 0))
         self.sync.layer_done(self.conv0.weight, self.conv0.bias)
 
     # ------------------------------------------------------------------ gradient penalty
@@ -698,25 +744,23 @@ class CriticEngine:
         H0 = S // 2
         npix0 = B * H0 * H0
         # step 1: forward on x_hat = eps*real + (1-eps)*fake (train-mode BN, running stats updated)
-        col_x = g(f"{tag}.col", (npix0, 64))
-        ops.im2col_img(real, col_x, y=fake, mode=1, eps_dev=eps_dev)
-        self.forward(tag=tag, col=col_x)
+        self.forward(real, tag=tag, mix=(fake, eps_dev))
         # step 2: g = d(sum out)/d(x_hat), keeping du_l, da_l and the BN backward sums
         grad_x = self.backward(B, 1.0, tag=tag, params=False, want_dimg=True, keep_du=True)
         ops.gp_norm(grad_x, lambd, self.gp_partial, self.gp_out)
         seed = self.gp_out[1:2]
         # step 3: adjoint sweep bottom -> top, seeded with A_g = seed * g
-        col_g = g(f"{tag}.colg", (npix0, 64))
-        ops.im2col_img(grad_x, col_g, mode=0, mul_dev=seed)
         da0 = g(f"{tag}.da0", (B, H0, H0, self.C0))
         h0 = g(f"{tag}.h0", (B, H0, H0, self.C0))
-        dcol = g("bwd.dcol", (self.C0, 64), F32)
-        ops.gemm_tn(da0.view(npix0, self.C0), col_g, out=dcol)
-        ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=0.0)
-        A_da0 = g(f"{tag}.Ada0", (B, H0, H0, self.C0))
-        ops.gemm_nt(col_g, self.w_col0, out=A_da0.view(npix0, self.C0))
         A_dh = g(f"{tag}.Adh0", (B, H0, H0, self.C0))
-        ops.lrelu_bwd(A_da0, h0, SLOPE, A_dh, npix0, self.C0)
+        self._wgrad0(da0, tag, 0.0, None, img=(grad_x, None, 0, None, seed))      # da0 (x) A_g
+        if self.fused_img:                   # A_dh0 = conv(A_g; W0) * lrelu'(h0), mask applied in the store loop
+            ops.img_conv_down(grad_x, self.conv0.weight.detach(), A_dh, mul_dev=seed, mask_src=h0, mask_slope=SLOPE)
+        else:
+            col_g = g("bwd.col0", (npix0, 64))                                     # still holds im2col(seed * grad_x)
+            A_da0 = g(f"{tag}.Ada0", (B, H0, H0, self.C0))
+            ops.gemm_nt(col_g, self.w_col0, out=A_da0.view(npix0, self.C0))
+            ops.lrelu_bwd(A_da0, h0, SLOPE, A_dh, npix0, self.C0)
         H = H0
         for l in range(1, n + 1):
             c, bn = self.convs[l - 1], self.bns[l - 1]
@@ -773,9 +817,7 @@ class CriticEngine:
                     A_h = g(f"{tag}.Ah{l - 1}", (B, H, H, Cs))
                     ops.conv_up(T, wup, Cs, out=A_h)
                     ops.lrelu_bwd(A_h, h0, SLOPE, A_a0, npix0, self.C0)
-                ops.gemm_tn(A_a0.view(npix0, self.C0), col_x, out=dcol)
-                ops.unpack_edge_grad(dcol, _grad_of(self.conv0.weight), acc=1.0)
-                ops.col_sum(A_a0, npix0, self.C0, self.tmpC, _grad_of(self.conv0.bias), 0.0)
+                self._wgrad0(A_a0, tag, 1.0, 0.0)                   # + A_a0 (x) x_hat, and the bias gradient
                 self.sync.layer_done(self.conv0.weight, self.conv0.bias)
         return self.gp_out
 

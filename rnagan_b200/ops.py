@@ -423,6 +423,45 @@ def conv_up_img_col(lo, w_colT, Cimg, col, out, bias=None, act_tanh=False, unit_
     return out
 
 
+# ---- fused image-side convolutions (csrc/rg_img.cu): need 64 channels on the wide side
+def img_conv_up(lo, W, out, bias=None, act_tanh=False, unit_nhwc=False, u8=False, bgr=False):
+    """lo bf16 [B, H, W, 64], W fp32 [64, Cimg, 4, 4] -> out: fp32 NCHW [B, Cimg, 2H, 2W] (default), fp32 NHWC (x+1)/2
+    (unit_nhwc) or uint8 NHWC trunc(255 (x+1)/2) (u8).  ConvTranspose2d(64, Cimg, 4, 2, 1) + bias + tanh."""
+    _chk(lo, BF16, "lo"); _chk(W, F32, "W")
+    B, H, Wd, Cp = lo.shape
+    Cimg = W.shape[1]
+    flags = int(act_tanh) | (2 if unit_nhwc else 0) | (4 if u8 else 0) | (8 if bgr else 0)
+    _prof("img_conv_up", 2.0 * B * H * Wd * Cp * 16 * Cimg, lambda: _lib.check(
+        _lib.lib().rg_img_conv_up(_p(lo), _p(W), _p(bias), flags, B, H, Wd, Cp, Cimg, _p(out), _st()), "rg_img_conv_up"))
+    return out
+
+
+def img_conv_down(x, W, out, y=None, mode=0, eps_dev=None, mul_dev=None, bias=None, slope=1.0, mask_src=None,
+                  mask_slope=1.0):
+    """x fp32 NCHW [B, Cimg, S, S] (transformed per `mode`, see rg_img_conv_down), W fp32 [64, Cimg, 4, 4] ->
+    out bf16 [B, S/2, S/2, 64] = lrelu(conv2d(x', W, stride 2, pad 1) + bias) (* LeakyReLU' mask of mask_src)."""
+    _chk(x, F32, "x"); _chk(W, F32, "W"); _chk(out, BF16, "out")
+    B, Cimg, S, _ = x.shape
+    Cp = W.shape[0]
+    _prof("img_conv_down", 2.0 * B * (S // 2) ** 2 * Cp * 16 * Cimg, lambda: _lib.check(
+        _lib.lib().rg_img_conv_down(_p(x), _p(y), mode, _p(eps_dev), _p(mul_dev), _p(W), _p(bias), float(slope),
+                                    _p(mask_src), float(mask_slope), B, Cimg, S, Cp, _p(out), _st()),
+        "rg_img_conv_down"))
+    return out
+
+
+def img_conv_wgrad(act, x, dW, y=None, mode=0, eps_dev=None, mul_dev=None, acc=0.0, dbias=None, acc_bias=0.0):
+    """dW fp32 [64, Cimg, 4, 4] (contiguous) = acc*dW + sum act (x) x'@tap; optional dbias[64] = acc_bias*dbias + sum act."""
+    _chk(act, BF16, "act"); _chk(x, F32, "x"); _chk(dW, F32, "dW")
+    B, Cimg, S, _ = x.shape
+    L = _lib.lib()
+    ws = _workspace(L.rg_img_conv_wgrad_ws_bytes(), x.device)
+    _prof("img_conv_wgrad", 2.0 * B * (S // 2) ** 2 * 64 * 16 * Cimg, lambda: _lib.check(
+        L.rg_img_conv_wgrad(_p(act), _p(x), _p(y), mode, _p(eps_dev), _p(mul_dev), B, Cimg, S, act.shape[-1], _p(ws),
+                            ws.numel() * 4, _p(dW), float(acc), _p(dbias), float(acc_bias), _st()), "rg_img_conv_wgrad"))
+    return dW
+
+
 def unpack_edge_grad(dcol, dW, acc=0.0):
     Cp, Cimg = dW.shape[0], dW.shape[1]
     _lib.check(_lib.lib().rg_unpack_edge_grad(_p(dcol), _p(dW), Cp, Cimg, float(acc), _st()), "rg_unpack_edge_grad")
@@ -482,6 +521,11 @@ def slices_sum(stage, nparts, n, out):
     _lib.check(_lib.lib().rg_slices_sum(_p(stage), int(nparts), int(stage.stride(0)), int(n), _p(out), _st()),
                "rg_slices_sum")
     return out
+
+
+def nvls_allreduce(mc_ptr, offset, n, max_ctas=0):
+    """In-switch SUM of floats [offset, offset+n) of a symmetric buffer through its multicast address (int)."""
+    _lib.check(_lib.lib().rg_nvls_allreduce(int(mc_ptr), int(offset), int(n), int(max_ctas), _st()), "rg_nvls_allreduce")
 
 
 class AdamTable:

@@ -110,7 +110,7 @@ class PeerExchange:
     """SUM all-reduce of ranges of one flat fp32 buffer through peer-mapped memory and the copy engines (see above).
     Opt-in (RG_DP_EXCHANGE=ce); every rank must issue the same sequence of `allreduce` calls."""
 
-    def __init__(self, numel, device, group=None):
+    def __init__(self, numel, device, group=None, use_nvls=False):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("PeerExchange needs CUDA devices with peer access (there is no CPU path)")
@@ -123,8 +123,15 @@ class PeerExchange:
         self.hdl = symm.rendezvous(self.flat, group)
         self.peers = [self.flat if r == self.rank else self.hdl.get_buffer(r, (self.numel,), torch.float32, 0)
                       for r in range(self.world)]
+        # NVSwitch multicast mapping of the same buffer (0 when the fabric has no multicast support)
+        self.mc_ptr = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.nvls = use_nvls and self.mc_ptr != 0
+        if use_nvls and not self.nvls and self.rank == 0:
+            import warnings
+            warnings.warn("RG_DP_EXCHANGE=nvls: no multicast support on this fabric, using the copy-engine exchange")
         per = slice_bounds(self.numel, self.world)[0]
-        self.stage = torch.empty(self.world, max(per[1] - per[0], 4), dtype=torch.float32, device=device)
+        self.stage = None if self.nvls else torch.empty(self.world, max(per[1] - per[0], 4), dtype=torch.float32,
+                                                        device=device)
         self.stream = torch.cuda.Stream(device=device)
 
     @staticmethod
@@ -143,6 +150,18 @@ class PeerExchange:
         if lo % 4 != 0 or hi <= lo:
             raise ValueError(f"PeerExchange.allreduce: bad range [{lo}, {hi})")
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if self.nvls:
+            # in-switch reduction: this rank reduces + broadcasts its slice of the bucket through the multicast mapping
+            from . import ops
+            a, b = slice_bounds(hi - lo, self.world)[self.rank]
+            with torch.cuda.stream(self.stream):
+                self.hdl.barrier(channel=0)        # every rank's bucket is final and visible
+                if b > a:
+                    ops.nvls_allreduce(self.mc_ptr, lo + a, b - a)
+                self.hdl.barrier(channel=0)        # every slice has been written back to every copy
+                done = torch.cuda.Event()
+                done.record(self.stream)
+            return _EventHandle(done, self.device)
         with torch.cuda.stream(self.stream):
             self.hdl.barrier(channel=0)            # every rank's bucket is final
             exchange_pull_reduce(self.rank, self.world, self.peers, self.stage, lo, hi - lo, self._copy, self._reduce)
@@ -155,8 +174,10 @@ class PeerExchange:
 
 
 def exchange_mode():
-    """'nccl' (default) or 'ce' (RG_DP_EXCHANGE=ce: PeerExchange)."""
-    return os.environ.get("RG_DP_EXCHANGE", "nccl").lower()
+    """How data-parallel gradients are summed: 'ce' (default: PeerExchange over symmetric memory and the copy engines --
+    measured fastest at 2 and 8 B200s, profiles/r2_dp_exchange_ab_n*.txt), 'nvls' (PeerExchange with the in-switch
+    multimem reduction) or 'nccl' (torch.distributed all_reduce; always used on CPU / gloo)."""
+    return os.environ.get("RG_DP_EXCHANGE", "ce").lower()
 
 
 class GradSync:
@@ -182,8 +203,8 @@ class GradSync:
         # copies per bucket whatever its size, and most layers are tiny: RG_DP_BUCKET_MB (default 16) in that mode.
         self.bucket_floats = 0
         self._open = None
-        if self.world() > 1 and exchange_mode() == "ce" and params[0].device.type == "cuda":
-            self.xchg = PeerExchange(max(off, 4), params[0].device)
+        if self.world() > 1 and exchange_mode() in ("ce", "nvls") and params[0].device.type == "cuda":
+            self.xchg = PeerExchange(max(off, 4), params[0].device, use_nvls=exchange_mode() == "nvls")
             self.flat = self.xchg.flat
             self.bucket_floats = int(float(os.environ.get("RG_DP_BUCKET_MB", "16")) * (1 << 20)) // 4
         else:
