@@ -213,8 +213,12 @@ int rg_col2im_img(const float* col, int ldc, const float* bias, int act_tanh, in
  * (autograd.grad w.r.t. the interpolate, src/wgan_loss.py:34-41).  `flags` as rg_col2im_img: bit 0 tanh, bit 1 fp32 NHWC
  * (v+1)/2 (src/gan_utils.py:236-241), bit 2 uint8 NHWC trunc(255*(v+1)/2) (src/generate_tissue_images.py:127-129),
  * bit 3 reversed channel order with bit 2.  H, W: low-resolution side (powers of two >= 8). */
-int rg_img_conv_up(const void* lo, const float* W, const float* bias, int flags, int B, int H, int Wd, int Cp, int Cimg,
-                   void* out, rg_stream_t st);
+int rg_img_conv_up(const void* lo, const void* wfrag, const float* bias, int flags, int B, int H, int Wd, int Cp,
+                   int Cimg, void* out, rg_stream_t st);
+/* wfrag: the weight W fp32 [64][Cimg][4][4] re-arranged into per-lane mma.sync B fragments (bf16), rg_img_conv_up_pack_bytes()
+ * bytes; refresh after every change of W (12 KB, one tiny launch). */
+size_t rg_img_conv_up_pack_bytes(void);
+int rg_img_conv_up_pack(const float* W, int Cp, int Cimg, void* wfrag, rg_stream_t st);
 /* rg_img_conv_down: Conv2d(Cimg, 64, 4, 2, 1) (+bias, LeakyReLU(slope); slope 1 = none) = the critic's first block
  * (torchgan DCGANDiscriminator) and the input gradient of the generator's output block.  The image operand is
  * transformed while it is staged: mode 0: x * mul_dev[0] (mul_dev may be NULL); mode 1: eps_dev[0]*x + (1-eps_dev[0])*y,

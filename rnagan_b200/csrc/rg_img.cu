@@ -12,6 +12,7 @@
 // mma.sync.m16n8k16 bf16 fragments (fp32 accumulate) -- the tensor pipe is idle >90 % of the time here either way, so the
 // point of the MMA is only to keep the arithmetic off the critical path; tcgen05 / TMEM would buy nothing.
 #include <algorithm>
+#include <type_traits>
 #include "rg_host.cuh"
 #include "rg_ptx.cuh"
 #include <cuda_bf16.h>
@@ -35,6 +36,12 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// hardware tanh (MUFU.TANH): max relative error 2^-11, two orders below the bf16 operand rounding of the contraction
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t bf2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -47,33 +54,73 @@ __device__ __forceinline__ void cp_commit_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-constexpr int kTH = 16, kTW = 32;                 // low-resolution pixels per CTA tile (the 64-channel side)
-constexpr int kThreads = 256;                     // 8 warps: warp w owns tile rows 2w, 2w+1
+constexpr int kTH = 8, kTW = 32;                  // low-resolution pixels per CTA tile (the 64-channel side)
+constexpr int kThreads = 128;                     // 4 warps: warp w owns tile rows 2w, 2w+1
+constexpr int kCtasPerSm = 4;                     // small CTAs, several per SM: one CTA's tile load overlaps the others' math
 constexpr int kC = 64;                            // channels of the 64-channel side (step_channels)
 
 // ------------------------------------------------------------------------------------------------ image patch (fp32)
-// patch[c][r][x]: image rows 2*y0-1 .. 2*y0+2*kTH, columns 2*x0-1 .. 2*x0+2*kTW (zero outside the image), optionally
-// transformed while loading.  Row pitch 80 floats: the two patch rows a fragment load touches land 16 banks apart.
-constexpr int kPR = 2 * kTH + 2, kPC = 2 * kTW + 2, kPitch = 80;
+// patch[c][r][kPX + gxl]: image rows 2*y0-1 .. 2*y0+2*kTH (r = 0 .. kPR-1), columns gxl = gx - 2*x0 in [-1, 2*kTW] (zero
+// outside the image), optionally transformed while loading.  The 64 interior columns of a row are 16 aligned float4 loads
+// (all of a thread's loads are issued before the first use), the two halo columns are scalars.
+constexpr int kPR = 2 * kTH + 2, kPX = 4, kPitch = 72;
 constexpr int kMaxCimg = 4;
+
+__device__ __forceinline__ float img_xform(float t, float y, int mode, float eps, float mul) {
+  if (mode == 1) t = eps * t + (1.0f - eps) * y;
+  else if (mode == 2) t = t * (1.0f - y * y);
+  return t * mul;
+}
 
 // mode 0: x * mul;  1: eps*x + (1-eps)*y (gradient-penalty interpolate);  2: x * (1 - y^2) (tanh backward, y = tanh)
 __device__ __forceinline__ void load_img_patch(float* patch, const float* __restrict__ x, const float* __restrict__ y,
                                                int mode, float eps, float mul, int b, int Cimg, int S, int y0, int x0) {
-  const int rows = Cimg * kPR;
-  for (int idx = threadIdx.x; idx < rows * kPitch; idx += kThreads) {
-    const int cr = idx / kPitch, xx = idx - cr * kPitch;
-    const int c = cr / kPR, r = cr - c * kPR;
-    const int gy = 2 * y0 - 1 + r, gx = 2 * x0 - 1 + xx;
-    float t = 0.0f;
-    if (xx < kPC && gy >= 0 && gy < S && gx >= 0 && gx < S) {
-      const size_t o = ((static_cast<size_t>(b) * Cimg + c) * S + gy) * S + gx;
-      t = __ldg(x + o);
-      if (mode == 1) t = eps * t + (1.0f - eps) * __ldg(y + o);
-      else if (mode == 2) { const float th = __ldg(y + o); t = t * (1.0f - th * th); }
-      t *= mul;
+  const int nrows = Cimg * kPR;
+  const int nvec = nrows * 16;
+  const size_t img0 = static_cast<size_t>(b) * Cimg * S * S;
+  for (int base = 0; base < nvec; base += kThreads * 4) {
+    float4 xv[4], yv[4];
+    int dst[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * kThreads + threadIdx.x;
+      xv[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      yv[j] = xv[j];
+      dst[j] = -1;
+      if (i < nvec) {
+        const int row = i >> 4, v = i & 15;
+        const int c = row / kPR, r = row - c * kPR;
+        const int gy = 2 * y0 - 1 + r, gx = 2 * x0 + 4 * v;
+        dst[j] = row * kPitch + kPX + 4 * v;
+        if (gy >= 0 && gy < S && gx < S) {
+          const size_t o = img0 + (static_cast<size_t>(c) * S + gy) * S + gx;
+          xv[j] = __ldg(reinterpret_cast<const float4*>(x + o));
+          if (mode != 0) yv[j] = __ldg(reinterpret_cast<const float4*>(y + o));
+        }
+      }
     }
-    patch[idx] = t;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (dst[j] >= 0) {
+        float4 t;
+        t.x = img_xform(xv[j].x, yv[j].x, mode, eps, mul);
+        t.y = img_xform(xv[j].y, yv[j].y, mode, eps, mul);
+        t.z = img_xform(xv[j].z, yv[j].z, mode, eps, mul);
+        t.w = img_xform(xv[j].w, yv[j].w, mode, eps, mul);
+        *reinterpret_cast<float4*>(patch + dst[j]) = t;
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < nrows * 2; i += kThreads) {
+    const int row = i >> 1, gxl = (i & 1) ? 2 * kTW : -1;
+    const int c = row / kPR, r = row - c * kPR;
+    const int gy = 2 * y0 - 1 + r, gx = 2 * x0 + gxl;
+    float t = 0.0f;
+    if (gy >= 0 && gy < S && gx >= 0 && gx < S) {
+      const size_t o = img0 + (static_cast<size_t>(c) * S + gy) * S + gx;
+      t = img_xform(__ldg(x + o), mode != 0 ? __ldg(y + o) : 0.0f, mode, eps, mul);
+    }
+    patch[row * kPitch + kPX + gxl] = t;
   }
 }
 
@@ -98,13 +145,36 @@ __device__ __forceinline__ void load_act_tile(uint8_t* tile, const __nv_bfloat16
 // Per 16-pixel M tile and channel chunk: one A fragment per shift (dy,dx), two accumulator tiles (py = 0 / 1) whose 8
 // columns are (px, c) pairs; a shift with dy = -1 feeds only py = 0, dy = +1 only py = 1, dy = 0 both: 12 MMAs per chunk.
 constexpr int kUpPH = kTH + 2, kUpPW = kTW + 2;
-constexpr int kUpTileBytes = kUpPH * kUpPW * 128;            // 78336
+constexpr int kUpTileBytes = kUpPH * kUpPW * 128;            // 43520
 constexpr int kUpFragBytes = 12 * 4 * 32 * 8;                // (py, shift) x channel chunk x lane x {b0, b1}
 constexpr int kUpSmem = kUpTileBytes + kUpFragBytes;
 
-__global__ void __launch_bounds__(kThreads, 2)
-img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const float* __restrict__ Wt, const float* __restrict__ bias,
-                   void* __restrict__ out, int B, int H, int W, int Cimg, int flags) {
+// B fragments of conv_up, ready for mma.sync: entry ((combo*4 + kc)*32 + lane) = {b0, b1} with
+// combo = py*6 + (dy - dymin(py))*3 + (dx+1) and B[k = channel][n = px*Cimg + c] = W[k][c][py+1-2dy][px+1-2dx]
+__global__ void img_up_pack_kernel(const float* __restrict__ Wt, int Cimg, uint2* __restrict__ bfrag) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 12 * 4 * 32) return;
+  const int l = idx & 31, kc = (idx >> 5) & 3, combo = idx >> 7;
+  const int py = combo / 6, rem = combo - py * 6;
+  const int dy = rem / 3 + (py == 0 ? -1 : 0), dx = rem % 3 - 1;
+  const int n = l >> 2, kq = l & 3;
+  const int px = n / Cimg, c = n - px * Cimg;
+  const int kh = py + 1 - 2 * dy, kw = px + 1 - 2 * dx;
+  float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (n < 2 * Cimg && kw >= 0 && kw <= 3) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int p = kc * 16 + kq * 2 + (e & 1) + (e >> 1) * 8;
+      v[e] = Wt[((static_cast<size_t>(p) * Cimg + c) * 4 + kh) * 4 + kw];
+    }
+  }
+  bfrag[idx] = make_uint2(bf2(v[0], v[1]), bf2(v[2], v[3]));
+}
+
+template <int Cimg>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const uint2* __restrict__ bfrag_g, const float* __restrict__ bias,
+                   void* __restrict__ out, int B, int H, int W, int flags) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* tile = smem;
   uint2* bfrag = reinterpret_cast<uint2*>(smem + kUpTileBytes);
@@ -115,23 +185,10 @@ img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const float* __restrict
   const int g = lane >> 2, q = lane & 3;
 
   load_act_tile(tile, lo, b, H, W, y0 - 1, x0 - 1, kUpPH, kUpPW);
-  // B fragments: combo = py*6 + (dy - dymin(py))*3 + (dx+1); B[k = channel][n = px*Cimg + c]
-  for (int idx = threadIdx.x; idx < 12 * 4 * 32; idx += kThreads) {
-    const int l = idx & 31, kc = (idx >> 5) & 3, combo = idx >> 7;
-    const int py = combo / 6, rem = combo - py * 6;
-    const int dy = rem / 3 + (py == 0 ? -1 : 0), dx = rem % 3 - 1;
-    const int n = l >> 2, kq = l & 3;
-    const int px = n / Cimg, c = n - px * Cimg;
-    const int kh = py + 1 - 2 * dy, kw = px + 1 - 2 * dx;
-    float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (n < 2 * Cimg && kw >= 0 && kw <= 3) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int p = kc * 16 + kq * 2 + (e & 1) + (e >> 1) * 8;
-        v[e] = __ldg(Wt + ((static_cast<size_t>(p) * Cimg + c) * 4 + kh) * 4 + kw);
-      }
-    }
-    bfrag[idx] = make_uint2(bf2(v[0], v[1]), bf2(v[2], v[3]));
+  {
+    const uint32_t fb = smem_u32(bfrag);
+    for (int i = threadIdx.x; i < kUpFragBytes / 16; i += kThreads)
+      cp16_zfill(fb + i * 16, reinterpret_cast<const uint8_t*>(bfrag_g) + i * 16, 16);
   }
   cp_commit_wait_all();
   __syncthreads();
@@ -176,62 +233,78 @@ img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const float* __restrict
   const bool do_tanh = (flags & 1) != 0, unit = (flags & 2) != 0, u8 = (flags & 4) != 0, bgr = (flags & 8) != 0;
   float* stf = reinterpret_cast<float*>(smem);
   uint8_t* stb = smem;
-  float bv[kMaxCimg];
+  // this lane's two accumulator columns n = 2q, 2q+1 are fixed: (px, c) and the bias are per-lane constants
+  int npx[2], nc[2];
+  float nb[2];
+  bool nvalid[2];
 #pragma unroll
-  for (int c = 0; c < kMaxCimg; ++c) bv[c] = (bias != nullptr && c < Cimg) ? __ldg(bias + c) : 0.0f;
+  for (int e = 0; e < 2; ++e) {
+    const int n = 2 * q + e;
+    nvalid[e] = n < 2 * Cimg;
+    npx[e] = n / Cimg;
+    nc[e] = n - npx[e] * Cimg;
+    nb[e] = (bias != nullptr && nvalid[e]) ? __ldg(bias + nc[e]) : 0.0f;
+  }
+  // mode: 0 fp32 NCHW, 1 fp32 NHWC unit range, 2 uint8 NHWC -- one specialised staging loop each
+  auto stage_out = [&](auto mode_tag) {
+    constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    const int yl = 2 * warp + (m >> 1), xl0 = (m & 1) * 16;
+    for (int m = 0; m < 4; ++m) {
+      const int yl = 2 * warp + (m >> 1), xl0 = (m & 1) * 16;
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < 2; ++t) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int n = 2 * q + (e & 1);
-        if (n >= 2 * Cimg) continue;
-        const int px = n / Cimg, c = n - px * Cimg;
-        const int Yl = 2 * yl + t, Xl = 2 * (xl0 + g + (e >> 1) * 8) + px;
-        float v = acc[m][t][e] + bv[c];
-        if (do_tanh) v = tanhf(v);
-        if (u8) {
-          const float u = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
-          stb[(Yl * 64 + Xl) * Cimg + (bgr ? Cimg - 1 - c : c)] =
-              static_cast<uint8_t>(__float2uint_rz(fminf(fmaxf(u, 0.0f), 255.0f)));
-        } else if (unit) {
-          stf[(Yl * 64 + Xl) * Cimg + c] = (v + 1.0f) * 0.5f;
-        } else {
-          stf[(c * 32 + Yl) * 64 + Xl] = v;
+        for (int e = 0; e < 4; ++e) {
+          if (!nvalid[e & 1]) continue;
+          const int px = npx[e & 1], c = nc[e & 1];
+          const int Yl = 2 * yl + t, Xl = 2 * (xl0 + g + (e >> 1) * 8) + px;
+          float v = acc[m][t][e] + nb[e & 1];
+          if (do_tanh) v = tanh_fast(v);
+          if (MODE == 2) {
+            const float u = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
+            stb[(Yl * 64 + Xl) * Cimg + (bgr ? Cimg - 1 - c : c)] =
+                static_cast<uint8_t>(__float2uint_rz(fminf(fmaxf(u, 0.0f), 255.0f)));
+          } else if (MODE == 1) {
+            stf[(Yl * 64 + Xl) * Cimg + c] = (v + 1.0f) * 0.5f;
+          } else {
+            stf[(c * (2 * kTH) + Yl) * 64 + Xl] = v;
+          }
         }
       }
     }
-  }
+  };
+  if (u8) stage_out(std::integral_constant<int, 2>{});
+  else if (unit) stage_out(std::integral_constant<int, 1>{});
+  else stage_out(std::integral_constant<int, 0>{});
   __syncthreads();
   const int Y0 = 2 * y0, X0 = 2 * x0;
   const int xvalid = min(64, OW - X0);           // multiple of 16 (W is a power of two >= 8)
+  constexpr int kOutRows = 2 * kTH;
   if (u8) {
     uint8_t* o = static_cast<uint8_t*>(out);
     const int vec_row = 4 * Cimg;                // 16-byte vectors per staged row of 64*Cimg bytes
-    for (int idx = threadIdx.x; idx < 32 * vec_row; idx += kThreads) {
-      const int Yl = idx / vec_row, v = idx - Yl * vec_row;
-      if (Y0 + Yl >= OH || v * 16 >= xvalid * Cimg) continue;
-      *reinterpret_cast<uint4*>(o + (((static_cast<size_t>(b) * OH + Y0 + Yl) * OW + X0) * Cimg) + v * 16) =
-          *reinterpret_cast<const uint4*>(stb + Yl * 64 * Cimg + v * 16);
+    for (int Yl = warp; Yl < kOutRows; Yl += kThreads / 32) {
+      if (Y0 + Yl >= OH) break;
+      for (int v = lane; v < vec_row && v * 16 < xvalid * Cimg; v += 32)
+        *reinterpret_cast<uint4*>(o + (((static_cast<size_t>(b) * OH + Y0 + Yl) * OW + X0) * Cimg) + v * 16) =
+            *reinterpret_cast<const uint4*>(stb + Yl * 64 * Cimg + v * 16);
     }
   } else if (unit) {
     float* o = static_cast<float*>(out);
     const int vec_row = 16 * Cimg;
-    for (int idx = threadIdx.x; idx < 32 * vec_row; idx += kThreads) {
-      const int Yl = idx / vec_row, v = idx - Yl * vec_row;
-      if (Y0 + Yl >= OH || v * 4 >= xvalid * Cimg) continue;
-      *reinterpret_cast<float4*>(o + (((static_cast<size_t>(b) * OH + Y0 + Yl) * OW + X0) * Cimg) + v * 4) =
-          *reinterpret_cast<const float4*>(stf + Yl * 64 * Cimg + v * 4);
+    for (int Yl = warp; Yl < kOutRows; Yl += kThreads / 32) {
+      if (Y0 + Yl >= OH) break;
+      for (int v = lane; v < vec_row && v * 4 < xvalid * Cimg; v += 32)
+        *reinterpret_cast<float4*>(o + (((static_cast<size_t>(b) * OH + Y0 + Yl) * OW + X0) * Cimg) + v * 4) =
+            *reinterpret_cast<const float4*>(stf + Yl * 64 * Cimg + v * 4);
     }
   } else {
     float* o = static_cast<float*>(out);
-    for (int idx = threadIdx.x; idx < Cimg * 32 * 16; idx += kThreads) {
-      const int v = idx & 15, Yl = (idx >> 4) & 31, c = idx >> 9;
+    for (int idx = threadIdx.x; idx < Cimg * kOutRows * 16; idx += kThreads) {
+      const int v = idx & 15, Yl = (idx >> 4) & (kOutRows - 1), c = idx / (16 * kOutRows);
       if (Y0 + Yl >= OH || v * 4 >= xvalid) continue;
       *reinterpret_cast<float4*>(o + ((static_cast<size_t>(b) * Cimg + c) * OH + Y0 + Yl) * OW + X0 + v * 4) =
-          *reinterpret_cast<const float4*>(stf + (c * 32 + Yl) * 64 + v * 4);
+          *reinterpret_cast<const float4*>(stf + (c * kOutRows + Yl) * 64 + v * 4);
     }
   }
 }
@@ -242,10 +315,10 @@ img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const float* __restrict
 // is four float2 loads of horizontally adjacent taps from the fp32 patch, the B fragments (the whole weight) live in
 // registers for the CTA's life.
 constexpr int kDownPatchBytes = kMaxCimg * kPR * kPitch * 4;          // 43520
-constexpr int kDownStageBytes = 8 * 16 * 128;                         // one 16-pixel x 64-channel bf16 tile per warp
+constexpr int kDownStageBytes = (kThreads / 32) * 16 * 128;            // one 16-pixel x 64-channel bf16 tile per warp
 constexpr int kDownSmem = kDownPatchBytes + kDownStageBytes;
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 img_conv_down_kernel(const float* __restrict__ x, const float* __restrict__ yimg, int mode,
                      const float* __restrict__ eps_dev, const float* __restrict__ mul_dev, const float* __restrict__ Wt,
                      const float* __restrict__ bias, float slope, const __nv_bfloat16* __restrict__ mask_src,
@@ -254,13 +327,11 @@ img_conv_down_kernel(const float* __restrict__ x, const float* __restrict__ yimg
   float* patch = reinterpret_cast<float*>(smem);
   const int H = S / 2, W = S / 2;
   const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
-  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, b = blockIdx.x / (tiles_x * tiles_y);
-  const int y0 = ty * kTH, x0 = tx * kTW;
+  const int ntiles = B * tiles_x * tiles_y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
   const float eps = eps_dev ? __ldg(eps_dev) : 0.0f;
   const float mul = mul_dev ? __ldg(mul_dev) : 1.0f;
-  load_img_patch(patch, x, yimg, mode, eps, mul, b, Cimg, S, y0, x0);
   // B fragments: B[k = kh*4 + kw (channel c)][n = p]; lane holds k = 2q, 2q+1 (kh = q/2) and k + 8 (kh + 2), n = g
   uint32_t breg[kMaxCimg][8][2];
   const int kh0 = q >> 1, kw0 = (q & 1) * 2;
@@ -282,8 +353,14 @@ img_conv_down_kernel(const float* __restrict__ x, const float* __restrict__ yimg
     bv[nt][0] = bias ? __ldg(bias + nt * 8 + 2 * q) : 0.0f;
     bv[nt][1] = bias ? __ldg(bias + nt * 8 + 2 * q + 1) : 0.0f;
   }
-  __syncthreads();
   uint8_t* stage = smem + kDownPatchBytes + warp * (16 * 128);
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+  const int y0 = ty * kTH, x0 = tx * kTW;
+  __syncthreads();                                              // previous patch fully consumed
+  load_img_patch(patch, x, yimg, mode, eps, mul, b, Cimg, S, y0, x0);
+  __syncthreads();
 #pragma unroll 1
   for (int m = 0; m < 4; ++m) {
     const int yl = 2 * warp + (m >> 1), xl0 = (m & 1) * 16;
@@ -295,12 +372,12 @@ img_conv_down_kernel(const float* __restrict__ x, const float* __restrict__ yimg
 #pragma unroll
     for (int c = 0; c < kMaxCimg; ++c) {
       if (c < Cimg) {
-        const float* pr = patch + (c * kPR + 2 * yl + kh0) * kPitch + 2 * (xl0 + g) + kw0;
-        const float2 f0 = *reinterpret_cast<const float2*>(pr);                       // row g,     kh0
-        const float2 f1 = *reinterpret_cast<const float2*>(pr + 16);                  // row g + 8, kh0
-        const float2 f2 = *reinterpret_cast<const float2*>(pr + 2 * kPitch);          // row g,     kh0 + 2
-        const float2 f3 = *reinterpret_cast<const float2*>(pr + 2 * kPitch + 16);     // row g + 8, kh0 + 2
-        const uint32_t a[4] = {bf2(f0.x, f0.y), bf2(f1.x, f1.y), bf2(f2.x, f2.y), bf2(f3.x, f3.y)};
+        // tap (kh, kw) of output pixel (yl, xl) sits at patch row 2*yl + kh, column gxl = 2*xl - 1 + kw
+        const float* pr = patch + (c * kPR + 2 * yl + kh0) * kPitch + kPX - 1 + 2 * (xl0 + g) + kw0;
+        const uint32_t a[4] = {bf2(pr[0], pr[1]),                                     // row g,     kh0
+                               bf2(pr[16], pr[17]),                                   // row g + 8, kh0
+                               bf2(pr[2 * kPitch], pr[2 * kPitch + 1]),               // row g,     kh0 + 2
+                               bf2(pr[2 * kPitch + 16], pr[2 * kPitch + 17])};        // row g + 8, kh0 + 2
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) mma16816(acc[nt], a, breg[c][nt][0], breg[c][nt][1]);
       }
@@ -343,19 +420,20 @@ img_conv_down_kernel(const float* __restrict__ x, const float* __restrict__ yimg
     }
     __syncwarp();
   }
+  }
 }
 
 // =================================================================================================== wgrad (K3)
 // part[cta][p][n] = sum over the CTA's tiles and pixels of act[b, y, x, p] * img'[b, c, 2y-1+kh, 2x-1+kw],
 // n = (c*2 + kh/2)*8 + (kh%2)*4 + kw; column 2*Cimg*8 holds sum act (the bias gradient of the 64-channel side).
 // GEMM view: M = p (64), N = taps, K = pixels.  A (p x pixel) comes transposed out of the activation tile with
-// ldmatrix.trans; B (pixel x tap) is gathered from the fp32 patch.  Warp w: pixel rows {w>>1, (w>>1)+4, ...} of the
+// ldmatrix.trans; B (pixel x tap) is gathered from the fp32 patch.  Warp w: pixel rows {w>>1, (w>>1)+2, ...} of the
 // tile, n tiles (w&1)*4 .. +3.  Fixed order everywhere: bit-reproducible.
-constexpr int kWgActBytes = kTH * kTW * 128;                   // 65536
-constexpr int kWgSmem = kWgActBytes + kDownPatchBytes;         // 109056
+constexpr int kWgActBytes = kTH * kTW * 128;                   // 32768
+constexpr int kWgSmem = kWgActBytes + kDownPatchBytes;
 constexpr int kWgN = 64;                                       // padded number of output columns
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 img_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ x,
                       const float* __restrict__ yimg, int mode, const float* __restrict__ eps_dev,
                       const float* __restrict__ mul_dev, float* __restrict__ part, int B, int Cimg, int S) {
@@ -391,7 +469,7 @@ img_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ act, const float* __rest
     cp_commit_wait_all();
     __syncthreads();
 #pragma unroll 1
-    for (int yl = kg; yl < kTH; yl += 4) {
+    for (int yl = kg; yl < kTH; yl += kThreads / 64) {
 #pragma unroll 1
       for (int xs = 0; xs < 2; ++xs) {
         const int xl0 = xs * 16;
@@ -407,7 +485,7 @@ img_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ act, const float* __rest
           uint32_t b0, b1;
           if (nt < bias_nt) {
             const int c = nt >> 1, kh = (nt & 1) * 2 + (g >> 2), kw = g & 3;
-            const float* pr = patch + (c * kPR + 2 * yl + kh) * kPitch + 2 * (xl0 + 2 * q) + kw;
+            const float* pr = patch + (c * kPR + 2 * yl + kh) * kPitch + kPX - 1 + 2 * (xl0 + 2 * q) + kw;
             b0 = bf2(pr[0], pr[2]);                             // pixels xl0+2q, xl0+2q+1
             b1 = bf2(pr[16], pr[18]);                           // pixels +8
           } else if (nt == bias_nt) {
@@ -423,7 +501,7 @@ img_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ act, const float* __rest
   }
   // cross-warp reduction over the four pixel groups (fixed order), then one [64][64] partial per CTA
   __syncthreads();
-  float* red = reinterpret_cast<float*>(smem);                  // [4 kg][64 p][64 n] = 64 KiB (the activation tile)
+  float* red = reinterpret_cast<float*>(smem);                  // [2 kg][64 p][64 n] = 32 KiB (the activation tile)
 #pragma unroll
   for (int m = 0; m < 4; ++m)
 #pragma unroll
@@ -435,8 +513,7 @@ img_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ act, const float* __rest
       }
   __syncthreads();
   for (int i = threadIdx.x; i < 64 * kWgN; i += kThreads)
-    part[static_cast<size_t>(blockIdx.x) * 64 * kWgN + i] =
-        ((red[i] + red[64 * kWgN + i]) + red[2 * 64 * kWgN + i]) + red[3 * 64 * kWgN + i];
+    part[static_cast<size_t>(blockIdx.x) * 64 * kWgN + i] = red[i] + red[64 * kWgN + i];
 }
 
 // dW[p][c][kh][kw] = acc*dW + sum_cta part;  dbias[p] = acc_b*dbias + sum_cta part[..][p][2*Cimg*8]
@@ -464,7 +541,10 @@ __global__ void __launch_bounds__(256) img_wgrad_finish_kernel(const float* __re
 int ensure_img_attrs() {
   static bool done = false;
   if (!done) {
-    RG_CUDA(cudaFuncSetAttribute(img_conv_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
+    RG_CUDA(cudaFuncSetAttribute(img_conv_up_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
+    RG_CUDA(cudaFuncSetAttribute(img_conv_up_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
+    RG_CUDA(cudaFuncSetAttribute(img_conv_up_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
+    RG_CUDA(cudaFuncSetAttribute(img_conv_up_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
     RG_CUDA(cudaFuncSetAttribute(img_conv_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDownSmem));
     RG_CUDA(cudaFuncSetAttribute(img_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
     done = true;
@@ -480,7 +560,18 @@ using namespace rg;
 
 extern "C" {
 
-int rg_img_conv_up(const void* lo, const float* W, const float* bias, int flags, int B, int H, int Wd, int Cp, int Cimg,
+size_t rg_img_conv_up_pack_bytes(void) { return kUpFragBytes; }
+
+int rg_img_conv_up_pack(const float* W, int Cp, int Cimg, void* wfrag, rg_stream_t st) {
+  RG_CHECK_ARG(W && wfrag && Cp == kC && Cimg >= 1 && Cimg <= kMaxCimg,
+               "rg_img_conv_up_pack: need 64 input channels and 1..4 image channels (Cp=%d Cimg=%d)", Cp, Cimg);
+  img_up_pack_kernel<<<ceil_div(12 * 4 * 32, 256), 256, 0, static_cast<cudaStream_t>(st)>>>(W, Cimg,
+                                                                                          static_cast<uint2*>(wfrag));
+  RG_LAUNCH_CHECK("rg_img_conv_up_pack");
+  return 0;
+}
+
+int rg_img_conv_up(const void* lo, const void* W, const float* bias, int flags, int B, int H, int Wd, int Cp, int Cimg,
                    void* out, rg_stream_t st) {
   RG_CHECK_ARG(lo && W && out && B > 0 && Cp == kC && Cimg >= 1 && Cimg <= kMaxCimg && is_pow2(H) && is_pow2(Wd) &&
                    H >= 8 && Wd >= 8,
@@ -488,8 +579,15 @@ int rg_img_conv_up(const void* lo, const float* W, const float* bias, int flags,
                Cp, Cimg, H, Wd);
   if (int rc = ensure_img_attrs()) return rc;
   const int grid = B * ceil_div(H, kTH) * ceil_div(Wd, kTW);
-  img_conv_up_kernel<<<grid, kThreads, kUpSmem, static_cast<cudaStream_t>(st)>>>(
-      static_cast<const __nv_bfloat16*>(lo), W, bias, out, B, H, Wd, Cimg, flags);
+  const __nv_bfloat16* lop = static_cast<const __nv_bfloat16*>(lo);
+  const uint2* wf = static_cast<const uint2*>(W);
+  cudaStream_t s = static_cast<cudaStream_t>(st);
+  switch (Cimg) {
+    case 1: img_conv_up_kernel<1><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags); break;
+    case 2: img_conv_up_kernel<2><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags); break;
+    case 3: img_conv_up_kernel<3><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags); break;
+    default: img_conv_up_kernel<4><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags); break;
+  }
   RG_LAUNCH_CHECK("rg_img_conv_up");
   return 0;
 }
@@ -502,7 +600,7 @@ int rg_img_conv_down(const float* x, const float* y, int mode, const float* eps_
                "rg_img_conv_down: need 64 output channels, 1..4 image channels, a power-of-two side >= 16, mode 0..2 "
                "(Cp=%d Cimg=%d S=%d mode=%d)", Cp, Cimg, S, mode);
   if (int rc = ensure_img_attrs()) return rc;
-  const int grid = B * ceil_div(S / 2, kTH) * ceil_div(S / 2, kTW);
+  const int grid = std::min(B * ceil_div(S / 2, kTH) * ceil_div(S / 2, kTW), kCtasPerSm * num_sms());
   img_conv_down_kernel<<<grid, kThreads, kDownSmem, static_cast<cudaStream_t>(st)>>>(
       x, y, mode, eps_dev, mul_dev, W, bias, slope, static_cast<const __nv_bfloat16*>(mask_src), mask_slope,
       static_cast<__nv_bfloat16*>(out), B, Cimg, S);
@@ -510,7 +608,9 @@ int rg_img_conv_down(const float* x, const float* y, int mode, const float* eps_
   return 0;
 }
 
-size_t rg_img_conv_wgrad_ws_bytes(void) { return static_cast<size_t>(2 * num_sms()) * 64 * kWgN * sizeof(float); }
+size_t rg_img_conv_wgrad_ws_bytes(void) {
+  return static_cast<size_t>(kCtasPerSm * num_sms()) * 64 * kWgN * sizeof(float);
+}
 
 int rg_img_conv_wgrad(const void* act, const float* x, const float* y, int mode, const float* eps_dev,
                       const float* mul_dev, int B, int Cimg, int S, int Cp, void* ws, size_t ws_bytes, float* dW,
@@ -522,7 +622,7 @@ int rg_img_conv_wgrad(const void* act, const float* x, const float* y, int mode,
                "side >= 16, mode 0..2 (Cp=%d Cimg=%d S=%d mode=%d)", Cp, Cimg, S, mode);
   if (int rc = ensure_img_attrs()) return rc;
   const int ntiles = B * ceil_div(S / 2, kTH) * ceil_div(S / 2, kTW);
-  const int grid = std::min(ntiles, 2 * num_sms());
+  const int grid = std::min(ntiles, kCtasPerSm * num_sms());
   if (ws_bytes < static_cast<size_t>(grid) * 64 * kWgN * sizeof(float)) {
     set_error("rg_img_conv_wgrad: workspace too small (need %zu bytes)", static_cast<size_t>(grid) * 64 * kWgN * 4);
     return RG_EWORKSPACE;

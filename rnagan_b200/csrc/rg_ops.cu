@@ -87,22 +87,22 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int kRedRows = 4;                       // rows per batch per thread
-constexpr int kRedStageBytes = 2 * kRedRows * 256 * 16;   // per input tensor: double-buffered, 16 B per thread per row
 
 // Functor F: static K (sums), static NT (input tensors), `const bf16* ptr(int t)`, and
 // `void acc(const uint4 (&d)[NT], int c0, float (&acc)[K][8])`.
-// Loads go global -> shared with cp.async into thread-private slots, a batch of kRedRows rows ahead of the arithmetic
-// (double-buffered): every thread keeps 2 x NT x 4 x 16 bytes in flight without holding them in registers.  (Plain
-// register loads were sunk next to their uses by ptxas -- one row in flight per thread, 38-48 % of HBM peak.)
+// Every thread issues a batch of kRedRows x NT 16-byte streaming loads (ldu4: `asm volatile`, so ptxas keeps the whole
+// batch ahead of the arithmetic instead of sinking each load next to its use) and only then accumulates; 2-4 CTAs per
+// SM keep ~100 KiB per SM in flight.  (The previous version staged the rows in shared memory with cp.async: ncu showed
+// L1TEX at 88 % of its peak with DRAM at 45 % -- the staging traffic, not HBM, was the limit; profiles/r2_ncu_hbm_summary.txt.)
 template <class F>
-__global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int rows_per_block, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256, F::NT >= 3 ? 2 : (F::NT == 2 ? 3 : 4)) colreduce_stage1(F f, int M, int C, int rows_per_block, float* __restrict__ partial) {
   griddep_wait();
   griddep_launch();
   constexpr int K = F::K;
   constexpr int NT = F::NT;
   constexpr int R = kRedRows;
   extern __shared__ __align__(16) uint8_t smraw[];
-  float* sm = reinterpret_cast<float*>(smraw);   // after the row loop: [lanes][K][C] cross-lane reduction scratch
+  float* sm = reinterpret_cast<float*>(smraw);   // [lanes][K][C] cross-lane reduction scratch
   const int cgs = C >> 3;
   const int lanes = cgs >= 256 ? 1 : 256 / cgs;            // row lanes per block iteration
   const int rl = cgs >= 256 ? 0 : threadIdx.x / cgs;
@@ -110,10 +110,6 @@ __global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int r
   const bool active = cgs >= 256 ? true : (threadIdx.x < lanes * cgs);
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
-  // slot(buf, j, t) for this thread
-  auto slot = [&](int buf, int j, int t) -> uint4* {
-    return reinterpret_cast<uint4*>(smraw + (static_cast<size_t>((t * 2 + buf) * R + j) * 256 + threadIdx.x) * 16);
-  };
   for (int cg = cg0; cg < cgs; cg += 256) {
     float acc[K][8];
 #pragma unroll
@@ -123,36 +119,23 @@ __global__ void __launch_bounds__(256) colreduce_stage1(F f, int M, int C, int r
     if (active) {
       const int c0 = cg * 8;
       const int step = R * lanes;
-      int rb = r0 + rl;                      // first row of the batch being fetched
-      auto fetch = [&](int buf, int row0) {
+      int r = r0 + rl;
+      for (; r + (R - 1) * lanes < r1; r += step) {          // full batches: R x NT loads, then the arithmetic
+        uint4 d[R][NT];
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int r = row0 + j * lanes;
-          if (r < r1) {
+        for (int j = 0; j < R; ++j)
 #pragma unroll
-            for (int t = 0; t < NT; ++t) cp_async16(slot(buf, j, t), f.ptr(t) + static_cast<size_t>(r) * C + c0);
-          }
-        }
-        cp_async_commit();
-      };
-      fetch(0, rb);
-      int buf = 0;
-      for (int r = rb; r < r1; r += step, buf ^= 1) {
-        fetch(buf ^ 1, r + step);            // next batch (possibly empty) while this one is consumed
-        cp_async_wait<1>();
+          for (int t = 0; t < NT; ++t) d[j][t] = ldu4(f.ptr(t) + static_cast<size_t>(r + j * lanes) * C + c0);
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          if (r + j * lanes < r1) {
-            uint4 d[NT];
-#pragma unroll
-            for (int t = 0; t < NT; ++t) d[t] = *slot(buf, j, t);
-            f.acc(d, c0, acc);
-          }
-        }
+        for (int j = 0; j < R; ++j) f.acc(d[j], c0, acc);
       }
-      cp_async_wait<0>();
+      for (; r < r1; r += lanes) {                           // ragged tail, one row at a time
+        uint4 d[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) d[t] = ldu4(f.ptr(t) + static_cast<size_t>(r) * C + c0);
+        f.acc(d, c0, acc);
+      }
     }
-    if (lanes > 1) __syncthreads();          // staging slots are reused as reduction scratch below
     if (lanes == 1) {
 #pragma unroll
       for (int k = 0; k < K; ++k)
@@ -216,15 +199,15 @@ static ReducePlan plan_reduce(int M, int C, int K, int NT = 1) {
   ReducePlan p;
   const int cgs = C / 8;
   const int lanes = cgs >= 256 ? 1 : 256 / cgs;
-  // one wave of resident CTAs: the cp.async staging (NT x 32 KiB) limits residency to 4 / 3 / 2 CTAs per SM.
+  // one wave of resident CTAs: 4 / 3 / 2 per SM for 1 / 2 / 3 input tensors (register budget of the load batches)
   // (NT = 1 yields the most blocks: the workspace query uses it as the upper bound.)
   int target = num_sms() * (NT <= 1 ? 4 : (NT == 2 ? 3 : 2));
   int rpb = std::max(lanes * 8, ceil_div(M, target));
   rpb = ceil_div(rpb, lanes) * lanes;
   p.rows_per_block = rpb;
   p.blocks = ceil_div(M, rpb);
-  p.smem = lanes > 1 ? static_cast<size_t>(lanes) * K * C * sizeof(float) : 0;   // cross-lane scratch; run_colreduce
-  return p;                                                                       // adds the cp.async staging
+  p.smem = lanes > 1 ? static_cast<size_t>(lanes) * K * C * sizeof(float) : 0;   // cross-lane scratch
+  return p;
 }
 static size_t reduce_ws_floats(int M, int C, int K) {
   ReducePlan p = plan_reduce(M, C, K);
@@ -244,7 +227,7 @@ static int run_colreduce(F f, int M, int C, float* ws, size_t ws_bytes, float* o
     set_error("%s: reduction workspace too small (need %zu, have %zu)", name, need, ws_bytes);
     return RG_EWORKSPACE;
   }
-  const size_t smem = std::max(p.smem, static_cast<size_t>(F::NT) * kRedStageBytes);
+  const size_t smem = p.smem;
   if (smem > 48 * 1024) {
     static bool attr_done = false;   // per instantiation
     if (!attr_done) {
@@ -311,8 +294,14 @@ static int run_ew(F f, int M, int C, cudaStream_t st, const char* name) {
 
 // Same driver for functors with the load / apply split (`In load(row, c0)`, `void apply(const In&, row, c0)`):
 // four rows of loads are issued before the first store.
+template <class F, class = void>
+struct ew_min_ctas { static constexpr int value = 1; };
 template <class F>
-__global__ void __launch_bounds__(256) ew_split_kernel(F f, unsigned nvec, int cgs, int cg_shift) {
+struct ew_min_ctas<F, decltype(void(F::MIN_CTAS))> { static constexpr int value = F::MIN_CTAS; };
+
+
+template <class F>
+__global__ void __launch_bounds__(256, ew_min_ctas<F>::value) ew_split_kernel(F f, unsigned nvec, int cgs, int cg_shift) {
   griddep_wait();
   griddep_launch();
   const unsigned stride = gridDim.x * blockDim.x;
@@ -394,6 +383,7 @@ struct StatsF {   // sum a, sum a^2
 
 struct BnActF {   // h = lrelu(scale*a + shift)
   struct In { uint4 x; };
+  static constexpr int MIN_CTAS = 6;
   const __nv_bfloat16* a;
   __nv_bfloat16* h;
   const float* scale;
@@ -437,8 +427,15 @@ struct BwdReduceF {   // S(du), S(du*xhat)
   }
 };
 
-struct BwdApplyF {   // da = scale*(du - s1/M - xhat*s2/M) (+ add); optional du output
+// da = scale*(du - s1/M - xhat*s2/M) (+ add); optional du output.  With xhat = (a - mean)*rstd this is
+//   da = scale*du - k2*a + k0 (+ add),  k2 = scale*rstd*s2/M,  k0 = k2*mean - scale*s1/M:
+// four per-channel vectors (scale, shift for the mask, k2, k0) stay live across the row loop instead of six, and the
+// `add` operand is a template flag, so the kernel fits three CTAs per SM (ncu: it ran at 2 with 102 registers and 24 %
+// active warps, profiles/r2_ncu_hbm_summary.txt).
+template <bool HAS_ADD>
+struct BwdApplyF {
   struct In { uint4 g, x, ad; };
+  static constexpr int MIN_CTAS = 3;
   const __nv_bfloat16* dh;
   const __nv_bfloat16* a;
   const __nv_bfloat16* add;
@@ -452,22 +449,34 @@ struct BwdApplyF {   // da = scale*(du - s1/M - xhat*s2/M) (+ add); optional du 
     In d;
     d.g = ldu4(dh + off);
     d.x = ldu4(a + off);
-    d.ad = add ? ldu4(add + off) : make_uint4(0u, 0u, 0u, 0u);
+    if (HAS_ADD) d.ad = ldu4(add + off);
     return d;
   }
   __device__ __forceinline__ void apply(const In& in, size_t row, int c0) const {
     const size_t off = row * C + c0;
-    const Vec8 g = unpack8(in.g), x = unpack8(in.x), ad = unpack8(in.ad);
-    const Vec8 mu = ldf8(mean + c0), rs = ldf8(rstd + c0), sc = ldf8(scale + c0), sh = ldf8(shift + c0);
-    const Vec8 s1 = ldf8(sums + c0), s2 = ldf8(sums + C + c0);
+    const Vec8 g = unpack8(in.g), x = unpack8(in.x);
+    const Vec8 sc = ldf8(scale + c0), sh = ldf8(shift + c0);
+    Vec8 k2, k0;
+    {   // loop-invariant for this thread (its channel group is fixed): hoisted out of the row loop
+      const Vec8 mu = ldf8(mean + c0), rs = ldf8(rstd + c0), s1 = ldf8(sums + c0), s2 = ldf8(sums + C + c0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        k2.v[e] = sc.v[e] * rs.v[e] * s2.v[e] * invM;
+        k0.v[e] = k2.v[e] * mu.v[e] - sc.v[e] * s1.v[e] * invM;
+      }
+    }
     Vec8 o, d;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float u = fmaf(x.v[e], sc.v[e], sh.v[e]);
       const float du = u > 0.0f ? g.v[e] : g.v[e] * slope;
-      const float xh = (x.v[e] - mu.v[e]) * rs.v[e];
       d.v[e] = du;
-      o.v[e] = sc.v[e] * (du - s1.v[e] * invM - xh * s2.v[e] * invM) + ad.v[e];
+      o.v[e] = fmaf(sc.v[e], du, fmaf(-k2.v[e], x.v[e], k0.v[e]));
+    }
+    if (HAS_ADD) {
+      const Vec8 ad = unpack8(in.ad);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o.v[e] += ad.v[e];
     }
     st8(da + off, o);
     if (du_out) st8(du_out + off, d);
@@ -476,6 +485,7 @@ struct BwdApplyF {   // da = scale*(du - s1/M - xhat*s2/M) (+ add); optional du 
 
 struct LreluBwdF {   // da = dh * lrelu'(h)   (layer without BatchNorm: mask from the stored activation)
   struct In { uint4 g, x; };
+  static constexpr int MIN_CTAS = 6;
   const __nv_bfloat16* dh;
   const __nv_bfloat16* h;
   __nv_bfloat16* da;
@@ -532,6 +542,7 @@ struct GpApplyF {
   // A_dh = lrelu'(u) * gamma*r/M*(M*ggI - q1 - xhat*q2)
   // A_a  = gamma*r^2/M * [ xhat*(q1*s1/M - q3 + 3*s2*q2/M) + q2*(s1/M - gO) + s2*(q1/M - ggI) ]
   struct In { uint4 gi, x, go; };
+  static constexpr int MIN_CTAS = 2;
   const __nv_bfloat16* ggI;
   const __nv_bfloat16* a;
   const __nv_bfloat16* gO;
@@ -1481,8 +1492,14 @@ int rg_bn_bwd_apply(const void* dh, const void* a, const void* add, const float*
                     const float* scale, const float* shift, float slope, const float* sums, int M, int C, void* da,
                     void* du_out, rg_stream_t st) {
   RG_CHECK_ARG(dh && a && mean && rstd && scale && shift && sums && da, "rg_bn_bwd_apply: null pointer");
-  BwdApplyF f{static_cast<const bf16*>(dh), static_cast<const bf16*>(a), static_cast<const bf16*>(add),
-              static_cast<bf16*>(da), static_cast<bf16*>(du_out), mean, rstd, scale, shift, sums, slope, 1.0f / M, C};
+  if (add != nullptr) {
+    BwdApplyF<true> f{static_cast<const bf16*>(dh), static_cast<const bf16*>(a), static_cast<const bf16*>(add),
+                      static_cast<bf16*>(da), static_cast<bf16*>(du_out), mean, rstd, scale, shift, sums, slope,
+                      1.0f / M, C};
+    return run_ew_split(f, M, C, static_cast<cudaStream_t>(st), "rg_bn_bwd_apply");
+  }
+  BwdApplyF<false> f{static_cast<const bf16*>(dh), static_cast<const bf16*>(a), nullptr, static_cast<bf16*>(da),
+                     static_cast<bf16*>(du_out), mean, rstd, scale, shift, sums, slope, 1.0f / M, C};
   return run_ew_split(f, M, C, static_cast<cudaStream_t>(st), "rg_bn_bwd_apply");
 }
 

@@ -271,7 +271,9 @@ class GeneratorEngine:
                 ops.pack_up_from_down(wd, wu, c.weight.shape[1])
             if w9 is not None:
                 ops.pack_up9_from_down(wd, c.weight.shape[1], out=w9)
-        if not self.fused_img:               # the fused image-side kernels read the fp32 parameter itself
+        if self.fused_img:                   # the other fused image-side kernels read the fp32 parameter itself
+            self.w_up_img = ops.img_conv_up_pack(self.conv_last.weight.detach(), getattr(self, "w_up_img", None))
+        else:
             ops.pack_edge_t(self.conv_last.weight.detach(), self.w_colT_last)
             ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
 
@@ -298,8 +300,8 @@ class GeneratorEngine:
             out = g(f"{tag}.img", (B, 2 * H, 2 * H, self.Cimg) if (unit_nhwc or u8) else (B, self.Cimg, 2 * H, 2 * H),
                     torch.uint8 if u8 else F32)
         if self.fused_img:
-            ops.img_conv_up(h, self.conv_last.weight.detach(), out, bias=self.conv_last.bias.detach(), act_tanh=True,
-                            unit_nhwc=unit_nhwc, u8=u8, bgr=bgr)
+            ops.img_conv_up(h, self.w_up_img, out, bias=self.conv_last.bias.detach(), act_tanh=True,
+                            unit_nhwc=unit_nhwc, u8=u8, bgr=bgr, Cimg=self.Cimg)
             return out
         col = g("fwd.colimg", (B * H * H, 16 * self.Cimg), F32)
         ops.conv_up_img_col(h, self.w_colT_last, self.Cimg, col, out, bias=self.conv_last.bias.detach(), act_tanh=True,
@@ -534,7 +536,9 @@ class CriticEngine:
 
     def pack(self, full=True):
         """See GeneratorEngine.pack: full=False right after the fused Adam step (w_down already re-emitted)."""
-        if not self.fused_img:               # the fused image-side kernels read the fp32 parameter itself
+        if self.fused_img:                   # the other fused image-side kernels read the fp32 parameter itself
+            self.w_up_img0 = ops.img_conv_up_pack(self.conv0.weight.detach(), getattr(self, "w_up_img0", None))
+        else:
             ops.pack_edge(self.conv0.weight.detach(), self.w_col0)
             ops.pack_edge_t(self.conv0.weight.detach(), self.w_colT0)
         if full:
@@ -647,7 +651,7 @@ class CriticEngine:
         if want_dimg:
             dimg = g(f"{tag}.dimg", (B, self.Cimg, 2 * H, 2 * H), F32)
             if self.fused_img:
-                ops.img_conv_up(da0, self.conv0.weight.detach(), dimg)
+                ops.img_conv_up(da0, self.w_up_img0, dimg, Cimg=self.Cimg)
             else:
                 colimg = g("bwd.colimg", (npix, 16 * self.Cimg), F32)
                 ops.conv_up_img_col(da0, self.w_colT0, self.Cimg, colimg, dimg)

@@ -424,12 +424,25 @@ def conv_up_img_col(lo, w_colT, Cimg, col, out, bias=None, act_tanh=False, unit_
 
 
 # ---- fused image-side convolutions (csrc/rg_img.cu): need 64 channels on the wide side
-def img_conv_up(lo, W, out, bias=None, act_tanh=False, unit_nhwc=False, u8=False, bgr=False):
-    """lo bf16 [B, H, W, 64], W fp32 [64, Cimg, 4, 4] -> out: fp32 NCHW [B, Cimg, 2H, 2W] (default), fp32 NHWC (x+1)/2
-    (unit_nhwc) or uint8 NHWC trunc(255 (x+1)/2) (u8).  ConvTranspose2d(64, Cimg, 4, 2, 1) + bias + tanh."""
-    _chk(lo, BF16, "lo"); _chk(W, F32, "W")
+def img_conv_up_pack(W, out=None):
+    """W fp32 [64, Cimg, 4, 4] -> the packed mma.sync B-fragment table of img_conv_up (uint8 buffer)."""
+    _chk(W, F32, "W")
+    L = _lib.lib()
+    if out is None:
+        out = torch.empty(L.rg_img_conv_up_pack_bytes(), dtype=torch.uint8, device=W.device)
+    _lib.check(L.rg_img_conv_up_pack(_p(W), W.shape[0], W.shape[1], _p(out), _st()), "rg_img_conv_up_pack")
+    return out
+
+
+def img_conv_up(lo, W, out, bias=None, act_tanh=False, unit_nhwc=False, u8=False, bgr=False, Cimg=None):
+    """lo bf16 [B, H, W, 64]; W: fp32 [64, Cimg, 4, 4] (packed on the fly) or the table of img_conv_up_pack (then pass
+    Cimg) -> out: fp32 NCHW [B, Cimg, 2H, 2W] (default), fp32 NHWC (x+1)/2 (unit_nhwc) or uint8 NHWC trunc(255 (x+1)/2)
+    (u8).  ConvTranspose2d(64, Cimg, 4, 2, 1) + bias + tanh."""
+    _chk(lo, BF16, "lo")
     B, H, Wd, Cp = lo.shape
-    Cimg = W.shape[1]
+    if W.dtype == F32:
+        Cimg = W.shape[1]
+        W = img_conv_up_pack(W)
     flags = int(act_tanh) | (2 if unit_nhwc else 0) | (4 if u8 else 0) | (8 if bgr else 0)
     _prof("img_conv_up", 2.0 * B * H * Wd * Cp * 16 * Cimg, lambda: _lib.check(
         _lib.lib().rg_img_conv_up(_p(lo), _p(W), _p(bias), flags, B, H, Wd, Cp, Cimg, _p(out), _st()), "rg_img_conv_up"))
