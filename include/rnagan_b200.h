@@ -35,6 +35,7 @@ typedef void* rg_stream_t; /* cudaStream_t */
 #define RG_EARCH (-2)    /* device is not sm_100 */
 #define RG_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable or failed */
 #define RG_EWORKSPACE (-4) /* caller-supplied workspace too small */
+#define RG_ENOTFOUND (-5) /* rg_lmdb_get: no such key */
 
 int rg_version(void);
 const char* rg_last_error(void);
@@ -268,7 +269,7 @@ int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st);
  * a symmetric buffer (every rank's copy at the same offset), the calling rank reduces floats [offset, offset+n) --
  * multimem.ld_reduce (fp32 sum inside the switch) then multimem.st (broadcast to every copy).  Ranks call it for disjoint
  * slices between two barriers; replaces the NCCL all-reduce of G/D gradients (src/histopathology_gan.py runs one process;
- * SURVEY.md 8e shards by batch).  max_ctas bounds the SMs it may take (0: 16). */
+ * SURVEY.md 8e shards by batch).  max_ctas bounds the SMs it may take (0: 32). */
 int rg_nvls_allreduce(float* mc, size_t offset, size_t n, int max_ctas, rg_stream_t st);
 /* data-parallel gradient exchange (what DistributedDataParallel's all-reduce would do around the
  * reference): out[i] = sum over r < nparts of src[r * stride + i], r ascending -- the reduction step of the peer-to-peer
@@ -282,6 +283,20 @@ int rg_slices_sum(const float* src, int nparts, size_t stride, size_t n, float* 
 int rg_tiles_u8_to_nchw(const void* tiles, float* img, int B, int C, int S, int swap_rb, rg_stream_t st);
 /* (x+1)/2 and NCHW -> NHWC fp32 (src/gan_utils.py:236-241) */
 int rg_tiles_to_unit_nhwc(const float* img, float* out, int B, int C, int S, rg_stream_t st);
+
+/* ---- tile data path, host side (csrc/rg_data.cu -- no device work) -----------------------------------
+ * What PatchRNADataset gets from the C extensions `lmdb` and `lz4framed` (src/read_data.py:284-371):
+ * `lmdb.open(path, subdir=False, readonly=True, lock=False)` + `txn.get(key)` + `txn.stat()['entries']` (:314-320,
+ * :346-351) and `lz4framed.decompress(value)` (:318, :332).
+ * rg_lmdb_open: memory-maps one LMDB file read-only; NULL on failure (see rg_last_error()).
+ * rg_lmdb_get: *val points into the mapping (valid until rg_lmdb_close); 0, RG_ENOTFOUND or RG_EINVAL (corrupt tree). */
+void* rg_lmdb_open(const char* path);
+void rg_lmdb_close(void* db);
+int rg_lmdb_stat(void* db, unsigned long long* entries, unsigned* page_size, unsigned* depth);
+int rg_lmdb_get(void* db, const void* key, size_t key_len, const void** val, size_t* val_len);
+/* one LZ4 frame -> dst; returns the bytes written, -1 for a malformed frame, -2 when `cap` is too small (retry with a
+ * larger buffer); *content_size = the frame header's content size field or -1 */
+long long rg_lz4f_decompress(const void* src, size_t n, void* dst, size_t cap, long long* content_size);
 
 /* ---- betaVAE training step (config 5; src/betaVAE.py:96-115, 145-162, 216-236) ---------------------------- */
 /* dst = bf16(src * mul * scale), zero pad columns: train-mode Dropout(0.5) with the caller's keep mask (mul may be NULL) */

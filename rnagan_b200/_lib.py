@@ -11,7 +11,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RG_LIB_PATH") or os.path.join(_HERE, "librnagan_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["rg_gemm_api.cu", "rg_ops.cu", "rg_img.cu"]
+SOURCES = ["rg_gemm_api.cu", "rg_ops.cu", "rg_img.cu", "rg_data.cu"]
 
 _c = ctypes
 _vp, _i, _f, _sz = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t
@@ -84,6 +84,11 @@ SIGNATURES = {
     "rg_slices_sum": (_i, [_vp, _i, _sz, _sz, _vp, _vp]),
     "rg_nvls_allreduce": (_i, [_vp, _sz, _sz, _i, _vp]),
     "rg_tiles_u8_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "rg_lmdb_open": (_vp, [_c.c_char_p]),
+    "rg_lmdb_close": (None, [_vp]),
+    "rg_lmdb_stat": (_i, [_vp, _c.POINTER(_c.c_ulonglong), _c.POINTER(_c.c_uint), _c.POINTER(_c.c_uint)]),
+    "rg_lmdb_get": (_i, [_vp, _c.c_char_p, _sz, _c.POINTER(_vp), _c.POINTER(_sz)]),
+    "rg_lz4f_decompress": (_c.c_longlong, [_c.c_char_p, _sz, _vp, _sz, _c.POINTER(_c.c_longlong)]),
     "rg_tiles_to_unit_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rg_upsample2x_reflectpad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rg_upsample2x_reflectpad_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

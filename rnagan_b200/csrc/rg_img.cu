@@ -19,8 +19,6 @@
 
 namespace rg {
 
-namespace {
-
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
@@ -551,8 +549,6 @@ int ensure_img_attrs() {
   }
   return 0;
 }
-
-}  // namespace
 
 }  // namespace rg
 

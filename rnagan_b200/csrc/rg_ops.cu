@@ -1079,8 +1079,22 @@ __global__ void __launch_bounds__(256) slices_sum_kernel(const float* __restrict
 // broadcast, so all ranks end with bit-identical values.  Needs a barrier before (all contributions written) and
 // after (all stores landed); a handful of CTAs saturates the link, the rest of the GPU keeps computing.
 __global__ void __launch_bounds__(512) nvls_allreduce_kernel(float* mc, size_t n4) {
+  // a switch round trip costs microseconds: keep kU independent 16-byte reductions in flight per thread
+  constexpr int kU = 8;
   const size_t step = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += step) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + (kU - 1) * step < n4; i += kU * step) {
+    float4 v[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(mc + (i + u * step) * 4) : "memory");
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                   :: "l"(mc + (i + u * step) * 4), "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w) : "memory");
+  }
+  for (; i < n4; i += step) {
     float* p = mc + i * 4;
     float x, y, z, w;
     asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -1729,8 +1743,8 @@ int rg_nvls_allreduce(float* mc, size_t offset, size_t n, int max_ctas, rg_strea
   RG_CHECK_ARG(mc && n > 0 && n % 4 == 0 && offset % 4 == 0 && reinterpret_cast<uintptr_t>(mc) % 16 == 0,
                "rg_nvls_allreduce: need a 16-byte aligned multicast pointer and offset / n multiples of 4 floats");
   const size_t n4 = n / 4;
-  const int cap = max_ctas > 0 ? max_ctas : 16;
-  const int grid = static_cast<int>(std::min<size_t>((n4 + 511) / 512, static_cast<size_t>(cap)));
+  const int cap = max_ctas > 0 ? max_ctas : 32;
+  const int grid = static_cast<int>(std::min<size_t>((n4 + 8 * 512 - 1) / (8 * 512), static_cast<size_t>(cap)));
   nvls_allreduce_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(st)>>>(mc + offset, n4);
   RG_LAUNCH_CHECK("rg_nvls_allreduce");
   return 0;

@@ -130,3 +130,160 @@ class DevicePrefetcher:
 
     def __len__(self):
         return len(self.loader)
+
+
+# ------------------------------------------------------------------------------------------------ tile reader (host)
+# PatchRNADataset of the reference (src/read_data.py:266-372): one LMDB file per slide under
+# `{patch_data_path}/{wsi}/{wsi with .svs -> .db}`, key `__keys__` -> lz4-framed pickle of the patch keys, every other
+# value an lz4-framed pickle `(name, raw uint8 bytes, shape)` of a BGR tile.  The container formats are read by the
+# host functions of the C ABI (csrc/rg_data.cu); `pickle` is the standard library's.
+class LMDBFile:
+    """Read-only view of one LMDB file (`lmdb.open(path, subdir=False, readonly=True, lock=False)` +
+    `txn.get` / `txn.stat()['entries']`, src/read_data.py:314-320, 346-351)."""
+
+    def __init__(self, path):
+        from . import _lib
+        import os
+        self._L = _lib.lib()
+        self.path = path
+        self._h = self._L.rg_lmdb_open(os.fsencode(path))
+        if not self._h:
+            raise OSError(self._L.rg_last_error().decode("utf-8", "replace"))
+
+    def stat(self):
+        import ctypes
+        e, p, d = ctypes.c_ulonglong(), ctypes.c_uint(), ctypes.c_uint()
+        from . import _lib
+        _lib.check(self._L.rg_lmdb_stat(self._h, ctypes.byref(e), ctypes.byref(p), ctypes.byref(d)), "rg_lmdb_stat")
+        return {"entries": e.value, "psize": p.value, "depth": d.value}
+
+    def get(self, key, default=None):
+        """The value stored under `key` (bytes) as a bytes copy, or `default`."""
+        import ctypes
+        from . import _lib
+        val, n = ctypes.c_void_p(), ctypes.c_size_t()
+        rc = self._L.rg_lmdb_get(self._h, key, len(key), ctypes.byref(val), ctypes.byref(n))
+        if rc == -5:                                   # RG_ENOTFOUND
+            return default
+        _lib.check(rc, "rg_lmdb_get")
+        return ctypes.string_at(val.value, n.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rg_lmdb_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def lz4f_decompress(data):
+    """`lz4framed.decompress(data)` (src/read_data.py:318, 332): one LZ4 frame -> bytes."""
+    import ctypes
+    from . import _lib
+    L = _lib.lib()
+    size = ctypes.c_longlong(-1)
+    cap = max(1 << 16, 4 * len(data))
+    while True:
+        buf = ctypes.create_string_buffer(cap)
+        n = L.rg_lz4f_decompress(data, len(data), buf, cap, ctypes.byref(size))
+        if n >= 0:
+            return buf.raw[:n]
+        if n == -2 and cap < (1 << 34):
+            cap = max(2 * cap, size.value if size.value > 0 else 0)
+            continue
+        raise ValueError("lz4f_decompress: malformed LZ4 frame")
+
+
+class PatchRNADataset(torch.utils.data.Dataset):
+    """Drop-in for the reference's PatchRNADataset (src/read_data.py:266-372): same constructor arguments, same per-slide
+    patch sampling (`random.sample` on the global `random` generator, in CSV row order), same item dictionary
+    `{'image', 'rna_data', 'labels'}`.
+
+    `raw=True` (not in the reference) returns the tile as it is stored -- uint8 HWC, BGR -- for
+    `DevicePrefetcher(bgr=True)`, which normalises on the GPU; the default applies the reference's host path: BGR->RGB,
+    `permute(2, 0, 1)` and `transforms` (src/read_data.py:336-343)."""
+
+    def __init__(self, patch_data_path, csv_path, img_size, transforms=None, max_patches_total=300, quick=False, le=None,
+                 raw=False):
+        self.patch_data_path, self.csv_path, self.img_size = patch_data_path, csv_path, img_size
+        self.transforms, self.max_patches_total, self.quick, self.le, self.raw = transforms, max_patches_total, quick, le, raw
+        self.keys, self.images, self.filenames, self.labels, self.lmdbs_path, self.rna_data_arrays = [], [], [], [], [], []
+        self._open = {}
+        self._preprocess()
+
+    def _preprocess(self):
+        import os
+        import pickle
+        import random
+        import pandas as pd
+        if isinstance(self.csv_path, str):
+            csv_file = pd.read_csv(self.csv_path)
+            csv_file["patch_data_path"] = [self.patch_data_path] * csv_file.shape[0]
+            csv_file["labels"] = [0] * csv_file.shape[0]
+        else:
+            csv_file = self.csv_path
+        if self.quick:
+            csv_file = csv_file.sample(150)
+        rna_cols = [c for c in csv_file.columns if "rna_" in c]
+        for _, row in csv_file.iterrows():
+            wsi = row["wsi_file_name"]
+            rna = torch.tensor(row[rna_cols].values.astype(np.float32), dtype=torch.float32)
+            label = np.asarray(row["labels"])
+            if self.le is not None:
+                label = self.le.transform(label.reshape(-1, 1))
+            label = torch.tensor(label, dtype=torch.float32)
+            path = os.path.join(row["patch_data_path"], wsi, wsi.replace(".svs", ".db"))
+            try:
+                with LMDBFile(path) as db:
+                    n_patches = db.stat()["entries"] - 1
+                    keys = pickle.loads(lz4f_decompress(db.get(b"__keys__")))
+                picked = random.sample(list(range(n_patches)), min(n_patches, self.max_patches_total))
+            except Exception:
+                print("Error with db {}".format(path))
+                continue
+            for i in picked:
+                self.images.append(i)
+                self.filenames.append(wsi)
+                self.labels.append(label)
+                self.lmdbs_path.append(path)
+                self.keys.append(keys[i])
+                self.rna_data_arrays.append(rna)
+
+    def decompress_and_deserialize(self, lmdb_value):
+        import pickle
+        try:
+            _, img_arr, img_shape = pickle.loads(lz4f_decompress(lmdb_value))
+        except Exception:
+            return None
+        image = np.frombuffer(img_arr, dtype=np.uint8).reshape(img_shape)
+        if self.raw:
+            return torch.from_numpy(np.copy(image))                       # uint8 HWC, BGR as stored
+        return torch.from_numpy(np.ascontiguousarray(image[..., ::-1])).permute(2, 0, 1)   # cv2.COLOR_BGR2RGB + CHW
+
+    def __len__(self):
+        return len(self.images)
+
+    def _db(self, path):
+        db = self._open.get(path)
+        if db is None:
+            db = self._open[path] = LMDBFile(path)        # kept open per worker (the reference re-opens per item)
+        return db
+
+    def __getitem__(self, idx):
+        image = self.decompress_and_deserialize(self._db(self.lmdbs_path[idx]).get(self.keys[idx]))
+        if image is None:
+            print(self.lmdbs_path[idx])
+        elif not self.raw and self.transforms is not None:
+            image = self.transforms(image)
+        return {"image": image, "rna_data": self.rna_data_arrays[idx], "labels": self.labels[idx]}
+
+    def __getstate__(self):                               # DataLoader workers: handles are per process
+        st = dict(self.__dict__)
+        st["_open"] = {}
+        return st

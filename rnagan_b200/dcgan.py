@@ -10,7 +10,10 @@ Same constructor keywords, attributes (``encoding_dims``, ``label_type``, ``samp
 The ``nn`` layers inside ``self.model`` are PARAMETER CONTAINERS (fp32 masters, checkpoint layout); ``forward`` never
 calls them -- it runs rnagan_b200.engine on the CUDA kernels and raises when the module is not on a B200.
 Training goes through the loss objects' ``train_ops`` (rnagan_b200.wgan_loss), which drive the same engines with a
-hand-scheduled backward; autograd through ``forward`` is not provided.
+hand-scheduled backward.  ``forward`` is also differentiable ONCE through ``torch.autograd`` (``_GeneratorFn`` /
+``_CriticFn`` below: a custom ``override_train_ops`` or a feature-matching style loss can call ``loss.backward()``);
+double backward (``create_graph=True``, i.e. a gradient penalty written with autograd) is not -- that schedule exists
+only inside ``WassersteinGradientPenalty*.train_ops``.
 """
 from math import ceil, log2
 
@@ -66,6 +69,91 @@ class Discriminator(nn.Module):
             elif isinstance(m, nn.Linear):
                 nn.init.kaiming_normal_(m.weight)
                 nn.init.constant_(m.bias, 0.0)
+
+
+# ------------------------------------------------------------------------------------------------ autograd bridge
+# The engines write parameter gradients in place (into the flat buffers that back `p.grad`).  For autograd the gradients
+# must instead be RETURNED so that the engine accumulates them (two critic passes in one graph, repeated backward calls):
+# every parameter's `.grad` is detached for the duration of the engine's backward, the engine fills a scratch gradient,
+# and the previous `.grad` is put back.
+_AG_TAGS = 4
+
+
+def _engine_param_grads(module, run):
+    params = list(module.parameters())
+    saved = [p.grad for p in params]
+    for p in params:
+        p.grad = None
+    try:
+        extra = run()
+        grads = [p.grad for p in params]
+    finally:
+        for p, g in zip(params, saved):
+            p.grad = g
+    return grads, extra
+
+
+def _need_train(module, what):
+    if not module.training:
+        raise NotImplementedError(f"{what}: backward through eval-mode BatchNorm is not implemented on the sm_100a path "
+                                  "(call .train() first, or wrap the forward in torch.no_grad())")
+
+
+class _GeneratorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        eng = module._engine()
+        lat = _ops.cast_pad_bf16(x, x.size(1))
+        n = module.__dict__["_rg_ag"] = (module.__dict__.get("_rg_ag", -1) + 1) % _AG_TAGS
+        ctx.module, ctx.tag, ctx.training = module, f"ag{n}", module.training
+        img = eng.forward(lat, tag=ctx.tag, training=module.training).clone()
+        ctx.save_for_backward(lat, img)
+        return img
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_img):
+        module = ctx.module
+        _need_train(module, "generator")
+        if ctx.training is not True:
+            raise NotImplementedError("generator: the forward ran in eval mode; its backward is not implemented")
+        lat, img = ctx.saved_tensors
+        eng = module._engine()
+        d_img = d_img.to(torch.float32).contiguous()
+
+        def run():
+            eng.backward(lat, d_img, img, tag=ctx.tag)
+            return eng.input_grad(lat.shape[0]).clone() if ctx.needs_input_grad[1] else None
+
+        grads, dx = _engine_param_grads(module, run)
+        return (None, dx) + tuple(grads)
+
+
+class _CriticFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        eng = module._engine()
+        n = module.__dict__["_rg_ag"] = (module.__dict__.get("_rg_ag", -1) + 1) % _AG_TAGS
+        ctx.module, ctx.tag, ctx.B, ctx.training = module, f"ag{n}", x.shape[0], module.training
+        return eng.forward(x, tag=ctx.tag, training=module.training).clone()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        module = ctx.module
+        _need_train(module, "critic")
+        if ctx.training is not True:
+            raise NotImplementedError("critic: the forward ran in eval mode; its backward is not implemented")
+        eng = module._engine()
+        dout = dout.to(torch.float32).contiguous()
+
+        def run():
+            dimg = eng.backward(ctx.B, 1.0, tag=ctx.tag, params=True, acc=0.0, want_dimg=ctx.needs_input_grad[1],
+                                dout=dout)
+            return dimg.clone() if dimg is not None else None
+
+        grads, dx = _engine_param_grads(module, run)
+        return (None, dx) + tuple(grads)
 
 
 def _repeats(size, what):
@@ -152,13 +240,15 @@ class DCGANGenerator(_EngineMixin, Generator):
         self.model = nn.Sequential(*layers)
         self._weight_initializer()
 
-    @torch.no_grad()
     def forward(self, x, feature_matching=False):
         """x: [B, encoding_dims] -> [B, out_channels, S, S] fp32 NCHW (batch statistics in train mode)."""
         eng = self._engine()
         x = x.view(-1, x.size(1)).to(device=eng.device, dtype=torch.float32).contiguous()
-        lat = _ops.cast_pad_bf16(x, x.size(1))
-        return eng.forward(lat, tag="module", training=self.training).clone()
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return _GeneratorFn.apply(self, x, *self.parameters())
+        with torch.no_grad():
+            lat = _ops.cast_pad_bf16(x, x.size(1))
+            return eng.forward(lat, tag="module", training=self.training).clone()
 
 
 class DCGANDiscriminator(_EngineMixin, Discriminator):
@@ -186,17 +276,21 @@ class DCGANDiscriminator(_EngineMixin, Discriminator):
         self.model = nn.Sequential(*layers)
         self._weight_initializer()
 
-    @torch.no_grad()
     def forward(self, x, feature_matching=False):
-        """x: [B, C, S, S] fp32 NCHW -> critic score [B] (or the last feature map when feature_matching)."""
+        """x: [B, C, S, S] fp32 NCHW -> critic score [B] (or the last feature map when feature_matching; that output is
+        not differentiable)."""
         eng = self._engine()
         x = x.to(device=eng.device, dtype=torch.float32).contiguous()
-        out = eng.forward(x, tag="module", training=self.training)
-        if feature_matching:
-            B = x.shape[0]
-            feat = eng.bufs.get(f"module.h{eng.n}", (B, 4, 4, eng.Cn))
-            return feat.float().permute(0, 3, 1, 2).contiguous()
-        return out.clone()
+        if (not feature_matching and torch.is_grad_enabled()
+                and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
+            return _CriticFn.apply(self, x, *self.parameters())
+        with torch.no_grad():
+            out = eng.forward(x, tag="module", training=self.training)
+            if feature_matching:
+                B = x.shape[0]
+                feat = eng.bufs.get(f"module.h{eng.n}", (B, 4, 4, eng.Cn))
+                return feat.float().permute(0, 3, 1, 2).contiguous()
+            return out.clone()
 
 
 class DCGANUpGenerator(_EngineMixin, Generator):

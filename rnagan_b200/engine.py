@@ -360,6 +360,12 @@ class GeneratorEngine:
         ops.proj_wgrad(lat, da0, _grad_of(self.conv0.weight))
         self.sync.layer_done(self.conv0.weight, self.bn0.mod.weight, self.bn0.mod.bias)
 
+    def input_grad(self, B):
+        """dL/d(latent) fp32 [B, E] of the backward pass that just ran (autograd through the module only: the train_ops
+        never need it -- the reference's encoder backward is discarded work)."""
+        da0 = self.bufs.get("bwd.da0", (B, 4, 4, self.C0))
+        return ops.gemm_nt(da0.view(B, 16 * self.C0), self.w_projkn, out_f32=True)
+
 
 # ====================================================================================================== resize-conv G
 class UpGeneratorEngine:
@@ -591,8 +597,10 @@ class CriticEngine:
         return out
 
     # ------------------------------------------------------------------ first-order backward
-    def backward(self, B, dout_const, tag="d", params=False, acc=0.0, want_dimg=False, keep_du=False, final=False):
-        """Backward of sum_b dout_const * out[b] through the pass saved under `tag`.
+    def backward(self, B, dout_const, tag="d", params=False, acc=0.0, want_dimg=False, keep_du=False, final=False,
+                 dout=None):
+        """Backward of sum_b dout_const * out[b] (or sum_b dout[b] * out[b] with a device vector `dout`) through the
+        pass saved under `tag`.
 
         params: also produce parameter gradients (acc=1.0 accumulates onto existing .grad).
         want_dimg: return dL/d(image) as fp32 NCHW.   keep_du: keep per-layer du / da (gradient-penalty step 2).
@@ -604,7 +612,7 @@ class CriticEngine:
         a6 = g(f"{tag}.a6", (B,), F32)
         da6 = g(f"{tag}.da6", (B,), F32)
         dh = g(f"{tag}.dh{n}", (B, H, H, self.Cn))
-        ops.head_bwd_data(a6, dout_const, self.w_head, B, 16 * self.Cn, SLOPE, da6, dh)
+        ops.head_bwd_data(a6, dout_const, self.w_head, B, 16 * self.Cn, SLOPE, da6, dh, dout=dout)
         if params:
             ops.head_wgrad(da6, hn, B, 16 * self.Cn, self.Cn, _grad_of(self.head.weight), acc)
             if final:

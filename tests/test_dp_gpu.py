@@ -12,12 +12,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_data_parallel_two_gpus(cuda_dev):
+@pytest.mark.parametrize("mode", ["nccl", "ce", "nvls"])
+def test_data_parallel_two_gpus(cuda_dev, mode):
+    """nccl: torch.distributed all_reduce; ce: copy-engine peer exchange (the default); nvls: in-switch multimem
+    reduction through the multicast mapping (falls back to ce with a warning when the fabric has no multicast)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29577", os.path.join(ROOT, "tests", "dp_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, RG_DP_EXCHANGE=mode))
     sys.stdout.write(res.stdout[-3000:])
     sys.stderr.write(res.stderr[-3000:])
     assert res.returncode == 0
@@ -34,14 +37,3 @@ def test_slices_sum_matches_ordered_sum(cuda_dev):
         for r in range(1, world):
             want += stage[r, :n]
         assert torch.equal(out, want)
-
-
-def test_data_parallel_two_gpus_peer_exchange(cuda_dev):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29578", os.path.join(ROOT, "tests", "dp_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, RG_DP_EXCHANGE="ce"))
-    sys.stdout.write(res.stdout[-3000:])
-    sys.stderr.write(res.stderr[-3000:])
-    assert res.returncode == 0

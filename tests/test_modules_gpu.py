@@ -348,3 +348,69 @@ def test_tiles_u8_normalise_bit_exact_and_prefetcher(cuda_dev):
     assert len(seen) == 2 and seen[0]["image"].device.type == "cuda" and seen[0]["image"].dtype == torch.float32
     assert torch.equal(torch.cat([b["image"] for b in seen]).cpu(), cpu_transform(tiles, True))
     assert torch.equal(torch.cat([b["rna_data"] for b in seen]).cpu(), rna)
+
+
+def test_autograd_through_modules(cuda_dev):
+    """`forward` of the drop-in modules is differentiable once through torch.autograd (a caller's own train step, e.g.
+    override_train_ops): loss.backward() through D(G(z)) and through two critic passes of one graph gives the oracle's
+    parameter / input gradients within the bf16 yardstick, gradients accumulate across backward calls like autograd's,
+    and a double backward (create_graph=True) is refused."""
+    import copy
+    from rnagan_b200 import dcgan
+    size, B = 32, 8
+    lrelu, tanh = torch.nn.LeakyReLU(0.2), torch.nn.Tanh()
+    oG = O.OracleGenerator(2048, size, 3, 64, nonlinearity=lrelu, last_nonlinearity=tanh).train()
+    oD = O.OracleCritic(size, 3, 64, nonlinearity=lrelu, last_nonlinearity=lrelu).train()
+    O.reinit_(oG, 1); O.reinit_(oD, 2)
+    G = dcgan.DCGANGenerator(2048, size, 3, 64, nonlinearity=torch.nn.LeakyReLU(0.2),
+                             last_nonlinearity=torch.nn.Tanh()).to(cuda_dev).train()
+    D = dcgan.DCGANDiscriminator(size, 3, 64, nonlinearity=torch.nn.LeakyReLU(0.2),
+                                 last_nonlinearity=torch.nn.LeakyReLU(0.2)).to(cuda_dev).train()
+    G.load_state_dict(oG.state_dict()); D.load_state_dict(oD.state_dict())
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(B, 2048, generator=g)
+    x = torch.rand(B, 3, size, size, generator=g) * 2 - 1
+
+    def cos(a, b):
+        a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+        return (a @ b / (a.norm() * b.norm()).clamp_min(1e-30)).item()
+
+    # (1) generator loss through both networks, gradient w.r.t. the latent too
+    aG, aD = copy.deepcopy(oG), copy.deepcopy(oD)
+    zr = z.clone().requires_grad_()
+    (-oD(oG(zr))).mean().backward()
+    za = z.clone().requires_grad_()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        (-aD(aG(za))).mean().backward()
+    zc = z.clone().to(cuda_dev).requires_grad_()
+    loss = (-D(G(zc))).mean()
+    assert loss.requires_grad
+    loss.backward()
+    worst_bf16 = min(cos(pa.grad, po.grad) for pa, po in zip(aG.parameters(), oG.parameters()) if po.grad.norm() > 0)
+    bound = 1.0 - 2.0 * (1.0 - min(worst_bf16, cos(za.grad, zr.grad))) - 0.01
+    for (n, po), (_, pm) in zip(oG.named_parameters(), G.named_parameters()):
+        if po.grad.norm() > 0:
+            assert cos(pm.grad, po.grad) >= bound, n
+    assert cos(zc.grad, zr.grad) >= bound
+    for (n, po), (_, pm) in zip(oD.named_parameters(), D.named_parameters()):
+        if po.grad.norm() > 0:
+            assert cos(pm.grad, po.grad) >= bound, n
+    # (2) two critic passes in ONE graph, accumulated ON TOP of the gradients already there (no zero_grad)
+    with torch.no_grad():
+        fake_o = oG(z)
+    fake_m = G(z.to(cuda_dev)).detach()
+    (oD(fake_o).mean() - oD(x).mean()).backward()
+    (D(fake_m).mean() - D(x.to(cuda_dev)).mean()).backward()
+    for (n, po), (_, pm) in zip(oD.named_parameters(), D.named_parameters()):
+        if po.grad.norm() > 0:
+            assert cos(pm.grad, po.grad) >= bound, n
+            assert abs(pm.grad.norm().item() / po.grad.norm().item() - 1.0) <= 0.1, n
+    # (3) double backward is refused with a clear error
+    xg = x.to(cuda_dev).requires_grad_()
+    out = D(xg)
+    with pytest.raises(RuntimeError):
+        gx = torch.autograd.grad(out, xg, torch.ones_like(out), create_graph=True)[0]
+        (gx.norm() - 1).pow(2).backward()
+    # no_grad / eval paths still return plain tensors
+    with torch.no_grad():
+        assert not G(z.to(cuda_dev)).requires_grad
