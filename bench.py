@@ -213,14 +213,15 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.lib().rg_launch_count()
+    launches0 = _lib.lib().rg_launch_count() + steps.GRAPH_STATS["kernel_launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(W, W + K):
         resident_step(i)
     e1.record()
     barrier()
-    launches = _lib.lib().rg_launch_count() - launches0
+    # kernels launched in the timed region: eager launches counted by the library + kernels inside replayed CUDA graphs
+    launches = _lib.lib().rg_launch_count() + steps.GRAPH_STATS["kernel_launches"] - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / K
@@ -441,7 +442,8 @@ def run_ours(args, rank, world, local_rank):
                        "step_unit": "one full iteration (3 optimiser steps) on a 64-sample batch; value sums ranks",
                        "l2_policy": "working set per step (>1 GB of activations) exceeds the 126 MB L2",
                        "precision": "bf16 operands / fp32 accumulate, fp32 master weights, stats, losses"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "e2e": e2e, "gpu_launches": int(launches), "cuda_graphs": dict(steps.GRAPH_STATS), "clocks": clocks,
+            "roofline": roofline,
             "cpu_baseline": cpu, "stock_torch_gpu": stock, "sustained": sustained, "dp_check": dp,
             "synthesis": synth, "vae_train": vae_train, "losses_finite": finite,
             "last_losses": [float(x) for x in losses_host[-1]],

@@ -264,6 +264,11 @@ int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms
 /* grad_scale multiplies every gradient first (1/world_size after a SUM all-reduce; 1.0 otherwise) */
 int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, float beta2, float eps, int step,
                  int do_clamp, float clamp_lo, float clamp_hi, float grad_scale, rg_stream_t st);
+/* the same step with the learning rate and the step count read from DEVICE memory, dyn = {lr, step}: the call first
+ * advances dyn[1] by one, then runs the update with bias corrections 1 - beta^dyn[1].  Nothing in the launch arguments
+ * changes between steps, so a captured CUDA graph of a whole optimiser step can be replayed. */
+int rg_adam_step_dyn(const void* table_dev, int num_chunks, float* dyn, float beta1, float beta2, float eps,
+                     int do_clamp, float clamp_lo, float clamp_hi, float grad_scale, rg_stream_t st);
 int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st);
 /* data-parallel gradient exchange through NVSwitch multicast (NVLink SHARP): in place, over the MULTICAST mapping `mc` of
  * a symmetric buffer (every rank's copy at the same offset), the calling rank reduces floats [offset, offset+n) --

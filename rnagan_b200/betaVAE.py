@@ -181,19 +181,119 @@ def train_step(model, optimizer, x, beta, keep_mask=None, eps=None):
     return out3
 
 
-def train_betaVAE(model, optimizer, dataloader, beta, num_epochs=1, scheduler=None, log_interval=None):
-    """Minimal epoch loop around ``train_step`` with the call order of the reference's train phase
-    (src/betaVAE.py:205-247): per batch step, then ``scheduler.step()``; returns the per-epoch mean losses."""
-    history = []
-    model.train()
-    for _ in range(num_epochs):
-        acc, n = torch.zeros(3, device=next(model.parameters()).device), 0
-        for batch in dataloader:
-            x = batch["rna_data"] if isinstance(batch, dict) else batch
-            acc += train_step(model, optimizer, x, beta)
-            n += 1
-            if scheduler is not None:
-                scheduler.step()
-        mean = (acc / max(n, 1)).tolist()
-        history.append({"total_loss": mean[0], "reconstruction_loss": mean[1], "kl_loss": mean[2]})
-    return history
+def _loss_means(acc, n):
+    m = (acc / max(n, 1)).tolist()
+    return {"total_loss": m[0], "reconstruction_loss": m[1], "kl_loss": m[2]}
+
+
+def train_betaVAE(model, optimizer, dataloader, save_dir="checkpoints/models/", device=None, log_interval=100,
+                  summary_writer=None, num_epochs=100, scheduler=None, verbose=True):
+    """Drop-in for the reference's ``train_betaVAE`` (src/betaVAE.py:164-284), same arguments and return value:
+    ``dataloader`` is ``{'train': ..., 'val': ...}`` of ``{'rna_data': [B, genes]}`` batches; every epoch runs the train
+    phase (``train_step`` per batch, then ``scheduler.step()`` -- any torch scheduler works, the fused Adam reads
+    ``param_groups[...]['lr']`` each step) and the val phase (eval-mode forward, total = reconstruction loss,
+    src/betaVAE.py:159-160); the best validation epoch is written to ``{save_dir}/model_dict_best.pt``, the final weights
+    to ``model_last.pt``, and the best ones are loaded back before returning ``(model, {'best_epoch', 'best_loss'})``.
+    Losses stay on the device during an epoch (one read-back per phase instead of three ``.item()`` per batch);
+    ``summary_writer.add_scalar`` is fed at ``log_interval`` like upstream when a writer is given."""
+    import os
+
+    import numpy as np
+    os.makedirs(save_dir, exist_ok=True)
+    dev = next(model.parameters()).device
+    best_epoch, best_loss = 0, {"total_loss": np.inf}
+    global_step = {"train": 0, "val": 0}
+    for epoch in range(num_epochs):
+        if verbose:
+            print("Epoch {}/{}".format(epoch, num_epochs - 1))
+            print("-" * 10)
+        for phase in ("train", "val"):
+            model.train(phase == "train")
+            acc, n = torch.zeros(3, device=dev), 0
+            last = torch.zeros(3, device=dev)
+            step = global_step[phase]
+            for batch in dataloader[phase]:
+                x = (batch["rna_data"] if isinstance(batch, dict) else batch).to(dev)
+                if phase == "train":
+                    acc += train_step(model, optimizer, x, model.beta)
+                    if scheduler:
+                        scheduler.step()
+                else:
+                    with torch.no_grad():
+                        out, z_mean, z_log_var = model(x)
+                        ls = betaVAEloss(x, out, z_mean, z_log_var, model.beta, training=False)
+                        acc += torch.stack([ls["total_loss"], ls["reconstruction_loss"], ls["kl_loss"]])
+                n += 1
+                step += 1
+                if summary_writer is not None and step % log_interval == 0:
+                    mean = acc / n                                  # upstream logs the change of the running mean
+                    for k, key in enumerate(("total_loss", "reconstruction_loss", "kl_loss")):
+                        summary_writer.add_scalar("{}/{}".format(phase, key), float(mean[k] - last[k]), step)
+                    last = mean.clone()
+            global_step[phase] = step
+            epoch_loss = _loss_means(acc, n)
+            if verbose:
+                print("{} Total Loss: {:.4f} | Reconstruction Loss: {:.4f} | KL Loss: {:.4f}".format(
+                    phase, epoch_loss["total_loss"], epoch_loss["reconstruction_loss"], epoch_loss["kl_loss"]))
+            if phase == "val" and epoch_loss["total_loss"] < best_loss["total_loss"]:
+                best_loss["total_loss"] = epoch_loss["total_loss"]
+                torch.save(model.state_dict(), os.path.join(save_dir, "model_dict_best.pt"))
+                best_epoch = epoch
+    torch.save(model.state_dict(), os.path.join(save_dir, "model_last.pt"))
+    model.load_state_dict(torch.load(os.path.join(save_dir, "model_dict_best.pt")))
+    return model, {"best_epoch": best_epoch, "best_loss": best_loss}
+
+
+def evaluate_betaVAE(model, dataloader, verbose=True):
+    """Drop-in for src/betaVAE.py:286-331: eval-mode losses over a loader plus the predictions / inputs as nested lists."""
+    import numpy as np
+    model.eval()
+    dev = next(model.parameters()).device
+    running = {"total_loss": [], "reconstruction_loss": [], "kl_loss": []}
+    predictions, real = [], []
+    for batch in dataloader:
+        x = (batch["rna_data"] if isinstance(batch, dict) else batch).to(dev)
+        with torch.no_grad():
+            out, z_mean, z_log_var = model(x)
+            ls = betaVAEloss(x, out, z_mean, z_log_var, model.beta, training=False)
+        predictions.append(out.detach().cpu().numpy().tolist())
+        real.append(x.detach().cpu().numpy().tolist())
+        for k in running:
+            running[k].append(ls[k].item())
+    test_loss = {k: np.mean(v) for k, v in running.items()}
+    if verbose:
+        print("Total Loss: {:.4f} | Reconstruction Loss: {:.4f} | KL Loss: {:.4f}".format(
+            test_loss["total_loss"], test_loss["reconstruction_loss"], test_loss["kl_loss"]))
+    return test_loss, predictions, real
+
+
+class GradualWarmupScheduler(torch.optim.lr_scheduler._LRScheduler):
+    """The warm-up wrapper the reference driver stacks on CosineAnnealingLR (src/betaVAE_training.py:14,165-166; the
+    third-party `warmup_scheduler` package, not installed here): the learning rate rises linearly from base_lr to
+    multiplier * base_lr (from 0 when multiplier == 1) over `total_epoch` steps, then `after_scheduler` takes over."""
+
+    def __init__(self, optimizer, multiplier, total_epoch, after_scheduler=None):
+        if multiplier < 1.0:
+            raise ValueError("multiplier should be greater than or equal to 1.")
+        self.multiplier, self.total_epoch, self.after_scheduler, self.finished = multiplier, total_epoch, after_scheduler, False
+        super().__init__(optimizer)
+
+    def get_lr(self):
+        if self.last_epoch > self.total_epoch:
+            if self.after_scheduler:
+                if not self.finished:
+                    self.after_scheduler.base_lrs = [b * self.multiplier for b in self.base_lrs]
+                    self.finished = True
+                return self.after_scheduler.get_last_lr()
+            return [b * self.multiplier for b in self.base_lrs]
+        if self.multiplier == 1.0:
+            return [b * (float(self.last_epoch) / self.total_epoch) for b in self.base_lrs]
+        return [b * ((self.multiplier - 1.0) * self.last_epoch / self.total_epoch + 1.0) for b in self.base_lrs]
+
+    def step(self, epoch=None):
+        if self.finished and self.after_scheduler:
+            self.after_scheduler.step(None if epoch is None else epoch - self.total_epoch)
+            self._last_lr = self.after_scheduler.get_last_lr()
+            self.last_epoch += 1
+        else:
+            super().step(epoch)

@@ -995,9 +995,18 @@ struct AdamChunk {
 };
 // torch.optim.Adam (no amsgrad, no weight decay), src/histopathology_gan.py:252,257:
 //   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+// dyn (optional, device): {learning rate, step count as float} read at run time instead of the by-value arguments, so a
+// CUDA graph that contains this launch stays valid from step to step (adam_tick_kernel advances the count)
+__global__ void adam_tick_kernel(float* dyn) { dyn[1] += 1.0f; }
 __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__ chunks, float lr, float b1, float b2,
                                                    float eps, float bc1, float bc2_sqrt, float clamp_lo, float clamp_hi,
-                                                   int do_clamp, float gscale) {
+                                                   int do_clamp, float gscale, const float* __restrict__ dyn) {
+  if (dyn != nullptr) {
+    lr = dyn[0];
+    const float t = dyn[1];
+    bc1 = 1.0f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+  }
   const AdamChunk ch = chunks[blockIdx.x];
   const float step = lr / bc1;
   const float ob1 = 1.0f - b1, ob2 = 1.0f - b2;
@@ -1726,8 +1735,20 @@ int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, f
   const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   adam_kernel<<<num_chunks, 256, 0, static_cast<cudaStream_t>(st)>>>(static_cast<const AdamChunk*>(table_dev), lr, beta1,
                                                                      beta2, eps, bc1, sqrtf(bc2), clamp_lo, clamp_hi,
-                                                                     do_clamp, grad_scale);
+                                                                     do_clamp, grad_scale, nullptr);
   RG_LAUNCH_CHECK("rg_adam_step");
+  return 0;
+}
+
+int rg_adam_step_dyn(const void* table_dev, int num_chunks, float* dyn, float beta1, float beta2, float eps,
+                     int do_clamp, float clamp_lo, float clamp_hi, float grad_scale, rg_stream_t st) {
+  RG_CHECK_ARG(table_dev && num_chunks > 0 && dyn, "rg_adam_step_dyn: bad arguments");
+  adam_tick_kernel<<<1, 1, 0, static_cast<cudaStream_t>(st)>>>(dyn);
+  RG_LAUNCH_CHECK("rg_adam_step_dyn(tick)");
+  adam_kernel<<<num_chunks, 256, 0, static_cast<cudaStream_t>(st)>>>(static_cast<const AdamChunk*>(table_dev), 0.0f, beta1,
+                                                                     beta2, eps, 1.0f, 1.0f, clamp_lo, clamp_hi, do_clamp,
+                                                                     grad_scale, dyn);
+  RG_LAUNCH_CHECK("rg_adam_step_dyn");
   return 0;
 }
 

@@ -566,6 +566,13 @@ class AdamTable:
         self.shadows = shadows
         self.ptrs = tuple(t.data_ptr() for ts in self.keep for t in ts)
 
+    def step_dyn(self, dyn, beta1, beta2, eps, clamp=None, grad_scale=1.0):
+        """The step with {lr, step count} in the device tensor `dyn` (fp32 [2]); the kernel advances the count itself."""
+        lo, hi = (clamp if clamp is not None else (0.0, 0.0))
+        _lib.check(_lib.lib().rg_adam_step_dyn(_p(self.table), self.num_chunks, _p(dyn), float(beta1), float(beta2),
+                                               float(eps), int(clamp is not None), float(lo), float(hi),
+                                               float(grad_scale), _st()), "rg_adam_step_dyn")
+
     def step(self, lr, beta1, beta2, eps, step, clamp=None, grad_scale=1.0):
         lo, hi = (clamp if clamp is not None else (0.0, 0.0))
         _lib.check(_lib.lib().rg_adam_step(_p(self.table), self.num_chunks, float(lr), float(beta1), float(beta2),

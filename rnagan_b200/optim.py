@@ -30,9 +30,31 @@ def _dense(t):
     return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
 
 
-def adam_step(opt, clamp=None, grad_scale=1.0):
+def group_step(opt, gi):
+    """Host-side step count of param group gi (0 before the first step)."""
+    for p in opt.param_groups[gi]["params"]:
+        st = opt.state.get(p)
+        if st and "step" in st:
+            return int(st["step"])
+    return 0
+
+
+def advance_host_steps(opt):
+    """Advance the optimizer's per-parameter `step` counters by one without launching anything (a replayed CUDA graph
+    has done the update; `optimizer.state_dict()` must keep telling the truth)."""
+    for group in opt.param_groups:
+        for p in group["params"]:
+            st = opt.state.get(p)
+            if st and "step" in st:
+                st["step"] += 1
+
+
+def adam_step(opt, clamp=None, grad_scale=1.0, dyn=None):
     """One Adam step over every parameter of ``opt`` that has a gradient (gradients are multiplied by grad_scale
-    first: 1/world_size after a SUM all-reduce). Returns nothing; asynchronous."""
+    first: 1/world_size after a SUM all-reduce). Returns nothing; asynchronous.
+    dyn: {group index: device fp32 [2] = (lr, step count)} -- the launch reads the learning rate and the step count from
+    the device and advances the count itself (CUDA-graph capture, steps.py); the host counters are then advanced by the
+    caller with advance_host_steps, once per replay."""
     if not isinstance(opt, torch.optim.Adam):
         raise NotImplementedError(f"only torch.optim.Adam is implemented on the sm_100a path (got {type(opt).__name__})")
     tables = opt.__dict__.setdefault("_rg_tables", {})
@@ -55,11 +77,14 @@ def adam_step(opt, clamp=None, grad_scale=1.0):
                                 [s["exp_avg"] for s in states], [s["exp_avg_sq"] for s in states], shadows)
             ent = (key, tab)
             tables[gi] = ent
+        b1, b2 = group["betas"]
+        if dyn is not None:
+            ent[1].step_dyn(dyn[gi], b1, b2, group["eps"], clamp=clamp, grad_scale=grad_scale)
+            continue
         for s in states:
             s["step"] += 1
         step = int(states[0]["step"])
         if len(states) > 1 and any(int(s["step"]) != step for s in states[1:]):
             # one bias correction per launch: a partially populated / merged optimizer state would be stepped wrongly
             raise NotImplementedError("fused Adam needs every parameter of a group at the same step count")
-        b1, b2 = group["betas"]
         ent[1].step(group["lr"], b1, b2, group["eps"], step, clamp=clamp, grad_scale=grad_scale)

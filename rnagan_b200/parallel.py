@@ -174,10 +174,19 @@ class PeerExchange:
 
 
 def exchange_mode():
-    """How data-parallel gradients are summed: 'ce' (default: PeerExchange over symmetric memory and the copy engines --
-    measured fastest at 2 and 8 B200s, profiles/r2_dp_exchange_ab_n*.txt), 'nvls' (PeerExchange with the in-switch
-    multimem reduction) or 'nccl' (torch.distributed all_reduce; always used on CPU / gloo)."""
-    return os.environ.get("RG_DP_EXCHANGE", "ce").lower()
+    """How data-parallel gradients are summed (RG_DP_EXCHANGE overrides):
+      'ce'    PeerExchange over symmetric memory and the copy engines: no SM is held while bytes move
+      'nvls'  PeerExchange with the in-switch multimem reduction (rg_nvls_allreduce): each rank's kernel touches 1/world
+              of the bytes, so its SM time shrinks with the world size while the copy-engine schedule grows
+      'nccl'  torch.distributed all_reduce (always used on CPU / gloo)
+    Default: 'ce' up to 3 ranks, 'nvls' from 4 (falls back to 'ce' when the fabric has no multicast).  Measured on B200s
+    (profiles/r2_dp_exchange_ab.txt, ms per iteration): 2 GPUs nccl 13.9 / ce 13.7 / nvls 13.0 vs ce 12.1 after the
+    kernel work; 8 GPUs nccl 14.4 / ce 14.2, then ce 12.50 / nvls 12.50 with nvls ahead end to end (611 vs 597 steps/s)."""
+    mode = os.environ.get("RG_DP_EXCHANGE", "auto").lower()
+    if mode == "auto":
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        mode = "nvls" if world >= 4 else "ce"
+    return mode
 
 
 class GradSync:

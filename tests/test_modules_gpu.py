@@ -414,3 +414,36 @@ def test_autograd_through_modules(cuda_dev):
     # no_grad / eval paths still return plain tensors
     with torch.no_grad():
         assert not G(z.to(cuda_dev)).requires_grad
+
+
+def test_train_betavae_loop_val_phase_and_best_checkpoint(cuda_dev, tmp_path):
+    """train_betaVAE / evaluate_betaVAE with the reference's signatures (src/betaVAE.py:164-331): train + val phases,
+    `model_dict_best.pt` at the best validation epoch, `model_last.pt`, best weights loaded back, warm-up + cosine
+    schedule (src/betaVAE_training.py:165-166) driving the fused Adam through param_groups['lr']."""
+    from rnagan_b200 import betaVAE as bv
+    feats, beta = 300, 0.0005
+    torch.manual_seed(3)
+    vae = bv.betaVAE(feats, 2048, [6000, 4000, 2048], [4000, 6000], beta=beta).to(cuda_dev)
+    g = torch.Generator().manual_seed(9)
+    basis = torch.randn(8, feats, generator=g)
+
+    def loader(n):
+        return [{"rna_data": torch.tanh(torch.randn(32, 8, generator=g) @ basis * 0.3)} for _ in range(n)]
+
+    loaders = {"train": loader(6), "val": loader(2)}
+    opt = torch.optim.Adam(vae.parameters(), lr=2e-4)
+    sched = bv.GradualWarmupScheduler(opt, multiplier=1, total_epoch=4,
+                                      after_scheduler=torch.optim.lr_scheduler.CosineAnnealingLR(opt, 50))
+    model, res = bv.train_betaVAE(vae, opt, loaders, save_dir=str(tmp_path), num_epochs=3, scheduler=sched, verbose=False)
+    assert model is vae and set(res) == {"best_epoch", "best_loss"} and 0 <= res["best_epoch"] <= 2
+    assert os.path.exists(tmp_path / "model_dict_best.pt") and os.path.exists(tmp_path / "model_last.pt")
+    best = torch.load(tmp_path / "model_dict_best.pt")
+    for k, v in vae.state_dict().items():
+        assert torch.equal(v.cpu(), best[k].cpu()), k                   # the best weights were loaded back
+    assert opt.param_groups[0]["lr"] < 2e-4                              # the schedule ran (18 steps: past the warm-up)
+    test_loss, preds, real = bv.evaluate_betaVAE(vae, loaders["val"], verbose=False)
+    # (the eval forward still draws reparametrisation noise, like the reference's: equal only statistically)
+    assert abs(test_loss["total_loss"] - res["best_loss"]["total_loss"]) <= 0.15 * res["best_loss"]["total_loss"] + 1e-3
+    assert test_loss["total_loss"] == test_loss["reconstruction_loss"]    # eval: total = reconstruction
+    assert len(preds) == 2 and len(preds[0]) == 32 and len(preds[0][0]) == feats and len(real[1]) == 32
+    assert not vae.training

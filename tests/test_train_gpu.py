@@ -326,3 +326,47 @@ def test_uint8_tiles_and_synthesis_job(cuda_dev):
         idx = torch.arange(t0, t0 + nb) % 7
         ref = gan_utils.generate_tiles(tr.generator, vae, profiles[idx], nb, chunk=nb, device=cuda_dev, u8=True)
         assert np.array_equal(ref.cpu().numpy(), got[t0]), t0
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager(cuda_dev):
+    """Single-process steps are captured into CUDA graphs after two eager calls (steps._run_step).  A replay launches the
+    same kernels in the same order on the same buffers, Adam reads its step count from device memory: six iterations with
+    graphs must be BIT-identical to six eager iterations (losses, weights, BatchNorm buffers, Adam moments and step
+    counters), the graphs must actually have been replayed, and an optimizer.load_state_dict in between (new moment
+    buffers) must trigger a fresh capture instead of replaying into stale memory."""
+    from rnagan_b200 import steps
+    size, batch, feats, _ = U.CONFIGS["mini32"]
+    data = O.make_batch(batch, feats, size, U.SEED_BATCH)
+    results = []
+    for use in (False, True):
+        steps.use_graphs(use)
+        steps._GRAPHS.clear()
+        replays0 = steps.GRAPH_STATS["replays"]
+        try:
+            oG, oD, oV, tr = _build(size, feats, cuda_dev)
+            tr.generator.load_state_dict(oG.state_dict())
+            tr.discriminator.load_state_dict(oD.state_dict())
+            tr.real_inputs, tr.batch_size = data, batch
+            torch.manual_seed(U.SEED_RUN)
+            losses = [tuple(tr.train_iter().values()) for _ in range(4)]
+            # swap the optimizer state for an equal copy in new buffers, then keep going
+            for opt in (tr.optimizer_generator, tr.optimizer_discriminator):
+                opt.load_state_dict(copy.deepcopy(opt.state_dict()))
+            losses += [tuple(tr.train_iter().values()) for _ in range(4)]
+            torch.cuda.synchronize()
+            state = {f"G.{k}": v.detach().clone().cpu() for k, v in tr.generator.state_dict().items()}
+            state.update({f"D.{k}": v.detach().clone().cpu() for k, v in tr.discriminator.state_dict().items()})
+            for name, opt in (("og", tr.optimizer_generator), ("od", tr.optimizer_discriminator)):
+                for i, st in enumerate(opt.state.values()):
+                    state[f"{name}.{i}.m"] = st["exp_avg"].detach().clone().cpu()
+                    state[f"{name}.{i}.v"] = st["exp_avg_sq"].detach().clone().cpu()
+                    state[f"{name}.{i}.step"] = torch.tensor(float(st["step"]))
+            results.append((losses, state, steps.GRAPH_STATS["replays"] - replays0))
+        finally:
+            steps.use_graphs(True)
+    (l0, s0, r0), (l1, s1, r1) = results
+    assert r0 == 0 and r1 >= 6, (r0, r1)          # 3 step kinds x (2 + 2 replays after each capture) at least
+    assert steps.GRAPH_STATS["failed"] == 0
+    assert l0 == l1
+    for k in s0:
+        assert torch.equal(s0[k], s1[k]), f"{k} differs between eager and graph replay"
