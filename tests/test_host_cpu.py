@@ -588,3 +588,33 @@ def test_frechet_distance_matches_reference_formula():
     assert abs(same) <= 1e-8 * np.trace(s1)
     with pytest.raises(ValueError):
         frechet_distance(mu1, s1, mu2[:-1], s2)
+
+
+def test_fid_pipeline_with_inception_architecture():
+    """src/fid.py:33-235 end to end on the CPU with RANDOM Inception weights (the pretrained file cannot be downloaded
+    here): the extractor refuses to run unweighted unless told to, loads a state_dict with torchvision's own key layout,
+    produces [N, 2048] activations of Mixed_7c, and calculate_fid is ~0 for identical stacks and > 0 for different ones."""
+    import numpy as np
+    import pytest
+    import torch
+    from rnagan_b200 import fid
+    with pytest.raises(ValueError):
+        fid.PartialInceptionNetwork()
+    torch.manual_seed(0)
+    net = fid.PartialInceptionNetwork(allow_random_weights=True)
+    for m in net.inception_network.modules():                  # init_weights=False leaves default init: make it tame
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eval()
+    state = net.inception_network.state_dict()
+    assert "Mixed_7c.branch_pool.conv.weight" in state and "Conv2d_1a_3x3.conv.weight" in state
+    net2 = fid.PartialInceptionNetwork(weights=state)           # same key layout as torchvision's checkpoint
+    rng = np.random.default_rng(0)
+    a = rng.random((6, 40, 40, 3), dtype=np.float32)
+    b = (rng.random((6, 40, 40, 3)) * 255).astype(np.uint8)
+    x = fid.preprocess_images(a)
+    assert x.shape == (6, 3, 299, 299) and x.dtype == torch.float32 and 0.0 <= float(x.min()) and float(x.max()) <= 1.0
+    act = fid.get_activations(x, 4, device="cpu", network=net2)
+    assert act.shape == (6, 2048) and np.isfinite(act).all()
+    same = fid.calculate_fid(a, a, False, 4, device="cpu", network=net2)
+    diff = fid.calculate_fid(a, b, True, 4, device="cpu", network=net2)
+    assert abs(same) <= 1e-6 * max(1.0, abs(diff)) and diff > 0

@@ -12,6 +12,8 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from rnagan_b200 import steps  # noqa: E402
 
+steps.use_graphs(False)      # per-kernel CUPTI records of eager launches (same kernels as the replayed graphs)
+
 
 def main(n_steps=3):
     dev = torch.device("cuda:0")
