@@ -123,6 +123,19 @@ def synthesize_job(generator, betavae, profiles, first, last, batch=1024, sink=N
     return done
 
 
+def _to_numpy(t):
+    """Device tensor -> fresh numpy array through a cached PINNED staging buffer: a pageable `.cpu()` of the 500 MB a
+    640-tile call returns runs at 2-3 GB/s and was 80 % of the call; pinned DMA + one host memcpy is ~4x faster."""
+    key = ("d2h", t.dtype)
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < t.numel():
+        buf = _PINNED[key] = torch.empty(t.numel(), dtype=t.dtype).pin_memory()
+    stage = buf[:t.numel()].view(t.shape)
+    stage.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return stage.numpy().copy()
+
+
 def generate_images(trainer, gene_exp=None, sample_size=64, betavae=None):
     """Same call signature and return value as the reference: numpy float32 [sample_size, S, S, 3] in [0, 1]."""
     generator = getattr(trainer, "generator").to(trainer.device)
@@ -136,6 +149,6 @@ def generate_images(trainer, gene_exp=None, sample_size=64, betavae=None):
                 hi = min(sample_size, lo + 10)
                 img = eng.forward(lat[lo:hi], tag=f"synth{hi - lo}", training=generator.training)
                 ops.tiles_to_unit_nhwc(img, out[lo:hi])
-        return out.cpu().numpy()
+        return _to_numpy(out)
     tiles = generate_tiles(generator, betavae, gene_exp, sample_size, chunk=10, device=trainer.device)
-    return tiles.cpu().numpy()
+    return _to_numpy(tiles)
