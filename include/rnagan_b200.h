@@ -215,7 +215,10 @@ int rg_col2im_img(const float* col, int ldc, const float* bias, int act_tanh, in
  * (v+1)/2 (src/gan_utils.py:236-241), bit 2 uint8 NHWC trunc(255*(v+1)/2) (src/generate_tissue_images.py:127-129),
  * bit 3 reversed channel order with bit 2.  H, W: low-resolution side (powers of two >= 8). */
 int rg_img_conv_up(const void* lo, const void* wfrag, const float* bias, int flags, int B, int H, int Wd, int Cp,
-                   int Cimg, void* out, rg_stream_t st);
+                   int Cimg, void* out, const float* bn_scale, const float* bn_shift, float bn_slope, rg_stream_t st);
+/* bn_scale / bn_shift (both or neither): `lo` is then the PRE-BatchNorm activation and h = lrelu(scale*a + shift, bn_slope)
+ * (nn.BatchNorm2d + LeakyReLU of the generator's last hidden block) is applied to the staged tile on the fly, so forward
+ * passes that are not differentiated (synthesis, the generator pass of the critic / penalty steps) never write h. */
 /* wfrag: the weight W fp32 [64][Cimg][4][4] re-arranged into per-lane mma.sync B fragments (bf16), rg_img_conv_up_pack_bytes()
  * bytes; refresh after every change of W (12 KB, one tiny launch). */
 size_t rg_img_conv_up_pack_bytes(void);

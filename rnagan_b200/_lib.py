@@ -63,7 +63,7 @@ SIGNATURES = {
     "rg_im2col_img": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "rg_img_channel_sum": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _f, _vp]),
     "rg_col2im_img": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
-    "rg_img_conv_up": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rg_img_conv_up": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "rg_img_conv_up_pack_bytes": (_sz, []),
     "rg_img_conv_up_pack": (_i, [_vp, _i, _i, _vp, _vp]),
     "rg_img_conv_down": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _f, _i, _i, _i, _i, _vp, _vp]),

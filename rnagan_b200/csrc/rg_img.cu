@@ -172,7 +172,8 @@ __global__ void img_up_pack_kernel(const float* __restrict__ Wt, int Cimg, uint2
 template <int Cimg>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const uint2* __restrict__ bfrag_g, const float* __restrict__ bias,
-                   void* __restrict__ out, int B, int H, int W, int flags) {
+                   void* __restrict__ out, int B, int H, int W, int flags, const float* __restrict__ bn_scale,
+                   const float* __restrict__ bn_shift, float bn_slope) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* tile = smem;
   uint2* bfrag = reinterpret_cast<uint2*>(smem + kUpTileBytes);
@@ -188,8 +189,47 @@ img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const uint2* __restrict
     for (int i = threadIdx.x; i < kUpFragBytes / 16; i += kThreads)
       cp16_zfill(fb + i * 16, reinterpret_cast<const uint8_t*>(bfrag_g) + i * 16, 16);
   }
+  // fused BatchNorm: this thread's 8-channel chunk is fixed (128 threads step by 16 pixels); fetch its scale / shift
+  // while the tile is still in flight
+  float sc[8], sh[8];
+  if (bn_scale != nullptr) {
+    const int ch0 = (threadIdx.x & 7) * 8;
+    const float4 sa = __ldg(reinterpret_cast<const float4*>(bn_scale + ch0));
+    const float4 sb = __ldg(reinterpret_cast<const float4*>(bn_scale + ch0) + 1);
+    const float4 ha = __ldg(reinterpret_cast<const float4*>(bn_shift + ch0));
+    const float4 hb = __ldg(reinterpret_cast<const float4*>(bn_shift + ch0) + 1);
+    sc[0] = sa.x; sc[1] = sa.y; sc[2] = sa.z; sc[3] = sa.w; sc[4] = sb.x; sc[5] = sb.y; sc[6] = sb.z; sc[7] = sb.w;
+    sh[0] = ha.x; sh[1] = ha.y; sh[2] = ha.z; sh[3] = ha.w; sh[4] = hb.x; sh[5] = hb.y; sh[6] = hb.z; sh[7] = hb.w;
+  }
   cp_commit_wait_all();
   __syncthreads();
+  if (bn_scale != nullptr) {
+    // `lo` is the PRE-BatchNorm activation a: h = lrelu(scale * a + shift) is applied to the staged tile in place (same
+    // arithmetic and bf16 rounding as rg_bn_act, so h is never written to HBM); halo pixels outside the image stay zero
+    // the pixel's (row, column) in the tile advances without a division
+    const int ch = threadIdx.x & 7;
+    int r = 0, c = threadIdx.x >> 3;                       // P = r * kUpPW + c, c < 16 < kUpPW
+    for (int P = threadIdx.x >> 3; P < kUpPH * kUpPW; P += kThreads / 8) {
+      const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        uint4* qp = reinterpret_cast<uint4*>(tile + P * 128 + ((ch ^ (P & 7)) << 4));
+        uint4 v = *qp;
+        __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(vh[e]);
+          float u0 = fmaf(f.x, sc[2 * e], sh[2 * e]), u1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+          u0 = u0 > 0.0f ? u0 : u0 * bn_slope;
+          u1 = u1 > 0.0f ? u1 : u1 * bn_slope;
+          vh[e] = __floats2bfloat162_rn(u0, u1);
+        }
+        *qp = v;
+      }
+      c += kThreads / 8;
+      if (c >= kUpPW) { c -= kUpPW; ++r; }
+    }
+    __syncthreads();
+  }
 
   float acc[4][2][4];
 #pragma unroll
@@ -576,9 +616,9 @@ int rg_img_conv_up_pack(const float* W, int Cp, int Cimg, void* wfrag, rg_stream
 }
 
 int rg_img_conv_up(const void* lo, const void* W, const float* bias, int flags, int B, int H, int Wd, int Cp, int Cimg,
-                   void* out, rg_stream_t st) {
+                   void* out, const float* bn_scale, const float* bn_shift, float bn_slope, rg_stream_t st) {
   RG_CHECK_ARG(lo && W && out && B > 0 && Cp == kC && Cimg >= 1 && Cimg <= kMaxCimg && is_pow2(H) && is_pow2(Wd) &&
-                   H >= 8 && Wd >= 8,
+                   H >= 8 && Wd >= 8 && ((bn_scale == nullptr) == (bn_shift == nullptr)),
                "rg_img_conv_up: need 64 input channels, 1..4 image channels and power-of-two H, W >= 8 (Cp=%d Cimg=%d H=%d W=%d)",
                Cp, Cimg, H, Wd);
   if (int rc = ensure_img_attrs()) return rc;
@@ -587,10 +627,10 @@ int rg_img_conv_up(const void* lo, const void* W, const float* bias, int flags, 
   const uint2* wf = static_cast<const uint2*>(W);
   cudaStream_t s = static_cast<cudaStream_t>(st);
   switch (Cimg) {
-    case 1: img_conv_up_kernel<1><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags); break;
-    case 2: img_conv_up_kernel<2><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags); break;
-    case 3: img_conv_up_kernel<3><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags); break;
-    default: img_conv_up_kernel<4><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags); break;
+    case 1: img_conv_up_kernel<1><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags, bn_scale, bn_shift, bn_slope); break;
+    case 2: img_conv_up_kernel<2><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags, bn_scale, bn_shift, bn_slope); break;
+    case 3: img_conv_up_kernel<3><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags, bn_scale, bn_shift, bn_slope); break;
+    default: img_conv_up_kernel<4><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags, bn_scale, bn_shift, bn_slope); break;
   }
   RG_LAUNCH_CHECK("rg_img_conv_up");
   return 0;

@@ -248,7 +248,7 @@ class DCGANGenerator(_EngineMixin, Generator):
             return _GeneratorFn.apply(self, x, *self.parameters())
         with torch.no_grad():
             lat = _ops.cast_pad_bf16(x, x.size(1))
-            return eng.forward(lat, tag="module", training=self.training).clone()
+            return eng.forward(lat, tag="module", training=self.training, keep=False).clone()
 
 
 class DCGANDiscriminator(_EngineMixin, Discriminator):

@@ -141,7 +141,9 @@ class _BN:
             return None
         return ops.stats_ws(self.C, self.device)
 
-    def forward(self, a, h, M, training=True, tag="", stats=None):
+    def forward(self, a, h, M, training=True, tag="", stats=None, apply=True):
+        """apply=False: only the statistics / scale / shift (and the running-statistics update); the caller's next kernel
+        applies lrelu(scale * a + shift) itself (GeneratorEngine's last block, img_conv_up bn=...)."""
         m, s = self.mod, self.st(tag)
         if training and stats is not None:
             ops.bn_finalize_partials(stats, m.weight, m.bias, M, self.C, m.eps, m.momentum, m.running_mean,
@@ -156,7 +158,8 @@ class _BN:
                 s.rstd.copy_((m.running_var + m.eps).rsqrt())
                 s.scale.copy_(m.weight * s.rstd)
                 s.shift.copy_(m.bias - s.mean * s.scale)
-        ops.bn_act(a, s.scale, s.shift, self.slope, h, M, self.C)
+        if apply:
+            ops.bn_act(a, s.scale, s.shift, self.slope, h, M, self.C)
 
     def bwd_ws(self, slot=1):
         """Partial-sum scratch for the fused backward (None: unfused)."""
@@ -277,8 +280,10 @@ class GeneratorEngine:
             ops.pack_edge_t(self.conv_last.weight.detach(), self.w_colT_last)
             ops.pack_edge(self.conv_last.weight.detach(), self.w_col_last)
 
-    def forward(self, lat, tag="g", training=True, out=None, unit_nhwc=False, u8=False, bgr=False):
+    def forward(self, lat, tag="g", training=True, out=None, unit_nhwc=False, u8=False, bgr=False, keep=True):
         """lat: bf16 [B, E] -> fp32 NCHW image [B, Cimg, S, S]; keeps activations under `tag` for backward.
+        keep=False (passes that are not differentiated: synthesis, the generator pass of the critic / penalty steps): the
+        last hidden activation h_n is not written -- the output kernel applies its BatchNorm + LeakyReLU on the fly.
         unit_nhwc (synthesis): `out` [B, S, S, Cimg] receives (image + 1) / 2 in NHWC straight from the last kernel;
         u8: `out` is a uint8 [B, S, S, Cimg] tensor receiving trunc(255 * (image + 1) / 2) (bgr: reversed channels)."""
         B = lat.shape[0]
@@ -288,6 +293,7 @@ class GeneratorEngine:
         ops.gemm_nn(lat, self.w_projkn, out=a.view(B, 16 * self.C0))
         self.bn0.forward(a, h, B * 16, training, tag=tag)
         H = 4
+        fuse_last = False
         for l, (c, bn) in enumerate(zip(self.convs, self.bns), start=1):
             Cs = c.weight.shape[1]
             a = g(f"{tag}.a{l}", (B, 2 * H, 2 * H, Cs))
@@ -295,13 +301,16 @@ class GeneratorEngine:
             ops.conv_up(h, _up_operand(self, l, B * H * H), Cs, out=a, stats=sws)
             H *= 2
             h = g(f"{tag}.h{l}", (B, H, H, Cs))
-            bn.forward(a, h, B * H * H, training, tag=tag, stats=sws)
+            fuse_last = (not keep) and l == self.n and self.fused_img
+            bn.forward(a, h, B * H * H, training, tag=tag, stats=sws, apply=not fuse_last)
         if out is None:
             out = g(f"{tag}.img", (B, 2 * H, 2 * H, self.Cimg) if (unit_nhwc or u8) else (B, self.Cimg, 2 * H, 2 * H),
                     torch.uint8 if u8 else F32)
         if self.fused_img:
-            ops.img_conv_up(h, self.w_up_img, out, bias=self.conv_last.bias.detach(), act_tanh=True,
-                            unit_nhwc=unit_nhwc, u8=u8, bgr=bgr, Cimg=self.Cimg)
+            st = self.bns[self.n - 1].st(tag) if fuse_last else None
+            ops.img_conv_up(a if fuse_last else h, self.w_up_img, out, bias=self.conv_last.bias.detach(), act_tanh=True,
+                            unit_nhwc=unit_nhwc, u8=u8, bgr=bgr, Cimg=self.Cimg,
+                            bn=(st.scale, st.shift, self.bns[self.n - 1].slope) if fuse_last else None)
             return out
         col = g("fwd.colimg", (B * H * H, 16 * self.Cimg), F32)
         ops.conv_up_img_col(h, self.w_colT_last, self.Cimg, col, out, bias=self.conv_last.bias.detach(), act_tanh=True,

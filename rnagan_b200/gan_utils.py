@@ -58,7 +58,7 @@ def generate_tiles(generator, betavae, gene_exp, sample_size, chunk=10, device=N
         hi = min(sample_size, lo + chunk)
         if hasattr(eng, "w_colT_last"):            # the last kernel writes (x + 1) / 2 (or the uint8 tile) in NHWC itself
             eng.forward(lat[lo:hi], tag=f"synth{hi - lo}", training=generator.training, out=out[lo:hi],
-                        unit_nhwc=not u8, u8=u8, bgr=bgr)
+                        unit_nhwc=not u8, u8=u8, bgr=bgr, keep=False)
         elif u8:
             raise NotImplementedError("uint8 tile output is implemented for the transposed-conv DCGANGenerator only")
         else:

@@ -434,18 +434,21 @@ def img_conv_up_pack(W, out=None):
     return out
 
 
-def img_conv_up(lo, W, out, bias=None, act_tanh=False, unit_nhwc=False, u8=False, bgr=False, Cimg=None):
+def img_conv_up(lo, W, out, bias=None, act_tanh=False, unit_nhwc=False, u8=False, bgr=False, Cimg=None, bn=None):
     """lo bf16 [B, H, W, 64]; W: fp32 [64, Cimg, 4, 4] (packed on the fly) or the table of img_conv_up_pack (then pass
     Cimg) -> out: fp32 NCHW [B, Cimg, 2H, 2W] (default), fp32 NHWC (x+1)/2 (unit_nhwc) or uint8 NHWC trunc(255 (x+1)/2)
-    (u8).  ConvTranspose2d(64, Cimg, 4, 2, 1) + bias + tanh."""
+    (u8).  ConvTranspose2d(64, Cimg, 4, 2, 1) + bias + tanh.  bn = (scale, shift, slope): `lo` is the pre-BatchNorm
+    activation and lrelu(scale * lo + shift) is applied on the fly."""
     _chk(lo, BF16, "lo")
     B, H, Wd, Cp = lo.shape
     if W.dtype == F32:
         Cimg = W.shape[1]
         W = img_conv_up_pack(W)
     flags = int(act_tanh) | (2 if unit_nhwc else 0) | (4 if u8 else 0) | (8 if bgr else 0)
+    bn_scale, bn_shift, bn_slope = bn if bn is not None else (None, None, 1.0)      # lo = pre-BatchNorm activation
     _prof("img_conv_up", 2.0 * B * H * Wd * Cp * 16 * Cimg, lambda: _lib.check(
-        _lib.lib().rg_img_conv_up(_p(lo), _p(W), _p(bias), flags, B, H, Wd, Cp, Cimg, _p(out), _st()), "rg_img_conv_up"))
+        _lib.lib().rg_img_conv_up(_p(lo), _p(W), _p(bias), flags, B, H, Wd, Cp, Cimg, _p(out), _p(bn_scale), _p(bn_shift),
+                                  float(bn_slope), _st()), "rg_img_conv_up"))
     return out
 
 

@@ -225,7 +225,7 @@ def critic_step(generator, discriminator, opt_d, noise_d, z, real, clip=None):
         lat = latent(ge, t["noise"], t["z"])
         out_real = de.forward(t["real"], tag="real", training=discriminator.training)
         apply_update(ge)                                    # G's reduction tail overlapped D(real)
-        fake = ge.forward(lat, tag="g", training=generator.training)
+        fake = ge.forward(lat, tag="g", training=generator.training, keep=False)      # G is not differentiated here
         out_fake = de.forward(fake, tag="fake", training=discriminator.training)
         loss = _loss_buf(ge, "loss_d")
         ops.wgan_loss(out_fake, 1.0, loss, b=out_real, sign_b=-1.0)      # mean(D(G(z)) - D(x))
@@ -245,7 +245,7 @@ def gp_step(generator, discriminator, opt_d, noise_d, z, real, eps_d, lambd=10.0
         ge, de = generator._engine(flush=False), discriminator._engine(flush=False)
         lat = latent(ge, t["noise"], t["z"])
         apply_update(ge)
-        fake = ge.forward(lat, tag="g", training=generator.training)
+        fake = ge.forward(lat, tag="g", training=generator.training, keep=False)      # G is not differentiated here
         apply_update(de)                                    # D's critic-step reduction overlapped this G forward
         out3 = de.gradient_penalty(t["real"], fake, t["eps"], lambd=lambd)
         _update(de, opt_d, dyn)

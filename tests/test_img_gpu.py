@@ -129,3 +129,32 @@ def test_img_conv_wgrad(cuda_dev, B, S, Cimg):
     dW2 = torch.empty_like(dW)
     ops.img_conv_wgrad(actn, x, dW2, y=y, mode=2, mul_dev=mul)
     assert torch.equal(dW, dW2)
+
+
+@pytest.mark.parametrize("B,S", [(3, 32), (2, 128)])
+def test_img_conv_up_fused_batchnorm_is_bit_identical(cuda_dev, B, S):
+    """bn=(scale, shift, slope): the output kernel applies the last hidden block's BatchNorm + LeakyReLU to the staged tile
+    with rg_bn_act's arithmetic and rounding, so it equals rg_bn_act followed by the plain kernel BIT for bit (including
+    the zero padding outside the image), and a generator forward with keep=False equals the keep=True one."""
+    from rnagan_b200 import dcgan, ops
+    H = S // 2
+    g = torch.Generator(device=cuda_dev).manual_seed(B + S)
+    a = torch.randn(B, H, H, 64, generator=g, device=cuda_dev).to(torch.bfloat16)
+    scale = (torch.rand(64, generator=g, device=cuda_dev) + 0.5).contiguous()
+    shift = (torch.randn(64, generator=g, device=cuda_dev) * 0.3).contiguous()
+    Wt = _bf(torch.randn(64, 3, 4, 4, generator=g, device=cuda_dev) * 0.05)
+    bias = torch.randn(3, generator=g, device=cuda_dev) * 0.1
+    h = torch.empty_like(a)
+    ops.bn_act(a, scale, shift, 0.2, h, B * H * H, 64)
+    ref = torch.empty(B, 3, S, S, device=cuda_dev)
+    out = torch.empty(B, 3, S, S, device=cuda_dev)
+    ops.img_conv_up(h, Wt, ref, bias=bias, act_tanh=True)
+    ops.img_conv_up(a, Wt, out, bias=bias, act_tanh=True, bn=(scale, shift, 0.2))
+    assert torch.equal(out, ref)
+    G = dcgan.DCGANGenerator(2048, S, 3, 64, nonlinearity=torch.nn.LeakyReLU(0.2),
+                             last_nonlinearity=torch.nn.Tanh()).to(cuda_dev).train()
+    eng = G._engine()
+    lat = torch.randn(4, 2048, generator=g, device=cuda_dev).to(torch.bfloat16)
+    img_keep = eng.forward(lat, tag="t1", training=True, keep=True).clone()
+    img_fused = eng.forward(lat, tag="t2", training=True, keep=False).clone()
+    assert torch.equal(img_keep, img_fused)
