@@ -264,6 +264,13 @@ int rg_adam_table_bytes(int num_chunks);
 int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms, void* const* vs,
                         void* const* shadows, const int64_t* sizes, int num_tensors, int chunk_elems, void* table_host,
                         int max_chunks);
+/* the same with PITCHED shadows: tensor i is a dense [rows][shadow_cols[i]] matrix whose bf16 copy has rows of
+ * shadow_pitch[i] >= shadow_cols[i] elements (nn.Linear weights whose K is padded for the 16-byte TMA stride rule, e.g.
+ * 19198 -> 19200 genes); pad columns are never written.  shadow_cols / shadow_pitch may be NULL (all dense). */
+int rg_adam_build_table_pitched(void* const* params, void* const* grads, void* const* ms, void* const* vs,
+                                void* const* shadows, const int* shadow_cols, const int* shadow_pitch,
+                                const int64_t* sizes, int num_tensors, int chunk_elems, void* table_host,
+                                int max_chunks);
 /* grad_scale multiplies every gradient first (1/world_size after a SUM all-reduce; 1.0 otherwise) */
 int rg_adam_step(const void* table_dev, int num_chunks, float lr, float beta1, float beta2, float eps, int step,
                  int do_clamp, float clamp_lo, float clamp_hi, float grad_scale, rg_stream_t st);

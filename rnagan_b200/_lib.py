@@ -79,6 +79,7 @@ SIGNATURES = {
     "rg_gp_norm": (_i, [_vp, _sz, _f, _vp, _i, _vp, _vp]),
     "rg_adam_table_bytes": (_i, [_i]),
     "rg_adam_build_table": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i]),
+    "rg_adam_build_table_pitched": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i]),
     "rg_adam_step": (_i, [_vp, _i, _f, _f, _f, _f, _i, _i, _f, _f, _f, _vp]),
     "rg_adam_step_dyn": (_i, [_vp, _i, _vp, _f, _f, _f, _i, _f, _f, _f, _vp]),
     "rg_clamp": (_i, [_vp, _sz, _f, _f, _vp]),

@@ -992,6 +992,10 @@ struct AdamChunk {
   __nv_bfloat16* shadow;   // optional bf16 copy of the updated parameters in the same element order (the packed GEMM
                            // operand of a channels_last weight): the optimiser step re-emits it, no pack kernel
   int n;
+  // pitched shadow (sh_cols > 0): the parameter is a dense [rows][sh_cols] matrix whose bf16 copy has rows of sh_pitch
+  // elements (K padded for the 16-byte TMA stride rule, e.g. 19198 -> 19200 genes); `shadow` then points at the start of
+  // the shadow row that holds this chunk's first element, which sits at column sh_col0 of it
+  int sh_cols, sh_pitch, sh_col0;
 };
 // torch.optim.Adam (no amsgrad, no weight decay), src/histopathology_gan.py:252,257:
 //   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
@@ -1016,7 +1020,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
   const float4* g4 = reinterpret_cast<const float4*>(ch.g);
   float4* m4 = reinterpret_cast<float4*>(ch.m);
   float4* v4 = reinterpret_cast<float4*>(ch.v);
-  uint2* s4 = (ch.shadow != nullptr && (reinterpret_cast<uintptr_t>(ch.shadow) & 7) == 0)
+  const bool pitched = ch.shadow != nullptr && ch.sh_cols > 0;
+  uint2* s4 = (ch.shadow != nullptr && !pitched && (reinterpret_cast<uintptr_t>(ch.shadow) & 7) == 0)
                   ? reinterpret_cast<uint2*>(ch.shadow) : nullptr;
   for (int i = threadIdx.x; i < n4; i += blockDim.x) {
     float4 p = p4[i], m = m4[i], v = v4[i];
@@ -1036,8 +1041,18 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
     }
     p4[i] = p; m4[i] = m; v4[i] = v;
     if (s4) s4[i] = make_uint2(pack_bf16x2_ops(p.x, p.y), pack_bf16x2_ops(p.z, p.w));
+    if (pitched) {
+      unsigned q = static_cast<unsigned>(ch.sh_col0) + 4u * static_cast<unsigned>(i);
+      unsigned r = q / static_cast<unsigned>(ch.sh_cols);
+      unsigned c = q - r * static_cast<unsigned>(ch.sh_cols);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        ch.shadow[static_cast<size_t>(r) * ch.sh_pitch + c] = __float2bfloat16(pp[e]);
+        if (++c == static_cast<unsigned>(ch.sh_cols)) { c = 0; ++r; }
+      }
+    }
   }
-  if (ch.shadow != nullptr && s4 == nullptr) {     // shadow not 8-byte aligned (offset views passed through the C ABI)
+  if (ch.shadow != nullptr && s4 == nullptr && !pitched) {     // shadow not 8-byte aligned (offset views through the C ABI)
     __syncthreads();                                // the elements below were written by other threads' float4 stores
     for (int i = threadIdx.x; i < n4 * 4; i += blockDim.x) ch.shadow[i] = __float2bfloat16(ch.p[i]);
   }
@@ -1050,7 +1065,13 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
     float p = ch.p[i] - step * (m / (sqrtf(v) / bc2_sqrt + eps));
     if (do_clamp) p = fminf(fmaxf(p, clamp_lo), clamp_hi);
     ch.p[i] = p;
-    if (ch.shadow) ch.shadow[i] = __float2bfloat16(p);
+    if (pitched) {
+      const unsigned q = static_cast<unsigned>(ch.sh_col0) + static_cast<unsigned>(i);
+      const unsigned r = q / static_cast<unsigned>(ch.sh_cols);
+      ch.shadow[static_cast<size_t>(r) * ch.sh_pitch + (q - r * static_cast<unsigned>(ch.sh_cols))] = __float2bfloat16(p);
+    } else if (ch.shadow) {
+      ch.shadow[i] = __float2bfloat16(p);
+    }
   }
 }
 __global__ void clamp_kernel(float* p, size_t n, float lo, float hi) {
@@ -1707,6 +1728,14 @@ int rg_adam_table_bytes(int num_chunks) { return static_cast<int>(sizeof(AdamChu
 int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms, void* const* vs,
                         void* const* shadows, const int64_t* sizes, int num_tensors, int chunk_elems, void* table_host,
                         int max_chunks) {
+  return rg_adam_build_table_pitched(params, grads, ms, vs, shadows, nullptr, nullptr, sizes, num_tensors, chunk_elems,
+                                     table_host, max_chunks);
+}
+
+int rg_adam_build_table_pitched(void* const* params, void* const* grads, void* const* ms, void* const* vs,
+                                void* const* shadows, const int* shadow_cols, const int* shadow_pitch,
+                                const int64_t* sizes, int num_tensors, int chunk_elems, void* table_host,
+                                int max_chunks) {
   RG_CHECK_ARG(params && grads && ms && vs && sizes && table_host && chunk_elems > 0, "rg_adam_build_table: bad arguments");
   AdamChunk* t = static_cast<AdamChunk*>(table_host);
   int n = 0;
@@ -1721,6 +1750,14 @@ int rg_adam_build_table(void* const* params, void* const* grads, void* const* ms
       t[n].m = static_cast<float*>(ms[i]) + off;
       t[n].v = static_cast<float*>(vs[i]) + off;
       t[n].shadow = (shadows && shadows[i]) ? static_cast<__nv_bfloat16*>(shadows[i]) + off : nullptr;
+      t[n].sh_cols = t[n].sh_pitch = t[n].sh_col0 = 0;
+      if (shadows && shadows[i] && shadow_cols && shadow_pitch && shadow_pitch[i] > shadow_cols[i] && shadow_cols[i] > 0) {
+        const int64_t row = off / shadow_cols[i];
+        t[n].shadow = static_cast<__nv_bfloat16*>(shadows[i]) + row * shadow_pitch[i];
+        t[n].sh_cols = shadow_cols[i];
+        t[n].sh_pitch = shadow_pitch[i];
+        t[n].sh_col0 = static_cast<int>(off - row * shadow_cols[i]);
+      }
       t[n].n = static_cast<int>(std::min<int64_t>(chunk_elems, sizes[i] - off));
       ++n;
     }

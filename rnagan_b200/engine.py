@@ -988,7 +988,9 @@ class VAETrainEngine:
         pairs += [(self.last.weight, self.w_last), (vae.z_mu.weight, self.w_cat[:self.Z]),
                   (vae.z_logvar.weight, self.w_cat[self.Z:])]
         for p, w in pairs:
-            if tuple(w.shape) == tuple(p.shape) and w.is_contiguous():
+            # same element order, or the same rows with a zero-padded K (Adam then writes the copy row by row:
+            # rg_adam_build_table_pitched) -- e.g. encoder layer 0, [6000, 19198] against a [6000, 19200] operand
+            if w.is_contiguous() and w.shape[0] == p.shape[0] and w.shape[1] >= p.shape[1]:
                 p._rg_shadow = w
                 self._shadowed.add(id(p))
         self.pack()

@@ -559,8 +559,16 @@ class AdamTable:
         arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
         host = torch.empty(L.rg_adam_table_bytes(max_chunks), dtype=torch.uint8).pin_memory()
         sh = (ctypes.c_void_p * n)(*[None if t is None else t.data_ptr() for t in shadows])
-        nch = L.rg_adam_build_table(arr(params), arr(grads), arr(ms), arr(vs), sh, (ctypes.c_int64 * n)(*sizes), n,
-                                    self.CHUNK, host.data_ptr(), max_chunks)
+        # a shadow with more columns than its 2-D parameter is a pitched copy (zero-padded K): Adam writes it row by row
+        cols = [p.shape[1] if (s_ is not None and p.dim() == 2 and s_.dim() == 2 and s_.shape[0] == p.shape[0]
+                               and s_.shape[1] > p.shape[1]) else 0 for p, s_ in zip(params, shadows)]
+        pitch = [s_.shape[1] if c else 0 for c, s_ in zip(cols, shadows)]
+        for p, s_, c in zip(params, shadows, cols):
+            if s_ is not None and not c and s_.numel() != p.numel():
+                raise ValueError("AdamTable: a shadow must have the parameter's element count or be a row-padded 2-D copy")
+        nch = L.rg_adam_build_table_pitched(arr(params), arr(grads), arr(ms), arr(vs), sh, (ctypes.c_int * n)(*cols),
+                                            (ctypes.c_int * n)(*pitch), (ctypes.c_int64 * n)(*sizes), n, self.CHUNK,
+                                            host.data_ptr(), max_chunks)
         if nch <= 0:
             _lib.check(nch if nch < 0 else -1, "rg_adam_build_table")
         self.num_chunks = nch

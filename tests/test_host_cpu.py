@@ -84,7 +84,7 @@ def test_size_queries_work_without_gpu():
     assert lib.rg_conv_wgrad_ws_bytes(64, 64, 64, 128, 64) > 0
     assert lib.rg_gemm_tn_ws_bytes(1 << 20, 64, 64) > 0
     assert lib.rg_reduce_ws_bytes(1 << 20, 64) > 0
-    assert lib.rg_adam_table_bytes(10) == 10 * 48   # 5 pointers + int, padded
+    assert lib.rg_adam_table_bytes(10) == 10 * 56   # 5 pointers + 4 ints (count, pitched-shadow geometry)
 
 
 def test_no_cpu_fallback():

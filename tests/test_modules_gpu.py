@@ -145,6 +145,21 @@ def test_adam_matches_torch(cuda_dev):
         assert (p - q).abs().max().item() <= 1e-6
     sd = o1.state_dict()
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 3.0
+    # bf16 shadows re-emitted by the step: a dense one and a PITCHED one (rows padded like a K = 19198 -> 19200 operand;
+    # 70001 columns: odd, so rows start at every alignment and chunks of 65536 elements straddle rows); the pad columns
+    # must stay untouched and the payload must equal a cast of the updated parameter bit for bit
+    w = torch.nn.Parameter(torch.randn(37, 70001, generator=g).to(cuda_dev))
+    d = torch.nn.Parameter(torch.randn(129, 64, generator=g).to(cuda_dev))
+    w._rg_shadow = torch.full((37, 70008), -7.0, dtype=torch.bfloat16, device=cuda_dev)
+    d._rg_shadow = torch.zeros(129, 64, dtype=torch.bfloat16, device=cuda_dev)
+    o3 = torch.optim.Adam([w, d], lr=1e-2)
+    for _ in range(2):
+        w.grad = torch.randn(w.shape, generator=g).to(cuda_dev)
+        d.grad = torch.randn(d.shape, generator=g).to(cuda_dev)
+        adam_step(o3)
+    assert torch.equal(w._rg_shadow[:, :70001], w.detach().to(torch.bfloat16))
+    assert (w._rg_shadow[:, 70001:] == -7.0).all()
+    assert torch.equal(d._rg_shadow, d.detach().to(torch.bfloat16))
 
 
 def test_checkpoint_roundtrip_and_errors(cuda_dev):
