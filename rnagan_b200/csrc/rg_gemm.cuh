@@ -41,7 +41,8 @@ constexpr int kGemmThreads = 224;            // warps: 0 A-producer, 1 MMA issue
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;              // TMEM columns per accumulator stage
 // weight-gradient kernel: fixed ring (4 x 48 KiB, or 3 x 64 KiB for 256-row units)
-constexpr int kWgradSmemBytes = 4 * (kAStageBytes + 256 * 128) + kSmemFixedBytes;
+constexpr int kWgradStageT = 4 * 4096;         // epilogue transpose slabs: 4 warps x (32 rows x 32 fp32)
+constexpr int kWgradSmemBytes = 4 * (kAStageBytes + 256 * 128) + kWgradStageT + kSmemFixedBytes;
 
 struct Tap {
   int8_t map;   // which A-view (parity map) this tap reads
@@ -815,7 +816,7 @@ gemm_fwd_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ F
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ WgradArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  const PipeSmem s = carve_smem(smem_raw, 4 * (kAStageBytes + 256 * 128), 0);
+  const PipeSmem s = carve_smem(smem_raw, 4 * (kAStageBytes + 256 * 128), kWgradStageT);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -951,34 +952,37 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
           for (int sl = 0; sl < p.slabs_per_tile; ++sl) {
             int tap, chunk;
             wgrad_slab(p, n_tile, sl, tap, chunk);
-            float* o = p.native_out + (static_cast<size_t>(prow) * p.num_taps + tap) * p.ld_out + chunk * 64;
+            // A thread owns one accumulator ROW (TMEM lane); stored as is, every store instruction would touch 32 rows
+            // x 16 bytes.  Each 32 x 32 fp32 block therefore goes through a per-warp shared-memory slab (16-byte chunks,
+            // chunk index XOR row: conflict-free both ways) and leaves as whole 128-byte row segments -- 8 lanes per row
+            // with 16-byte stores, or 16 lanes per row with 8-byte stores when the row pitch is only 8-byte aligned
+            // (ragged N of an nn.Linear, e.g. 19198).  These launches are store-bound (K = batch rows): the gradient
+            // of betaVAE's 6000 x 19198 layer is 460 MB of fp32.
+            const size_t col0 = static_cast<size_t>(tap) * p.ld_out + chunk * 64;
             const bool vec4 = (p.ld_out & 3) == 0;
+            float* slab = reinterpret_cast<float*>(s.staging) + q * 1024;
+            const int prow0 = (m_tile * msub + ms) * 128 + q * 32;           // first row of this warp's 32
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               uint32_t v[32];
               tmem_ld_32x32(taddr + sl * 64 + h * 32, v);
               tmem_ld_wait();
-              if (row_ok && !vec4) {
-                // ragged row pitch (even, not a multiple of 4 floats): 8-byte stores
 #pragma unroll
-                for (int g = 0; g < 16; ++g) {
-                  if (chunk * 64 + h * 32 + g * 2 + 2 <= p.n_out) {
-                    float2 f = make_float2(a * __uint_as_float(v[g * 2 + 0]), a * __uint_as_float(v[g * 2 + 1]));
-                    float2* dst = reinterpret_cast<float2*>(o + h * 32 + g * 2);
-                    if (beta != 0.0f) {
-                      const float2 old = *dst;
-                      f.x += beta * old.x; f.y += beta * old.y;
-                    }
-                    *dst = f;
-                  }
-                }
-              } else if (row_ok) {
+              for (int c4 = 0; c4 < 8; ++c4)
+                *reinterpret_cast<float4*>(slab + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+                    make_float4(a * __uint_as_float(v[c4 * 4 + 0]), a * __uint_as_float(v[c4 * 4 + 1]),
+                                a * __uint_as_float(v[c4 * 4 + 2]), a * __uint_as_float(v[c4 * 4 + 3]));
+              __syncwarp();
+              const int cbase = chunk * 64 + h * 32;                          // first column of this block in the row
+              if (vec4) {
+                const int c4 = lane & 7;
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                  if (chunk * 64 + h * 32 + g * 4 + 4 <= p.n_out) {
-                    float4 f = make_float4(a * __uint_as_float(v[g * 4 + 0]), a * __uint_as_float(v[g * 4 + 1]),
-                                           a * __uint_as_float(v[g * 4 + 2]), a * __uint_as_float(v[g * 4 + 3]));
-                    float4* dst = reinterpret_cast<float4*>(o + h * 32 + g * 4);
+                for (int it = 0; it < 8; ++it) {
+                  const int rr = it * 4 + (lane >> 3);
+                  if (prow0 + rr < p.Cp && cbase + c4 * 4 + 4 <= p.n_out) {
+                    float4 f = *reinterpret_cast<const float4*>(slab + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+                    float4* dst = reinterpret_cast<float4*>(p.native_out + static_cast<size_t>(prow0 + rr) * p.num_taps * p.ld_out +
+                                                            col0 + h * 32 + c4 * 4);
                     if (beta != 0.0f) {
                       const float4 old = *dst;
                       f.x += beta * old.x; f.y += beta * old.y; f.z += beta * old.z; f.w += beta * old.w;
@@ -986,7 +990,24 @@ gemm_wgrad_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
                     *dst = f;
                   }
                 }
+              } else {
+                const int c2 = lane & 15;
+#pragma unroll
+                for (int it = 0; it < 16; ++it) {
+                  const int rr = it * 2 + (lane >> 4);
+                  if (prow0 + rr < p.Cp && cbase + c2 * 2 + 2 <= p.n_out) {
+                    float2 f = *reinterpret_cast<const float2*>(slab + rr * 32 + (((c2 >> 1) ^ (rr & 7)) << 2) + (c2 & 1) * 2);
+                    float2* dst = reinterpret_cast<float2*>(p.native_out + static_cast<size_t>(prow0 + rr) * p.num_taps * p.ld_out +
+                                                            col0 + h * 32 + c2 * 2);
+                    if (beta != 0.0f) {
+                      const float2 old = *dst;
+                      f.x += beta * old.x; f.y += beta * old.y;
+                    }
+                    *dst = f;
+                  }
+                }
               }
+              __syncwarp();
             }
           }
         } else if (p.direct_out != nullptr) {
