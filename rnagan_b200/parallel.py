@@ -213,7 +213,14 @@ class GradSync:
         self.bucket_floats = 0
         self._open = None
         if self.world() > 1 and exchange_mode() in ("ce", "nvls") and params[0].device.type == "cuda":
-            self.xchg = PeerExchange(max(off, 4), params[0].device, use_nvls=exchange_mode() == "nvls")
+            try:
+                self.xchg = PeerExchange(max(off, 4), params[0].device, use_nvls=exchange_mode() == "nvls")
+            except Exception as ex:          # no peer access / symmetric memory on this system: NCCL still works
+                import warnings
+                warnings.warn(f"rnagan_b200: peer-memory gradient exchange unavailable ({type(ex).__name__}: {ex}); "
+                              "using the NCCL all-reduce")
+                self.xchg = None
+        if self.xchg is not None:
             self.flat = self.xchg.flat
             self.bucket_floats = int(float(os.environ.get("RG_DP_BUCKET_MB", "16")) * (1 << 20)) // 4
         else:

@@ -128,6 +128,8 @@ def _run_step(kind, generator, discriminator, opt, inputs, body, extra_key=()):
            tuple((g["betas"], g["eps"]) for g in opt.param_groups))
     ent = _GRAPHS.get(key)
     if ent is None:
+        if len(_GRAPHS) >= 32:               # engines / optimizers were rebuilt many times: drop the stale captures
+            _GRAPHS.clear()
         ent = _GRAPHS[key] = _Graphed()
     if ent.failed or ent.calls < GRAPH_WARMUP:
         ent.calls += 1

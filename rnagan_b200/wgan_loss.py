@@ -44,6 +44,17 @@ def wasserstein_discriminator_loss_vae(fx, fgz, reduction="mean"):
     return reduce_vae(fgz - fx, reduction="mean")
 
 
+def wasserstein_gradient_penalty_vae(interpolate, d_interpolate, reduction="mean"):
+    """The penalty VALUE (||d D(x_hat) / d x_hat||_F - 1)^2 over the whole batch tensor (src/wgan_loss.py:32-44) from an
+    autograd graph `d_interpolate = D(interpolate)` through this package's critic (first-order autograd, dcgan._CriticFn).
+    The result can be logged or compared; differentiating it AGAIN (`penalty.backward()`) needs the critic's double
+    backward, which autograd cannot provide here and raises -- the trainable form is `train_ops`, whose hand-scheduled
+    double backward (CriticEngine.gradient_penalty) produces the parameter gradients of lambda * penalty directly."""
+    g, = torch.autograd.grad(d_interpolate, interpolate, grad_outputs=torch.ones_like(d_interpolate), create_graph=True,
+                             retain_graph=True)
+    return reduce_vae((g.norm(2) - 1) ** 2, reduction)
+
+
 class GeneratorLoss(nn.Module):
     """torchgan.losses.GeneratorLoss contract (reduction / override_train_ops / arg_map)."""
 
@@ -281,8 +292,7 @@ class WassersteinGradientPenaltyVAE(_VAEConditioned, DiscriminatorLoss):
         self._init_vae(checkpoint, rna_features, beta)
 
     def forward(self, interpolate, d_interpolate):
-        raise NotImplementedError("the penalty is computed inside train_ops by CriticEngine.gradient_penalty "
-                                  "(hand-scheduled double backward); there is no autograd graph to differentiate")
+        return wasserstein_gradient_penalty_vae(interpolate, d_interpolate, self.reduction)
 
     def train_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
         return self.device_ops(generator, discriminator, optimizer_discriminator, real_inputs, device, labels).item()
@@ -347,8 +357,7 @@ class WassersteinGradientPenalty(DiscriminatorLoss):
         self.lambd = lambd
 
     def forward(self, interpolate, d_interpolate):
-        raise NotImplementedError("the penalty is computed inside train_ops by CriticEngine.gradient_penalty "
-                                  "(hand-scheduled double backward); there is no autograd graph to differentiate")
+        return wasserstein_gradient_penalty_vae(interpolate, d_interpolate, self.reduction)
 
     def train_ops(self, generator, discriminator, optimizer_discriminator, real_inputs, device, labels=None):
         return self.device_ops(generator, discriminator, optimizer_discriminator, real_inputs, device, labels).item()

@@ -462,3 +462,24 @@ def test_train_betavae_loop_val_phase_and_best_checkpoint(cuda_dev, tmp_path):
     assert test_loss["total_loss"] == test_loss["reconstruction_loss"]    # eval: total = reconstruction
     assert len(preds) == 2 and len(preds[0]) == 32 and len(preds[0][0]) == feats and len(real[1]) == 32
     assert not vae.training
+
+
+def test_gradient_penalty_forward_value(cuda_dev):
+    """WassersteinGradientPenalty[VAE].forward(interpolate, d_interpolate) (src/wgan_loss.py:296-312, 32-44): the penalty
+    value through first-order autograd of the critic module equals the oracle's; differentiating it again is refused."""
+    from rnagan_b200 import dcgan, wgan_loss
+    size, B = 32, 8
+    lrelu = torch.nn.LeakyReLU(0.2)
+    oD = O.OracleCritic(size, 3, 64, nonlinearity=lrelu, last_nonlinearity=lrelu).train()
+    O.reinit_(oD, 2)
+    D = dcgan.DCGANDiscriminator(size, 3, 64, nonlinearity=torch.nn.LeakyReLU(0.2),
+                                 last_nonlinearity=torch.nn.LeakyReLU(0.2)).to(cuda_dev).train()
+    D.load_state_dict(oD.state_dict())
+    x = torch.rand(B, 3, size, size, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    xo = x.clone().requires_grad_()
+    ref = O.gradient_penalty(xo, oD(xo)).item()
+    xm = x.to(cuda_dev).requires_grad_()
+    pen = wgan_loss.WassersteinGradientPenalty().forward(xm, D(xm))
+    assert abs(pen.item() - ref) <= 0.02 + 0.03 * abs(ref), (pen.item(), ref)
+    with pytest.raises(RuntimeError):
+        pen.backward()
