@@ -475,7 +475,13 @@ def test_gradient_penalty_forward_value(cuda_dev):
     D = dcgan.DCGANDiscriminator(size, 3, 64, nonlinearity=torch.nn.LeakyReLU(0.2),
                                  last_nonlinearity=torch.nn.LeakyReLU(0.2)).to(cuda_dev).train()
     D.load_state_dict(oD.state_dict())
-    x = torch.rand(B, 3, size, size, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    # a head pre-activation next to zero flips the LeakyReLU' of the whole sample between bf16 and fp32 (slope 0.2 vs 1):
+    # a legitimate kink, not an error -- take the first seeded batch whose critic outputs stay clear of it
+    for seed in range(5, 40):
+        x = torch.rand(B, 3, size, size, generator=torch.Generator().manual_seed(seed)) * 2 - 1
+        with torch.no_grad():
+            if oD(x).abs().min().item() > 0.05:
+                break
     xo = x.clone().requires_grad_()
     ref = O.gradient_penalty(xo, oD(xo)).item()
     xm = x.to(cuda_dev).requires_grad_()
