@@ -284,7 +284,7 @@ int rg_clamp(float* p, size_t n, float lo, float hi, rg_stream_t st);
  * a symmetric buffer (every rank's copy at the same offset), the calling rank reduces floats [offset, offset+n) --
  * multimem.ld_reduce (fp32 sum inside the switch) then multimem.st (broadcast to every copy).  Ranks call it for disjoint
  * slices between two barriers; replaces the NCCL all-reduce of G/D gradients (src/histopathology_gan.py runs one process;
- * SURVEY.md 8e shards by batch).  max_ctas bounds the SMs it may take (0: 32). */
+ * SURVEY.md 8e shards by batch).  max_ctas bounds its CTAs of 128 threads (0: 128); the CTAs are small enough to co-reside with a tile-engine CTA. */
 int rg_nvls_allreduce(float* mc, size_t offset, size_t n, int max_ctas, rg_stream_t st);
 /* data-parallel gradient exchange (what DistributedDataParallel's all-reduce would do around the
  * reference): out[i] = sum over r < nparts of src[r * stride + i], r ascending -- the reduction step of the peer-to-peer

@@ -1108,7 +1108,9 @@ __global__ void __launch_bounds__(256) slices_sum_kernel(const float* __restrict
 // result back into every GPU's copy.  Each element is reduced exactly once (by the rank that owns its slice) and then
 // broadcast, so all ranks end with bit-identical values.  Needs a barrier before (all contributions written) and
 // after (all stores landed); a handful of CTAs saturates the link, the rest of the GPU keeps computing.
-__global__ void __launch_bounds__(512) nvls_allreduce_kernel(float* mc, size_t n4) {
+// CTAs of 128 threads and <= 64 registers: small enough to CO-RESIDE with a persistent tile-engine CTA (224 threads x 236
+// registers, ~200 KiB of shared memory) on the same SM, so the exchange does not displace GEMM CTAs into a second wave.
+__global__ void __launch_bounds__(128, 4) nvls_allreduce_kernel(float* mc, size_t n4) {
   // a switch round trip costs microseconds: keep kU independent 16-byte reductions in flight per thread
   constexpr int kU = 8;
   const size_t step = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -1801,9 +1803,9 @@ int rg_nvls_allreduce(float* mc, size_t offset, size_t n, int max_ctas, rg_strea
   RG_CHECK_ARG(mc && n > 0 && n % 4 == 0 && offset % 4 == 0 && reinterpret_cast<uintptr_t>(mc) % 16 == 0,
                "rg_nvls_allreduce: need a 16-byte aligned multicast pointer and offset / n multiples of 4 floats");
   const size_t n4 = n / 4;
-  const int cap = max_ctas > 0 ? max_ctas : 32;
-  const int grid = static_cast<int>(std::min<size_t>((n4 + 8 * 512 - 1) / (8 * 512), static_cast<size_t>(cap)));
-  nvls_allreduce_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(st)>>>(mc + offset, n4);
+  const int cap = max_ctas > 0 ? max_ctas : 128;
+  const int grid = static_cast<int>(std::min<size_t>((n4 + 8 * 128 - 1) / (8 * 128), static_cast<size_t>(cap)));
+  nvls_allreduce_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(st)>>>(mc + offset, n4);
   RG_LAUNCH_CHECK("rg_nvls_allreduce");
   return 0;
 }
