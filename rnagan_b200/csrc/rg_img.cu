@@ -12,6 +12,7 @@
 // mma.sync.m16n8k16 bf16 fragments (fp32 accumulate) -- the tensor pipe is idle >90 % of the time here either way, so the
 // point of the MMA is only to keep the arithmetic off the critical path; tcgen05 / TMEM would buy nothing.
 #include <algorithm>
+#include <stdlib.h>
 #include <type_traits>
 #include "rg_host.cuh"
 #include "rg_ptx.cuh"
@@ -53,16 +54,56 @@ __device__ __forceinline__ void cp_commit_wait_all() {
 }
 
 constexpr int kTH = 8, kTW = 32;                  // low-resolution pixels per CTA tile (the 64-channel side)
+constexpr int kWgTH = 4;                          // the weight-gradient kernel walks 4 x 32 tiles (two stages fit four CTAs per SM)
 constexpr int kThreads = 128;                     // 4 warps: warp w owns tile rows 2w, 2w+1
 constexpr int kCtasPerSm = 4;                     // small CTAs, several per SM: one CTA's tile load overlaps the others' math
 constexpr int kC = 64;                            // channels of the 64-channel side (step_channels)
 
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~static_cast<uintptr_t>(1023));
+}
+
 // ------------------------------------------------------------------------------------------------ image patch (fp32)
-// patch[c][r][kPX + gxl]: image rows 2*y0-1 .. 2*y0+2*kTH (r = 0 .. kPR-1), columns gxl = gx - 2*x0 in [-1, 2*kTW] (zero
-// outside the image), optionally transformed while loading.  The 64 interior columns of a row are 16 aligned float4 loads
-// (all of a thread's loads are issued before the first use), the two halo columns are scalars.
-constexpr int kPR = 2 * kTH + 2, kPX = 4, kPitch = 72;
+// One stage holds `planes` planes (the CIMG channels of x, then -- for the modes that need it -- the CIMG channels of y) of
+// R = 2*TH + 2 image rows 2*y0-1 .. 2*y0+2*TH; a row is kPitch = 72 floats = 18 aligned float4 covering the image columns
+// gxl = gx - 2*x0 in [-4, 67] at kPX + gxl (the taps use [-1, 64]; zero outside the image).  The stage is filled with
+// 16-byte cp.async (zero-fill for out-of-image vectors): no registers are staged, so the NEXT tile's patch is in flight
+// while the current one is contracted.  Thread t < 126 owns column vector v = t % 18 of rows rr, rr+7, rr+14 (rr = t / 18)
+// of EVERY plane -- the thread that copied an x vector also copied the matching y vector, so the transform below needs no
+// barrier between the copy and the arithmetic, only the thread's own cp.async.wait_group.
+constexpr int kPX = 4, kPitch = 72, kPVec = kPitch / 4;
 constexpr int kMaxCimg = 4;
+
+template <int TH, int CIMG>
+__device__ __forceinline__ void patch_prefetch(uint32_t stage, const float* __restrict__ x, const float* __restrict__ y,
+                                               int b, int S, int y0, int x0, int v, int rr) {
+  constexpr int R = 2 * TH + 2;
+  if (rr >= 7) return;                                          // threads 126, 127
+  const int gx = 2 * x0 - 4 + 4 * v;
+  const bool okx = gx >= 0 && gx < S;                           // S and gx are multiples of 4: a vector is all in or all out
+  const size_t img0 = static_cast<size_t>(b) * CIMG * S * S;
+  const float* xb = x + img0;
+  const float* yb = y != nullptr ? y + img0 : nullptr;
+#pragma unroll
+  for (int k = 0; k < (R + 6) / 7; ++k) {
+    const int r = rr + 7 * k;
+    if (r < R) {
+      const int gy = 2 * y0 - 1 + r;
+      const bool ok = okx && gy >= 0 && gy < S;
+      const int off = ok ? gy * S + gx : 0;
+      const int nbytes = ok ? 16 : 0;
+      const uint32_t d = stage + static_cast<uint32_t>((r * kPitch + 4 * v) * 4);
+#pragma unroll
+      for (int c = 0; c < CIMG; ++c) {
+        cp16_zfill(d + c * (R * kPitch * 4), xb + c * S * S + off, nbytes);
+        if (yb != nullptr) cp16_zfill(d + (CIMG + c) * (R * kPitch * 4), yb + c * S * S + off, nbytes);
+      }
+    }
+  }
+}
 
 __device__ __forceinline__ float img_xform(float t, float y, int mode, float eps, float mul) {
   if (mode == 1) t = eps * t + (1.0f - eps) * y;
@@ -70,55 +111,30 @@ __device__ __forceinline__ float img_xform(float t, float y, int mode, float eps
   return t * mul;
 }
 
-// mode 0: x * mul;  1: eps*x + (1-eps)*y (gradient-penalty interpolate);  2: x * (1 - y^2) (tanh backward, y = tanh)
-__device__ __forceinline__ void load_img_patch(float* patch, const float* __restrict__ x, const float* __restrict__ y,
-                                               int mode, float eps, float mul, int b, int Cimg, int S, int y0, int x0) {
-  const int nrows = Cimg * kPR;
-  const int nvec = nrows * 16;
-  const size_t img0 = static_cast<size_t>(b) * Cimg * S * S;
-  for (int base = 0; base < nvec; base += kThreads * 4) {
-    float4 xv[4], yv[4];
-    int dst[4];
+// mode 0: x * mul;  1: (eps*x + (1-eps)*y) * mul (gradient-penalty interpolate);  2: x * (1 - y^2) * mul (tanh backward,
+// y = tanh).  In place on the x planes, by the thread that copied the vectors (after its own cp.async.wait_group);
+// zero-filled vectors stay zero.
+template <int TH, int CIMG>
+__device__ __forceinline__ void patch_transform(float* stage, int mode, float eps, float mul, int v, int rr) {
+  constexpr int R = 2 * TH + 2;
+  if (rr >= 7) return;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = base + j * kThreads + threadIdx.x;
-      xv[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      yv[j] = xv[j];
-      dst[j] = -1;
-      if (i < nvec) {
-        const int row = i >> 4, v = i & 15;
-        const int c = row / kPR, r = row - c * kPR;
-        const int gy = 2 * y0 - 1 + r, gx = 2 * x0 + 4 * v;
-        dst[j] = row * kPitch + kPX + 4 * v;
-        if (gy >= 0 && gy < S && gx < S) {
-          const size_t o = img0 + (static_cast<size_t>(c) * S + gy) * S + gx;
-          xv[j] = __ldg(reinterpret_cast<const float4*>(x + o));
-          if (mode != 0) yv[j] = __ldg(reinterpret_cast<const float4*>(y + o));
-        }
+  for (int k = 0; k < (R + 6) / 7; ++k) {
+    const int r = rr + 7 * k;
+    if (r < R) {
+#pragma unroll
+      for (int c = 0; c < CIMG; ++c) {
+        float4* px = reinterpret_cast<float4*>(stage + (c * R + r) * kPitch + 4 * v);
+        float4 t = *px;
+        float4 yv = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (mode != 0) yv = *reinterpret_cast<const float4*>(stage + ((CIMG + c) * R + r) * kPitch + 4 * v);
+        t.x = img_xform(t.x, yv.x, mode, eps, mul);
+        t.y = img_xform(t.y, yv.y, mode, eps, mul);
+        t.z = img_xform(t.z, yv.z, mode, eps, mul);
+        t.w = img_xform(t.w, yv.w, mode, eps, mul);
+        *px = t;
       }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (dst[j] >= 0) {
-        float4 t;
-        t.x = img_xform(xv[j].x, yv[j].x, mode, eps, mul);
-        t.y = img_xform(xv[j].y, yv[j].y, mode, eps, mul);
-        t.z = img_xform(xv[j].z, yv[j].z, mode, eps, mul);
-        t.w = img_xform(xv[j].w, yv[j].w, mode, eps, mul);
-        *reinterpret_cast<float4*>(patch + dst[j]) = t;
-      }
-    }
-  }
-  for (int i = threadIdx.x; i < nrows * 2; i += kThreads) {
-    const int row = i >> 1, gxl = (i & 1) ? 2 * kTW : -1;
-    const int c = row / kPR, r = row - c * kPR;
-    const int gy = 2 * y0 - 1 + r, gx = 2 * x0 + gxl;
-    float t = 0.0f;
-    if (gy >= 0 && gy < S && gx >= 0 && gx < S) {
-      const size_t o = img0 + (static_cast<size_t>(c) * S + gy) * S + gx;
-      t = img_xform(__ldg(x + o), mode != 0 ? __ldg(y + o) : 0.0f, mode, eps, mul);
-    }
-    patch[row * kPitch + kPX + gxl] = t;
   }
 }
 
@@ -142,10 +158,13 @@ __device__ __forceinline__ void load_act_tile(uint8_t* tile, const __nv_bfloat16
 // out[b, c, 2i+py, 2j+px] = bias[c] + sum_{dy,dx,p} lo[b, i+dy, j+dx, p] * W[p, c, py+1-2dy, px+1-2dx]
 // Per 16-pixel M tile and channel chunk: one A fragment per shift (dy,dx), two accumulator tiles (py = 0 / 1) whose 8
 // columns are (px, c) pairs; a shift with dy = -1 feeds only py = 0, dy = +1 only py = 1, dy = 0 both: 12 MMAs per chunk.
+// The halo'd tile (10 x 34 pixels x 128 B) arrives through ONE TMA box load (SWIZZLE_128B = the chunk ^ (P & 7) layout
+// ldmatrix wants; out-of-image pixels are zero-filled by the TMA unit): the per-thread cp.async loop it replaces was a
+// third of the kernel's instructions, and the kernel is issue-bound (ncu: 53 % issue-active at 24 % occupancy).
 constexpr int kUpPH = kTH + 2, kUpPW = kTW + 2;
 constexpr int kUpTileBytes = kUpPH * kUpPW * 128;            // 43520
 constexpr int kUpFragBytes = 12 * 4 * 32 * 8;                // (py, shift) x channel chunk x lane x {b0, b1}
-constexpr int kUpSmem = kUpTileBytes + kUpFragBytes;
+constexpr int kUpSmem = 1024 + kUpTileBytes + kUpFragBytes + 16;   // alignment slack + tile + B fragments + mbarrier
 
 // B fragments of conv_up, ready for mma.sync: entry ((combo*4 + kc)*32 + lane) = {b0, b1} with
 // combo = py*6 + (dy - dymin(py))*3 + (dx+1) and B[k = channel][n = px*Cimg + c] = W[k][c][py+1-2dy][px+1-2dx]
@@ -171,19 +190,32 @@ __global__ void img_up_pack_kernel(const float* __restrict__ Wt, int Cimg, uint2
 
 template <int Cimg>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const uint2* __restrict__ bfrag_g, const float* __restrict__ bias,
-                   void* __restrict__ out, int B, int H, int W, int flags, const float* __restrict__ bn_scale,
-                   const float* __restrict__ bn_shift, float bn_slope) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+img_conv_up_kernel(const __grid_constant__ CUtensorMap lomap, int use_tma, const __nv_bfloat16* __restrict__ lo,
+                   const uint2* __restrict__ bfrag_g, const float* __restrict__ bias, void* __restrict__ out, int B, int H,
+                   int W, int flags, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                   float bn_slope) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
   uint8_t* tile = smem;
   uint2* bfrag = reinterpret_cast<uint2*>(smem + kUpTileBytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kUpTileBytes + kUpFragBytes);
   const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
-  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, b = blockIdx.x / (tiles_x * tiles_y);
+  const int txs = 31 - __clz(tiles_x), tys = 31 - __clz(tiles_y);          // H, W are powers of two: so are the tile counts
+  const int tx = blockIdx.x & (tiles_x - 1), ty = (blockIdx.x >> txs) & (tiles_y - 1), b = blockIdx.x >> (txs + tys);
   const int y0 = ty * kTH, x0 = tx * kTW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
 
-  load_act_tile(tile, lo, b, H, W, y0 - 1, x0 - 1, kUpPH, kUpPW);
+  if (use_tma) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_barrier_init();
+      mbar_expect_tx(bar, kUpTileBytes);
+      tma_load_4d(&lomap, bar, tile, 0, x0 - 1, y0 - 1, b);
+    }
+  } else {
+    load_act_tile(tile, lo, b, H, W, y0 - 1, x0 - 1, kUpPH, kUpPW);
+  }
   {
     const uint32_t fb = smem_u32(bfrag);
     for (int i = threadIdx.x; i < kUpFragBytes / 16; i += kThreads)
@@ -202,7 +234,8 @@ img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const uint2* __restrict
     sh[0] = ha.x; sh[1] = ha.y; sh[2] = ha.z; sh[3] = ha.w; sh[4] = hb.x; sh[5] = hb.y; sh[6] = hb.z; sh[7] = hb.w;
   }
   cp_commit_wait_all();
-  __syncthreads();
+  __syncthreads();                       // B fragments (and the cp.async tile) landed; the mbarrier init is visible
+  if (use_tma) mbar_wait(bar, 0);
   if (bn_scale != nullptr) {
     // `lo` is the PRE-BatchNorm activation a: h = lrelu(scale * a + shift) is applied to the staged tile in place (same
     // arithmetic and bf16 rounding as rg_bn_act, so h is never written to HBM); halo pixels outside the image stay zero
@@ -266,54 +299,64 @@ img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const uint2* __restrict
   }
   __syncthreads();                       // the activation tile is dead: reuse it as the output staging buffer
 
-  // ---- epilogue: bias, tanh, layout / dtype of the output, staged so that global stores are whole 16-byte vectors
+  // ---- epilogue: bias, tanh, layout / dtype of the output, staged so that global stores are whole 16-byte vectors.
+  // This lane's two accumulator columns n = 2q, 2q+1 are (px, c) pairs with n = px*Cimg + c: both valid iff q < Cimg, and
+  // in the NHWC formats they are ADJACENT elements of the staged row (offset 2*Cimg*xl + n), so a lane stores pairs.
   const int OH = 2 * H, OW = 2 * W;
   const bool do_tanh = (flags & 1) != 0, unit = (flags & 2) != 0, u8 = (flags & 4) != 0, bgr = (flags & 8) != 0;
   float* stf = reinterpret_cast<float*>(smem);
   uint8_t* stb = smem;
-  // this lane's two accumulator columns n = 2q, 2q+1 are fixed: (px, c) and the bias are per-lane constants
-  int npx[2], nc[2];
-  float nb[2];
-  bool nvalid[2];
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int n = 2 * q + e;
-    nvalid[e] = n < 2 * Cimg;
-    npx[e] = n / Cimg;
-    nc[e] = n - npx[e] * Cimg;
-    nb[e] = (bias != nullptr && nvalid[e]) ? __ldg(bias + nc[e]) : 0.0f;
-  }
-  // mode: 0 fp32 NCHW, 1 fp32 NHWC unit range, 2 uint8 NHWC -- one specialised staging loop each
-  auto stage_out = [&](auto mode_tag) {
-    constexpr int MODE = decltype(mode_tag)::value;
+  if (q < Cimg) {
+    const int n0 = 2 * q, n1 = 2 * q + 1;
+    const int px0 = n0 / Cimg, c0 = n0 - px0 * Cimg, px1 = n1 / Cimg, c1 = n1 - px1 * Cimg;
+    const float nb0 = bias != nullptr ? __ldg(bias + c0) : 0.0f, nb1 = bias != nullptr ? __ldg(bias + c1) : 0.0f;
+    // element offsets of this lane for (m = 0, t = 0, h = 0); the loop adds compile-time constants
+    const int yl_w = 2 * warp;
+    int off0, off1;                                   // per-format lane bases of the two columns
+    if (u8 || unit) {
+      const bool rev = u8 && bgr;
+      const int o0 = rev ? px0 * Cimg + (Cimg - 1 - c0) : n0, o1 = rev ? px1 * Cimg + (Cimg - 1 - c1) : n1;
+      off0 = (2 * yl_w * 64 + 2 * g) * Cimg + o0;
+      off1 = (2 * yl_w * 64 + 2 * g) * Cimg + o1;
+    } else {
+      off0 = (c0 * (2 * kTH) + 2 * yl_w) * 64 + 2 * g + px0;
+      off1 = (c1 * (2 * kTH) + 2 * yl_w) * 64 + 2 * g + px1;
+    }
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      const int yl = 2 * warp + (m >> 1), xl0 = (m & 1) * 16;
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (!nvalid[e & 1]) continue;
-          const int px = npx[e & 1], c = nc[e & 1];
-          const int Yl = 2 * yl + t, Xl = 2 * (xl0 + g + (e >> 1) * 8) + px;
-          float v = acc[m][t][e] + nb[e & 1];
-          if (do_tanh) v = tanh_fast(v);
-          if (MODE == 2) {
-            const float u = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
-            stb[(Yl * 64 + Xl) * Cimg + (bgr ? Cimg - 1 - c : c)] =
-                static_cast<uint8_t>(__float2uint_rz(fminf(fmaxf(u, 0.0f), 255.0f)));
-          } else if (MODE == 1) {
-            stf[(Yl * 64 + Xl) * Cimg + c] = (v + 1.0f) * 0.5f;
+        for (int h = 0; h < 2; ++h) {
+          // staged pixel (Yl, Xl) = (2*yl + t, 2*xl + px), yl = 2*warp + (m >> 1), xl = (m & 1)*16 + g + 8*h
+          constexpr int kRowNhwc = 64 * Cimg;
+          const int dY = 2 * (m >> 1) + t, dXl = (m & 1) * 16 + 8 * h;
+          float v0 = acc[m][t][2 * h] + nb0, v1 = acc[m][t][2 * h + 1] + nb1;
+          if (do_tanh) { v0 = tanh_fast(v0); v1 = tanh_fast(v1); }
+          if (u8) {
+            const float u0 = __fmul_rn(__fmul_rn(__fadd_rn(v0, 1.0f), 0.5f), 255.0f);
+            const float u1 = __fmul_rn(__fmul_rn(__fadd_rn(v1, 1.0f), 0.5f), 255.0f);
+            const uint32_t b0 = __float2uint_rz(fminf(fmaxf(u0, 0.0f), 255.0f));
+            const uint32_t b1 = __float2uint_rz(fminf(fmaxf(u1, 0.0f), 255.0f));
+            const int d = dY * kRowNhwc + 2 * Cimg * dXl;
+            if (bgr) {
+              stb[off0 + d] = static_cast<uint8_t>(b0);
+              stb[off1 + d] = static_cast<uint8_t>(b1);
+            } else {
+              *reinterpret_cast<uint16_t*>(stb + off0 + d) = static_cast<uint16_t>(b0 | (b1 << 8));
+            }
+          } else if (unit) {
+            const int d = dY * kRowNhwc + 2 * Cimg * dXl;
+            *reinterpret_cast<float2*>(stf + off0 + d) = make_float2((v0 + 1.0f) * 0.5f, (v1 + 1.0f) * 0.5f);
           } else {
-            stf[(c * (2 * kTH) + Yl) * 64 + Xl] = v;
+            const int d = dY * 64 + 2 * dXl;
+            stf[off0 + d] = v0;
+            stf[off1 + d] = v1;
           }
         }
       }
     }
-  };
-  if (u8) stage_out(std::integral_constant<int, 2>{});
-  else if (unit) stage_out(std::integral_constant<int, 1>{});
-  else stage_out(std::integral_constant<int, 0>{});
+  }
   __syncthreads();
   const int Y0 = 2 * y0, X0 = 2 * x0;
   const int xvalid = min(64, OW - X0);           // multiple of 16 (W is a power of two >= 8)
@@ -349,69 +392,87 @@ img_conv_up_kernel(const __nv_bfloat16* __restrict__ lo, const uint2* __restrict
 
 // =================================================================================================== conv_down (K1)
 // out[b, y, x, p] = act(bias[p] + sum_{c,kh,kw} img[b, c, 2y-1+kh, 2x-1+kw] * W[p, c, kh, kw])   (bf16 NHWC, 64 channels)
-// GEMM view: M = pixels, N = 64, K = Cimg*16 with one k16 step per image channel (k = kh*4 + kw): the A fragment of a lane
+// GEMM view: M = pixels, N = 64, K = CIMG*16 with one k16 step per image channel (k = kh*4 + kw): the A fragment of a lane
 // is four float2 loads of horizontally adjacent taps from the fp32 patch, the B fragments (the whole weight) live in
-// registers for the CTA's life.
-constexpr int kDownPatchBytes = kMaxCimg * kPR * kPitch * 4;          // 43520
+// registers for the CTA's life.  Persistent CTAs, two patch stages: the next tile's cp.async traffic is in flight while
+// the current tile is contracted and stored.
+constexpr int kDownR = 2 * kTH + 2;
 constexpr int kDownStageBytes = (kThreads / 32) * 16 * 128;            // one 16-pixel x 64-channel bf16 tile per warp
-constexpr int kDownSmem = kDownPatchBytes + kDownStageBytes;
+__host__ __device__ constexpr int down_patch_bytes(int cimg, int mode) {
+  return (mode != 0 ? 2 : 1) * cimg * kDownR * kPitch * 4;
+}
+__host__ __device__ constexpr int down_smem_bytes(int cimg, int mode) {
+  return 2 * down_patch_bytes(cimg, mode) + kDownStageBytes + kC * 4;
+}
 
+template <int CIMG>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 img_conv_down_kernel(const float* __restrict__ x, const float* __restrict__ yimg, int mode,
                      const float* __restrict__ eps_dev, const float* __restrict__ mul_dev, const float* __restrict__ Wt,
                      const float* __restrict__ bias, float slope, const __nv_bfloat16* __restrict__ mask_src,
-                     float mask_slope, __nv_bfloat16* __restrict__ out, int B, int Cimg, int S) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  float* patch = reinterpret_cast<float*>(smem);
+                     float mask_slope, __nv_bfloat16* __restrict__ out, int B, int S) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  const int pbytes = down_patch_bytes(CIMG, mode);
   const int H = S / 2, W = S / 2;
   const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
   const int ntiles = B * tiles_x * tiles_y;
+  const int txs = 31 - __clz(tiles_x), tys = 31 - __clz(tiles_y);          // S is a power of two: so are the tile counts
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
+  const int pv = threadIdx.x % kPVec, prr = threadIdx.x / kPVec;      // this thread's patch vectors (patch_prefetch)
   const float eps = eps_dev ? __ldg(eps_dev) : 0.0f;
   const float mul = mul_dev ? __ldg(mul_dev) : 1.0f;
+  const bool xform = mode != 0 || mul != 1.0f;
+  const float* ysrc = mode != 0 ? yimg : nullptr;
+  uint8_t* stage = smem_dyn + 2 * pbytes + warp * (16 * 128);
+  float* sbias = reinterpret_cast<float*>(smem_dyn + 2 * pbytes + kDownStageBytes);
+  if (threadIdx.x < kC) sbias[threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.0f;   // read after the first barrier
   // B fragments: B[k = kh*4 + kw (channel c)][n = p]; lane holds k = 2q, 2q+1 (kh = q/2) and k + 8 (kh + 2), n = g
-  uint32_t breg[kMaxCimg][8][2];
+  uint32_t breg[CIMG][8][2];
   const int kh0 = q >> 1, kw0 = (q & 1) * 2;
 #pragma unroll
-  for (int c = 0; c < kMaxCimg; ++c)
+  for (int c = 0; c < CIMG; ++c)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
-      if (c < Cimg) {
-        const float* wp = Wt + ((static_cast<size_t>(nt * 8 + g) * Cimg + c) * 4 + kh0) * 4 + kw0;
-        w0 = __ldg(wp); w1 = __ldg(wp + 1); w2 = __ldg(wp + 8); w3 = __ldg(wp + 9);
-      }
-      breg[c][nt][0] = bf2(w0, w1);
-      breg[c][nt][1] = bf2(w2, w3);
+      const float* wp = Wt + ((static_cast<size_t>(nt * 8 + g) * CIMG + c) * 4 + kh0) * 4 + kw0;
+      breg[c][nt][0] = bf2(__ldg(wp), __ldg(wp + 1));
+      breg[c][nt][1] = bf2(__ldg(wp + 8), __ldg(wp + 9));
     }
-  float bv[8][2];
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    bv[nt][0] = bias ? __ldg(bias + nt * 8 + 2 * q) : 0.0f;
-    bv[nt][1] = bias ? __ldg(bias + nt * 8 + 2 * q + 1) : 0.0f;
-  }
-  uint8_t* stage = smem + kDownPatchBytes + warp * (16 * 128);
+  const uint32_t patch_u32 = smem_u32(smem_dyn);
+  auto prefetch = [&](int tile, int s) {
+    const int tx = tile & (tiles_x - 1), ty = (tile >> txs) & (tiles_y - 1), b = tile >> (txs + tys);
+    patch_prefetch<kTH, CIMG>(patch_u32 + s * pbytes, x, ysrc, b, S, ty * kTH, tx * kTW, pv, prr);
+  };
+  int it = 0;
+  if (static_cast<int>(blockIdx.x) < ntiles) prefetch(blockIdx.x, 0);
+  cp_commit();
 #pragma unroll 1
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
-  const int y0 = ty * kTH, x0 = tx * kTW;
-  __syncthreads();                                              // previous patch fully consumed
-  load_img_patch(patch, x, yimg, mode, eps, mul, b, Cimg, S, y0, x0);
-  __syncthreads();
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int cur = it & 1;
+    const int nxt = tile + gridDim.x;
+    if (nxt < ntiles) prefetch(nxt, cur ^ 1);            // stage cur^1 was released by the barrier that ended tile it-1
+    cp_commit();                                         // (possibly empty) group: the count per iteration is uniform
+    cp_wait<1>();                                        // this thread's copies of the current stage have landed
+    float* patch = reinterpret_cast<float*>(smem_dyn + cur * pbytes);
+    if (xform) patch_transform<kTH, CIMG>(patch, mode, eps, mul, pv, prr);
+    __syncthreads();
+    const int tx = tile & (tiles_x - 1), ty = (tile >> txs) & (tiles_y - 1), b = tile >> (txs + tys);
+    const int y0 = ty * kTH, x0 = tx * kTW;
+    // this lane's 16-byte store slot: pixel (lane >> 3) of a group of four, channel chunk lane & 7
+    const size_t obase = ((static_cast<size_t>(b) * H + y0) * W + x0 + (lane >> 3)) * kC + (lane & 7) * 8;
+    const int xlim = W - x0 - (lane >> 3), ylim = H - y0;
 #pragma unroll 1
-  for (int m = 0; m < 4; ++m) {
-    const int yl = 2 * warp + (m >> 1), xl0 = (m & 1) * 16;
-    float acc[8][4];
+    for (int m = 0; m < 4; ++m) {
+      const int yl = 2 * warp + (m >> 1), xl0 = (m & 1) * 16;
+      float acc[8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
 #pragma unroll
-    for (int c = 0; c < kMaxCimg; ++c) {
-      if (c < Cimg) {
+      for (int c = 0; c < CIMG; ++c) {
         // tap (kh, kw) of output pixel (yl, xl) sits at patch row 2*yl + kh, column gxl = 2*xl - 1 + kw
-        const float* pr = patch + (c * kPR + 2 * yl + kh0) * kPitch + kPX - 1 + 2 * (xl0 + g) + kw0;
+        const float* pr = patch + (c * kDownR + 2 * yl + kh0) * kPitch + kPX - 1 + 2 * (xl0 + g) + kw0;
         const uint32_t a[4] = {bf2(pr[0], pr[1]),                                     // row g,     kh0
                                bf2(pr[16], pr[17]),                                   // row g + 8, kh0
                                bf2(pr[2 * kPitch], pr[2 * kPitch + 1]),               // row g,     kh0 + 2
@@ -419,74 +480,93 @@ img_conv_down_kernel(const float* __restrict__ x, const float* __restrict__ yimg
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) mma16816(acc[nt], a, breg[c][nt][0], breg[c][nt][1]);
       }
-    }
-    // epilogue: bias + LeakyReLU, bf16, swizzled per-warp staging (16 pixels x 128 B), then 16-byte global stores
+      // epilogue: bias + LeakyReLU, bf16, swizzled per-warp staging (16 pixels x 128 B), then 16-byte global stores
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 bb = *reinterpret_cast<const float2*>(sbias + nt * 8 + 2 * q);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v0 = acc[nt][2 * h] + bv[nt][0], v1 = acc[nt][2 * h + 1] + bv[nt][1];
-        v0 = v0 > 0.0f ? v0 : v0 * slope;
-        v1 = v1 > 0.0f ? v1 : v1 * slope;
-        const int row = g + 8 * h;
-        *reinterpret_cast<uint32_t*>(stage + row * 128 + ((nt ^ (row & 7)) << 4) + q * 4) = bf2(v0, v1);
+        for (int h = 0; h < 2; ++h) {
+          float v0 = acc[nt][2 * h] + bb.x, v1 = acc[nt][2 * h + 1] + bb.y;
+          v0 = v0 > 0.0f ? v0 : v0 * slope;
+          v1 = v1 > 0.0f ? v1 : v1 * slope;
+          const int row = g + 8 * h;
+          *reinterpret_cast<uint32_t*>(stage + row * 128 + ((nt ^ (row & 7)) << 4) + q * 4) = bf2(v0, v1);
+        }
       }
-    }
-    __syncwarp();
+      __syncwarp();
+      if (yl < ylim) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int vi = it * 32 + lane, row = vi >> 3, ch = vi & 7;
-      const int gy = y0 + yl, gx = x0 + xl0 + row;
-      if (gy < H && gx < W) {
-        uint4 v = *reinterpret_cast<const uint4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
-        const size_t o = ((static_cast<size_t>(b) * H + gy) * W + gx) * kC + ch * 8;
-        if (mask_src != nullptr) {          // LeakyReLU backward mask from a stored activation: out *= (m > 0 ? 1 : slope)
-          const uint4 mk = *reinterpret_cast<const uint4*>(mask_src + o);
-          const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk);
-          __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&v);
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int row = i4 * 4 + (lane >> 3), ch = lane & 7;
+          if (xl0 + i4 * 4 < xlim) {
+            uint4 v = *reinterpret_cast<const uint4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
+            const size_t o = obase + static_cast<size_t>((yl * W + xl0 + i4 * 4) * kC);
+            if (mask_src != nullptr) {        // LeakyReLU backward mask from a stored activation: out *= (m > 0 ? 1 : slope)
+              const uint4 mk = *reinterpret_cast<const uint4*>(mask_src + o);
+              const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk);
+              __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&v);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 mf = __bfloat1622float2(mh[e]);
-            float2 vf = __bfloat1622float2(vh[e]);
-            vf.x *= mf.x > 0.0f ? 1.0f : mask_slope;
-            vf.y *= mf.y > 0.0f ? 1.0f : mask_slope;
-            vh[e] = __floats2bfloat162_rn(vf.x, vf.y);
+              for (int e = 0; e < 4; ++e) {
+                const float2 mf = __bfloat1622float2(mh[e]);
+                float2 vf = __bfloat1622float2(vh[e]);
+                vf.x *= mf.x > 0.0f ? 1.0f : mask_slope;
+                vf.y *= mf.y > 0.0f ? 1.0f : mask_slope;
+                vh[e] = __floats2bfloat162_rn(vf.x, vf.y);
+              }
+            }
+            *reinterpret_cast<uint4*>(out + o) = v;
           }
         }
-        *reinterpret_cast<uint4*>(out + o) = v;
       }
+      __syncwarp();
     }
-    __syncwarp();
+    __syncthreads();                                            // every warp is done with this stage's patch
   }
-  }
+  cp_wait<0>();
 }
 
 // =================================================================================================== wgrad (K3)
 // part[cta][p][n] = sum over the CTA's tiles and pixels of act[b, y, x, p] * img'[b, c, 2y-1+kh, 2x-1+kw],
-// n = (c*2 + kh/2)*8 + (kh%2)*4 + kw; column 2*Cimg*8 holds sum act (the bias gradient of the 64-channel side).
+// n = (c*2 + kh/2)*8 + (kh%2)*4 + kw; column 2*CIMG*8 holds sum act (the bias gradient of the 64-channel side).
 // GEMM view: M = p (64), N = taps, K = pixels.  A (p x pixel) comes transposed out of the activation tile with
-// ldmatrix.trans; B (pixel x tap) is gathered from the fp32 patch.  Warp w: pixel rows {w>>1, (w>>1)+2, ...} of the
-// tile, n tiles (w&1)*4 .. +3.  Fixed order everywhere: bit-reproducible.
-constexpr int kWgActBytes = kTH * kTW * 128;                   // 32768
-constexpr int kWgSmem = kWgActBytes + kDownPatchBytes;
+// ldmatrix.trans; B (pixel x tap) is gathered from the fp32 patch.  Warp w: pixel rows {w>>1, (w>>1)+2} of the 4 x 32
+// tile, n tiles (w&1)*4 .. +3.  Fixed order everywhere: bit-reproducible.  Two stages: the activation tile of the next
+// tile arrives through one TMA box load (SWIZZLE_128B = the layout ldmatrix wants), its image patch through cp.async,
+// both in flight while the current tile is contracted.
+constexpr int kWgR = 2 * kWgTH + 2;
+constexpr int kWgActBytes = kWgTH * kTW * 128;                 // 16384 per stage; the two stages later hold the 32 KiB reduction
 constexpr int kWgN = 64;                                       // padded number of output columns
+__host__ __device__ constexpr int wg_patch_bytes(int cimg, int mode) {
+  return (mode != 0 ? 2 : 1) * cimg * kWgR * kPitch * 4;
+}
+__host__ __device__ constexpr int wg_smem_bytes(int cimg, int mode) {
+  return 1024 + 2 * kWgActBytes + 2 * wg_patch_bytes(cimg, mode) + 16;
+}
 
+template <int CIMG>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-img_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ x,
-                      const float* __restrict__ yimg, int mode, const float* __restrict__ eps_dev,
-                      const float* __restrict__ mul_dev, float* __restrict__ part, int B, int Cimg, int S) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* atile = smem;
-  float* patch = reinterpret_cast<float*>(smem + kWgActBytes);
+img_conv_wgrad_kernel(const __grid_constant__ CUtensorMap amap, int use_tma, const __nv_bfloat16* __restrict__ act,
+                      const float* __restrict__ x, const float* __restrict__ yimg, int mode,
+                      const float* __restrict__ eps_dev, const float* __restrict__ mul_dev, float* __restrict__ part,
+                      int B, int S) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  const int pbytes = wg_patch_bytes(CIMG, mode);
+  uint8_t* patch_base = smem + 2 * kWgActBytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(patch_base + 2 * pbytes);
   const int H = S / 2, W = S / 2;
-  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
+  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kWgTH - 1) / kWgTH;
   const int ntiles = B * tiles_x * tiles_y;
+  const int txs = 31 - __clz(tiles_x), tys = 31 - __clz(tiles_y);          // S is a power of two: so are the tile counts
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int nh = warp & 1, kg = warp >> 1;
+  const int pv = threadIdx.x % kPVec, prr = threadIdx.x / kPVec;
   const float eps = eps_dev ? __ldg(eps_dev) : 0.0f;
   const float mul = mul_dev ? __ldg(mul_dev) : 1.0f;
-  const int bias_nt = 2 * Cimg;                                 // n tile whose column 0 is the all-ones tap
+  const bool xform = mode != 0 || mul != 1.0f;
+  const float* ysrc = mode != 0 ? yimg : nullptr;
+  constexpr int bias_nt = 2 * CIMG;                             // n tile whose column 0 is the all-ones tap
   float acc[4][4][4];
 #pragma unroll
   for (int m = 0; m < 4; ++m)
@@ -494,20 +574,46 @@ img_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ act, const float* __rest
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.0f;
-  const uint32_t atile_u32 = smem_u32(atile);
+  if (use_tma && threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const uint32_t patch_u32 = smem_u32(patch_base);
+  auto issue = [&](int tile, int s) {
+    const int tx = tile & (tiles_x - 1), ty = (tile >> txs) & (tiles_y - 1), b = tile >> (txs + tys);
+    const int y0 = ty * kWgTH, x0 = tx * kTW;
+    if (use_tma) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar[s], kWgActBytes);
+        tma_load_4d(&amap, &bar[s], smem + s * kWgActBytes, 0, x0, y0, b);
+      }
+    } else {
+      load_act_tile(smem + s * kWgActBytes, act, b, H, W, y0, x0, kWgTH, kTW);
+    }
+    patch_prefetch<kWgTH, CIMG>(patch_u32 + s * pbytes, x, ysrc, b, S, y0, x0, pv, prr);
+  };
   // ldmatrix.trans addressing: lanes 0-7 / 8-15 -> pixels 0-7, channel chunk 2m / 2m+1; lanes 16-31 -> pixels 8-15
   const int lpx = (lane & 7) + (lane >> 4) * 8, lch = (lane >> 3) & 1;
   const uint32_t one_bf2 = bf2(1.0f, 1.0f);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
-    const int y0 = ty * kTH, x0 = tx * kTW;
-    __syncthreads();                                            // previous tile fully consumed
-    load_act_tile(atile, act, b, H, W, y0, x0, kTH, kTW);
-    load_img_patch(patch, x, yimg, mode, eps, mul, b, Cimg, S, y0, x0);
-    cp_commit_wait_all();
-    __syncthreads();
+  int it = 0;
+  if (static_cast<int>(blockIdx.x) < ntiles) issue(blockIdx.x, 0);
+  cp_commit();
 #pragma unroll 1
-    for (int yl = kg; yl < kTH; yl += kThreads / 64) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int cur = it & 1;
+    const int nxt = tile + gridDim.x;
+    if (nxt < ntiles) issue(nxt, cur ^ 1);               // stage cur^1 was released by the barrier that ended tile it-1
+    cp_commit();
+    cp_wait<1>();
+    float* patch = reinterpret_cast<float*>(patch_base + cur * pbytes);
+    if (xform) patch_transform<kWgTH, CIMG>(patch, mode, eps, mul, pv, prr);
+    if (use_tma) mbar_wait(&bar[cur], (it >> 1) & 1);
+    __syncthreads();
+    const uint32_t atile_u32 = smem_u32(smem + cur * kWgActBytes);
+#pragma unroll 1
+    for (int yl = kg; yl < kWgTH; yl += kThreads / 64) {
 #pragma unroll 1
       for (int xs = 0; xs < 2; ++xs) {
         const int xl0 = xs * 16;
@@ -523,7 +629,7 @@ img_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ act, const float* __rest
           uint32_t b0, b1;
           if (nt < bias_nt) {
             const int c = nt >> 1, kh = (nt & 1) * 2 + (g >> 2), kw = g & 3;
-            const float* pr = patch + (c * kPR + 2 * yl + kh) * kPitch + kPX - 1 + 2 * (xl0 + 2 * q) + kw;
+            const float* pr = patch + (c * kWgR + 2 * yl + kh) * kPitch + kPX - 1 + 2 * (xl0 + 2 * q) + kw;
             b0 = bf2(pr[0], pr[2]);                             // pixels xl0+2q, xl0+2q+1
             b1 = bf2(pr[16], pr[18]);                           // pixels +8
           } else if (nt == bias_nt) {
@@ -536,10 +642,11 @@ img_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ act, const float* __rest
         }
       }
     }
+    __syncthreads();                                            // every warp is done with this stage
   }
-  // cross-warp reduction over the four pixel groups (fixed order), then one [64][64] partial per CTA
-  __syncthreads();
-  float* red = reinterpret_cast<float*>(smem);                  // [2 kg][64 p][64 n] = 32 KiB (the activation tile)
+  cp_wait<0>();
+  // cross-warp reduction over the two pixel groups (fixed order), then one [64][64] partial per CTA
+  float* red = reinterpret_cast<float*>(smem);                  // [2 kg][64 p][64 n] = 32 KiB (the two activation stages)
 #pragma unroll
   for (int m = 0; m < 4; ++m)
 #pragma unroll
@@ -584,17 +691,103 @@ __global__ void __launch_bounds__(256) img_wgrad_finish_kernel(const float* __re
   }
 }
 
-int ensure_img_attrs() {
-  static bool done = false;
-  if (!done) {
-    RG_CUDA(cudaFuncSetAttribute(img_conv_up_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
-    RG_CUDA(cudaFuncSetAttribute(img_conv_up_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
-    RG_CUDA(cudaFuncSetAttribute(img_conv_up_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
-    RG_CUDA(cudaFuncSetAttribute(img_conv_up_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
-    RG_CUDA(cudaFuncSetAttribute(img_conv_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDownSmem));
-    RG_CUDA(cudaFuncSetAttribute(img_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
-    done = true;
+// ------------------------------------------------------------------------------------------------ host side
+// Per (kernel instantiation, patch-mode class): opt into the dynamic shared-memory size once and ask the runtime how many
+// CTAs fit per SM (the modes that stage y as well have twice the patch bytes: three CTAs per SM instead of four).
+struct ImgLaunch {
+  int ctas_per_sm = 0;      // 0: not initialised
+};
+
+template <typename K>
+static int img_prepare(ImgLaunch& L, K kernel, int smem_max, int smem) {
+  if (L.ctas_per_sm > 0) return 0;
+  RG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  int n = 0;
+  RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem));
+  if (n < 1) {
+    set_error("image-side kernel does not fit an SM with %d bytes of shared memory", smem);
+    return RG_EINVAL;
   }
+  L.ctas_per_sm = std::min(n, kCtasPerSm);
+  return 0;
+}
+
+// TMA view of the bf16 NHWC activation [B][H][W][64] with a (64, bw, bh, 1) box.  A box may be larger than the tensor
+// (small test images): should a driver refuse that, the kernels fall back to their cp.async tile loader.
+static int img_act_map(CUtensorMap* m, const void* act, int B, int H, int W, int bw, int bh, int* use_tma) {
+  memset(m, 0, sizeof(*m));
+  static int env_off = -1;                   // RG_IMG_TMA=0: debugging aid, forces the cp.async tile loader
+  if (env_off < 0) {
+    const char* e = getenv("RG_IMG_TMA");
+    env_off = (e && e[0] == '0') ? 1 : 0;
+  }
+  if (env_off) {
+    *use_tma = 0;
+    return 0;
+  }
+  *use_tma = 1;
+  const int rc = encode_map_4d(m, act, kC, W, H, B, kC, static_cast<uint64_t>(W) * kC,
+                               static_cast<uint64_t>(H) * W * kC, kC, bw, bh, 1);
+  if (rc != 0) {
+    if (W >= bw && H >= bh) return rc;       // a real error
+    *use_tma = 0;
+  }
+  return 0;
+}
+
+template <int CIMG>
+static int launch_up(const void* lo, const void* wfrag, const float* bias, int flags, int B, int H, int Wd, void* out,
+                     const float* bn_scale, const float* bn_shift, float bn_slope, cudaStream_t s) {
+  static ImgLaunch L;
+  if (int rc = img_prepare(L, img_conv_up_kernel<CIMG>, kUpSmem, kUpSmem)) return rc;
+  CUtensorMap map;
+  int use_tma = 0;
+  if (int rc = img_act_map(&map, lo, B, H, Wd, kUpPW, kUpPH, &use_tma)) return rc;
+  const int grid = B * ceil_div(H, kTH) * ceil_div(Wd, kTW);
+  img_conv_up_kernel<CIMG><<<grid, kThreads, kUpSmem, s>>>(map, use_tma, static_cast<const __nv_bfloat16*>(lo),
+                                                           static_cast<const uint2*>(wfrag), bias, out, B, H, Wd, flags,
+                                                           bn_scale, bn_shift, bn_slope);
+  RG_LAUNCH_CHECK("rg_img_conv_up");
+  return 0;
+}
+
+template <int CIMG>
+static int launch_down(const float* x, const float* y, int mode, const float* eps_dev, const float* mul_dev,
+                       const float* W, const float* bias, float slope, const void* mask_src, float mask_slope, int B,
+                       int S, void* out, cudaStream_t s) {
+  static ImgLaunch L[2];
+  const int smem = down_smem_bytes(CIMG, mode);
+  ImgLaunch& l = L[mode != 0];
+  if (int rc = img_prepare(l, img_conv_down_kernel<CIMG>, down_smem_bytes(CIMG, 1), smem)) return rc;
+  const int grid = std::min(B * ceil_div(S / 2, kTH) * ceil_div(S / 2, kTW), l.ctas_per_sm * num_sms());
+  img_conv_down_kernel<CIMG><<<grid, kThreads, smem, s>>>(x, y, mode, eps_dev, mul_dev, W, bias, slope,
+                                                          static_cast<const __nv_bfloat16*>(mask_src), mask_slope,
+                                                          static_cast<__nv_bfloat16*>(out), B, S);
+  RG_LAUNCH_CHECK("rg_img_conv_down");
+  return 0;
+}
+
+template <int CIMG>
+static int launch_wgrad(const void* act, const float* x, const float* y, int mode, const float* eps_dev,
+                        const float* mul_dev, int B, int S, void* ws, size_t ws_bytes, int* grid_out, cudaStream_t s) {
+  static ImgLaunch L[2];
+  const int smem = wg_smem_bytes(CIMG, mode);
+  ImgLaunch& l = L[mode != 0];
+  if (int rc = img_prepare(l, img_conv_wgrad_kernel<CIMG>, wg_smem_bytes(CIMG, 1), smem)) return rc;
+  const int H = S / 2;
+  CUtensorMap map;
+  int use_tma = 0;
+  if (int rc = img_act_map(&map, act, B, H, H, kTW, kWgTH, &use_tma)) return rc;
+  const int ntiles = B * ceil_div(H, kWgTH) * ceil_div(H, kTW);
+  const int grid = std::min(ntiles, l.ctas_per_sm * num_sms());
+  if (ws_bytes < static_cast<size_t>(grid) * 64 * kWgN * sizeof(float)) {
+    set_error("rg_img_conv_wgrad: workspace too small (need %zu bytes)", static_cast<size_t>(grid) * 64 * kWgN * 4);
+    return RG_EWORKSPACE;
+  }
+  img_conv_wgrad_kernel<CIMG><<<grid, kThreads, smem, s>>>(map, use_tma, static_cast<const __nv_bfloat16*>(act), x, y,
+                                                           mode, eps_dev, mul_dev, static_cast<float*>(ws), B, S);
+  RG_LAUNCH_CHECK("rg_img_conv_wgrad");
+  *grid_out = grid;
   return 0;
 }
 
@@ -621,19 +814,13 @@ int rg_img_conv_up(const void* lo, const void* W, const float* bias, int flags, 
                    H >= 8 && Wd >= 8 && ((bn_scale == nullptr) == (bn_shift == nullptr)),
                "rg_img_conv_up: need 64 input channels, 1..4 image channels and power-of-two H, W >= 8 (Cp=%d Cimg=%d H=%d W=%d)",
                Cp, Cimg, H, Wd);
-  if (int rc = ensure_img_attrs()) return rc;
-  const int grid = B * ceil_div(H, kTH) * ceil_div(Wd, kTW);
-  const __nv_bfloat16* lop = static_cast<const __nv_bfloat16*>(lo);
-  const uint2* wf = static_cast<const uint2*>(W);
   cudaStream_t s = static_cast<cudaStream_t>(st);
   switch (Cimg) {
-    case 1: img_conv_up_kernel<1><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags, bn_scale, bn_shift, bn_slope); break;
-    case 2: img_conv_up_kernel<2><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags, bn_scale, bn_shift, bn_slope); break;
-    case 3: img_conv_up_kernel<3><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags, bn_scale, bn_shift, bn_slope); break;
-    default: img_conv_up_kernel<4><<<grid, kThreads, kUpSmem, s>>>(lop, wf, bias, out, B, H, Wd, flags, bn_scale, bn_shift, bn_slope); break;
+    case 1: return launch_up<1>(lo, W, bias, flags, B, H, Wd, out, bn_scale, bn_shift, bn_slope, s);
+    case 2: return launch_up<2>(lo, W, bias, flags, B, H, Wd, out, bn_scale, bn_shift, bn_slope, s);
+    case 3: return launch_up<3>(lo, W, bias, flags, B, H, Wd, out, bn_scale, bn_shift, bn_slope, s);
+    default: return launch_up<4>(lo, W, bias, flags, B, H, Wd, out, bn_scale, bn_shift, bn_slope, s);
   }
-  RG_LAUNCH_CHECK("rg_img_conv_up");
-  return 0;
 }
 
 int rg_img_conv_down(const float* x, const float* y, int mode, const float* eps_dev, const float* mul_dev,
@@ -643,13 +830,13 @@ int rg_img_conv_down(const float* x, const float* y, int mode, const float* eps_
                    mode >= 0 && mode <= 2 && (mode == 0 || y != nullptr) && (mode != 1 || eps_dev != nullptr),
                "rg_img_conv_down: need 64 output channels, 1..4 image channels, a power-of-two side >= 16, mode 0..2 "
                "(Cp=%d Cimg=%d S=%d mode=%d)", Cp, Cimg, S, mode);
-  if (int rc = ensure_img_attrs()) return rc;
-  const int grid = std::min(B * ceil_div(S / 2, kTH) * ceil_div(S / 2, kTW), kCtasPerSm * num_sms());
-  img_conv_down_kernel<<<grid, kThreads, kDownSmem, static_cast<cudaStream_t>(st)>>>(
-      x, y, mode, eps_dev, mul_dev, W, bias, slope, static_cast<const __nv_bfloat16*>(mask_src), mask_slope,
-      static_cast<__nv_bfloat16*>(out), B, Cimg, S);
-  RG_LAUNCH_CHECK("rg_img_conv_down");
-  return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(st);
+  switch (Cimg) {
+    case 1: return launch_down<1>(x, y, mode, eps_dev, mul_dev, W, bias, slope, mask_src, mask_slope, B, S, out, s);
+    case 2: return launch_down<2>(x, y, mode, eps_dev, mul_dev, W, bias, slope, mask_src, mask_slope, B, S, out, s);
+    case 3: return launch_down<3>(x, y, mode, eps_dev, mul_dev, W, bias, slope, mask_src, mask_slope, B, S, out, s);
+    default: return launch_down<4>(x, y, mode, eps_dev, mul_dev, W, bias, slope, mask_src, mask_slope, B, S, out, s);
+  }
 }
 
 size_t rg_img_conv_wgrad_ws_bytes(void) {
@@ -664,17 +851,15 @@ int rg_img_conv_wgrad(const void* act, const float* x, const float* y, int mode,
                    (dbias == nullptr || Cimg <= 3),
                "rg_img_conv_wgrad: need 64 channels, 1..4 image channels (<= 3 with a fused bias gradient), a power-of-two "
                "side >= 16, mode 0..2 (Cp=%d Cimg=%d S=%d mode=%d)", Cp, Cimg, S, mode);
-  if (int rc = ensure_img_attrs()) return rc;
-  const int ntiles = B * ceil_div(S / 2, kTH) * ceil_div(S / 2, kTW);
-  const int grid = std::min(ntiles, kCtasPerSm * num_sms());
-  if (ws_bytes < static_cast<size_t>(grid) * 64 * kWgN * sizeof(float)) {
-    set_error("rg_img_conv_wgrad: workspace too small (need %zu bytes)", static_cast<size_t>(grid) * 64 * kWgN * 4);
-    return RG_EWORKSPACE;
-  }
   cudaStream_t s = static_cast<cudaStream_t>(st);
-  img_conv_wgrad_kernel<<<grid, kThreads, kWgSmem, s>>>(static_cast<const __nv_bfloat16*>(act), x, y, mode, eps_dev,
-                                                        mul_dev, static_cast<float*>(ws), B, Cimg, S);
-  RG_LAUNCH_CHECK("rg_img_conv_wgrad");
+  int grid = 0, rc = 0;
+  switch (Cimg) {
+    case 1: rc = launch_wgrad<1>(act, x, y, mode, eps_dev, mul_dev, B, S, ws, ws_bytes, &grid, s); break;
+    case 2: rc = launch_wgrad<2>(act, x, y, mode, eps_dev, mul_dev, B, S, ws, ws_bytes, &grid, s); break;
+    case 3: rc = launch_wgrad<3>(act, x, y, mode, eps_dev, mul_dev, B, S, ws, ws_bytes, &grid, s); break;
+    default: rc = launch_wgrad<4>(act, x, y, mode, eps_dev, mul_dev, B, S, ws, ws_bytes, &grid, s); break;
+  }
+  if (rc) return rc;
   img_wgrad_finish_kernel<<<64, 256, 0, s>>>(static_cast<const float*>(ws), grid, Cimg, dW, acc, dbias, acc_bias);
   RG_LAUNCH_CHECK("rg_img_conv_wgrad(finish)");
   return 0;
