@@ -264,6 +264,10 @@ img_conv_up_kernel(const __grid_constant__ CUtensorMap lomap, int use_tma, const
     __syncthreads();
   }
 
+  // Warp w owns the four pixel rows 4*(w >> 1) .. +3 of one 16-pixel half (w & 1): M tile m = row 4*(w >> 1) + m.  Shift
+  // (dy, dx) of row m reads halo'd tile row 4*(w >> 1) + m + 1 + dy, so the four rows share SIX tile rows: one ldmatrix
+  // per (tile row, dx, channel chunk) feeds every (m, dy) pair that lands on it -- 72 ldmatrix per tile instead of 144
+  // (the kernel is bound by shared-memory bandwidth: 512 B per ldmatrix against 1-2 N = 8 MMAs).
   float acc[4][2][4];
 #pragma unroll
   for (int m = 0; m < 4; ++m)
@@ -274,25 +278,31 @@ img_conv_up_kernel(const __grid_constant__ CUtensorMap lomap, int use_tma, const
   // ldmatrix row of this lane inside an M tile: pixel i = (lane & 7) + 8 * ((lane >> 3) & 1), k half = lane >> 4
   const int li = (lane & 7) + ((lane >> 3) & 1) * 8, lk = lane >> 4;
   const uint32_t tile_u32 = smem_u32(tile);
-  int P0[4];
-#pragma unroll
-  for (int m = 0; m < 4; ++m) P0[m] = (2 * warp + (m >> 1) + 1) * kUpPW + (m & 1) * 16 + 1 + li;
+  const int rg4 = 4 * (warp >> 1), xh = (warp & 1) * 16;
+  const int Pw = rg4 * kUpPW + xh + 1 + li;            // halo'd tile row rg4, shift dx = 0
 #pragma unroll 1
   for (int kc = 0; kc < 4; ++kc) {
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
+    for (int dx = -1; dx <= 1; ++dx) {
+      // B fragments of this (kc, dx): py = 0 takes dy = -1, 0; py = 1 takes dy = 0, +1
+      const uint2 b0m = bfrag[((0 * 3 + dx + 1) * 4 + kc) * 32 + lane];     // py 0, dy -1
+      const uint2 b0z = bfrag[((1 * 3 + dx + 1) * 4 + kc) * 32 + lane];     // py 0, dy  0
+      const uint2 b1z = bfrag[((6 + dx + 1) * 4 + kc) * 32 + lane];         // py 1, dy  0
+      const uint2 b1p = bfrag[((6 + 3 + dx + 1) * 4 + kc) * 32 + lane];     // py 1, dy +1
 #pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        uint2 b0 = make_uint2(0u, 0u), b1 = make_uint2(0u, 0u);
-        if (dy <= 0) b0 = bfrag[(((dy + 1) * 3 + dx + 1) * 4 + kc) * 32 + lane];
-        if (dy >= 0) b1 = bfrag[((6 + dy * 3 + dx + 1) * 4 + kc) * 32 + lane];
+      for (int tr = 0; tr < 6; ++tr) {
+        const int P = Pw + tr * kUpPW + dx;
+        uint32_t a[4];
+        ldsm_x4(a, tile_u32 + P * 128 + (((kc * 2 + lk) ^ (P & 7)) << 4));
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          const int P = P0[m] + dy * kUpPW + dx;
-          uint32_t a[4];
-          ldsm_x4(a, tile_u32 + P * 128 + (((kc * 2 + lk) ^ (P & 7)) << 4));
-          if (dy <= 0) mma16816(acc[m][0], a, b0.x, b0.y);
-          if (dy >= 0) mma16816(acc[m][1], a, b1.x, b1.y);
+          const int dy = tr - 1 - m;
+          if (dy == -1) mma16816(acc[m][0], a, b0m.x, b0m.y);
+          if (dy == 0) {
+            mma16816(acc[m][0], a, b0z.x, b0z.y);
+            mma16816(acc[m][1], a, b1z.x, b1z.y);
+          }
+          if (dy == 1) mma16816(acc[m][1], a, b1p.x, b1p.y);
         }
       }
     }
@@ -311,16 +321,16 @@ img_conv_up_kernel(const __grid_constant__ CUtensorMap lomap, int use_tma, const
     const int px0 = n0 / Cimg, c0 = n0 - px0 * Cimg, px1 = n1 / Cimg, c1 = n1 - px1 * Cimg;
     const float nb0 = bias != nullptr ? __ldg(bias + c0) : 0.0f, nb1 = bias != nullptr ? __ldg(bias + c1) : 0.0f;
     // element offsets of this lane for (m = 0, t = 0, h = 0); the loop adds compile-time constants
-    const int yl_w = 2 * warp;
+    const int xg = xh + g;
     int off0, off1;                                   // per-format lane bases of the two columns
     if (u8 || unit) {
       const bool rev = u8 && bgr;
       const int o0 = rev ? px0 * Cimg + (Cimg - 1 - c0) : n0, o1 = rev ? px1 * Cimg + (Cimg - 1 - c1) : n1;
-      off0 = (2 * yl_w * 64 + 2 * g) * Cimg + o0;
-      off1 = (2 * yl_w * 64 + 2 * g) * Cimg + o1;
+      off0 = (2 * rg4 * 64 + 2 * xg) * Cimg + o0;
+      off1 = (2 * rg4 * 64 + 2 * xg) * Cimg + o1;
     } else {
-      off0 = (c0 * (2 * kTH) + 2 * yl_w) * 64 + 2 * g + px0;
-      off1 = (c1 * (2 * kTH) + 2 * yl_w) * 64 + 2 * g + px1;
+      off0 = (c0 * (2 * kTH) + 2 * rg4) * 64 + 2 * xg + px0;
+      off1 = (c1 * (2 * kTH) + 2 * rg4) * 64 + 2 * xg + px1;
     }
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
@@ -328,9 +338,9 @@ img_conv_up_kernel(const __grid_constant__ CUtensorMap lomap, int use_tma, const
       for (int t = 0; t < 2; ++t) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          // staged pixel (Yl, Xl) = (2*yl + t, 2*xl + px), yl = 2*warp + (m >> 1), xl = (m & 1)*16 + g + 8*h
+          // staged pixel (Yl, Xl) = (2*yl + t, 2*xl + px), yl = 4*(warp >> 1) + m, xl = (warp & 1)*16 + g + 8*h
           constexpr int kRowNhwc = 64 * Cimg;
-          const int dY = 2 * (m >> 1) + t, dXl = (m & 1) * 16 + 8 * h;
+          const int dY = 2 * m + t, dXl = 8 * h;
           float v0 = acc[m][t][2 * h] + nb0, v1 = acc[m][t][2 * h + 1] + nb1;
           if (do_tanh) { v0 = tanh_fast(v0); v1 = tanh_fast(v1); }
           if (u8) {

@@ -10,3 +10,4 @@ if [ $rc -ne 0 ]; then
   echo "rc=$?"; tail -15 gpurun_out/${tag}_tests_notma.log
 fi
 timeout 200 python tools/hbm_bench.py img_conv > gpurun_out/${tag}_bench.txt 2>&1; cat gpurun_out/${tag}_bench.txt
+timeout 200 python tools/synth_profile.py 2>&1 | grep -v -i warn | head -6
