@@ -7,12 +7,15 @@
 //                      or the tanh backward fused into the patch load; also the generator output layer's input gradient
 //   rg_img_conv_wgrad  the weight (and bias) gradient of either layer
 //
-// These layers carry 6 GFLOP per pass against 134 MB of activations: HBM-bound.  Each CTA stages a halo'd tile in shared
-// memory ONCE (the old path wrote and re-read a 134-201 MB `col` matrix per pass) and contracts it with warp-level
-// mma.sync.m16n8k16 bf16 fragments (fp32 accumulate) -- the tensor pipe is idle >90 % of the time here either way, so the
-// point of the MMA is only to keep the arithmetic off the critical path; tcgen05 / TMEM would buy nothing.
+// These layers carry 6 GFLOP per pass against 134 MB of activations: HBM is the floor (28 us at B = 64).  Each CTA stages a
+// halo'd tile in shared memory ONCE (the old path wrote and re-read a 134-201 MB `col` matrix per pass) -- the bf16
+// activation tile through one TMA box load (SWIZZLE_128B, zero fill outside the image), the fp32 image patch through
+// 16-byte cp.async, double-buffered in the persistent kernels -- and contracts it with warp-level mma.sync.m16n8k16 bf16
+// fragments (fp32 accumulate).  N is 6..12 useful columns here, so tcgen05 would not help: a UMMA re-reads the 4 KB A
+// slice from shared memory for every shift, while ldmatrix fragments are reused across the shifts that share a tile row.
+// What bounds them (ncu, profiles/r2_ncu_hbm_summary.txt): conv_up the legacy tensor pipe (57-60 % busy) and L1/shared
+// bandwidth (77-82 %); conv_down / wgrad instruction issue and 2-way bank conflicts of the stride-2 fp32 tap gather.
 #include <algorithm>
-#include <stdlib.h>
 #include <type_traits>
 #include "rg_host.cuh"
 #include "rg_ptx.cuh"
@@ -138,22 +141,6 @@ __device__ __forceinline__ void patch_transform(float* stage, int mode, float ep
   }
 }
 
-// ------------------------------------------------------------------------------------------------ activation tile (bf16)
-// tile[P][64 channels] with P = r * pw + c over a (ph x pw) pixel window whose top-left pixel is (ya, xa); 128-byte rows,
-// 16-byte chunk index XOR (P & 7): ldmatrix over 8 consecutive pixels is conflict-free.  Out-of-image pixels are zero.
-__device__ __forceinline__ void load_act_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ act, int b, int H, int W,
-                                              int ya, int xa, int ph, int pw) {
-  const uint32_t base = smem_u32(tile);
-  for (int idx = threadIdx.x; idx < ph * pw * 8; idx += kThreads) {
-    const int P = idx >> 3, ch = idx & 7;
-    const int r = P / pw, c = P - r * pw;
-    const int gy = ya + r, gx = xa + c;
-    const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-    const __nv_bfloat16* src = act + ((static_cast<size_t>(b) * H + (ok ? gy : 0)) * W + (ok ? gx : 0)) * kC + ch * 8;
-    cp16_zfill(base + P * 128 + ((ch ^ (P & 7)) << 4), src, ok ? 16 : 0);
-  }
-}
-
 // =================================================================================================== conv_up (K2)
 // out[b, c, 2i+py, 2j+px] = bias[c] + sum_{dy,dx,p} lo[b, i+dy, j+dx, p] * W[p, c, py+1-2dy, px+1-2dx]
 // Per 16-pixel M tile and channel chunk: one A fragment per shift (dy,dx), two accumulator tiles (py = 0 / 1) whose 8
@@ -190,8 +177,7 @@ __global__ void img_up_pack_kernel(const float* __restrict__ Wt, int Cimg, uint2
 
 template <int Cimg>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-img_conv_up_kernel(const __grid_constant__ CUtensorMap lomap, int use_tma, const __nv_bfloat16* __restrict__ lo,
-                   const uint2* __restrict__ bfrag_g, const float* __restrict__ bias, void* __restrict__ out, int B, int H,
+img_conv_up_kernel(const __grid_constant__ CUtensorMap lomap, const uint2* __restrict__ bfrag_g, const float* __restrict__ bias, void* __restrict__ out, int B, int H,
                    int W, int flags, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
                    float bn_slope) {
   extern __shared__ uint8_t smem_raw[];
@@ -206,15 +192,11 @@ img_conv_up_kernel(const __grid_constant__ CUtensorMap lomap, int use_tma, const
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
 
-  if (use_tma) {
-    if (threadIdx.x == 0) {
-      mbar_init(bar, 1);
-      fence_barrier_init();
-      mbar_expect_tx(bar, kUpTileBytes);
-      tma_load_4d(&lomap, bar, tile, 0, x0 - 1, y0 - 1, b);
-    }
-  } else {
-    load_act_tile(tile, lo, b, H, W, y0 - 1, x0 - 1, kUpPH, kUpPW);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    mbar_expect_tx(bar, kUpTileBytes);
+    tma_load_4d(&lomap, bar, tile, 0, x0 - 1, y0 - 1, b);
   }
   {
     const uint32_t fb = smem_u32(bfrag);
@@ -234,8 +216,8 @@ img_conv_up_kernel(const __grid_constant__ CUtensorMap lomap, int use_tma, const
     sh[0] = ha.x; sh[1] = ha.y; sh[2] = ha.z; sh[3] = ha.w; sh[4] = hb.x; sh[5] = hb.y; sh[6] = hb.z; sh[7] = hb.w;
   }
   cp_commit_wait_all();
-  __syncthreads();                       // B fragments (and the cp.async tile) landed; the mbarrier init is visible
-  if (use_tma) mbar_wait(bar, 0);
+  __syncthreads();                       // B fragments landed; the mbarrier init is visible
+  mbar_wait(bar, 0);
   if (bn_scale != nullptr) {
     // `lo` is the PRE-BatchNorm activation a: h = lrelu(scale * a + shift) is applied to the staged tile in place (same
     // arithmetic and bf16 rounding as rg_bn_act, so h is never written to HBM); halo pixels outside the image stay zero
@@ -555,8 +537,7 @@ __host__ __device__ constexpr int wg_smem_bytes(int cimg, int mode) {
 
 template <int CIMG>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-img_conv_wgrad_kernel(const __grid_constant__ CUtensorMap amap, int use_tma, const __nv_bfloat16* __restrict__ act,
-                      const float* __restrict__ x, const float* __restrict__ yimg, int mode,
+img_conv_wgrad_kernel(const __grid_constant__ CUtensorMap amap, const float* __restrict__ x, const float* __restrict__ yimg, int mode,
                       const float* __restrict__ eps_dev, const float* __restrict__ mul_dev, float* __restrict__ part,
                       int B, int S) {
   extern __shared__ uint8_t smem_raw[];
@@ -584,7 +565,7 @@ img_conv_wgrad_kernel(const __grid_constant__ CUtensorMap amap, int use_tma, con
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.0f;
-  if (use_tma && threadIdx.x == 0) {
+  if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
     fence_barrier_init();
@@ -594,13 +575,9 @@ img_conv_wgrad_kernel(const __grid_constant__ CUtensorMap amap, int use_tma, con
   auto issue = [&](int tile, int s) {
     const int tx = tile & (tiles_x - 1), ty = (tile >> txs) & (tiles_y - 1), b = tile >> (txs + tys);
     const int y0 = ty * kWgTH, x0 = tx * kTW;
-    if (use_tma) {
-      if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar[s], kWgActBytes);
-        tma_load_4d(&amap, &bar[s], smem + s * kWgActBytes, 0, x0, y0, b);
-      }
-    } else {
-      load_act_tile(smem + s * kWgActBytes, act, b, H, W, y0, x0, kWgTH, kTW);
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar[s], kWgActBytes);
+      tma_load_4d(&amap, &bar[s], smem + s * kWgActBytes, 0, x0, y0, b);
     }
     patch_prefetch<kWgTH, CIMG>(patch_u32 + s * pbytes, x, ysrc, b, S, y0, x0, pv, prr);
   };
@@ -619,7 +596,7 @@ img_conv_wgrad_kernel(const __grid_constant__ CUtensorMap amap, int use_tma, con
     cp_wait<1>();
     float* patch = reinterpret_cast<float*>(patch_base + cur * pbytes);
     if (xform) patch_transform<kWgTH, CIMG>(patch, mode, eps, mul, pv, prr);
-    if (use_tma) mbar_wait(&bar[cur], (it >> 1) & 1);
+    mbar_wait(&bar[cur], (it >> 1) & 1);
     __syncthreads();
     const uint32_t atile_u32 = smem_u32(smem + cur * kWgActBytes);
 #pragma unroll 1
@@ -672,25 +649,28 @@ img_conv_wgrad_kernel(const __grid_constant__ CUtensorMap amap, int use_tma, con
 }
 
 // dW[p][c][kh][kw] = acc*dW + sum_cta part;  dbias[p] = acc_b*dbias + sum_cta part[..][p][2*Cimg*8]
-// One block per output row p: thread (sub, n) sums every 4th partial of column n (256-byte coalesced reads across n), the
-// four sub-sums are combined in a fixed order -- the ~600 partials of 16 KiB are read in a few microseconds instead of by
-// one serial strided loop per output element.
-__global__ void __launch_bounds__(256) img_wgrad_finish_kernel(const float* __restrict__ part, int nparts, int Cimg,
-                                                               float* __restrict__ dW, float acc,
-                                                               float* __restrict__ dbias, float acc_b) {
-  __shared__ float sm[4][kWgN];
+// One block per output row p: thread (sub, n) sums every 16th partial of column n (256-byte coalesced reads across n, two
+// loads in flight), the sixteen sub-sums are combined in a fixed order -- the ~600 partials of 16 KiB are read in a few
+// microseconds instead of by one serial strided loop per output element.
+constexpr int kFinSubs = 16;
+__global__ void __launch_bounds__(kFinSubs * kWgN) img_wgrad_finish_kernel(const float* __restrict__ part, int nparts,
+                                                                           int Cimg, float* __restrict__ dW, float acc,
+                                                                           float* __restrict__ dbias, float acc_b) {
+  __shared__ float sm[kFinSubs][kWgN];
   const int p = blockIdx.x, n = threadIdx.x & (kWgN - 1), sub = threadIdx.x >> 6;
   float s0 = 0.0f, s1 = 0.0f;
   int r = sub;
-  for (; r + 4 < nparts; r += 8) {
+  for (; r + kFinSubs < nparts; r += 2 * kFinSubs) {
     s0 += part[(static_cast<size_t>(r) * 64 + p) * kWgN + n];
-    s1 += part[(static_cast<size_t>(r + 4) * 64 + p) * kWgN + n];
+    s1 += part[(static_cast<size_t>(r + kFinSubs) * 64 + p) * kWgN + n];
   }
   if (r < nparts) s0 += part[(static_cast<size_t>(r) * 64 + p) * kWgN + n];
   sm[sub][n] = s0 + s1;
   __syncthreads();
   if (sub != 0) return;
-  const float s = (sm[0][n] + sm[1][n]) + (sm[2][n] + sm[3][n]);
+  float s = 0.0f;
+#pragma unroll
+  for (int l = 0; l < kFinSubs; ++l) s += sm[l][n];
   const int nt = n >> 3, e = n & 7;
   if (nt < 2 * Cimg) {
     const int c = nt >> 1, kh = (nt & 1) * 2 + (e >> 2), kw = e & 3;
@@ -722,27 +702,12 @@ static int img_prepare(ImgLaunch& L, K kernel, int smem_max, int smem) {
   return 0;
 }
 
-// TMA view of the bf16 NHWC activation [B][H][W][64] with a (64, bw, bh, 1) box.  A box may be larger than the tensor
-// (small test images): should a driver refuse that, the kernels fall back to their cp.async tile loader.
-static int img_act_map(CUtensorMap* m, const void* act, int B, int H, int W, int bw, int bh, int* use_tma) {
+// TMA view of the bf16 NHWC activation [B][H][W][64] with a (64, bw, bh, 1) box, SWIZZLE_128B, zero fill outside the
+// tensor (boxes larger than a small test image are fine: the whole overhang is zero-filled).
+static int img_act_map(CUtensorMap* m, const void* act, int B, int H, int W, int bw, int bh) {
   memset(m, 0, sizeof(*m));
-  static int env_off = -1;                   // RG_IMG_TMA=0: debugging aid, forces the cp.async tile loader
-  if (env_off < 0) {
-    const char* e = getenv("RG_IMG_TMA");
-    env_off = (e && e[0] == '0') ? 1 : 0;
-  }
-  if (env_off) {
-    *use_tma = 0;
-    return 0;
-  }
-  *use_tma = 1;
-  const int rc = encode_map_4d(m, act, kC, W, H, B, kC, static_cast<uint64_t>(W) * kC,
-                               static_cast<uint64_t>(H) * W * kC, kC, bw, bh, 1);
-  if (rc != 0) {
-    if (W >= bw && H >= bh) return rc;       // a real error
-    *use_tma = 0;
-  }
-  return 0;
+  return encode_map_4d(m, act, kC, W, H, B, kC, static_cast<uint64_t>(W) * kC, static_cast<uint64_t>(H) * W * kC, kC, bw,
+                       bh, 1);
 }
 
 template <int CIMG>
@@ -751,12 +716,10 @@ static int launch_up(const void* lo, const void* wfrag, const float* bias, int f
   static ImgLaunch L;
   if (int rc = img_prepare(L, img_conv_up_kernel<CIMG>, kUpSmem, kUpSmem)) return rc;
   CUtensorMap map;
-  int use_tma = 0;
-  if (int rc = img_act_map(&map, lo, B, H, Wd, kUpPW, kUpPH, &use_tma)) return rc;
+  if (int rc = img_act_map(&map, lo, B, H, Wd, kUpPW, kUpPH)) return rc;
   const int grid = B * ceil_div(H, kTH) * ceil_div(Wd, kTW);
-  img_conv_up_kernel<CIMG><<<grid, kThreads, kUpSmem, s>>>(map, use_tma, static_cast<const __nv_bfloat16*>(lo),
-                                                           static_cast<const uint2*>(wfrag), bias, out, B, H, Wd, flags,
-                                                           bn_scale, bn_shift, bn_slope);
+  img_conv_up_kernel<CIMG><<<grid, kThreads, kUpSmem, s>>>(map, static_cast<const uint2*>(wfrag), bias, out, B, H, Wd,
+                                                           flags, bn_scale, bn_shift, bn_slope);
   RG_LAUNCH_CHECK("rg_img_conv_up");
   return 0;
 }
@@ -786,16 +749,15 @@ static int launch_wgrad(const void* act, const float* x, const float* y, int mod
   if (int rc = img_prepare(l, img_conv_wgrad_kernel<CIMG>, wg_smem_bytes(CIMG, 1), smem)) return rc;
   const int H = S / 2;
   CUtensorMap map;
-  int use_tma = 0;
-  if (int rc = img_act_map(&map, act, B, H, H, kTW, kWgTH, &use_tma)) return rc;
+  if (int rc = img_act_map(&map, act, B, H, H, kTW, kWgTH)) return rc;
   const int ntiles = B * ceil_div(H, kWgTH) * ceil_div(H, kTW);
   const int grid = std::min(ntiles, l.ctas_per_sm * num_sms());
   if (ws_bytes < static_cast<size_t>(grid) * 64 * kWgN * sizeof(float)) {
     set_error("rg_img_conv_wgrad: workspace too small (need %zu bytes)", static_cast<size_t>(grid) * 64 * kWgN * 4);
     return RG_EWORKSPACE;
   }
-  img_conv_wgrad_kernel<CIMG><<<grid, kThreads, smem, s>>>(map, use_tma, static_cast<const __nv_bfloat16*>(act), x, y,
-                                                           mode, eps_dev, mul_dev, static_cast<float*>(ws), B, S);
+  img_conv_wgrad_kernel<CIMG><<<grid, kThreads, smem, s>>>(map, x, y, mode, eps_dev, mul_dev, static_cast<float*>(ws), B,
+                                                           S);
   RG_LAUNCH_CHECK("rg_img_conv_wgrad");
   *grid_out = grid;
   return 0;
@@ -870,7 +832,7 @@ int rg_img_conv_wgrad(const void* act, const float* x, const float* y, int mode,
     default: rc = launch_wgrad<4>(act, x, y, mode, eps_dev, mul_dev, B, S, ws, ws_bytes, &grid, s); break;
   }
   if (rc) return rc;
-  img_wgrad_finish_kernel<<<64, 256, 0, s>>>(static_cast<const float*>(ws), grid, Cimg, dW, acc, dbias, acc_bias);
+  img_wgrad_finish_kernel<<<64, kFinSubs * kWgN, 0, s>>>(static_cast<const float*>(ws), grid, Cimg, dW, acc, dbias, acc_bias);
   RG_LAUNCH_CHECK("rg_img_conv_wgrad(finish)");
   return 0;
 }
