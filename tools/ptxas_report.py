@@ -3,7 +3,7 @@
 shared memory from `nvcc -Xptxas -v`, plus how often the SASS mnemonics that prove the Blackwell paths (tcgen05 MMA,
 TMA loads / stores, TMEM loads, programmatic dependent launch) occur per kernel (`cuobjdump -sass`).
 
-    python tools/ptxas_report.py > profiles/r1_ptxas_report.txt
+    python tools/ptxas_report.py > profiles/r2_ptxas_report.txt
 """
 import os
 import re
@@ -13,9 +13,9 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "rnagan_b200", "csrc")
-SOURCES = ["rg_gemm_api.cu", "rg_ops.cu"]
+SOURCES = ["rg_gemm_api.cu", "rg_ops.cu", "rg_img.cu", "rg_data.cu"]
 MNEMONICS = {"UTCMMA": "UTC(H|Q|O)?MMA", "UTMALDG": "UTMALDG", "UTMASTG": "UTMASTG", "LDTM": "LDTM", "ACQBULK": "ACQBULK",
-             "PREEXIT": "PREEXIT"}
+             "PREEXIT": "PREEXIT", "HMMA": r"HMMA\.", "LDSM": "LDSM", "LDGSTS": "LDGSTS"}
 
 
 def demangle(names):
