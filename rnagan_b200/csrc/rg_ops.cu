@@ -191,6 +191,64 @@ __global__ void __launch_bounds__(1024) colreduce_stage2(const float* __restrict
   }
 }
 
+// Few rows (BatchNorm1d over a batch of 128 in the betaVAE step, the top of the conv stacks in small jobs): the two-stage
+// plan above would run 16 CTAs and a second launch for 1.5 MB.  Here one CTA owns a 128-channel column block over ALL rows
+// -- 16 column groups x 16 row lanes, the same batched streaming loads -- and combines the lanes in a fixed order: one
+// launch, no workspace, bit-reproducible.
+constexpr int kSmallLanes = 16;
+constexpr int kSmallM = 256;
+template <class F>
+__global__ void __launch_bounds__(256) colreduce_small(F f, int M, int C, float* __restrict__ out) {
+  griddep_wait();
+  griddep_launch();
+  constexpr int K = F::K;
+  constexpr int NT = F::NT;
+  constexpr int R = kRedRows;
+  __shared__ float sm[kSmallLanes][K][16 * 8];
+  const int cgs = C >> 3;
+  const int cgl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int cg = blockIdx.x * 16 + cgl;
+  float acc[K][8];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[k][e] = 0.0f;
+  if (cg < cgs) {
+    const int c0 = cg * 8;
+    int r = rl;
+    for (; r + (R - 1) * kSmallLanes < M; r += R * kSmallLanes) {      // full batches: R x NT loads, then the arithmetic
+      uint4 d[R][NT];
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) d[j][t] = ldu4(f.ptr(t) + static_cast<size_t>(r + j * kSmallLanes) * C + c0);
+#pragma unroll
+      for (int j = 0; j < R; ++j) f.acc(d[j], c0, acc);
+    }
+    for (; r < M; r += kSmallLanes) {                                   // ragged tail, one row at a time
+      uint4 d[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) d[t] = ldu4(f.ptr(t) + static_cast<size_t>(r) * C + c0);
+      f.acc(d, c0, acc);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sm[rl][k][cgl * 8 + e] = acc[k][e];
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * 128; i += 256) {
+    const int k = i >> 7, col = i & 127;
+    const int c = blockIdx.x * 128 + col;
+    if (c < C) {
+      float t = sm[0][k][col];
+#pragma unroll
+      for (int l = 1; l < kSmallLanes; ++l) t += sm[l][k][col];
+      out[static_cast<size_t>(k) * C + c] = t;
+    }
+  }
+}
+
 struct ReducePlan {
   int blocks, rows_per_block;
   size_t smem;
@@ -220,6 +278,11 @@ static int run_colreduce(F f, int M, int C, float* ws, size_t ws_bytes, float* o
   if (C % 8 != 0 || C < 8 || C > 65536 || M <= 0) {
     set_error("%s: need C %% 8 == 0, 8 <= C <= 65536, M > 0 (M=%d C=%d)", name, M, C);
     return RG_EINVAL;
+  }
+  if (M <= kSmallM) {
+    RG_CUDA(launch_pdl(colreduce_small<F>, dim3(ceil_div(C / 8, 16)), dim3(256), 0, st, 1, f, M, C, out));
+    RG_LAUNCH_CHECK(name);
+    return 0;
   }
   ReducePlan p = plan_reduce(M, C, K, F::NT);
   const size_t need = static_cast<size_t>(p.blocks) * K * C * sizeof(float);
