@@ -78,6 +78,46 @@ def test_dependent_launch_kernels_wait_before_memory():
             assert not re.search(touches, before), f"{k}: memory access before the wait"
 
 
+def test_shipped_kernels_use_the_blackwell_paths():
+    """Static check of the shipped library's SASS (no GPU): the tile engine issues tcgen05.mma (`UTC*MMA`), loads its
+    operands with TMA (`UTMALDG`), stores through TMA (`UTMASTG`) and reads accumulators from TMEM (`LDTM`); the fused
+    image-side kernels take their activation tile through a TMA box load and their image patch through cp.async
+    (`LDGSTS`), contract with mma.sync (`HMMA`) and -- conv_up -- issue 18 ldmatrix per channel chunk (6 tile rows x 3
+    column shifts: the fragment reuse that halves its shared-memory traffic); the NVSwitch exchange kernel reduces with
+    multimem.ld_reduce (`LDGMC...ADD.F32x4`)."""
+    import shutil
+    from rnagan_b200 import _lib
+    if shutil.which("cuobjdump") is None or shutil.which("c++filt") is None:
+        pytest.skip("cuobjdump / c++filt not on PATH")
+    if _lib._needs_build():
+        _lib.build()
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)[1:]
+    mangled = [f.split("\n", 1)[0].strip() for f in funcs]
+    pretty = subprocess.run(["c++filt"] + mangled, capture_output=True, text=True, check=True).stdout.split("\n")
+
+    def bodies(kernel):
+        out = [b for n, b in zip(pretty, funcs) if re.search(r"\b" + kernel + r"\b", n.split("(")[0])]
+        assert out, f"{kernel}: not in the library"
+        return out
+
+    def count(body, pat):
+        return len(re.findall(r"\b" + pat, body))
+
+    for b in bodies("gemm_fwd_kernel") + bodies("gemm_wgrad_kernel"):
+        assert count(b, r"UTC\w*MMA") > 0 and count(b, "UTMALDG") > 0 and count(b, "LDTM") > 0
+        assert count(b, r"HMMA\.") == 0, "legacy mma.sync inside the tile engine"
+    assert any(count(b, "UTMASTG") > 0 for b in bodies("gemm_fwd_kernel"))
+    for b in bodies("img_conv_up_kernel"):
+        assert count(b, "UTMALDG") == 1 and count(b, r"HMMA\.") == 48 and count(b, "LDSM") == 18
+    for b in bodies("img_conv_wgrad_kernel"):
+        assert count(b, "UTMALDG") == 2 and count(b, "LDGSTS") > 0 and count(b, r"HMMA\.") > 0
+    for b in bodies("img_conv_down_kernel"):
+        assert count(b, "LDGSTS") > 0 and count(b, r"HMMA\.") > 0
+    for b in bodies("nvls_allreduce_kernel"):      # multimem.ld_reduce: the sum happens inside the NVSwitch
+        assert count(b, r"LDGMC\.E\.ADD\.F32x4") > 0
+
+
 def test_size_queries_work_without_gpu():
     from rnagan_b200 import _lib
     lib = _lib.lib()
